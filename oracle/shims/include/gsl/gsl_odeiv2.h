@@ -1,0 +1,22 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY -- mini-GSL subset: RKF45 with GSL's
+ * "standard" step-size controller (eps_abs, eps_rel, a_y, a_dydt). */
+#ifndef MINIGSL_ODEIV2_H
+#define MINIGSL_ODEIV2_H
+#include <stddef.h>
+typedef struct {
+    int (*function)(double t, const double y[], double dydt[], void *params);
+    int (*jacobian)(double t, const double y[], double *dfdy, double dfdt[], void *params);
+    size_t dimension;
+    void *params;
+} gsl_odeiv2_system;
+typedef struct { const char *name; } gsl_odeiv2_step_type;
+extern const gsl_odeiv2_step_type *gsl_odeiv2_step_rkf45;
+typedef struct {
+    const gsl_odeiv2_system *sys;
+    double h, epsabs, epsrel, a_y, a_dydt;
+} gsl_odeiv2_driver;
+gsl_odeiv2_driver *gsl_odeiv2_driver_alloc_standard_new(const gsl_odeiv2_system *sys,
+        const gsl_odeiv2_step_type *T, double hstart, double epsabs, double epsrel, double a_y, double a_dydt);
+int gsl_odeiv2_driver_apply(gsl_odeiv2_driver *d, double *t, double t1, double y[]);
+void gsl_odeiv2_driver_free(gsl_odeiv2_driver *d);
+#endif
