@@ -1,0 +1,450 @@
+// fastpm_b200 -- the extern "C" boundary declared in include/fastpm_b200.h.
+#include "common.cuh"
+#include "mesh.cuh"
+#include "../../include/fastpm_b200.h"
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+#include <vector>
+
+unsigned long long fpm_launch_counter = 0;
+
+// launchers defined in the kernel files
+int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
+int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
+int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
+int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st);
+int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
+int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
+int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2, long long np, cudaStream_t st);
+int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st);
+int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, double *host_out, cudaStream_t st);
+int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st);
+int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st);
+int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st);
+int fpm_scale_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
+int fpm_divide_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
+int fpm_muladd_launch(float *source, const float *a, const float *b, size_t nfloats, int sign, cudaStream_t st);
+int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const double *d_tp, int size, cudaStream_t st);
+int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed, cudaStream_t st);
+int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st);
+
+// ------------------------------------------------------------------ runtime state
+static char g_error[1024] = "";
+static cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+
+extern "C" void fpm_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static int ensure_init()
+{
+    if (g_device >= 0) return 0;
+    return fpm_device_init(0);
+}
+
+extern "C" {
+
+const char *fpm_last_error(void) { return g_error; }
+const char *fpm_version(void) { return "fastpm_b200 0.1 (sm_100a)"; }
+
+int fpm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fpm_device_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        fpm_set_error("fastpm_b200 needs a CUDA device (sm_100a); none is visible: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    FPM_CUDA_OK(cudaSetDevice(device));
+    if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    if (!g_stream) FPM_CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    return 0;
+}
+
+int fpm_device_mem_info(size_t *free_bytes, size_t *total_bytes)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaMemGetInfo(free_bytes, total_bytes));
+    return 0;
+}
+
+void *fpm_malloc(size_t bytes)
+{
+    if (ensure_init()) return NULL;
+    void *p = NULL;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fpm_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
+    return p;
+}
+void fpm_free(void *ptr) { if (ptr) cudaFree(ptr); }
+
+void *fpm_host_alloc_pinned(size_t bytes)
+{
+    void *p = NULL;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fpm_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
+    return p;
+}
+void fpm_host_free_pinned(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int fpm_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int fpm_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int fpm_memcpy_d2d(void *dst, const void *src, size_t bytes)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
+    return 0;
+}
+int fpm_memset(void *dst, int value, size_t bytes)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaMemsetAsync(dst, value, bytes, g_stream));
+    return 0;
+}
+int fpm_sync(void)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+struct FpmTimer { cudaEvent_t a, b; };
+int fpm_timer_create(void **timer)
+{
+    if (ensure_init()) return -1;
+    FpmTimer *t = new FpmTimer();
+    FPM_CUDA_OK(cudaEventCreate(&t->a));
+    FPM_CUDA_OK(cudaEventCreate(&t->b));
+    *timer = t;
+    return 0;
+}
+int fpm_timer_start(void *timer) { FPM_CUDA_OK(cudaEventRecord(((FpmTimer *) timer)->a, g_stream)); return 0; }
+int fpm_timer_stop(void *timer) { FPM_CUDA_OK(cudaEventRecord(((FpmTimer *) timer)->b, g_stream)); return 0; }
+int fpm_timer_elapsed_ms(void *timer, double *ms)
+{
+    FpmTimer *t = (FpmTimer *) timer;
+    FPM_CUDA_OK(cudaEventSynchronize(t->b));
+    float f = 0;
+    FPM_CUDA_OK(cudaEventElapsedTime(&f, t->a, t->b));
+    *ms = f;
+    return 0;
+}
+void fpm_timer_destroy(void *timer)
+{
+    FpmTimer *t = (FpmTimer *) timer;
+    if (!t) return;
+    cudaEventDestroy(t->a); cudaEventDestroy(t->b);
+    delete t;
+}
+uint64_t fpm_kernel_launch_count(void) { return fpm_launch_counter; }
+
+// ------------------------------------------------------------------ mesh
+static double sinc_unnormed(double x)
+{
+    if (x < 1e-5 && x > -1e-5) {
+        double x2 = x * x;
+        return 1.0 - x2 / 6. + x2 * x2 / 120.;
+    }
+    return sin(x) / x;
+}
+
+// pm_create_k_factors, pmapi.c:235-275: every quantity goes through float exactly where the reference's does
+static void host_ktables(int n, double boxsize, std::vector<float> &tab, std::vector<double> &decic)
+{
+    tab.assign((size_t) 5 * n, 0.f);
+    decic.assign(n, 0.0);
+    const double CellSize = boxsize / n;
+    for (int ind = 0; ind < n; ind++) {
+        int ii = ind;
+        if (ii >= n / 2) ii -= n;
+        const double MeshtoK = ii * 2 * M_PI / boxsize;                 // pmpfft.c:332-340
+        volatile float k = (float) MeshtoK;
+        volatile float w = (float) (k * CellSize);
+        volatile float ff1 = (float) sinc_unnormed(0.5 * w);
+        volatile float ff2 = (float) sinc_unnormed(w);
+        volatile float kk = k * k;
+        tab[0 * n + ind] = k;
+        tab[1 * n + ind] = kk;
+        tab[2 * n + ind] = (float) (1 / CellSize * (1 / 6.0 * (8 * sin((double) w) - sin(2 * (double) w))));
+        volatile float f11 = ff1 * ff1;
+        tab[3 * n + ind] = kk * f11;
+        tab[4 * n + ind] = (float) (kk * (4 / 3.0 * ff1 * ff1 - 1 / 3.0 * ff2 * ff2));
+        // decic table, transfer.c:88-96
+        const double wd = (double) k * boxsize / (double) n;
+        const double cic = sinc_unnormed(0.5 * wd);
+        decic[ind] = 1.0 / pow(cic, 2);
+    }
+}
+
+fpm_mesh *fpm_mesh_create(int nmesh, double boxsize, int nranks, int rank)
+{
+    if (ensure_init()) return NULL;
+    if (nranks < 1 || nranks > FPM_MAX_RANKS || rank < 0 || rank >= nranks) { fpm_set_error("bad rank %d / %d", rank, nranks); return NULL; }
+    if (nmesh % nranks != 0) { fpm_set_error("Nmesh = %d is not divisible by the number of slabs %d (cf. solver.c:113-121)", nmesh, nranks); return NULL; }
+    FpmMesh *m = new FpmMesh();
+    memset(m, 0, sizeof(*m));
+    FpmGeom &g = m->geom;
+    g.n = nmesh; g.nranks = nranks; g.rank = rank;
+    g.nxl = nmesh / nranks; g.x0 = rank * g.nxl;
+    g.nyl = nmesh / nranks; g.y0 = rank * g.nyl;
+    g.pitch_c = ((nmesh / 2 + 1 + 15) / 16) * 16;
+    g.pitch_r = 2 * g.pitch_c;
+    g.boxsize = boxsize;
+    g.cellsize = boxsize / nmesh;
+    g.inv_cellsize = 1.0 / g.cellsize;                 // pmpfft.c:150-151
+    if (fpm_fft_plan_create(nmesh, &m->plan)) { delete m; return NULL; }
+    std::vector<float> tab; std::vector<double> decic;
+    host_ktables(nmesh, boxsize, tab, decic);
+    if (cudaMalloc(&m->d_ktab_store, sizeof(float) * tab.size()) != cudaSuccess ||
+        cudaMalloc(&m->d_decic, sizeof(double) * nmesh) != cudaSuccess) {
+        fpm_set_error("mesh tables: cudaMalloc failed"); delete m; return NULL;
+    }
+    cudaMemcpy(m->d_ktab_store, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(m->d_decic, decic.data(), sizeof(double) * nmesh, cudaMemcpyHostToDevice);
+    m->ktab.k = m->d_ktab_store;
+    m->ktab.kk = m->d_ktab_store + nmesh;
+    m->ktab.k_finite = m->d_ktab_store + 2 * nmesh;
+    m->ktab.kk_finite = m->d_ktab_store + 3 * nmesh;
+    m->ktab.kk_finite2 = m->d_ktab_store + 4 * nmesh;
+    m->ktab.n = nmesh;
+    return m;
+}
+
+void fpm_mesh_destroy(fpm_mesh *m)
+{
+    if (!m) return;
+    fpm_fft_plan_destroy(m->plan);
+    cudaFree(m->d_ktab_store); cudaFree(m->d_decic);
+    delete m;
+}
+
+static int halo_planes(const FpmGeom &g) { return g.nranks > 1 ? 1 : 0; }
+
+static size_t mesh_alloc_floats(const FpmGeom &g)
+{
+    size_t planes_r = (size_t) g.nxl + halo_planes(g), planes_c = (size_t) g.nyl;
+    size_t p = planes_r > planes_c ? planes_r : planes_c;
+    return p * (size_t) g.n * (size_t) g.pitch_r;
+}
+
+int fpm_mesh_info(const fpm_mesh *m, int64_t info[16])
+{
+    const FpmGeom &g = m->geom;
+    memset(info, 0, sizeof(int64_t) * 16);
+    info[0] = g.n; info[1] = (int64_t) mesh_alloc_floats(g); info[2] = g.pitch_r; info[3] = g.pitch_c;
+    info[4] = g.nxl; info[5] = g.x0; info[6] = g.nyl; info[7] = g.y0; info[8] = g.nranks; info[9] = g.rank;
+    info[10] = halo_planes(g);
+    return 0;
+}
+
+int fpm_mesh_ktables_host(const fpm_mesh *m, float *host_out)
+{
+    FPM_CUDA_OK(cudaMemcpy(host_out, m->d_ktab_store, sizeof(float) * 5 * m->geom.n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------ paint / readout
+int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np, double M0, const float *mass, const float *field, int field_stride)
+{
+    return fpm_paint_launch(m, canvas, x, mass, M0, field, field_stride, np, g_stream);
+}
+
+int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np, float *out, int out_stride, double prescale)
+{
+    return fpm_readout_launch(m, canvas, x, out, out_stride, prescale, np, g_stream);
+}
+
+// ------------------------------------------------------------------ FFT
+static void to_spec(const fpm_transfer *k, FpmTransferSpec *s)
+{
+    s->active = k->active; s->potorder = k->potorder; s->negate = k->negate; s->ngrad = k->ngrad;
+    s->graddir[0] = k->graddir[0]; s->graddir[1] = k->graddir[1]; s->gradorder = k->gradorder;
+    s->zero_selfconj = k->zero_selfconj; s->scale = k->scale;
+}
+
+int fpm_r2c_ws(fpm_mesh *m, const float *real, float *work, float *cplx, double scale)
+{
+    if (m->geom.nranks != 1) { fpm_set_error("fpm_r2c: multi-GPU meshes go through the communicator entry points"); return -1; }
+    if (work == cplx) { fpm_set_error("fpm_r2c: the work buffer and the k-space output must differ (the y-pass transposes)"); return -1; }
+    float *peers[FPM_MAX_RANKS] = { cplx };
+    return fpm_fft_r2c(m, real, work, peers, (float) scale, g_stream);
+}
+
+int fpm_r2c(fpm_mesh *m, float *real, float *cplx, double scale) { return fpm_r2c_ws(m, real, real, cplx, scale); }
+
+int fpm_c2r_ws(fpm_mesh *m, const float *cplx, float *work, float *real, const fpm_transfer *kernel)
+{
+    if (m->geom.nranks != 1) { fpm_set_error("fpm_c2r: multi-GPU meshes go through the communicator entry points"); return -1; }
+    if (work == cplx) { fpm_set_error("fpm_c2r: the work buffer and the k-space input must differ (the x-pass transposes)"); return -1; }
+    float *peers[FPM_MAX_RANKS] = { work };
+    FpmTransferSpec s;
+    if (kernel && kernel->active) { to_spec(kernel, &s); return fpm_fft_c2r(m, cplx, peers, real, &s, g_stream); }
+    return fpm_fft_c2r(m, cplx, peers, real, NULL, g_stream);
+}
+
+int fpm_c2r(fpm_mesh *m, const float *cplx, float *real, const fpm_transfer *kernel) { return fpm_c2r_ws(m, cplx, real, real, kernel); }
+
+// fastpm_kernel_type_get_orders, gravity.c:111-171.  enum order: api/fastpm/libfastpm.h:45-51
+int fpm_transfer_for_kernel(int kernel_type, int attr, int memb, fpm_transfer *out)
+{
+    int potorder, gradorder;
+    switch (kernel_type) {
+        case 0: potorder = 1; gradorder = 1; break;   /* 3_4 */
+        case 1: potorder = 1; gradorder = 0; break;   /* 3_2 */
+        case 2: potorder = 2; gradorder = 1; break;   /* 5_4 */
+        case 3: potorder = 0; gradorder = 1; break;   /* 1_4 */
+        case 4: potorder = 0; gradorder = 1; break;   /* 1_4_DIFF0 */
+        case 5: potorder = 0; gradorder = 1; break;   /* GADGET */
+        case 6: potorder = 0; gradorder = 0; break;   /* EASTWOOD */
+        case 7: potorder = 0; gradorder = 0; break;   /* NAIVE */
+        default: fpm_set_error("Wrong kernel type %d", kernel_type); return -1;
+    }
+    memset(out, 0, sizeof(*out));
+    out->active = 1; out->potorder = potorder; out->negate = 1; out->gradorder = gradorder; out->zero_selfconj = 1; out->scale = 1.0;
+    if (attr == 0) { out->ngrad = 1; out->graddir[0] = memb; }
+    else if (attr == 1) { out->ngrad = 0; }
+    else { fpm_set_error("Unknown type for gravity attribute %d", attr); return -1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ k-space sweeps
+int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fpm_transfer *kernel)
+{
+    FpmTransferSpec s; to_spec(kernel, &s);
+    return fpm_transfer_launch(m, from, to, &s, g_stream);
+}
+int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to) { return fpm_decic_launch(m, from, to, g_stream); }
+int fpm_scale(const float *from, float *to, size_t nfloats, double value) { return fpm_scale_launch(from, to, nfloats, value, g_stream); }
+int fpm_divide(const float *from, float *to, size_t nfloats, double value) { return fpm_divide_launch(from, to, nfloats, value, g_stream); }
+int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign) { return fpm_muladd_launch(source, a, b, nfloats, sign, g_stream); }
+int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im) { return fpm_set_mode_launch(m, cplx, ix, iy, iz, re, im, g_stream); }
+
+int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host, const double *p_host, int size)
+{
+    double *d_k = NULL, *d_p = NULL;
+    FPM_CUDA_OK(cudaMalloc(&d_k, sizeof(double) * size));
+    FPM_CUDA_OK(cudaMalloc(&d_p, sizeof(double) * size));
+    FPM_CUDA_OK(cudaMemcpyAsync(d_k, k_host, sizeof(double) * size, cudaMemcpyHostToDevice, g_stream));
+    FPM_CUDA_OK(cudaMemcpyAsync(d_p, p_host, sizeof(double) * size, cudaMemcpyHostToDevice, g_stream));
+    int rc = fpm_induce_launch(m, cplx, d_k, d_p, size, g_stream);
+    cudaStreamSynchronize(g_stream);
+    cudaFree(d_k); cudaFree(d_p);
+    return rc;
+}
+
+int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed) { return fpm_whitenoise_launch(m, real, seed, g_stream); }
+
+int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, double *sums_host)
+{
+    const int nbins = m->geom.n / 2;
+    double *d_out = NULL;
+    FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
+    int rc = fpm_powerspectrum_launch(m, cplx, decic, d_out, g_stream);
+    if (!rc) {
+        FPM_CUDA_OK(cudaMemcpyAsync(sums_host, d_out, sizeof(double) * (3 * nbins + 1), cudaMemcpyDeviceToHost, g_stream));
+        FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+int fpm_powerspectrum(const fpm_mesh *m, const float *cplx, int decic, double *k_host, double *p_host, double *nmodes_host)
+{
+    const int nbins = m->geom.n / 2;
+    std::vector<double> sums((size_t) 3 * nbins + 1);
+    if (fpm_powerspectrum_sums(m, cplx, decic, sums.data())) return -1;
+    const double L = m->geom.boxsize, volume = L * L * L;
+    for (int i = 0; i < nbins; i++) {                       // powerspectrum.c:117-123
+        const double nm = sums[i];
+        nmodes_host[i] = nm;
+        if (nm == 0) { k_host[i] = 0; p_host[i] = 0; continue; }
+        k_host[i] = sums[2 * nbins + i] / nm;
+        p_host[i] = sums[nbins + i] / nm * volume;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ particles
+int fpm_kick(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, int64_t np,
+             int forcemode, double dda, double q1, double q2, double Dv1, double Dv2)
+{
+    const int cola = (forcemode == 2);
+    if (cola && (!dx1 || !dx2)) { fpm_set_error("COLA kick needs the dx1 and dx2 columns (solver.c:84-88)"); return -1; }
+    return fpm_kick_launch(v_out, v_in, acc, dx1, dx2, dda, q1, q2, Dv1, Dv2, cola, np, g_stream);
+}
+
+int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, int64_t np,
+              int forcemode, double dyyy, double da1, double da2, double Dv1, double Dv2)
+{
+    if (forcemode >= 2 && (!dx1 || (forcemode != 4 && !dx2))) { fpm_set_error("drift mode %d needs the dx1/dx2 columns", forcemode); return -1; }
+    return fpm_drift_launch(x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, forcemode, np, g_stream);
+}
+
+// The "too far" flag of the previous wrap is examined when the next one is issued (or by fpm_wrap_check), so that
+// the integrator never drains the stream just to look at it.
+static int *d_wrap_bad = NULL, *h_wrap_bad = NULL;
+int fpm_wrap_check(void)
+{
+    if (!h_wrap_bad) return 0;
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    if (*h_wrap_bad) { *h_wrap_bad = 0; fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)"); return -1; }
+    return 0;
+}
+int fpm_wrap(double *x, int64_t np, double boxsize)
+{
+    if (ensure_init()) return -1;
+    if (!d_wrap_bad) {
+        FPM_CUDA_OK(cudaMalloc(&d_wrap_bad, sizeof(int)));
+        FPM_CUDA_OK(cudaHostAlloc(&h_wrap_bad, sizeof(int), cudaHostAllocDefault));
+        *h_wrap_bad = 0;
+        FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
+    }
+    if (*h_wrap_bad) { *h_wrap_bad = 0; fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)"); return -1; }
+    if (fpm_wrap_launch(x, np, boxsize, d_wrap_bad, g_stream)) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(h_wrap_bad, d_wrap_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    return 0;
+}
+
+int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out)
+{
+    return fpm_summary_launch(column, dtype, ncomp, np, host_out, g_stream);
+}
+
+int fpm_fill_grid(double *x, uint64_t *id, float *v, int nc, int i0, int64_t np, double boxsize, double shift)
+{
+    return fpm_fill_grid_launch(x, (unsigned long long *) id, v, nc, i0, np, boxsize / nc, shift, g_stream);
+}
+
+int fpm_lpt_evolve(double *x, float *v, const float *dx1, const float *dx2, int64_t np, double D1, double D2, double Dv1, double Dv2)
+{
+    return fpm_lpt_evolve_launch(x, v, dx1, dx2, D1, D2, Dv1, Dv2, np, g_stream);
+}
+
+}   // extern "C"

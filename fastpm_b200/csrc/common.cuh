@@ -1,0 +1,62 @@
+// fastpm_b200 -- shared device/host definitions for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stddef.h>
+
+#define FPM_MAX_RANKS 8
+#define FPM_MAX_STAGES 16
+
+// ---------------------------------------------------------------- errors
+extern "C" void fpm_set_error(const char *fmt, ...);
+extern unsigned long long fpm_launch_counter;      // kernels launched by this library (bench "gpu_launches")
+
+#define FPM_CUDA_OK(expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            fpm_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+#define FPM_CHECK_LAUNCH()                                                                   \
+    do {                                                                                     \
+        fpm_launch_counter++;                                                                \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            fpm_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- mesh geometry
+// One PM mesh of Nmesh^3 cells over a periodic box, x-slab decomposed over `nranks` GPUs.
+//
+// Real-space layout (this rank):   real[xl][y][z],  xl in [0, nxl (+1 halo plane)), pitch_r floats per row
+// k-space layout (this rank):      cplx[kyl][kx][kz], kyl in [0, nyl), pitch_c complex per row, kz in [0, N/2]
+//   (the "transposed-out" order the reference asks PFFT for, pmpfft.c:198-203, with ky slowest so the
+//    slab all-to-all is folded into the y-pass / inverse x-pass stores)
+// pitch_c = N/2+1 rounded up to 16 complex (128 B) so every tile row is sector aligned; pitch_r = 2*pitch_c.
+struct FpmGeom {
+    int n;              // Nmesh
+    int nranks, rank;
+    int nxl, x0;        // local x planes [x0, x0+nxl)
+    int nyl, y0;        // local ky planes [y0, y0+nyl) in k-space
+    int pitch_c;        // complex elements per row
+    int pitch_r;        // floats per row (= 2*pitch_c)
+    double boxsize;
+    double cellsize, inv_cellsize;
+};
+
+// ---------------------------------------------------------------- complex helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i : (x + iy)(-i) = y - ix
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 cmul_pi(float2 a) { return make_float2(-a.y, a.x); }

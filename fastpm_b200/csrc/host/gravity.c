@@ -1,0 +1,107 @@
+/* fastpm_b200 host layer -- the PM force pipeline (reference: libfastpm/gravity.c:273-529).
+ *
+ *   paint -> [halo add] -> r2c (mean-density normalisation and 1/Norm folded into the first FFT pass)
+ *   for each of ACC_x, ACC_y, ACC_z [, POTENTIAL]:
+ *       c2r with the Green's function and i*k_d gradient fused into its first pass -> [halo fetch] -> readout
+ *
+ * against the reference's: ghosts, clear, paint(p)+paint(ghosts), multiply sweep, 2 check sweeps, r2c,
+ * 1/Norm sweep, then per component 3 transfer sweeps + 2 check sweeps + c2r + 2 readouts, ghost reduce.
+ * The particle ghosts of pmghosts.c are replaced by one mesh plane (support 2 needs planes [x0, x0+nxl]).
+ */
+#include "internal.h"
+
+void fastpm_kernel_type_get_orders(FastPMKernelType type, int *potorder, int *gradorder, int *difforder, int *deconvolveorder)
+{
+    fpm_transfer t;
+    if (fpm_transfer_for_kernel((int) type, 0, 0, &t) != 0) fastpm_raise(-1, "Wrong kernel type\n");
+    *potorder = t.potorder;
+    *gradorder = t.gradorder;
+    *difforder = (type == FASTPM_KERNEL_1_4_DIFF0) ? 0 : 1;
+    *deconvolveorder = (type == FASTPM_KERNEL_EASTWOOD || type == FASTPM_KERNEL_GADGET) ? 2 : 0;
+}
+
+/* stand-alone version of the fused kernel: canvas = kernel(delta_k) for one field component */
+void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *delta_k, FastPMFloat *canvas, FastPMFieldDescr field)
+{
+    fpm_transfer t;
+    int attr;
+    if (field.attribute == COLUMN_ACC) attr = 0;
+    else if (field.attribute == COLUMN_POTENTIAL) attr = 1;
+    else { fastpm_raise(-1, "fastpm_b200: gravity attribute %d (density / tidal) is not implemented\n", (int) field.attribute); return; }
+    if (fpm_transfer_for_kernel((int) type, attr, field.memb, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    FPM_MUST(fpm_apply_transfer(pm->mesh, delta_k, canvas, &t));
+}
+
+extern void fpm_halo_add(PM *pm, FastPMFloat *canvas);        /* comm.c */
+extern void fpm_halo_fetch(PM *pm, FastPMFloat *canvas);
+extern void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale);
+extern void fpm_dist_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel);
+
+void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, FastPMSofteningType dealias,
+                                 FastPMKernelType kernel, FastPMFloat *delta_k, double Time)
+{
+    (void) Time;
+    if (dealias != FASTPM_SOFTENING_NONE) fastpm_raise(-1, "fastpm_b200: force softening type %d is not implemented (default is none)\n", (int) dealias);
+    if (fastpm->cosmology->ncdm_linearresponse) fastpm_raise(-1, "fastpm_b200: ncdm linear response is out of scope\n");
+    CLOCK(paint);
+    LEAVE(paint);
+    CLOCK(r2c);
+    LEAVE(r2c);
+    CLOCK(c2r);
+    LEAVE(c2r);
+    CLOCK(readout);
+    LEAVE(readout);
+
+    FastPMFloat *canvas = pm_alloc_noclear(pm, __FILE__, __LINE__);
+
+    /* ---- density: gravity.c:305-353 */
+    ENTER(paint);
+    pm_clear(pm, canvas);
+    double total_mass = 0;
+    for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
+        FastPMStore *p = fastpm_solver_get_species(fastpm, si);
+        if (!p) continue;
+        if (p->mass) {
+            double s[4];
+            FPM_MUST(fpm_summary(p->mass, 4, 1, (int64_t) p->np, s));
+            total_mass += p->meta.M0 * p->np + s[2];
+        } else {
+            total_mass += p->meta.M0 * p->np;         /* sum of fastpm_store_get_mass, gravity.c:330-334 */
+        }
+        FastPMFieldDescr none = { 0, 0 };
+        fastpm_paint_local(painter, canvas, p, p->np, none);
+    }
+    if (pm->NTask > 1) fpm_halo_add(pm, canvas);
+    LEAVE(paint);
+    fpm_comm_allreduce_double(fastpm->comm, &total_mass, 1, 0);
+    const double mean_mass_per_cell = total_mass / pm->Norm;
+
+    ENTER(r2c);
+    /* canvas * (1/mean) (gravity.c:345) and the 1/Norm of pm_r2c (pmpfft.c:382) as one factor on the FFT input */
+    const double scale = (1.0 / mean_mass_per_cell) * (1.0 / pm->Norm);
+    if (pm->NTask > 1) fpm_dist_r2c(pm, canvas, delta_k, scale);
+    else FPM_MUST(fpm_r2c(pm->mesh, canvas, delta_k, scale));
+    LEAVE(r2c);
+
+    /* ---- force components: gravity.c:359-396 */
+    FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    const int nacc = (cdm && cdm->potential) ? 4 : 3;
+    for (int d = 0; d < nacc; d++) {
+        fpm_transfer t;
+        if (fpm_transfer_for_kernel((int) kernel, d < 3 ? 0 : 1, d < 3 ? d : 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        ENTER(c2r);
+        if (pm->NTask > 1) { fpm_dist_c2r(pm, delta_k, canvas, &t); fpm_halo_fetch(pm, canvas); }
+        else FPM_MUST(fpm_c2r(pm->mesh, delta_k, canvas, &t));
+        LEAVE(c2r);
+        ENTER(readout);
+        for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
+            FastPMStore *p = fastpm_solver_get_species(fastpm, si);
+            if (!p) continue;
+            FastPMFieldDescr f = { d < 3 ? COLUMN_ACC : COLUMN_POTENTIAL, d < 3 ? d : 0 };
+            if (d == 3 && !p->potential) continue;
+            fastpm_readout_local(painter, canvas, p, p->np, f);
+        }
+        LEAVE(readout);
+    }
+    pm_free(pm, canvas);
+}

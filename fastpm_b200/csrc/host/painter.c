@@ -1,0 +1,52 @@
+/* fastpm_b200 host layer -- painter object (reference: libfastpm/painter.c:128-374, painter-cic.c).
+ * Only the CIC window (the default, lua-runtime-fastpm.lua:132-138, and the one BASELINE.json names) runs
+ * on the device; the struct keeps the reference's public layout. */
+#include "internal.h"
+
+static void no_host_paint(FastPMPainter *painter, FastPMFloat *canvas, double pos[3], double weight, int diffdir)
+{ (void) painter; (void) canvas; (void) pos; (void) weight; (void) diffdir;
+  fastpm_raise(-1, "painter->paint on a single particle: the canvas is device memory; use fastpm_paint_local\n"); }
+static double no_host_readout(FastPMPainter *painter, FastPMFloat *canvas, double pos[3], int diffdir)
+{ (void) painter; (void) canvas; (void) pos; (void) diffdir;
+  fastpm_raise(-1, "painter->readout on a single particle: the canvas is device memory; use fastpm_readout_local\n"); return 0; }
+
+void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type, int support)
+{
+    if (type != FASTPM_PAINTER_CIC) fastpm_raise(-1, "fastpm_b200: only the CIC painter is implemented (painter type %d requested)\n", (int) type);
+    (void) support;
+    painter->pm = pm;
+    painter->paint = no_host_paint; painter->readout = no_host_readout;
+    painter->kernel = NULL; painter->diff = NULL;
+    painter->diffdir = -1;
+    painter->support = 2;                       /* painter.c:134-137: CIC forces support = 2 */
+    painter->hsupport = 1.0; painter->invh = 1.0;
+    painter->left = 0; painter->Npoints = 8; painter->shift = 0;
+}
+
+void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
+{
+    const float *fcol = NULL; int fstride = 1;
+    if (field.attribute) {
+        int ci = fastpm_store_find_column_id(p, field.attribute);
+        if (ci < 0 || !p->columns[ci] || p->_column_info[ci].membsize != 4) fastpm_raise(-1, "paint: field column must be an allocated float column\n");
+        fcol = (const float *) p->columns[ci] + field.memb;
+        fstride = (int) p->_column_info[ci].nmemb;
+    }
+    FPM_MUST(fpm_paint(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) size, p->meta.M0, p->mass, fcol, fstride));
+}
+
+void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
+{
+    int ci = fastpm_store_find_column_id(p, field.attribute);
+    if (ci < 0 || !p->columns[ci] || p->_column_info[ci].from_double == NULL) fastpm_raise(-1, "readout: target column is not an allocated float column\n");
+    float *out = (float *) p->columns[ci] + field.memb;
+    FPM_MUST(fpm_readout(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) size, out, (int) p->_column_info[ci].nmemb, 1.0));
+}
+
+/* painter.c:342-356: clear + paint (the ghost exchange of the reference is the mesh-plane halo here) */
+void fastpm_paint(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, FastPMFieldDescr field)
+{
+    pm_clear(painter->pm, canvas);
+    fastpm_paint_local(painter, canvas, p, p->np, field);
+    if (painter->pm->NTask > 1) fastpm_raise(-1, "fastpm_paint on several GPUs: use fastpm_solver_compute_force in this build\n");
+}

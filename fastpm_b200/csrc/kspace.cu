@@ -1,0 +1,317 @@
+// fastpm_b200 -- whole-mesh sweeps that are not folded into an FFT pass: stand-alone k-space kernels,
+// CIC deconvolution, P(k) binning, power-spectrum colouring of white noise, 2LPT source terms.
+// Reference: libfastpm/transfer.c:78-113 (decic), :154-220 (laplace / multiply), :189-210 (any_transfer);
+// powerspectrum.c:35-124; initialcondition.c:56-64 (induce_correlation); pm2lpt.c:97-122 (2LPT source);
+// powerspectrum.c:392-433 (funck_eval, log-log interpolation of the input table).
+//
+// k-space layout of this build: cplx[ky_local][kx][kz] with pitch_c complex per row (see common.cuh).
+#include "common.cuh"
+#include "mesh.cuh"
+
+// ------------------------------------------------------------------ generic mode iterator
+// one thread per complex element of the local k-space block, kz fastest (coalesced)
+struct ModeIdx { int ix, iy, iz; size_t off; bool valid; };
+
+__device__ __forceinline__ ModeIdx mode_from_linear(const FpmGeom &g, size_t t)
+{
+    ModeIdx m;
+    const int hc = g.n / 2 + 1;
+    const int pc = g.pitch_c;
+    m.iz = (int) (t % pc);
+    const size_t row = t / pc;
+    m.ix = (int) (row % g.n);
+    const int iyl = (int) (row / g.n);
+    m.iy = iyl + g.y0;
+    m.off = t;
+    m.valid = (m.iz < hc) && (iyl < g.nyl);
+    return m;
+}
+
+__global__ void __launch_bounds__(256) transfer_kernel(const FpmGeom g, const FpmKTables kt, const FpmTransferSpec s,
+        const float2 *__restrict__ from, float2 *__restrict__ to, size_t total)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        to[m.off] = fpm_apply_transfer(s, kt, from[m.off], m.ix, m.iy, m.iz);
+    }
+}
+
+// transfer.c:78-113: kernel[d][i] = 1/sinc^2(k h/2) in double (table prepared on the host), product in
+// double, one rounding to float per component.
+__global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const double *__restrict__ dtab,
+        const float2 *__restrict__ from, float2 *__restrict__ to, size_t total)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        double smth = 1.0;
+        smth *= dtab[m.ix]; smth *= dtab[m.iy]; smth *= dtab[m.iz];
+        float2 v = from[m.off];
+        v.x = (float) ((double) v.x * smth);
+        v.y = (float) ((double) v.y * smth);
+        to[m.off] = v;
+    }
+}
+
+// powerspectrum.c:35-124.  bins = n/2 integer shells of |i|; per bin: sum w, sum w*|delta|^2, sum w*|k|.
+// Shared-memory histograms per CTA (double), flushed with one global atomic per non-empty bin.
+// `decic` folds the deconvolution (rounded to float like the reference's in-place sweep) into the read.
+__global__ void __launch_bounds__(256) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
+        const float2 *__restrict__ dk, size_t total, double k0, double *__restrict__ out /* [3][nbins] + 1 */)
+{
+    extern __shared__ double hist[];     // [3][nbins], then one slot: sum over ALL modes of w |delta|^2 (pm_compute_variance)
+    const int nbins = g.n / 2;
+    for (int i = threadIdx.x; i < 3 * nbins + 1; i += blockDim.x) hist[i] = 0;
+    double allsum = 0;
+    __syncthreads();
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    const int n = g.n, h = n / 2;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        {
+            const float2 v0 = dk[m.off];
+            allsum += ((m.iz == 0 || m.iz == h) ? 1.0 : 2.0) * ((double) v0.x * (double) v0.x + (double) v0.y * (double) v0.y);
+        }
+        if (m.ix == 0 && m.iy == 0 && m.iz == 0) continue;
+        long long ikx = m.ix > h ? m.ix - n : m.ix;
+        long long iky = m.iy > h ? m.iy - n : m.iy;
+        long long ikz = m.iz > h ? m.iz - n : m.iz;
+        const long long kk = ikx * ikx + iky * iky + ikz * ikz;
+        long long bin = (long long) floor(sqrt((double) kk)) - 2;
+        if (bin < 0) bin = 0;
+        while ((bin + 1) * (bin + 1) <= kk) bin++;
+        if (bin >= nbins) continue;
+        float2 v = dk[m.off];
+        if (decic) {
+            double smth = 1.0;
+            smth *= dtab[m.ix]; smth *= dtab[m.iy]; smth *= dtab[m.iz];
+            v.x = (float) ((double) v.x * smth);
+            v.y = (float) ((double) v.y * smth);
+        }
+        const double value = (double) v.x * (double) v.x + (double) v.y * (double) v.y;
+        const double w = (m.iz == 0 || m.iz == h) ? 1.0 : 2.0;
+        const double k = sqrt((double) kk) * k0;
+        atomicAdd(&hist[bin], w);
+        atomicAdd(&hist[nbins + bin], w * value);
+        atomicAdd(&hist[2 * nbins + bin], w * k);
+    }
+    for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
+    if ((threadIdx.x & 31) == 0 && allsum != 0) atomicAdd(&hist[3 * nbins], allsum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * nbins + 1; i += blockDim.x)
+        if (hist[i] != 0) atomicAdd(&out[i], hist[i]);
+}
+
+// buf[i] = (float)(buf[i] * value): fastpm_apply_multiply_transfer, transfer.c:213-220
+__global__ void __launch_bounds__(256) scale_kernel(const float *__restrict__ from, float *__restrict__ to, size_t nfloats, double value)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < nfloats; i += stride) to[i] = (float) ((double) from[i] * value);
+}
+
+// buf[i] = (float)(buf[i] / value): the unit conversion reverted in fastpm_unset_species_snapshot, solver.c:738-742
+__global__ void __launch_bounds__(256) divide_kernel(const float *__restrict__ from, float *__restrict__ to, size_t nfloats, double value)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < nfloats; i += stride) to[i] = (float) ((double) from[i] / value);
+}
+
+// pm2lpt.c:103-105 / :118-120:  source += a*b   or   source -= a*a   (float arithmetic, like the reference)
+__global__ void __launch_bounds__(256) muladd_kernel(float *__restrict__ source, const float *__restrict__ a, const float *__restrict__ b,
+        size_t nfloats, float sign)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < nfloats; i += stride) {
+        const float prod = __fmul_rn(a[i], b[i]);
+        source[i] = sign > 0 ? __fadd_rn(source[i], prod) : __fsub_rn(source[i], prod);
+    }
+}
+
+// fastpm_funck_eval (powerspectrum.c:392-433): piecewise log-log (or linear where a value is <= 0) interpolation
+__device__ double funck_eval(const double *__restrict__ tk, const double *__restrict__ tf, int size, double k)
+{
+    if (k == 0) return 1;
+    int l = 0, r = size - 1;
+    while (r - l > 1) {
+        const int mid = (r + l) / 2;
+        if (k < tk[mid]) r = mid; else l = mid;
+    }
+    const double k2 = tk[r], k1 = tk[l], f2 = tf[r], f1 = tf[l];
+    if (l == r) return tf[l];
+    if (f1 <= 0 || f2 <= 0 || k1 == 0 || k2 == 0) {
+        double f = (k - k1) * f2 + (k2 - k) * f1;
+        return f / (k2 - k1);
+    }
+    const double lk = log(k), lf1 = log(f1), lf2 = log(f2), lk1 = log(k1), lk2 = log(k2);
+    double f = (lk - lk1) * lf2 + (lk2 - lk) * lf1;
+    f /= (lk2 - lk1);
+    return exp(f);
+}
+
+// fastpm_ic_induce_correlation: delta_k *= sqrt(P(|k|)/V)   with |k| = sqrt(sum of float kk[d])
+__global__ void __launch_bounds__(256) induce_kernel(const FpmGeom g, const FpmKTables kt, float2 *__restrict__ dk, size_t total,
+        const double *__restrict__ tk, const double *__restrict__ tp, int size, double volume)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        double kk = 0;
+        kk += (double) kt.kk[m.ix]; kk += (double) kt.kk[m.iy]; kk += (double) kt.kk[m.iz];
+        const double k = sqrt(kk);
+        double f = sqrt(funck_eval(tk, tp, size, k));
+        f *= sqrt(1.0 / volume);
+        float2 v = dk[m.off];
+        v.x = (float) ((double) v.x * f);
+        v.y = (float) ((double) v.y * f);
+        dk[m.off] = v;
+    }
+}
+
+// ------------------------------------------------------------------ synthetic white noise (bench ICs)
+// Counter-based generator (Philox-4x32-10) so that a 1024^3 field needs no serial RANLUX stream; the
+// field is Hermitian by construction because it is the r2c transform of a REAL white-noise field:
+// this kernel fills the real mesh with unit-variance Gaussians (Box-Muller).  Declared deviation from
+// initialcondition.c:145-273, used only for benchmark-size synthetic ICs; parity tests feed both sides
+// the oracle's Gadget-scheme delta_k instead.
+__device__ __forceinline__ void philox_round(unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3, unsigned k0, unsigned k1)
+{
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned h0 = (unsigned) (p0 >> 32), l0 = (unsigned) p0, h1 = (unsigned) (p1 >> 32), l1 = (unsigned) p1;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+}
+__global__ void __launch_bounds__(256) whitenoise_kernel(const FpmGeom g, float *__restrict__ real, unsigned long long seed)
+{
+    const size_t ncell = (size_t) g.nxl * g.n * g.n;
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; 2 * t < ncell; t += stride) {
+        const size_t cell = 2 * t;                   // two cells (adjacent in z) per counter
+        const int z = (int) (cell % g.n);
+        const size_t row = cell / g.n;               // xl*n + y
+        const size_t gcell = ((size_t) g.x0 * g.n * g.n + cell) / 2;
+        unsigned c0 = (unsigned) gcell, c1 = (unsigned) (gcell >> 32), c2 = 0x5eedu, c3 = 0;
+        unsigned k0 = (unsigned) seed, k1 = (unsigned) (seed >> 32);
+        #pragma unroll
+        for (int r = 0; r < 10; r++) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        const float u1 = ((float) c0 + 1.0f) * 2.3283064365386963e-10f;     // (0, 1]
+        const float u2 = (float) c1 * 2.3283064365386963e-10f;
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        float *p = real + row * g.pitch_r + z;
+        p[0] = rad * cs; p[1] = rad * sn;
+    }
+}
+
+// set one mode (and nothing else): used for delta_k(0,0,0) = 1 (src/fastpm.c:541-544)
+__global__ void set_mode_kernel(const FpmGeom g, float2 *dk, int ix, int iy, int iz, float re, float im)
+{
+    const int iyl = iy - g.y0;
+    if (iyl < 0 || iyl >= g.nyl) return;
+    dk[((size_t) iyl * g.n + ix) * g.pitch_c + iz] = make_float2(re, im);
+}
+
+// ------------------------------------------------------------------ launchers
+static inline unsigned sweep_grid(size_t n)
+{
+    size_t b = (n + 255) / 256;
+    const size_t cap = 148 * 16;
+    return (unsigned) (b < cap ? (b > 0 ? b : 1) : cap);
+}
+static inline size_t cplx_total(const FpmGeom &g) { return (size_t) g.nyl * g.n * g.pitch_c; }
+
+int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, *s, (const float2 *) from, (float2 *) to, total);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    decic_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->d_decic, (const float2 *) from, (float2 *) to, total);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// d_out: [3][n/2] = Nmodes, sum w*|d|^2, sum w*k (not yet normalised; multi-GPU callers all-reduce first), then 1 slot:
+// the sum of w*|d|^2 over every mode including DC and the corners beyond the last shell
+int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const int nbins = g.n / 2;
+    const size_t total = cplx_total(g);
+    const size_t smem = sizeof(double) * (3 * nbins + 1);
+    FPM_CUDA_OK(cudaMemsetAsync(d_out, 0, smem, st));
+    static bool attr_done = false;
+    if (!attr_done) {
+        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    if (smem > 96 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
+    const double k0 = 2 * M_PI / g.boxsize;
+    powerspectrum_kernel<<<148 * 4, 256, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, total, k0, d_out);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_scale_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st)
+{
+    scale_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_divide_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st)
+{
+    divide_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_muladd_launch(float *source, const float *a, const float *b, size_t nfloats, int sign, cudaStream_t st)
+{
+    muladd_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(source, a, b, nfloats, sign > 0 ? 1.f : -1.f);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const double *d_tp, int size, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const size_t total = cplx_total(g);
+    const double volume = g.boxsize * g.boxsize * g.boxsize;
+    induce_kernel<<<sweep_grid(total), 256, 0, st>>>(g, m->ktab, (float2 *) dk, total, d_tk, d_tp, size, volume);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const size_t ncell = (size_t) g.nxl * g.n * g.n;
+    whitenoise_kernel<<<sweep_grid(ncell / 2), 256, 0, st>>>(g, real, seed);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st)
+{
+    set_mode_kernel<<<1, 1, 0, st>>>(m->geom, (float2 *) dk, ix, iy, iz, re, im);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}

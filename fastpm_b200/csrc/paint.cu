@@ -1,0 +1,147 @@
+// fastpm_b200 -- CIC mass deposition and force readout for sm_100a.
+// Reference: libfastpm/painter-cic.c:34-110 (cic_paint_tuned), :113-190 (cic_readout_tuned),
+// driven per particle by painter.c:320-339 / :358-374.
+//
+// Arithmetic follows the reference: cell coordinate, cell index and the eight weights are evaluated
+// in double (positions need > 24 mantissa bits at Nmesh = 2048), D[1]/T[1] carry the particle weight,
+// products are formed in the order  w_z * w_x * w_y, the mesh is float32.  Readout sums the eight
+// products in double, in the reference's order, and rounds once to float (store.c:79-91), so it is
+// bit-identical to the reference for an identical mesh.  Paint differs from the reference only in the
+// order in which float32 additions reach a cell (the reference itself is unordered: `omp atomic`).
+//
+// Particles are kept in (nearly) Lagrangian order, which is spatially coherent, so that the 8 scatter
+// /gather addresses of a warp fall into a few L2-resident mesh planes; red.global.add.f32 is used for
+// the scatter.  x-slab decomposition: a particle of this rank has floor(x/h) in [x0, x0+nxl); its +1
+// plane may be the halo plane nxl, which is exchanged with the next rank (single GPU: periodic wrap).
+#include "common.cuh"
+#include "mesh.cuh"
+
+struct CicIndex {
+    int lx0, lx1, j0, j1, k0, k1;      // lx*: local plane index or -1 when outside this rank
+    double D[3], T[3];
+};
+
+__device__ __forceinline__ void cic_setup(const FpmGeom &g, const double *pos, CicIndex &c)
+{
+    const int n = g.n;
+    int I[3];
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double xyz = pos[d] * g.inv_cellsize;
+        const double fl = floor(xyz);
+        I[d] = (int) fl;
+        c.D[d] = xyz - (double) I[d];
+        c.T[d] = 1. - c.D[d];
+    }
+    int I1[3];
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        I1[d] = I[d] + 1;
+        I[d] %= n; if (I[d] < 0) I[d] += n;
+        I1[d] %= n; if (I1[d] < 0) I1[d] += n;
+    }
+    c.j0 = I[1]; c.j1 = I1[1]; c.k0 = I[2]; c.k1 = I1[2];
+    if (g.nranks == 1) {
+        c.lx0 = I[0]; c.lx1 = I1[0];
+    } else {
+        // planes [x0, x0+nxl] are addressable (the last one is the halo); periodic in the global index
+        int l0 = I[0] - g.x0; if (l0 < 0) l0 += n;
+        int l1 = I1[0] - g.x0; if (l1 < 0) l1 += n;
+        c.lx0 = (l0 <= g.nxl) ? l0 : -1;
+        c.lx1 = (l1 <= g.nxl) ? l1 : -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
+        const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
+        int field_stride, long long np)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    CicIndex c;
+    cic_setup(g, pos, c);
+    double weight = mass ? M0 + (double) mass[i] : M0;        // fastpm_store_get_mass, store.c:120-128
+    if (field) weight *= (double) field[i * field_stride];
+    c.D[1] *= weight; c.T[1] *= weight;
+    const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    if (c.lx0 >= 0) {
+        float *p0 = canvas + (size_t) c.lx0 * pl;
+        atomicAdd(p0 + c.j0 * pr + c.k0, (float) (c.T[2] * c.T[0] * c.T[1]));
+        atomicAdd(p0 + c.j0 * pr + c.k1, (float) (c.D[2] * c.T[0] * c.T[1]));
+        atomicAdd(p0 + c.j1 * pr + c.k0, (float) (c.T[2] * c.T[0] * c.D[1]));
+        atomicAdd(p0 + c.j1 * pr + c.k1, (float) (c.D[2] * c.T[0] * c.D[1]));
+    }
+    if (c.lx1 >= 0) {
+        float *p1 = canvas + (size_t) c.lx1 * pl;
+        atomicAdd(p1 + c.j0 * pr + c.k0, (float) (c.T[2] * c.D[0] * c.T[1]));
+        atomicAdd(p1 + c.j0 * pr + c.k1, (float) (c.D[2] * c.D[0] * c.T[1]));
+        atomicAdd(p1 + c.j1 * pr + c.k0, (float) (c.T[2] * c.D[0] * c.D[1]));
+        atomicAdd(p1 + c.j1 * pr + c.k1, (float) (c.D[2] * c.D[0] * c.D[1]));
+    }
+}
+
+__global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    CicIndex c;
+    cic_setup(g, pos, c);
+    const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    double value = 0;
+    // a uniform pre-scale reproduces fastpm_apply_multiply_transfer on the real field (pm2lpt.c:133)
+    #define CELL(ptr) (prescale == 1.0 ? (double) __ldg(ptr) : (double) (float) ((double) __ldg(ptr) * prescale))
+    if (c.lx0 >= 0) {
+        const float *p0 = canvas + (size_t) c.lx0 * pl;
+        value += CELL(p0 + c.j0 * pr + c.k0) * (c.T[2] * c.T[0] * c.T[1]);
+        value += CELL(p0 + c.j0 * pr + c.k1) * (c.D[2] * c.T[0] * c.T[1]);
+        value += CELL(p0 + c.j1 * pr + c.k0) * (c.T[2] * c.T[0] * c.D[1]);
+        value += CELL(p0 + c.j1 * pr + c.k1) * (c.D[2] * c.T[0] * c.D[1]);
+    }
+    if (c.lx1 >= 0) {
+        const float *p1 = canvas + (size_t) c.lx1 * pl;
+        value += CELL(p1 + c.j0 * pr + c.k0) * (c.T[2] * c.D[0] * c.T[1]);
+        value += CELL(p1 + c.j0 * pr + c.k1) * (c.D[2] * c.D[0] * c.T[1]);
+        value += CELL(p1 + c.j1 * pr + c.k0) * (c.T[2] * c.D[0] * c.D[1]);
+        value += CELL(p1 + c.j1 * pr + c.k1) * (c.D[2] * c.D[0] * c.D[1]);
+    }
+    #undef CELL
+    out[i * out_stride] = (float) value;
+}
+
+// adds the received halo plane into local plane 0 (multi-GPU paint epilogue)
+__global__ void plane_add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t nfloats)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < nfloats; i += stride) dst[i] += src[i];
+}
+
+int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0,
+                     const float *field, int field_stride, long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    const unsigned grid = (unsigned) ((np + 255) / 256);
+    cic_paint_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride,
+                       double prescale, long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    const unsigned grid = (unsigned) ((np + 255) / 256);
+    cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st)
+{
+    plane_add_kernel<<<148 * 8, 256, 0, st>>>(dst, src, nfloats);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,241 @@
+// fastpm_b200 -- streaming particle updates for sm_100a: kick, drift, periodic wrap, 2LPT
+// displacement, grid fill and column summaries.
+// Reference: libfastpm/factors.c:73-115 (fastpm_drift_one), :148-171 (fastpm_kick_one), :176-197,
+// :374-392 (the store loops); store.c:447-475 (wrap), :723-806 (fill), :808-908 (summary);
+// pm2lpt.c:168-210 (pm_2lpt_evolve).
+//
+// The factor tables (32 samples, interpolated at a_f and at the particle time stamp) are looked up on
+// the host exactly as the reference does (factors.c:40-71,117-146) and arrive here as scalars.  Each
+// expression keeps the reference's types: float columns, double factors, double position, one rounding
+// to float where the reference stores a float -- so kick and drift are bit-identical to the reference.
+#include "common.cuh"
+
+struct KickArgs {
+    float *v_out; const float *v_in; const float *acc; const float *dx1; const float *dx2;
+    double dda, q1, q2, Dv1, Dv2;
+    int cola;
+    long long n3;      // 3 * np
+};
+
+__global__ void __launch_bounds__(256) kick_kernel(const KickArgs a)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < a.n3; i += stride) {
+        float ax = a.acc[i];
+        if (a.cola) {
+            const double t = (double) a.dx1[i] * a.q1 + (double) a.dx2[i] * a.q2;
+            ax = (float) ((double) ax + t);                                  // ax += (...)
+        }
+        float vo = (float) ((double) a.v_in[i] + (double) ax * a.dda);       // vo[d] = v + ax * dda
+        if (a.cola) {
+            const double t = (double) a.dx1[i] * a.Dv1 + (double) a.dx2[i] * a.Dv2;
+            vo = (float) ((double) vo + t);                                  // vo[d] += (...)
+        }
+        a.v_out[i] = vo;
+    }
+}
+
+struct DriftArgs {
+    double *x_out; const double *x_in; const float *v; const float *dx1; const float *dx2;
+    double dyyy, da1, da2, Dv1, Dv2;
+    int mode;          // FastPMForceType: 0 FASTPM, 1 PM, 2 COLA, 3 2LPT, 4 ZA
+    long long n3;
+};
+
+__global__ void __launch_bounds__(256) drift_kernel(const DriftArgs a)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < a.n3; i += stride) {
+        double xo;
+        const double x = a.x_in[i];
+        switch (a.mode) {
+            case 3: xo = x + (double) a.dx1[i] * a.da1 + (double) a.dx2[i] * a.da2; break;
+            case 4: xo = x + (double) a.dx1[i] * a.da1; break;
+            case 2: {
+                const double v = (double) a.v[i] - ((double) a.dx1[i] * a.Dv1 + (double) a.dx2[i] * a.Dv2);
+                xo = x + v * a.dyyy;
+                xo += (double) a.dx1[i] * a.da1 + (double) a.dx2[i] * a.da2;
+                break;
+            }
+            default: xo = x + (double) a.v[i] * a.dyyy; break;
+        }
+        a.x_out[i] = xo;
+    }
+}
+
+// store.c:447-475: remainder() then fold into [0, L]; a particle further than 10000 boxes away is an error
+__global__ void __launch_bounds__(256) wrap_kernel(double *x, long long n3, double L, int *bad)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < n3; i += stride) {
+        const double xi = x[i];
+        // the reference applies integer abs() to a double here (store.c:453): the truncated ratio
+        const double nwrap = (double) abs((int) (xi / L));
+        double x1 = remainder(xi, L);
+        while (x1 < 0) x1 += L;
+        while (x1 > L) x1 -= L;
+        x[i] = x1;
+        if (nwrap > 10000) atomicExch(bad, 1);
+    }
+}
+
+// pm2lpt.c:192-208
+struct LptEvolveArgs {
+    double *x; float *v; const float *dx1; const float *dx2;
+    double D1, D2, Dv1, Dv2;
+    long long n3;
+};
+__global__ void __launch_bounds__(256) lpt_evolve_kernel(const LptEvolveArgs a)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < a.n3; i += stride) {
+        a.x[i] += a.D1 * (double) a.dx1[i] + a.D2 * (double) a.dx2[i];
+        if (a.v) {
+            float v = a.v[i];
+            v = (float) ((double) v + (double) a.dx2[i] * a.Dv2);
+            v = (float) ((double) v + a.Dv1 * (double) a.dx1[i]);
+            a.v[i] = v;
+        }
+    }
+}
+
+// store.c:756-793: one particle per cell of the nc^3 Lagrangian grid owned by this rank,
+// id = i*nc^2 + j*nc + k, x = id-derived index * (L/nc) + shift (store.c:676-692)
+__global__ void __launch_bounds__(256) fill_grid_kernel(double *x, unsigned long long *id, float *v, int nc, int i0, long long np,
+        double scale, double shift)
+{
+    long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; p < np; p += stride) {
+        const long long plane = (long long) nc * nc;
+        const int i = (int) (p / plane) + i0;
+        const long long rem = p % plane;
+        const int j = (int) (rem / nc), k = (int) (rem % nc);
+        if (id) id[p] = (unsigned long long) i * plane + (unsigned long long) j * nc + k;
+        x[3 * p + 0] = i * scale + shift;
+        x[3 * p + 1] = j * scale + shift;
+        x[3 * p + 2] = k * scale + shift;
+        if (v) { v[3 * p] = 0.f; v[3 * p + 1] = 0.f; v[3 * p + 2] = 0.f; }
+    }
+}
+
+// ------------------------------------------------------------------ summary (min, max, sum, sum of squares)
+template <typename T>
+__global__ void __launch_bounds__(256) summary_kernel(const T *col, long long np, int ncomp, double *partial)
+{
+    // partial[block][comp][4]
+    __shared__ double sh[8][4 * 9];
+    double mn[9], mx[9], s1[9], s2[9];
+    for (int d = 0; d < ncomp; d++) { mn[d] = 1e20; mx[d] = -1e20; s1[d] = 0; s2[d] = 0; }
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < np; i += stride)
+        for (int d = 0; d < ncomp; d++) {
+            const double v = (double) col[i * ncomp + d];
+            s1[d] += v; s2[d] += v * v; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 0; d < ncomp; d++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+            s1[d] += __shfl_xor_sync(0xffffffffu, s1[d], o);
+            s2[d] += __shfl_xor_sync(0xffffffffu, s2[d], o);
+        }
+        if (lane == 0) { sh[warp][4 * d] = mn[d]; sh[warp][4 * d + 1] = mx[d]; sh[warp][4 * d + 2] = s1[d]; sh[warp][4 * d + 3] = s2[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < ncomp) {
+        const int d = threadIdx.x;
+        double a = 1e20, b = -1e20, c = 0, e = 0;
+        for (int w = 0; w < (int) (blockDim.x >> 5); w++) {
+            a = fmin(a, sh[w][4 * d]); b = fmax(b, sh[w][4 * d + 1]); c += sh[w][4 * d + 2]; e += sh[w][4 * d + 3];
+        }
+        double *out = partial + ((size_t) blockIdx.x * ncomp + d) * 4;
+        out[0] = a; out[1] = b; out[2] = c; out[3] = e;
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static inline unsigned stream_grid(long long n)
+{
+    long long b = (n + 255) / 256;
+    const long long cap = 148 * 16;
+    return (unsigned) (b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2,
+                    double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    KickArgs a = { v_out, v_in, acc, dx1, dx2, dda, q1, q2, Dv1, Dv2, cola, 3 * np };
+    kick_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2,
+                     double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    DriftArgs a = { x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, mode, 3 * np };
+    drift_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    wrap_kernel<<<stream_grid(3 * np), 256, 0, st>>>(x, 3 * np, L, d_bad);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2,
+                          long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    LptEvolveArgs a = { x, v, dx1, dx2, D1, D2, Dv1, Dv2, 3 * np };
+    lpt_evolve_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    fill_grid_kernel<<<stream_grid(np), 256, 0, st>>>(x, id, v, nc, i0, np, scale, shift);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// dtype: 4 = float32 column, 8 = float64 column.  host_out[comp][4] = {min, max, sum, sumsq}
+int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, double *host_out, cudaStream_t st)
+{
+    if (ncomp < 1 || ncomp > 9) { fpm_set_error("summary: ncomp %d out of range", ncomp); return -1; }
+    const unsigned grid = stream_grid(np);
+    double *d_partial = nullptr;
+    FPM_CUDA_OK(cudaMalloc(&d_partial, sizeof(double) * 4 * ncomp * grid));
+    if (dtype == 4) summary_kernel<float><<<grid, 256, 0, st>>>((const float *) col, np, ncomp, d_partial);
+    else summary_kernel<double><<<grid, 256, 0, st>>>((const double *) col, np, ncomp, d_partial);
+    FPM_CHECK_LAUNCH();
+    double *h = (double *) malloc(sizeof(double) * 4 * ncomp * grid);
+    FPM_CUDA_OK(cudaMemcpyAsync(h, d_partial, sizeof(double) * 4 * ncomp * grid, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    for (int d = 0; d < ncomp; d++) { host_out[4 * d] = 1e20; host_out[4 * d + 1] = -1e20; host_out[4 * d + 2] = 0; host_out[4 * d + 3] = 0; }
+    for (unsigned b = 0; b < grid; b++)
+        for (int d = 0; d < ncomp; d++) {
+            const double *p = h + ((size_t) b * ncomp + d) * 4;
+            if (p[0] < host_out[4 * d]) host_out[4 * d] = p[0];
+            if (p[1] > host_out[4 * d + 1]) host_out[4 * d + 1] = p[1];
+            host_out[4 * d + 2] += p[2]; host_out[4 * d + 3] += p[3];
+        }
+    free(h);
+    FPM_CUDA_OK(cudaFree(d_partial));
+    return 0;
+}

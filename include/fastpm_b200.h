@@ -1,0 +1,147 @@
+/* fastpm_b200 -- C ABI of the B200 (sm_100a) particle-mesh force step.
+ *
+ * This is the drop-in boundary for the hot path of fastpm/fastpm: plain pointers and sizes, no C++
+ * or torch types.  Every entry point names the reference function (file:line under libfastpm/ or
+ * api/fastpm/ of the reference tree) whose work it replaces.  The C host layer in
+ * fastpm_b200/csrc/host/ (FastPMSolver / fastpm_solver_evolve mirror, include/fastpm_b200_solver.h)
+ * and the Python bindings (fastpm_b200/_lib.py) are both built on exactly these calls.
+ *
+ * Conventions
+ *   - all `*_dev` / mesh / particle pointers are DEVICE pointers from fpm_malloc() unless a name ends in _host;
+ *   - functions return 0 on success, -1 on failure; fpm_last_error() describes the failure;
+ *   - work is issued on the library's stream for the current device; fpm_sync() waits for it;
+ *   - one process drives one GPU (one rank of an x-slab decomposition over `nranks` GPUs).
+ *
+ * Device layouts (FpmGeom in csrc/common.cuh)
+ *   real mesh   float  [nx_local (+1 halo plane when nranks > 1)][N][pitch_r],  pitch_r = 2*pitch_c
+ *   k mesh      float2 [ny_local][N (kx)][pitch_c],  kz = 0..N/2 used, pitch_c = roundup(N/2+1, 16)
+ *               (ky-slab "transposed out" order, cf. PFFT_TRANSPOSED_OUT in pmpfft.c:198-203,281-291)
+ *   particles   the reference's column layout (api/fastpm/store.h:101-134): x double[np][3],
+ *               v/acc/dx1/dx2 float[np][3], id uint64[np]
+ */
+#ifndef FASTPM_B200_H
+#define FASTPM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct FpmMesh fpm_mesh;
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+const char *fpm_last_error(void);
+const char *fpm_version(void);
+int fpm_device_init(int device);                       /* libfastpm_init, libfastpm.c:10 */
+int fpm_device_count(void);
+int fpm_device_mem_info(size_t *free_bytes, size_t *total_bytes);
+void *fpm_malloc(size_t bytes);                        /* pm_alloc / store columns: memory.c:182 */
+void fpm_free(void *ptr);                              /* memory.c:260 */
+void *fpm_host_alloc_pinned(size_t bytes);
+void fpm_host_free_pinned(void *ptr);
+int fpm_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int fpm_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int fpm_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes);    /* pm_assign, pmapi.c:24 */
+int fpm_memset(void *dst_dev, int value, size_t bytes);                  /* pm_clear, pmapi.c:30 */
+int fpm_sync(void);
+/* CUDA-event timers on the library stream (the reference's CLOCK/ENTER/LEAVE, api/fastpm/prof.h:24-28) */
+int fpm_timer_create(void **timer);
+int fpm_timer_start(void *timer);
+int fpm_timer_stop(void *timer);
+int fpm_timer_elapsed_ms(void *timer, double *ms);     /* synchronises on the stop event */
+void fpm_timer_destroy(void *timer);
+uint64_t fpm_kernel_launch_count(void);                /* kernels launched by this library so far */
+
+/* ---- mesh object: struct PM, pm_init / pm_destroy, pmpfft.c:108-342 -------------------------- */
+fpm_mesh *fpm_mesh_create(int nmesh, double boxsize, int nranks, int rank);
+void fpm_mesh_destroy(fpm_mesh *m);
+/* info: [0] Nmesh [1] floats per mesh buffer (pm_allocsize) [2] pitch_r [3] pitch_c [4] nx_local [5] x0
+ *       [6] ny_local [7] y0 [8] nranks [9] rank [10] halo planes */
+int fpm_mesh_info(const fpm_mesh *m, int64_t info[16]);
+/* the five float32 per-axis tables of pm_create_k_factors (pmapi.c:235-275), copied to host_out[5][N]
+ * in the order k, kk, k_finite, kk_finite, kk_finite2 */
+int fpm_mesh_ktables_host(const fpm_mesh *m, float *host_out);
+
+/* ---- K1 CIC paint: fastpm_paint_local + cic_paint_tuned, painter.c:320 / painter-cic.c:34 ---- */
+/* canvas += CIC(x) * (M0 + mass[i]) * field[i*field_stride];  mass and field may be NULL.  The
+ * canvas is NOT cleared (call fpm_memset first, like pm_clear in gravity.c:310). */
+int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np,
+              double M0, const float *mass, const float *field, int field_stride);
+/* ---- K5 CIC readout: fastpm_readout_local + cic_readout_tuned, painter.c:358 / painter-cic.c:113 */
+/* out[i*out_stride] = (float) sum_8 (float)(canvas * prescale) * w   (prescale 1.0 = none) */
+int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np,
+                float *out, int out_stride, double prescale);
+
+/* ---- K2 / K4 FFT: pm_r2c, pm_c2r, pmpfft.c:370-399 ------------------------------------------ */
+/* r2c: cplx = DFT(real) * scale.  `real` is destroyed (as with PFFT_DESTROY_INPUT, pmpfft.c:290).
+ * The reference's 1/Norm (pmpfft.c:382-385) is passed as scale = 1/N^3 by the caller. */
+int fpm_r2c(fpm_mesh *m, float *real, float *cplx, double scale);
+/* same, keeping `real` intact: the z- and y-pass intermediate goes to `work` (work != cplx; work == real allowed) */
+int fpm_r2c_ws(fpm_mesh *m, const float *real, float *work, float *cplx, double scale);
+
+/* k-space kernel description: see FpmTransferSpec in csrc/mesh.cuh.  Fused into the first pass of c2r. */
+typedef struct {
+    int32_t active;
+    int32_t potorder;        /* -1 none, 0 kk, 1 kk_finite, 2 kk_finite2: fastpm_apply_laplace_transfer, transfer.c:154 */
+    int32_t negate;          /* apply_pot_transfer multiplies by -1, gravity.c:14-18 */
+    int32_t ngrad;           /* number of i*k gradients: apply_grad_transfer gravity.c:21 / fastpm_apply_diff_transfer transfer.c:116 */
+    int32_t graddir[2];
+    int32_t gradorder;       /* 0 k, 1 k_finite */
+    int32_t zero_selfconj;   /* 1 on the force path (gravity.c:48-56) and for the in-place IC calls (transfer.c:133-148, see device.py) */
+    double scale;
+} fpm_transfer;
+
+/* c2r: real = IDFT(kernel(cplx)), unnormalised; cplx is preserved; kernel may be NULL (plain pm_c2r).
+ * Replaces gravity_apply_kernel_transfer (gravity.c:174-242) + pm_c2r for one field component. */
+int fpm_c2r(fpm_mesh *m, const float *cplx, float *real, const fpm_transfer *kernel);
+/* same with an explicit work buffer for the x- and y-pass (work != cplx); `real` may then alias `cplx`,
+ * which gives the reference's in-place pm_c2r(pm, inplace) */
+int fpm_c2r_ws(fpm_mesh *m, const float *cplx, float *work, float *real, const fpm_transfer *kernel);
+/* fills an fpm_transfer for FastPMKernelType `kernel_type` (fastpm_kernel_type_get_orders, gravity.c:111-171):
+ * attr 0 = ACC component `memb`, attr 1 = POTENTIAL */
+int fpm_transfer_for_kernel(int kernel_type, int attr, int memb, fpm_transfer *out);
+
+/* ---- K3 stand-alone k-space sweeps ----------------------------------------------------------- */
+int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fpm_transfer *kernel);
+int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to);      /* transfer.c:78 */
+int fpm_scale(const float *from, float *to, size_t nfloats, double value); /* transfer.c:213 */
+int fpm_divide(const float *from, float *to, size_t nfloats, double value); /* solver.c:738-742 */
+int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign); /* pm2lpt.c:103,118 */
+int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im); /* transfer.c:306 */
+/* delta_k *= sqrt(P(k)/V), P log-log interpolated from the table: initialcondition.c:56-64 */
+int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host, const double *p_host, int size);
+/* unit-variance real white noise from a counter-based generator (benchmark-size synthetic ICs only) */
+int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed);
+
+/* ---- K9 P(k): fastpm_powerspectrum_init_from_delta, powerspectrum.c:35-124 -------------------- */
+/* host outputs, each [N/2]: k (mode-weighted mean |k|), p (<|delta|^2> V), nmodes.  decic != 0 applies
+ * fastpm_apply_decic_transfer on the fly (solver.c:471) without writing the mesh. */
+int fpm_powerspectrum(const fpm_mesh *m, const float *cplx, int decic, double *k_host, double *p_host, double *nmodes_host);
+/* raw sums for multi-GPU callers: sums_host[3*(N/2) + 1] = sum w, sum w |delta|^2, sum w |k| per shell, then the sum of
+ * w |delta|^2 over ALL modes (pm_compute_variance, pmapi.c:277-295) */
+int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, double *sums_host);
+
+/* ---- K6 / K7 kick, drift: fastpm_kick_store / fastpm_drift_store, factors.c:176,374 ----------- */
+/* factors are the already interpolated differences (fastpm_kick_one, factors.c:148-171) */
+int fpm_kick(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, int64_t np,
+             int forcemode, double dda, double q1, double q2, double Dv1, double Dv2);
+int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, int64_t np,
+              int forcemode, double dyyy, double da1, double da2, double Dv1, double Dv2);
+/* ---- K8 wrap: fastpm_store_wrap, store.c:447 -------------------------------------------------- */
+/* the reference aborts when a particle is > 10000 boxes away (store.c:460-471): that flag is reported by the NEXT
+ * fpm_wrap call or by fpm_wrap_check() (which waits for the stream), so the integrator itself never blocks on it */
+int fpm_wrap(double *x, int64_t np, double boxsize);
+int fpm_wrap_check(void);
+/* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;
+ * host_out[ncomp][4] = min, max, sum, sum of squares */
+int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out);
+/* ---- IC helpers: fastpm_store_fill store.c:723, pm_2lpt_evolve pm2lpt.c:168 ------------------- */
+int fpm_fill_grid(double *x, uint64_t *id, float *v, int nc, int i0, int64_t np, double boxsize, double shift);
+int fpm_lpt_evolve(double *x, float *v, const float *dx1, const float *dx2, int64_t np,
+                   double D1, double D2, double Dv1, double Dv2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
