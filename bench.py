@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- PM-step throughput of the B200 path, with roofline, CPU baseline and end-to-end numbers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nc NC]
+
+Workload (BASELINE.json): nc^3 particles on a (2 nc)^3 force mesh, COLA, K PM steps
+(time_step = linspace(0.1, 1, K): K force evaluations and K-1 kick-drift-kick cycles, the reference's own
+meaning of "K steps", tests/standard.lua:19-22), synthetic 2LPT initial conditions at a = 0.1 from the
+reference's linear P(k) table, P(k) handler on (one measurement + device->host read per force evaluation).
+
+metric  particles/s = nc^3 * K / t_evolve   (src/fastpm.c:368-370 times exactly fastpm_solver_evolve)
+value   t_evolve measured with CUDA events around fastpm_solver_evolve, particle state resident in HBM
+e2e     the same call with HOST particle buffers: pinned host -> device copy of x, v, dx1, dx2, id, the evolve,
+        and the device -> host copy of x, v, id, all inside the timed region
+The reference arm (--impl reference) and the cpu_baseline object time the reference's own sources
+(oracle/_ref, built from /root/reference against the shims in oracle/shims) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pm_step_particles_per_second"
+UNIT = "particles/s"
+KCLASSES = ["paint", "readout", "fft_tile", "fft_z", "kick", "drift", "kspace", "pk", "summary", "other"]
+
+
+def read_pk():
+    import numpy as np
+    tab = np.loadtxt(os.path.join(ROOT, "tests", "golden", "powerspec.txt"))
+    return tab[:, 0].copy(), tab[:, 1].copy()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(nc, B, mode, K, W, threads):
+    """The reference's own CPU implementation (oracle/_ref) on a bounded sample of the workload."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    import numpy as np
+    from oracle import ref
+    if not ref.available():
+        return None
+    pk_text = open(os.path.join(ROOT, "tests", "golden", "powerspec.txt")).read()
+    s = ref.Session(nc=nc, boxsize=float(nc), pm_nc_factor=B, force_mode=mode, growth_mode="LCDM", np_alloc_factor=2.0)
+    dk, _, _ = s.ic_deltak(100, pk_text)
+    s.setup_lpt(dk, 0.1)
+    p0 = s.get_particles()
+    ts = np.linspace(0.1, 1.0, K)
+    if W >= 2:
+        s.evolve(ts[:W])
+        s.set_particles(p0["x"], v=p0["v"], id=p0["id"], dx1=p0.get("dx1"), dx2=p0.get("dx2"), meta=p0["meta"])
+    t = s.evolve(ts)
+    s.close()
+    return dict(value=nc ** 3 * K / t, seconds=t, np=nc ** 3)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    nc_s = args.ref_nc
+    r = cpu_reference_run(nc_s, args.pm_nc_factor, args.mode, args.steps, args.warmup, threads)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfastpm_ref.so is not built"}))
+        return 0
+    sample = "nc=%d^3 particles, %d^3 mesh, %s, %d steps (bounded sample of the nc=%d workload)" % (
+        nc_s, nc_s * args.pm_nc_factor, args.mode, args.steps, args.nc)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 mesh / f64 positions", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "nc=%d^3 particles, %d^3 mesh (B=%d), %s, %d PM steps linspace(0.1,1,%d), 2LPT ICs, P(k) each step" % (
+        args.nc, args.nc * args.pm_nc_factor, args.pm_nc_factor, args.mode.upper(), args.steps, args.steps),
+        "nc": args.nc, "nmesh": args.nc * args.pm_nc_factor, "boxsize_mpc_h": float(args.nc), "force_mode": args.mode,
+        "l2": "mesh (%.1f GB) and particle columns exceed the 126 MB L2; no flush needed" % (
+            4.0 * (args.nc * args.pm_nc_factor) ** 2 * (args.nc * args.pm_nc_factor + 2) / 1e9)}
+
+
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        from fastpm_b200 import multigpu
+        return multigpu.bench_main(args)
+    from fastpm_b200 import _lib
+    from fastpm_b200.solver import Solver, ForceEvent
+    lib = _lib.require_device(int(os.environ.get("LOCAL_RANK", "0")))
+    nc, B, K, W = args.nc, args.pm_nc_factor, args.steps, args.warmup
+    N = nc * B
+    Np = nc ** 3
+    k_tab, p_tab = read_pk()
+    ts = np.linspace(0.1, 1.0, K)
+
+    g = Solver(nc=nc, boxsize=float(nc), pm_nc_factor=B, force_mode=args.mode, growth_mode="LCDM", np_alloc_factor=1.0)
+    g.setup_synthetic_ic(100, k_tab, p_tab, ts[0])
+    meta0 = g.meta
+    cola = args.mode == "cola"
+    cols_in = ["x", "v", "id"] + (["dx1", "dx2"] if cola else [])
+    cols_out = ["x", "v", "id"]
+    itemsize = dict(x=24, v=12, id=8, dx1=12, dx2=12)
+    dtypes = dict(x=np.float64, v=np.float32, id=np.uint64, dx1=np.float32, dx2=np.float32)
+    host = {}
+    for c in cols_in:                                   # pinned host copies of the initial state
+        ptr = lib.fpm_host_alloc_pinned(Np * itemsize[c])
+        if not ptr:
+            raise RuntimeError("pinned host allocation failed: " + lib.fpm_last_error().decode())
+        n_el = Np * itemsize[c] // np.dtype(dtypes[c]).itemsize
+        host[c] = (ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtypes[c]))), (n_el,)))
+        _lib.check(lib.fpm_memcpy_d2h(ptr, g.column_ptr(c), Np * itemsize[c]), "save IC")
+
+    def restore():
+        for c in cols_in:
+            _lib.check(lib.fpm_memcpy_h2d(g.column_ptr(c), host[c][0], Np * itemsize[c]), "restore IC")
+        g.set_meta(meta0["a_x"], meta0["a_v"], meta0["M0"])
+
+    spectra = []
+
+    def on_force_after(solver_ptr, event_ptr, userdata):      # the reference's write_powerspectrum handler, src/fastpm.c:1711-1776
+        ev = C.cast(event_ptr, C.POINTER(ForceEvent)).contents
+        spectra.append(g.powerspectrum_of(ev.pm, ev.delta_k))
+        return 0
+
+    g.add_handler("FORCE", 1, on_force_after)
+
+    if W >= 1:                                          # warm-up: the first max(W,2) entries of the same table
+        g.evolve(ts[:max(W, 2)])
+        restore()
+
+    # ---- device-resident timed run
+    timer = C.c_void_p()
+    _lib.check(lib.fpm_timer_create(C.byref(timer)))
+    lib.fpm_prof_reset()
+    lib.fpm_prof_enable(1)
+    launches0 = int(lib.fpm_kernel_launch_count())
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    _lib.check(lib.fpm_sync())
+    t_wall = time.perf_counter()
+    lib.fpm_timer_start(timer)
+    g.evolve(ts)
+    lib.fpm_timer_stop(timer)
+    ms = C.c_double()
+    _lib.check(lib.fpm_timer_elapsed_ms(timer, C.byref(ms)))
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = int(lib.fpm_kernel_launch_count()) - launches0
+    lib.fpm_prof_enable(0)
+    counts = (C.c_int64 * len(KCLASSES))()
+    totals = (C.c_double * len(KCLASSES))()
+    _lib.check(lib.fpm_prof_get(counts, totals, len(KCLASSES)))
+    stages = {nm: {"launches": int(counts[i]), "ms": round(float(totals[i]), 3)} for i, nm in enumerate(KCLASSES)}
+    t_evolve = ms.value / 1e3
+    value = Np * K / t_evolve
+
+    # ---- end-to-end run: host buffers in, host buffers out
+    _lib.check(lib.fpm_sync())
+    t0 = time.perf_counter()
+    restore()
+    g.evolve(ts)
+    for c in cols_out:
+        _lib.check(lib.fpm_memcpy_d2h(host[c][0], g.column_ptr(c), Np * itemsize[c]), "result d2h")
+    _lib.check(lib.fpm_sync())
+    t_e2e = time.perf_counter() - t0
+    h2d = sum(Np * itemsize[c] for c in cols_in)
+    d2h = sum(Np * itemsize[c] for c in cols_out) + K * 3 * (N // 2) * 8
+    x_final = host["x"][1]
+    finite = bool(np.isfinite(x_final[:: max(1, x_final.size // 100000)]).all())
+
+    # ---- roofline of the dominant kernel (the strided FFT tile pass: 4 of the 6 passes of every transform)
+    S = 4.0 * N * N * (N + 2)                           # bytes of one padded real mesh
+    peak, peak_src = measured_peak()
+    tile = stages["fft_tile"]
+    avg_ms = tile["ms"] / max(1, tile["launches"])
+    achieved = 2 * S / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    fftz = stages["fft_z"]
+    n_transforms = max(1, fftz["launches"])
+    t_transform_ms = (tile["ms"] + fftz["ms"]) / n_transforms
+    fft_gbs = 6 * S / (t_transform_ms * 1e-3) / 1e9 if t_transform_ms > 0 else 0.0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_evolve / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 mesh / f64 positions", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": Np * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                "seconds": round(t_e2e, 4)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "fft_tile_kernel (strided y/x FFT pass)", "achieved": round(achieved, 1), "peak": peak,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": round(avg_ms, 4)},
+        "fft": {"gbs_6S": round(fft_gbs, 1), "frac_of_peak": round(fft_gbs / peak, 4), "ms_per_transform": round(t_transform_ms, 4),
+                "transforms": n_transforms},
+        "stages": stages,
+        "evolve_wall_s": round(t_wall, 4), "result_finite": finite,
+        "pk_last_bin0": float(spectra[-1][1][0]) if spectra else None,
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = cpu_reference_run(args.ref_nc, B, args.mode, min(K, args.ref_steps), 0, threads)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
+                                    "sample": "reference sources (oracle/_ref, shimmed FFT/GSL/MPI), 1 rank x %d threads: nc=%d^3, %d^3 mesh, %s, %d steps, %.1f s" % (
+                                        threads, args.ref_nc, args.ref_nc * B, args.mode, min(K, args.ref_steps), r["seconds"])}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref not built"}
+    if rank == 0:
+        print(json.dumps(line))
+    g.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nc", type=int, default=int(os.environ.get("FASTPM_B200_BENCH_NC", "512")))
+    ap.add_argument("--pm-nc-factor", type=int, default=2)
+    ap.add_argument("--mode", default="cola", choices=["cola", "pm", "fastpm"])
+    ap.add_argument("--ref-nc", type=int, default=128, help="particle grid of the bounded CPU sample")
+    ap.add_argument("--ref-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 2:
+        args.steps = 2
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

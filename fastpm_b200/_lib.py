@@ -15,9 +15,9 @@ ABI_SYMBOLS = [
     "fpm_malloc", "fpm_free", "fpm_host_alloc_pinned", "fpm_host_free_pinned",
     "fpm_memcpy_h2d", "fpm_memcpy_d2h", "fpm_memcpy_d2d", "fpm_memset", "fpm_sync",
     "fpm_timer_create", "fpm_timer_start", "fpm_timer_stop", "fpm_timer_elapsed_ms", "fpm_timer_destroy",
-    "fpm_kernel_launch_count",
+    "fpm_kernel_launch_count", "fpm_prof_enable", "fpm_prof_reset", "fpm_prof_get",
     "fpm_mesh_create", "fpm_mesh_destroy", "fpm_mesh_info", "fpm_mesh_ktables_host",
-    "fpm_paint", "fpm_readout", "fpm_r2c", "fpm_r2c_ws", "fpm_c2r", "fpm_c2r_ws", "fpm_transfer_for_kernel",
+    "fpm_paint", "fpm_readout", "fpm_r2c", "fpm_r2c_ws", "fpm_c2r", "fpm_c2r_ws", "fpm_fft_set_generic", "fpm_transfer_for_kernel",
     "fpm_apply_transfer", "fpm_apply_decic", "fpm_scale", "fpm_divide", "fpm_muladd", "fpm_set_mode",
     "fpm_induce_correlation", "fpm_fill_whitenoise", "fpm_powerspectrum", "fpm_powerspectrum_sums",
     "fpm_kick", "fpm_drift", "fpm_wrap", "fpm_wrap_check", "fpm_summary", "fpm_fill_grid", "fpm_lpt_evolve",
@@ -67,6 +67,7 @@ def load():
     lib.fpm_timer_elapsed_ms.argtypes = [vp, C.POINTER(dbl)]
     lib.fpm_timer_destroy.argtypes = [vp]
     lib.fpm_kernel_launch_count.restype = C.c_uint64
+    lib.fpm_prof_get.argtypes = [vp, vp, i32]
     lib.fpm_mesh_create.restype = vp
     lib.fpm_mesh_create.argtypes = [i32, dbl, i32, i32]
     lib.fpm_mesh_destroy.argtypes = [vp]

@@ -10,6 +10,31 @@
 
 unsigned long long fpm_launch_counter = 0;
 
+// ------------------------------------------------------------------ per-class event timing (common.cuh)
+int fpm_prof_on = 0;
+struct ProfPair { cudaEvent_t a, b; int cls; };
+static std::vector<ProfPair> g_prof_pairs;
+static size_t g_prof_used = 0;
+static int g_prof_open = -1;
+void fpm_prof_begin(int cls, cudaStream_t st)
+{
+    if (g_prof_used == g_prof_pairs.size()) {
+        ProfPair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.cls = cls;
+        g_prof_pairs.push_back(p);
+    }
+    g_prof_pairs[g_prof_used].cls = cls;
+    cudaEventRecord(g_prof_pairs[g_prof_used].a, st);
+    g_prof_open = (int) g_prof_used;
+}
+void fpm_prof_end(int cls, cudaStream_t st)
+{
+    (void) cls;
+    if (g_prof_open < 0) return;
+    cudaEventRecord(g_prof_pairs[g_prof_open].b, st);
+    g_prof_used++;
+    g_prof_open = -1;
+}
+
 // launchers defined in the kernel files
 int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
@@ -29,6 +54,7 @@ int fpm_muladd_launch(float *source, const float *a, const float *b, size_t nflo
 int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const double *d_tp, int size, cudaStream_t st);
 int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed, cudaStream_t st);
 int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st);
+void fpm_fft_force_generic(int on);
 
 // ------------------------------------------------------------------ runtime state
 static char g_error[1024] = "";
@@ -164,6 +190,23 @@ void fpm_timer_destroy(void *timer)
     delete t;
 }
 uint64_t fpm_kernel_launch_count(void) { return fpm_launch_counter; }
+
+int fpm_prof_enable(int on) { fpm_prof_on = on; return 0; }
+int fpm_prof_reset(void) { g_prof_used = 0; g_prof_open = -1; return 0; }
+// counts[c], total_ms[c] for c < FPM_K_COUNT (paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other)
+int fpm_prof_get(int64_t *counts, double *total_ms, int ncls)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    for (int c = 0; c < ncls; c++) { counts[c] = 0; total_ms[c] = 0; }
+    for (size_t i = 0; i < g_prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g_prof_pairs[i].a, g_prof_pairs[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+        int c = g_prof_pairs[i].cls;
+        if (c >= 0 && c < ncls) { counts[c]++; total_ms[c] += ms; }
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------ mesh
 static double sinc_unnormed(double x)
@@ -333,6 +376,9 @@ int fpm_transfer_for_kernel(int kernel_type, int attr, int memb, fpm_transfer *o
     else { fpm_set_error("Unknown type for gravity attribute %d", attr); return -1; }
     return 0;
 }
+
+// 1: always use the generic shared-memory FFT passes (fft.cu); 0: TMA/register passes where supported (fft_tma.cu)
+int fpm_fft_set_generic(int on) { fpm_fft_force_generic(on); return 0; }
 
 // ------------------------------------------------------------------ k-space sweeps
 int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fpm_transfer *kernel)

@@ -31,6 +31,18 @@ extern unsigned long long fpm_launch_counter;      // kernels launched by this l
         }                                                                                    \
     } while (0)
 
+// ---------------------------------------------------------------- per-kernel-class CUDA-event timing
+// Off by default.  When enabled (fpm_prof_enable), every launch of this library is bracketed by two events on
+// the launching stream; fpm_prof_get sums the elapsed times per class.  bench.py uses it for the roofline line.
+enum FpmKernelClass {
+    FPM_K_PAINT = 0, FPM_K_READOUT, FPM_K_FFT_TILE, FPM_K_FFT_Z, FPM_K_KICK, FPM_K_DRIFT, FPM_K_KSPACE,
+    FPM_K_PK, FPM_K_SUMMARY, FPM_K_OTHER, FPM_K_COUNT
+};
+extern int fpm_prof_on;
+void fpm_prof_begin(int cls, cudaStream_t st);
+void fpm_prof_end(int cls, cudaStream_t st);
+#define FPM_TIMED(cls, st, stmt) do { if (fpm_prof_on) fpm_prof_begin(cls, st); stmt; if (fpm_prof_on) fpm_prof_end(cls, st); } while (0)
+
 // ---------------------------------------------------------------- mesh geometry
 // One PM mesh of Nmesh^3 cells over a periodic box, x-slab decomposed over `nranks` GPUs.
 //

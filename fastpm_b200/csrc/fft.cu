@@ -15,6 +15,8 @@
 #include "fft_core.h"
 #include "mesh.cuh"
 #include <vector>
+#include <stdlib.h>
+#include <string.h>
 
 // ------------------------------------------------------------------ tile pass
 struct TilePassArgs {
@@ -184,6 +186,7 @@ struct FpmFftPlan {
     float2 *d_twN = nullptr, *d_twH = nullptr;
     int *d_revN = nullptr, *d_invN = nullptr, *d_revH = nullptr, *d_invH = nullptr;
     int K, R, thr_tile, thr_z;
+    int pitch_c;
     size_t smem_tile, smem_z;
 };
 
@@ -220,6 +223,7 @@ int fpm_fft_plan_create(int n, FpmFftPlan **out)
     if (!hN.ok || !hH.ok) { fpm_set_error("Nmesh = %d has a prime factor other than 2, 3, 5", n); return -1; }
     FpmFftPlan *p = new FpmFftPlan();
     p->n = n;
+    p->pitch_c = ((n / 2 + 1 + 15) / 16) * 16;
     if (upload_plan(hN, &p->tN, &p->d_twN, &p->d_revN, &p->d_invN)) return -1;
     if (upload_plan(hH, &p->tH, &p->d_twH, &p->d_revH, &p->d_invH)) return -1;
     p->K = n <= 512 ? 16 : (n <= 2048 ? 8 : 4);
@@ -250,13 +254,29 @@ void fpm_fft_plan_destroy(FpmFftPlan *p)
     delete p;
 }
 
+int fpm_fft_tma_supported(int n);
+int fpm_fft_tma_tile_k(int n);
+int fpm_fft_tma_pass_from_tile(int n, const TilePassArgs &a, int pitch_c, int nouter, cudaStream_t st);
+
+static int g_fft_generic = -1;
+void fpm_fft_force_generic(int on) { g_fft_generic = on ? 1 : 0; }
+static int use_tma(int n)
+{
+    if (g_fft_generic < 0) { const char *e = getenv("FASTPM_B200_FFT"); g_fft_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
+    return !g_fft_generic && fpm_fft_tma_supported(n);
+}
+
 static int launch_tile(const FpmFftPlan *p, const TilePassArgs &a, int nouter, cudaStream_t st)
 {
+    if (use_tma(p->n) && a.src_estride == (size_t) p->pitch_c && a.src_ostride == (size_t) p->n * p->pitch_c)
+        return fpm_fft_tma_pass_from_tile(p->n, a, p->pitch_c, nouter, st);
     const unsigned grid = (unsigned) ((size_t) nouter * a.ntile_k);
     if (grid == 0) return 0;
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_TILE, st);
     if (p->K == 16) fft_tile_kernel<16><<<grid, p->thr_tile, p->smem_tile, st>>>(a);
     else if (p->K == 8) fft_tile_kernel<8><<<grid, p->thr_tile, p->smem_tile, st>>>(a);
     else fft_tile_kernel<4><<<grid, p->thr_tile, p->smem_tile, st>>>(a);
+    if (fpm_prof_on) fpm_prof_end(FPM_K_FFT_TILE, st);
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -265,11 +285,13 @@ static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaSt
 {
     const unsigned grid = (unsigned) ((a.nrows + p->R - 1) / p->R);
     if (grid == 0) return 0;
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_Z, st);
     if (p->R == 16) {
         if (forward) fft_zfwd_kernel<16><<<grid, p->thr_z, p->smem_z, st>>>(a); else fft_zbwd_kernel<16><<<grid, p->thr_z, p->smem_z, st>>>(a);
     } else {
         if (forward) fft_zfwd_kernel<8><<<grid, p->thr_z, p->smem_z, st>>>(a); else fft_zbwd_kernel<8><<<grid, p->thr_z, p->smem_z, st>>>(a);
     }
+    if (fpm_prof_on) fpm_prof_end(FPM_K_FFT_Z, st);
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -334,4 +356,15 @@ int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *
     ZPassArgs z; z.src = real; z.dst = real_out ? real_out : real; z.nrows = (size_t) g.nxl * n; z.pitch_c = g.pitch_c; z.scale = 1.f; z.th = p->tH; z.twN = p->d_twN;
     if (launch_z(p, z, 0, st)) return -1;
     return 0;
+}
+
+// adapter: the generic tile-pass description -> the TMA kernel's arguments (fft_tma.cu)
+#include "fft_tma_args.h"
+int fpm_fft_tma_pass_from_tile(int n, const TilePassArgs &a, int pitch_c, int nouter, cudaStream_t st)
+{
+    TmaPassArgs t;
+    for (int d = 0; d < FPM_MAX_RANKS; d++) t.dst[d] = a.dst[d];
+    t.rows_per_rank = a.rows_per_rank; t.dst_estride = a.dst_estride; t.dst_ostride = a.dst_ostride; t.dst_ooffset = a.dst_ooffset;
+    t.ntile_k = 0; t.nouter = nouter; t.conj = a.conj; t.outer0 = a.outer0; t.tw = a.t.tw; t.xfer = a.xfer; t.kt = a.kt;
+    return fpm_fft_tma_pass(n, a.src, pitch_c, nouter, t, st);
 }

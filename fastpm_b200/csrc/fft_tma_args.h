@@ -1,0 +1,19 @@
+// fastpm_b200 -- argument block of the TMA FFT tile pass (fft_tma.cu), shared with its caller (fft.cu)
+#pragma once
+#include "common.cuh"
+#include "mesh.cuh"
+
+struct TmaPassArgs {
+    float2 *dst[FPM_MAX_RANKS];
+    int rows_per_rank;
+    size_t dst_estride, dst_ostride;
+    int dst_ooffset;
+    int ntile_k, nouter;
+    int conj;
+    int outer0;
+    const float2 *tw;           // [N] exp(-2 pi i t / N)
+    FpmTransferSpec xfer;
+    FpmKTables kt;
+};
+
+int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const TmaPassArgs &args, cudaStream_t st);

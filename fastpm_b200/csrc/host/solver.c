@@ -459,3 +459,24 @@ void fastpm_b200_host_drift_factor(const double *cosmo, int growth_mode, int for
 { FastPMSolver s; host_only_solver(&s, cosmo, growth_mode, force_mode, nLPT); fastpm_b200_drift_factor(&s, ai, ac, af, out); }
 void fastpm_b200_host_growth(const double *cosmo, int growth_mode, double a, double *out)
 { FastPMSolver s; host_only_solver(&s, cosmo, growth_mode, 0, 0); fastpm_b200_growth(&s, a, out); }
+
+/* ------------------------------------------------------------------ synthetic ICs for benchmark sizes
+ * White noise from the counter-based device generator (instead of the serial RANLUX stream of
+ * pmic_fill_gaussian_gadget, initialcondition.c:145-273), coloured by the tabulated linear P(k) exactly as
+ * src/fastpm.c:415-545 does for a white-noise input (read_grafic path :448-462: real field * sqrt(Norm), r2c,
+ * induce_correlation, DC mode = 1), then 2LPT at a0.  Everything stays on the device. */
+void fastpm_b200_setup_synthetic_ic(FastPMSolver *fastpm, uint64_t seed, const double *k, const double *p, int size, double a0)
+{
+    PM *pm = fastpm->lptpm;
+    if (pm->NTask > 1) fastpm_raise(-1, "synthetic ICs on several GPUs are not wired in this build\n");
+    FastPMFloat *delta_k = pm_alloc_noclear(pm, __FILE__, __LINE__);
+    FastPMFloat *g_x = pm_alloc_noclear(pm, __FILE__, __LINE__);
+    FPM_MUST(fpm_fill_whitenoise(pm->mesh, g_x, seed));
+    FPM_MUST(fpm_r2c(pm->mesh, g_x, delta_k, sqrt(pm->Norm) / pm->Norm));
+    pm_free(pm, g_x);
+    FPM_MUST(fpm_induce_correlation(pm->mesh, delta_k, k, p, size));
+    ptrdiff_t mode[4] = { 0, 0, 0, 0 };
+    fastpm_apply_modify_mode_transfer(pm, delta_k, delta_k, mode, 1.0);
+    fastpm_solver_setup_lpt(fastpm, FASTPM_SPECIES_CDM, delta_k, NULL, a0);
+    pm_free(pm, delta_k);
+}

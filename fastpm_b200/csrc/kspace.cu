@@ -235,7 +235,7 @@ static inline size_t cplx_total(const FpmGeom &g) { return (size_t) g.nyl * g.n 
 int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st)
 {
     const size_t total = cplx_total(m->geom);
-    transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, *s, (const float2 *) from, (float2 *) to, total);
+    FPM_TIMED(FPM_K_KSPACE, st, (transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, *s, (const float2 *) from, (float2 *) to, total)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -243,7 +243,7 @@ int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const Fp
 int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st)
 {
     const size_t total = cplx_total(m->geom);
-    decic_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->d_decic, (const float2 *) from, (float2 *) to, total);
+    FPM_TIMED(FPM_K_KSPACE, st, (decic_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->d_decic, (const float2 *) from, (float2 *) to, total)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -264,28 +264,28 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
     }
     if (smem > 96 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
     const double k0 = 2 * M_PI / g.boxsize;
-    powerspectrum_kernel<<<148 * 4, 256, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, total, k0, d_out);
+    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<<<148 * 4, 256, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, total, k0, d_out)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
 int fpm_scale_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st)
 {
-    scale_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value);
+    FPM_TIMED(FPM_K_KSPACE, st, (scale_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
 int fpm_divide_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st)
 {
-    divide_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value);
+    FPM_TIMED(FPM_K_KSPACE, st, (divide_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(from, to, nfloats, value)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
 int fpm_muladd_launch(float *source, const float *a, const float *b, size_t nfloats, int sign, cudaStream_t st)
 {
-    muladd_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(source, a, b, nfloats, sign > 0 ? 1.f : -1.f);
+    FPM_TIMED(FPM_K_KSPACE, st, (muladd_kernel<<<sweep_grid(nfloats), 256, 0, st>>>(source, a, b, nfloats, sign > 0 ? 1.f : -1.f)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -295,7 +295,7 @@ int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const dou
     const FpmGeom &g = m->geom;
     const size_t total = cplx_total(g);
     const double volume = g.boxsize * g.boxsize * g.boxsize;
-    induce_kernel<<<sweep_grid(total), 256, 0, st>>>(g, m->ktab, (float2 *) dk, total, d_tk, d_tp, size, volume);
+    FPM_TIMED(FPM_K_KSPACE, st, (induce_kernel<<<sweep_grid(total), 256, 0, st>>>(g, m->ktab, (float2 *) dk, total, d_tk, d_tp, size, volume)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -304,14 +304,14 @@ int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed
 {
     const FpmGeom &g = m->geom;
     const size_t ncell = (size_t) g.nxl * g.n * g.n;
-    whitenoise_kernel<<<sweep_grid(ncell / 2), 256, 0, st>>>(g, real, seed);
+    FPM_TIMED(FPM_K_OTHER, st, (whitenoise_kernel<<<sweep_grid(ncell / 2), 256, 0, st>>>(g, real, seed)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
 int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st)
 {
-    set_mode_kernel<<<1, 1, 0, st>>>(m->geom, (float2 *) dk, ix, iy, iz, re, im);
+    FPM_TIMED(FPM_K_OTHER, st, (set_mode_kernel<<<1, 1, 0, st>>>(m->geom, (float2 *) dk, ix, iy, iz, re, im)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

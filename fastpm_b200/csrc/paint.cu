@@ -124,7 +124,7 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
-    cic_paint_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np);
+    FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -134,14 +134,14 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
-    cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np);
+    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st)
 {
-    plane_add_kernel<<<148 * 8, 256, 0, st>>>(dst, src, nfloats);
+    FPM_TIMED(FPM_K_OTHER, st, (plane_add_kernel<<<148 * 8, 256, 0, st>>>(dst, src, nfloats)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -173,7 +173,7 @@ int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const flo
 {
     if (np <= 0) return 0;
     KickArgs a = { v_out, v_in, acc, dx1, dx2, dda, q1, q2, Dv1, Dv2, cola, 3 * np };
-    kick_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_TIMED(FPM_K_KICK, st, (kick_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -183,7 +183,7 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
 {
     if (np <= 0) return 0;
     DriftArgs a = { x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, mode, 3 * np };
-    drift_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_TIMED(FPM_K_DRIFT, st, (drift_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -191,7 +191,7 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st)
 {
     if (np <= 0) return 0;
-    wrap_kernel<<<stream_grid(3 * np), 256, 0, st>>>(x, 3 * np, L, d_bad);
+    FPM_TIMED(FPM_K_OTHER, st, (wrap_kernel<<<stream_grid(3 * np), 256, 0, st>>>(x, 3 * np, L, d_bad)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -201,7 +201,7 @@ int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx
 {
     if (np <= 0) return 0;
     LptEvolveArgs a = { x, v, dx1, dx2, D1, D2, Dv1, Dv2, 3 * np };
-    lpt_evolve_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a);
+    FPM_TIMED(FPM_K_OTHER, st, (lpt_evolve_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -209,7 +209,7 @@ int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx
 int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st)
 {
     if (np <= 0) return 0;
-    fill_grid_kernel<<<stream_grid(np), 256, 0, st>>>(x, id, v, nc, i0, np, scale, shift);
+    FPM_TIMED(FPM_K_OTHER, st, (fill_grid_kernel<<<stream_grid(np), 256, 0, st>>>(x, id, v, nc, i0, np, scale, shift)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -221,8 +221,8 @@ int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, doub
     const unsigned grid = stream_grid(np);
     double *d_partial = nullptr;
     FPM_CUDA_OK(cudaMalloc(&d_partial, sizeof(double) * 4 * ncomp * grid));
-    if (dtype == 4) summary_kernel<float><<<grid, 256, 0, st>>>((const float *) col, np, ncomp, d_partial);
-    else summary_kernel<double><<<grid, 256, 0, st>>>((const double *) col, np, ncomp, d_partial);
+    if (dtype == 4) FPM_TIMED(FPM_K_SUMMARY, st, (summary_kernel<float><<<grid, 256, 0, st>>>((const float *) col, np, ncomp, d_partial)));
+    else FPM_TIMED(FPM_K_SUMMARY, st, (summary_kernel<double><<<grid, 256, 0, st>>>((const double *) col, np, ncomp, d_partial)));
     FPM_CHECK_LAUNCH();
     double *h = (double *) malloc(sizeof(double) * 4 * ncomp * grid);
     FPM_CUDA_OK(cudaMemcpyAsync(h, d_partial, sizeof(double) * 4 * ncomp * grid, cudaMemcpyDeviceToHost, st));

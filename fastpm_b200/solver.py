@@ -85,6 +85,7 @@ def _bind(lib):
     lib.fastpm_powerspectrum_init_from_delta.argtypes = [vp, vp, vp, vp]
     lib.fastpm_b200_clock_get.argtypes = [C.c_char_p, C.POINTER(dbl)]
     lib.fastpm_b200_memory_trim.argtypes = []
+    lib.fastpm_b200_setup_synthetic_ic.argtypes = [vp, C.c_uint64, vp, vp, i32, dbl]
     return lib
 
 
@@ -155,6 +156,12 @@ class Solver:
         _lib.check(self.lib.fastpm_b200_mesh_set_complex(self.lptpm, dk, arr.ctypes.data), "mesh_set_complex")
         self.lib.fastpm_solver_setup_lpt(self.h, 1, dk, None, float(a0))
         self.lib.pm_free(self.lptpm, dk)
+
+    def setup_synthetic_ic(self, seed, k, p, a0):
+        """Counter-based white noise coloured by the table P(k), then 2LPT at a0, all on the device."""
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        self.lib.fastpm_b200_setup_synthetic_ic(self.h, int(seed), k.ctypes.data, p.ctypes.data, len(k), float(a0))
 
     def setup_lpt_device(self, delta_k_dev_ptr, a0):
         self.lib.fastpm_solver_setup_lpt(self.h, 1, delta_k_dev_ptr, None, float(a0))

@@ -52,6 +52,11 @@ int fpm_timer_stop(void *timer);
 int fpm_timer_elapsed_ms(void *timer, double *ms);     /* synchronises on the stop event */
 void fpm_timer_destroy(void *timer);
 uint64_t fpm_kernel_launch_count(void);                /* kernels launched by this library so far */
+/* optional per-kernel-class timing with CUDA events on the launching stream (off by default); classes in order:
+ * paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other */
+int fpm_prof_enable(int on);
+int fpm_prof_reset(void);
+int fpm_prof_get(int64_t *counts, double *total_ms, int ncls);
 
 /* ---- mesh object: struct PM, pm_init / pm_destroy, pmpfft.c:108-342 -------------------------- */
 fpm_mesh *fpm_mesh_create(int nmesh, double boxsize, int nranks, int rank);
@@ -79,6 +84,10 @@ int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t
 int fpm_r2c(fpm_mesh *m, float *real, float *cplx, double scale);
 /* same, keeping `real` intact: the z- and y-pass intermediate goes to `work` (work != cplx; work == real allowed) */
 int fpm_r2c_ws(fpm_mesh *m, const float *real, float *work, float *cplx, double scale);
+
+/* 1: force the generic shared-memory FFT passes (any Nmesh = 2^a 3^b 5^c); 0 (default): the TMA + register passes for
+ * Nmesh in {512, 1024, 2048, 4096}.  Used by the tests to cross-check one against the other. */
+int fpm_fft_set_generic(int on);
 
 /* k-space kernel description: see FpmTransferSpec in csrc/mesh.cuh.  Fused into the first pass of c2r. */
 typedef struct {
