@@ -460,7 +460,12 @@ int fpm_wrap_check(void)
 {
     if (!h_wrap_bad) return 0;
     FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
-    if (*h_wrap_bad) { *h_wrap_bad = 0; fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)"); return -1; }
+    if (*h_wrap_bad) {
+        *h_wrap_bad = 0;
+        FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
+        fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)");
+        return -1;
+    }
     return 0;
 }
 int fpm_wrap(double *x, int64_t np, double boxsize)
@@ -472,7 +477,13 @@ int fpm_wrap(double *x, int64_t np, double boxsize)
         *h_wrap_bad = 0;
         FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
     }
-    if (*h_wrap_bad) { *h_wrap_bad = 0; fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)"); return -1; }
+    if (*h_wrap_bad) {
+        FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+        *h_wrap_bad = 0;
+        FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
+        fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)");
+        return -1;
+    }
     if (fpm_wrap_launch(x, np, boxsize, d_wrap_bad, g_stream)) return -1;
     FPM_CUDA_OK(cudaMemcpyAsync(h_wrap_bad, d_wrap_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     return 0;

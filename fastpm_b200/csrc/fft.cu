@@ -281,8 +281,14 @@ static int launch_tile(const FpmFftPlan *p, const TilePassArgs &a, int nouter, c
     return 0;
 }
 
+int fpm_fft_zrow_supported(int n, size_t nrows);
+int fpm_fft_zrow_pass(int n, const float *src, float *dst, size_t nrows, int pitch_c, float scale,
+                      const float2 *twH, const float2 *twN, int forward, cudaStream_t st);
+
 static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaStream_t st)
 {
+    if (use_tma(p->n) && fpm_fft_zrow_supported(p->n, a.nrows))
+        return fpm_fft_zrow_pass(p->n, a.src, a.dst, a.nrows, a.pitch_c, a.scale, a.th.tw, a.twN, forward, st);
     const unsigned grid = (unsigned) ((a.nrows + p->R - 1) / p->R);
     if (grid == 0) return 0;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_Z, st);

@@ -1,0 +1,209 @@
+// fastpm_b200 -- register-resident FFT building blocks shared by the TMA tile pass (fft_tma.cu) and the row
+// (z) passes (fft_zrow.cu): PTX wrappers for mbarrier / TMA, the unrolled radix-2^k register FFT, and the
+// three-stage transform of one column held E = R1 elements per thread with two shared-memory exchanges.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+// ------------------------------------------------------------------ small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ------------------------------------------------------------------ register FFT (radix-2 DIF, unrolled)
+// twiddle exp(-2 pi i idx/16), idx = 0..7, as compile-time constants
+__device__ __forceinline__ float2 w16(int idx)
+{
+    constexpr float c[8] = { 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                             0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f };
+    constexpr float s[8] = { 0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                             -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f };
+    return make_float2(c[idx], s[idx]);
+}
+
+// in-place DIF on R registers; afterwards X[q] sits in v[bitrev_R(q)]
+template <int R>
+__device__ __forceinline__ void fft_reg(float2 (&v)[R])
+{
+    #pragma unroll
+    for (int half = R / 2; half >= 1; half >>= 1) {
+        #pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * half) {
+            #pragma unroll
+            for (int j = 0; j < half; j++) {
+                const float2 a = v[blk + j], b = v[blk + j + half];
+                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
+                const float2 d = make_float2(a.x - b.x, a.y - b.y);
+                const int idx = j * (8 / half);              // exp(-2 pi i j / (2 half)) = w16(j * 16 / (2 half))
+                if (idx == 0) v[blk + j + half] = d;
+                else if (idx == 4) v[blk + j + half] = make_float2(d.y, -d.x);
+                else {
+                    const float2 w = w16(idx);
+                    v[blk + j + half] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+                }
+            }
+        }
+    }
+}
+template <int R> __device__ __forceinline__ constexpr int bitrev(int q)
+{
+    int r = 0;
+    for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (q & 1); q >>= 1; }
+    return r;
+}
+
+// ------------------------------------------------------------------ the kernel
+
+template <int R1, int R2, int R3> struct TmaCfg {
+    static constexpr int N = R1 * R2 * R3;
+    static constexpr int E = R1;               // elements per thread
+    static constexpr int T = N / E;            // threads per column
+    static constexpr int M1 = N / R1;          // = T
+    static constexpr int M2 = M1 / R2;         // = R3
+};
+template <int R> struct Log2Of { static constexpr int v = (R >= 16) ? 4 : (R >= 8 ? 3 : (R >= 4 ? 2 : (R >= 2 ? 1 : 0))); };
+
+// Exchange buffer B: floats [N][K]; physical row = row ^ ((row >> log2 R3) & MASK), MASK = 32/K - 1, keeps every
+// access pattern of the three stages on distinct banks.  Because MASK < R3 <= M1 the swizzle only ever touches
+// bits that come from a single index of each pattern, so all addresses below are "per-thread base + immediate":
+//   X1 write   rows q*M1 + t            -> q*M1 + swz(t)
+//   X1 read /  rows q1*M1 + k*M2 + p2   -> q1*M1 + k*M2 + (p2 ^ (k & MASK))
+//   X2 write
+//   X2 read    rows b*R3 + k            -> b*R3 + (k ^ (b & MASK))
+// Input: v[k] = element t + k*M1 of the column.  Output: v[i*R3 + q3] = frequency q1 + R1*q2 + R1*R2*q3 with
+// (q1, q2) = ((t + i*T) / R2, (t + i*T) % R2).
+template <int R1, int R2, int R3, int K>
+struct Fft3 {
+    using C = TmaCfg<R1, R2, R3>;
+    static constexpr int N = C::N, E = C::E, T = C::T, M1 = C::M1, M2 = C::M2;
+    static constexpr int SH = Log2Of<R3>::v;
+    static constexpr int MASK = 32 / K - 1;
+    static_assert(R3 > 1 && M2 == R3, "three-stage configurations only");
+    static_assert(MASK < R3 && (T % (MASK + 1)) == 0 && (1 << SH) * (MASK + 1) <= M1 && (T % M2) == 0, "swizzle assumptions");
+
+    float *Bx1w, *Bx2, *Bx3;
+    int pm[MASK + 1];
+    int bm, tw2i, t;
+    const float2 *tw;
+
+    __device__ __forceinline__ Fft3(float *B, int t_, int c, const float2 *tw_) : t(t_), tw(tw_)
+    {
+        Bx1w = B + (t ^ ((t >> SH) & MASK)) * K + c;                    // + q*M1*K
+        const int p2 = t % M2, q1_0 = t / M2;                           // butterfly b = t + i*T -> (q1_0 + i*T/M2, p2)
+        Bx2 = B + (q1_0 * M1) * K + c;                                  // + i*(T/M2)*M1*K + k*M2*K + pm[k & MASK]
+        #pragma unroll
+        for (int m = 0; m <= MASK; m++) pm[m] = (p2 ^ m) * K;
+        Bx3 = B + (t * R3) * K + c;                                     // + i*T*R3*K + ((k ^ bm))*K
+        bm = t & MASK;
+        tw2i = p2 * R1;                                                 // w_M1^(q p2) = tw[q*p2*R1]
+    }
+
+    template <typename Hook>
+    __device__ __forceinline__ void run(float2 (&v)[E], Hook after_first_barrier)
+    {
+        const float2 *tw1 = tw;
+        // ---- stage 1: radix R1 over rows t + k*M1; output q goes to row q*M1 + t, times w_N^(q t)
+        fft_reg<R1>(v);
+        #pragma unroll
+        for (int q = 1; q < R1; q++) {
+            const float2 w = __ldg(tw1 + q * t);
+            const float2 y = v[bitrev<R1>(q)];
+            v[bitrev<R1>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+        }
+
+        // ---- exchange 1 (B), then stage 2
+        float2 u[E];
+        #pragma unroll
+        for (int half = 0; half < 2; half++) {
+            __syncthreads();                    // B free (and, in round 0: every thread is done reading A)
+            if (half == 0) after_first_barrier();
+            #pragma unroll
+            for (int q = 0; q < R1; q++) {
+                const float2 y = v[bitrev<R1>(q)];
+                Bx1w[q * M1 * K] = half ? y.y : y.x;
+            }
+            __syncthreads();
+            #pragma unroll
+            for (int i = 0; i < E / R2; i++) {
+                #pragma unroll
+                for (int k = 0; k < R2; k++) {
+                    const float val = Bx2[i * (T / M2) * M1 * K + k * M2 * K + pm[k & MASK]];
+                    if (half) u[i * R2 + k].y = val; else u[i * R2 + k].x = val;
+                }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < E / R2; i++) {
+            float2 w2[R2];
+            #pragma unroll
+            for (int k = 0; k < R2; k++) w2[k] = u[i * R2 + k];
+            fft_reg<R2>(w2);
+            #pragma unroll
+            for (int q = 1; q < R2; q++) {
+                const float2 w = __ldg(tw + q * tw2i);
+                const float2 y = w2[bitrev<R2>(q)];
+                w2[bitrev<R2>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+            }
+            #pragma unroll
+            for (int q = 0; q < R2; q++) u[i * R2 + q] = w2[bitrev<R2>(q)];      // natural order: u[i*R2 + q2]
+        }
+
+        // ---- exchange 2, then stage 3 (radix R3, no twiddles) on butterflies b = t + i*T = q1*R2 + q2
+        #pragma unroll
+        for (int half = 0; half < 2; half++) {
+            __syncthreads();
+            #pragma unroll
+            for (int i = 0; i < E / R2; i++) {
+                #pragma unroll
+                for (int q = 0; q < R2; q++)
+                    Bx2[i * (T / M2) * M1 * K + q * M2 * K + pm[q & MASK]] = half ? u[i * R2 + q].y : u[i * R2 + q].x;
+            }
+            __syncthreads();
+            #pragma unroll
+            for (int i = 0; i < E / R3; i++) {
+                #pragma unroll
+                for (int k = 0; k < R3; k++) {
+                    // k = kh*(MASK+1) + kl: (k ^ bm) = kh*(MASK+1) + (kl ^ bm)
+                    const float val = Bx3[i * T * R3 * K + (k & ~MASK) * K + ((k & MASK) ^ bm) * K];
+                    if (half) v[i * R3 + k].y = val; else v[i * R3 + k].x = val;
+                }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < E / R3; i++) {
+            float2 w3[R3];
+            #pragma unroll
+            for (int k = 0; k < R3; k++) w3[k] = v[i * R3 + k];
+            fft_reg<R3>(w3);
+            #pragma unroll
+            for (int q = 0; q < R3; q++) v[i * R3 + q] = w3[bitrev<R3>(q)];
+        }
+
+    }
+};
