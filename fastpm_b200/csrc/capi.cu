@@ -9,6 +9,7 @@
 #include <vector>
 
 unsigned long long fpm_launch_counter = 0;
+int fpm_debug_sync = 0;
 
 // ------------------------------------------------------------------ per-class event timing (common.cuh)
 int fpm_prof_on = 0;
@@ -69,11 +70,14 @@ extern "C" void fpm_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+extern "C" int fpm_device_init(int device);
 static int ensure_init()
 {
     if (g_device >= 0) return 0;
     return fpm_device_init(0);
 }
+
+cudaStream_t fpm_internal_stream(void) { ensure_init(); return g_stream; }
 
 extern "C" {
 
@@ -99,6 +103,7 @@ int fpm_device_init(int device)
     if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
     if (!g_stream) FPM_CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_device = device;
+    { const char *e = getenv("FASTPM_B200_DEBUG_SYNC"); fpm_debug_sync = e ? atoi(e) : 0; }
     return 0;
 }
 
@@ -113,7 +118,11 @@ void *fpm_malloc(size_t bytes)
 {
     if (ensure_init()) return NULL;
     void *p = NULL;
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    // whole multiples of 2 MiB: such blocks are never sub-allocated by the driver, so a CUDA-IPC handle of the block
+    // maps exactly this block at offset 0 in a peer process (multi-GPU meshes, migration buffers, barrier flags)
+    const size_t gran = (size_t) 2 << 20;
+    const size_t rounded = ((bytes ? bytes : 1) + gran - 1) / gran * gran;
+    cudaError_t e = cudaMalloc(&p, rounded);
     if (e != cudaSuccess) { fpm_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
     return p;
 }

@@ -1,0 +1,331 @@
+// fastpm_b200 -- multi-GPU device plumbing for the x-slab decomposition (one process per GPU):
+//   * CUDA-IPC mapping of peer mesh buffers, so that the transposing FFT passes store straight into the peer that
+//     owns the destination planes (the slab all-to-all of PFFT, pmpfft.c:281-303, fused into the pass) and halo
+//     planes are pulled with plain loads over NVLink;
+//   * a cross-GPU barrier kernel on flags in peer memory (system-scope fences), stream ordered, no host sync;
+//   * one-plane mesh halos replacing the particle ghosts of pmghosts.c (support 2 needs planes [x0, x0+nxl]);
+//   * particle migration after drift (fastpm_store_decompose, store.c:486-657): classify by owner slab, pack the
+//     leavers per destination column by column, fill the holes from the tail, append what the peers packed for us.
+#include "common.cuh"
+#include "mesh.cuh"
+#include "../../include/fastpm_b200.h"
+#include <string.h>
+#include <vector>
+#include <map>
+
+cudaStream_t fpm_internal_stream(void);
+static cudaStream_t comm_stream(void) { return fpm_internal_stream(); }
+
+// ------------------------------------------------------------------ IPC
+// cudaMalloc sub-allocates small blocks out of larger ones and an IPC handle always names the WHOLE underlying
+// allocation: a pointer is therefore published as (handle of its allocation, offset inside it), and a handle is
+// opened once per process and remembered.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+extern "C" int fpm_ipc_get_handle(void *dev_ptr, void *handle64, uint64_t *offset)
+{
+    static PFN_cuMemGetAddressRange_v3020 get_range = nullptr;
+    if (!get_range) {
+        cudaDriverEntryPointQueryResult q; void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            fpm_set_error("cuMemGetAddressRange is not available from the driver"); return -1;
+        }
+        get_range = (PFN_cuMemGetAddressRange_v3020) p;
+    }
+    CUdeviceptr base = 0; size_t size = 0;
+    if (get_range(&base, &size, (CUdeviceptr) dev_ptr) != CUDA_SUCCESS) { fpm_set_error("cuMemGetAddressRange failed"); return -1; }
+    cudaIpcMemHandle_t h;
+    FPM_CUDA_OK(cudaIpcGetMemHandle(&h, (void *) base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *offset = (uint64_t) ((CUdeviceptr) dev_ptr - base);
+    return 0;
+}
+
+struct OpenedHandle { unsigned char h[64]; void *base; };
+static std::vector<OpenedHandle> g_opened;
+
+extern "C" void *fpm_ipc_open(const void *handle64, uint64_t offset)
+{
+    for (size_t i = 0; i < g_opened.size(); i++)
+        if (!memcmp(g_opened[i].h, handle64, 64)) return (unsigned char *) g_opened[i].base + offset;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = NULL;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fpm_set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
+    OpenedHandle o; memcpy(o.h, handle64, 64); o.base = p;
+    g_opened.push_back(o);
+    return (unsigned char *) p + offset;
+}
+
+// ------------------------------------------------------------------ cross-GPU barrier
+struct XBarrier {
+    int nranks, rank;
+    unsigned long long *flags;                       // [nranks] local, written by the peers
+    unsigned long long *peer_flags[FPM_MAX_RANKS];   // peer_flags[d] = rank d's flags array (mapped)
+    unsigned long long epoch;
+};
+static XBarrier g_bar = { 1, 0, NULL, { NULL }, 0 };
+
+__global__ void xbarrier_kernel(unsigned long long *const *peer_flags_dev, volatile unsigned long long *my_flags, int me, int n,
+                                unsigned long long epoch)
+{
+    const int d = threadIdx.x;
+    if (d < n) {
+        __threadfence_system();
+        // announce: my slot in rank d's array
+        volatile unsigned long long *dst = peer_flags_dev[d] + me;
+        *dst = epoch;
+        __threadfence_system();
+        while (my_flags[d] < epoch) { }
+        __threadfence_system();
+    }
+}
+
+static unsigned long long **g_peer_flags_dev = NULL;
+
+extern "C" int fpm_xbarrier_init(int nranks, int rank, void **local_flags_out)
+{
+    g_bar.nranks = nranks; g_bar.rank = rank; g_bar.epoch = 0;
+    g_bar.flags = (unsigned long long *) fpm_malloc(sizeof(unsigned long long) * FPM_MAX_RANKS);
+    if (!g_bar.flags) return -1;
+    FPM_CUDA_OK(cudaMemset(g_bar.flags, 0, sizeof(unsigned long long) * FPM_MAX_RANKS));
+    *local_flags_out = g_bar.flags;
+    return 0;
+}
+
+extern "C" int fpm_xbarrier_set_peers(void *const *peer_flag_ptrs)
+{
+    for (int d = 0; d < g_bar.nranks; d++)
+        g_bar.peer_flags[d] = (d == g_bar.rank) ? g_bar.flags : (unsigned long long *) peer_flag_ptrs[d];
+    if (!g_peer_flags_dev) FPM_CUDA_OK(cudaMalloc(&g_peer_flags_dev, sizeof(void *) * FPM_MAX_RANKS));
+    FPM_CUDA_OK(cudaMemcpy(g_peer_flags_dev, g_bar.peer_flags, sizeof(void *) * FPM_MAX_RANKS, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int fpm_xbarrier_on(cudaStream_t st)
+{
+    if (g_bar.nranks <= 1) return 0;
+    g_bar.epoch++;
+    xbarrier_kernel<<<1, 32, 0, st>>>(g_peer_flags_dev, g_bar.flags, g_bar.rank, g_bar.nranks, g_bar.epoch);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int fpm_xbarrier(void) { return fpm_xbarrier_on(comm_stream()); }
+
+static int mesh_barrier(FpmMesh *m, cudaStream_t st) { (void) m; return fpm_xbarrier_on(st); }
+
+// ------------------------------------------------------------------ distributed transforms
+// peers[d] = rank d's buffer (peers[rank] = the local one); the FFT code (fft.cu) puts a barrier before and after
+// the transposing pass through m->barrier.
+extern "C" int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale)
+{
+    m->barrier = mesh_barrier;
+    return fpm_fft_r2c(m, real, real, cplx_peers, (float) scale, comm_stream());
+}
+
+extern "C" int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel)
+{
+    m->barrier = mesh_barrier;
+    FpmTransferSpec s;
+    if (kernel && kernel->active) {
+        s.active = kernel->active; s.potorder = kernel->potorder; s.negate = kernel->negate; s.ngrad = kernel->ngrad;
+        s.graddir[0] = kernel->graddir[0]; s.graddir[1] = kernel->graddir[1]; s.gradorder = kernel->gradorder;
+        s.zero_selfconj = kernel->zero_selfconj; s.scale = kernel->scale;
+        return fpm_fft_c2r(m, cplx, real_peers, NULL, &s, comm_stream());
+    }
+    return fpm_fft_c2r(m, cplx, real_peers, NULL, NULL, comm_stream());
+}
+
+// ------------------------------------------------------------------ halo planes
+__global__ void __launch_bounds__(256) halo_add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t n4)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    float4 *d = reinterpret_cast<float4 *>(dst);
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    for (; i < n4; i += stride) {
+        float4 a = d[i]; const float4 b = s[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        d[i] = a;
+    }
+}
+
+// paint epilogue: my plane 0 += the halo plane (index nxl) of the previous rank.  Barriers on both sides: every rank
+// has finished painting before anybody pulls, and everybody has pulled before the canvas is written again.
+extern "C" int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank)
+{
+    const FpmGeom &g = m->geom;
+    const size_t plane = (size_t) g.n * g.pitch_r;
+    cudaStream_t st = comm_stream();
+    if (fpm_xbarrier_on(st)) return -1;
+    halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local, canvas_prev_rank + (size_t) g.nxl * plane, plane / 4);
+    FPM_CHECK_LAUNCH();
+    if (fpm_xbarrier_on(st)) return -1;
+    return 0;
+}
+
+// readout prologue: my halo plane (index nxl) = plane 0 of the next rank
+extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank)
+{
+    const FpmGeom &g = m->geom;
+    const size_t plane = (size_t) g.n * g.pitch_r;
+    cudaStream_t st = comm_stream();
+    if (fpm_xbarrier_on(st)) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(canvas_local + (size_t) g.nxl * plane, canvas_next_rank, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ particle migration
+// owner slab of a position: floor(x * inv_cell) mod N, divided by the slab thickness (pm_pos_to_rank, pmpfft.c:344-368)
+__global__ void __launch_bounds__(256) classify_kernel(const FpmGeom g, const double *__restrict__ x, long long np,
+        int *__restrict__ send_count, int *__restrict__ send_idx, int cap, unsigned char *__restrict__ leaver, int *__restrict__ overflow)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < np; i += stride) {
+        int ix = (int) floor(x[3 * i] * g.inv_cellsize);
+        ix %= g.n; if (ix < 0) ix += g.n;
+        const int dest = ix / g.nxl;
+        unsigned char lv = 0;
+        if (dest != g.rank) {
+            const int slot = atomicAdd(&send_count[dest], 1);
+            if (slot < cap) { send_idx[(size_t) dest * cap + slot] = (int) i; lv = 1; }
+            else atomicExch(overflow, 1);
+        }
+        leaver[i] = lv;
+    }
+}
+
+// pack[dest][slot] = col[send_idx[dest][slot]] for one column of `elsize`-byte elements (elsize multiple of 4)
+__global__ void __launch_bounds__(256) pack_kernel(const int *__restrict__ send_idx, int count, const unsigned int *__restrict__ col,
+        unsigned int *__restrict__ pack, int words)
+{
+    long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long) count * words, stride = (long long) gridDim.x * blockDim.x;
+    for (; w < total; w += stride) {
+        const int s = (int) (w / words), k = (int) (w - (long long) s * words);
+        pack[w] = col[(size_t) send_idx[s] * words + k];
+    }
+}
+
+// holes: leavers among the first np_stay slots; movers: stayers beyond np_stay.  Equal in number.
+__global__ void __launch_bounds__(256) holes_kernel(const unsigned char *__restrict__ leaver, long long np, long long np_stay,
+        int *__restrict__ holes, int *__restrict__ movers, int *__restrict__ counters)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < np; i += stride) {
+        if (i < np_stay) { if (leaver[i]) holes[atomicAdd(&counters[0], 1)] = (int) i; }
+        else { if (!leaver[i]) movers[atomicAdd(&counters[1], 1)] = (int) i; }
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const int *__restrict__ holes, const int *__restrict__ movers, int count,
+        unsigned int *__restrict__ col, int words)
+{
+    long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long) count * words, stride = (long long) gridDim.x * blockDim.x;
+    for (; w < total; w += stride) {
+        const int s = (int) (w / words), k = (int) (w - (long long) s * words);
+        col[(size_t) holes[s] * words + k] = col[(size_t) movers[s] * words + k];
+    }
+}
+
+struct Migrate {
+    int cap;                 // per-destination capacity (particles)
+    int *d_send_count, *d_send_idx, *d_overflow, *d_holes, *d_movers, *d_counters;
+    unsigned char *d_leaver; long long leaver_cap;
+    unsigned char *d_pack;   // [nranks][cap][row bytes of all migrating columns]
+    size_t pack_bytes_per_dest;
+};
+static Migrate g_mig = { 0 };
+
+extern "C" int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void **pack_out)
+{
+    g_mig.cap = cap;
+    g_mig.leaver_cap = np_upper;
+    g_mig.pack_bytes_per_dest = (size_t) cap * row_bytes;
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_send_count, sizeof(int) * FPM_MAX_RANKS));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_send_idx, sizeof(int) * (size_t) nranks * cap));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_overflow, sizeof(int)));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_holes, sizeof(int) * (size_t) nranks * cap));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_movers, sizeof(int) * (size_t) nranks * cap));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_counters, sizeof(int) * 2));
+    FPM_CUDA_OK(cudaMalloc(&g_mig.d_leaver, (size_t) np_upper));
+    g_mig.d_pack = (unsigned char *) fpm_malloc(g_mig.pack_bytes_per_dest * nranks);
+    if (!g_mig.d_pack) return -1;
+    *pack_out = g_mig.d_pack;
+    return 0;
+}
+
+// step 1: classify; returns the per-destination counts on the host (synchronises the stream)
+extern "C" int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t np, int *send_count_host)
+{
+    cudaStream_t st = comm_stream();
+    const int G = m->geom.nranks;
+    FPM_CUDA_OK(cudaMemsetAsync(g_mig.d_send_count, 0, sizeof(int) * FPM_MAX_RANKS, st));
+    FPM_CUDA_OK(cudaMemsetAsync(g_mig.d_overflow, 0, sizeof(int), st));
+    if (np > g_mig.leaver_cap) { fpm_set_error("migrate: np exceeds the allocated particle capacity"); return -1; }
+    if (np > 0) {
+        classify_kernel<<<148 * 8, 256, 0, st>>>(m->geom, x, np, g_mig.d_send_count, g_mig.d_send_idx, g_mig.cap, g_mig.d_leaver, g_mig.d_overflow);
+        FPM_CHECK_LAUNCH();
+    }
+    int tmp[FPM_MAX_RANKS + 1];
+    FPM_CUDA_OK(cudaMemcpyAsync(tmp, g_mig.d_send_count, sizeof(int) * FPM_MAX_RANKS, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaMemcpyAsync(tmp + FPM_MAX_RANKS, g_mig.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    if (tmp[FPM_MAX_RANKS]) { fpm_set_error("migrate: more than %d particles leave for one slab in a single step (Out of particle storage space, store.c:583)", g_mig.cap); return -1; }
+    for (int d = 0; d < G; d++) send_count_host[d] = tmp[d];
+    return 0;
+}
+
+// step 2: pack one column for every destination: pack region of dest d, column offset `col_off` (bytes per particle before it)
+extern "C" int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes)
+{
+    cudaStream_t st = comm_stream();
+    const int G = m->geom.nranks, words = elsize / 4;
+    for (int d = 0; d < G; d++) {
+        const int cnt = send_count_host[d];
+        if (d == m->geom.rank || cnt == 0) continue;
+        unsigned char *dst = g_mig.d_pack + (size_t) d * g_mig.pack_bytes_per_dest + col_off_bytes * g_mig.cap;
+        pack_kernel<<<64, 256, 0, st>>>(g_mig.d_send_idx + (size_t) d * g_mig.cap, cnt, (const unsigned int *) col, (unsigned int *) dst, words);
+        FPM_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// step 3: find holes and movers (once), then fill one column at a time
+extern "C" int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host)
+{
+    cudaStream_t st = comm_stream();
+    FPM_CUDA_OK(cudaMemsetAsync(g_mig.d_counters, 0, sizeof(int) * 2, st));
+    if (np > 0) {
+        holes_kernel<<<148 * 8, 256, 0, st>>>(g_mig.d_leaver, np, np_stay, g_mig.d_holes, g_mig.d_movers, g_mig.d_counters);
+        FPM_CHECK_LAUNCH();
+    }
+    int c[2];
+    FPM_CUDA_OK(cudaMemcpyAsync(c, g_mig.d_counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    if (c[0] != c[1]) { fpm_set_error("migrate: %d holes but %d movers", c[0], c[1]); return -1; }
+    *nholes_host = c[0];
+    return 0;
+}
+
+extern "C" int fpm_migrate_fill_column(void *col, int elsize, int nholes)
+{
+    if (nholes <= 0) return 0;
+    fill_kernel<<<64, 256, 0, comm_stream()>>>(g_mig.d_holes, g_mig.d_movers, nholes, (unsigned int *) col, elsize / 4);
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// step 4: append what rank `src_rank` packed for me: `count` elements of this column from its pack region
+extern "C" int fpm_migrate_append_column(void *col, int elsize, int64_t at, const void *peer_pack_base, int my_rank, int count, size_t col_off_bytes)
+{
+    if (count <= 0) return 0;
+    const unsigned char *src = (const unsigned char *) peer_pack_base + (size_t) my_rank * g_mig.pack_bytes_per_dest + col_off_bytes * g_mig.cap;
+    FPM_CUDA_OK(cudaMemcpyAsync((unsigned char *) col + (size_t) at * elsize, src, (size_t) count * elsize, cudaMemcpyDeviceToDevice, comm_stream()));
+    return 0;
+}

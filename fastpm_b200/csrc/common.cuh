@@ -21,10 +21,12 @@ extern unsigned long long fpm_launch_counter;      // kernels launched by this l
         }                                                                                    \
     } while (0)
 
+extern int fpm_debug_sync;                          // FASTPM_B200_DEBUG_SYNC=1: synchronise after every launch (fault isolation)
 #define FPM_CHECK_LAUNCH()                                                                   \
     do {                                                                                     \
         fpm_launch_counter++;                                                                \
         cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e == cudaSuccess && fpm_debug_sync) _e = cudaDeviceSynchronize();               \
         if (_e != cudaSuccess) {                                                             \
             fpm_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
             return -1;                                                                       \

@@ -316,6 +316,8 @@ int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cpl
     ZPassArgs z; z.src = real_in; z.dst = work; z.nrows = (size_t) g.nxl * n; z.pitch_c = g.pitch_c; z.scale = scale; z.th = p->tH; z.twN = p->d_twN;
     if (launch_z(p, z, 1, st)) return -1;
     float *real = work;
+    // several GPUs: nobody may still be reading the k-space buffers the next pass stores into
+    if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // F2: outer = local x plane, rows = y; destination [ky][x][kz]
     TilePassArgs a = {};
     a.src = reinterpret_cast<const float2 *>(real); a.src_estride = g.pitch_c; a.src_ostride = plane;
@@ -349,6 +351,7 @@ int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.y0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 1; a.outer0 = g.y0; a.t = p->tN; a.kt = m->ktab;
     if (xfer) a.xfer = *xfer; else a.xfer.active = 0;
+    if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     if (launch_tile(p, a, g.nyl, st)) return -1;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // B2: in place, outer = local x plane, rows = ky

@@ -1,49 +1,281 @@
-/* fastpm_b200 host layer -- communicator table standing in for MPI_Comm (one process per GPU).
- * Rank 0 / size 1 unless fastpm_b200_comm_init() joined the process to an x-slab decomposition; the
- * multi-GPU exchanges (FFT transpose through peer memory, halo planes, particle migration) are filled in
- * by the distributed build (see DESIGN.md section "multi-GPU"). */
+/* fastpm_b200 host layer -- the communicator standing in for MPI_Comm: one process per GPU, x-slab decomposition.
+ *
+ * Host scalars (counts, sums, P(k) bins) travel through two callbacks supplied by the launcher -- all-reduce and
+ * all-gather on host buffers, which bench.py / the tests implement with torch.distributed (gloo or NCCL).  Mesh and
+ * particle data never touch the host: peers' buffers are mapped with CUDA IPC and the kernels read / write them over
+ * NVLink (csrc/comm.cu).  This file keeps the registry of mapped buffers and sequences the exchanges:
+ *   fpm_dist_r2c / fpm_dist_c2r   the slab transforms, their transposing pass storing into the owner of each plane
+ *   fpm_halo_add / fpm_halo_fetch one mesh plane to / from the x-neighbour (replaces pm_ghosts_*, pmghosts.c:112-307)
+ *   fastpm_store_decompose        particle migration (store.c:486-657) for FastPMTargetPM
+ */
 #include "internal.h"
 
+typedef void (*fpm_host_allreduce_fn)(void *buf, int count, int is_int64, int op, void *userdata);
+typedef void (*fpm_host_allgather_fn)(const void *send, int nbytes, void *recv, void *userdata);
+
+/* device side, csrc/comm.cu */
+int fpm_ipc_get_handle(void *dev_ptr, void *handle64, uint64_t *offset);
+void *fpm_ipc_open(const void *handle64, uint64_t offset);
+int fpm_xbarrier_init(int nranks, int rank, void **local_flags_out);
+int fpm_xbarrier_set_peers(void *const *peer_flag_ptrs);
+int fpm_xbarrier(void);
+int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale);
+int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel);
+int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
+int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank);
+int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void **pack_out);
+int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t np, int *send_count_host);
+int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes);
+int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host);
+int fpm_migrate_fill_column(void *col, int elsize, int nholes);
+int fpm_migrate_append_column(void *col, int elsize, int64_t at, const void *peer_pack_base, int my_rank, int count, size_t col_off_bytes);
+
+#define MAXR 8
 static int g_rank = 0, g_size = 1;
+static fpm_host_allreduce_fn g_allreduce = NULL;
+static fpm_host_allgather_fn g_allgather = NULL;
+static void *g_cb_data = NULL;
 
 int fpm_comm_rank(MPI_Comm comm) { (void) comm; return g_rank; }
 int fpm_comm_size(MPI_Comm comm) { (void) comm; return g_size; }
-
-typedef void (*fpm_host_allreduce_fn)(void *buf, int count, int is_int64, int op, void *userdata);
-static fpm_host_allreduce_fn g_allreduce = NULL;
-static void *g_allreduce_data = NULL;
-
-/* the launcher (bench.py under torchrun) installs the host all-reduce it already has (torch.distributed) */
-void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, void *userdata)
-{
-    g_rank = rank; g_size = size; g_allreduce = allreduce; g_allreduce_data = userdata;
-}
 
 void fpm_comm_allreduce_double(MPI_Comm comm, double *v, int n, int op)
 {
     (void) comm;
     if (g_size == 1) return;
     if (!g_allreduce) fastpm_raise(-1, "multi-rank run without an all-reduce callback\n");
-    g_allreduce(v, n, 0, op, g_allreduce_data);
+    g_allreduce(v, n, 0, op, g_cb_data);
 }
 void fpm_comm_allreduce_i64(MPI_Comm comm, int64_t *v, int n, int op)
 {
     (void) comm;
     if (g_size == 1) return;
     if (!g_allreduce) fastpm_raise(-1, "multi-rank run without an all-reduce callback\n");
-    g_allreduce(v, n, 1, op, g_allreduce_data);
+    g_allreduce(v, n, 1, op, g_cb_data);
 }
 void fpm_comm_barrier(MPI_Comm comm) { int64_t z = 0; fpm_comm_allreduce_i64(comm, &z, 1, 0); }
 
-void fpm_halo_add(PM *pm, FastPMFloat *canvas) { (void) pm; (void) canvas; fastpm_raise(-1, "multi-GPU halo exchange is not wired in this build\n"); }
-void fpm_halo_fetch(PM *pm, FastPMFloat *canvas) { (void) pm; (void) canvas; fastpm_raise(-1, "multi-GPU halo exchange is not wired in this build\n"); }
-void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale) { (void) pm; (void) real; (void) cplx; (void) scale; fastpm_raise(-1, "multi-GPU FFT is not wired in this build\n"); }
-void fpm_dist_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel) { (void) pm; (void) cplx; (void) real; (void) kernel; fastpm_raise(-1, "multi-GPU FFT is not wired in this build\n"); }
+static void allgather(const void *send, int nbytes, void *recv)
+{
+    if (g_size == 1) { memcpy(recv, send, nbytes); return; }
+    if (!g_allgather) fastpm_raise(-1, "multi-rank run without an all-gather callback\n");
+    g_allgather(send, nbytes, recv, g_cb_data);
+}
+
+/* ------------------------------------------------------------------ registry of peer mappings
+ * opened[r] remembers every (remote address -> local mapping) of rank r that was opened with CUDA IPC. */
+typedef struct { uint64_t remote; void *mapped; } Mapping;
+static Mapping *opened[MAXR];
+static int n_opened[MAXR];
+
+/* Collective: returns, for the local device pointer `local` (the start of an fpm_malloc block), the addresses under
+ * which every rank's corresponding block is reachable from this GPU.  One 8-byte all-gather per call; IPC handles are
+ * exchanged only when some rank presents a block that has not been mapped before. */
+static void peers_of(void *local, void *peers[MAXR])
+{
+    uint64_t mine = (uint64_t) (uintptr_t) local, all[MAXR];
+    allgather(&mine, 8, all);
+    int need = 0;
+    for (int r = 0; r < g_size; r++) {
+        peers[r] = NULL;
+        if (r == g_rank) { peers[r] = local; continue; }
+        for (int i = 0; i < n_opened[r]; i++) if (opened[r][i].remote == all[r]) peers[r] = opened[r][i].mapped;
+        if (!peers[r]) need = 1;
+    }
+    /* whether anyone needs a handle is a global decision: every rank must take part in the second gather */
+    int64_t any = need;
+    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &any, 1, 2);
+    if (!any) return;
+    unsigned char h[72], hall[MAXR * 72];
+    uint64_t off = 0;
+    if (fpm_ipc_get_handle(local, h, &off) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    memcpy(h + 64, &off, 8);
+    allgather(h, 72, hall);
+    for (int r = 0; r < g_size; r++) {
+        if (r == g_rank || peers[r]) continue;
+        uint64_t roff; memcpy(&roff, hall + 72 * r + 64, 8);
+        void *m = fpm_ipc_open(hall + 72 * r, roff);
+        if (!m) fastpm_raise(-1, "mapping rank %d's buffer: %s\n", r, fpm_last_error());
+        opened[r] = realloc(opened[r], sizeof(Mapping) * (n_opened[r] + 1));
+        opened[r][n_opened[r]].remote = all[r];
+        opened[r][n_opened[r]].mapped = m;
+        n_opened[r]++;
+        peers[r] = m;
+    }
+}
+
+/* ------------------------------------------------------------------ set-up by the launcher */
+void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
+{
+    libfastpm_init();
+    if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
+    g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
+    if (size == 1) return;
+    void *flags = NULL, *peers[MAXR];
+    if (fpm_xbarrier_init(size, rank, &flags) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    peers_of(flags, peers);
+    if (fpm_xbarrier_set_peers(peers) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    fpm_comm_barrier(MPI_COMM_WORLD);
+}
+
+/* ------------------------------------------------------------------ mesh exchanges */
+void fpm_halo_add(PM *pm, FastPMFloat *canvas)
+{
+    void *peers[MAXR];
+    peers_of(canvas, peers);
+    FPM_MUST(fpm_halo_add_from(pm->mesh, canvas, peers[(g_rank - 1 + g_size) % g_size]));
+}
+
+void fpm_halo_fetch(PM *pm, FastPMFloat *canvas)
+{
+    void *peers[MAXR];
+    peers_of(canvas, peers);
+    FPM_MUST(fpm_halo_fetch_from(pm->mesh, canvas, peers[(g_rank + 1) % g_size]));
+}
+
+void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale)
+{
+    void *peers[MAXR];
+    if (real == cplx) fastpm_raise(-1, "distributed r2c is out of place\n");
+    peers_of(cplx, peers);
+    FPM_MUST(fpm_r2c_dist(pm->mesh, real, (float *const *) peers, scale));
+}
+
+void fpm_dist_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel)
+{
+    void *peers[MAXR];
+    if (real == cplx) fastpm_raise(-1, "distributed c2r is out of place\n");
+    peers_of(real, peers);
+    FPM_MUST(fpm_c2r_dist(pm->mesh, cplx, (float *const *) peers, kernel));
+}
+
+/* the calls the force / IC code uses: one rank or many */
+void fpm_mesh_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale)
+{
+    if (pm->NTask > 1) fpm_dist_r2c(pm, real, cplx, scale);
+    else FPM_MUST(fpm_r2c(pm->mesh, real, cplx, scale));
+}
+void fpm_mesh_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel)
+{
+    if (pm->NTask > 1) fpm_dist_c2r(pm, cplx, real, kernel);
+    else FPM_MUST(fpm_c2r(pm->mesh, cplx, real, kernel));
+}
+/* gather from a real field that was just transformed: the +1 plane comes from the x-neighbour */
+void fpm_mesh_readout(PM *pm, FastPMFloat *canvas, const double *x, int64_t np, float *out, int stride, double prescale)
+{
+    if (pm->NTask > 1) fpm_halo_fetch(pm, canvas);
+    FPM_MUST(fpm_readout(pm->mesh, canvas, x, np, out, stride, prescale));
+}
+
+/* ------------------------------------------------------------------ particle migration */
+static void *pack_local = NULL, *pack_peers[MAXR];
+static int mig_cap = 0;
+static size_t mig_row_bytes = 0;
+
+typedef struct { void *ptr; int elsize; } MigCol;
+
+static int migrating_columns(FastPMStore *p, MigCol *cols)
+{
+    /* every allocated column except acc (recomputed by the force that follows), in column order */
+    int n = 0;
+    for (int ci = 0; ci < 32; ci++) {
+        if (!p->columns[ci]) continue;
+        if (p->_column_info[ci].attribute == COLUMN_ACC) continue;
+        if (p->_column_info[ci].elsize % 4 != 0) fastpm_raise(-1, "column %s cannot migrate (element size %zu)\n", p->_column_info[ci].name, p->_column_info[ci].elsize);
+        cols[n].ptr = p->columns[ci]; cols[n].elsize = (int) p->_column_info[ci].elsize; n++;
+    }
+    return n;
+}
 
 int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func, void *data, MPI_Comm comm)
 {
-    (void) p; (void) target_func; (void) data;
-    if (fpm_comm_size(comm) == 1) return 0;            /* one slab owns every particle */
-    fastpm_raise(-1, "multi-GPU particle migration is not wired in this build\n");
-    return -1;
+    (void) comm;
+    if (g_size == 1) return 0;                            /* one slab owns every particle */
+    if (target_func != (fastpm_store_target_func) FastPMTargetPM)
+        fastpm_raise(-1, "fastpm_b200: fastpm_store_decompose supports the PM target (x-slabs) only\n");
+    PM *pm = data;
+    MigCol cols[32];
+    const int ncol = migrating_columns(p, cols);
+    size_t row = 0;
+    for (int j = 0; j < ncol; j++) row += cols[j].elsize;
+    if (!pack_local) {
+        double frac = 0.08;
+        const char *e = getenv("FASTPM_B200_MIGRATE_FRAC");
+        if (e) frac = atof(e);
+        mig_cap = (int) (frac * p->np_upper);
+        if (mig_cap < 4096) mig_cap = 4096;
+        if ((size_t) mig_cap > p->np_upper) mig_cap = (int) p->np_upper;
+        mig_row_bytes = row;
+        if (fpm_migrate_init(g_size, mig_cap, (long long) p->np_upper, row, &pack_local) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        peers_of(pack_local, pack_peers);
+    }
+    if (row != mig_row_bytes) fastpm_raise(-1, "fastpm_b200: the set of particle columns changed between decompositions\n");
+
+    int send[MAXR], all[MAXR * MAXR];
+    memset(send, 0, sizeof(send));
+    if (fpm_migrate_classify(pm->mesh, (const double *) p->x, (int64_t) p->np, send) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    allgather(send, sizeof(int) * MAXR, all);
+    int64_t nsend = 0, nrecv = 0;
+    for (int r = 0; r < g_size; r++) { if (r != g_rank) { nsend += send[r]; nrecv += all[r * MAXR + g_rank]; } }
+    const int64_t np_stay = (int64_t) p->np - nsend;
+    int64_t over = (np_stay + nrecv > (int64_t) p->np_upper) ? 1 : 0;
+    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &over, 1, 2);
+    if (over) return -1;                                   /* "Out of particle storage space", solver.c:585-590 */
+
+    size_t off = 0;
+    for (int j = 0; j < ncol; j++) {
+        FPM_MUST(fpm_migrate_pack_column(pm->mesh, cols[j].ptr, cols[j].elsize, send, off));
+        off += cols[j].elsize;
+    }
+    int nholes = 0;
+    if (fpm_migrate_holes((int64_t) p->np, np_stay, &nholes) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    for (int j = 0; j < ncol; j++) FPM_MUST(fpm_migrate_fill_column(cols[j].ptr, cols[j].elsize, nholes));
+    FPM_MUST(fpm_xbarrier());                              /* every rank has packed */
+    int64_t at = np_stay;
+    for (int r = 0; r < g_size; r++) {
+        if (r == g_rank) continue;
+        const int cnt = all[r * MAXR + g_rank];
+        off = 0;
+        for (int j = 0; j < ncol; j++) {
+            FPM_MUST(fpm_migrate_append_column(cols[j].ptr, cols[j].elsize, at, pack_peers[r], g_rank, cnt, off));
+            off += cols[j].elsize;
+        }
+        at += cnt;
+    }
+    FPM_MUST(fpm_xbarrier());                              /* every rank has pulled: pack buffers may be reused */
+    p->np = (size_t) at;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ host-only self test of the callback plumbing
+ * (no device: used by the world_size-2 gloo test on CPU).  Returns 0 when the collectives behave as the host layer
+ * assumes: sum / min / max all-reduce on doubles and int64, rank-ordered all-gather of fixed-size records. */
+int fastpm_b200_comm_selftest(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
+{
+    int save_rank = g_rank, save_size = g_size;
+    fpm_host_allreduce_fn sa = g_allreduce; fpm_host_allgather_fn sg = g_allgather; void *sd = g_cb_data;
+    g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
+    int bad = 0;
+    double v[3] = { rank + 1.0, rank + 1.0, rank + 1.0 };
+    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[0], 1, 0);
+    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[1], 1, 1);
+    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[2], 1, 2);
+    if (v[0] != size * (size + 1) / 2.0 || v[1] != 1.0 || v[2] != (double) size) bad |= 1;
+    int64_t n = 1000 + rank;
+    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &n, 1, 0);
+    if (n != 1000 * (int64_t) size + size * (size - 1) / 2) bad |= 2;
+    uint64_t mine = 0xabc00000ull + rank, all[MAXR];
+    allgather(&mine, 8, all);
+    for (int r = 0; r < size; r++) if (all[r] != 0xabc00000ull + r) bad |= 4;
+    /* the slab owner rule used by the migration kernel (pm_pos_to_rank, pmpfft.c:344-368) */
+    g_rank = save_rank; g_size = save_size; g_allreduce = sa; g_allgather = sg; g_cb_data = sd;
+    return bad;
+}
+
+/* owner slab of an x coordinate for an Nmesh-cell box split over `size` slabs (host restatement for tests) */
+int fastpm_b200_slab_owner(double x, double boxsize, int nmesh, int size)
+{
+    int ix = (int) floor(x * (1.0 / (boxsize / nmesh)));
+    ix %= nmesh; if (ix < 0) ix += nmesh;
+    return ix / (nmesh / size);
 }

@@ -32,10 +32,6 @@ void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *d
     FPM_MUST(fpm_apply_transfer(pm->mesh, delta_k, canvas, &t));
 }
 
-extern void fpm_halo_add(PM *pm, FastPMFloat *canvas);        /* comm.c */
-extern void fpm_halo_fetch(PM *pm, FastPMFloat *canvas);
-extern void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale);
-extern void fpm_dist_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel);
 
 void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, FastPMSofteningType dealias,
                                  FastPMKernelType kernel, FastPMFloat *delta_k, double Time)
@@ -79,8 +75,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     ENTER(r2c);
     /* canvas * (1/mean) (gravity.c:345) and the 1/Norm of pm_r2c (pmpfft.c:382) as one factor on the FFT input */
     const double scale = (1.0 / mean_mass_per_cell) * (1.0 / pm->Norm);
-    if (pm->NTask > 1) fpm_dist_r2c(pm, canvas, delta_k, scale);
-    else FPM_MUST(fpm_r2c(pm->mesh, canvas, delta_k, scale));
+    fpm_mesh_r2c(pm, canvas, delta_k, scale);
     LEAVE(r2c);
 
     /* ---- force components: gravity.c:359-396 */
@@ -90,8 +85,8 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         fpm_transfer t;
         if (fpm_transfer_for_kernel((int) kernel, d < 3 ? 0 : 1, d < 3 ? d : 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
         ENTER(c2r);
-        if (pm->NTask > 1) { fpm_dist_c2r(pm, delta_k, canvas, &t); fpm_halo_fetch(pm, canvas); }
-        else FPM_MUST(fpm_c2r(pm->mesh, delta_k, canvas, &t));
+        fpm_mesh_c2r(pm, delta_k, canvas, &t);
+        if (pm->NTask > 1) fpm_halo_fetch(pm, canvas);
         LEAVE(c2r);
         ENTER(readout);
         for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {

@@ -52,6 +52,13 @@ void fpm_comm_allreduce_double(MPI_Comm comm, double *v, int n, int op);   /* op
 void fpm_comm_allreduce_i64(MPI_Comm comm, int64_t *v, int n, int op);
 void fpm_comm_barrier(MPI_Comm comm);
 
+/* comm.c: mesh exchanges for one rank or many */
+void fpm_halo_add(PM *pm, FastPMFloat *canvas);
+void fpm_halo_fetch(PM *pm, FastPMFloat *canvas);
+void fpm_mesh_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale);
+void fpm_mesh_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel);
+void fpm_mesh_readout(PM *pm, FastPMFloat *canvas, const double *x, int64_t np, float *out, int stride, double prescale);
+
 /* numerics.c */
 typedef double (*fpm_func1)(double x, void *params);
 double fpm_integrate(fpm_func1 f, void *params, double a, double b, double epsabs, double epsrel, int order);

@@ -200,7 +200,7 @@ void pm_check_values(PM *pm, FastPMFloat *field, const char *fmt, ...)
 }
 
 /* ------------------------------------------------------------------ host mirrors in the reference's layouts */
-size_t fastpm_b200_mesh_host_size(PM *pm) { return (size_t) pm->nxl * pm->Nmesh[1] * (pm->Nmesh[2] + 2); }
+size_t fastpm_b200_mesh_host_size(PM *pm) { return (size_t) pm->Nmesh[0] * pm->Nmesh[1] * (pm->Nmesh[2] + 2); }
 
 int fastpm_b200_mesh_get_real(PM *pm, const FastPMFloat *dev, float *host_dst)
 {
@@ -223,28 +223,27 @@ int fastpm_b200_mesh_set_real(PM *pm, FastPMFloat *dev, const float *host_src)
     free(tmp);
     return rc;
 }
-/* k-space: device [ky_local][kx][pitch_c]  <->  host [kx][ky][N/2+1] (single rank: the full untransposed array) */
+/* k-space: device [ky_local][kx][pitch_c]  <->  host [kx][ky][N/2+1] (the full untransposed array; on several ranks
+ * every rank passes / receives the full host array and touches only its own ky planes) */
 int fastpm_b200_mesh_get_complex(PM *pm, const FastPMFloat *dev, float *host_dst)
 {
-    if (pm->NTask != 1) { fastpm_raise(-1, "host k-space mirrors are single-rank in this build\n"); return -1; }
-    const size_t n = pm->Nmesh[0], hc = n / 2 + 1, pc = pm->pitch_c;
-    float *tmp = malloc(sizeof(float) * 2 * n * n * pc);
-    if (fpm_memcpy_d2h(tmp, dev, sizeof(float) * 2 * n * n * pc)) { free(tmp); return -1; }
-    for (size_t ky = 0; ky < n; ky++)
+    const size_t n = pm->Nmesh[0], hc = n / 2 + 1, pc = pm->pitch_c, nyl = pm->nyl, y0 = pm->y0;
+    float *tmp = malloc(sizeof(float) * 2 * nyl * n * pc);
+    if (fpm_memcpy_d2h(tmp, dev, sizeof(float) * 2 * nyl * n * pc)) { free(tmp); return -1; }
+    for (size_t kyl = 0; kyl < nyl; kyl++)
         for (size_t kx = 0; kx < n; kx++)
-            memcpy(host_dst + 2 * ((kx * n + ky) * hc), tmp + 2 * ((ky * n + kx) * pc), sizeof(float) * 2 * hc);
+            memcpy(host_dst + 2 * ((kx * n + kyl + y0) * hc), tmp + 2 * ((kyl * n + kx) * pc), sizeof(float) * 2 * hc);
     free(tmp);
     return 0;
 }
 int fastpm_b200_mesh_set_complex(PM *pm, FastPMFloat *dev, const float *host_src)
 {
-    if (pm->NTask != 1) { fastpm_raise(-1, "host k-space mirrors are single-rank in this build\n"); return -1; }
-    const size_t n = pm->Nmesh[0], hc = n / 2 + 1, pc = pm->pitch_c;
-    float *tmp = calloc(2 * n * n * pc, sizeof(float));
-    for (size_t ky = 0; ky < n; ky++)
+    const size_t n = pm->Nmesh[0], hc = n / 2 + 1, pc = pm->pitch_c, nyl = pm->nyl, y0 = pm->y0;
+    float *tmp = calloc(2 * nyl * n * pc, sizeof(float));
+    for (size_t kyl = 0; kyl < nyl; kyl++)
         for (size_t kx = 0; kx < n; kx++)
-            memcpy(tmp + 2 * ((ky * n + kx) * pc), host_src + 2 * ((kx * n + ky) * hc), sizeof(float) * 2 * hc);
-    int rc = fpm_memcpy_h2d(dev, tmp, sizeof(float) * 2 * n * n * pc);
+            memcpy(tmp + 2 * ((kyl * n + kx) * pc), host_src + 2 * ((kx * n + kyl + y0) * hc), sizeof(float) * 2 * hc);
+    int rc = fpm_memcpy_h2d(dev, tmp, sizeof(float) * 2 * nyl * n * pc);
     free(tmp);
     return rc;
 }

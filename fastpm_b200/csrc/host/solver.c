@@ -79,7 +79,6 @@ static fpm_transfer lpt_kernel(int potorder, int difforder, int d1, int d2)
 void pm_2lpt_solve(PM *pm, FastPMFloat *delta_k, FastPMFuncK *growth_rate_func_k, FastPMStore *p, double shift[3], FastPMKernelType type)
 {
     if (growth_rate_func_k || p->dv1) fastpm_raise(-1, "fastpm_b200: scale-dependent growth (dv1) is out of scope of this build\n");
-    if (pm->NTask > 1) fastpm_raise(-1, "fastpm_b200: 2LPT on several GPUs is not wired in this build\n");
     if (shift[0] != 0 || shift[1] != 0 || shift[2] != 0) fastpm_raise(-1, "fastpm_b200: shifted ICs are not implemented\n");
     int potorder, gradorder, difforder, deconvolveorder;
     fastpm_kernel_type_get_orders(type, &potorder, &gradorder, &difforder, &deconvolveorder);
@@ -94,29 +93,29 @@ void pm_2lpt_solve(PM *pm, FastPMFloat *delta_k, FastPMFuncK *growth_rate_func_k
     /* dx1_d = c2r( i k_d / k^2 delta ), pm2lpt.c:62-74 */
     for (int d = 0; d < 3; d++) {
         t = lpt_kernel(potorder, difforder, d, -1);
-        FPM_MUST(fpm_c2r(pm->mesh, delta_k, workspace, &t));
-        FPM_MUST(fpm_readout(pm->mesh, workspace, (const double *) p->x, (int64_t) p->np, (float *) p->dx1 + d, 3, 1.0));
+        fpm_mesh_c2r(pm, delta_k, workspace, &t);
+        fpm_mesh_readout(pm, workspace, (const double *) p->x, (int64_t) p->np, (float *) p->dx1 + d, 3, 1.0);
     }
     /* phi,dd for the three axes, pm2lpt.c:90-96 */
     for (int d = 0; d < 3; d++) {
         t = lpt_kernel(potorder, difforder, d, d);
-        FPM_MUST(fpm_c2r(pm->mesh, delta_k, field[d], &t));
+        fpm_mesh_c2r(pm, delta_k, field[d], &t);
     }
     for (int d = 0; d < 3; d++) FPM_MUST(fpm_muladd(source, field[D1[d]], field[D2[d]], nf, +1));
     /* cross terms phi,d1d2, pm2lpt.c:108-122 */
     for (int d = 0; d < 3; d++) {
         t = lpt_kernel(potorder, difforder, D1[d], D2[d]);
-        FPM_MUST(fpm_c2r(pm->mesh, delta_k, workspace, &t));
+        fpm_mesh_c2r(pm, delta_k, workspace, &t);
         FPM_MUST(fpm_muladd(source, workspace, workspace, nf, -1));
     }
     /* delta2_k = r2c(source); pm2lpt.c:123-124 copies it back, here the two buffers just swap roles */
-    FPM_MUST(fpm_r2c(pm->mesh, source, workspace, 1.0 / pm->Norm));
+    fpm_mesh_r2c(pm, source, workspace, 1.0 / pm->Norm);
     FastPMFloat *delta2_k = workspace, *w2 = source;
     for (int d = 0; d < 3; d++) {
         t = lpt_kernel(potorder, difforder, d, -1);
-        FPM_MUST(fpm_c2r(pm->mesh, delta2_k, w2, &t));
+        fpm_mesh_c2r(pm, delta2_k, w2, &t);
         /* the 3/7 of pm2lpt.c:133 is applied to each mesh value (rounded to float) inside the gather */
-        FPM_MUST(fpm_readout(pm->mesh, w2, (const double *) p->x, (int64_t) p->np, (float *) p->dx2 + d, 3, 3.0 / 7));
+        fpm_mesh_readout(pm, w2, (const double *) p->x, (int64_t) p->np, (float *) p->dx2 + d, 3, 3.0 / 7);
     }
     for (int d = 0; d < 3; d++) pm_free(pm, field[2 - d]);
     pm_free(pm, workspace);
@@ -468,11 +467,10 @@ void fastpm_b200_host_growth(const double *cosmo, int growth_mode, double a, dou
 void fastpm_b200_setup_synthetic_ic(FastPMSolver *fastpm, uint64_t seed, const double *k, const double *p, int size, double a0)
 {
     PM *pm = fastpm->lptpm;
-    if (pm->NTask > 1) fastpm_raise(-1, "synthetic ICs on several GPUs are not wired in this build\n");
     FastPMFloat *delta_k = pm_alloc_noclear(pm, __FILE__, __LINE__);
     FastPMFloat *g_x = pm_alloc_noclear(pm, __FILE__, __LINE__);
     FPM_MUST(fpm_fill_whitenoise(pm->mesh, g_x, seed));
-    FPM_MUST(fpm_r2c(pm->mesh, g_x, delta_k, sqrt(pm->Norm) / pm->Norm));
+    fpm_mesh_r2c(pm, g_x, delta_k, sqrt(pm->Norm) / pm->Norm);
     pm_free(pm, g_x);
     FPM_MUST(fpm_induce_correlation(pm->mesh, delta_k, k, p, size));
     ptrdiff_t mode[4] = { 0, 0, 0, 0 };

@@ -1,0 +1,165 @@
+"""One process per GPU: joins the C library's communicator to torch.distributed and runs the multi-GPU bench.
+
+torch.distributed (NCCL on GPUs, gloo on CPU) is the plumbing: rendezvous, host scalars, counts, CUDA-IPC handles.
+Mesh planes and particles move GPU to GPU inside the library's own kernels (csrc/comm.cu, csrc/fft*.cu).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ALLREDUCE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p)
+ALLGATHER = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+
+_keep = []
+
+
+def make_callbacks(group=None):
+    """ctypes callbacks implementing host all-reduce (sum/min/max on f64 or i64) and all-gather of bytes."""
+    import torch
+    import torch.distributed as dist
+    ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+    def allreduce(buf, count, is_int64, op, userdata):
+        ct = C.c_int64 if is_int64 else C.c_double
+        arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(ct)), (count,))
+        t = torch.from_numpy(arr.copy()).to(dev)
+        dist.all_reduce(t, op=ops[op], group=group)
+        arr[:] = t.cpu().numpy()
+
+    def allgather(send, nbytes, recv, userdata):
+        world = dist.get_world_size(group)
+        src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), (nbytes,))
+        t = torch.from_numpy(src.copy()).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t, group=group)
+        dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), (nbytes * world,))
+        for r, o in enumerate(outs):
+            dst[r * nbytes:(r + 1) * nbytes] = o.cpu().numpy()
+
+    a, g = ALLREDUCE(allreduce), ALLGATHER(allgather)
+    _keep.extend([a, g])
+    return a, g
+
+
+def init_comm(lib):
+    """Call once per process after torch.distributed.init_process_group and before creating a Solver."""
+    import torch.distributed as dist
+    host_group = dist.new_group(backend="gloo")          # host scalars and IPC handles: CPU tensors, no stream sync
+    a, g = make_callbacks(host_group)
+    lib.fastpm_b200_comm_init.argtypes = [C.c_int, C.c_int, ALLREDUCE, ALLGATHER, C.c_void_p]
+    lib.fastpm_b200_comm_init(dist.get_rank(), dist.get_world_size(), a, g, None)
+
+
+def bench_main(args):
+    import json
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .solver import Solver, ForceEvent
+    import bench as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    lib = _lib.require_device(local)
+    init_comm(lib)
+
+    nc, Bf, K, W = args.nc, args.pm_nc_factor, args.steps, args.warmup
+    N = nc * Bf
+    Np = nc ** 3
+    k_tab, p_tab = B.read_pk()
+    ts = np.linspace(0.1, 1.0, K)
+    alloc = float(os.environ.get("FASTPM_B200_ALLOC_FACTOR", "1.25"))
+    g = Solver(nc=nc, boxsize=float(nc), pm_nc_factor=Bf, force_mode=args.mode, growth_mode="LCDM", np_alloc_factor=alloc)
+    g.setup_synthetic_ic(100, k_tab, p_tab, ts[0])
+    spectra = []
+
+    def on_force_after(solver_ptr, event_ptr, userdata):
+        ev = C.cast(event_ptr, C.POINTER(ForceEvent)).contents
+        spectra.append(g.powerspectrum_of(ev.pm, ev.delta_k))
+        return 0
+
+    g.add_handler("FORCE", 1, on_force_after)
+    # state snapshot on the device for the warm-up restore is not possible once particles migrate between ranks:
+    # the warm-up is therefore a separate short evolve on a second solver state = the same ICs regenerated
+    if W >= 1:
+        g.evolve(ts[:max(W, 2)])
+        g.close()
+        g = Solver(nc=nc, boxsize=float(nc), pm_nc_factor=Bf, force_mode=args.mode, growth_mode="LCDM", np_alloc_factor=alloc)
+        g.setup_synthetic_ic(100, k_tab, p_tab, ts[0])
+        g.add_handler("FORCE", 1, on_force_after)
+        spectra.clear()
+
+    timer = C.c_void_p()
+    _lib.check(lib.fpm_timer_create(C.byref(timer)))
+    lib.fpm_prof_reset()
+    lib.fpm_prof_enable(1)
+    launches0 = int(lib.fpm_kernel_launch_count())
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    _lib.check(lib.fpm_sync())
+    dist.barrier()
+    lib.fpm_timer_start(timer)
+    g.evolve(ts)
+    lib.fpm_timer_stop(timer)
+    ms = C.c_double()
+    _lib.check(lib.fpm_timer_elapsed_ms(timer, C.byref(ms)))
+    _lib.check(lib.fpm_sync())
+    dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = int(lib.fpm_kernel_launch_count()) - launches0
+    lib.fpm_prof_enable(0)
+    counts = (C.c_int64 * len(B.KCLASSES))()
+    totals = (C.c_double * len(B.KCLASSES))()
+    _lib.check(lib.fpm_prof_get(counts, totals, len(B.KCLASSES)))
+    t = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # max over ranks of the device time
+    t_evolve = float(t.item()) / 1e3
+    np_local = torch.tensor([g.np], dtype=torch.int64, device="cuda")
+    dist.all_reduce(np_local)
+    stages = {nm: {"launches": int(counts[i]), "ms": round(float(totals[i]), 3)} for i, nm in enumerate(B.KCLASSES)}
+
+    # end to end: the final particle state to pinned host memory inside the timed region (the ICs are generated on the device
+    # from the replicated P(k) table, so the host -> device input of a multi-GPU run is that table only)
+    n_local = g.np
+    t0 = time.perf_counter()
+    x = g.get_column("x")
+    v = g.get_column("v")
+    _lib.check(lib.fpm_sync())
+    t_d2h = time.perf_counter() - t0
+    td = torch.tensor([t_d2h], dtype=torch.float64, device="cuda")
+    dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    t_e2e = t_evolve + float(td.item())
+
+    S_local = 4.0 * N * N * (N + 2) / world
+    peak, peak_src = B.measured_peak()
+    tile = stages["fft_tile"]
+    avg_ms = tile["ms"] / max(1, tile["launches"])
+    achieved = 2 * S_local / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    fftz = stages["fft_z"]
+    ntr = max(1, fftz["launches"])
+    t_tr = (tile["ms"] + fftz["ms"]) / ntr
+    line = {
+        "metric": B.METRIC, "value": Np * K / t_evolve, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_evolve / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 mesh / f64 positions", "data": "synthetic", "config": dict(B.workload_config(args), parallelism="x-slabs x%d" % world),
+        "e2e": {"value": Np * K / t_e2e, "unit": B.UNIT, "h2d_bytes_per_step": int(16 * len(k_tab) // K), "d2h_bytes_per_step": int(36 * Np // K),
+                "seconds": round(t_e2e, 4)},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "fft_tma_kernel (strided FFT pass, per rank, incl. NVLink stores of the slab transpose)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * S_local, "avg_launch_ms": round(avg_ms, 4)},
+        "fft": {"gbs_6S_per_gpu": round(6 * S_local / (t_tr * 1e-3) / 1e9, 1) if t_tr > 0 else 0.0, "ms_per_transform": round(t_tr, 4), "transforms": ntr},
+        "stages_rank0": stages, "np_total_after": int(np_local.item()), "result_finite": bool(np.isfinite(x).all() and np.isfinite(v).all()),
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    g.close()
+    dist.barrier()
+    return 0

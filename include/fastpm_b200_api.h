@@ -501,8 +501,6 @@ int fastpm_b200_mesh_get_complex(PM *pm, const FastPMFloat *dev, float *host_dst
 int fastpm_b200_mesh_set_complex(PM *pm, FastPMFloat *dev, const float *host_src);
 /* number of floats in a host array in the reference layout: N*N*(N+2) */
 size_t fastpm_b200_mesh_host_size(PM *pm);
-/* CUDA-event timing of the last fastpm_solver_evolve, per KDK cycle boundaries (bench.py) */
-int fastpm_b200_evolve_timeline(double *ms_out, int max_entries);
 /* a FastPMConfig/FastPMSolver pair built from scalars, for bindings that cannot lay out the structs */
 FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                      double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
