@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libfastpm_b200.so")
 
 # every symbol include/fastpm_b200.h declares; tests check that the library exports all of them
 ABI_SYMBOLS = [
-    "fpm_last_error", "fpm_version", "fpm_device_init", "fpm_device_count", "fpm_device_mem_info",
+    "fpm_last_error", "fpm_version", "fpm_device_init", "fpm_device_count", "fpm_device_mem_info", "fpm_debug_state",
     "fpm_malloc", "fpm_free", "fpm_host_alloc_pinned", "fpm_host_free_pinned",
     "fpm_memcpy_h2d", "fpm_memcpy_d2h", "fpm_memcpy_d2d", "fpm_memset", "fpm_sync",
     "fpm_timer_create", "fpm_timer_start", "fpm_timer_stop", "fpm_timer_elapsed_ms", "fpm_timer_destroy",
@@ -105,8 +105,21 @@ def check(rc, what=""):
         raise FastPMB200Error("%s failed: %s" % (what or "fastpm_b200 call", load().fpm_last_error().decode()))
 
 
-def require_device(device=0):
-    """Initialise the CUDA device; raises if there is none (the product has no CPU path)."""
+_device = None
+
+
+def require_device(device=None):
+    """Initialise the CUDA device; raises if there is none (the product has no CPU path).
+
+    device=None keeps the device this process already initialised, else FASTPM_B200_DEVICE / LOCAL_RANK / 0
+    (the same rule as libfastpm_init in csrc/host/support.c)."""
+    global _device
     lib = load()
-    check(lib.fpm_device_init(int(device)), "fpm_device_init")
+    if device is None:
+        if _device is not None:
+            return lib
+        device = int(os.environ.get("FASTPM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if _device != int(device):
+        check(lib.fpm_device_init(int(device)), "fpm_device_init")
+        _device = int(device)
     return lib

@@ -73,7 +73,12 @@ extern "C" void fpm_set_error(const char *fmt, ...)
 extern "C" int fpm_device_init(int device);
 static int ensure_init()
 {
-    if (g_device >= 0) return 0;
+    if (g_device >= 0) {
+        // the caller (or a library it uses) may have made another device current on this thread since the last call
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != g_device) cudaSetDevice(g_device);
+        return 0;
+    }
     return fpm_device_init(0);
 }
 
@@ -104,6 +109,20 @@ int fpm_device_init(int device)
     if (!g_stream) FPM_CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_device = device;
     { const char *e = getenv("FASTPM_B200_DEBUG_SYNC"); fpm_debug_sync = e ? atoi(e) : 0; }
+    return 0;
+}
+
+// diagnostic: current device of this thread, the library's device, and the device that owns `ptr` (or -1)
+int fpm_debug_state(const void *ptr, int out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = -1;
+    cudaGetDevice(&out[0]);
+    out[1] = g_device;
+    if (ptr) {
+        cudaPointerAttributes at; memset(&at, 0, sizeof(at));
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess) { out[2] = at.device; out[3] = (int) at.type; }
+        else cudaGetLastError();
+    }
     return 0;
 }
 
@@ -293,7 +312,7 @@ void fpm_mesh_destroy(fpm_mesh *m)
 {
     if (!m) return;
     fpm_fft_plan_destroy(m->plan);
-    cudaFree(m->d_ktab_store); cudaFree(m->d_decic);
+    cudaFree(m->d_ktab_store); cudaFree(m->d_decic); cudaFree(m->d_pkgeom);
     delete m;
 }
 

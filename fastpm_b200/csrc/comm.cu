@@ -10,6 +10,7 @@
 #include "mesh.cuh"
 #include "../../include/fastpm_b200.h"
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <map>
 
@@ -52,8 +53,17 @@ extern "C" void *fpm_ipc_open(const void *handle64, uint64_t offset)
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     void *p = NULL;
+    int dev_before = -1, dev_after = -1;
+    cudaGetDevice(&dev_before);
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) { fpm_set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
+    cudaGetDevice(&dev_after);
+    if (getenv("FASTPM_B200_DEBUG_IPC")) {
+        cudaPointerAttributes at; memset(&at, 0, sizeof(at));
+        cudaPointerGetAttributes(&at, p);
+        fprintf(stderr, "fpm_ipc_open: device before %d, after %d; mapped %p lives on device %d (type %d)\n", dev_before, dev_after, p, at.device, (int) at.type);
+    }
+    if (dev_before >= 0) cudaSetDevice(dev_before);      // mapping a peer's memory must not leave another device current
     OpenedHandle o; memcpy(o.h, handle64, 64); o.base = p;
     g_opened.push_back(o);
     return (unsigned char *) p + offset;
@@ -85,13 +95,11 @@ __global__ void xbarrier_kernel(unsigned long long *const *peer_flags_dev, volat
 
 static unsigned long long **g_peer_flags_dev = NULL;
 
-extern "C" int fpm_xbarrier_init(int nranks, int rank, void **local_flags_out)
+extern "C" int fpm_xbarrier_init(int nranks, int rank, void *local_flags)
 {
     g_bar.nranks = nranks; g_bar.rank = rank; g_bar.epoch = 0;
-    g_bar.flags = (unsigned long long *) fpm_malloc(sizeof(unsigned long long) * FPM_MAX_RANKS);
-    if (!g_bar.flags) return -1;
+    g_bar.flags = (unsigned long long *) local_flags;
     FPM_CUDA_OK(cudaMemset(g_bar.flags, 0, sizeof(unsigned long long) * FPM_MAX_RANKS));
-    *local_flags_out = g_bar.flags;
     return 0;
 }
 
@@ -242,7 +250,7 @@ struct Migrate {
 };
 static Migrate g_mig = { 0 };
 
-extern "C" int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void **pack_out)
+extern "C" int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void *pack)
 {
     g_mig.cap = cap;
     g_mig.leaver_cap = np_upper;
@@ -254,10 +262,17 @@ extern "C" int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t 
     FPM_CUDA_OK(cudaMalloc(&g_mig.d_movers, sizeof(int) * (size_t) nranks * cap));
     FPM_CUDA_OK(cudaMalloc(&g_mig.d_counters, sizeof(int) * 2));
     FPM_CUDA_OK(cudaMalloc(&g_mig.d_leaver, (size_t) np_upper));
-    g_mig.d_pack = (unsigned char *) fpm_malloc(g_mig.pack_bytes_per_dest * nranks);
-    if (!g_mig.d_pack) return -1;
-    *pack_out = g_mig.d_pack;
+    g_mig.d_pack = (unsigned char *) pack;       // [nranks][cap][row_bytes], in the symmetric arena (host/comm.c)
     return 0;
+}
+
+extern "C" void fpm_migrate_destroy(void)
+{
+    if (!g_mig.d_send_count) return;
+    cudaStreamSynchronize(comm_stream());
+    cudaFree(g_mig.d_send_count); cudaFree(g_mig.d_send_idx); cudaFree(g_mig.d_overflow); cudaFree(g_mig.d_holes);
+    cudaFree(g_mig.d_movers); cudaFree(g_mig.d_counters); cudaFree(g_mig.d_leaver);
+    memset(&g_mig, 0, sizeof(g_mig));
 }
 
 // step 1: classify; returns the per-destination counts on the host (synchronises the stream)

@@ -36,6 +36,24 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *t
         : "memory");
 }
 
+// 1-D bulk copies (TMA without a tensor map): global -> shared signalled on an mbarrier, shared -> global in bulk groups.
+// Addresses 16-byte aligned, sizes multiples of 16 bytes.
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// makes this thread's generic-proxy shared-memory writes visible to the async proxy (bulk stores)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------ register FFT (radix-2 DIF, unrolled)
 // twiddle exp(-2 pi i idx/16), idx = 0..7, as compile-time constants
 __device__ __forceinline__ float2 w16(int idx)

@@ -16,14 +16,14 @@ typedef void (*fpm_host_allgather_fn)(const void *send, int nbytes, void *recv, 
 /* device side, csrc/comm.cu */
 int fpm_ipc_get_handle(void *dev_ptr, void *handle64, uint64_t *offset);
 void *fpm_ipc_open(const void *handle64, uint64_t offset);
-int fpm_xbarrier_init(int nranks, int rank, void **local_flags_out);
+int fpm_xbarrier_init(int nranks, int rank, void *local_flags);
 int fpm_xbarrier_set_peers(void *const *peer_flag_ptrs);
 int fpm_xbarrier(void);
 int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale);
 int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel);
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
 int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank);
-int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void **pack_out);
+int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void *pack);
 int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t np, int *send_count_host);
 int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes);
 int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host);
@@ -62,46 +62,28 @@ static void allgather(const void *send, int nbytes, void *recv)
     g_allgather(send, nbytes, recv, g_cb_data);
 }
 
-/* ------------------------------------------------------------------ registry of peer mappings
- * opened[r] remembers every (remote address -> local mapping) of rank r that was opened with CUDA IPC. */
-typedef struct { uint64_t remote; void *mapped; } Mapping;
-static Mapping *opened[MAXR];
-static int n_opened[MAXR];
+/* ------------------------------------------------------------------ the symmetric arena (host/support.c)
+ * Every device buffer of a multi-GPU run lives in one arena per process; arena_peer[r] is rank r's arena as mapped
+ * into this process with CUDA IPC at start-up.  All ranks allocate the same sizes in the same order, so the peer
+ * copies of a local buffer sit at the same offset: no per-call handle exchange, nothing can go stale. */
+int fastpm_b200_arena_init(size_t bytes);
+void *fastpm_b200_arena_base(void);
+size_t fastpm_b200_arena_size(void);
+int fastpm_b200_arena_contains(const void *p);
+static char *arena_peer[MAXR];
 
-/* Collective: returns, for the local device pointer `local` (the start of an fpm_malloc block), the addresses under
- * which every rank's corresponding block is reachable from this GPU.  One 8-byte all-gather per call; IPC handles are
- * exchanged only when some rank presents a block that has not been mapped before. */
 static void peers_of(void *local, void *peers[MAXR])
 {
-    uint64_t mine = (uint64_t) (uintptr_t) local, all[MAXR];
-    allgather(&mine, 8, all);
-    int need = 0;
-    for (int r = 0; r < g_size; r++) {
-        peers[r] = NULL;
-        if (r == g_rank) { peers[r] = local; continue; }
-        for (int i = 0; i < n_opened[r]; i++) if (opened[r][i].remote == all[r]) peers[r] = opened[r][i].mapped;
-        if (!peers[r]) need = 1;
+    if (!fastpm_b200_arena_contains(local))
+        fastpm_raise(-1, "multi-GPU exchange on a buffer (%p) that was not allocated from the symmetric arena (pm_alloc / fastpm_memory_alloc)\n", local);
+    const size_t off = (size_t) ((char *) local - (char *) fastpm_b200_arena_base());
+    if (getenv("FASTPM_B200_CHECK_SYMMETRY")) {
+        uint64_t mine = off, all[MAXR];
+        allgather(&mine, 8, all);
+        for (int r = 0; r < g_size; r++)
+            if (all[r] != mine) fastpm_raise(-1, "asymmetric allocation: offset %zu here, %zu on rank %d\n", off, (size_t) all[r], r);
     }
-    /* whether anyone needs a handle is a global decision: every rank must take part in the second gather */
-    int64_t any = need;
-    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &any, 1, 2);
-    if (!any) return;
-    unsigned char h[72], hall[MAXR * 72];
-    uint64_t off = 0;
-    if (fpm_ipc_get_handle(local, h, &off) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
-    memcpy(h + 64, &off, 8);
-    allgather(h, 72, hall);
-    for (int r = 0; r < g_size; r++) {
-        if (r == g_rank || peers[r]) continue;
-        uint64_t roff; memcpy(&roff, hall + 72 * r + 64, 8);
-        void *m = fpm_ipc_open(hall + 72 * r, roff);
-        if (!m) fastpm_raise(-1, "mapping rank %d's buffer: %s\n", r, fpm_last_error());
-        opened[r] = realloc(opened[r], sizeof(Mapping) * (n_opened[r] + 1));
-        opened[r][n_opened[r]].remote = all[r];
-        opened[r][n_opened[r]].mapped = m;
-        n_opened[r]++;
-        peers[r] = m;
-    }
+    for (int r = 0; r < g_size; r++) peers[r] = arena_peer[r] + off;
 }
 
 /* ------------------------------------------------------------------ set-up by the launcher */
@@ -111,8 +93,26 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
     if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
     g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
     if (size == 1) return;
-    void *flags = NULL, *peers[MAXR];
-    if (fpm_xbarrier_init(size, rank, &flags) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    /* arena: FASTPM_B200_ARENA_GB, else 85 % of what is free now; the smallest over ranks so that offsets stay in range everywhere */
+    size_t free_b = 0, total_b = 0;
+    if (fpm_device_mem_info(&free_b, &total_b) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    const char *e = getenv("FASTPM_B200_ARENA_GB");
+    int64_t want = e ? (int64_t) (atof(e) * 1073741824.0) : (int64_t) (0.85 * free_b);
+    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &want, 1, 1);
+    if (fastpm_b200_arena_init((size_t) want) != 0) fastpm_raise(-1, "arena of %lld bytes: %s\n", (long long) want, fpm_last_error());
+    unsigned char h[72], hall[MAXR * 72];
+    uint64_t off = 0;
+    if (fpm_ipc_get_handle(fastpm_b200_arena_base(), h, &off) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    memcpy(h + 64, &off, 8);
+    allgather(h, 72, hall);
+    for (int r = 0; r < size; r++) {
+        if (r == rank) { arena_peer[r] = fastpm_b200_arena_base(); continue; }
+        uint64_t roff; memcpy(&roff, hall + 72 * r + 64, 8);
+        arena_peer[r] = fpm_ipc_open(hall + 72 * r, roff);
+        if (!arena_peer[r]) fastpm_raise(-1, "mapping rank %d's arena: %s\n", r, fpm_last_error());
+    }
+    void *flags = fastpm_memory_alloc(_libfastpm_get_gmem(), "xbarrier flags", 4096, FASTPM_MEMORY_FLOATING), *peers[MAXR];
+    if (fpm_xbarrier_init(size, rank, flags) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
     peers_of(flags, peers);
     if (fpm_xbarrier_set_peers(peers) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
     fpm_comm_barrier(MPI_COMM_WORLD);
@@ -172,6 +172,17 @@ static void *pack_local = NULL, *pack_peers[MAXR];
 static int mig_cap = 0;
 static size_t mig_row_bytes = 0;
 
+void fpm_migrate_destroy(void);
+/* called when the particle store goes away (fastpm_solver_destroy): the pack buffers are sized for that store */
+void fpm_comm_release_migration(void)
+{
+    if (!pack_local) return;
+    fpm_comm_barrier(MPI_COMM_WORLD);           /* nobody is still pulling from our pack buffers */
+    fpm_migrate_destroy();
+    fastpm_memory_free(_libfastpm_get_gmem(), pack_local);
+    pack_local = NULL; mig_cap = 0; mig_row_bytes = 0;
+}
+
 typedef struct { void *ptr; int elsize; } MigCol;
 
 static int migrating_columns(FastPMStore *p, MigCol *cols)
@@ -206,7 +217,8 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
         if (mig_cap < 4096) mig_cap = 4096;
         if ((size_t) mig_cap > p->np_upper) mig_cap = (int) p->np_upper;
         mig_row_bytes = row;
-        if (fpm_migrate_init(g_size, mig_cap, (long long) p->np_upper, row, &pack_local) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        pack_local = fastpm_memory_alloc(p->mem, "migration pack buffers", (size_t) g_size * mig_cap * row, FASTPM_MEMORY_FLOATING);
+        if (fpm_migrate_init(g_size, mig_cap, (long long) p->np_upper, row, pack_local) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
         peers_of(pack_local, pack_peers);
     }
     if (row != mig_row_bytes) fastpm_raise(-1, "fastpm_b200: the set of particle columns changed between decompositions\n");

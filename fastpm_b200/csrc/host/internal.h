@@ -51,6 +51,7 @@ int fpm_comm_size(MPI_Comm comm);
 void fpm_comm_allreduce_double(MPI_Comm comm, double *v, int n, int op);   /* op: 0 sum, 1 min, 2 max */
 void fpm_comm_allreduce_i64(MPI_Comm comm, int64_t *v, int n, int op);
 void fpm_comm_barrier(MPI_Comm comm);
+void fpm_comm_release_migration(void);
 
 /* comm.c: mesh exchanges for one rank or many */
 void fpm_halo_add(PM *pm, FastPMFloat *canvas);

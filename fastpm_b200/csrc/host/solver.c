@@ -50,6 +50,7 @@ void fastpm_solver_init(FastPMSolver *fastpm, FastPMConfig *config, MPI_Comm com
 
 void fastpm_solver_destroy(FastPMSolver *fastpm)
 {
+    fpm_comm_release_migration();
     pm_delete(fastpm->lptpm);
     pm_delete(fastpm->basepm);
     fastpm_store_destroy(fastpm->cdm);

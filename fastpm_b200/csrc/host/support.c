@@ -173,6 +173,66 @@ void fastpm_memory_dump_status_str(FastPMMemory *m, char *buf, int n)
         off += snprintf(buf + off, n - off, "  %p %012zu : %s\n", b->p, b->size, b->tag);
 }
 
+/* ---- symmetric arena (several GPUs): one device allocation per process, mapped once into every peer with CUDA IPC
+ * (host/comm.c).  Every rank performs the same sequence of allocations with the same sizes (meshes, particle columns,
+ * exchange buffers), and the first-fit policy below is deterministic, so a buffer sits at the SAME offset in every
+ * rank's arena: the address of a peer's copy is peer_base + (p - my_base), no handle exchange per call, and no mapping
+ * can go stale because the arena is never freed while the communicator lives. */
+static char *arena_base = NULL;
+static size_t arena_size = 0;
+typedef struct { size_t off, size; } ArenaBlock;
+static ArenaBlock *arena_blocks = NULL;     /* sorted by offset */
+static int arena_nblocks = 0;
+#define ARENA_ALIGN ((size_t) 1 << 20)
+
+int fastpm_b200_arena_init(size_t bytes)
+{
+    if (arena_base) return 0;
+    bytes = bytes / ARENA_ALIGN * ARENA_ALIGN;
+    arena_base = fpm_malloc(bytes);
+    if (!arena_base) return -1;
+    arena_size = bytes;
+    return 0;
+}
+void *fastpm_b200_arena_base(void) { return arena_base; }
+size_t fastpm_b200_arena_size(void) { return arena_size; }
+int fastpm_b200_arena_contains(const void *p) { return arena_base && (const char *) p >= arena_base && (const char *) p < arena_base + arena_size; }
+
+static void *arena_alloc(size_t s)
+{
+    s = (s + ARENA_ALIGN - 1) / ARENA_ALIGN * ARENA_ALIGN;
+    size_t off = 0;
+    int at = 0;
+    for (; at < arena_nblocks; at++) {
+        if (arena_blocks[at].off - off >= s) break;
+        off = arena_blocks[at].off + arena_blocks[at].size;
+    }
+    if (at == arena_nblocks && arena_size - off < s) return NULL;
+    arena_blocks = realloc(arena_blocks, sizeof(ArenaBlock) * (arena_nblocks + 1));
+    memmove(arena_blocks + at + 1, arena_blocks + at, sizeof(ArenaBlock) * (arena_nblocks - at));
+    arena_blocks[at].off = off; arena_blocks[at].size = s;
+    arena_nblocks++;
+    return arena_base + off;
+}
+static void arena_free(void *p)
+{
+    const size_t off = (size_t) ((char *) p - arena_base);
+    for (int i = 0; i < arena_nblocks; i++) {
+        if (arena_blocks[i].off != off) continue;
+        memmove(arena_blocks + i, arena_blocks + i + 1, sizeof(ArenaBlock) * (arena_nblocks - i - 1));
+        arena_nblocks--;
+        return;
+    }
+    fastpm_raise(-1, "arena_free: %p is not the start of an arena block\n", p);
+}
+void fastpm_b200_arena_destroy(void)
+{
+    if (arena_nblocks) fastpm_raise(-1, "arena destroyed with %d live blocks\n", arena_nblocks);
+    if (arena_base) fpm_free(arena_base);
+    free(arena_blocks);
+    arena_base = NULL; arena_size = 0; arena_blocks = NULL; arena_nblocks = 0;
+}
+
 void *fastpm_memory_alloc_details(FastPMMemory *m, const char *name, size_t s, enum FastPMMemoryLocation loc, const char *file, const int line)
 {
     if (s == 0) s = 1;
@@ -181,7 +241,15 @@ void *fastpm_memory_alloc_details(FastPMMemory *m, const char *name, size_t s, e
         fastpm_raise(-1, "Out of memory bound allocating %zu bytes for %s at %s:%d\n", s, name, file, line);
     }
     void *p = NULL;
-    for (int i = 0; i < NCACHE; i++) if (cache[i].p && cache[i].size == s) { p = cache[i].p; cache[i].p = NULL; break; }
+    if (arena_base) {
+        p = arena_alloc(s);
+        if (!p) {
+            if (m->abortfunc) m->abortfunc(m, m->userdata);
+            fastpm_raise(-1, "Out of device memory: the %zu-byte arena cannot hold %zu more bytes for %s at %s:%d (FASTPM_B200_ARENA_GB)\n",
+                         arena_size, s, name, file, line);
+        }
+    }
+    if (!p) for (int i = 0; i < NCACHE; i++) if (cache[i].p && cache[i].size == s) { p = cache[i].p; cache[i].p = NULL; break; }
     if (!p) p = fpm_malloc(s);
     if (!p) {
         /* drop the cache and retry once */
@@ -213,6 +281,7 @@ void fastpm_memory_free(FastPMMemory *m, void *p)
     }
     *pp = b->prev;
     m->used_bytes -= b->size;
+    if (fastpm_b200_arena_contains(p)) { arena_free(p); free(b); return; }
     int slot = -1;
     for (int i = 0; i < NCACHE; i++) if (!cache[i].p) { slot = i; break; }
     if (slot < 0) {                     /* evict the smallest */

@@ -59,54 +59,120 @@ __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const doubl
 }
 
 // powerspectrum.c:35-124.  bins = n/2 integer shells of |i|; per bin: sum w, sum w*|delta|^2, sum w*|k|.
-// Shared-memory histograms per CTA (double), flushed with one global atomic per non-empty bin.
-// `decic` folds the deconvolution (rounded to float like the reference's in-place sweep) into the read.
-__global__ void __launch_bounds__(256) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
-        const float2 *__restrict__ dk, size_t total, double k0, double *__restrict__ out /* [3][nbins] + 1 */)
+// One warp per k-space row (ky, kx fixed; kz = 0..N/2 contiguous), two adjacent modes per lane: along a row the shell
+// index is non-decreasing in kz, so the 64 modes of a warp-wide load fall into a few CONTIGUOUS runs of equal bin.
+// Each run is summed with a segmented shuffle reduction and only the head lane of a run touches the CTA's
+// shared-memory histogram (double), which is flushed with one global atomic per non-empty bin.
+// sum w and sum w*|k| depend on the mesh geometry only: GEOM = true accumulates those two (once per mesh, cached),
+// GEOM = false accumulates the data-dependent sum w*|delta|^2 and the all-mode variance.  `decic` folds the
+// deconvolution (rounded to float like the reference's in-place sweep, transfer.c:78-113) into the read.
+#define PK_WARPS 8
+#define PK_UNROLL 2
+template <bool GEOM>
+__global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
+        const float2 *__restrict__ dk, double k0, double *__restrict__ out /* GEOM: [2][nbins]; else [nbins] + 1 */)
 {
-    extern __shared__ double hist[];     // [3][nbins], then one slot: sum over ALL modes of w |delta|^2 (pm_compute_variance)
+    extern __shared__ double hist[];
     const int nbins = g.n / 2;
-    for (int i = threadIdx.x; i < 3 * nbins + 1; i += blockDim.x) hist[i] = 0;
+    const int nslots = GEOM ? 2 * nbins : nbins + 1;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int n = g.n, h = n / 2, lane = threadIdx.x & 31;
+    const size_t nrows = (size_t) g.nyl * n;
+    const size_t wstride = (size_t) gridDim.x * PK_WARPS;
+    const int nchunk = (h + 1 + 63) / 64;
     double allsum = 0;
-    __syncthreads();
-    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    const int n = g.n, h = n / 2;
-    for (; t < total; t += stride) {
-        ModeIdx m = mode_from_linear(g, t);
-        if (!m.valid) continue;
-        {
-            const float2 v0 = dk[m.off];
-            allsum += ((m.iz == 0 || m.iz == h) ? 1.0 : 2.0) * ((double) v0.x * (double) v0.x + (double) v0.y * (double) v0.y);
+    for (size_t row = (size_t) blockIdx.x * PK_WARPS + (threadIdx.x >> 5); row < nrows; row += wstride) {
+        const int ix = (int) (row % n), iy = (int) (row / n) + g.y0;
+        const int ikx = ix > h ? ix - n : ix, iky = iy > h ? iy - n : iy;
+        const int kxy = ikx * ikx + iky * iky;
+        const double dxy = (!GEOM && decic) ? dtab[ix] * dtab[iy] : 1.0;      // (1 * d[ix]) * d[iy], the reference's order
+        const float4 *src = reinterpret_cast<const float4 *>(dk + row * (size_t) g.pitch_c);
+        for (int c0 = 0; c0 < nchunk; c0 += PK_UNROLL) {
+            float4 vv[PK_UNROLL];
+            if (!GEOM) {
+                #pragma unroll
+                for (int u = 0; u < PK_UNROLL; u++) {
+                    const int iz = (c0 + u) * 64 + 2 * lane;          // pitch_c is a multiple of 16: iz + 1 stays inside the row
+                    vv[u] = (c0 + u < nchunk && iz <= h) ? __ldg(src + (iz >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < PK_UNROLL; u++) {
+                if (c0 + u >= nchunk) break;                         // warp-uniform
+                int bins[2];
+                double acc[2], acc2[2];
+                #pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int iz = (c0 + u) * 64 + 2 * lane + e;
+                    const bool inrow = iz <= h;
+                    const double w = (iz == 0 || iz == h) ? 1.0 : 2.0;
+                    const int kk = kxy + iz * iz;                    // iz <= h: never wrapped
+                    const float sf = sqrtf((float) kk);              // kk < 2^24: exact in float; the estimate is off by at most 1
+                    int bin = (int) sf;
+                    if ((bin + 1) * (bin + 1) <= kk) bin++;
+                    if (bin * bin > kk) bin--;
+                    if (!inrow || bin > nbins) bin = nbins;          // dropped: beyond the last shell or row padding
+                    const bool counted = inrow && bin < nbins && kk != 0;
+                    acc[e] = 0; acc2[e] = 0;
+                    if (GEOM) {
+                        if (counted) { acc[e] = w; acc2[e] = w * (sqrt((double) kk) * k0); }
+                    } else {
+                        float2 v = e ? make_float2(vv[u].z, vv[u].w) : make_float2(vv[u].x, vv[u].y);
+                        if (inrow) allsum += w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
+                        if (counted) {
+                            if (decic) {
+                                const double smth = dxy * dtab[iz];
+                                v.x = (float) ((double) v.x * smth);
+                                v.y = (float) ((double) v.y * smth);
+                            }
+                            acc[e] = w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
+                        }
+                    }
+                    bins[e] = bin;
+                }
+                // the lane's two modes: merge when they share a bin, else the first one goes out on its own
+                int bin = bins[1];
+                double s1 = acc[1], s2 = acc2[1];
+                if (bins[0] == bin) { s1 += acc[0]; s2 += acc2[0]; }
+                else if (bins[0] < nbins && (acc[0] != 0 || acc2[0] != 0)) {
+                    if (GEOM) { atomicAdd(&hist[bins[0]], acc[0]); atomicAdd(&hist[nbins + bins[0]], acc2[0]); }
+                    else atomicAdd(&hist[bins[0]], acc[0]);
+                }
+                // segmented reduction over runs of equal bin (contiguous because bin is monotone in iz)
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int ob = __shfl_down_sync(0xffffffffu, bin, o);
+                    const double o1 = __shfl_down_sync(0xffffffffu, s1, o);
+                    double o2 = 0;
+                    if (GEOM) o2 = __shfl_down_sync(0xffffffffu, s2, o);
+                    if (lane + o < 32 && ob == bin) { s1 += o1; s2 += o2; }
+                }
+                // NB: a lane whose first mode left on its own still heads the run of its second mode only if the previous
+                // lane's LAST bin differs, which is what bins[1] of the previous lane tells
+                const int pb = __shfl_up_sync(0xffffffffu, bin, 1);
+                if ((lane == 0 || pb != bin) && bin < nbins && (s1 != 0 || s2 != 0)) {
+                    atomicAdd(&hist[bin], s1);
+                    if (GEOM) atomicAdd(&hist[nbins + bin], s2);
+                }
+            }
         }
-        if (m.ix == 0 && m.iy == 0 && m.iz == 0) continue;
-        long long ikx = m.ix > h ? m.ix - n : m.ix;
-        long long iky = m.iy > h ? m.iy - n : m.iy;
-        long long ikz = m.iz > h ? m.iz - n : m.iz;
-        const long long kk = ikx * ikx + iky * iky + ikz * ikz;
-        long long bin = (long long) floor(sqrt((double) kk)) - 2;
-        if (bin < 0) bin = 0;
-        while ((bin + 1) * (bin + 1) <= kk) bin++;
-        if (bin >= nbins) continue;
-        float2 v = dk[m.off];
-        if (decic) {
-            double smth = 1.0;
-            smth *= dtab[m.ix]; smth *= dtab[m.iy]; smth *= dtab[m.iz];
-            v.x = (float) ((double) v.x * smth);
-            v.y = (float) ((double) v.y * smth);
-        }
-        const double value = (double) v.x * (double) v.x + (double) v.y * (double) v.y;
-        const double w = (m.iz == 0 || m.iz == h) ? 1.0 : 2.0;
-        const double k = sqrt((double) kk) * k0;
-        atomicAdd(&hist[bin], w);
-        atomicAdd(&hist[nbins + bin], w * value);
-        atomicAdd(&hist[2 * nbins + bin], w * k);
     }
-    for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
-    if ((threadIdx.x & 31) == 0 && allsum != 0) atomicAdd(&hist[3 * nbins], allsum);
+    if (!GEOM) {
+        for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
+        if (lane == 0 && allsum != 0) atomicAdd(&hist[nbins], allsum);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * nbins + 1; i += blockDim.x)
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x)
         if (hist[i] != 0) atomicAdd(&out[i], hist[i]);
+}
+
+// out[3*nbins + 1] = geometry sums (cached) and data sums laid out as the callers expect: [sum w][sum w |d|^2][sum w k][variance]
+__global__ void pk_assemble_kernel(const double *__restrict__ geom, const double *__restrict__ data, int nbins, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbins) { out[i] = geom[i]; out[nbins + i] = data[i]; out[2 * nbins + i] = geom[nbins + i]; }
+    if (i == 0) out[3 * nbins] = data[nbins];
 }
 
 // buf[i] = (float)(buf[i] * value): fastpm_apply_multiply_transfer, transfer.c:213-220
@@ -254,17 +320,27 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
 {
     const FpmGeom &g = m->geom;
     const int nbins = g.n / 2;
-    const size_t total = cplx_total(g);
-    const size_t smem = sizeof(double) * (3 * nbins + 1);
-    FPM_CUDA_OK(cudaMemsetAsync(d_out, 0, smem, st));
+    const size_t smem = sizeof(double) * (2 * nbins + 1);
     static bool attr_done = false;
     if (!attr_done) {
-        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_done = true;
     }
     if (smem > 96 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
     const double k0 = 2 * M_PI / g.boxsize;
-    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<<<148 * 4, 256, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, total, k0, d_out)));
+    FpmMesh *mm = const_cast<FpmMesh *>(m);           // the per-mesh cache of the geometry sums
+    if (!mm->d_pkgeom) {
+        FPM_CUDA_OK(cudaMalloc(&mm->d_pkgeom, sizeof(double) * (3 * nbins + 1)));
+        FPM_CUDA_OK(cudaMemsetAsync(mm->d_pkgeom, 0, sizeof(double) * (3 * nbins + 1), st));
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<true><<<148 * 4, 32 * PK_WARPS, smem, st>>>(g, m->d_decic, 0, nullptr, k0, mm->d_pkgeom)));
+        FPM_CHECK_LAUNCH();
+    }
+    double *d_data = mm->d_pkgeom + 2 * nbins;        // [nbins] + 1
+    FPM_CUDA_OK(cudaMemsetAsync(d_data, 0, sizeof(double) * (nbins + 1), st));
+    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * 4, 32 * PK_WARPS, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+    FPM_CHECK_LAUNCH();
+    pk_assemble_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(mm->d_pkgeom, d_data, nbins, d_out);
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -84,6 +84,7 @@ struct FpmMesh {
     FpmKTables ktab;        // device pointers
     float *d_ktab_store;    // one allocation behind ktab
     double *d_decic;        // [n] 1/sinc^2(k h/2) per index (double, as the reference's per-thread table)
+    double *d_pkgeom;       // P(k) cache: [2][n/2] sum w, sum w|k| of this rank's modes (geometry only), then [n/2 + 1] scratch
     fpm_barrier_fn barrier; // cross-GPU barrier between a transposing pass and the next (multi-GPU only)
     void *comm;             // opaque communicator (multi-GPU only)
 };

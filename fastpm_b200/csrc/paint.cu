@@ -15,6 +15,7 @@
 // plane may be the halo plane nxl, which is exchanged with the next rank (single GPU: periodic wrap).
 #include "common.cuh"
 #include "mesh.cuh"
+#include <stdlib.h>
 
 struct CicIndex {
     int lx0, lx1, j0, j1, k0, k1;      // lx*: local plane index or -1 when outside this rank
@@ -52,6 +53,29 @@ __device__ __forceinline__ void cic_setup(const FpmGeom &g, const double *pos, C
     }
 }
 
+// Adds (w0, w1) to row[k0], row[k1].  VEC = 2 / 4: when both cells fall into one aligned float2 / float4 of the row the pair goes
+// out as ONE vector reduction (red.global.add.v2/v4.f32, sm_90+), halving the number of reductions the LSU has to issue; the
+// padding lanes of a float4 add +0.0f, which leaves the cell unchanged.  Each element is still an independent float32 atomic
+// add, so the result is the same as with scalar atomics (up to the order of additions, which is unordered anyway).
+template <int VEC>
+__device__ __forceinline__ void cic_add_pair(float *row, int k0, int k1, float w0, float w1)
+{
+    if (VEC == 4 && k1 == k0 + 1 && (k0 & 3) != 3) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int q = k0 & 3;
+        if (q == 0) { v.x = w0; v.y = w1; } else if (q == 1) { v.y = w0; v.z = w1; } else { v.z = w0; v.w = w1; }
+        atomicAdd(reinterpret_cast<float4 *>(row + (k0 & ~3)), v);
+        return;
+    }
+    if (VEC >= 2 && k1 == k0 + 1 && (k0 & 1) == 0) {
+        atomicAdd(reinterpret_cast<float2 *>(row + k0), make_float2(w0, w1));
+        return;
+    }
+    atomicAdd(row + k0, w0);
+    atomicAdd(row + k1, w1);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
         const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
         int field_stride, long long np)
@@ -67,17 +91,13 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
     const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
     if (c.lx0 >= 0) {
         float *p0 = canvas + (size_t) c.lx0 * pl;
-        atomicAdd(p0 + c.j0 * pr + c.k0, (float) (c.T[2] * c.T[0] * c.T[1]));
-        atomicAdd(p0 + c.j0 * pr + c.k1, (float) (c.D[2] * c.T[0] * c.T[1]));
-        atomicAdd(p0 + c.j1 * pr + c.k0, (float) (c.T[2] * c.T[0] * c.D[1]));
-        atomicAdd(p0 + c.j1 * pr + c.k1, (float) (c.D[2] * c.T[0] * c.D[1]));
+        cic_add_pair<VEC>(p0 + c.j0 * pr, c.k0, c.k1, (float) (c.T[2] * c.T[0] * c.T[1]), (float) (c.D[2] * c.T[0] * c.T[1]));
+        cic_add_pair<VEC>(p0 + c.j1 * pr, c.k0, c.k1, (float) (c.T[2] * c.T[0] * c.D[1]), (float) (c.D[2] * c.T[0] * c.D[1]));
     }
     if (c.lx1 >= 0) {
         float *p1 = canvas + (size_t) c.lx1 * pl;
-        atomicAdd(p1 + c.j0 * pr + c.k0, (float) (c.T[2] * c.D[0] * c.T[1]));
-        atomicAdd(p1 + c.j0 * pr + c.k1, (float) (c.D[2] * c.D[0] * c.T[1]));
-        atomicAdd(p1 + c.j1 * pr + c.k0, (float) (c.T[2] * c.D[0] * c.D[1]));
-        atomicAdd(p1 + c.j1 * pr + c.k1, (float) (c.D[2] * c.D[0] * c.D[1]));
+        cic_add_pair<VEC>(p1 + c.j0 * pr, c.k0, c.k1, (float) (c.T[2] * c.D[0] * c.T[1]), (float) (c.D[2] * c.D[0] * c.T[1]));
+        cic_add_pair<VEC>(p1 + c.j1 * pr, c.k0, c.k1, (float) (c.T[2] * c.D[0] * c.D[1]), (float) (c.D[2] * c.D[0] * c.D[1]));
     }
 }
 
@@ -124,7 +144,11 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
-    FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np)));
+    static int vec = -1;          // FASTPM_B200_PAINT_VEC = 0 | 2 | 4 (default): width of the vector reductions
+    if (vec < 0) { const char *e = getenv("FASTPM_B200_PAINT_VEC"); vec = e ? atoi(e) : 4; }
+    if (vec >= 4) { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<4><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
+    else if (vec >= 2) { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<2><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
+    else { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<0><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -36,6 +36,8 @@ const char *fpm_version(void);
 int fpm_device_init(int device);                       /* libfastpm_init, libfastpm.c:10 */
 int fpm_device_count(void);
 int fpm_device_mem_info(size_t *free_bytes, size_t *total_bytes);
+/* diagnostic: out = { current device of this thread, the library's device, device owning ptr, memory type of ptr } */
+int fpm_debug_state(const void *ptr, int out[4]);
 void *fpm_malloc(size_t bytes);                        /* pm_alloc / store columns: memory.c:182 */
 void fpm_free(void *ptr);                              /* memory.c:260 */
 void *fpm_host_alloc_pinned(size_t bytes);
