@@ -131,6 +131,31 @@ def run_reference_arm(args):
     return 0
 
 
+def default_nc(args):
+    """nc = 1024 (the configuration BASELINE.json's metric is quoted on) needs 156 GB of HBM on one GPU (2 meshes of 34.9 GB +
+    80 B per particle) and, for the end-to-end leg, 73 GB of pinned host memory; otherwise the largest power-of-two case that fits."""
+    if args.impl == "reference":
+        return 1024
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")), args.gpus)
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = [int(l.split()[1]) for l in f if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail_kb = 0
+    try:
+        import ctypes as C
+        from fastpm_b200 import _lib
+        lib = _lib.require_device(int(os.environ.get("LOCAL_RANK", "0")))
+        free_b, total_b = C.c_size_t(), C.c_size_t()
+        lib.fpm_device_mem_info(C.byref(free_b), C.byref(total_b))
+        dev_free = free_b.value
+    except Exception:
+        dev_free = 0
+    need_dev = (2 * 34.9e9 + 80.0 * 1024 ** 3 * (1.0 if world == 1 else 1.3)) / world + 4e9
+    need_host = 73e9 / world + 16e9
+    return 1024 if (dev_free >= need_dev and avail_kb * 1024.0 >= need_host) else 512
+
+
 def workload_config(args):
     return {"workload": "nc=%d^3 particles, %d^3 mesh (B=%d), %s, %d PM steps linspace(0.1,1,%d), 2LPT ICs, P(k) each step" % (
         args.nc, args.nc * args.pm_nc_factor, args.pm_nc_factor, args.mode.upper(), args.steps, args.steps),
@@ -213,6 +238,13 @@ def run_ours(args):
     totals = (C.c_double * len(KCLASSES))()
     _lib.check(lib.fpm_prof_get(counts, totals, len(KCLASSES)))
     stages = {nm: {"launches": int(counts[i]), "ms": round(float(totals[i]), 3)} for i, nm in enumerate(KCLASSES)}
+    # launch by launch (issue order) for the last full step: which pass of which transform costs what
+    ncap = 4096
+    lcls = (C.c_int32 * ncap)()
+    lms = (C.c_double * ncap)()
+    nl = min(int(lib.fpm_prof_get_launches(lcls, lms, ncap)), ncap)
+    per_step = max(1, nl // K)
+    trace = [[KCLASSES[lcls[i]], round(lms[i], 3)] for i in range(max(0, nl - per_step), nl)]
     t_evolve = ms.value / 1e3
     value = Np * K / t_evolve
 
@@ -254,7 +286,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": round(avg_ms, 4)},
         "fft": {"gbs_6S": round(fft_gbs, 1), "frac_of_peak": round(fft_gbs / peak, 4), "ms_per_transform": round(t_transform_ms, 4),
                 "transforms": n_transforms},
-        "stages": stages,
+        "stages": stages, "last_step_launches": trace,
         "evolve_wall_s": round(t_wall, 4), "result_finite": finite,
         "pk_last_bin0": float(spectra[-1][1][0]) if spectra else None,
     }
@@ -279,7 +311,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nc", type=int, default=int(os.environ.get("FASTPM_B200_BENCH_NC", "512")))
+    ap.add_argument("--nc", type=int, default=int(os.environ.get("FASTPM_B200_BENCH_NC", "0")),
+                    help="particles per side; 0 = BASELINE.json's nc=1024 (2048^3 mesh) when device and host memory allow, else 512")
     ap.add_argument("--pm-nc-factor", type=int, default=2)
     ap.add_argument("--mode", default="cola", choices=["cola", "pm", "fastpm"])
     ap.add_argument("--ref-nc", type=int, default=128, help="particle grid of the bounded CPU sample")
@@ -288,6 +321,8 @@ def main():
     args = ap.parse_args()
     if args.steps < 2:
         args.steps = 2
+    if args.nc <= 0:
+        args.nc = default_nc(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

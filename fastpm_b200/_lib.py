@@ -15,12 +15,12 @@ ABI_SYMBOLS = [
     "fpm_malloc", "fpm_free", "fpm_host_alloc_pinned", "fpm_host_free_pinned",
     "fpm_memcpy_h2d", "fpm_memcpy_d2h", "fpm_memcpy_d2d", "fpm_memset", "fpm_sync",
     "fpm_timer_create", "fpm_timer_start", "fpm_timer_stop", "fpm_timer_elapsed_ms", "fpm_timer_destroy",
-    "fpm_kernel_launch_count", "fpm_prof_enable", "fpm_prof_reset", "fpm_prof_get",
+    "fpm_kernel_launch_count", "fpm_prof_enable", "fpm_prof_reset", "fpm_prof_get", "fpm_prof_get_launches",
     "fpm_mesh_create", "fpm_mesh_destroy", "fpm_mesh_info", "fpm_mesh_ktables_host",
-    "fpm_paint", "fpm_readout", "fpm_r2c", "fpm_r2c_ws", "fpm_c2r", "fpm_c2r_ws", "fpm_fft_set_generic", "fpm_transfer_for_kernel",
-    "fpm_apply_transfer", "fpm_apply_decic", "fpm_scale", "fpm_divide", "fpm_muladd", "fpm_set_mode",
+    "fpm_paint", "fpm_readout", "fpm_particle_grid_hint", "fpm_r2c", "fpm_r2c_ws", "fpm_c2r", "fpm_c2r_ws", "fpm_fft_set_generic", "fpm_transfer_for_kernel",
+    "fpm_apply_transfer", "fpm_apply_decic", "fpm_decic_defer", "fpm_decic_cancel", "fpm_scale", "fpm_divide", "fpm_muladd", "fpm_set_mode",
     "fpm_induce_correlation", "fpm_fill_whitenoise", "fpm_powerspectrum", "fpm_powerspectrum_sums",
-    "fpm_kick", "fpm_drift", "fpm_wrap", "fpm_wrap_check", "fpm_summary", "fpm_fill_grid", "fpm_lpt_evolve",
+    "fpm_kick", "fpm_drift", "fpm_update_fused", "fpm_wrap", "fpm_wrap_paint", "fpm_wrap_check", "fpm_summary", "fpm_fill_grid", "fpm_lpt_evolve",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     lib.fpm_timer_destroy.argtypes = [vp]
     lib.fpm_kernel_launch_count.restype = C.c_uint64
     lib.fpm_prof_get.argtypes = [vp, vp, i32]
+    lib.fpm_prof_get_launches.argtypes = [vp, vp, i32]
     lib.fpm_mesh_create.restype = vp
     lib.fpm_mesh_create.argtypes = [i32, dbl, i32, i32]
     lib.fpm_mesh_destroy.argtypes = [vp]
@@ -80,6 +81,8 @@ def load():
     lib.fpm_transfer_for_kernel.argtypes = [i32, i32, i32, C.POINTER(FpmTransfer)]
     lib.fpm_apply_transfer.argtypes = [vp, vp, vp, C.POINTER(FpmTransfer)]
     lib.fpm_apply_decic.argtypes = [vp, vp, vp]
+    lib.fpm_decic_defer.argtypes = [vp, vp]
+    lib.fpm_decic_cancel.argtypes = [vp]
     lib.fpm_scale.argtypes = [vp, vp, sz, dbl]
     lib.fpm_divide.argtypes = [vp, vp, sz, dbl]
     lib.fpm_r2c_ws.argtypes = [vp, vp, vp, vp, dbl]
@@ -92,7 +95,9 @@ def load():
     lib.fpm_powerspectrum_sums.argtypes = [vp, vp, i32, vp]
     lib.fpm_kick.argtypes = [vp, vp, vp, vp, vp, i64, i32, dbl, dbl, dbl, dbl, dbl]
     lib.fpm_drift.argtypes = [vp, vp, vp, vp, vp, i64, i32, dbl, dbl, dbl, dbl, dbl]
+    lib.fpm_update_fused.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
     lib.fpm_wrap.argtypes = [vp, i64, dbl]
+    lib.fpm_wrap_paint.argtypes = [vp, vp, vp, i64, dbl, vp, vp, i32]
     lib.fpm_summary.argtypes = [vp, i32, i32, i64, vp]
     lib.fpm_fill_grid.argtypes = [vp, vp, vp, i32, i32, i64, dbl, dbl]
     lib.fpm_lpt_evolve.argtypes = [vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl]

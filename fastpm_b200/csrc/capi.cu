@@ -37,12 +37,13 @@ void fpm_prof_end(int cls, cudaStream_t st)
 }
 
 // launchers defined in the kernel files
-int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
+int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, int *wrap_bad, cudaStream_t st);
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
 int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st);
 int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
+int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np, int nops, const double *ops, cudaStream_t st);
 int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2, long long np, cudaStream_t st);
 int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st);
 int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, double *host_out, cudaStream_t st);
@@ -56,6 +57,7 @@ int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const dou
 int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed, cudaStream_t st);
 int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st);
 void fpm_fft_force_generic(int on);
+void fpm_set_lagrangian_hint(int nc);
 
 // ------------------------------------------------------------------ runtime state
 static char g_error[1024] = "";
@@ -83,6 +85,27 @@ static int ensure_init()
 }
 
 cudaStream_t fpm_internal_stream(void) { ensure_init(); return g_stream; }
+
+// ------------------------------------------------------------------ deferred CIC deconvolution
+// fastpm_do_force deconvolves delta_k in place (transfer.c:78, solver.c:471) just before the FORCE/after event, whose usual
+// consumer is the P(k) handler.  fpm_decic_defer() records the request instead of sweeping the mesh; fpm_powerspectrum* then
+// folds the factor into its read (same roundings: the mode is rounded to float before it is squared), and EVERY other entry
+// point of this library that is handed the buffer applies the pending sweep first (lazy_touch), so the deferral is not
+// observable through the C ABI.  fpm_decic_cancel() drops it (the buffer is about to be released).
+static const fpm_mesh *g_lazy_mesh = NULL;
+static const char *g_lazy_buf = NULL;
+static size_t g_lazy_bytes = 0;
+int fpm_lazy_touch(const void *p, size_t bytes)
+{
+    if (!g_lazy_buf || !p) return 0;
+    const char *q = (const char *) p;
+    if (q + (bytes ? bytes : 1) <= g_lazy_buf || q >= g_lazy_buf + g_lazy_bytes) return 0;
+    const fpm_mesh *m = g_lazy_mesh;
+    float *buf = (float *) g_lazy_buf;
+    g_lazy_buf = NULL; g_lazy_mesh = NULL; g_lazy_bytes = 0;
+    return fpm_decic_launch(m, buf, buf, g_stream);
+}
+#define LAZY1(p) do { if (fpm_lazy_touch((p), 0)) return -1; } while (0)
 
 extern "C" {
 
@@ -145,7 +168,9 @@ void *fpm_malloc(size_t bytes)
     if (e != cudaSuccess) { fpm_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
     return p;
 }
-void fpm_free(void *ptr) { if (ptr) cudaFree(ptr); }
+void fpm_free(void *ptr) {
+    if (ptr && ptr == (void *) g_lazy_buf) { g_lazy_buf = NULL; g_lazy_mesh = NULL; g_lazy_bytes = 0; }
+ if (ptr) cudaFree(ptr); }
 
 void *fpm_host_alloc_pinned(size_t bytes)
 {
@@ -158,6 +183,7 @@ void fpm_host_free_pinned(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int fpm_memcpy_h2d(void *dst, const void *src, size_t bytes)
 {
+    if (fpm_lazy_touch(dst, bytes)) return -1;
     if (ensure_init()) return -1;
     FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
     FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
@@ -165,6 +191,7 @@ int fpm_memcpy_h2d(void *dst, const void *src, size_t bytes)
 }
 int fpm_memcpy_d2h(void *dst, const void *src, size_t bytes)
 {
+    if (fpm_lazy_touch(src, bytes)) return -1;
     if (ensure_init()) return -1;
     FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
     FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
@@ -172,12 +199,15 @@ int fpm_memcpy_d2h(void *dst, const void *src, size_t bytes)
 }
 int fpm_memcpy_d2d(void *dst, const void *src, size_t bytes)
 {
+    if (fpm_lazy_touch(src, bytes) || fpm_lazy_touch(dst, bytes)) return -1;
     if (ensure_init()) return -1;
     FPM_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
     return 0;
 }
 int fpm_memset(void *dst, int value, size_t bytes)
 {
+    if ((const char *) dst == g_lazy_buf && bytes >= g_lazy_bytes) { g_lazy_buf = NULL; g_lazy_mesh = NULL; g_lazy_bytes = 0; }
+    else if (fpm_lazy_touch(dst, bytes)) return -1;
     if (ensure_init()) return -1;
     FPM_CUDA_OK(cudaMemsetAsync(dst, value, bytes, g_stream));
     return 0;
@@ -234,6 +264,19 @@ int fpm_prof_get(int64_t *counts, double *total_ms, int ncls)
         if (c >= 0 && c < ncls) { counts[c]++; total_ms[c] += ms; }
     }
     return 0;
+}
+
+// per-launch list in issue order: cls[i], ms[i]; returns the number of launches recorded (may exceed max)
+int fpm_prof_get_launches(int32_t *cls, double *ms, int max)
+{
+    if (ensure_init()) return -1;
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    for (size_t i = 0; i < g_prof_used && (int) i < max; i++) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, g_prof_pairs[i].a, g_prof_pairs[i].b) != cudaSuccess) { cudaGetLastError(); f = 0; }
+        cls[i] = g_prof_pairs[i].cls; ms[i] = f;
+    }
+    return (int) g_prof_used;
 }
 
 // ------------------------------------------------------------------ mesh
@@ -344,11 +387,13 @@ int fpm_mesh_ktables_host(const fpm_mesh *m, float *host_out)
 // ------------------------------------------------------------------ paint / readout
 int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np, double M0, const float *mass, const float *field, int field_stride)
 {
-    return fpm_paint_launch(m, canvas, x, mass, M0, field, field_stride, np, g_stream);
+    LAZY1(canvas);
+    return fpm_paint_launch(m, canvas, x, mass, M0, field, field_stride, np, NULL, g_stream);
 }
 
 int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np, float *out, int out_stride, double prescale)
 {
+    LAZY1(canvas);
     return fpm_readout_launch(m, canvas, x, out, out_stride, prescale, np, g_stream);
 }
 
@@ -362,6 +407,7 @@ static void to_spec(const fpm_transfer *k, FpmTransferSpec *s)
 
 int fpm_r2c_ws(fpm_mesh *m, const float *real, float *work, float *cplx, double scale)
 {
+    LAZY1(real); LAZY1(work); LAZY1(cplx);
     if (m->geom.nranks != 1) { fpm_set_error("fpm_r2c: multi-GPU meshes go through the communicator entry points"); return -1; }
     if (work == cplx) { fpm_set_error("fpm_r2c: the work buffer and the k-space output must differ (the y-pass transposes)"); return -1; }
     float *peers[FPM_MAX_RANKS] = { cplx };
@@ -372,6 +418,7 @@ int fpm_r2c(fpm_mesh *m, float *real, float *cplx, double scale) { return fpm_r2
 
 int fpm_c2r_ws(fpm_mesh *m, const float *cplx, float *work, float *real, const fpm_transfer *kernel)
 {
+    LAZY1(cplx); LAZY1(work); LAZY1(real);
     if (m->geom.nranks != 1) { fpm_set_error("fpm_c2r: multi-GPU meshes go through the communicator entry points"); return -1; }
     if (work == cplx) { fpm_set_error("fpm_c2r: the work buffer and the k-space input must differ (the x-pass transposes)"); return -1; }
     float *peers[FPM_MAX_RANKS] = { work };
@@ -411,17 +458,19 @@ int fpm_fft_set_generic(int on) { fpm_fft_force_generic(on); return 0; }
 // ------------------------------------------------------------------ k-space sweeps
 int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fpm_transfer *kernel)
 {
+    LAZY1(from); LAZY1(to);
     FpmTransferSpec s; to_spec(kernel, &s);
     return fpm_transfer_launch(m, from, to, &s, g_stream);
 }
-int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to) { return fpm_decic_launch(m, from, to, g_stream); }
-int fpm_scale(const float *from, float *to, size_t nfloats, double value) { return fpm_scale_launch(from, to, nfloats, value, g_stream); }
-int fpm_divide(const float *from, float *to, size_t nfloats, double value) { return fpm_divide_launch(from, to, nfloats, value, g_stream); }
-int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign) { return fpm_muladd_launch(source, a, b, nfloats, sign, g_stream); }
-int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im) { return fpm_set_mode_launch(m, cplx, ix, iy, iz, re, im, g_stream); }
+int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to) { LAZY1(from); LAZY1(to); return fpm_decic_launch(m, from, to, g_stream); }
+int fpm_scale(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_scale_launch(from, to, nfloats, value, g_stream); }
+int fpm_divide(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_divide_launch(from, to, nfloats, value, g_stream); }
+int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign) { if (fpm_lazy_touch(source, 4 * nfloats) || fpm_lazy_touch(a, 4 * nfloats) || fpm_lazy_touch(b, 4 * nfloats)) return -1; return fpm_muladd_launch(source, a, b, nfloats, sign, g_stream); }
+int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im) { LAZY1(cplx); return fpm_set_mode_launch(m, cplx, ix, iy, iz, re, im, g_stream); }
 
 int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host, const double *p_host, int size)
 {
+    LAZY1(cplx);
     double *d_k = NULL, *d_p = NULL;
     FPM_CUDA_OK(cudaMalloc(&d_k, sizeof(double) * size));
     FPM_CUDA_OK(cudaMalloc(&d_p, sizeof(double) * size));
@@ -433,10 +482,12 @@ int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host,
     return rc;
 }
 
-int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed) { return fpm_whitenoise_launch(m, real, seed, g_stream); }
+int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed) { LAZY1(real); return fpm_whitenoise_launch(m, real, seed, g_stream); }
 
 int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, double *sums_host)
 {
+    if ((const char *) cplx == g_lazy_buf && m == g_lazy_mesh && !decic) decic = 1;      // pending deconvolution folded into the read
+    else LAZY1(cplx);
     const int nbins = m->geom.n / 2;
     double *d_out = NULL;
     FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
@@ -465,6 +516,22 @@ int fpm_powerspectrum(const fpm_mesh *m, const float *cplx, int decic, double *k
     return 0;
 }
 
+int fpm_decic_defer(const fpm_mesh *m, float *cplx)
+{
+    if (ensure_init()) return -1;
+    if (g_lazy_buf && fpm_lazy_touch(g_lazy_buf, 0)) return -1;           // one pending buffer at a time
+    if (fpm_lazy_touch(cplx, 0)) return -1;
+    int64_t info[16];
+    fpm_mesh_info(m, info);
+    g_lazy_mesh = m; g_lazy_buf = (const char *) cplx; g_lazy_bytes = (size_t) info[1] * sizeof(float);
+    return 0;
+}
+int fpm_decic_cancel(const float *cplx)
+{
+    if ((const char *) cplx == g_lazy_buf) { g_lazy_buf = NULL; g_lazy_mesh = NULL; g_lazy_bytes = 0; }
+    return 0;
+}
+
 // ------------------------------------------------------------------ particles
 int fpm_kick(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, int64_t np,
              int forcemode, double dda, double q1, double q2, double Dv1, double Dv2)
@@ -479,6 +546,12 @@ int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx
 {
     if (forcemode >= 2 && (!dx1 || (forcemode != 4 && !dx2))) { fpm_set_error("drift mode %d needs the dx1/dx2 columns", forcemode); return -1; }
     return fpm_drift_launch(x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, forcemode, np, g_stream);
+}
+
+int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, const float *dx2, int64_t np, int nops, const double *ops)
+{
+    if (ensure_init()) return -1;
+    return fpm_fused_update_launch(x, v, acc, dx1, dx2, np, nops, ops, g_stream);
 }
 
 // The "too far" flag of the previous wrap is examined when the next one is issued (or by fpm_wrap_check), so that
@@ -516,6 +589,51 @@ int fpm_wrap(double *x, int64_t np, double boxsize)
     FPM_CUDA_OK(cudaMemcpyAsync(h_wrap_bad, d_wrap_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     return 0;
 }
+
+// the device flag of "a particle is too far" for kernels of other files that wrap on the way (comm.cu: classify); the
+// caller enqueues its kernel and then fpm_wrap_flag_fetch() so that the next fpm_wrap / fpm_wrap_check sees the result
+int *fpm_wrap_flag_device(void)
+{
+    if (ensure_init()) return NULL;
+    if (!d_wrap_bad) {
+        if (cudaMalloc(&d_wrap_bad, sizeof(int)) != cudaSuccess) return NULL;
+        if (cudaHostAlloc(&h_wrap_bad, sizeof(int), cudaHostAllocDefault) != cudaSuccess) return NULL;
+        *h_wrap_bad = 0;
+        cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream);
+    }
+    return d_wrap_bad;
+}
+int fpm_wrap_flag_fetch(void)
+{
+    FPM_CUDA_OK(cudaMemcpyAsync(h_wrap_bad, d_wrap_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    return 0;
+}
+
+// fastpm_store_wrap + fastpm_paint_local in one pass over the positions (see cic_paint_kernel<.., WRAP>)
+int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, double M0, const float *mass, const float *field, int field_stride)
+{
+    LAZY1(canvas);
+    if (ensure_init()) return -1;
+    if (!d_wrap_bad) {
+        FPM_CUDA_OK(cudaMalloc(&d_wrap_bad, sizeof(int)));
+        FPM_CUDA_OK(cudaHostAlloc(&h_wrap_bad, sizeof(int), cudaHostAllocDefault));
+        *h_wrap_bad = 0;
+        FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
+    }
+    if (*h_wrap_bad) {
+        FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+        *h_wrap_bad = 0;
+        FPM_CUDA_OK(cudaMemsetAsync(d_wrap_bad, 0, sizeof(int), g_stream));
+        fpm_set_error("A particle is too far from the bounds. Wrapping failed. (store.c:460-471)");
+        return -1;
+    }
+    if (fpm_paint_launch(m, canvas, x, mass, M0, field, field_stride, np, d_wrap_bad, g_stream)) return -1;
+    FPM_CUDA_OK(cudaMemcpyAsync(h_wrap_bad, d_wrap_bad, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    return 0;
+}
+
+// performance hint: stores of exactly nc^3 particles are in fastpm_store_fill order (store.c:756-793); 0 clears it
+int fpm_particle_grid_hint(int nc) { fpm_set_lagrangian_hint(nc); return 0; }
 
 int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out)
 {

@@ -127,14 +127,17 @@ static int mesh_barrier(FpmMesh *m, cudaStream_t st) { (void) m; return fpm_xbar
 // ------------------------------------------------------------------ distributed transforms
 // peers[d] = rank d's buffer (peers[rank] = the local one); the FFT code (fft.cu) puts a barrier before and after
 // the transposing pass through m->barrier.
+int fpm_lazy_touch(const void *p, size_t bytes);      // capi.cu: applies a deferred deconvolution of that buffer first
 extern "C" int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale)
 {
+    if (fpm_lazy_touch(real, 0) || fpm_lazy_touch(cplx_peers[m->geom.rank], 0)) return -1;
     m->barrier = mesh_barrier;
     return fpm_fft_r2c(m, real, real, cplx_peers, (float) scale, comm_stream());
 }
 
 extern "C" int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel)
 {
+    if (fpm_lazy_touch(cplx, 0) || fpm_lazy_touch(real_peers[m->geom.rank], 0)) return -1;
     m->barrier = mesh_barrier;
     FpmTransferSpec s;
     if (kernel && kernel->active) {
@@ -187,12 +190,29 @@ extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const
 
 // ------------------------------------------------------------------ particle migration
 // owner slab of a position: floor(x * inv_cell) mod N, divided by the slab thickness (pm_pos_to_rank, pmpfft.c:344-368)
-__global__ void __launch_bounds__(256) classify_kernel(const FpmGeom g, const double *__restrict__ x, long long np,
-        int *__restrict__ send_count, int *__restrict__ send_idx, int cap, unsigned char *__restrict__ leaver, int *__restrict__ overflow)
+// wrap_bad != NULL: fastpm_store_wrap (store.c:447-475) folded in -- same operations as wrap_kernel (particles.cu), positions
+// written back only where they changed
+__global__ void __launch_bounds__(256) classify_kernel(const FpmGeom g, double *__restrict__ x, long long np,
+        int *__restrict__ send_count, int *__restrict__ send_idx, int cap, unsigned char *__restrict__ leaver, int *__restrict__ overflow,
+        int *__restrict__ wrap_bad)
 {
     long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long) gridDim.x * blockDim.x;
     for (; i < np; i += stride) {
+        if (wrap_bad) {
+            const double L = g.boxsize;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double xi = x[3 * i + d];
+                if (xi >= 0 && xi < L) continue;
+                const double nwrap = (double) abs((int) (xi / L));
+                double x1 = remainder(xi, L);
+                while (x1 < 0) x1 += L;
+                while (x1 > L) x1 -= L;
+                if (nwrap > 10000) atomicExch(wrap_bad, 1);
+                x[3 * i + d] = x1;
+            }
+        }
         int ix = (int) floor(x[3 * i] * g.inv_cellsize);
         ix %= g.n; if (ix < 0) ix += g.n;
         const int dest = ix / g.nxl;
@@ -276,7 +296,9 @@ extern "C" void fpm_migrate_destroy(void)
 }
 
 // step 1: classify; returns the per-destination counts on the host (synchronises the stream)
-extern "C" int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t np, int *send_count_host)
+extern "C" int *fpm_wrap_flag_device(void);
+extern "C" int fpm_wrap_flag_fetch(void);
+extern "C" int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap)
 {
     cudaStream_t st = comm_stream();
     const int G = m->geom.nranks;
@@ -284,8 +306,11 @@ extern "C" int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t 
     FPM_CUDA_OK(cudaMemsetAsync(g_mig.d_overflow, 0, sizeof(int), st));
     if (np > g_mig.leaver_cap) { fpm_set_error("migrate: np exceeds the allocated particle capacity"); return -1; }
     if (np > 0) {
-        classify_kernel<<<148 * 8, 256, 0, st>>>(m->geom, x, np, g_mig.d_send_count, g_mig.d_send_idx, g_mig.cap, g_mig.d_leaver, g_mig.d_overflow);
+        int *bad = wrap ? fpm_wrap_flag_device() : NULL;
+        if (wrap && !bad) { fpm_set_error("migrate: no wrap flag"); return -1; }
+        classify_kernel<<<148 * 8, 256, 0, st>>>(m->geom, x, np, g_mig.d_send_count, g_mig.d_send_idx, g_mig.cap, g_mig.d_leaver, g_mig.d_overflow, bad);
         FPM_CHECK_LAUNCH();
+        if (wrap && fpm_wrap_flag_fetch()) return -1;
     }
     int tmp[FPM_MAX_RANKS + 1];
     FPM_CUDA_OK(cudaMemcpyAsync(tmp, g_mig.d_send_count, sizeof(int) * FPM_MAX_RANKS, cudaMemcpyDeviceToHost, st));

@@ -116,7 +116,8 @@ template <int R> struct Log2Of { static constexpr int v = (R >= 16) ? 4 : (R >= 
 //   X2 read    rows b*R3 + k            -> b*R3 + (k ^ (b & MASK))
 // Input: v[k] = element t + k*M1 of the column.  Output: v[i*R3 + q3] = frequency q1 + R1*q2 + R1*R2*q3 with
 // (q1, q2) = ((t + i*T) / R2, (t + i*T) % R2).
-template <int R1, int R2, int R3, int K>
+// TWS: the twiddle table lives in shared memory (copied there once per CTA) instead of being read through L1
+template <int R1, int R2, int R3, int K, bool TWS = false>
 struct Fft3 {
     using C = TmaCfg<R1, R2, R3>;
     static constexpr int N = C::N, E = C::E, T = C::T, M1 = C::M1, M2 = C::M2;
@@ -150,7 +151,7 @@ struct Fft3 {
         fft_reg<R1>(v);
         #pragma unroll
         for (int q = 1; q < R1; q++) {
-            const float2 w = __ldg(tw1 + q * t);
+            const float2 w = TWS ? tw1[q * t] : __ldg(tw1 + q * t);
             const float2 y = v[bitrev<R1>(q)];
             v[bitrev<R1>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
         }
@@ -184,7 +185,7 @@ struct Fft3 {
             fft_reg<R2>(w2);
             #pragma unroll
             for (int q = 1; q < R2; q++) {
-                const float2 w = __ldg(tw + q * tw2i);
+                const float2 w = TWS ? tw[q * tw2i] : __ldg(tw + q * tw2i);
                 const float2 y = w2[bitrev<R2>(q)];
                 w2[bitrev<R2>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
             }

@@ -42,6 +42,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const float2 *A = reinterpret_cast<const float2 *>(smem_raw);            // [N][K] complex, written by TMA
     float *B = reinterpret_cast<float *>(smem_raw + (size_t) N * K * 8);     // [N][K] floats, swizzled rows
+    float2 *TW = reinterpret_cast<float2 *>(smem_raw + (size_t) N * K * 12); // [N] exp(-2 pi i t / N)
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
@@ -54,6 +55,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < N; i += T * K) TW[i] = __ldg(a.tw + i);
     __syncthreads();
 
     int tile = blockIdx.x;
@@ -67,81 +69,34 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
 
     // per-thread constant addresses
     const float2 *Ard = A + t * K + c;                                                   // + k*M1*K
-    Fft3<R1, R2, R3, K> fx(B, t, c, a.tw);
+    Fft3<R1, R2, R3, K, true> fx(B, t, c, TW);
     const bool single = (a.rows_per_rank == N);
     const int h = N / 2;
+
+    // The gravity kernel, specialised for the tile pass (operations of fpm_apply_transfer, mesh.cuh, i.e. of
+    // transfer.c:154-186 + gravity.c:17,21-64), kept to ~20 instructions per mode:
+    //   * s = kk[ix] + kk[iy] + kk[iz] is a sum of three floats whose exponents differ by < 2^20: exact in double in any
+    //     order; it is split into a float pair (s_hi, s_lo);
+    //   * the reference's (float)((double) v * (1 / s)) is the correctly rounded float quotient v / s up to double
+    //     rounding; here q = v * rcp(s_hi), corrected once with the exact remainder v - q * (s_hi + s_lo): the same float
+    //     except when v / s lies within ~2^-46 (relative) of a rounding boundary -- about one mode in 4 million then
+    //     differs by one float ulp, far below the round-off of the FFT itself;
+    //   * the i*k_d product of two floats rounded to float is exactly what (float)((double) v * (double) kf) yields;
+    //   * the modes the reference sets to zero (s == 0; gradient of a self-conjugate mode) are patched after the loop.
+    const bool xf = a.xfer.active;
 
     #pragma unroll 1
     for (; tile < ntiles; tile += gridDim.x) {
         const int o = tile / a.ntile_k, kz0 = (tile - o * a.ntile_k) * K;
         float2 v[E];
 
-        // The gravity kernel, specialised for the tile pass (same operations and roundings as fpm_apply_transfer,
-        // mesh.cuh): sum_d kk[i_d] is accumulated x, y, z in double like the reference (transfer.c:171-174); 1/sum is
-        // the correctly rounded double reciprocal; the i*k_d product of two floats rounded to float is exactly what
-        // the reference's (float)((double) v * (double) kf) yields, so it is done as a float multiply.
-        const bool xf = a.xfer.active;
-        const int iy = a.outer0 + o, iz = kz0 + c;
-        const bool pad = iz > h;
-        const float *kkt = a.xfer.potorder == 1 ? a.kt.kk_finite : (a.xfer.potorder == 2 ? a.kt.kk_finite2 : a.kt.kk);
-        const float *kft = a.xfer.gradorder == 0 ? a.kt.k : a.kt.k_finite;
-        double kky = 0, kkz = 0;
-        float gf[2] = { 1.f, 1.f };
-        bool gx[2] = { false, false };
-        bool sc_yz = false;
-        float sgn = a.xfer.negate ? -1.f : 1.f;
-        if (xf && !pad) {
-            kky = (double) __ldg(kkt + iy); kkz = (double) __ldg(kkt + iz);
-            sc_yz = a.xfer.zero_selfconj && (iy == 0 || iy == h) && (iz == 0 || iz == h);
-            #pragma unroll
-            for (int g = 0; g < 2; g++) {
-                if (g < a.xfer.ngrad) {
-                    const int dir = a.xfer.graddir[g];
-                    gx[g] = (dir == 0);
-                    gf[g] = dir == 1 ? __ldg(kft + iy) : (dir == 2 ? __ldg(kft + iz) : 1.f);
-                }
-            }
-        }
-        const int ngrad = a.xfer.ngrad;
-        const bool has_pot = a.xfer.potorder >= 0;
-        const bool has_scale = a.xfer.scale != 1.0;
-
-        // ---- tile has landed: pull this thread's E elements (rows t + k*M1) out of A
+        // ---- tile has landed: pull this thread's E elements (rows t + k*M1) out of A, then let the next tile's TMA
+        //      start at once: everything below overlaps with that load
         mbar_wait(&bar, phase);
         phase ^= 1;
         #pragma unroll
-        for (int k = 0; k < E; k++) {
-            float2 x = Ard[k * M1 * K];
-            if (xf && !pad) {
-                const int ix = t + k * M1;
-                if (has_pot) {
-                    double sum = 0;
-                    sum += (double) __ldg(kkt + ix); sum += kky; sum += kkz;
-                    const double inv = (sum != 0) ? __drcp_rn(sum) : 0.0;
-                    x.x = sgn * (float) ((double) x.x * inv);
-                    x.y = sgn * (float) ((double) x.y * inv);
-                } else { x.x *= sgn; x.y *= sgn; }
-                if (ngrad > 0) {
-                    const bool zero = sc_yz && (ix == 0 || ix == h);
-                    const float kfx = __ldg(kft + ix);
-                    #pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        if (g < ngrad) {
-                            const float f = zero ? 0.f : (gx[g] ? kfx : gf[g]);
-                            const float re = -__fmul_rn(x.y, f), im = __fmul_rn(x.x, f);
-                            x.x = re; x.y = im;
-                        }
-                    }
-                }
-                if (has_scale) { x.x = (float) ((double) x.x * a.xfer.scale); x.y = (float) ((double) x.y * a.xfer.scale); }
-            }
-            if (a.conj) x.y = -x.y;
-            v[k] = x;
-        }
-
-        // ---- three register stages with two exchanges through B; the next tile's TMA is issued as soon as every
-        //      thread has left buffer A (first barrier of the first exchange)
-        fx.run(v, [&]() {
+        for (int k = 0; k < E; k++) v[k] = Ard[k * M1 * K];
+        auto prefetch_next = [&]() {
             if (tid == 0) {
                 const int nxt = tile + gridDim.x;
                 if (nxt < ntiles) {
@@ -151,7 +106,67 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
                     for (int r0 = 0; r0 < N; r0 += BOX) tma_load_3d(const_cast<float2 *>(A) + (size_t) r0 * K, &tmap, &bar, 2 * kz2, r0, o2);
                 }
             }
-        });
+        };
+        if (a.early) { __syncthreads(); prefetch_next(); }
+
+        const int iy = a.outer0 + o, iz = kz0 + c;
+        if (xf && iz <= h) {
+            const float *kkt = a.xfer.potorder == 1 ? a.kt.kk_finite : (a.xfer.potorder == 2 ? a.kt.kk_finite2 : a.kt.kk);
+            const float *kft = a.xfer.gradorder == 0 ? a.kt.k : a.kt.k_finite;
+            const int ngrad = a.xfer.ngrad;
+            const bool has_pot = a.xfer.potorder >= 0, has_scale = a.xfer.scale != 1.0, negate = a.xfer.negate != 0;
+            const bool sc_yz = (iy == 0 || iy == h) && (iz == 0 || iz == h);
+            if (has_pot) {
+                const double yz = (double) __ldg(kkt + iy) + (double) __ldg(kkt + iz);
+                #pragma unroll
+                for (int k = 0; k < E; k++) {
+                    const double sd = yz + (double) __ldg(kkt + t + k * M1);
+                    const float s_hi = (float) sd;
+                    const float s_lo = (float) (sd - (double) s_hi);
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s_hi));
+                    const float qx = __fmul_rn(v[k].x, r), qy = __fmul_rn(v[k].y, r);
+                    const float rx = __fmaf_rn(-qx, s_lo, __fmaf_rn(-qx, s_hi, v[k].x));
+                    const float ry = __fmaf_rn(-qy, s_lo, __fmaf_rn(-qy, s_hi, v[k].y));
+                    v[k].x = __fmaf_rn(rx, r, qx);
+                    v[k].y = __fmaf_rn(ry, r, qy);
+                }
+                if (iy == 0 && iz == 0 && t == 0) v[0] = make_float2(0.f, 0.f);          // s == 0 (transfer.c:176-181)
+            }
+            if (negate) {
+                #pragma unroll
+                for (int k = 0; k < E; k++) { v[k].x = -v[k].x; v[k].y = -v[k].y; }
+            }
+            #pragma unroll
+            for (int g = 0; g < 2; g++) {
+                if (g < ngrad) {
+                    // factor of element k: kf[gbase + k * gstride]  (direction 0 runs along the rows of the tile)
+                    const int dir = a.xfer.graddir[g];
+                    const int gbase = dir == 0 ? t : (dir == 1 ? iy : iz), gstride = dir == 0 ? M1 : 0;
+                    #pragma unroll
+                    for (int k = 0; k < E; k++) {
+                        const float f = __ldg(kft + gbase + k * gstride);
+                        const float re = -__fmul_rn(v[k].y, f), im = __fmul_rn(v[k].x, f);
+                        v[k].x = re; v[k].y = im;
+                    }
+                    if (a.xfer.zero_selfconj && sc_yz && t == 0) {                           // gravity.c:48-56: ix in {0, N/2}
+                        v[0] = make_float2(0.f, 0.f);
+                        v[E / 2] = make_float2(0.f, 0.f);
+                    }
+                }
+            }
+            if (has_scale) {
+                #pragma unroll
+                for (int k = 0; k < E; k++) { v[k].x = (float) ((double) v[k].x * a.xfer.scale); v[k].y = (float) ((double) v[k].y * a.xfer.scale); }
+            }
+        }
+        if (a.conj) {
+            #pragma unroll
+            for (int k = 0; k < E; k++) v[k].y = -v[k].y;
+        }
+
+        // ---- three register stages with two exchanges through B
+        fx.run(v, [&]() { if (!a.early) prefetch_next(); });
 
         // ---- store: frequency kf = q1 + R1*q2 + R1*R2*q3, K*8 B contiguous per row
         const size_t obase = (size_t) (a.dst_ooffset + o) * a.dst_ostride + kz0 + c;
@@ -203,7 +218,7 @@ template <int R1, int R2, int R3, int K>
 static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cudaStream_t st)
 {
     using C = TmaCfg<R1, R2, R3>;
-    const size_t smem = (size_t) C::N * K * 8 + (size_t) C::N * K * 4;
+    const size_t smem = (size_t) C::N * K * 8 + (size_t) C::N * K * 4 + (size_t) C::N * 8;
     static bool attr = false;
     if (!attr) {
         FPM_CUDA_OK(cudaFuncSetAttribute(fft_tma_kernel<R1, R2, R3, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -251,6 +266,9 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
     TmaPassArgs a = args;
+    static int early = -1;        // FASTPM_B200_TMA_EARLY=1: issue the next tile's TMA right after the tile has been read (one more barrier)
+    if (early < 0) { const char *e = getenv("FASTPM_B200_TMA_EARLY"); early = e ? atoi(e) : 0; }
+    a.early = early == 1 || (early == 2 && args.xfer.active);
     a.nouter = nouter;
     a.ntile_k = (n / 2 + 1 + K - 1) / K;
     switch (n) {

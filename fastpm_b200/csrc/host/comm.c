@@ -24,7 +24,7 @@ int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
 int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank);
 int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void *pack);
-int fpm_migrate_classify(const fpm_mesh *m, const double *x, int64_t np, int *send_count_host);
+int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap);
 int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes);
 int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host);
 int fpm_migrate_fill_column(void *col, int elsize, int nholes);
@@ -202,6 +202,7 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
 {
     (void) comm;
     if (g_size == 1) return 0;                            /* one slab owns every particle */
+    fpm_store_flush(p);
     if (target_func != (fastpm_store_target_func) FastPMTargetPM)
         fastpm_raise(-1, "fastpm_b200: fastpm_store_decompose supports the PM target (x-slabs) only\n");
     PM *pm = data;
@@ -225,7 +226,9 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
 
     int send[MAXR], all[MAXR * MAXR];
     memset(send, 0, sizeof(send));
-    if (fpm_migrate_classify(pm->mesh, (const double *) p->x, (int64_t) p->np, send) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+    const int wrap = (fpm_pending_wrap == p);              /* fastpm_decompose left the periodic wrap to the classification pass */
+    if (wrap) fpm_pending_wrap = NULL;
+    if (fpm_migrate_classify(pm->mesh, (double *) p->x, (int64_t) p->np, send, wrap) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
     allgather(send, sizeof(int) * MAXR, all);
     int64_t nsend = 0, nrecv = 0;
     for (int r = 0; r < g_size; r++) { if (r != g_rank) { nsend += send[r]; nrecv += all[r * MAXR + g_rank]; } }

@@ -142,12 +142,47 @@ void fpm_drift_factors_at(FastPMDriftFactor *drift, double a_x, double af, doubl
     *dyyy = f[0] - i[0]; *da1 = f[1] - i[1]; *da2 = f[2] - i[2];
 }
 
+/* ------------------------------------------------------------------ deferred in-place updates
+ * fastpm_solver_evolve issues K K D D between two force evaluations (solver.c:283-356).  When a kick or drift is in place
+ * (pi == po) it is queued here instead of launched; the queue is applied by ONE kernel (fpm_update_fused: same operations,
+ * order and roundings, v and x in registers in between) as soon as anything else touches the store -- every function of this
+ * layer that reads or writes store columns calls fpm_store_flush first, and fastpm_emit_event flushes before it calls a
+ * handler.  The time stamps meta.a_x / meta.a_v are updated at once, like the reference's. */
+static struct { FastPMStore *p; int n; double ops[8][7]; } pending_updates;
+
+void fpm_store_flush(FastPMStore *p)
+{
+    if (pending_updates.n == 0 || (p != NULL && p != pending_updates.p)) return;
+    FastPMStore *q = pending_updates.p;
+    const int n = pending_updates.n;
+    pending_updates.n = 0; pending_updates.p = NULL;
+    FPM_MUST(fpm_update_fused((double *) q->x, (float *) q->v, (const float *) q->acc, (const float *) q->dx1, (const float *) q->dx2,
+                              (int64_t) q->np, n, &pending_updates.ops[0][0]));
+}
+
+static int defer_update(FastPMStore *p, int kind, int mode, double f0, double f1, double f2, double f3, double f4)
+{
+    static int enabled = -1;
+    if (enabled < 0) enabled = getenv("FASTPM_B200_NO_FUSED_UPDATE") ? 0 : 1;
+    if (!enabled) return 0;
+    if (pending_updates.n && pending_updates.p != p) fpm_store_flush(NULL);
+    if (pending_updates.n == 8) fpm_store_flush(NULL);
+    double *o = pending_updates.ops[pending_updates.n++];
+    pending_updates.p = p;
+    o[0] = kind; o[1] = mode; o[2] = f0; o[3] = f1; o[4] = f2; o[5] = f3; o[6] = f4;
+    return 1;
+}
+
 /* fastpm_kick_store / fastpm_drift_store (factors.c:176-197, 374-392): pi and po may be the same store or two
  * stores with separate v / x columns (snapshots, solver.c:647-702) */
 void fastpm_kick_store(FastPMKickFactor *kick, FastPMStore *pi, FastPMStore *po, double af)
 {
     double dda, Dv1, Dv2;
     fpm_kick_factors_at(kick, pi->meta.a_v, af, &dda, &Dv1, &Dv2);
+    const int cola = kick->forcemode == FASTPM_FORCE_COLA;
+    if (cola && (!pi->dx1 || !pi->dx2)) fastpm_raise(-1, "COLA kick needs the dx1 and dx2 columns (solver.c:84-88)\n");
+    if (pi == po && pi->v == po->v && defer_update(pi, 0, cola, dda, kick->q1, kick->q2, Dv1, Dv2)) { po->meta.a_v = af; return; }
+    fpm_store_flush(NULL);
     FPM_MUST(fpm_kick((float *) po->v, (const float *) pi->v, (const float *) pi->acc, (const float *) pi->dx1, (const float *) pi->dx2,
                       (int64_t) pi->np, (int) kick->forcemode, dda, kick->q1, kick->q2, Dv1, Dv2));
     po->meta.a_v = af;
@@ -158,6 +193,10 @@ void fastpm_drift_store(FastPMDriftFactor *drift, FastPMStore *pi, FastPMStore *
     double dyyy, da1, da2;
     fpm_drift_factors_at(drift, pi->meta.a_x, af, &dyyy, &da1, &da2);
     if (pi->pgdc) fastpm_raise(-1, "fastpm_b200: the PGD correction column is out of scope of this build (pgdcorrection.c).\n");
+    const int mode = (int) drift->forcemode;
+    if (mode >= 2 && (!pi->dx1 || (mode != 4 && !pi->dx2))) fastpm_raise(-1, "drift mode %d needs the dx1/dx2 columns\n", mode);
+    if (pi == po && pi->x == po->x && defer_update(pi, 1, mode, dyyy, da1, da2, drift->Dv1, drift->Dv2)) { po->meta.a_x = af; return; }
+    fpm_store_flush(NULL);
     FPM_MUST(fpm_drift((double *) po->x, (const double *) pi->x, (const float *) pi->v, (const float *) pi->dx1, (const float *) pi->dx2,
                        (int64_t) pi->np, (int) drift->forcemode, dyyy, da1, da2, drift->Dv1, drift->Dv2));
     po->meta.a_x = af;

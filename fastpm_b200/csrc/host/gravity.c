@@ -37,6 +37,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
                                  FastPMKernelType kernel, FastPMFloat *delta_k, double Time)
 {
     (void) Time;
+    fpm_store_flush(NULL);
     if (dealias != FASTPM_SOFTENING_NONE) fastpm_raise(-1, "fastpm_b200: force softening type %d is not implemented (default is none)\n", (int) dealias);
     if (fastpm->cosmology->ncdm_linearresponse) fastpm_raise(-1, "fastpm_b200: ncdm linear response is out of scope\n");
     CLOCK(paint);

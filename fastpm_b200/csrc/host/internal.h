@@ -60,6 +60,12 @@ void fpm_mesh_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale);
 void fpm_mesh_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel);
 void fpm_mesh_readout(PM *pm, FastPMFloat *canvas, const double *x, int64_t np, float *out, int stride, double prescale);
 
+/* solver.c: store whose wrap is folded into the next fastpm_paint_local */
+extern FastPMStore *fpm_pending_wrap;
+
+/* factors.c: applies the queued in-place kicks / drifts of p (NULL: of any store); call before touching store columns */
+void fpm_store_flush(FastPMStore *p);
+
 /* numerics.c */
 typedef double (*fpm_func1)(double x, void *params);
 double fpm_integrate(fpm_func1 f, void *params, double a, double b, double epsabs, double epsrel, int order);

@@ -25,6 +25,7 @@ void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type,
 
 void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
 {
+    fpm_store_flush(p);
     const float *fcol = NULL; int fstride = 1;
     if (field.attribute) {
         int ci = fastpm_store_find_column_id(p, field.attribute);
@@ -32,11 +33,18 @@ void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore
         fcol = (const float *) p->columns[ci] + field.memb;
         fstride = (int) p->_column_info[ci].nmemb;
     }
+    if (fpm_pending_wrap == p && size == p->np) {
+        fpm_pending_wrap = NULL;
+        if (fpm_wrap_paint(painter->pm->mesh, canvas, (double *) p->x, (int64_t) size, p->meta.M0, p->mass, fcol, fstride) != 0)
+            fastpm_raise(-1, "%s\n", fpm_last_error());
+        return;
+    }
     FPM_MUST(fpm_paint(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) size, p->meta.M0, p->mass, fcol, fstride));
 }
 
 void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
 {
+    fpm_store_flush(p);
     int ci = fastpm_store_find_column_id(p, field.attribute);
     if (ci < 0 || !p->columns[ci] || p->_column_info[ci].from_double == NULL) fastpm_raise(-1, "readout: target column is not an allocated float column\n");
     float *out = (float *) p->columns[ci] + field.memb;

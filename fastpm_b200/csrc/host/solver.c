@@ -140,6 +140,7 @@ void fastpm_solver_setup_lpt(FastPMSolver *fastpm, enum FastPMSpecies species, F
 {
     FastPMStore *p = fastpm_solver_get_species(fastpm, species);
     if (!p) fastpm_raise(-1, "Species requested (%d) does not exist", species);
+    fpm_store_flush(NULL);
     PM *pm = fastpm->lptpm;
     FastPMConfig *config = fastpm->config;
     if (species == FASTPM_SPECIES_CDM) {
@@ -197,6 +198,7 @@ static void do_force(FastPMSolver *fastpm, FastPMTransition *trans)
     fastpm_emit_event(fastpm->event_handlers, FASTPM_EVENT_FORCE, FASTPM_EVENT_STAGE_BEFORE, (FastPMEvent *) event, fastpm);
     ENTER(force);
     fastpm_solver_compute_force(fastpm, pm, painter, fastpm->config->SOFTENING_TYPE, fastpm->config->KERNEL_TYPE, delta_k, trans->a.f);
+    if (fpm_pending_wrap) { FastPMStore *pw = fpm_pending_wrap; fpm_pending_wrap = NULL; fastpm_store_wrap(pw, pm->BoxSize); }
     LEAVE(force);
     ENTER(event);
     /* solver.c:471: the event sees the CIC-compensated density.  Nobody else reads delta_k afterwards, so the
@@ -205,8 +207,12 @@ static void do_force(FastPMSolver *fastpm, FastPMTransition *trans)
     for (FastPMEventHandler *h = fastpm->event_handlers; h; h = h->next)
         if (h->stage == FASTPM_EVENT_STAGE_AFTER && !strcmp(h->type, FASTPM_EVENT_FORCE)) has_after = 1;
     if (has_after) {
-        fastpm_apply_decic_transfer(pm, delta_k, delta_k);
+        /* deferred: fastpm_powerspectrum_init_from_delta folds the factor into its read; any other use of the buffer through
+         * this library applies the sweep first (fpm_decic_defer, include/fastpm_b200.h) */
+        if (getenv("FASTPM_B200_NO_LAZY_DECIC")) fastpm_apply_decic_transfer(pm, delta_k, delta_k);
+        else FPM_MUST(fpm_decic_defer(pm->mesh, delta_k));
         fastpm_emit_event(fastpm->event_handlers, FASTPM_EVENT_FORCE, FASTPM_EVENT_STAGE_AFTER, (FastPMEvent *) event, fastpm);
+        FPM_MUST(fpm_decic_cancel(delta_k));
     }
     LEAVE(event);
     pm_free(pm, delta_k);
@@ -272,6 +278,7 @@ static void do_interpolation(FastPMSolver *fastpm, FastPMDriftFactor *drift, Fas
 void fastpm_solver_evolve(FastPMSolver *fastpm, double *time_step, int nstep)
 {
     /* warm-up: clear acc (solver.c:378-391) */
+    fpm_store_flush(NULL);
     for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
         FastPMStore *p = fastpm_solver_get_species(fastpm, si);
         if (p) FPM_MUST(fpm_memset(p->acc, 0, sizeof(p->acc[0]) * p->np));
@@ -306,14 +313,36 @@ void fastpm_solver_evolve(FastPMSolver *fastpm, double *time_step, int nstep)
     fastpm_drift_init(&drift, fastpm, a1, a1, a1);
     do_interpolation(fastpm, &drift, &kick, a1, a1, TIMESTEP_END);
     fastpm_tevo_destroy_states(states);
+    fpm_store_flush(NULL);                          /* the state is complete when evolve returns */
     if (fpm_wrap_check() != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
 }
 
+/* The store whose periodic wrap has been postponed into the mass deposit that follows (one GPU, nobody looks at the
+ * positions in between): fastpm_paint_local wraps while it reads x, see cic_paint_kernel<.., WRAP> in csrc/paint.cu. */
+FastPMStore *fpm_pending_wrap = NULL;
+
 static void fastpm_decompose(FastPMSolver *fastpm, PM *pm)
 {
+    if (fastpm->NTask > 1) fpm_store_flush(NULL);
+    int before_handlers = 0, nspecies = 0;
+    for (FastPMEventHandler *h = fastpm->event_handlers; h; h = h->next)
+        if (h->stage == FASTPM_EVENT_STAGE_BEFORE && !strcmp(h->type, FASTPM_EVENT_FORCE)) before_handlers = 1;
+    for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) if (fastpm_solver_get_species(fastpm, si)) nspecies++;
     for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
         FastPMStore *p = fastpm_solver_get_species(fastpm, si);
         if (!p) continue;
+        if (nspecies == 1 && !getenv("FASTPM_B200_NO_FUSED_WRAP")) {
+            if (fastpm->NTask == 1 && !before_handlers) {
+                fpm_pending_wrap = p;                   /* one slab owns every particle: nothing to migrate; the deposit wraps */
+                continue;
+            }
+            if (fastpm->NTask > 1) {
+                fpm_pending_wrap = p;                   /* the classification pass of the migration wraps */
+                if (0 != fastpm_store_decompose(p, (fastpm_store_target_func) FastPMTargetPM, pm, fastpm->comm))
+                    fastpm_raise(-1, "Out of particle storage space\n");
+                continue;
+            }
+        }
         fastpm_store_wrap(p, pm->BoxSize);
         if (0 != fastpm_store_decompose(p, (fastpm_store_target_func) FastPMTargetPM, pm, fastpm->comm))
             fastpm_raise(-1, "Out of particle storage space\n");
@@ -326,6 +355,7 @@ static void fastpm_decompose(FastPMSolver *fastpm, PM *pm)
 void fastpm_set_species_snapshot(FastPMSolver *fastpm, FastPMStore *p, FastPMDriftFactor *drift, FastPMKickFactor *kick,
                                  FastPMStore *po, double aout)
 {
+    fpm_store_flush(NULL);
     memcpy(po, p, sizeof(FastPMStore));
     if (drift) fastpm_drift_store(drift, p, po, aout);
     if (kick) fastpm_kick_store(kick, p, po, aout);
@@ -341,6 +371,7 @@ void fastpm_set_species_snapshot(FastPMSolver *fastpm, FastPMStore *p, FastPMDri
 void fastpm_unset_species_snapshot(FastPMSolver *fastpm, FastPMStore *p, FastPMDriftFactor *drift, FastPMKickFactor *kick,
                                    FastPMStore *po, double aout)
 {
+    fpm_store_flush(NULL);
     FPM_MUST(fpm_divide((const float *) po->v, (float *) po->v, 3 * po->np, HubbleConstant / aout));
     if (po->potential) {
         double potfactor = 1.5 * Omega_source(1, fastpm->cosmology) / (HubbleDistance * HubbleDistance);
@@ -395,7 +426,7 @@ int64_t fastpm_b200_store_np(FastPMStore *p) { return (int64_t) p->np; }
 void fastpm_b200_store_meta(FastPMStore *p, double *out) { out[0] = p->meta.a_x; out[1] = p->meta.a_v; out[2] = p->meta.M0; }
 void fastpm_b200_store_set_meta(FastPMStore *p, const double *in) { p->meta.a_x = in[0]; p->meta.a_v = in[1]; p->meta.M0 = in[2]; }
 void *fastpm_b200_store_column_ptr(FastPMStore *p, FastPMColumnTags attribute)
-{ int ci = fastpm_store_find_column_id(p, attribute); return ci < 0 ? NULL : p->columns[ci]; }
+{ fpm_store_flush(p); int ci = fastpm_store_find_column_id(p, attribute); return ci < 0 ? NULL : p->columns[ci]; }
 PM *fastpm_b200_solver_lptpm(FastPMSolver *s) { return s->lptpm; }
 void fastpm_b200_add_handler(FastPMSolver *s, const char *type, int stage, FastPMEventHandlerFunction fn, void *userdata)
 { fastpm_add_event_handler(&s->event_handlers, type, stage, fn, userdata); }

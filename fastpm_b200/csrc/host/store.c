@@ -6,15 +6,15 @@
 #include "internal.h"
 
 static void dev_pack(FastPMStore *p, ptrdiff_t index, int ci, void *packed)
-{ size_t es = p->_column_info[ci].elsize; FPM_MUST(fpm_memcpy_d2h(packed, p->columns[ci] + index * es, es)); }
+{ fpm_store_flush(p); size_t es = p->_column_info[ci].elsize; FPM_MUST(fpm_memcpy_d2h(packed, p->columns[ci] + index * es, es)); }
 static void dev_unpack(FastPMStore *p, ptrdiff_t index, int ci, void *packed)
-{ size_t es = p->_column_info[ci].elsize; FPM_MUST(fpm_memcpy_h2d(p->columns[ci] + index * es, packed, es)); }
+{ fpm_store_flush(p); size_t es = p->_column_info[ci].elsize; FPM_MUST(fpm_memcpy_h2d(p->columns[ci] + index * es, packed, es)); }
 static double dev_to_double_f4(FastPMStore *p, ptrdiff_t index, int ci, int memb)
-{ float v; FPM_MUST(fpm_memcpy_d2h(&v, p->columns[ci] + index * p->_column_info[ci].elsize + 4 * memb, 4)); return v; }
+{ fpm_store_flush(p); float v; FPM_MUST(fpm_memcpy_d2h(&v, p->columns[ci] + index * p->_column_info[ci].elsize + 4 * memb, 4)); return v; }
 static double dev_to_double_f8(FastPMStore *p, ptrdiff_t index, int ci, int memb)
-{ double v; FPM_MUST(fpm_memcpy_d2h(&v, p->columns[ci] + index * p->_column_info[ci].elsize + 8 * memb, 8)); return v; }
+{ fpm_store_flush(p); double v; FPM_MUST(fpm_memcpy_d2h(&v, p->columns[ci] + index * p->_column_info[ci].elsize + 8 * memb, 8)); return v; }
 static void dev_from_double_f4(FastPMStore *p, ptrdiff_t index, int ci, int memb, const double value)
-{ float v = (float) value; FPM_MUST(fpm_memcpy_h2d(p->columns[ci] + index * p->_column_info[ci].elsize + 4 * memb, &v, 4)); }
+{ fpm_store_flush(p); float v = (float) value; FPM_MUST(fpm_memcpy_h2d(p->columns[ci] + index * p->_column_info[ci].elsize + 4 * memb, &v, 4)); }
 
 const char *fastpm_species_get_name(enum FastPMSpecies species)
 {
@@ -89,7 +89,7 @@ size_t fastpm_store_init_evenly_details(FastPMStore *p, const char *name, size_t
     return 0;
 }
 
-void fastpm_store_destroy(FastPMStore *p) { fastpm_memory_free(p->mem, p->_base); p->_base = NULL; }
+void fastpm_store_destroy(FastPMStore *p) { fpm_store_flush(p); fastpm_memory_free(p->mem, p->_base); p->_base = NULL; }
 
 int fastpm_store_find_column_id(FastPMStore *p, FastPMColumnTags attribute)
 {
@@ -110,6 +110,7 @@ size_t fastpm_store_get_np_total(FastPMStore *p, MPI_Comm comm)
 void fastpm_store_fill(FastPMStore *p, PM *pm, double *shift, ptrdiff_t *Nc)
 {
     ptrdiff_t nc[3];
+    fpm_store_flush(p);
     for (int d = 0; d < 3; d++) nc[d] = Nc ? Nc[d] : pm->Nmesh[d];
     if (nc[0] != nc[1] || nc[0] != nc[2]) fastpm_raise(-1, "fastpm_b200: cubic particle grids only\n");
     ptrdiff_t start = pm->IRegion.start[0] * nc[0] / pm->Nmesh[0];
@@ -124,12 +125,15 @@ void fastpm_store_fill(FastPMStore *p, PM *pm, double *shift, ptrdiff_t *Nc)
     p->meta._q_strides[0] = nc[1] * nc[2]; p->meta._q_strides[1] = nc[2]; p->meta._q_strides[2] = 1;
     FPM_MUST(fpm_fill_grid((double *) p->x, p->id, (float *) p->v, (int) nc[0], (int) start, (int64_t) p->np,
                            pm->BoxSize[0], p->meta._q_shift[0]));
+    /* one slab holding the whole nc^3 grid in id order: let paint / readout walk it in Lagrangian bricks */
+    FPM_MUST(fpm_particle_grid_hint((fpm_comm_size(pm->comm) == 1 && start == 0 && end == nc[0]) ? (int) nc[0] : 0));
     if (p->q) fastpm_raise(-1, "fastpm_b200: the q column is not filled on the device yet\n");
     p->meta.a_x = p->meta.a_v = 0.;
 }
 
 void fastpm_store_wrap(FastPMStore *p, double BoxSize[3])
 {
+    fpm_store_flush(p);
     if (fpm_wrap((double *) p->x, (int64_t) p->np, BoxSize[0]) != 0)
         fastpm_raise(-1, "%s\n", fpm_last_error());
 }
@@ -138,6 +142,7 @@ void fastpm_store_wrap(FastPMStore *p, double BoxSize[3])
 int FastPMTargetPM(FastPMStore *p, ptrdiff_t i, PM *pm)
 {
     double pos[3];
+    fpm_store_flush(p);
     FPM_MUST(fpm_memcpy_d2h(pos, p->x + i, sizeof(pos)));
     return pm_pos_to_rank(pm, pos);
 }
@@ -147,6 +152,7 @@ void fastpm_store_summary(FastPMStore *p, FastPMColumnTags attribute, MPI_Comm c
 {
     va_list va;
     va_start(va, fmt);
+    fpm_store_flush(p);
     int ci = fastpm_store_find_column_id(p, attribute);
     if (ci < 0 || !p->columns[ci]) fastpm_raise(-1, "Column for attribute %d is not allocated\n", (int) attribute);
     struct FastPMColumnInfo *c = &p->_column_info[ci];
@@ -183,6 +189,7 @@ void fastpm_store_summary(FastPMStore *p, FastPMColumnTags attribute, MPI_Comm c
 /* bulk host mirrors */
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count)
 {
+    fpm_store_flush(p);
     int ci = fastpm_store_find_column_id(p, attribute);
     if (ci < 0 || !p->columns[ci]) return -1;
     size_t es = p->_column_info[ci].elsize;
@@ -190,6 +197,7 @@ int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, voi
 }
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count)
 {
+    fpm_store_flush(p);
     int ci = fastpm_store_find_column_id(p, attribute);
     if (ci < 0 || !p->columns[ci]) return -1;
     size_t es = p->_column_info[ci].elsize;

@@ -145,7 +145,10 @@ void fastpm_emit_event(FastPMEventHandler *handlers, const char *type, enum Fast
     strncpy(event->type, type, 31); event->type[31] = 0;
     event->stage = stage;
     for (FastPMEventHandler *h = handlers; h; h = h->next)
-        if (h->stage == stage && !strcmp(h->type, type)) h->function(context, event, h->userdata);
+        if (h->stage == stage && !strcmp(h->type, type)) {
+            fpm_store_flush(NULL);                 /* a handler may look at the particles: no queued kick / drift may be outstanding */
+            h->function(context, event, h->userdata);
+        }
 }
 
 /* ------------------------------------------------------------------ memory (memory.c): tagged DEVICE allocator */

@@ -119,15 +119,14 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
                         if (counted) { acc[e] = w; acc2[e] = w * (sqrt((double) kk) * k0); }
                     } else {
                         float2 v = e ? make_float2(vv[u].z, vv[u].w) : make_float2(vv[u].x, vv[u].y);
-                        if (inrow) allsum += w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
-                        if (counted) {
-                            if (decic) {
-                                const double smth = dxy * dtab[iz];
-                                v.x = (float) ((double) v.x * smth);
-                                v.y = (float) ((double) v.y * smth);
-                            }
-                            acc[e] = w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
+                        if (decic && inrow) {                        // the field IS the deconvolved one: also for the variance
+                            const double smth = dxy * dtab[iz];
+                            v.x = (float) ((double) v.x * smth);
+                            v.y = (float) ((double) v.y * smth);
                         }
+                        const double p2 = w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
+                        if (inrow) allsum += p2;
+                        if (counted) acc[e] = p2;
                     }
                     bins[e] = bin;
                 }

@@ -17,6 +17,26 @@
 #include "mesh.cuh"
 #include <stdlib.h>
 
+// Traversal order.  A store filled by fastpm_store_fill (store.c:756-793) holds particle (i, j, k) of the nc^3 Lagrangian grid
+// at index (i*nc + j)*nc + k and, on one GPU, is never permuted.  Walking it linearly makes the ~300k particles in flight at
+// any moment one thin i-plane whose mesh footprint (displacements of +-10 cells) spans ~20 full mesh planes -- more than
+// the L2 at N = 2048.  With the hint `lag_nc` set, a CTA takes a 4 x 8 x 8 brick of the Lagrangian grid and consecutive CTAs
+// walk k, then j, then i, so that the CTAs in flight cover a compact 4 x ~70 x nc slab (footprint ~40 MB at N = 2048) and
+// successive waves reuse each other's mesh lines in L2.  Any permutation of thread -> particle is a valid traversal: the
+// hint affects speed only.
+__device__ __forceinline__ long long cic_particle_index(int lag_nc, long long np)
+{
+    if (lag_nc == 0) {
+        const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        return i < np ? i : -1;
+    }
+    const int nb = lag_nc >> 3;
+    const int b = blockIdx.x;
+    const int bk = b % nb, bj = (b / nb) % nb, bi = b / (nb * nb);
+    const int tk = threadIdx.x & 7, tj = (threadIdx.x >> 3) & 7, ti = threadIdx.x >> 6;
+    return ((long long) (bi * 4 + ti) * lag_nc + (bj * 8 + tj)) * lag_nc + (bk * 8 + tk);
+}
+
 struct CicIndex {
     int lx0, lx1, j0, j1, k0, k1;      // lx*: local plane index or -1 when outside this rank
     double D[3], T[3];
@@ -75,14 +95,32 @@ __device__ __forceinline__ void cic_add_pair(float *row, int k0, int k1, float w
     atomicAdd(row + k1, w1);
 }
 
-template <int VEC>
+// WRAP: fastpm_store_wrap (store.c:447-475) folded into the deposit -- the same operations on the same values as the
+// stand-alone wrap kernel (particles.cu), the position is written back only where it changed, and the pass over x that
+// the reference spends on wrapping disappears.
+template <int VEC, bool WRAP>
 __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
-        const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
-        int field_stride, long long np)
+        double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
+        int field_stride, long long np, int *__restrict__ bad, int lag_nc)
 {
-    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
+    const long long i = cic_particle_index(lag_nc, np);
+    if (i < 0) return;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    if (WRAP) {
+        const double L = g.boxsize;
+        #pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double xi = pos[d];
+            if (xi >= 0 && xi < L) continue;                         // remainder() + fold leave such a value unchanged (x == L goes to 0)
+            const double nwrap = (double) abs((int) (xi / L));       // integer abs() on the truncated ratio, store.c:453
+            double x1 = remainder(xi, L);
+            while (x1 < 0) x1 += L;
+            while (x1 > L) x1 -= L;
+            if (nwrap > 10000) atomicExch(bad, 1);
+            pos[d] = x1;
+            x[3 * i + d] = x1;
+        }
+    }
     CicIndex c;
     cic_setup(g, pos, c);
     double weight = mass ? M0 + (double) mass[i] : M0;        // fastpm_store_get_mass, store.c:120-128
@@ -102,10 +140,10 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
 }
 
 __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
-        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np)
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc)
 {
-    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
+    const long long i = cic_particle_index(lag_nc, np);
+    if (i < 0) return;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
     CicIndex c;
     cic_setup(g, pos, c);
@@ -139,16 +177,40 @@ __global__ void plane_add_kernel(float *__restrict__ dst, const float *__restric
     for (; i < nfloats; i += stride) dst[i] += src[i];
 }
 
+// see cic_particle_index(): stores of exactly nc^3 particles are walked in Lagrangian bricks (nc a multiple of 8)
+static long long g_lag_np = 0;
+static int g_lag_nc = 0;
+void fpm_set_lagrangian_hint(int nc)
+{
+    static int off = -1;
+    if (off < 0) off = getenv("FASTPM_B200_NO_BRICKS") ? 1 : 0;
+    if (nc > 0 && nc % 8 == 0 && !off) { g_lag_nc = nc; g_lag_np = (long long) nc * nc * nc; }
+    else { g_lag_nc = 0; g_lag_np = 0; }
+}
+// Bricks pay off only when the linear walk's footprint (~24 mesh planes) no longer fits the 126 MB L2: measured on B200, they
+// cost 15 % at N = 1024 (4.3 MB planes, linear walk already L2 resident) and gain 25 % at N = 2048 (17 MB planes).
+static int fpm_lagrangian_hint(long long np, const FpmGeom &g)
+{
+    const size_t plane_bytes = (size_t) g.n * g.pitch_r * sizeof(float);
+    return (g_lag_nc && np == g_lag_np && plane_bytes > ((size_t) 6 << 20)) ? g_lag_nc : 0;
+}
+
+// wrap_bad != NULL: wrap the positions on the way (x is then written where it changed)
 int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0,
-                     const float *field, int field_stride, long long np, cudaStream_t st)
+                     const float *field, int field_stride, long long np, int *wrap_bad, cudaStream_t st)
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
     static int vec = -1;          // FASTPM_B200_PAINT_VEC = 0 | 2 | 4 (default): width of the vector reductions
     if (vec < 0) { const char *e = getenv("FASTPM_B200_PAINT_VEC"); vec = e ? atoi(e) : 4; }
-    if (vec >= 4) { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<4><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
-    else if (vec >= 2) { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<2><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
-    else { FPM_TIMED(FPM_K_PAINT, st, (cic_paint_kernel<0><<<grid, 256, 0, st>>>(m->geom, canvas, x, mass, M0, field, field_stride, np))); }
+    double *xw = const_cast<double *>(x);
+    const int lag_nc = fpm_lagrangian_hint(np, m->geom);
+    #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc)
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_PAINT, st);
+    if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
+    else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
+    if (fpm_prof_on) fpm_prof_end(FPM_K_PAINT, st);
+    #undef PAINT_LAUNCH
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -158,7 +220,8 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
-    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np)));
+    const int lag_nc = fpm_lagrangian_hint(np, m->geom);
+    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -65,6 +65,62 @@ __global__ void __launch_bounds__(256) drift_kernel(const DriftArgs a)
     }
 }
 
+// A run of consecutive in-place kicks and drifts of one store (the K K D D between two force evaluations, solver.c:283-356)
+// applied in ONE pass: every particle component goes through the same operations, in the same order and with the same
+// roundings as kick_kernel / drift_kernel above, but v and x stay in registers between them.
+struct FpmUpdateOp { int kind; int mode; double f[5]; };    // kind 0 kick: dda q1 q2 Dv1 Dv2 (mode = cola); 1 drift: dyyy da1 da2 Dv1 Dv2
+#define FPM_MAX_UPDATE_OPS 8
+struct FusedArgs {
+    double *x; float *v; const float *acc; const float *dx1; const float *dx2;
+    long long n3;
+    int nops, any_kick, any_drift, any_dx;
+    FpmUpdateOp ops[FPM_MAX_UPDATE_OPS];
+};
+
+__global__ void __launch_bounds__(256) fused_update_kernel(const FusedArgs a)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < a.n3; i += stride) {
+        float v = a.v[i];
+        double x = a.any_drift ? a.x[i] : 0.0;
+        const float acc = a.any_kick ? a.acc[i] : 0.f;
+        const float d1 = a.any_dx ? a.dx1[i] : 0.f, d2 = (a.any_dx && a.dx2) ? a.dx2[i] : 0.f;
+        for (int j = 0; j < a.nops; j++) {
+            const FpmUpdateOp &op = a.ops[j];
+            if (op.kind == 0) {
+                float ax = acc;
+                if (op.mode) {
+                    const double t = (double) d1 * op.f[1] + (double) d2 * op.f[2];
+                    ax = (float) ((double) ax + t);
+                }
+                float vo = (float) ((double) v + (double) ax * op.f[0]);
+                if (op.mode) {
+                    const double t = (double) d1 * op.f[3] + (double) d2 * op.f[4];
+                    vo = (float) ((double) vo + t);
+                }
+                v = vo;
+            } else {
+                double xo;
+                switch (op.mode) {
+                    case 3: xo = x + (double) d1 * op.f[1] + (double) d2 * op.f[2]; break;
+                    case 4: xo = x + (double) d1 * op.f[1]; break;
+                    case 2: {
+                        const double vv = (double) v - ((double) d1 * op.f[3] + (double) d2 * op.f[4]);
+                        xo = x + vv * op.f[0];
+                        xo += (double) d1 * op.f[1] + (double) d2 * op.f[2];
+                        break;
+                    }
+                    default: xo = x + (double) v * op.f[0]; break;
+                }
+                x = xo;
+            }
+        }
+        if (a.any_kick) a.v[i] = v;
+        if (a.any_drift) a.x[i] = x;
+    }
+}
+
 // store.c:447-475: remainder() then fold into [0, L]; a particle further than 10000 boxes away is an error
 __global__ void __launch_bounds__(256) wrap_kernel(double *x, long long n3, double L, int *bad)
 {
@@ -184,6 +240,29 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
     if (np <= 0) return 0;
     DriftArgs a = { x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, mode, 3 * np };
     FPM_TIMED(FPM_K_DRIFT, st, (drift_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ops: [nops][7] doubles = kind, mode, f0..f4
+int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np,
+                            int nops, const double *ops, cudaStream_t st)
+{
+    if (np <= 0 || nops <= 0) return 0;
+    if (nops > FPM_MAX_UPDATE_OPS) { fpm_set_error("fused update: at most %d operations", FPM_MAX_UPDATE_OPS); return -1; }
+    FusedArgs a;
+    a.x = x; a.v = v; a.acc = acc; a.dx1 = dx1; a.dx2 = dx2; a.n3 = 3 * np; a.nops = nops;
+    a.any_kick = a.any_drift = a.any_dx = 0;
+    for (int j = 0; j < nops; j++) {
+        const double *o = ops + 7 * j;
+        a.ops[j].kind = (int) o[0]; a.ops[j].mode = (int) o[1];
+        for (int q = 0; q < 5; q++) a.ops[j].f[q] = o[2 + q];
+        if (a.ops[j].kind == 0) { a.any_kick = 1; if (a.ops[j].mode) a.any_dx = 1; }
+        else { a.any_drift = 1; if (a.ops[j].mode >= 2) a.any_dx = 1; }
+    }
+    if (a.any_kick && !acc) { fpm_set_error("fused update: a kick needs the acc column"); return -1; }
+    if (a.any_dx && !dx1) { fpm_set_error("fused update: COLA / LPT operations need the dx1 (and dx2) columns"); return -1; }
+    FPM_TIMED(a.any_drift ? FPM_K_DRIFT : FPM_K_KICK, st, (fused_update_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -59,6 +59,8 @@ uint64_t fpm_kernel_launch_count(void);                /* kernels launched by th
 int fpm_prof_enable(int on);
 int fpm_prof_reset(void);
 int fpm_prof_get(int64_t *counts, double *total_ms, int ncls);
+/* the same, launch by launch in issue order (class index, milliseconds); returns the number of launches recorded */
+int fpm_prof_get_launches(int32_t *cls, double *ms, int max);
 
 /* ---- mesh object: struct PM, pm_init / pm_destroy, pmpfft.c:108-342 -------------------------- */
 fpm_mesh *fpm_mesh_create(int nmesh, double boxsize, int nranks, int rank);
@@ -75,6 +77,10 @@ int fpm_mesh_ktables_host(const fpm_mesh *m, float *host_out);
  * canvas is NOT cleared (call fpm_memset first, like pm_clear in gravity.c:310). */
 int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np,
               double M0, const float *mass, const float *field, int field_stride);
+/* Performance hint for fpm_paint / fpm_readout: stores of exactly nc^3 particles are in fastpm_store_fill order
+ * (index (i*nc + j)*nc + k, store.c:756-793) and are walked in 4x8x8 Lagrangian bricks for L2 locality.  nc = 0 clears the
+ * hint.  Results do not depend on it (any traversal order is valid). */
+int fpm_particle_grid_hint(int nc);
 /* ---- K5 CIC readout: fastpm_readout_local + cic_readout_tuned, painter.c:358 / painter-cic.c:113 */
 /* out[i*out_stride] = (float) sum_8 (float)(canvas * prescale) * w   (prescale 1.0 = none) */
 int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np,
@@ -116,6 +122,10 @@ int fpm_transfer_for_kernel(int kernel_type, int attr, int memb, fpm_transfer *o
 /* ---- K3 stand-alone k-space sweeps ----------------------------------------------------------- */
 int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fpm_transfer *kernel);
 int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to);      /* transfer.c:78 */
+/* in-place fpm_apply_decic(m, cplx, cplx), deferred: fpm_powerspectrum* folds it into its read, any other entry point of this
+ * library that is handed the buffer applies it first, fpm_decic_cancel drops it (solver.c:471 before the FORCE/after event) */
+int fpm_decic_defer(const fpm_mesh *m, float *cplx);
+int fpm_decic_cancel(const float *cplx);
 int fpm_scale(const float *from, float *to, size_t nfloats, double value); /* transfer.c:213 */
 int fpm_divide(const float *from, float *to, size_t nfloats, double value); /* solver.c:738-742 */
 int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign); /* pm2lpt.c:103,118 */
@@ -139,10 +149,18 @@ int fpm_kick(float *v_out, const float *v_in, const float *acc, const float *dx1
              int forcemode, double dda, double q1, double q2, double Dv1, double Dv2);
 int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, int64_t np,
               int forcemode, double dyyy, double da1, double da2, double Dv1, double Dv2);
+/* A run of consecutive IN-PLACE kicks and drifts of one store in one pass over the particles (the K K D D between two force
+ * evaluations of fastpm_solver_evolve, solver.c:283-356): same operations, order and roundings as the separate calls, v and x
+ * stay in registers in between.  ops[nops][7] = { kind (0 kick, 1 drift), mode (kick: 1 = COLA; drift: FastPMForceType),
+ * then the five factors in the argument order of fpm_kick (dda q1 q2 Dv1 Dv2) / fpm_drift (dyyy da1 da2 Dv1 Dv2) }; nops <= 8 */
+int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, const float *dx2, int64_t np, int nops, const double *ops);
 /* ---- K8 wrap: fastpm_store_wrap, store.c:447 -------------------------------------------------- */
 /* the reference aborts when a particle is > 10000 boxes away (store.c:460-471): that flag is reported by the NEXT
  * fpm_wrap call or by fpm_wrap_check() (which waits for the stream), so the integrator itself never blocks on it */
 int fpm_wrap(double *x, int64_t np, double boxsize);
+/* fpm_wrap followed by fpm_paint in ONE pass over the positions (same operations on the same values; x is written back only
+ * where wrapping changed it).  store.c:447 + painter.c:320 */
+int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, double M0, const float *mass, const float *field, int field_stride);
 int fpm_wrap_check(void);
 /* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;
  * host_out[ncomp][4] = min, max, sum, sum of squares */

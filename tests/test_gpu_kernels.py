@@ -172,6 +172,16 @@ def test_powerspectrum_matches_reference(dev, ref_mod):
     k2, p2, n2 = m.powerspectrum(src, decic=True)
     k3, p3, n3 = s.powerspectrum(s.decic(dk))
     np.testing.assert_allclose(p2, p3, rtol=1e-12)
+    # deferred deconvolution (solver.c:471 before the FORCE/after event): P(k) folds it into its read ...
+    dev.check(m.lib.fpm_decic_defer(m.h, src.ptr))
+    k4, p4, n4 = m.powerspectrum(src)
+    np.testing.assert_allclose(p4, p2, rtol=1e-12)       # same values, double atomics in a different order
+    assert np.array_equal(n4, n2)
+    # ... and any other access through the library sees the deconvolved field (bit-exact with the reference's sweep)
+    got = m.download_complex(src)
+    assert np.array_equal(got, s.complex_view(s.decic(dk)))
+    k5, p5, n5 = m.powerspectrum(src)                    # now materialised: a plain measurement gives the same numbers
+    np.testing.assert_allclose(p5, p2, rtol=1e-12)
     s.close()
 
 
@@ -205,6 +215,19 @@ def test_kick_drift_bit_exact(dev, ref_mod, pk_text, mode):
                             df["dyyy"][-1] - df["dyyy"][0], df["da1"][-1] - df["da1"][0], df["da2"][-1] - df["da2"][0], df["Dv1"], df["Dv2"]))
     assert np.array_equal(v.download(np.float32).reshape(n, 3), p1["v"])
     assert np.array_equal(x.download(np.float64).reshape(n, 3), p1["x"])
+    # the same kick and drift, then a second kick and two half drifts, as ONE fused pass: bit-identical to the sequence
+    x2, v2 = B(p0["x"]), B(p0["v"])
+    cola = 1 if mode == "cola" else 0
+    k_op = [0, cola, kf["dda"][-1] - kf["dda"][0], kf["q1"], kf["q2"], kf["Dv1"][-1] - kf["Dv1"][0], kf["Dv2"][-1] - kf["Dv2"][0]]
+    d_op = [1, fm, df["dyyy"][-1] - df["dyyy"][0], df["da1"][-1] - df["da1"][0], df["da2"][-1] - df["da2"][0], df["Dv1"], df["Dv2"]]
+    d_half = [1, fm, 0.5 * d_op[2], 0.5 * d_op[3], 0.5 * d_op[4], df["Dv1"], df["Dv2"]]
+    ops = np.array([k_op, d_op, k_op, d_half, d_half], dtype=np.float64)
+    dev.check(lib.fpm_update_fused(x2.ptr, v2.ptr, acc.ptr, dx1.ptr if dx1 else None, dx2.ptr if dx2 else None, n, len(ops), ops.ctypes.data))
+    dev.check(lib.fpm_kick(v.ptr, v.ptr, acc.ptr, dx1.ptr if dx1 else None, dx2.ptr if dx2 else None, n, fm, *k_op[2:]))
+    for _ in range(2):
+        dev.check(lib.fpm_drift(x.ptr, x.ptr, v.ptr, dx1.ptr if dx1 else None, dx2.ptr if dx2 else None, n, fm, *d_half[2:]))
+    assert np.array_equal(v2.download(np.float32), v.download(np.float32))
+    assert np.array_equal(x2.download(np.float64), x.download(np.float64))
     s.close()
 
 
