@@ -144,7 +144,11 @@ struct Fft3 {
     }
 
     template <typename Hook>
-    __device__ __forceinline__ void run(float2 (&v)[E], Hook after_first_barrier)
+    __device__ __forceinline__ void run(float2 (&v)[E], Hook after_first_barrier) { run(v, after_first_barrier, []() {}); }
+
+    // hooks: called by every thread right after the first barrier of exchange 1 / of exchange 2
+    template <typename Hook, typename Hook2>
+    __device__ __forceinline__ void run(float2 (&v)[E], Hook after_first_barrier, Hook2 after_x2_barrier)
     {
         const float2 *tw1 = tw;
         // ---- stage 1: radix R1 over rows t + k*M1; output q goes to row q*M1 + t, times w_N^(q t)
@@ -197,6 +201,7 @@ struct Fft3 {
         #pragma unroll
         for (int half = 0; half < 2; half++) {
             __syncthreads();
+            if (half == 0) after_x2_barrier();
             #pragma unroll
             for (int i = 0; i < E / R2; i++) {
                 #pragma unroll

@@ -107,7 +107,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
                 }
             }
         };
-        if (a.early) { __syncthreads(); prefetch_next(); }
+        if (a.early == 1) { __syncthreads(); prefetch_next(); }
 
         const int iy = a.outer0 + o, iz = kz0 + c;
         if (xf && iz <= h) {
@@ -166,8 +166,9 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
         }
 
         // ---- three register stages with two exchanges through B
-        fx.run(v, [&]() { if (!a.early) prefetch_next(); });
+        fx.run(v, [&]() { if (a.early == 0) prefetch_next(); }, [&]() { if (a.early == 3) prefetch_next(); });
 
+        if (a.early == 5) prefetch_next();
         // ---- store: frequency kf = q1 + R1*q2 + R1*R2*q3, K*8 B contiguous per row
         const size_t obase = (size_t) (a.dst_ooffset + o) * a.dst_ostride + kz0 + c;
         if (single) {
@@ -266,9 +267,15 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
     TmaPassArgs a = args;
-    static int early = -1;        // FASTPM_B200_TMA_EARLY=1: issue the next tile's TMA right after the tile has been read (one more barrier)
-    if (early < 0) { const char *e = getenv("FASTPM_B200_TMA_EARLY"); early = e ? atoi(e) : 0; }
-    a.early = early == 1 || (early == 2 && args.xfer.active);
+    static int early = -1;        // FASTPM_B200_TMA_EARLY: where the next tile's TMA is issued (diagnostic; 4 = measured best per pass)
+    if (early < 0) { const char *e = getenv("FASTPM_B200_TMA_EARLY"); early = e ? atoi(e) : 4; }
+    // When the next tile's TMA is issued: 0 at the first barrier of exchange 1; 1 right after the tile has been read (one more
+    // barrier); 3 at the first barrier of exchange 2; 5 just before the stores.  Measured on B200 (scripts/fft_passes.py): a
+    // load that overlaps the register/shared-memory phases only from exchange 2 on is best for the in-place passes and for the
+    // pass with the k-space kernel (N = 2048: 14.6 ms against 18-20 ms at position 0); the scattered stores of a transposing
+    // pass collide with an in-flight load, so at N = 2048 the plain transposing pass issues it last (22 ms against 24-27 ms).
+    const bool transposing = args.dst_estride != (size_t) pitch_c;
+    a.early = early == 4 ? ((transposing && !args.xfer.active && n >= 2048) ? 5 : 3) : early;
     a.nouter = nouter;
     a.ntile_k = (n / 2 + 1 + K - 1) / K;
     switch (n) {

@@ -25,6 +25,7 @@ struct ZRowArgs {
     float scale;
     const float2 *twH;      // [H] exp(-2 pi i t / H)
     const float2 *twN;      // [N] exp(-2 pi i t / N)
+    int late;               // 1: the next tile's rows are requested at the first barrier of exchange 2 instead of exchange 1
 };
 
 // PREFETCH: input rows (A) and the exchange / output staging buffer (O) are separate, the next tile is loaded while this
@@ -100,12 +101,13 @@ fft_zrow_kernel(const ZRowArgs a)
         }
         if (PREFETCH && tid == 0) bulk_wait_read0();            // O (= B) is free again before anybody writes it
 
-        fx.run(v, [&]() {
+        auto prefetch_next = [&]() {
             if (PREFETCH && tid == 0) {
                 const int nxt = tile + gridDim.x;
                 if (nxt < ntiles) issue_load(nxt);
             }
-        });
+        };
+        fx.run(v, [&]() { if (a.late == 0) prefetch_next(); }, [&]() { if (a.late) prefetch_next(); });
 
         // ---- third exchange: frequency kf = q1 + R1*q2 + R1*R2*q3 of row c -> O[c][kf]
         __syncthreads();
@@ -191,7 +193,9 @@ int fpm_fft_zrow_supported(int n, size_t nrows)
 int fpm_fft_zrow_pass(int n, const float *src, float *dst, size_t nrows, int pitch_c, float scale,
                       const float2 *twH, const float2 *twN, int forward, cudaStream_t st)
 {
-    ZRowArgs a = { src, dst, nrows, pitch_c, scale, twH, twN };
+    static int late = -1;
+    if (late < 0) { const char *e = getenv("FASTPM_B200_ZROW_LATE"); late = e ? atoi(e) : 0; }
+    ZRowArgs a = { src, dst, nrows, pitch_c, scale, twH, twN, late };
     static int single = -1;       // FASTPM_B200_ZROW_SINGLE=1: one shared buffer per CTA (more CTAs per SM) at N = 2048
     if (single < 0) { const char *e = getenv("FASTPM_B200_ZROW_SINGLE"); single = e ? atoi(e) : 0; }
     switch (n) {

@@ -125,8 +125,8 @@ void fastpm_store_fill(FastPMStore *p, PM *pm, double *shift, ptrdiff_t *Nc)
     p->meta._q_strides[0] = nc[1] * nc[2]; p->meta._q_strides[1] = nc[2]; p->meta._q_strides[2] = 1;
     FPM_MUST(fpm_fill_grid((double *) p->x, p->id, (float *) p->v, (int) nc[0], (int) start, (int64_t) p->np,
                            pm->BoxSize[0], p->meta._q_shift[0]));
-    /* one slab holding the whole nc^3 grid in id order: let paint / readout walk it in Lagrangian bricks */
-    FPM_MUST(fpm_particle_grid_hint((fpm_comm_size(pm->comm) == 1 && start == 0 && end == nc[0]) ? (int) nc[0] : 0));
+    /* i-planes of nc x nc particles in id order: let paint / readout walk them in Lagrangian bricks */
+    FPM_MUST(fpm_particle_grid_hint((int) nc[0]));
     if (p->q) fastpm_raise(-1, "fastpm_b200: the q column is not filled on the device yet\n");
     p->meta.a_x = p->meta.a_v = 0.;
 }

@@ -24,14 +24,14 @@
 // walk k, then j, then i, so that the CTAs in flight cover a compact 4 x ~70 x nc slab (footprint ~40 MB at N = 2048) and
 // successive waves reuse each other's mesh lines in L2.  Any permutation of thread -> particle is a valid traversal: the
 // hint affects speed only.
-__device__ __forceinline__ long long cic_particle_index(int lag_nc, long long np)
+__device__ __forceinline__ long long cic_particle_index(int lag_nc, int nbrick_blocks, long long np)
 {
-    if (lag_nc == 0) {
-        const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    if (b >= nbrick_blocks) {            // no hint, or the tail beyond the last complete group of 4 i-planes: linear
+        const long long i = (long long) b * blockDim.x + threadIdx.x;
         return i < np ? i : -1;
     }
     const int nb = lag_nc >> 3;
-    const int b = blockIdx.x;
     const int bk = b % nb, bj = (b / nb) % nb, bi = b / (nb * nb);
     const int tk = threadIdx.x & 7, tj = (threadIdx.x >> 3) & 7, ti = threadIdx.x >> 6;
     return ((long long) (bi * 4 + ti) * lag_nc + (bj * 8 + tj)) * lag_nc + (bk * 8 + tk);
@@ -101,9 +101,9 @@ __device__ __forceinline__ void cic_add_pair(float *row, int k0, int k1, float w
 template <int VEC, bool WRAP>
 __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
         double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
-        int field_stride, long long np, int *__restrict__ bad, int lag_nc)
+        int field_stride, long long np, int *__restrict__ bad, int lag_nc, int nbrick_blocks)
 {
-    const long long i = cic_particle_index(lag_nc, np);
+    const long long i = cic_particle_index(lag_nc, nbrick_blocks, np);
     if (i < 0) return;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
     if (WRAP) {
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
 }
 
 __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
-        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc)
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc, int nbrick_blocks)
 {
-    const long long i = cic_particle_index(lag_nc, np);
+    const long long i = cic_particle_index(lag_nc, nbrick_blocks, np);
     if (i < 0) return;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
     CicIndex c;
@@ -177,22 +177,30 @@ __global__ void plane_add_kernel(float *__restrict__ dst, const float *__restric
     for (; i < nfloats; i += stride) dst[i] += src[i];
 }
 
-// see cic_particle_index(): stores of exactly nc^3 particles are walked in Lagrangian bricks (nc a multiple of 8)
-static long long g_lag_np = 0;
-static int g_lag_nc = 0;
+// see cic_particle_index(): a store laid out as i-planes of nc x nc particles (fastpm_store_fill order; on several GPUs the
+// local slab of it, which migration perturbs only slightly) is walked in Lagrangian bricks over its complete groups of 4 planes
+static int g_lag_nc = 0, g_lag_force = 0;
 void fpm_set_lagrangian_hint(int nc)
 {
     static int off = -1;
     if (off < 0) off = getenv("FASTPM_B200_NO_BRICKS") ? 1 : 0;
-    if (nc > 0 && nc % 8 == 0 && !off) { g_lag_nc = nc; g_lag_np = (long long) nc * nc * nc; }
-    else { g_lag_nc = 0; g_lag_np = 0; }
+    g_lag_force = nc < 0;                    // negative: use the bricks whatever the mesh size (tests)
+    if (nc < 0) nc = -nc;
+    g_lag_nc = (nc > 0 && nc % 8 == 0 && !off) ? nc : 0;
 }
 // Bricks pay off only when the linear walk's footprint (~24 mesh planes) no longer fits the 126 MB L2: measured on B200, they
 // cost 15 % at N = 1024 (4.3 MB planes, linear walk already L2 resident) and gain 25 % at N = 2048 (17 MB planes).
-static int fpm_lagrangian_hint(long long np, const FpmGeom &g)
+// Returns the number of leading 256-particle blocks that use the brick mapping (0: linear walk).
+static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc)
 {
     const size_t plane_bytes = (size_t) g.n * g.pitch_r * sizeof(float);
-    return (g_lag_nc && np == g_lag_np && plane_bytes > ((size_t) 6 << 20)) ? g_lag_nc : 0;
+    *lag_nc = 0;
+    if (!g_lag_nc || (plane_bytes <= ((size_t) 6 << 20) && !g_lag_force)) return 0;
+    const long long group = 4LL * g_lag_nc * g_lag_nc;          // particles in 4 i-planes
+    const long long ngroups = np / group;
+    if (ngroups == 0) return 0;
+    *lag_nc = g_lag_nc;
+    return (int) (ngroups * group / 256);
 }
 
 // wrap_bad != NULL: wrap the positions on the way (x is then written where it changed)
@@ -204,8 +212,9 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
     static int vec = -1;          // FASTPM_B200_PAINT_VEC = 0 | 2 | 4 (default): width of the vector reductions
     if (vec < 0) { const char *e = getenv("FASTPM_B200_PAINT_VEC"); vec = e ? atoi(e) : 4; }
     double *xw = const_cast<double *>(x);
-    const int lag_nc = fpm_lagrangian_hint(np, m->geom);
-    #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc)
+    int lag_nc = 0;
+    const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
+    #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick)
     if (fpm_prof_on) fpm_prof_begin(FPM_K_PAINT, st);
     if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
     else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
@@ -220,8 +229,9 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
 {
     if (np <= 0) return 0;
     const unsigned grid = (unsigned) ((np + 255) / 256);
-    const int lag_nc = fpm_lagrangian_hint(np, m->geom);
-    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc)));
+    int lag_nc = 0;
+    const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
+    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

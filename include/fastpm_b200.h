@@ -77,9 +77,10 @@ int fpm_mesh_ktables_host(const fpm_mesh *m, float *host_out);
  * canvas is NOT cleared (call fpm_memset first, like pm_clear in gravity.c:310). */
 int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np,
               double M0, const float *mass, const float *field, int field_stride);
-/* Performance hint for fpm_paint / fpm_readout: stores of exactly nc^3 particles are in fastpm_store_fill order
- * (index (i*nc + j)*nc + k, store.c:756-793) and are walked in 4x8x8 Lagrangian bricks for L2 locality.  nc = 0 clears the
- * hint.  Results do not depend on it (any traversal order is valid). */
+/* Performance hint for fpm_paint / fpm_readout: stores are laid out as i-planes of nc x nc particles in fastpm_store_fill
+ * order (index (i*nc + j)*nc + k, store.c:756-793; on several GPUs the local slab of it) and are walked in 4x8x8 Lagrangian
+ * bricks for L2 locality when the mesh is large.  nc = 0 clears the hint.  Results do not depend on it (any traversal order
+ * is valid, every particle is visited exactly once). */
 int fpm_particle_grid_hint(int nc);
 /* ---- K5 CIC readout: fastpm_readout_local + cic_readout_tuned, painter.c:358 / painter-cic.c:113 */
 /* out[i*out_stride] = (float) sum_8 (float)(canvas * prescale) * w   (prescale 1.0 = none) */

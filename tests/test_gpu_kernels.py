@@ -71,6 +71,41 @@ def test_readout_bit_exact(dev, ref_mod, nmesh, kind):
     s.close()
 
 
+def test_brick_traversal_is_a_permutation(dev):
+    """The Lagrangian-brick walk of paint / readout (large meshes) visits every particle exactly once: same mesh (up to the
+    order of float additions) and bit-identical readout as the linear walk, including a tail that is not a whole group."""
+    nc, nmesh, L = 16, 32, 64.0
+    rng = np.random.default_rng(21)
+    n = nc ** 3 + 4 * nc * nc + 77                       # 5 complete groups of 4 planes + a ragged tail
+    x = rng.uniform(-0.2 * L, 1.2 * L, size=(n, 3))
+    m = dev.Mesh(nmesh, L)
+    lib = m.lib
+    xd = dev.DeviceBuffer.from_host(x)
+    res = {}
+    for tag, hint in (("linear", 0), ("bricks", -nc)):
+        dev.check(lib.fpm_particle_grid_hint(hint))
+        canvas = m.alloc()
+        m.paint(canvas, xd, n, M0=1.5)
+        out = dev.DeviceBuffer(4 * n)
+        out.zero()
+        m.readout(canvas, xd, n, out)
+        res[tag] = (m.download_real(canvas), out.download(np.float32))
+    dev.check(lib.fpm_particle_grid_hint(0))
+    a, b = res["linear"], res["bricks"]
+    assert abs(a[0].sum(dtype=np.float64) - 1.5 * n) < 1e-3 * n * 1e-3 + 1e-2
+    assert np.abs(a[0] - b[0]).max() <= 4e-6 * np.abs(a[0]).max()
+    # each readout gathers from its own canvas: compare each against a gather of the SAME canvas walked the other way
+    dev.check(lib.fpm_particle_grid_hint(-nc))
+    canvas = m.alloc()
+    m.upload_real(canvas, a[0])
+    out = dev.DeviceBuffer(4 * n)
+    m.readout(canvas, xd, n, out)
+    dev.check(lib.fpm_particle_grid_hint(0))
+    out2 = dev.DeviceBuffer(4 * n)
+    m.readout(canvas, xd, n, out2)
+    assert np.array_equal(out.download(np.float32), out2.download(np.float32))
+
+
 @pytest.mark.parametrize("nmesh", [16, 24, 32, 48, 64, 96, 128, 160])
 def test_r2c_c2r_match_reference(dev, ref_mod, nmesh):
     L = 200.0
