@@ -58,7 +58,13 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     for (int i = tid; i < N; i += T * K) TW[i] = __ldg(a.tw + i);
     __syncthreads();
 
-    int tile = blockIdx.x;
+    // A CTA may take `chunk` kz-adjacent tiles in a row before it jumps ahead (so that the two 64-byte halves of a line are
+    // written by the same SM close in time at N = 2048).  Measured: no gain for the transposing passes, 10-25 % loss for the
+    // in-place ones (scripts/fft_passes.py with FASTPM_B200_TMA_CHUNK = 2, 4); kept as a diagnostic, default 1.
+    const int chunk = a.chunk;
+    const int jump = 1 + ((int) gridDim.x - 1) * chunk;
+    auto next_tile = [&](int tl) { return (tl % chunk != chunk - 1) ? tl + 1 : tl + jump; };
+    int tile = blockIdx.x * chunk;
     if (tid == 0 && tile < ntiles) {
         const int o = tile / a.ntile_k, kz0 = (tile - o * a.ntile_k) * K;
         mbar_expect_tx(&bar, tile_bytes);
@@ -86,7 +92,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     const bool xf = a.xfer.active;
 
     #pragma unroll 1
-    for (; tile < ntiles; tile += gridDim.x) {
+    for (; tile < ntiles; tile = next_tile(tile)) {
         const int o = tile / a.ntile_k, kz0 = (tile - o * a.ntile_k) * K;
         float2 v[E];
 
@@ -98,7 +104,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
         for (int k = 0; k < E; k++) v[k] = Ard[k * M1 * K];
         auto prefetch_next = [&]() {
             if (tid == 0) {
-                const int nxt = tile + gridDim.x;
+                const int nxt = next_tile(tile);
                 if (nxt < ntiles) {
                     const int o2 = nxt / a.ntile_k, kz2 = (nxt - o2 * a.ntile_k) * K;
                     mbar_expect_tx(&bar, tile_bytes);
@@ -278,6 +284,9 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     a.early = early == 4 ? ((transposing && !args.xfer.active && n >= 2048) ? 5 : 3) : early;
     a.nouter = nouter;
     a.ntile_k = (n / 2 + 1 + K - 1) / K;
+    static int chunk = -1;        // FASTPM_B200_TMA_CHUNK: kz-adjacent tiles a CTA processes back to back (diagnostic, default 1)
+    if (chunk < 0) { const char *e = getenv("FASTPM_B200_TMA_CHUNK"); chunk = e ? atoi(e) : 1; }
+    a.chunk = chunk > 0 ? chunk : 1;
     switch (n) {
         case 512: return launch_cfg<8, 8, 8, 16>(tmap, a, nsm, st);
         case 1024: return K == 8 ? launch_cfg<16, 16, 4, 8>(tmap, a, nsm, st) : launch_cfg<16, 16, 4, 16>(tmap, a, nsm, st);

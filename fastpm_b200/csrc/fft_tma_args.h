@@ -10,6 +10,7 @@ struct TmaPassArgs {
     int dst_ooffset;
     int ntile_k, nouter;
     int conj;
+    int chunk;                  // kz-adjacent tiles a CTA processes back to back
     int early;                  // 1: prefetch the next tile before the arithmetic of this one
     int outer0;
     const float2 *tw;           // [N] exp(-2 pi i t / N)

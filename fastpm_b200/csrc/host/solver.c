@@ -423,6 +423,14 @@ void fastpm_b200_solver_free(FastPMSolver *solver)
 /* small accessors for bindings that do not lay out the structs */
 FastPMStore *fastpm_b200_solver_cdm(FastPMSolver *s) { return fastpm_solver_get_species(s, FASTPM_SPECIES_CDM); }
 int64_t fastpm_b200_store_np(FastPMStore *p) { return (int64_t) p->np; }
+/* resets the particle count (a host buffer with np particles is about to be copied in with fastpm_b200_store_set_column) */
+int fastpm_b200_store_set_np(FastPMStore *p, int64_t np)
+{
+    fpm_store_flush(p);
+    if (np < 0 || (size_t) np > p->np_upper) return -1;
+    p->np = (size_t) np;
+    return 0;
+}
 void fastpm_b200_store_meta(FastPMStore *p, double *out) { out[0] = p->meta.a_x; out[1] = p->meta.a_v; out[2] = p->meta.M0; }
 void fastpm_b200_store_set_meta(FastPMStore *p, const double *in) { p->meta.a_x = in[0]; p->meta.a_v = in[1]; p->meta.M0 = in[2]; }
 void *fastpm_b200_store_column_ptr(FastPMStore *p, FastPMColumnTags attribute)

@@ -68,15 +68,19 @@ __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const doubl
 // deconvolution (rounded to float like the reference's in-place sweep, transfer.c:78-113) into the read.
 #define PK_WARPS 8
 #define PK_UNROLL 2
+// Each warp owns a private histogram in shared memory: the head lanes of one warp-wide step hold DISTINCT bins (runs of a
+// monotone sequence), so they update it with plain read-modify-writes -- no atomics, no contention between warps (double
+// atomicAdd on shared memory is a CAS loop; with all warps of an SM hitting neighbouring shells it was 70 % of the kernel).
 template <bool GEOM>
 __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
         const float2 *__restrict__ dk, double k0, double *__restrict__ out /* GEOM: [2][nbins]; else [nbins] + 1 */)
 {
-    extern __shared__ double hist[];
+    extern __shared__ double hist_all[];
     const int nbins = g.n / 2;
     const int nslots = GEOM ? 2 * nbins : nbins + 1;
-    for (int i = threadIdx.x; i < nslots; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < nslots * PK_WARPS; i += blockDim.x) hist_all[i] = 0;
     __syncthreads();
+    volatile double *hist = hist_all + (size_t) (threadIdx.x >> 5) * nslots;
     const int n = g.n, h = n / 2, lane = threadIdx.x & 31;
     const size_t nrows = (size_t) g.nyl * n;
     const size_t wstride = (size_t) gridDim.x * PK_WARPS;
@@ -130,14 +134,16 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
                     }
                     bins[e] = bin;
                 }
-                // the lane's two modes: merge when they share a bin, else the first one goes out on its own
+                // the lane's two modes: merge when they share a bin, else the first one goes out on its own.  bins[0] of the
+                // lanes that do so are strictly increasing across the warp: distinct addresses, plain update.
                 int bin = bins[1];
                 double s1 = acc[1], s2 = acc2[1];
                 if (bins[0] == bin) { s1 += acc[0]; s2 += acc2[0]; }
                 else if (bins[0] < nbins && (acc[0] != 0 || acc2[0] != 0)) {
-                    if (GEOM) { atomicAdd(&hist[bins[0]], acc[0]); atomicAdd(&hist[nbins + bins[0]], acc2[0]); }
-                    else atomicAdd(&hist[bins[0]], acc[0]);
+                    hist[bins[0]] += acc[0];
+                    if (GEOM) hist[nbins + bins[0]] += acc2[0];
                 }
+                __syncwarp();
                 // segmented reduction over runs of equal bin (contiguous because bin is monotone in iz)
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -147,23 +153,27 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
                     if (GEOM) o2 = __shfl_down_sync(0xffffffffu, s2, o);
                     if (lane + o < 32 && ob == bin) { s1 += o1; s2 += o2; }
                 }
-                // NB: a lane whose first mode left on its own still heads the run of its second mode only if the previous
-                // lane's LAST bin differs, which is what bins[1] of the previous lane tells
+                // the head lane of every run (distinct bins) adds the run's total
                 const int pb = __shfl_up_sync(0xffffffffu, bin, 1);
                 if ((lane == 0 || pb != bin) && bin < nbins && (s1 != 0 || s2 != 0)) {
-                    atomicAdd(&hist[bin], s1);
-                    if (GEOM) atomicAdd(&hist[nbins + bin], s2);
+                    hist[bin] += s1;
+                    if (GEOM) hist[nbins + bin] += s2;
                 }
+                __syncwarp();
             }
         }
     }
     if (!GEOM) {
         for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
-        if (lane == 0 && allsum != 0) atomicAdd(&hist[nbins], allsum);
+        if (lane == 0) hist[nbins] += allsum;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nslots; i += blockDim.x)
-        if (hist[i] != 0) atomicAdd(&out[i], hist[i]);
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+        double t = 0;
+        #pragma unroll
+        for (int w = 0; w < PK_WARPS; w++) t += hist_all[(size_t) w * nslots + i];
+        if (t != 0) atomicAdd(&out[i], t);
+    }
 }
 
 // out[3*nbins + 1] = geometry sums (cached) and data sums laid out as the callers expect: [sum w][sum w |d|^2][sum w k][variance]
@@ -319,25 +329,26 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
 {
     const FpmGeom &g = m->geom;
     const int nbins = g.n / 2;
-    const size_t smem = sizeof(double) * (2 * nbins + 1);
+    const size_t smem_geom = sizeof(double) * (size_t) (2 * nbins) * PK_WARPS, smem_data = sizeof(double) * (size_t) (nbins + 1) * PK_WARPS;
     static bool attr_done = false;
     if (!attr_done) {
-        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    if (smem > 96 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
+    if (smem_geom > 227 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
+    const int ctas_per_sm = smem_data <= 56 * 1024 ? 4 : (smem_data <= 75 * 1024 ? 3 : (smem_data <= 113 * 1024 ? 2 : 1));
     const double k0 = 2 * M_PI / g.boxsize;
     FpmMesh *mm = const_cast<FpmMesh *>(m);           // the per-mesh cache of the geometry sums
     if (!mm->d_pkgeom) {
         FPM_CUDA_OK(cudaMalloc(&mm->d_pkgeom, sizeof(double) * (3 * nbins + 1)));
         FPM_CUDA_OK(cudaMemsetAsync(mm->d_pkgeom, 0, sizeof(double) * (3 * nbins + 1), st));
-        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<true><<<148 * 4, 32 * PK_WARPS, smem, st>>>(g, m->d_decic, 0, nullptr, k0, mm->d_pkgeom)));
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<true><<<148, 32 * PK_WARPS, smem_geom, st>>>(g, m->d_decic, 0, nullptr, k0, mm->d_pkgeom)));
         FPM_CHECK_LAUNCH();
     }
     double *d_data = mm->d_pkgeom + 2 * nbins;        // [nbins] + 1
     FPM_CUDA_OK(cudaMemsetAsync(d_data, 0, sizeof(double) * (nbins + 1), st));
-    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * 4, 32 * PK_WARPS, smem, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * PK_WARPS, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
     FPM_CHECK_LAUNCH();
     pk_assemble_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(mm->d_pkgeom, d_data, nbins, d_out);
     FPM_CHECK_LAUNCH();

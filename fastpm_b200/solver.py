@@ -54,6 +54,7 @@ def _bind(lib):
     lib.fastpm_b200_solver_lptpm.argtypes = [vp]
     lib.fastpm_b200_store_np.restype = i64
     lib.fastpm_b200_store_np.argtypes = [vp]
+    lib.fastpm_b200_store_set_np.argtypes = [vp, i64]
     lib.fastpm_b200_store_meta.argtypes = [vp, vp]
     lib.fastpm_b200_store_set_meta.argtypes = [vp, vp]
     lib.fastpm_b200_store_column_ptr.restype = vp
@@ -117,6 +118,10 @@ class Solver:
     @property
     def np(self):
         return int(self.lib.fastpm_b200_store_np(self.cdm))
+
+    def set_np(self, n):
+        if self.lib.fastpm_b200_store_set_np(self.cdm, int(n)) != 0:
+            raise _lib.FastPMB200Error("particle count %d exceeds the allocated %s" % (n, "np_upper"))
 
     def column_ptr(self, name):
         return self.lib.fastpm_b200_store_column_ptr(self.cdm, COLUMNS[name])

@@ -490,6 +490,7 @@ void gravity_apply_kernel_transfer(FastPMKernelType kernel, PM *pm, FastPMFloat 
  * Host mirrors of device-resident data, for callers (snapshot writers, FOF, lightcone, custom event
  * handlers) that the reference lets dereference mesh buffers and store columns directly. */
 /* copy `count` elements of a store column to / from host memory (elements are whole rows, e.g. double[3]) */
+int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count);
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count);
 /* mesh buffers: copy to / from a host array in the REFERENCE's layouts -- real [x][y][N+2] floats

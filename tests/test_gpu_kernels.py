@@ -71,6 +71,34 @@ def test_readout_bit_exact(dev, ref_mod, nmesh, kind):
     s.close()
 
 
+def test_empty_and_single_particle(dev, ref_mod):
+    """Edge cases of the store loops (painter.c:320-374, factors.c:176-197): np = 0 leaves everything untouched, np = 1 on a
+    cell corner, on the box edge and outside the box deposits unit mass into the periodic images the reference uses."""
+    nmesh, L = 16, 32.0
+    m = dev.Mesh(nmesh, L)
+    lib = m.lib
+    canvas = m.alloc()
+    xd = dev.DeviceBuffer(24)
+    m.paint(canvas, xd, 0)
+    out = dev.DeviceBuffer(4)
+    out.upload(np.array([7.0], dtype=np.float32))
+    m.readout(canvas, xd, 0, out)
+    dev.check(lib.fpm_kick(out.ptr, out.ptr, out.ptr, None, None, 0, 0, 1.0, 0.0, 0.0, 0.0, 0.0))
+    dev.check(lib.fpm_wrap(xd.ptr, 0, L))
+    assert m.download_real(canvas).sum() == 0 and out.download(np.float32)[0] == 7.0
+    s = ref_mod.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    for pos in ([0.0, 0.0, 0.0], [L, L, L], [-0.25, L + 0.5, 3.0 * L + 1.0], [L - 1e-12, 1.0, 2.0]):
+        x = np.array([pos], dtype=np.float64)
+        canvas.zero()
+        xd.upload(x)
+        m.paint(canvas, xd, 1, M0=1.0)
+        got = m.download_real(canvas)
+        want = s.real_view(s.paint(x))
+        assert np.array_equal(got, want), pos             # a single particle: no summation-order freedom, bit-exact
+        assert abs(got.sum(dtype=np.float64) - 1.0) < 1e-6
+    s.close()
+
+
 def test_brick_traversal_is_a_permutation(dev):
     """The Lagrangian-brick walk of paint / readout (large meshes) visits every particle exactly once: same mesh (up to the
     order of float additions) and bit-identical readout as the linear walk, including a tail that is not a whole group."""
