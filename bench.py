@@ -36,6 +36,15 @@ def read_pk():
     return tab[:, 0].copy(), tab[:, 1].copy()
 
 
+def measured_traffic(nmesh):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)["fft_tile_bytes_per_launch"][str(nmesh)])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -115,7 +124,7 @@ def run_reference_arm(args):
     nc_s = args.ref_nc
     r = cpu_reference_run(nc_s, args.pm_nc_factor, args.mode, args.steps, args.warmup, threads)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfastpm_ref.so is not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libfastpm_ref.so is not built"})
         return 0
     sample = "nc=%d^3 particles, %d^3 mesh, %s, %d steps (bounded sample of the nc=%d workload)" % (
         nc_s, nc_s * args.pm_nc_factor, args.mode, args.steps, args.nc)
@@ -127,7 +136,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -282,7 +291,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "fft_tile_kernel (strided y/x FFT pass)", "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": measured_traffic(N), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": round(avg_ms, 4)},
         "fft": {"gbs_6S": round(fft_gbs, 1), "frac_of_peak": round(fft_gbs / peak, 4), "ms_per_transform": round(t_transform_ms, 4),
                 "transforms": n_transforms},
@@ -300,12 +309,32 @@ def run_ours(args):
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref not built"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     g.close()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Prints the one JSON line on the process's original stdout (fd 1 itself is redirected to stderr in main(), so that
+    banners printed by native libraries -- e.g. NCCL's version line -- cannot end up next to it)."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = os.environ.get("FASTPM_B200_BENCH_STDOUT_FD")       # set by main(); also seen by `import bench` from fastpm_b200.multigpu
+    if fd is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(int(fd), data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.environ["FASTPM_B200_BENCH_STDOUT_FD"] = str(_REAL_STDOUT)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -127,6 +127,9 @@ static int mesh_barrier(FpmMesh *m, cudaStream_t st) { (void) m; return fpm_xbar
 // ------------------------------------------------------------------ distributed transforms
 // peers[d] = rank d's buffer (peers[rank] = the local one); the FFT code (fft.cu) puts a barrier before and after
 // the transposing pass through m->barrier.
+// local staging mesh for the slab transposes of this mesh (fft.cu: staged_transpose); NULL = direct peer stores
+extern "C" int fpm_mesh_set_stage(fpm_mesh *m, float *stage) { m->stage = stage; return 0; }
+
 int fpm_lazy_touch(const void *p, size_t bytes);      // capi.cu: applies a deferred deconvolution of that buffer first
 extern "C" int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale)
 {

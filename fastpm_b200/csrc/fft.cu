@@ -28,6 +28,9 @@ struct TilePassArgs {
     size_t dst_estride;
     size_t dst_ostride;
     int dst_ooffset;        // added to the outer index on the destination side
+    int self_rank, self_ooffset;        // staged transpose: rows of rank self_rank (>= 0) go straight to self_dst
+    float2 *self_dst;
+    size_t self_estride, self_ostride;
     int ntile_k;            // tiles along kz
     int conj;               // 1: inverse transform by conjugation
     int outer0;             // global index of outer 0 (ky0 for B1: needed by the transfer)
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(512) fft_tile_kernel(const TilePassArgs a)
             const int kl = k - d * a.rows_per_rank;
             float2 v = smem[pos * K + c];
             if (a.conj) v.y = -v.y;
-            a.dst[d][(size_t) kl * a.dst_estride + obase] = v;
+            if (d == a.self_rank) a.self_dst[(size_t) kl * a.self_estride + (size_t) (a.self_ooffset + o) * a.self_ostride + kz0 + c] = v;
+            else a.dst[d][(size_t) kl * a.dst_estride + obase] = v;
         }
     }
 }
@@ -302,6 +306,57 @@ static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaSt
     return 0;
 }
 
+// ------------------------------------------------------------------ staged slab transpose (several GPUs)
+// The transposing pass writes rows of K*8 = 64..128 contiguous bytes; sent straight over NVLink such small stores reach about
+// half of the link rate.  Staged: the pass writes into a LOCAL buffer laid out [destination rank][its row][my plane][kz],
+// chunk of planes by chunk, and each finished chunk is pushed to its owners by the copy engines as large 2-D copies on a second
+// stream while the next chunk is being transformed -- NVLink runs at its bulk rate, overlapped with the arithmetic.
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_ev_chunk[8], g_ev_done;
+static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float *const *final_peers, int nouter, int off0, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const FpmFftPlan *p = m->plan;
+    const int G = g.nranks, n = g.n, per = n / G;          // rows per destination rank
+    const size_t pc = (size_t) g.pitch_c, plane = (size_t) n * pc;
+    if (!g_copy_stream) {
+        FPM_CUDA_OK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_chunk[i], cudaEventDisableTiming));
+        FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
+    }
+    float2 *stage = reinterpret_cast<float2 *>(m->stage);
+    const size_t blk = (size_t) per * nouter * pc;          // one destination's block: [per rows][nouter planes][pitch_c]
+    // my own rows keep the direct destination the caller set up (final layout); everybody else's go to their staging block
+    a.self_rank = g.rank; a.self_dst = a.dst[g.rank]; a.self_estride = a.dst_estride; a.self_ostride = a.dst_ostride;
+    const int self_ooffset0 = a.dst_ooffset;
+    for (int d = 0; d < G; d++) a.dst[d] = stage + (size_t) d * blk;
+    a.rows_per_rank = per; a.dst_estride = (size_t) nouter * pc; a.dst_ostride = pc;
+    int nch = nouter >= 64 ? 4 : 1;
+    while (nouter % nch) nch--;
+    const int cp = nouter / nch;
+    const int outer0 = a.outer0;
+    for (int ch = 0; ch < nch; ch++) {
+        a.src = src + (size_t) ch * cp * plane;
+        a.dst_ooffset = ch * cp;
+        a.self_ooffset = self_ooffset0 + ch * cp;
+        a.outer0 = outer0 + ch * cp;
+        if (launch_tile(p, a, cp, st)) return -1;
+        FPM_CUDA_OK(cudaEventRecord(g_ev_chunk[ch], st));
+        FPM_CUDA_OK(cudaStreamWaitEvent(g_copy_stream, g_ev_chunk[ch], 0));
+        for (int dd = 0; dd < G - 1; dd++) {
+            const int d = (g.rank + 1 + dd) % G;            // start with the neighbour: spreads the traffic over the links
+            // my planes [off0 + ch*cp, +cp) of every row kl that rank d owns: final[d][kl][off0 + ch*cp ..][kz]
+            float2 *dst = reinterpret_cast<float2 *>(final_peers[d]) + (size_t) (off0 + ch * cp) * pc;
+            const float2 *s2 = stage + (size_t) d * blk + (size_t) ch * cp * pc;
+            FPM_CUDA_OK(cudaMemcpy2DAsync(dst, plane * sizeof(float2), s2, (size_t) nouter * pc * sizeof(float2),
+                                          (size_t) cp * pc * sizeof(float2), per, cudaMemcpyDeviceToDevice, g_copy_stream));
+        }
+    }
+    FPM_CUDA_OK(cudaEventRecord(g_ev_done, g_copy_stream));
+    FPM_CUDA_OK(cudaStreamWaitEvent(st, g_ev_done, 0));
+    return 0;
+}
+
 // ------------------------------------------------------------------ transforms
 // Forward: real -> cplx, scaled by `scale`.  `work` receives the z- and y-pass intermediate (pass `real`
 // itself to transform in place and destroy the input).  cplx_peers[d] is rank d's k-space buffer
@@ -320,11 +375,13 @@ int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cpl
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // F2: outer = local x plane, rows = y; destination [ky][x][kz]
     TilePassArgs a = {};
+    a.self_rank = -1;
     a.src = reinterpret_cast<const float2 *>(real); a.src_estride = g.pitch_c; a.src_ostride = plane;
     for (int d = 0; d < g.nranks; d++) a.dst[d] = reinterpret_cast<float2 *>(cplx_peers[d]);
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.x0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 0; a.outer0 = g.x0; a.t = p->tN; a.xfer.active = 0; a.kt = m->ktab;
-    if (launch_tile(p, a, g.nxl, st)) return -1;
+    if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, cplx_peers, g.nxl, g.x0, st)) return -1; }
+    else if (launch_tile(p, a, g.nxl, st)) return -1;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // F3: in place on the local k-space buffer: outer = local ky plane, rows = kx
     TilePassArgs b = a;
@@ -346,13 +403,15 @@ int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *
     const size_t plane = (size_t) n * g.pitch_c;
     // B1: outer = local ky plane, rows = kx; destination [x][ky][kz]
     TilePassArgs a = {};
+    a.self_rank = -1;
     a.src = reinterpret_cast<const float2 *>(cplx); a.src_estride = g.pitch_c; a.src_ostride = plane;
     for (int d = 0; d < g.nranks; d++) a.dst[d] = reinterpret_cast<float2 *>(real_peers[d]);
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.y0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 1; a.outer0 = g.y0; a.t = p->tN; a.kt = m->ktab;
     if (xfer) a.xfer = *xfer; else a.xfer.active = 0;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
-    if (launch_tile(p, a, g.nyl, st)) return -1;
+    if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, real_peers, g.nyl, g.y0, st)) return -1; }
+    else if (launch_tile(p, a, g.nyl, st)) return -1;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // B2: in place, outer = local x plane, rows = ky
     float *real = real_peers[g.rank];
@@ -374,6 +433,7 @@ int fpm_fft_tma_pass_from_tile(int n, const TilePassArgs &a, int pitch_c, int no
     TmaPassArgs t;
     for (int d = 0; d < FPM_MAX_RANKS; d++) t.dst[d] = a.dst[d];
     t.rows_per_rank = a.rows_per_rank; t.dst_estride = a.dst_estride; t.dst_ostride = a.dst_ostride; t.dst_ooffset = a.dst_ooffset;
+    t.self_rank = a.self_rank; t.self_ooffset = a.self_ooffset; t.self_dst = a.self_dst; t.self_estride = a.self_estride; t.self_ostride = a.self_ostride;
     t.ntile_k = 0; t.nouter = nouter; t.conj = a.conj; t.outer0 = a.outer0; t.tw = a.t.tw; t.xfer = a.xfer; t.kt = a.kt;
     return fpm_fft_tma_pass(n, a.src, pitch_c, nouter, t, st);
 }

@@ -32,7 +32,9 @@ __device__ __forceinline__ float2 *pick_dst(const TmaPassArgs &a, int d)
 
 #include "fft_reg.cuh"
 
-template <int R1, int R2, int R3, int K>
+// MULTI: the output rows are spread over several destination buffers (slab transpose on several GPUs).  A separate
+// instantiation: the extra addressing of that path costs the one-GPU kernel registers and 30 % of its speed otherwise.
+template <int R1, int R2, int R3, int K, bool MULTI>
 __global__ void __launch_bounds__(TmaCfg<R1, R2, R3>::T * K, (TmaCfg<R1, R2, R3>::T * K <= 512) ? 2 : 1)
 fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
 {
@@ -76,7 +78,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     // per-thread constant addresses
     const float2 *Ard = A + t * K + c;                                                   // + k*M1*K
     Fft3<R1, R2, R3, K, true> fx(B, t, c, TW);
-    const bool single = (a.rows_per_rank == N);
+    constexpr bool single = !MULTI;
     const int h = N / 2;
 
     // The gravity kernel, specialised for the tile pass (operations of fpm_apply_transfer, mesh.cuh, i.e. of
@@ -177,7 +179,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
         if (a.early == 5) prefetch_next();
         // ---- store: frequency kf = q1 + R1*q2 + R1*R2*q3, K*8 B contiguous per row
         const size_t obase = (size_t) (a.dst_ooffset + o) * a.dst_ostride + kz0 + c;
-        if (single) {
+        if constexpr (single) {
             float2 *d0 = a.dst[0] + obase;
             const size_t s3 = (size_t) (R1 * R2) * a.dst_estride;
             #pragma unroll
@@ -192,6 +194,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
                 }
             }
         } else {
+            const size_t obase_self = (size_t) (a.self_ooffset + o) * a.self_ostride + kz0 + c;
             #pragma unroll
             for (int i = 0; i < E / R3; i++) {
                 const int b = t + i * T, q1 = b / R2, q2 = b - q1 * R2;
@@ -201,7 +204,8 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
                     const int d = kf / a.rows_per_rank, kl = kf - d * a.rows_per_rank;
                     float2 y = v[i * R3 + q3];
                     if (a.conj) y.y = -y.y;
-                    pick_dst(a, d)[(size_t) kl * a.dst_estride + obase] = y;
+                    if (d == a.self_rank) a.self_dst[(size_t) kl * a.self_estride + obase_self] = y;
+                    else pick_dst(a, d)[(size_t) kl * a.dst_estride + obase] = y;
                 }
             }
         }
@@ -228,7 +232,8 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
     const size_t smem = (size_t) C::N * K * 8 + (size_t) C::N * K * 4 + (size_t) C::N * 8;
     static bool attr = false;
     if (!attr) {
-        FPM_CUDA_OK(cudaFuncSetAttribute(fft_tma_kernel<R1, R2, R3, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        FPM_CUDA_OK(cudaFuncSetAttribute(fft_tma_kernel<R1, R2, R3, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        FPM_CUDA_OK(cudaFuncSetAttribute(fft_tma_kernel<R1, R2, R3, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr = true;
     }
     const int ntiles = a.nouter * a.ntile_k;
@@ -236,7 +241,8 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
     const int grid = ntiles < nsm * per_sm ? ntiles : nsm * per_sm;
     if (grid <= 0) return 0;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_TILE, st);
-    fft_tma_kernel<R1, R2, R3, K><<<grid, C::T * K, smem, st>>>(tmap, a);
+    if (a.rows_per_rank == C::N) fft_tma_kernel<R1, R2, R3, K, false><<<grid, C::T * K, smem, st>>>(tmap, a);
+    else fft_tma_kernel<R1, R2, R3, K, true><<<grid, C::T * K, smem, st>>>(tmap, a);
     if (fpm_prof_on) fpm_prof_end(FPM_K_FFT_TILE, st);
     FPM_CHECK_LAUNCH();
     return 0;

@@ -8,6 +8,10 @@ struct TmaPassArgs {
     int rows_per_rank;
     size_t dst_estride, dst_ostride;
     int dst_ooffset;
+    // staged slab transpose: rows owned by rank `self_rank` (>= 0) bypass the staging block and go to their final place
+    int self_rank, self_ooffset;
+    float2 *self_dst;
+    size_t self_estride, self_ostride;
     int ntile_k, nouter;
     int conj;
     int chunk;                  // kz-adjacent tiles a CTA processes back to back

@@ -19,6 +19,7 @@ void *fpm_ipc_open(const void *handle64, uint64_t offset);
 int fpm_xbarrier_init(int nranks, int rank, void *local_flags);
 int fpm_xbarrier_set_peers(void *const *peer_flag_ptrs);
 int fpm_xbarrier(void);
+int fpm_mesh_set_stage(fpm_mesh *m, float *stage);
 int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale);
 int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel);
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
@@ -133,9 +134,18 @@ void fpm_halo_fetch(PM *pm, FastPMFloat *canvas)
     FPM_MUST(fpm_halo_fetch_from(pm->mesh, canvas, peers[(g_rank + 1) % g_size]));
 }
 
+/* one extra mesh per PM: the slab transposes are staged locally and pushed by the copy engines (csrc/fft.cu) */
+static void ensure_stage(PM *pm)
+{
+    if (pm->stage || getenv("FASTPM_B200_NO_STAGE")) return;
+    pm->stage = fastpm_memory_alloc(pm->mem, "FFT transpose staging", sizeof(FastPMFloat) * pm->allocsize, FASTPM_MEMORY_FLOATING);
+    FPM_MUST(fpm_mesh_set_stage(pm->mesh, pm->stage));
+}
+
 void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale)
 {
     void *peers[MAXR];
+    ensure_stage(pm);
     if (real == cplx) fastpm_raise(-1, "distributed r2c is out of place\n");
     peers_of(cplx, peers);
     FPM_MUST(fpm_r2c_dist(pm->mesh, real, (float *const *) peers, scale));
@@ -144,6 +154,7 @@ void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale)
 void fpm_dist_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel)
 {
     void *peers[MAXR];
+    ensure_stage(pm);
     if (real == cplx) fastpm_raise(-1, "distributed c2r is out of place\n");
     peers_of(real, peers);
     FPM_MUST(fpm_c2r_dist(pm->mesh, cplx, (float *const *) peers, kernel));

@@ -28,6 +28,7 @@ struct PM {
     double CellSize[3], InvCellSize[3];
     FastPMMemory *mem;
     FastPMFloat *scratch;         /* lazily allocated, for the in-place public pm_c2r / pm_r2c */
+    FastPMFloat *stage;           /* several GPUs: staging mesh of the slab transposes (lazily allocated) */
     int transposed;
     int pitch_r, pitch_c, nxl, x0, nyl, y0, halo;
 };

@@ -87,6 +87,7 @@ struct FpmMesh {
     double *d_pkgeom;       // P(k) cache: [2][n/2] sum w, sum w|k| of this rank's modes (geometry only), then [n/2 + 1] scratch
     fpm_barrier_fn barrier; // cross-GPU barrier between a transposing pass and the next (multi-GPU only)
     void *comm;             // opaque communicator (multi-GPU only)
+    float *stage;           // multi-GPU: local staging mesh for the slab transpose (NULL: store straight into the peers)
 };
 
 int fpm_fft_plan_create(int n, FpmFftPlan **out);

@@ -188,7 +188,7 @@ def bench_main(args):
         "pk_last_bin1": float(spectra[-1][1][1]) if spectra else None,
     }
     if rank == 0:
-        print(json.dumps(line))
+        B.emit(line)
     g.close()
     dist.barrier()
     return 0
