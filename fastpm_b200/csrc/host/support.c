@@ -236,6 +236,37 @@ void fastpm_b200_arena_destroy(void)
     arena_base = NULL; arena_size = 0; arena_blocks = NULL; arena_nblocks = 0;
 }
 
+/* Host-only self test of the arena's placement policy (no device memory is touched: a fake base address is used).  The
+ * multi-GPU design rests on it being deterministic -- the same sequence of sizes must give the same offsets on every rank --
+ * first-fit, 1 MiB granular, reusing freed gaps and failing cleanly when full.  Returns 0 on success, else the failed check. */
+int fastpm_b200_arena_selftest(void)
+{
+    if (arena_base) return -1;                         /* only before a real arena exists */
+    int bad = 0;
+    const size_t MiB = ARENA_ALIGN;
+    for (int pass = 0; pass < 2 && !bad; pass++) {     /* two identical passes: identical offsets (determinism) */
+        static size_t first[6];
+        arena_base = (char *) (uintptr_t) 0x100000000ull; arena_size = 64 * MiB; arena_blocks = NULL; arena_nblocks = 0;
+        char *a = arena_alloc(1), *b = arena_alloc(10 * MiB), *c = arena_alloc(3 * MiB + 5), *d = arena_alloc(20 * MiB);
+        size_t off[6] = { (size_t) (a - arena_base), (size_t) (b - arena_base), (size_t) (c - arena_base), (size_t) (d - arena_base), 0, 0 };
+        if (off[0] != 0 || off[1] != MiB || off[2] != 11 * MiB || off[3] != 15 * MiB) bad = 1;      /* packed, rounded up to 1 MiB */
+        arena_free(b);                                   /* a 10 MiB gap at 1 MiB */
+        char *e = arena_alloc(12 * MiB);                 /* does not fit the gap: goes behind d */
+        char *f = arena_alloc(4 * MiB);                  /* first fit: into the gap */
+        off[4] = (size_t) (e - arena_base); off[5] = (size_t) (f - arena_base);
+        if (!bad && (off[4] != 35 * MiB || off[5] != MiB)) bad = 2;
+        if (!bad && arena_alloc(30 * MiB) != NULL) bad = 3;                    /* 47 MiB used at the top: 17 left */
+        if (!bad && arena_alloc(17 * MiB) == NULL) bad = 4;                    /* exactly the tail */
+        if (!bad && !fastpm_b200_arena_contains(f)) bad = 5;
+        if (!bad && fastpm_b200_arena_contains(arena_base + arena_size)) bad = 6;
+        if (pass == 0) memcpy(first, off, sizeof(off));
+        else if (!bad && memcmp(first, off, sizeof(off))) bad = 7;
+        free(arena_blocks);
+    }
+    arena_base = NULL; arena_size = 0; arena_blocks = NULL; arena_nblocks = 0;
+    return bad;
+}
+
 void *fastpm_memory_alloc_details(FastPMMemory *m, const char *name, size_t s, enum FastPMMemoryLocation loc, const char *file, const int line)
 {
     if (s == 0) s = 1;

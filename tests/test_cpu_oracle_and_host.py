@@ -180,3 +180,9 @@ def test_product_fails_loudly_without_a_device(lib):
         _lib.require_device(0)
     assert lib.fpm_malloc(1024) is None
     assert b"CUDA device" in lib.fpm_last_error()
+
+
+def test_symmetric_arena_placement_is_deterministic(lib):
+    """The multi-GPU buffers of every rank live at the same offsets of a per-process arena (csrc/host/support.c): the
+    placement policy (first fit, 1 MiB granular, gap reuse, clean failure when full) is checked on the host."""
+    assert lib.fastpm_b200_arena_selftest() == 0
