@@ -186,3 +186,43 @@ def test_symmetric_arena_placement_is_deterministic(lib):
     """The multi-GPU buffers of every rank live at the same offsets of a per-process arena (csrc/host/support.c): the
     placement policy (first fit, 1 MiB granular, gap reuse, clean failure when full) is checked on the host."""
     assert lib.fastpm_b200_arena_selftest() == 0
+
+
+def test_register_fft_emulated_on_cpu(tmp_path):
+    """struct Fft3 of csrc/fft_reg.cuh -- the register-resident three-stage transform inside the TMA tile pass and the row
+    pass -- run on the CPU with one OS thread per CUDA thread and a pthread barrier for __syncthreads(), for every mesh size
+    the fast path supports (512 ... 4096), against a naive double-precision DFT (tests/emul/fft_reg_emul.cpp)."""
+    import subprocess
+    exe = str(tmp_path / "fft_reg_emul")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-w", "-I" + inc, "-o", exe, os.path.join(ROOT, "tests", "emul", "fft_reg_emul.cpp")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 8 and all(l.endswith("OK") for l in lines), r.stdout
+
+
+def test_generic_fft_passes_emulated_on_cpu(tmp_path):
+    """The mixed-radix (2, 3, 4, 5) shared-memory FFT stages, digit-reversal tables and the real <-> half-complex untangling of
+    csrc/fft_core.h are plain inline functions: tests/emul/fft_emul.cpp runs them thread by thread on the CPU against a naive
+    double-precision DFT (the GPU tests then only have to show that the kernels launch them correctly)."""
+    import subprocess
+    exe = str(tmp_path / "fft_emul")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-I" + inc, "-o", exe, os.path.join(ROOT, "tests", "emul", "fft_emul.cpp")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert lines and all(l.endswith("OK") for l in lines), r.stdout
