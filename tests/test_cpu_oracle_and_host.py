@@ -226,3 +226,40 @@ def test_generic_fft_passes_emulated_on_cpu(tmp_path):
     assert r.returncode == 0, r.stdout
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert lines and all(l.endswith("OK") for l in lines), r.stdout
+
+
+def test_fused_green_function_rounding_claim():
+    """The fused tile pass (csrc/fft_tma.cu) evaluates the reference's (float)((double) v * (1 / sum kk)) of transfer.c:171-179
+    without the FP64 pipe: sum kk as a float pair, q = v * rcp(s_hi) corrected once with the exact remainder.  Restated here
+    with numpy in the same operation order, for an exact, a +1 ulp and a -1 ulp reciprocal estimate (rcp.approx is within one
+    ulp): the result is the reference's float except for at most a few modes in a million, and then by one ulp."""
+    rng = np.random.default_rng(5)
+    n, L = 1024, 1024.0
+    ii = np.arange(n)
+    ii = np.where(ii >= n // 2, ii - n, ii)
+    k = (ii * 2 * np.pi / L).astype(np.float32)          # pmapi.c:255-262: float k, float k*k
+    kk = (k * k).astype(np.float32)
+    M = 1_000_000
+    ix, iy, iz = rng.integers(0, n, M), rng.integers(0, n, M), rng.integers(0, n // 2 + 1, M)
+    good = (ix != 0) | (iy != 0) | (iz != 0)
+    ix, iy, iz = ix[good], iy[good], iz[good]
+    v = (rng.standard_normal(len(ix)) * 1e-3).astype(np.float32)
+    s = kk[ix].astype(np.float64) + kk[iy].astype(np.float64) + kk[iz].astype(np.float64)
+    ref = (v.astype(np.float64) * (1.0 / s)).astype(np.float32)
+    sd = (kk[iy].astype(np.float64) + kk[iz].astype(np.float64)) + kk[ix].astype(np.float64)
+    assert np.array_equal(sd, s)                          # the sum of three floats is exact in double in any order
+    s_hi = sd.astype(np.float32)
+    s_lo = (sd - s_hi.astype(np.float64)).astype(np.float32)
+
+    def fma(a, b, c):                                     # a*b is exact in double; one rounding to float like fmaf
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    for pert in (0, 1, -1):
+        r = (np.float32(1.0) / s_hi).astype(np.float32)
+        if pert:
+            r = np.nextafter(r, np.float32(np.inf if pert > 0 else -np.inf)).astype(np.float32)
+        q = (v * r).astype(np.float32)
+        out = fma(fma(-q, s_lo, fma(-q, s_hi, v)), r, q)
+        ulp = np.abs(out.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1
+        assert (ulp != 0).sum() <= 5, (pert, int((ulp != 0).sum()))
