@@ -57,6 +57,7 @@ int fpm_induce_launch(const FpmMesh *m, float *dk, const double *d_tk, const dou
 int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed, cudaStream_t st);
 int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, float re, float im, cudaStream_t st);
 void fpm_fft_force_generic(int on);
+int fpm_gadget_fill_launch(const FpmMesh *m, float *dk, int seed, cudaStream_t st);
 void fpm_set_lagrangian_hint(int nc);
 
 // ------------------------------------------------------------------ runtime state
@@ -480,6 +481,13 @@ int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host,
     cudaStreamSynchronize(g_stream);
     cudaFree(d_k); cudaFree(d_p);
     return rc;
+}
+
+int fpm_fill_gaussian_gadget(const fpm_mesh *m, float *cplx, int seed)
+{
+    if (ensure_init()) return -1;
+    LAZY1(cplx);
+    return fpm_gadget_fill_launch(m, cplx, seed, g_stream);
 }
 
 int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed) { LAZY1(real); return fpm_whitenoise_launch(m, real, seed, g_stream); }

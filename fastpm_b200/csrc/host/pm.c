@@ -152,6 +152,14 @@ void fastpm_apply_modify_mode_transfer(PM *pm, FastPMFloat *from, FastPMFloat *t
 }
 
 static struct { fastpm_fkfunc f; void *d; } induce_cb;
+/* initialcondition.c:10-27: the Gadget scheme (the default of the CLI, src/fastpm.c:478) runs on the device */
+void fastpm_ic_fill_gaussiank(PM *pm, FastPMFloat *delta_k, int seed, enum FastPMFillDeltaKScheme scheme)
+{
+    if (scheme != FASTPM_DELTAK_GADGET)
+        fastpm_raise(-1, "fastpm_b200: only the FASTPM_DELTAK_GADGET scheme of fastpm_ic_fill_gaussiank is implemented\n");
+    FPM_MUST(fpm_fill_gaussian_gadget(pm->mesh, delta_k, seed));
+}
+
 void fastpm_ic_induce_correlation(PM *pm, FastPMFloat *delta_k, fastpm_fkfunc pkfunc, void *data)
 {
     /* initialcondition.c:56-64 multiplies by sqrt(P(k)/V) through a host callback per mode.  A host callback

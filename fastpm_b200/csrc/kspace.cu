@@ -7,6 +7,8 @@
 // k-space layout of this build: cplx[ky_local][kx][kz] with pitch_c complex per row (see common.cuh).
 #include "common.cuh"
 #include "mesh.cuh"
+#include "ic_gadget.h"
+#include <vector>
 
 // ------------------------------------------------------------------ generic mode iterator
 // one thread per complex element of the local k-space block, kz fastest (coalesced)
@@ -298,6 +300,19 @@ __global__ void set_mode_kernel(const FpmGeom g, float2 *dk, int ix, int iy, int
     dk[((size_t) iyl * g.n + ix) * g.pitch_c + iz] = make_float2(re, im);
 }
 
+// ------------------------------------------------------------------ Gadget-scheme Gaussian field (ic_gadget.h)
+// One thread per (kx, ky_local) column of this rank's k-space slab; every thread runs its two RANLUX generators (local
+// memory) down kz.  The rows are written one float2 at a time (uncoalesced): an initial-condition step, run once.
+__global__ void __launch_bounds__(64) gadget_fill_kernel(const FpmGeom g, const unsigned int *__restrict__ self,
+        const unsigned int *__restrict__ conj, float2 *__restrict__ dk)
+{
+    const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t) g.nyl * g.n) return;
+    const int i = (int) (idx % g.n), jl = (int) (idx / g.n), j = jl + g.y0;
+    const size_t q = (size_t) i * g.n + j;
+    fpm_gadget_fill_column(g.n, i, j, self[q], conj[q], dk + ((size_t) jl * g.n + i) * g.pitch_c);
+}
+
 // ------------------------------------------------------------------ launchers
 static inline unsigned sweep_grid(size_t n)
 {
@@ -392,6 +407,29 @@ int fpm_whitenoise_launch(const FpmMesh *m, float *real, unsigned long long seed
     const size_t ncell = (size_t) g.nxl * g.n * g.n;
     FPM_TIMED(FPM_K_OTHER, st, (whitenoise_kernel<<<sweep_grid(ncell / 2), 256, 0, st>>>(g, real, seed)));
     FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// pmic_fill_gaussian_gadget (initialcondition.c:145-273): the seed table on the host (a serial stream of ~N^2 draws), the
+// columns on the device.  The whole buffer is cleared first like the reference's memset.
+int fpm_gadget_fill_launch(const FpmMesh *m, float *dk, int seed, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const size_t nn = (size_t) g.n * g.n;
+    std::vector<unsigned int> self(nn), conj(nn);
+    fpm_gadget_seed_table(g.n, seed, self.data(), conj.data());
+    unsigned int *d_tab = NULL;
+    FPM_CUDA_OK(cudaMalloc(&d_tab, 2 * nn * sizeof(unsigned int)));
+    FPM_CUDA_OK(cudaMemcpyAsync(d_tab, self.data(), nn * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+    FPM_CUDA_OK(cudaMemcpyAsync(d_tab + nn, conj.data(), nn * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+    FPM_CUDA_OK(cudaMemsetAsync(dk, 0, cplx_total(g) * sizeof(float2), st));
+    const size_t ncol = (size_t) g.nyl * g.n;
+    FPM_TIMED(FPM_K_OTHER, st, (gadget_fill_kernel<<<(unsigned) ((ncol + 63) / 64), 64, 0, st>>>(g, d_tab, d_tab + nn, (float2 *) dk)));
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(st);                       // the host tables and d_tab go away below
+    cudaFree(d_tab);
+    fpm_launch_counter++;
+    if (e != cudaSuccess) { fpm_set_error("gadget_fill_kernel launch failed: %s", cudaGetErrorString(e)); return -1; }
     return 0;
 }
 

@@ -157,6 +157,10 @@ class Mesh:
         check(self.lib.fpm_powerspectrum(self.h, cplx.ptr, int(decic), k.ctypes.data, p.ctypes.data, nm.ctypes.data), "fpm_powerspectrum")
         return k, p, nm
 
+    def fill_gaussian_gadget(self, cplx, seed):
+        """fastpm_ic_fill_gaussiank(..., FASTPM_DELTAK_GADGET): RANLUX white noise with the Gadget seeding scheme."""
+        check(self.lib.fpm_fill_gaussian_gadget(self.h, cplx.ptr, int(seed)), "fpm_fill_gaussian_gadget")
+
     def induce_correlation(self, cplx, k, p):
         k = np.ascontiguousarray(k, dtype=np.float64)
         p = np.ascontiguousarray(p, dtype=np.float64)

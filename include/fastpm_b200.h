@@ -133,6 +133,10 @@ int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, in
 int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im); /* transfer.c:306 */
 /* delta_k *= sqrt(P(k)/V), P log-log interpolated from the table: initialcondition.c:56-64 */
 int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host, const double *p_host, int size);
+/* Gaussian white noise in k-space with the Gadget / N-GenIC seeding scheme and RANLUX (gsl_rng_ranlxd1), the reference's
+ * default generator: pmic_fill_gaussian_gadget, initialcondition.c:145-273 (fastpm_ic_fill_gaussiank, FASTPM_DELTAK_GADGET).
+ * Same seed -> same field as the reference, up to the last bit of the device's double sin / cos / log. */
+int fpm_fill_gaussian_gadget(const fpm_mesh *m, float *cplx, int seed);
 /* unit-variance real white noise from a counter-based generator (benchmark-size synthetic ICs only) */
 int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed);
 

@@ -359,6 +359,9 @@ double fastpm_powerspectrum_sigma(FastPMPowerSpectrum *ps, double R);
 void fastpm_powerspectrum_scale(FastPMPowerSpectrum *ps, double factor);
 
 /* ------------------------------------------------------------------ [initialcondition.h:3-17] */
+enum FastPMFillDeltaKScheme { FASTPM_DELTAK_GADGET, FASTPM_DELTAK_FAST, FASTPM_DELTAK_SLOW };     /* [initialcondition.h:3-7] */
+/* only the default scheme, FASTPM_DELTAK_GADGET, is implemented (on the device); the others raise */
+void fastpm_ic_fill_gaussiank(PM *pm, FastPMFloat *delta_k, int seed, enum FastPMFillDeltaKScheme scheme);
 void fastpm_ic_induce_correlation(PM *pm, FastPMFloat *delta_k, fastpm_fkfunc pk, void *pkdata);
 
 /* ------------------------------------------------------------------ [pgdcorrection.h:3-11] */

@@ -139,6 +139,12 @@ class Session:
                                   _p(out), C.byref(sigma8))
         return out, float(var), sigma8.value
 
+    def fill_gaussian(self, seed):
+        """Raw Gadget-scheme white noise in k-space on the LPT mesh (pm_alloc layout of lptpm)."""
+        out = self._buf(1, 1.0)
+        lib().ref_fill_gaussian(self._h, C.c_int(seed), _p(out))
+        return out
+
     def setup_lpt(self, delta_k, a0):
         lib().ref_setup_lpt(self._h, _p(np.ascontiguousarray(delta_k, dtype=np.float32)), C.c_double(a0))
         d1, d2 = np.zeros(3), np.zeros(3)

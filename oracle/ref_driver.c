@@ -229,6 +229,16 @@ double ref_ic_deltak(RefSession *s, int seed, int remove_variance, const char *p
     return variance;
 }
 
+/* the raw Gaussian field alone: fastpm_ic_fill_gaussiank with the Gadget scheme (initialcondition.c:145-273) on the LPT mesh */
+void ref_fill_gaussian(RefSession *s, int seed, float *delta_k_out)
+{
+    PM *pm = s->solver->lptpm;
+    FastPMFloat *delta_k = pm_alloc(pm);
+    fastpm_ic_fill_gaussiank(pm, delta_k, seed, FASTPM_DELTAK_GADGET);
+    memcpy(delta_k_out, delta_k, sizeof(FastPMFloat) * pm->allocsize);
+    pm_free(pm, delta_k);
+}
+
 void ref_setup_lpt(RefSession *s, const float *delta_k_in, double a0)
 {
     PM *pm = s->solver->lptpm;
