@@ -17,8 +17,10 @@
 #else
 #define FPM_HD inline
 #include <math.h>
+#ifndef __VECTOR_TYPES_H__       /* a host build that has not pulled in CUDA's vector types */
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
 #endif
 
 #define FPM_FFT_MAX_STAGES 16

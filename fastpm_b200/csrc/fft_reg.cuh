@@ -5,6 +5,9 @@
 #include "common.cuh"
 #include <cuda.h>
 
+#ifndef FPM_EMULATE
+// dynamic shared memory of a kernel
+#define FPM_DYN_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
 // ------------------------------------------------------------------ small PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -12,6 +15,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
+// reciprocal estimate, within one ulp (MUFU.RCP)
+__device__ __forceinline__ float fpm_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -53,6 +59,47 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // makes this thread's generic-proxy shared-memory writes visible to the async proxy (bulk stores)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#else
+// ------------------------------------------------------------------ CPU emulation of the wrappers (tests/emul/*.cpp)
+// Every CUDA thread is an OS thread, __syncthreads() a pthread barrier, shared memory an ordinary array.  Asynchronous copies
+// are done synchronously by the issuing thread; the mbarrier keeps a completed-phase count (low word) and the bytes still
+// expected (high word), so that waiting threads really wait for the data.  A "tensor map" is a plain descriptor.
+#define FPM_DYN_SMEM(name, alignment) unsigned char *name = fpm_emul_dyn_smem
+extern unsigned char *fpm_emul_dyn_smem;
+struct FpmEmulTmap { const float *base; uint64_t gstr_bytes[2]; uint32_t box[3]; };      // lives in the bytes of a CUtensorMap
+inline void mbar_init(uint64_t *bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+inline float fpm_rcp_approx(float x) { return 1.0f / x; }
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t) bytes << 32, __ATOMIC_SEQ_CST); }
+inline void fpm_emul_complete_tx(uint64_t *bar, uint32_t bytes)
+{
+    uint64_t v = __atomic_sub_fetch(bar, (uint64_t) bytes << 32, __ATOMIC_SEQ_CST);
+    if ((v >> 32) == 0) __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);                   // phase complete
+}
+inline void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (((uint32_t) __atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1u) == parity) sched_yield();
+}
+inline void tma_load_3d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2)
+{
+    const FpmEmulTmap *t = reinterpret_cast<const FpmEmulTmap *>(tmap);
+    float *d = (float *) smem_dst;
+    for (uint32_t z = 0; z < t->box[2]; z++)
+        for (uint32_t y = 0; y < t->box[1]; y++) {
+            const float *src = t->base + ((size_t) (c2 + z) * t->gstr_bytes[1] + (size_t) (c1 + y) * t->gstr_bytes[0]) / 4 + c0;
+            memcpy(d, src, t->box[0] * 4);
+            d += t->box[0];
+        }
+    fpm_emul_complete_tx(bar, t->box[0] * t->box[1] * t->box[2] * 4);
+}
+inline void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) { memcpy(smem_dst, gsrc, bytes); fpm_emul_complete_tx(bar, bytes); }
+inline void bulk_store_1d(void *gdst, const void *smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait0() {}
+inline void fence_async_smem() {}
+#endif
 
 // ------------------------------------------------------------------ register FFT (radix-2 DIF, unrolled)
 // twiddle exp(-2 pi i idx/16), idx = 0..7, as compile-time constants

@@ -41,7 +41,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     using C = TmaCfg<R1, R2, R3>;
     constexpr int N = C::N, E = C::E, T = C::T, M1 = C::M1, M2 = C::M2;
     constexpr int BOX = N < 256 ? N : 256;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FPM_DYN_SMEM(smem_raw, 1024);
     const float2 *A = reinterpret_cast<const float2 *>(smem_raw);            // [N][K] complex, written by TMA
     float *B = reinterpret_cast<float *>(smem_raw + (size_t) N * K * 8);     // [N][K] floats, swizzled rows
     float2 *TW = reinterpret_cast<float2 *>(smem_raw + (size_t) N * K * 12); // [N] exp(-2 pi i t / N)
@@ -55,7 +55,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
 
     if (tid == 0) {
         mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     for (int i = tid; i < N; i += T * K) TW[i] = __ldg(a.tw + i);
     __syncthreads();
@@ -131,8 +131,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
                     const double sd = yz + (double) __ldg(kkt + t + k * M1);
                     const float s_hi = (float) sd;
                     const float s_lo = (float) (sd - (double) s_hi);
-                    float r;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s_hi));
+                    const float r = fpm_rcp_approx(s_hi);
                     const float qx = __fmul_rn(v[k].x, r), qy = __fmul_rn(v[k].y, r);
                     const float rx = __fmaf_rn(-qx, s_lo, __fmaf_rn(-qx, s_hi, v[k].x));
                     const float ry = __fmaf_rn(-qy, s_lo, __fmaf_rn(-qy, s_hi, v[k].y));
@@ -213,6 +212,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
 }
 
 // ------------------------------------------------------------------ host side
+#ifndef FPM_EMULATE          // not part of the CPU emulation of the kernel (tests/emul/tma_emul.cpp)
 static PFN_cuTensorMapEncodeTiled get_encode()
 {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -302,3 +302,4 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     fpm_set_error("fpm_fft_tma_pass: unsupported N = %d", n);
     return -1;
 }
+#endif

@@ -39,7 +39,7 @@ fft_zrow_kernel(const ZRowArgs a)
     constexpr int H = C::N, E = C::E, T = C::T, M1 = C::M1;
     constexpr int P = H + 2;                                    // complex pitch of a staged row (16-byte multiple, banks spread)
     constexpr uint32_t IN_BYTES = (FWD ? H : H + 2) * 8, OUT_BYTES = (FWD ? H + 2 : H) * 8;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FPM_DYN_SMEM(smem_raw, 128);
     float2 *A = reinterpret_cast<float2 *>(smem_raw);          // [8][P]
     float2 *O = PREFETCH ? A + K * P : A;                       // [8][P]; the exchange buffer B aliases it
     float *B = reinterpret_cast<float *>(O);
@@ -53,7 +53,7 @@ fft_zrow_kernel(const ZRowArgs a)
 
     if (tid == 0) {
         mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
@@ -155,6 +155,7 @@ fft_zrow_kernel(const ZRowArgs a)
     if (tid == 0) bulk_wait0();
 }
 
+#ifndef FPM_EMULATE          // host side: not part of the CPU emulation of the kernel (tests/emul/zrow_emul.cpp)
 static int zrow_sm_count()
 {
     static int nsm = 0;
@@ -207,3 +208,4 @@ int fpm_fft_zrow_pass(int n, const float *src, float *dst, size_t nrows, int pit
     fpm_set_error("fpm_fft_zrow_pass: unsupported N = %d", n);
     return -1;
 }
+#endif
