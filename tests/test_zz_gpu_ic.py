@@ -25,3 +25,31 @@ def test_device_gadget_ic_matches_reference(ref_mod, n, seed):
     assert diff.mean() < 1e-3, diff.mean()
     assert np.abs(a - b).max() <= 2e-7 * max(1.0, np.abs(b).max())
     assert abs((np.abs(got) ** 2).mean() - (np.abs(want) ** 2).mean()) < 1e-6
+
+
+def test_libfastpm_user_program_runs_and_matches_fixture(tmp_path):
+    """tests/abi/dropin_example.c (plain C against the libfastpm API names, linked with libfastpm_b200.so) reproduces the
+    committed reference fixture: 2LPT + 3 KDK cycles, positions within 1e-4 Mpc/h."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    from test_abi_layout import build_dropin_example
+    fx = np.load(os.path.join(here, "golden", "small_run.npz"))
+    exe = build_dropin_example(str(tmp_path))
+    dk, ts = str(tmp_path / "dk.f32"), str(tmp_path / "ts.f64")
+    np.ascontiguousarray(fx["delta_k"], dtype=np.float32).tofile(dk)
+    np.ascontiguousarray(fx["steps"], dtype=np.float64).tofile(ts)
+    out_x, out_pk = str(tmp_path / "x.f64"), str(tmp_path / "pk.f64")
+    r = subprocess.run([exe, dk, ts, out_x, out_pk], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    L = 32.0
+    x = np.fromfile(out_x, dtype=np.float64).reshape(-1, 3)
+    d = np.abs(np.mod(x, L) - np.mod(fx["x1"], L))
+    assert np.minimum(d, L - d).max() < 1e-4
+    pk = np.fromfile(out_pk, dtype=np.float64)
+    assert len(pk) == 2 * 16 and np.isfinite(pk).all()
+    want_p, want_k = fx["pk_p"][-1], fx["pk_k"][-1]
+    np.testing.assert_allclose(pk[:16], want_k, rtol=1e-9)
+    np.testing.assert_allclose(pk[16:], want_p, rtol=1e-5)        # the tolerance BASELINE.json states for P(k)
