@@ -177,6 +177,7 @@ __global__ void plane_add_kernel(float *__restrict__ dst, const float *__restric
     for (; i < nfloats; i += stride) dst[i] += src[i];
 }
 
+#ifndef FPM_EMULATE          // host side: not part of the CPU emulation of the kernels (tests/emul/particles_emul.cpp)
 // see cic_particle_index(): a store laid out as i-planes of nc x nc particles (fastpm_store_fill order; on several GPUs the
 // local slab of it, which migration perturbs only slightly) is walked in Lagrangian bricks over its complete groups of 4 planes
 static int g_lag_nc = 0, g_lag_force = 0;
@@ -242,3 +243,4 @@ int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStrea
     FPM_CHECK_LAUNCH();
     return 0;
 }
+#endif

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(256) fill_grid_kernel(double *x, unsigned long
     }
 }
 
+#ifndef FPM_EMULATE          // warp-shuffle reduction and host side: not part of the CPU emulation (tests/emul/particles_emul.cpp)
 // ------------------------------------------------------------------ summary (min, max, sum, sum of squares)
 template <typename T>
 __global__ void __launch_bounds__(256) summary_kernel(const T *col, long long np, int ncomp, double *partial)
@@ -318,3 +319,4 @@ int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, doub
     FPM_CUDA_OK(cudaFree(d_partial));
     return 0;
 }
+#endif

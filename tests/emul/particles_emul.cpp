@@ -1,0 +1,129 @@
+// CPU run of the particle KERNEL SOURCES, fastpm_b200/csrc/paint.cu and csrc/particles.cu (CIC deposit with the vector
+// reductions, the fused periodic wrap and the Lagrangian-brick traversal; CIC readout; kick, drift, fused K-K-D-D update; wrap).
+// These kernels have no barriers: CUDA threads run one after the other, atomics are plain updates, so the deposit happens in
+// particle order -- exactly the reference's serial order (painter.c:320-339 with one OpenMP thread), which makes even the float32
+// mesh comparable bit for bit.  Built with -ffp-contract=off (the kernels are compiled with -fmad=false).
+//
+//   particles_emul <op> <in.bin> <out.bin>     all arrays raw little-endian; layout per op documented at each reader below
+#include "cuda_emul.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <string>
+#include <cuda_runtime.h>
+static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
+static inline void atomicAdd(float2 *p, float2 v) { p->x += v.x; p->y += v.y; }
+static inline void atomicAdd(float4 *p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }
+static inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
+#include "../../fastpm_b200/csrc/paint.cu"
+#include "../../fastpm_b200/csrc/particles.cu"
+
+template <typename Kernel>
+static void launch_seq(unsigned grid, unsigned block, Kernel kernel)
+{
+    gridDim.x = grid; blockDim.x = block;
+    for (unsigned b = 0; b < grid; b++) { blockIdx.x = b; for (unsigned t = 0; t < block; t++) { threadIdx.x = t; kernel(); } }
+}
+
+struct Reader {
+    FILE *f;
+    explicit Reader(const char *fn) : f(fopen(fn, "rb")) { if (!f) { fprintf(stderr, "cannot open %s\n", fn); exit(2); } }
+    template <typename T> T one() { T v; if (fread(&v, sizeof(T), 1, f) != 1) exit(2); return v; }
+    template <typename T> std::vector<T> many(size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) exit(2); return v; }
+};
+template <typename T> static void dump(FILE *f, const std::vector<T> &v) { fwrite(v.data(), sizeof(T), v.size(), f); }
+
+static FpmGeom geom(int n, double L)
+{
+    FpmGeom g;
+    memset(&g, 0, sizeof(g));
+    g.n = n; g.nranks = 1; g.rank = 0; g.nxl = n; g.x0 = 0; g.nyl = n; g.y0 = 0;
+    g.pitch_c = ((n / 2 + 1 + 15) / 16) * 16; g.pitch_r = 2 * g.pitch_c;
+    g.boxsize = L; g.cellsize = L / n; g.inv_cellsize = 1.0 / g.cellsize;
+    return g;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) { fprintf(stderr, "usage: particles_emul op in out\n"); return 2; }
+    const std::string op = argv[1];
+    Reader in(argv[2]);
+    FILE *out = fopen(argv[3], "wb");
+    if (op == "paint" || op == "readout") {
+        // in: int32 n, int32 lag_nc (0 linear, else brick walk), int32 wrap, int32 vec, float64 L, float64 M0, int64 np, x[np][3] f64, (readout: canvas f32)
+        const int n = in.one<int32_t>(), lag_nc = in.one<int32_t>(), wrap = in.one<int32_t>(), vec = in.one<int32_t>();
+        const double L = in.one<double>(), M0 = in.one<double>();
+        const long long np = in.one<int64_t>();
+        std::vector<double> x = in.many<double>((size_t) 3 * np);
+        const FpmGeom g = geom(n, L);
+        std::vector<float> canvas((size_t) n * n * g.pitch_r, 0.f);
+        const unsigned grid = (unsigned) ((np + 255) / 256);
+        int nbrick = 0;
+        if (lag_nc) nbrick = (int) ((np / (4LL * lag_nc * lag_nc)) * (4LL * lag_nc * lag_nc) / 256);
+        int bad = 0;
+        if (op == "paint") {
+            auto k = [&]() {
+                if (wrap) { if (vec == 4) cic_paint_kernel<4, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick);
+                            else cic_paint_kernel<0, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick); }
+                else { if (vec == 4) cic_paint_kernel<4, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick);
+                       else if (vec == 2) cic_paint_kernel<2, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick);
+                       else cic_paint_kernel<0, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick); }
+            };
+            launch_seq(grid, 256, k);
+            std::vector<float> dense((size_t) n * n * n);            // unpadded [x][y][z]
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&dense[((size_t) i * n + j) * n], &canvas[((size_t) i * n + j) * g.pitch_r], sizeof(float) * n);
+            dump(out, dense);
+            dump(out, x);                                              // positions after the fused wrap
+            std::vector<int32_t> flag(1, bad); dump(out, flag);
+        } else {
+            std::vector<float> dense = in.many<float>((size_t) n * n * n);
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
+            std::vector<float> res((size_t) np, 0.f);
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick); });
+            dump(out, res);
+        }
+    } else if (op == "update") {
+        // in: int64 np, int32 cola, int32 drift_mode, kick f64[5] (dda q1 q2 Dv1 Dv2), drift f64[5] (dyyy da1 da2 Dv1 Dv2),
+        //     x f64[3np], v f32[3np], acc f32[3np], dx1 f32[3np], dx2 f32[3np]
+        // out: separate kernels K, D then K, D/2, D/2 (x, v), then the same five operations as ONE fused pass (x, v)
+        const long long np = in.one<int64_t>();
+        const int cola = in.one<int32_t>(), dmode = in.one<int32_t>();
+        std::vector<double> kf = in.many<double>(5), df = in.many<double>(5);
+        std::vector<double> x0 = in.many<double>((size_t) 3 * np);
+        std::vector<float> v0 = in.many<float>((size_t) 3 * np), acc = in.many<float>((size_t) 3 * np), d1 = in.many<float>((size_t) 3 * np), d2 = in.many<float>((size_t) 3 * np);
+        std::vector<double> x = x0; std::vector<float> v = v0;
+        const unsigned grid = 7;
+        auto kick = [&]() { KickArgs a = { v.data(), v.data(), acc.data(), d1.data(), d2.data(), kf[0], kf[1], kf[2], kf[3], kf[4], cola, 3 * np };
+                            launch_seq(grid, 256, [&]() { kick_kernel(a); }); };
+        auto drift = [&](double s) { DriftArgs a = { x.data(), x.data(), v.data(), d1.data(), d2.data(), s * df[0], s * df[1], s * df[2], df[3], df[4], dmode, 3 * np };
+                                     launch_seq(grid, 256, [&]() { drift_kernel(a); }); };
+        kick(); drift(1.0);
+        dump(out, x); dump(out, v);                                    // after one kick + one drift (what the oracle does)
+        kick(); drift(0.5); drift(0.5);
+        dump(out, x); dump(out, v);
+        FusedArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        std::vector<double> xf = x0; std::vector<float> vf = v0;
+        fa.x = xf.data(); fa.v = vf.data(); fa.acc = acc.data(); fa.dx1 = d1.data(); fa.dx2 = d2.data(); fa.n3 = 3 * np; fa.nops = 5;
+        fa.any_kick = 1; fa.any_drift = 1; fa.any_dx = cola || dmode >= 2;
+        const double scl[5] = { 0, 1.0, 0, 0.5, 0.5 };
+        for (int j = 0; j < 5; j++) {
+            const bool isk = (j == 0 || j == 2);
+            fa.ops[j].kind = isk ? 0 : 1; fa.ops[j].mode = isk ? cola : dmode;
+            for (int q = 0; q < 5; q++) fa.ops[j].f[q] = isk ? kf[q] : (q < 3 ? scl[j] * df[q] : df[q]);
+        }
+        launch_seq(grid, 256, [&]() { fused_update_kernel(fa); });
+        dump(out, xf); dump(out, vf);
+    } else if (op == "wrap") {
+        // in: int64 n3, float64 L, x f64[n3]; out: x, int32 flag
+        const long long n3 = in.one<int64_t>();
+        const double L = in.one<double>();
+        std::vector<double> x = in.many<double>((size_t) n3);
+        int bad = 0;
+        launch_seq(3, 256, [&]() { wrap_kernel(x.data(), n3, L, &bad); });
+        dump(out, x);
+        std::vector<int32_t> flag(1, bad); dump(out, flag);
+    } else { fprintf(stderr, "unknown op %s\n", op.c_str()); return 2; }
+    fclose(out);
+    return 0;
+}

@@ -1,0 +1,137 @@
+"""CPU parity of the particle KERNEL SOURCES against the oracle, bit for bit (tests/emul/particles_emul.cpp: csrc/paint.cu and
+csrc/particles.cu compiled for the host).  The deposit runs in particle order there, which is the reference's own order with one
+OpenMP thread, so even the float32 mesh is identical; readout, kick, drift, the fused K-K-D-D pass and wrap are exact anyway."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    if not os.path.exists(os.path.join(INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path_factory.mktemp("emul") / "particles_emul")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-pthread", "-w", "-I" + INC, "-o", exe,
+                        os.path.join(ROOT, "tests", "emul", "particles_emul.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+
+    def run(op, payload, tmp):
+        fin, fout = os.path.join(tmp, op + ".in"), os.path.join(tmp, op + ".out")
+        with open(fin, "wb") as f:
+            f.write(payload)
+        subprocess.run([exe, op, fin, fout], check=True)
+        return open(fout, "rb").read()
+    return run
+
+
+@pytest.fixture(scope="module")
+def one_thread_ref(ref_mod):
+    old = os.environ.get("OMP_NUM_THREADS")
+    os.environ["OMP_NUM_THREADS"] = "1"          # serial deposit order on the reference side
+    yield ref_mod
+    if old is None:
+        os.environ.pop("OMP_NUM_THREADS", None)
+    else:
+        os.environ["OMP_NUM_THREADS"] = old
+
+
+def _positions(rng, n, L):
+    x = rng.uniform(0, L, size=(n, 3))
+    x[: n // 8] = np.round(x[: n // 8] / (L / 16)) * (L / 16)        # on cell faces, including x == L
+    x[0] = [L, L, L]
+    x[1] = [0, 0, 0]
+    x[2] = [np.nextafter(L, 0)] * 3
+    return x
+
+
+@pytest.mark.parametrize("vec", [0, 2, 4])
+def test_paint_and_readout_kernels_bit_exact(emul, one_thread_ref, tmp_path, vec):
+    nmesh, L, npart = 32, 100.0, 6000
+    rng = np.random.default_rng(40 + vec)
+    x = _positions(rng, npart, L)
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint(x)).copy()
+    head = struct.pack("<iiiiddq", nmesh, 0, 0, vec, L, 1.0, npart)
+    out = emul("paint", head + x.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    # same cells, same double-precision weights, same order.  The reference adds the DOUBLE weight to the float cell
+    # (painter-cic.c:25, one rounding); a float reduction rounds the weight first (two roundings): cells differ by <= 1 ulp per add
+    assert np.array_equal(got != 0, want != 0)
+    assert np.abs(got - want).max() <= 4e-7 * want.max()
+    assert abs(got.sum(dtype=np.float64) - npart) < 1e-4
+    # readout of a random mesh at the same positions
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    want_r = s.readout(s.real_pack(field), x)
+    out = emul("readout", head + x.tobytes() + field.tobytes(), str(tmp_path))
+    assert np.array_equal(np.frombuffer(out, dtype=np.float32), want_r)
+    s.close()
+
+
+def test_fused_wrap_and_brick_walk(emul, one_thread_ref, tmp_path):
+    """Positions outside the box: wrap folded into the deposit == the reference's wrap followed by its paint; the Lagrangian
+    brick walk (any permutation of the particles) gives the same mesh up to the order of float additions."""
+    nc, nmesh, L = 16, 32, 64.0
+    npart = nc ** 3 + 4 * nc * nc + 77
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1.5 * L, 2.5 * L, size=(npart, 3))
+    x[0] = [L, -L, 2 * L]
+    xw = np.frombuffer(emul("wrap", struct.pack("<qd", 3 * npart, L) + x.tobytes(), str(tmp_path)), dtype=np.float64, count=3 * npart).reshape(npart, 3)
+    dist = np.abs(xw - np.mod(x, L))                                 # store.c:447-475: remainder() + fold, result in [0, L]
+    assert np.minimum(dist, L - dist).max() < 1e-9 and xw.min() >= 0 and xw.max() <= L
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint(xw)).copy()
+    s.close()
+    out = emul("paint", struct.pack("<iiiiddq", nmesh, 0, 1, 4, L, 1.0, npart) + x.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    x_after = np.frombuffer(out, dtype=np.float64, count=3 * npart, offset=4 * nmesh ** 3).reshape(npart, 3)
+    assert np.array_equal(x_after, xw)                               # same operations as the stand-alone wrap kernel
+    assert np.array_equal(got != 0, want != 0) and np.abs(got - want).max() <= 4e-7 * want.max()
+    out = emul("paint", struct.pack("<iiiiddq", nmesh, nc, 0, 4, L, 1.0, npart) + xw.tobytes(), str(tmp_path))
+    brick = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    assert abs(brick.sum(dtype=np.float64) - npart) < 1e-2
+    assert np.abs(brick - want).max() <= 4e-6 * want.max()
+
+
+@pytest.mark.parametrize("mode", ["fastpm", "pm", "cola"])
+def test_kick_drift_and_fused_update_kernels_bit_exact(emul, one_thread_ref, pk_text, tmp_path, mode):
+    nc, L = 16, 64.0
+    s = one_thread_ref.Session(nc=nc, boxsize=L, pm_nc_factor=2, force_mode=mode, growth_mode="LCDM")
+    dk, _, _ = s.ic_deltak(11, pk_text)
+    s.setup_lpt(dk, 0.1)
+    s.compute_force(0.1)
+    p0 = s.get_particles()
+    n = s.np
+    ai, ac, af = 0.1, 0.1, 0.2
+    kf, df = s.kick_factor(ai, ac, af), s.drift_factor(ai, ac, af)
+    s.kick(ai, ac, af)
+    s.drift(ai, ac, af)
+    p1 = s.get_particles()
+    s.close()
+    cola = 1 if mode == "cola" else 0
+    fm = {"fastpm": 0, "pm": 1, "cola": 2}[mode]
+    k5 = [kf["dda"][-1] - kf["dda"][0], kf["q1"], kf["q2"], kf["Dv1"][-1] - kf["Dv1"][0], kf["Dv2"][-1] - kf["Dv2"][0]]
+    d5 = [df["dyyy"][-1] - df["dyyy"][0], df["da1"][-1] - df["da1"][0], df["da2"][-1] - df["da2"][0], df["Dv1"], df["Dv2"]]
+    zeros = np.zeros((n, 3), dtype=np.float32)
+    payload = struct.pack("<qii", n, cola, fm) + np.array(k5).tobytes() + np.array(d5).tobytes() + p0["x"].tobytes() + p0["v"].tobytes() + \
+        p0["acc"].tobytes() + (p0["dx1"] if cola else zeros).tobytes() + (p0["dx2"] if cola else zeros).tobytes()
+    out = emul("update", payload, str(tmp_path))
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(out, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a.reshape(n, 3)
+    x_kd, v_kd = take(np.float64, 3 * n), take(np.float32, 3 * n)
+    x_seq, v_seq = take(np.float64, 3 * n), take(np.float32, 3 * n)
+    x_fused, v_fused = take(np.float64, 3 * n), take(np.float32, 3 * n)
+    assert np.array_equal(v_kd, p1["v"]) and np.array_equal(x_kd, p1["x"])           # kick + drift == the reference's
+    assert np.array_equal(v_fused, v_seq) and np.array_equal(x_fused, x_seq)         # one fused pass == five separate kernels
