@@ -8,6 +8,15 @@
 #define FPM_MAX_RANKS 8
 #define FPM_MAX_STAGES 16
 
+// ---------------------------------------------------------------- dynamic shared memory of a kernel
+// (FPM_EMULATE: the kernel sources are also compiled for the CPU by tests/emul/, where shared memory is an ordinary array)
+#ifndef FPM_EMULATE
+#define FPM_DYN_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
+#else
+extern unsigned char *fpm_emul_dyn_smem;
+#define FPM_DYN_SMEM(name, alignment) unsigned char *name = fpm_emul_dyn_smem
+#endif
+
 // ---------------------------------------------------------------- errors
 extern "C" void fpm_set_error(const char *fmt, ...);
 extern unsigned long long fpm_launch_counter;      // kernels launched by this library (bench "gpu_launches")

@@ -6,8 +6,6 @@
 #include <cuda.h>
 
 #ifndef FPM_EMULATE
-// dynamic shared memory of a kernel
-#define FPM_DYN_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
 // ------------------------------------------------------------------ small PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -65,8 +63,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Every CUDA thread is an OS thread, __syncthreads() a pthread barrier, shared memory an ordinary array.  Asynchronous copies
 // are done synchronously by the issuing thread; the mbarrier keeps a completed-phase count (low word) and the bytes still
 // expected (high word), so that waiting threads really wait for the data.  A "tensor map" is a plain descriptor.
-#define FPM_DYN_SMEM(name, alignment) unsigned char *name = fpm_emul_dyn_smem
-extern unsigned char *fpm_emul_dyn_smem;
 struct FpmEmulTmap { const float *base; uint64_t gstr_bytes[2]; uint32_t box[3]; };      // lives in the bytes of a CUtensorMap
 inline void mbar_init(uint64_t *bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
 inline float fpm_rcp_approx(float x) { return 1.0f / x; }

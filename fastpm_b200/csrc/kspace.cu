@@ -72,12 +72,14 @@ __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const doubl
 #define PK_UNROLL 2
 // Each warp owns a private histogram in shared memory: the head lanes of one warp-wide step hold DISTINCT bins (runs of a
 // monotone sequence), so they update it with plain read-modify-writes -- no atomics, no contention between warps (double
-// atomicAdd on shared memory is a CAS loop; with all warps of an SM hitting neighbouring shells it was 70 % of the kernel).
+// atomicAdd on shared memory is a CAS loop).  Measured: no faster than the shared atomics it replaced -- the kernel is bound
+// by instruction issue (fp64, shuffles), see DESIGN.md section 9.
 template <bool GEOM>
 __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
         const float2 *__restrict__ dk, double k0, double *__restrict__ out /* GEOM: [2][nbins]; else [nbins] + 1 */)
 {
-    extern __shared__ double hist_all[];
+    FPM_DYN_SMEM(hist_raw, 8);
+    double *hist_all = reinterpret_cast<double *>(hist_raw);
     const int nbins = g.n / 2;
     const int nslots = GEOM ? 2 * nbins : nbins + 1;
     for (int i = threadIdx.x; i < nslots * PK_WARPS; i += blockDim.x) hist_all[i] = 0;
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(64) gadget_fill_kernel(const FpmGeom g, const 
     fpm_gadget_fill_column(g.n, i, j, self[q], conj[q], dk + ((size_t) jl * g.n + i) * g.pitch_c);
 }
 
+#ifndef FPM_EMULATE          // host side: not part of the CPU emulation of the kernels (tests/emul/kspace_emul.cpp)
 // ------------------------------------------------------------------ launchers
 static inline unsigned sweep_grid(size_t n)
 {
@@ -439,3 +442,4 @@ int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, flo
     FPM_CHECK_LAUNCH();
     return 0;
 }
+#endif

@@ -15,7 +15,7 @@ struct FpmEmulDim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local FpmEmulDim3 threadIdx;
 static FpmEmulDim3 blockIdx, blockDim, gridDim;
 static pthread_barrier_t fpm_emul_barrier;
-unsigned char *fpm_emul_dyn_smem = nullptr;
+unsigned char *fpm_emul_dyn_smem = nullptr;     // declared extern by csrc/common.cuh under FPM_EMULATE
 #define __syncthreads() pthread_barrier_wait(&fpm_emul_barrier)
 #define __ldg(p) (*(p))
 #define __global__
@@ -29,6 +29,34 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 static inline double __drcp_rn(double a) { return 1.0 / a; }
 
+// ---- warp primitives: the 32 lanes of a warp meet at a per-warp barrier around an exchange buffer (the kernels call them
+// with warp-uniform control flow, like the hardware requires for *_sync with a full mask)
+static pthread_barrier_t fpm_emul_warp_barrier[32];
+static double fpm_emul_shfl_buf[32][32];
+template <typename T> static T fpm_emul_shfl(T v, int src)
+{
+    static_assert(sizeof(T) <= sizeof(double), "shuffle of at most 8 bytes");
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    memcpy(&fpm_emul_shfl_buf[warp][lane], &v, sizeof(T));
+    pthread_barrier_wait(&fpm_emul_warp_barrier[warp]);
+    T r = v;
+    if (src >= 0 && src < 32) memcpy(&r, &fpm_emul_shfl_buf[warp][src], sizeof(T));
+    pthread_barrier_wait(&fpm_emul_warp_barrier[warp]);
+    return r;
+}
+template <typename T> static T __shfl_down_sync(unsigned, T v, int d) { return fpm_emul_shfl(v, (int) (threadIdx.x % 32) + d); }
+template <typename T> static T __shfl_up_sync(unsigned, T v, int d) { return fpm_emul_shfl(v, (int) (threadIdx.x % 32) - d); }
+template <typename T> static T __shfl_xor_sync(unsigned, T v, int x) { return fpm_emul_shfl(v, (int) (threadIdx.x % 32) ^ x); }
+static inline void __syncwarp() { pthread_barrier_wait(&fpm_emul_warp_barrier[threadIdx.x / 32]); }
+static pthread_mutex_t fpm_emul_atomic_lock = PTHREAD_MUTEX_INITIALIZER;
+static inline double atomicAdd(double *p, double v)
+{
+    pthread_mutex_lock(&fpm_emul_atomic_lock);
+    const double o = *p; *p = o + v;
+    pthread_mutex_unlock(&fpm_emul_atomic_lock);
+    return o;
+}
+
 // runs kernel(args...) as a grid of `grid` CTAs of `block` threads with `smem_bytes` of dynamic shared memory, CTA after CTA
 template <typename Kernel>
 static void fpm_emul_launch(unsigned grid, unsigned block, size_t smem_bytes, Kernel kernel)
@@ -39,9 +67,12 @@ static void fpm_emul_launch(unsigned grid, unsigned block, size_t smem_bytes, Ke
     for (unsigned b = 0; b < grid; b++) {
         blockIdx.x = b;
         pthread_barrier_init(&fpm_emul_barrier, NULL, block);
+        for (unsigned w = 0; w < (block + 31) / 32 && w < 32; w++)
+            pthread_barrier_init(&fpm_emul_warp_barrier[w], NULL, (w + 1) * 32 <= block ? 32 : block - w * 32);
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < block; t++) pool.emplace_back([&, t]() { threadIdx.x = t; kernel(); });
         for (auto &th : pool) th.join();
         pthread_barrier_destroy(&fpm_emul_barrier);
+        for (unsigned w = 0; w < (block + 31) / 32 && w < 32; w++) pthread_barrier_destroy(&fpm_emul_warp_barrier[w]);
     }
 }

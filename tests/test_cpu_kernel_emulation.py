@@ -135,3 +135,94 @@ def test_kick_drift_and_fused_update_kernels_bit_exact(emul, one_thread_ref, pk_
     x_fused, v_fused = take(np.float64, 3 * n), take(np.float32, 3 * n)
     assert np.array_equal(v_kd, p1["v"]) and np.array_equal(x_kd, p1["x"])           # kick + drift == the reference's
     assert np.array_equal(v_fused, v_seq) and np.array_equal(x_fused, x_seq)         # one fused pass == five separate kernels
+
+
+# ---------------------------------------------------------------- k-space kernels (tests/emul/kspace_emul.cpp)
+@pytest.fixture(scope="module")
+def kspace_emul(tmp_path_factory):
+    if not os.path.exists(os.path.join(INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path_factory.mktemp("kemul") / "kspace_emul")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-pthread", "-w", "-I" + INC, "-o", exe,
+                        os.path.join(ROOT, "tests", "emul", "kspace_emul.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert r.returncode == 0, r.stdout
+
+    def run(op, payload, tmp):
+        fin, fout = os.path.join(tmp, op + ".in"), os.path.join(tmp, op + ".out")
+        with open(fin, "wb") as f:
+            f.write(payload)
+        subprocess.run([exe, op, fin, fout], check=True)
+        return open(fout, "rb").read()
+    return run
+
+
+def _sinc(x):
+    x = np.asarray(x, dtype=np.float64)
+    small = np.abs(x) < 1e-5
+    xs = np.where(small, 1.0, x)
+    return np.where(small, 1.0 - x * x / 6.0 + x ** 4 / 120.0, np.sin(xs) / xs)
+
+
+def _tables(n, L):
+    """pm_create_k_factors (pmapi.c:235-275) and the decic table (transfer.c:88-96), every intermediate in float where the
+    reference's is -- the same restatement as host_ktables in csrc/capi.cu."""
+    cell = L / n
+    ii = np.arange(n)
+    ii = np.where(ii >= n // 2, ii - n, ii)
+    k = (ii * 2 * np.pi / L).astype(np.float32)
+    w = (k.astype(np.float64) * cell).astype(np.float32)
+    ff1 = _sinc(0.5 * w.astype(np.float64)).astype(np.float32)
+    ff2 = _sinc(w.astype(np.float64)).astype(np.float32)
+    kk = (k * k).astype(np.float32)
+    kf = (1 / cell * (1 / 6.0 * (8 * np.sin(w.astype(np.float64)) - np.sin(2 * w.astype(np.float64))))).astype(np.float32)
+    kkf = (kk * (ff1 * ff1).astype(np.float32)).astype(np.float32)
+    kkf2 = (kk.astype(np.float64) * (4 / 3.0 * ff1.astype(np.float64) * ff1.astype(np.float64) - 1 / 3.0 * ff2.astype(np.float64) * ff2.astype(np.float64))).astype(np.float32)
+    dec = 1.0 / _sinc(0.5 * (k.astype(np.float64) * L / n)) ** 2
+    return np.stack([k, kk, kf, kkf, kkf2]).astype(np.float32), dec
+
+
+def _to_device_layout(c, n):
+    pitch_c = ((n // 2 + 1 + 15) // 16) * 16
+    full = np.zeros((n, n, pitch_c), dtype=np.complex64)
+    full[:, :, :n // 2 + 1] = np.transpose(c, (1, 0, 2))          # [kx, ky, kz] -> [ky][kx][kz]
+    return full
+
+
+def _from_device_layout(buf, n):
+    pitch_c = ((n // 2 + 1 + 15) // 16) * 16
+    full = np.frombuffer(buf, dtype=np.complex64).reshape(n, n, pitch_c)
+    return np.transpose(full[:, :, :n // 2 + 1], (1, 0, 2))
+
+
+def test_kspace_kernels_against_reference(kspace_emul, ref_mod, tmp_path):
+    nmesh, L = 32, 123.0
+    rng = np.random.default_rng(5)
+    field = rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32)
+    s = ref_mod.Session(nc=nmesh, boxsize=L, pm_nc_factor=1, kernel_type="1_4")
+    dk = s.r2c(s.real_pack(field))
+    c = s.complex_view(dk)
+    tab, dec = _tables(nmesh, L)
+    head = struct.pack("<id", nmesh, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(c, nmesh).tobytes()
+    # force components and potential of the default kernel (potorder 0, gradorder 1): gravity.c:174-242
+    for attr, memb in [(0, 0), (0, 1), (0, 2), (1, 0)]:
+        want = s.complex_view(s.kernel_transfer(dk, memb, attr=attr))
+        spec = struct.pack("<iiiiiii", 0, 1, 1 if attr == 0 else 0, memb, 0, 1, 1)
+        got = _from_device_layout(kspace_emul("transfer", head + spec, str(tmp_path)), nmesh)
+        assert np.array_equal(got.view(np.float32), want.view(np.float32)), (attr, memb)
+    # CIC deconvolution, transfer.c:78-113
+    want = s.complex_view(s.decic(dk))
+    got = _from_device_layout(kspace_emul("decic", head, str(tmp_path)), nmesh)
+    assert np.array_equal(got.view(np.float32), want.view(np.float32))
+    # P(k): powerspectrum.c:35-124, plain and with the deconvolution folded into the read
+    nb = nmesh // 2
+    for decic, src in ((0, dk), (1, s.decic(dk))):
+        k0, p0, n0 = s.powerspectrum(src)
+        sums = np.frombuffer(kspace_emul("pk", head + struct.pack("<i", decic), str(tmp_path)), dtype=np.float64)
+        nm, sp, sk = sums[:nb], sums[nb:2 * nb], sums[2 * nb:3 * nb]
+        assert np.array_equal(nm, n0)
+        sel = nm > 0
+        np.testing.assert_allclose(sk[sel] / nm[sel], k0[sel], rtol=1e-13)
+        np.testing.assert_allclose(sp[sel] / nm[sel] * L ** 3, p0[sel], rtol=1e-12)
+    s.close()
