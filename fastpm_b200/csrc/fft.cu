@@ -42,7 +42,8 @@ struct TilePassArgs {
 template <int K>
 __global__ void __launch_bounds__(512) fft_tile_kernel(const TilePassArgs a)
 {
-    extern __shared__ __align__(16) float2 smem[];
+    FPM_DYN_SMEM(smem_raw, 16);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     const int n = a.t.n;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int o = blockIdx.x / a.ntile_k;
@@ -105,7 +106,8 @@ struct ZPassArgs {
 template <int R>
 __global__ void __launch_bounds__(512) fft_zfwd_kernel(const ZPassArgs a)
 {
-    extern __shared__ __align__(16) float2 smem[];
+    FPM_DYN_SMEM(smem_raw, 16);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     constexpr int KP = R + 1;
     const int h = a.th.n;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(512) fft_zfwd_kernel(const ZPassArgs a)
 template <int R>
 __global__ void __launch_bounds__(512) fft_zbwd_kernel(const ZPassArgs a)
 {
-    extern __shared__ __align__(16) float2 smem[];
+    FPM_DYN_SMEM(smem_raw, 16);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     constexpr int KP = R + 1;
     const int h = a.th.n;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(512) fft_zbwd_kernel(const ZPassArgs a)
     }
 }
 
+#ifndef FPM_EMULATE          // host side: not part of the CPU emulation of the kernels (tests/emul/fft_generic_emul.cpp)
 // ------------------------------------------------------------------ plan
 struct FpmFftPlan {
     int n;
@@ -437,3 +441,4 @@ int fpm_fft_tma_pass_from_tile(int n, const TilePassArgs &a, int pitch_c, int no
     t.ntile_k = 0; t.nouter = nouter; t.conj = a.conj; t.outer0 = a.outer0; t.tw = a.t.tw; t.xfer = a.xfer; t.kt = a.kt;
     return fpm_fft_tma_pass(n, a.src, pitch_c, nouter, t, st);
 }
+#endif

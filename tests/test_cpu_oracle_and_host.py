@@ -297,10 +297,11 @@ def test_gadget_ic_generator_matches_reference_bit_for_bit(tmp_path, ref_mod, n,
         assert np.array_equal(pl, mirror)
 
 
-@pytest.mark.parametrize("name,nlines", [("zrow_emul", 5), ("tma_emul", 15)])
+@pytest.mark.parametrize("name,nlines", [("zrow_emul", 5), ("tma_emul", 15), ("fft_generic_emul", 9)])
 def test_fft_kernel_sources_emulated_on_cpu(tmp_path, name, nlines):
-    """The KERNEL SOURCE nvcc compiles -- csrc/fft_zrow.cu (row pass) and csrc/fft_tma.cu (strided pass with the fused gravity
-    kernel and the slab-transpose store path) -- built for the CPU with tests/emul/cuda_emul.h (one OS thread per CUDA thread,
+    """The KERNEL SOURCE nvcc compiles -- csrc/fft_zrow.cu (row pass), csrc/fft_tma.cu (strided pass with the fused gravity
+    kernel and the slab-transpose store path) and csrc/fft.cu (the generic passes for meshes with factors 3 and 5: 768, 1280,
+    1536 ...) -- built for the CPU with tests/emul/cuda_emul.h (one OS thread per CUDA thread,
     pthread barrier for __syncthreads(), synchronous stand-ins for TMA / bulk copies and the mbarrier) and checked against naive
     double-precision DFTs and the reference-order transfer of csrc/mesh.cuh, for every mesh size of the fast path, including
     N = 4096 which no single-GPU test can reach."""
