@@ -135,10 +135,15 @@ void fpm_halo_fetch(PM *pm, FastPMFloat *canvas)
 }
 
 /* one extra mesh per PM: the slab transposes are staged locally and pushed by the copy engines (csrc/fft.cu) */
+size_t fastpm_b200_arena_largest_free(void);
 static void ensure_stage(PM *pm)
 {
-    if (pm->stage || getenv("FASTPM_B200_NO_STAGE")) return;
-    pm->stage = fastpm_memory_alloc(pm->mem, "FFT transpose staging", sizeof(FastPMFloat) * pm->allocsize, FASTPM_MEMORY_FLOATING);
+    if (pm->stage || pm->stage_off || getenv("FASTPM_B200_NO_STAGE")) return;
+    /* capacity runs (BASELINE.json config 5: 4096^3 mesh on 8 GPUs) have no room for a third mesh: the transposes then store
+     * straight into the peers.  Every rank sees the same arena state, so the decision is the same everywhere. */
+    const size_t need = sizeof(FastPMFloat) * pm->allocsize;
+    if (fastpm_b200_arena_largest_free() < need + need / 8) { pm->stage_off = 1; return; }
+    pm->stage = fastpm_memory_alloc(pm->mem, "FFT transpose staging", need, FASTPM_MEMORY_FLOATING);
     FPM_MUST(fpm_mesh_set_stage(pm->mesh, pm->stage));
 }
 

@@ -29,6 +29,7 @@ struct PM {
     FastPMMemory *mem;
     FastPMFloat *scratch;         /* lazily allocated, for the in-place public pm_c2r / pm_r2c */
     FastPMFloat *stage;           /* several GPUs: staging mesh of the slab transposes (lazily allocated) */
+    int stage_off;                /* no room for it in the arena: direct peer stores */
     int transposed;
     int pitch_r, pitch_c, nxl, x0, nyl, y0, halo;
 };

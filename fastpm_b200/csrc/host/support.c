@@ -201,6 +201,19 @@ void *fastpm_b200_arena_base(void) { return arena_base; }
 size_t fastpm_b200_arena_size(void) { return arena_size; }
 int fastpm_b200_arena_contains(const void *p) { return arena_base && (const char *) p >= arena_base && (const char *) p < arena_base + arena_size; }
 
+/* the largest block arena_alloc could still hand out */
+size_t fastpm_b200_arena_largest_free(void)
+{
+    if (!arena_base) return 0;
+    size_t best = 0, off = 0;
+    for (int i = 0; i < arena_nblocks; i++) {
+        if (arena_blocks[i].off - off > best) best = arena_blocks[i].off - off;
+        off = arena_blocks[i].off + arena_blocks[i].size;
+    }
+    if (arena_size - off > best) best = arena_size - off;
+    return best;
+}
+
 static void *arena_alloc(size_t s)
 {
     s = (s + ARENA_ALIGN - 1) / ARENA_ALIGN * ARENA_ALIGN;
@@ -255,6 +268,7 @@ int fastpm_b200_arena_selftest(void)
         char *f = arena_alloc(4 * MiB);                  /* first fit: into the gap */
         off[4] = (size_t) (e - arena_base); off[5] = (size_t) (f - arena_base);
         if (!bad && (off[4] != 35 * MiB || off[5] != MiB)) bad = 2;
+        if (!bad && fastpm_b200_arena_largest_free() != 17 * MiB) bad = 8;     /* the tail; the inner gap is 6 MiB */
         if (!bad && arena_alloc(30 * MiB) != NULL) bad = 3;                    /* 47 MiB used at the top: 17 left */
         if (!bad && arena_alloc(17 * MiB) == NULL) bad = 4;                    /* exactly the tail */
         if (!bad && !fastpm_b200_arena_contains(f)) bad = 5;
