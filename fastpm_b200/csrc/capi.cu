@@ -40,6 +40,7 @@ void fpm_prof_end(int cls, cudaStream_t st)
 int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, int *wrap_bad, cudaStream_t st);
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
+int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, const float *c2, const double *x, float *out, long long np, cudaStream_t st);
 int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st);
 int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
@@ -396,6 +397,12 @@ int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t
 {
     LAZY1(canvas);
     return fpm_readout_launch(m, canvas, x, out, out_stride, prescale, np, g_stream);
+}
+
+int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3)
+{
+    LAZY1(canvas0); LAZY1(canvas1); LAZY1(canvas2);
+    return fpm_readout3_launch(m, canvas0, canvas1, canvas2, x, out3, np, g_stream);
 }
 
 // ------------------------------------------------------------------ FFT

@@ -33,6 +33,34 @@ void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *d
 }
 
 
+size_t fastpm_b200_arena_size(void);             /* host/support.c */
+size_t fastpm_b200_arena_largest_free(void);
+
+/* opt-in; only when CDM is the only species and two more meshes fit beside what is allocated now */
+static int fused_readout_wanted(FastPMSolver *fastpm, PM *pm)
+{
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("FASTPM_B200_FUSED_READOUT"); want = (e && atoi(e) > 0) ? 1 : 0; }
+    if (!want) return 0;
+    FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    if (!cdm || !cdm->acc) return 0;
+    for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++)
+        if (si != FASTPM_SPECIES_CDM && fastpm_solver_get_species(fastpm, si)) return 0;
+    const size_t need = 2 * sizeof(FastPMFloat) * pm->allocsize;
+    if (pm->mem->used_bytes + need > pm->mem->total_bytes) return 0;
+    int ok;
+    if (fastpm_b200_arena_size() > 0) {
+        ok = fastpm_b200_arena_largest_free() >= need + (need >> 3);
+    } else {
+        size_t fr = 0, tot = 0;
+        ok = fpm_device_mem_info(&fr, &tot) == 0 && fr >= need + (need >> 3);
+    }
+    /* every rank must take the same branch: the transforms are collective */
+    double all = ok ? 1.0 : 0.0;
+    if (pm->NTask > 1) fpm_comm_allreduce_double(fastpm->comm, &all, 1, 1);
+    return all > 0.5;
+}
+
 void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, FastPMSofteningType dealias,
                                  FastPMKernelType kernel, FastPMFloat *delta_k, double Time)
 {
@@ -82,7 +110,28 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     /* ---- force components: gravity.c:359-396 */
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
     const int nacc = (cdm && cdm->potential) ? 4 : 3;
-    for (int d = 0; d < nacc; d++) {
+    int d0 = 0;
+    if (fused_readout_wanted(fastpm, pm)) {
+        /* FASTPM_B200_FUSED_READOUT=1: the three inverse transforms into three meshes, then ONE pass over the particles
+         * (positions read once instead of three times, ACC written as whole elements). Same values bit for bit. */
+        FastPMFloat *cv[3] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__), pm_alloc_noclear(pm, __FILE__, __LINE__) };
+        ENTER(c2r);
+        for (int d = 0; d < 3; d++) {
+            fpm_transfer t;
+            if (fpm_transfer_for_kernel((int) kernel, 0, d, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+            fpm_mesh_c2r(pm, delta_k, cv[d], &t);
+            if (pm->NTask > 1) fpm_halo_fetch(pm, cv[d]);
+        }
+        LEAVE(c2r);
+        ENTER(readout);
+        fpm_store_flush(cdm);
+        FPM_MUST(fpm_readout3(pm->mesh, cv[0], cv[1], cv[2], (const double *) cdm->x, (int64_t) cdm->np, (float *) cdm->acc));
+        LEAVE(readout);
+        pm_free(pm, cv[2]);
+        pm_free(pm, cv[1]);
+        d0 = 3;
+    }
+    for (int d = d0; d < nacc; d++) {
         fpm_transfer t;
         if (fpm_transfer_for_kernel((int) kernel, d < 3 ? 0 : 1, d < 3 ? d : 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
         ENTER(c2r);

@@ -169,6 +169,43 @@ __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const
     out[i * out_stride] = (float) value;
 }
 
+// The three force components in ONE pass over the particles (x read once, acc written as whole 12-byte elements): each
+// component is the same sum of the same eight products, in the same order, as cic_readout_kernel gives for its canvas.
+// Needs the three inverse transforms resident at the same time (two more meshes); opt-in, see csrc/host/gravity.c.
+__global__ void __launch_bounds__(256) cic_readout3_kernel(const FpmGeom g, const float *__restrict__ c0, const float *__restrict__ c1,
+        const float *__restrict__ c2, const double *__restrict__ x, float *__restrict__ out, long long np, int lag_nc, int nbrick_blocks)
+{
+    const long long i = cic_particle_index(lag_nc, nbrick_blocks, np);
+    if (i < 0) return;
+    double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    CicIndex c;
+    cic_setup(g, pos, c);
+    const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    const float *canv[3] = { c0, c1, c2 };
+    double w[8];
+    w[0] = c.T[2] * c.T[0] * c.T[1]; w[1] = c.D[2] * c.T[0] * c.T[1]; w[2] = c.T[2] * c.T[0] * c.D[1]; w[3] = c.D[2] * c.T[0] * c.D[1];
+    w[4] = c.T[2] * c.D[0] * c.T[1]; w[5] = c.D[2] * c.D[0] * c.T[1]; w[6] = c.T[2] * c.D[0] * c.D[1]; w[7] = c.D[2] * c.D[0] * c.D[1];
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double value = 0;
+        if (c.lx0 >= 0) {
+            const float *p0 = canv[d] + (size_t) c.lx0 * pl;
+            value += (double) __ldg(p0 + c.j0 * pr + c.k0) * w[0];
+            value += (double) __ldg(p0 + c.j0 * pr + c.k1) * w[1];
+            value += (double) __ldg(p0 + c.j1 * pr + c.k0) * w[2];
+            value += (double) __ldg(p0 + c.j1 * pr + c.k1) * w[3];
+        }
+        if (c.lx1 >= 0) {
+            const float *p1 = canv[d] + (size_t) c.lx1 * pl;
+            value += (double) __ldg(p1 + c.j0 * pr + c.k0) * w[4];
+            value += (double) __ldg(p1 + c.j0 * pr + c.k1) * w[5];
+            value += (double) __ldg(p1 + c.j1 * pr + c.k0) * w[6];
+            value += (double) __ldg(p1 + c.j1 * pr + c.k1) * w[7];
+        }
+        out[3 * i + d] = (float) value;
+    }
+}
+
 // adds the received halo plane into local plane 0 (multi-GPU paint epilogue)
 __global__ void plane_add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t nfloats)
 {
@@ -233,6 +270,18 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
     int lag_nc = 0;
     const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
     FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, const float *c2, const double *x, float *out,
+                        long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    const unsigned grid = (unsigned) ((np + 255) / 256);
+    int lag_nc = 0;
+    const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
+    FPM_TIMED(FPM_K_READOUT, st, (cic_readout3_kernel<<<grid, 256, 0, st>>>(m->geom, c0, c1, c2, x, out, np, lag_nc, nbrick)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

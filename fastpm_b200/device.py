@@ -131,6 +131,10 @@ class Mesh:
         check(self.lib.fpm_readout(self.h, canvas.ptr, x_dev.ptr, int(np_), out_dev.ptr + out_offset_bytes,
                                    int(out_stride), float(prescale)), "fpm_readout")
 
+    def readout3(self, canvases, x_dev, np_, out_dev):
+        """out[i][d] = readout(canvases[d]) for d = 0, 1, 2 in one pass over the particles."""
+        check(self.lib.fpm_readout3(self.h, canvases[0].ptr, canvases[1].ptr, canvases[2].ptr, x_dev.ptr, int(np_), out_dev.ptr), "fpm_readout3")
+
     def r2c(self, real, cplx, scale=None):
         if scale is None:
             scale = 1.0 / float(self.n) ** 3          # pm_r2c carries 1/Norm, pmpfft.c:382-385

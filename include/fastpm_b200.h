@@ -87,6 +87,10 @@ int fpm_particle_grid_hint(int nc);
 int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np,
                 float *out, int out_stride, double prescale);
 
+/* three readouts in one pass over the particles: out3[i][d] = fpm_readout(canvas_d) for d = 0, 1, 2 (the ACC column of the
+ * store, gravity.c:359-396), bit-identical to three separate calls; needs the three fields resident at the same time */
+int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3);
+
 /* ---- K2 / K4 FFT: pm_r2c, pm_c2r, pmpfft.c:370-399 ------------------------------------------ */
 /* r2c: cplx = DFT(real) * scale.  `real` is destroyed (as with PFFT_DESTROY_INPUT, pmpfft.c:290).
  * The reference's 1/Norm (pmpfft.c:382-385) is passed as scale = 1/N^3 by the caller. */

@@ -1,5 +1,5 @@
 // CPU run of the particle KERNEL SOURCES, fastpm_b200/csrc/paint.cu and csrc/particles.cu (CIC deposit with the vector
-// reductions, the fused periodic wrap and the Lagrangian-brick traversal; CIC readout; kick, drift, fused K-K-D-D update; wrap).
+// reductions, the fused periodic wrap and the Lagrangian-brick traversal; CIC readout, one canvas and three at once; kick, drift, fused K-K-D-D update; wrap).
 // These kernels have no barriers: CUDA threads run one after the other, atomics are plain updates, so the deposit happens in
 // particle order -- exactly the reference's serial order (painter.c:320-339 with one OpenMP thread), which makes even the float32
 // mesh comparable bit for bit.  Built with -ffp-contract=off (the kernels are compiled with -fmad=false).
@@ -82,6 +82,29 @@ int main(int argc, char **argv)
             launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick); });
             dump(out, res);
         }
+    } else if (op == "readout3") {
+        // in: int32 n, int32 lag_nc, float64 L, int64 np, x[np][3] f64, three dense canvases f32[n^3]
+        // out: three separate readouts into a stride-3 column (f32[np][3]), then the one-pass kernel (f32[np][3])
+        const int n = in.one<int32_t>(), lag_nc = in.one<int32_t>();
+        const double L = in.one<double>();
+        const long long np = in.one<int64_t>();
+        std::vector<double> x = in.many<double>((size_t) 3 * np);
+        const FpmGeom g = geom(n, L);
+        std::vector<float> canvas[3];
+        for (int d = 0; d < 3; d++) {
+            std::vector<float> dense = in.many<float>((size_t) n * n * n);
+            canvas[d].assign((size_t) n * n * g.pitch_r, 0.f);
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[d][((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
+        }
+        const unsigned grid = (unsigned) ((np + 255) / 256);
+        int nbrick = 0;
+        if (lag_nc) nbrick = (int) ((np / (4LL * lag_nc * lag_nc)) * (4LL * lag_nc * lag_nc) / 256);
+        std::vector<float> sep((size_t) 3 * np, -7.f), one((size_t) 3 * np, -9.f);
+        for (int d = 0; d < 3; d++)
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick); });
+        launch_seq(grid, 256, [&]() { cic_readout3_kernel(g, canvas[0].data(), canvas[1].data(), canvas[2].data(), x.data(), one.data(), np, lag_nc, nbrick); });
+        dump(out, sep);
+        dump(out, one);
     } else if (op == "update") {
         // in: int64 np, int32 cola, int32 drift_mode, kick f64[5] (dda q1 q2 Dv1 Dv2), drift f64[5] (dyyy da1 da2 Dv1 Dv2),
         //     x f64[3np], v f32[3np], acc f32[3np], dx1 f32[3np], dx2 f32[3np]

@@ -75,6 +75,24 @@ def test_paint_and_readout_kernels_bit_exact(emul, one_thread_ref, tmp_path, vec
     s.close()
 
 
+@pytest.mark.parametrize("lag_nc", [0, 16])
+def test_three_component_readout_equals_three_readouts(emul, one_thread_ref, tmp_path, lag_nc):
+    """cic_readout3_kernel (FASTPM_B200_FUSED_READOUT=1: positions read once, ACC written as whole elements) against three
+    passes of cic_readout_kernel and against the reference's readout, bit for bit, in particle order and in the brick walk."""
+    nmesh, L = 32, 77.0
+    npart = 16 ** 3 + 333
+    rng = np.random.default_rng(5 + lag_nc)
+    x = _positions(rng, npart, L)
+    fields = rng.standard_normal((3, nmesh, nmesh, nmesh)).astype(np.float32)
+    out = emul("readout3", struct.pack("<iidq", nmesh, lag_nc, L, npart) + x.tobytes() + fields.tobytes(), str(tmp_path))
+    both = np.frombuffer(out, dtype=np.float32).reshape(2, npart, 3)
+    assert np.array_equal(both[0], both[1])
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    for d in range(3):
+        assert np.array_equal(both[1][:, d], s.readout(s.real_pack(fields[d]), x))
+    s.close()
+
+
 def test_fused_wrap_and_brick_walk(emul, one_thread_ref, tmp_path):
     """Positions outside the box: wrap folded into the deposit == the reference's wrap followed by its paint; the Lagrangian
     brick walk (any permutation of the particles) gives the same mesh up to the order of float additions."""

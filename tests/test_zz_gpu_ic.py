@@ -53,3 +53,31 @@ def test_libfastpm_user_program_runs_and_matches_fixture(tmp_path):
     want_p, want_k = fx["pk_p"][-1], fx["pk_k"][-1]
     np.testing.assert_allclose(pk[:16], want_k, rtol=1e-9)
     np.testing.assert_allclose(pk[16:], want_p, rtol=1e-5)        # the tolerance BASELINE.json states for P(k)
+
+
+def test_fused_readout_option_gives_the_same_run(tmp_path):
+    """FASTPM_B200_FUSED_READOUT=1 (three inverse transforms resident, one pass over the particles) is the same run as the
+    default one-canvas loop of gravity.c:359-396."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    from test_abi_layout import build_dropin_example
+    fx = np.load(os.path.join(here, "golden", "small_run.npz"))
+    exe = build_dropin_example(str(tmp_path))
+    dk, ts = str(tmp_path / "dk.f32"), str(tmp_path / "ts.f64")
+    np.ascontiguousarray(fx["delta_k"], dtype=np.float32).tofile(dk)
+    np.ascontiguousarray(fx["steps"], dtype=np.float64).tofile(ts)
+    res = []
+    for fused in ("0", "1"):
+        out_x, out_pk = str(tmp_path / ("x%s.f64" % fused)), str(tmp_path / ("pk%s.f64" % fused))
+        env = dict(os.environ, FASTPM_B200_FUSED_READOUT=fused)
+        r = subprocess.run([exe, dk, ts, out_x, out_pk], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout
+        res.append((np.fromfile(out_x, dtype=np.float64), np.fromfile(out_pk, dtype=np.float64)))
+    # the readout itself is bit-identical (test_three_component_readout_equals_three_readouts); two RUNS differ by the order of
+    # the float reductions of the deposit, far below the 1e-4 Mpc/h / 1e-5 tolerances of the path
+    d = np.abs(res[0][0] - res[1][0])
+    assert np.minimum(d, 32.0 - d).max() < 1e-5
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
