@@ -50,6 +50,8 @@ int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, in
 int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, double *host_out, cudaStream_t st);
 int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st);
 int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st);
+int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, double alpha, double kl, double ks, cudaStream_t st);
+int fpm_pgd_shift_launch(double *x, const float *pgdc, double dyyy, double dyyy_last, long long np, cudaStream_t st);
 int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st);
 int fpm_scale_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
 int fpm_divide_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
@@ -471,6 +473,12 @@ int fpm_apply_transfer(const fpm_mesh *m, const float *from, float *to, const fp
     return fpm_transfer_launch(m, from, to, &s, g_stream);
 }
 int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to) { LAZY1(from); LAZY1(to); return fpm_decic_launch(m, from, to, g_stream); }
+int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, double alpha, double kl, double ks)
+{
+    LAZY1(from); LAZY1(to);
+    if (!(ks > 0)) { fpm_set_error("pgd transfer: ks must be positive"); return -1; }
+    return fpm_pgd_transfer_launch(m, from, to, alpha, kl, ks, g_stream);
+}
 int fpm_scale(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_scale_launch(from, to, nfloats, value, g_stream); }
 int fpm_divide(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_divide_launch(from, to, nfloats, value, g_stream); }
 int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign) { if (fpm_lazy_touch(source, 4 * nfloats) || fpm_lazy_touch(a, 4 * nfloats) || fpm_lazy_touch(b, 4 * nfloats)) return -1; return fpm_muladd_launch(source, a, b, nfloats, sign, g_stream); }
@@ -561,6 +569,13 @@ int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx
 {
     if (forcemode >= 2 && (!dx1 || (forcemode != 4 && !dx2))) { fpm_set_error("drift mode %d needs the dx1/dx2 columns", forcemode); return -1; }
     return fpm_drift_launch(x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, forcemode, np, g_stream);
+}
+
+int fpm_pgd_shift(double *x, const float *pgdc, int64_t np, double dyyy, double dyyy_last)
+{
+    if (ensure_init()) return -1;
+    if (dyyy_last == 0) { fpm_set_error("pgd shift: empty drift interval (factors.c:110-111 skips it)"); return -1; }
+    return fpm_pgd_shift_launch(x, pgdc, dyyy, dyyy_last, np, g_stream);
 }
 
 int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, const float *dx2, int64_t np, int nops, const double *ops)

@@ -192,12 +192,15 @@ void fastpm_drift_store(FastPMDriftFactor *drift, FastPMStore *pi, FastPMStore *
 {
     double dyyy, da1, da2;
     fpm_drift_factors_at(drift, pi->meta.a_x, af, &dyyy, &da1, &da2);
-    if (pi->pgdc) fastpm_raise(-1, "fastpm_b200: the PGD correction column is out of scope of this build (pgdcorrection.c).\n");
     const int mode = (int) drift->forcemode;
     if (mode >= 2 && (!pi->dx1 || (mode != 4 && !pi->dx2))) fastpm_raise(-1, "drift mode %d needs the dx1/dx2 columns\n", mode);
-    if (pi == po && pi->x == po->x && defer_update(pi, 1, mode, dyyy, da1, da2, drift->Dv1, drift->Dv2)) { po->meta.a_x = af; return; }
+    /* with a PGD column the drift is followed at once by the PGD displacement (not queued) */
+    if (!pi->pgdc && pi == po && pi->x == po->x && defer_update(pi, 1, mode, dyyy, da1, da2, drift->Dv1, drift->Dv2)) { po->meta.a_x = af; return; }
     fpm_store_flush(NULL);
     FPM_MUST(fpm_drift((double *) po->x, (const double *) pi->x, (const float *) pi->v, (const float *) pi->dx1, (const float *) pi->dx2,
                        (int64_t) pi->np, (int) drift->forcemode, dyyy, da1, da2, drift->Dv1, drift->Dv2));
+    /* factors.c:108-113: xo += 0.5 * pgdc * dyyy / dyyy[last], except for an empty interval ("no drift; to protect the pgdc line") */
+    if (pi->pgdc && drift->ai != drift->af)
+        FPM_MUST(fpm_pgd_shift((double *) po->x, (const float *) pi->pgdc, (int64_t) pi->np, dyyy, drift->dyyy[drift->nsamples - 1]));
     po->meta.a_x = af;
 }

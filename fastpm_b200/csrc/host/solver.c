@@ -21,8 +21,12 @@ void fastpm_solver_init(FastPMSolver *fastpm, FastPMConfig *config, MPI_Comm com
         fastpm->cosmology[0] = *config->cosmology;
     }
     fastpm_cosmology_init(fastpm->cosmology);
-    if (config->pgdc) fastpm_raise(-1, "fastpm_b200: the PGD correction (pgdcorrection.c) is out of scope of this build\n");
     memset(fastpm->pgdc, 0, sizeof(fastpm->pgdc));
+    if (config->pgdc) {                                  /* solver.c:55-66 */
+        fastpm->pgdc[0].PainterType = config->PAINTER_TYPE; fastpm->pgdc[0].PainterSupport = config->painter_support;
+        fastpm->pgdc[0].alpha0 = config->pgdc_alpha0; fastpm->pgdc[0].A = config->pgdc_A; fastpm->pgdc[0].B = config->pgdc_B;
+        fastpm->pgdc[0].kl = config->pgdc_kl; fastpm->pgdc[0].ks = config->pgdc_ks;
+    }
     fastpm->event_handlers = NULL;
     fastpm->comm = comm;
     fastpm->ThisTask = fpm_comm_rank(comm);
@@ -200,6 +204,12 @@ static void do_force(FastPMSolver *fastpm, FastPMTransition *trans)
     fastpm_solver_compute_force(fastpm, pm, painter, fastpm->config->SOFTENING_TYPE, fastpm->config->KERNEL_TYPE, delta_k, trans->a.f);
     if (fpm_pending_wrap) { FastPMStore *pw = fpm_pending_wrap; fpm_pending_wrap = NULL; fastpm_store_wrap(pw, pm->BoxSize); }
     LEAVE(force);
+    if (p->pgdc) {
+        /* solver.c:458-464; delta_k is input, unchanged (and not yet deconvolved) */
+        CLOCK(pgdc);
+        fastpm_pgdc_calculate(fastpm->pgdc, pm, p, delta_k, trans->a.f, 1.0);
+        LEAVE(pgdc);
+    }
     ENTER(event);
     /* solver.c:471: the event sees the CIC-compensated density.  Nobody else reads delta_k afterwards, so the
      * sweep is skipped when no FORCE/after handler is installed. */
@@ -396,6 +406,15 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      int growth_mode, int compute_potential, double nLPT,
                                      double Omega_m_, double h, double T_cmb, double N_eff, int N_nu)
 {
+    return fastpm_b200_solver_new_ex(nc, boxsize, pm_nc_factor_pairs, npairs, alloc_factor, lpt_nc_factor, force_mode, kernel_type,
+                                     growth_mode, compute_potential, nLPT, Omega_m_, h, T_cmb, N_eff, N_nu, NULL);
+}
+
+FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
+                                        double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
+                                        int growth_mode, int compute_potential, double nLPT,
+                                        double Omega_m_, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc)
+{
     libfastpm_init();
     SolverBox *b = calloc(1, sizeof(*b));
     if (npairs > 8) npairs = 8;
@@ -408,6 +427,10 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
     cfg->nc = nc; cfg->boxsize = boxsize; cfg->alloc_factor = alloc_factor; cfg->lpt_nc_factor = lpt_nc_factor;
     cfg->cosmology = c; cfg->vpminit = b->vpminit; cfg->USE_DX1_ONLY = 0; cfg->USE_SHIFT = 0;
     cfg->ExtraAttributes = compute_potential ? COLUMN_POTENTIAL : 0;
+    if (pgdc) {
+        cfg->pgdc = 1; cfg->pgdc_alpha0 = pgdc[0]; cfg->pgdc_A = pgdc[1]; cfg->pgdc_B = pgdc[2]; cfg->pgdc_kl = pgdc[3]; cfg->pgdc_ks = pgdc[4];
+        cfg->ExtraAttributes |= COLUMN_PGDC;
+    }
     cfg->nLPT = nLPT; cfg->PAINTER_TYPE = FASTPM_PAINTER_CIC; cfg->painter_support = 2;
     cfg->FORCE_TYPE = force_mode; cfg->KERNEL_TYPE = kernel_type; cfg->SOFTENING_TYPE = FASTPM_SOFTENING_NONE;
     fastpm_solver_init(&b->solver, cfg, MPI_COMM_WORLD);

@@ -41,6 +41,30 @@ __global__ void __launch_bounds__(256) transfer_kernel(const FpmGeom g, const Fp
     }
 }
 
+// pgdcorrection.c:28-59 apply_pgdpot_transfer: to = (float)(alpha * exp(-kl^2/kk - kk^2/ks^4) / kk * from), kk = k_x^2 + k_y^2 + k_z^2
+// summed in double from the float tables in that order; 0 where kk == 0.
+__global__ void __launch_bounds__(256) pgd_transfer_kernel(const FpmGeom g, const FpmKTables kt, const double alpha, const double kl2,
+        const double ks4, const float2 *__restrict__ from, float2 *__restrict__ to, size_t total)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        double kk = 0;
+        kk += (double) kt.kk[m.ix]; kk += (double) kt.kk[m.iy]; kk += (double) kt.kk[m.iz];
+        float2 v = from[m.off];
+        if (kk > 0) {
+            const double fac = alpha * exp(-kl2 / kk - kk * kk / ks4) / kk;
+            v.x = (float) (fac * (double) v.x);
+            v.y = (float) (fac * (double) v.y);
+        } else {
+            v.x = 0.f; v.y = 0.f;
+        }
+        to[m.off] = v;
+    }
+}
+
 // transfer.c:78-113: kernel[d][i] = 1/sinc^2(k h/2) in double (table prepared on the host), product in
 // double, one rounding to float per component.
 __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const double *__restrict__ dtab,
@@ -329,6 +353,15 @@ int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const Fp
 {
     const size_t total = cplx_total(m->geom);
     FPM_TIMED(FPM_K_KSPACE, st, (transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, *s, (const float2 *) from, (float2 *) to, total)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, double alpha, double kl, double ks, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    const double kl2 = kl * kl, ks4 = ks * ks * ks * ks;              // pgdcorrection.c:35-36
+    FPM_TIMED(FPM_K_KSPACE, st, (pgd_transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, alpha, kl2, ks4, (const float2 *) from, (float2 *) to, total)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -65,6 +65,17 @@ __global__ void __launch_bounds__(256) drift_kernel(const DriftArgs a)
     }
 }
 
+// The PGD displacement every drift carries when the store has a pgdc column (factors.c:108-113):
+//   xo += 0.5 * pgdc * dyyy / dyyy_table[last], added to the drifted position in double (x is stored as double, so adding it in
+//   a second pass over x gives the reference's bits).
+__global__ void __launch_bounds__(256) pgd_shift_kernel(double *__restrict__ x, const float *__restrict__ pgdc, const double dyyy,
+        const double dyyy_last, const long long n3)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < n3; i += stride) x[i] = x[i] + 0.5 * (double) pgdc[i] * dyyy / dyyy_last;
+}
+
 // A run of consecutive in-place kicks and drifts of one store (the K K D D between two force evaluations, solver.c:283-356)
 // applied in ONE pass: every particle component goes through the same operations, in the same order and with the same
 // roundings as kick_kernel / drift_kernel above, but v and x stay in registers between them.
@@ -241,6 +252,14 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
     if (np <= 0) return 0;
     DriftArgs a = { x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, mode, 3 * np };
     FPM_TIMED(FPM_K_DRIFT, st, (drift_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_pgd_shift_launch(double *x, const float *pgdc, double dyyy, double dyyy_last, long long np, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    FPM_TIMED(FPM_K_DRIFT, st, (pgd_shift_kernel<<<stream_grid(3 * np), 256, 0, st>>>(x, pgdc, dyyy, dyyy_last, 3 * np)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

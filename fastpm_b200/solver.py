@@ -12,9 +12,9 @@ from .device import FORCE_MODES, KERNELS
 
 GROWTH_MODES = {"LCDM": 0, "ODE": 1}
 COLUMNS = dict(mask=1 << 0, x=1 << 1, q=1 << 2, v=1 << 3, dx1=1 << 4, dx2=1 << 5, dv1=1 << 6, acc=1 << 7,
-               id=1 << 8, potential=1 << 11, mass=1 << 20)
+               id=1 << 8, potential=1 << 11, pgdc=1 << 13, mass=1 << 20)
 _COL_DTYPE = dict(x=(np.float64, 3), v=(np.float32, 3), acc=(np.float32, 3), dx1=(np.float32, 3), dx2=(np.float32, 3),
-                  id=(np.uint64, 1), potential=(np.float32, 1))
+                  id=(np.uint64, 1), potential=(np.float32, 1), pgdc=(np.float32, 3))
 
 HANDLER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
@@ -47,6 +47,8 @@ def _bind(lib):
     vp, dbl, i64, i32 = C.c_void_p, C.c_double, C.c_int64, C.c_int
     lib.fastpm_b200_solver_new.restype = vp
     lib.fastpm_b200_solver_new.argtypes = [i64, dbl, vp, i32, dbl, dbl, i32, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, i32]
+    lib.fastpm_b200_solver_new_ex.restype = vp
+    lib.fastpm_b200_solver_new_ex.argtypes = [i64, dbl, vp, i32, dbl, dbl, i32, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, i32, vp]
     lib.fastpm_b200_solver_free.argtypes = [vp]
     lib.fastpm_b200_solver_cdm.restype = vp
     lib.fastpm_b200_solver_cdm.argtypes = [vp]
@@ -95,16 +97,21 @@ class Solver:
 
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4", growth_mode="ODE",
                  np_alloc_factor=1.0, lpt_nc_factor=1, compute_potential=False, Omega_m=0.307494, h=0.6774,
-                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5):
+                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5, pgdc=None):
+        """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (pgdcorrection.c, src/fastpm.c:204-217)."""
         self.lib = _bind(_lib.require_device())
+        par = None if pgdc is None else np.array([float(v) for v in pgdc], dtype=np.float64)
+        if par is not None and par.shape != (5,):
+            raise ValueError("pgdc = (alpha0, A, B, kl, ks)")
         pairs = pm_nc_factor if isinstance(pm_nc_factor, (list, tuple)) else [(0.0, pm_nc_factor)]
         flat = np.array([v for pr in pairs for v in pr], dtype=np.float64)
         self.nc, self.boxsize, self.force_mode = int(nc), float(boxsize), force_mode
         self._handlers = []
-        self.h = self.lib.fastpm_b200_solver_new(int(nc), float(boxsize), flat.ctypes.data, len(pairs), float(np_alloc_factor),
-                                                 float(lpt_nc_factor), FORCE_MODES[force_mode], KERNELS[kernel_type],
-                                                 GROWTH_MODES[growth_mode], int(compute_potential), float(nLPT),
-                                                 float(Omega_m), float(h), float(T_cmb), float(N_eff), int(N_nu))
+        self.h = self.lib.fastpm_b200_solver_new_ex(int(nc), float(boxsize), flat.ctypes.data, len(pairs), float(np_alloc_factor),
+                                                    float(lpt_nc_factor), FORCE_MODES[force_mode], KERNELS[kernel_type],
+                                                    GROWTH_MODES[growth_mode], int(compute_potential), float(nLPT),
+                                                    float(Omega_m), float(h), float(T_cmb), float(N_eff), int(N_nu),
+                                                    None if par is None else par.ctypes.data)
         self.cdm = self.lib.fastpm_b200_solver_cdm(self.h)
         self.lptpm = self.lib.fastpm_b200_solver_lptpm(self.h)
 

@@ -131,6 +131,8 @@ int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to);      /* tr
  * library that is handed the buffer applies it first, fpm_decic_cancel drops it (solver.c:471 before the FORCE/after event) */
 int fpm_decic_defer(const fpm_mesh *m, float *cplx);
 int fpm_decic_cancel(const float *cplx);
+/* PGD potential, apply_pgdpot_transfer pgdcorrection.c:28-59: to = alpha exp(-kl^2/k^2 - k^4/ks^4) / k^2 * from */
+int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, double alpha, double kl, double ks);
 int fpm_scale(const float *from, float *to, size_t nfloats, double value); /* transfer.c:213 */
 int fpm_divide(const float *from, float *to, size_t nfloats, double value); /* solver.c:738-742 */
 int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign); /* pm2lpt.c:103,118 */
@@ -163,6 +165,9 @@ int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx
  * stay in registers in between.  ops[nops][7] = { kind (0 kick, 1 drift), mode (kick: 1 = COLA; drift: FastPMForceType),
  * then the five factors in the argument order of fpm_kick (dda q1 q2 Dv1 Dv2) / fpm_drift (dyyy da1 da2 Dv1 Dv2) }; nops <= 8 */
 int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, const float *dx2, int64_t np, int nops, const double *ops);
+/* the PGD term of fastpm_drift_one (factors.c:108-113), added to already drifted positions:
+ * x += 0.5 * pgdc * dyyy / dyyy_last, with dyyy_last = drift->dyyy[nsamples - 1] != 0 */
+int fpm_pgd_shift(double *x, const float *pgdc, int64_t np, double dyyy, double dyyy_last);
 /* ---- K8 wrap: fastpm_store_wrap, store.c:447 -------------------------------------------------- */
 /* the reference aborts when a particle is > 10000 boxes away (store.c:460-471): that flag is reported by the NEXT
  * fpm_wrap call or by fpm_wrap_check() (which waits for the stream), so the integrator itself never blocks on it */

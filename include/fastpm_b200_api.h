@@ -366,6 +366,11 @@ void fastpm_ic_induce_correlation(PM *pm, FastPMFloat *delta_k, fastpm_fkfunc pk
 
 /* ------------------------------------------------------------------ [pgdcorrection.h:3-11] */
 typedef struct { FastPMPainterType PainterType; int PainterSupport; double alpha0, A, B, kl, ks; } FastPMPGDCorrection;
+double fastpm_pgdc_get_alpha(FastPMPGDCorrection *pgdc, double a);      /* pgdcorrection.h:14-22 */
+double fastpm_pgdc_get_kl(FastPMPGDCorrection *pgdc, double a);
+double fastpm_pgdc_get_ks(FastPMPGDCorrection *pgdc, double a);
+/* fills p->pgdc (device column) from delta_k, which is left unchanged; pgdcorrection.h:24-27 */
+void fastpm_pgdc_calculate(FastPMPGDCorrection *pgdc, PM *pm, FastPMStore *p, FastPMFloat *delta_k, double a, double fac);
 
 /* ------------------------------------------------------------------ [timemachine.h:5-47] */
 enum FastPMAction { FASTPM_ACTION_FORCE, FASTPM_ACTION_KICK, FASTPM_ACTION_DRIFT };
@@ -510,6 +515,11 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                      int growth_mode, int compute_potential, double nLPT,
                                      double Omega_m, double h, double T_cmb, double N_eff, int N_nu);
+/* same, with the PGD correction of src/fastpm.c:204-217: pgdc = NULL (off) or {alpha0, A, B, kl, ks} (adds COLUMN_PGDC) */
+FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
+                                        double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
+                                        int growth_mode, int compute_potential, double nLPT,
+                                        double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc);
 void fastpm_b200_solver_free(FastPMSolver *solver);
 
 #ifdef __cplusplus

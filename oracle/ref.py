@@ -27,6 +27,7 @@ class RefConfig(C.Structure):
         ("Omega_m", C.c_double), ("h", C.c_double), ("T_cmb", C.c_double), ("Omega_k", C.c_double),
         ("w0", C.c_double), ("wa", C.c_double), ("N_eff", C.c_double),
         ("N_nu", C.c_int), ("enforce_broadband_kmax", C.c_int),
+        ("pgdc", C.c_double * 6),
     ]
 
 
@@ -58,7 +59,8 @@ class Session:
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4",
                  growth_mode="ODE", np_alloc_factor=4.0, lpt_nc_factor=1, compute_potential=False,
                  Omega_m=0.307494, h=0.6774, T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5,
-                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4):
+                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None):
+        """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (src/fastpm.c:204-217)."""
         cfg = RefConfig()
         cfg.nc = nc
         cfg.boxsize = boxsize
@@ -79,6 +81,7 @@ class Session:
         cfg.Omega_m, cfg.h, cfg.T_cmb, cfg.Omega_k = Omega_m, h, T_cmb, 0.0
         cfg.w0, cfg.wa, cfg.N_eff, cfg.N_nu = -1.0, 0.0, N_eff, N_nu
         cfg.enforce_broadband_kmax = enforce_broadband_kmax
+        cfg.pgdc = (C.c_double * 6)(*([0.0] * 6 if pgdc is None else [1.0] + [float(v) for v in pgdc]))
         self.cfg = cfg
         self.nc, self.boxsize, self.force_mode = nc, boxsize, force_mode
         self._h = C.c_void_p(lib().ref_session_new(C.byref(cfg)))
@@ -173,6 +176,23 @@ class Session:
             dx2 = out["dx2"] = np.zeros((n, 3), dtype=np.float32)
         lib().ref_get_particles(self._h, _p(out["x"]), _p(out["v"]), _p(out["acc"]), _p(out["id"]), _p(dx1), _p(dx2), _p(out["meta"]))
         return out
+
+    def pgdc_calculate(self, delta_k, x, par, which=0, a=1.0):
+        """fastpm_pgdc_calculate for positions x: par = (alpha0, A, B, kl, ks); returns float32 [np][3]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        dk = np.ascontiguousarray(delta_k, dtype=np.float32)
+        out = np.zeros((len(x), 3), dtype=np.float32)
+        lib().ref_pgdc(self._h, C.c_int(which), C.c_double(a), _p(dk), _p(x), C.c_int64(len(x)), _p(par), _p(out))
+        return out
+
+    def get_pgdc(self):
+        out = np.zeros((self.np, 3), dtype=np.float32)
+        lib().ref_get_pgdc(self._h, _p(out))
+        return out
+
+    def set_pgdc(self, pgdc):
+        lib().ref_set_pgdc(self._h, _p(np.ascontiguousarray(pgdc, dtype=np.float32)))
 
     def set_particles(self, x, v=None, id=None, dx1=None, dx2=None, meta=None):
         x = np.ascontiguousarray(x, dtype=np.float64)

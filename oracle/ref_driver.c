@@ -39,6 +39,7 @@ typedef struct {
     double Omega_m, h, T_cmb, Omega_k, w0, wa, N_eff;
     int N_nu;
     int enforce_broadband_kmax;
+    double pgdc[6];              /* {enabled, alpha0, A, B, kl, ks}: the PGD correction of src/fastpm.c:204-217 */
 } RefConfig;
 
 #define MAX_FORCE_RECORDS 256
@@ -151,6 +152,12 @@ RefSession *ref_session_new(const RefConfig *cfg)
     config->NprocY = 0; config->UseFFTW = 0;
     config->ExtraAttributes = 0;
     if (cfg->compute_potential) config->ExtraAttributes |= COLUMN_POTENTIAL;
+    if (cfg->pgdc[0] != 0) {
+        config->pgdc = 1;
+        config->pgdc_alpha0 = cfg->pgdc[1]; config->pgdc_A = cfg->pgdc[2]; config->pgdc_B = cfg->pgdc[3];
+        config->pgdc_kl = cfg->pgdc[4]; config->pgdc_ks = cfg->pgdc[5];
+        config->ExtraAttributes |= COLUMN_PGDC;
+    }
 
     fastpm_solver_init(s->solver, config, MPI_COMM_WORLD);
 
@@ -406,6 +413,37 @@ void ref_kernel_transfer(RefSession *s, int which, double a, const float *delta_
     gravity_apply_kernel_transfer(s->solver->config->KERNEL_TYPE, pm, dk, canvas, f);
     memcpy(out, canvas, sizeof(FastPMFloat) * pm->allocsize);
     pm_free(pm, canvas); pm_free(pm, dk);
+}
+
+/* fastpm_pgdc_calculate (pgdcorrection.c:61-137) for np positions: par = {alpha0, A, B, kl, ks}; out[np][3] */
+void ref_pgdc(RefSession *s, int which, double a, const float *delta_k_in, const double *x, int64_t np, const double *par, float *out)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMPGDCorrection pgdc[1] = {{ FASTPM_PAINTER_CIC, 2, par[0], par[1], par[2], par[3], par[4] }};
+    FastPMStore p[1];
+    fastpm_store_init(p, "tmp", np > 0 ? np : 1, COLUMN_POS | COLUMN_PGDC, FASTPM_MEMORY_HEAP);
+    p->np = np;
+    memcpy(p->x, x, sizeof(p->x[0]) * np);
+    FastPMFloat *dk = pm_alloc(pm);
+    memcpy(dk, delta_k_in, sizeof(FastPMFloat) * pm->allocsize);
+    fastpm_pgdc_calculate(pgdc, pm, p, dk, a, 1.0);
+    memcpy(out, p->pgdc, sizeof(p->pgdc[0]) * np);
+    pm_free(pm, dk);
+    fastpm_store_destroy(p);
+}
+
+/* the pgdc column of the session's particles (zeros when the correction is off) */
+void ref_get_pgdc(RefSession *s, float *out)
+{
+    FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
+    if (p->pgdc) memcpy(out, p->pgdc, sizeof(p->pgdc[0]) * p->np);
+    else memset(out, 0, sizeof(float) * 3 * p->np);
+}
+
+void ref_set_pgdc(RefSession *s, const float *in)
+{
+    FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
+    if (p->pgdc) memcpy(p->pgdc, in, sizeof(p->pgdc[0]) * p->np);
 }
 
 void ref_decic(RefSession *s, int which, double a, const float *in, float *out)

@@ -7,6 +7,7 @@
 //               complex64 dk[n][n][pitch_c] in the device layout [ky][kx][kz];  then per op:
 //   transfer: int32 potorder, negate, ngrad, dir0, dir1, gradorder, zero_selfconj      -> complex64 out (device layout)
 //   decic                                                                               -> complex64 out
+//   pgd:      float64 alpha, kl, ks; int32 dir                                          -> complex64 out
 //   pk:       int32 decic                                                               -> float64 sums[3*(n/2) + 1]
 #include "cuda_emul.h"
 #include <cstdio>
@@ -44,6 +45,17 @@ int main(int argc, char **argv)
         s.active = 1; s.potorder = one<int32_t>(in); s.negate = one<int32_t>(in); s.ngrad = one<int32_t>(in);
         s.graddir[0] = one<int32_t>(in); s.graddir[1] = one<int32_t>(in); s.gradorder = one<int32_t>(in); s.zero_selfconj = one<int32_t>(in); s.scale = 1.0;
         fpm_emul_launch(3, 256, 0, [&]() { transfer_kernel(g, kt, s, dk.data(), res.data(), total); });
+        fwrite(res.data(), sizeof(float2), total, out);
+    } else if (op == "pgd") {
+        // double alpha, kl, ks; int32 dir: the PGD potential sweep, then the gradient i*k_finite[dir] (what fpm_mesh_c2r fuses)
+        const double alpha = one<double>(in), kl = one<double>(in), ks = one<double>(in);
+        const int dir = one<int32_t>(in);
+        std::vector<float2> pot(total);
+        fpm_emul_launch(3, 256, 0, [&]() { pgd_transfer_kernel(g, kt, alpha, kl * kl, ks * ks * ks * ks, dk.data(), pot.data(), total); });
+        FpmTransferSpec s;
+        memset(&s, 0, sizeof(s));
+        s.active = 1; s.potorder = -1; s.ngrad = 1; s.graddir[0] = dir; s.gradorder = 1; s.zero_selfconj = 1; s.scale = 1.0;
+        fpm_emul_launch(3, 256, 0, [&]() { transfer_kernel(g, kt, s, pot.data(), res.data(), total); });
         fwrite(res.data(), sizeof(float2), total, out);
     } else if (op == "decic") {
         fpm_emul_launch(3, 256, 0, [&]() { decic_kernel(g, dtab.data(), dk.data(), res.data(), total); });

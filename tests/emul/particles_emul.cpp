@@ -105,6 +105,19 @@ int main(int argc, char **argv)
         launch_seq(grid, 256, [&]() { cic_readout3_kernel(g, canvas[0].data(), canvas[1].data(), canvas[2].data(), x.data(), one.data(), np, lag_nc, nbrick); });
         dump(out, sep);
         dump(out, one);
+    } else if (op == "pgddrift") {
+        // in: int64 np, int32 drift_mode, drift f64[5] (dyyy da1 da2 Dv1 Dv2), f64 dyyy_last, x f64[3np], v, dx1, dx2, pgdc f32[3np]
+        // out: x after drift_kernel followed by pgd_shift_kernel (factors.c:75-114 with a pgdc column)
+        const long long np = in.one<int64_t>();
+        const int dmode = in.one<int32_t>();
+        std::vector<double> df = in.many<double>(5);
+        const double dyyy_last = in.one<double>();
+        std::vector<double> x = in.many<double>((size_t) 3 * np);
+        std::vector<float> v = in.many<float>((size_t) 3 * np), d1 = in.many<float>((size_t) 3 * np), d2 = in.many<float>((size_t) 3 * np), pg = in.many<float>((size_t) 3 * np);
+        DriftArgs a = { x.data(), x.data(), v.data(), d1.data(), d2.data(), df[0], df[1], df[2], df[3], df[4], dmode, 3 * np };
+        launch_seq(5, 256, [&]() { drift_kernel(a); });
+        launch_seq(5, 256, [&]() { pgd_shift_kernel(x.data(), pg.data(), df[0], dyyy_last, 3 * np); });
+        dump(out, x);
     } else if (op == "update") {
         // in: int64 np, int32 cola, int32 drift_mode, kick f64[5] (dda q1 q2 Dv1 Dv2), drift f64[5] (dyyy da1 da2 Dv1 Dv2),
         //     x f64[3np], v f32[3np], acc f32[3np], dx1 f32[3np], dx2 f32[3np]

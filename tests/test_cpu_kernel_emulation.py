@@ -155,6 +155,33 @@ def test_kick_drift_and_fused_update_kernels_bit_exact(emul, one_thread_ref, pk_
     assert np.array_equal(v_fused, v_seq) and np.array_equal(x_fused, x_seq)         # one fused pass == five separate kernels
 
 
+@pytest.mark.parametrize("mode", ["fastpm", "cola"])
+def test_drift_with_pgd_column_bit_exact(emul, one_thread_ref, pk_text, tmp_path, mode):
+    """fastpm_drift_one with a pgdc column (factors.c:108-113): drift_kernel + pgd_shift_kernel == the reference's positions."""
+    nc, L = 16, 64.0
+    s = one_thread_ref.Session(nc=nc, boxsize=L, pm_nc_factor=2, force_mode=mode, growth_mode="LCDM", pgdc=(0.8, 4.0, 2.0, 1.0, 10.0))
+    dk, _, _ = s.ic_deltak(12, pk_text)
+    s.setup_lpt(dk, 0.1)
+    n = s.np
+    rng = np.random.default_rng(3)
+    pg = (rng.standard_normal((n, 3)) * 0.3).astype(np.float32)
+    s.set_pgdc(pg)
+    p0 = s.get_particles()
+    ai, ac, af = 0.1, 0.15, 0.2
+    df = s.drift_factor(ai, ac, af)
+    s.drift(ai, ac, af)
+    p1 = s.get_particles()
+    s.close()
+    fm = {"fastpm": 0, "pm": 1, "cola": 2}[mode]
+    d5 = [df["dyyy"][-1] - df["dyyy"][0], df["da1"][-1] - df["da1"][0], df["da2"][-1] - df["da2"][0], df["Dv1"], df["Dv2"]]
+    zeros = np.zeros((n, 3), dtype=np.float32)
+    payload = struct.pack("<qi", n, fm) + np.array(d5).tobytes() + struct.pack("<d", df["dyyy"][-1]) + p0["x"].tobytes() + p0["v"].tobytes() + \
+        (p0["dx1"] if fm == 2 else zeros).tobytes() + (p0["dx2"] if fm == 2 else zeros).tobytes() + pg.tobytes()
+    x = np.frombuffer(emul("pgddrift", payload, str(tmp_path)), dtype=np.float64).reshape(n, 3)
+    assert np.abs(x - p0["x"]).max() > 1e-3                 # something moved
+    assert np.array_equal(x, p1["x"])
+
+
 # ---------------------------------------------------------------- k-space kernels (tests/emul/kspace_emul.cpp)
 @pytest.fixture(scope="module")
 def kspace_emul(tmp_path_factory):
@@ -243,4 +270,27 @@ def test_kspace_kernels_against_reference(kspace_emul, ref_mod, tmp_path):
         sel = nm > 0
         np.testing.assert_allclose(sk[sel] / nm[sel], k0[sel], rtol=1e-13)
         np.testing.assert_allclose(sp[sel] / nm[sel] * L ** 3, p0[sel], rtol=1e-12)
+    s.close()
+
+
+def test_pgd_transfer_kernel_against_reference(kspace_emul, ref_mod, tmp_path):
+    """pgdcorrection.c:28-137: the PGD potential sweep + gradient of the kernel sources, pushed through the reference's own
+    c2r and readout, equals fastpm_pgdc_calculate bit for bit (same libm exp on the CPU)."""
+    nmesh, L = 32, 50.0
+    rng = np.random.default_rng(6)
+    field = rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32)
+    x = rng.uniform(0, L, size=(3000, 3))
+    par = (0.8, 4.0, 2.0, 1.3, 9.5)                          # alpha0, A, B, kl, ks
+    a = 0.7
+    alpha = par[0] * 10 ** (par[1] * a * a - par[2] * a)    # fastpm_pgdc_get_alpha, pgdcorrection.c:10-14
+    s = ref_mod.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    dk = s.r2c(s.real_pack(field))
+    want = s.pgdc_calculate(dk, x, par, a=a)
+    assert np.abs(want).max() > 0
+    tab, dec = _tables(nmesh, L)
+    head = struct.pack("<id", nmesh, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(s.complex_view(dk), nmesh).tobytes()
+    for d in range(3):
+        got_k = _from_device_layout(kspace_emul("pgd", head + struct.pack("<dddi", alpha, par[3], par[4], d), str(tmp_path)), nmesh)
+        got = s.readout(s.c2r(s.complex_pack(got_k)), x)
+        assert np.array_equal(got, want[:, d]), d
     s.close()

@@ -71,26 +71,6 @@ def test_readout_bit_exact(dev, ref_mod, nmesh, kind):
     s.close()
 
 
-def test_three_component_readout_equals_three_readouts(dev):
-    """fpm_readout3 (the FASTPM_B200_FUSED_READOUT path of fastpm_solver_compute_force) == three fpm_readout calls, bit for bit."""
-    nmesh, L, npart = 64, 64.0, 50000
-    rng = np.random.default_rng(77)
-    x = _positions(rng, npart, L, "edges")
-    m = dev.Mesh(nmesh, L)
-    canv = []
-    for d in range(3):
-        c = m.alloc()
-        m.upload_real(c, rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32))
-        canv.append(c)
-    xd = dev.DeviceBuffer.from_host(x)
-    sep = dev.DeviceBuffer(12 * npart)
-    one = dev.DeviceBuffer(12 * npart)
-    for d in range(3):
-        m.readout(canv[d], xd, npart, sep, out_stride=3, out_offset_bytes=4 * d)
-    m.readout3(canv, xd, npart, one)
-    assert np.array_equal(sep.download(np.float32), one.download(np.float32))
-
-
 def test_empty_and_single_particle(dev, ref_mod):
     """Edge cases of the store loops (painter.c:320-374, factors.c:176-197): np = 0 leaves everything untouched, np = 1 on a
     cell corner, on the box edge and outside the box deposits unit mass into the periodic images the reference uses."""

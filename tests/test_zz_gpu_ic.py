@@ -81,3 +81,61 @@ def test_fused_readout_option_gives_the_same_run(tmp_path):
     d = np.abs(res[0][0] - res[1][0])
     assert np.minimum(d, 32.0 - d).max() < 1e-5
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
+
+
+def test_three_component_readout_equals_three_readouts():
+    """fpm_readout3 (the FASTPM_B200_FUSED_READOUT path of fastpm_solver_compute_force) == three fpm_readout calls, bit for bit."""
+    from fastpm_b200 import device as dev
+    dev._lib.require_device()
+    nmesh, L, npart = 64, 64.0, 50000
+    rng = np.random.default_rng(77)
+    x = rng.uniform(0, L, size=(npart, 3))
+    x[: npart // 4] = np.round(x[: npart // 4] / (L / 8)) * (L / 8)      # on cell faces, including x == L
+    x[0], x[1] = [L, L, L], [0, 0, 0]
+    m = dev.Mesh(nmesh, L)
+    canv = []
+    for d in range(3):
+        c = m.alloc()
+        m.upload_real(c, rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32))
+        canv.append(c)
+    xd = dev.DeviceBuffer.from_host(x)
+    sep = dev.DeviceBuffer(12 * npart)
+    one = dev.DeviceBuffer(12 * npart)
+    for d in range(3):
+        m.readout(canv[d], xd, npart, sep, out_stride=3, out_offset_bytes=4 * d)
+    m.readout3(canv, xd, npart, one)
+    assert np.array_equal(sep.download(np.float32), one.download(np.float32))
+
+
+def test_pgd_correction_matches_reference(ref_mod, pk_text):
+    """Row N3 of SURVEY.md section 8f: the PGD correction (pgdcorrection.c) switched on -- the pgdc column after every force and
+    the extra displacement in every drift (factors.c:108-113) -- against the oracle on identical initial conditions."""
+    from fastpm_b200.solver import Solver
+    nc, L, B = 32, 64.0, 2
+    par = (0.2, 0.5, 1.0, 1.0, 5.0)                      # alpha0, A, B, kl, ks
+    steps = np.linspace(0.1, 1.0, 5)
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, pgdc=par)
+    dk, _, _ = s.ic_deltak(100, pk_text)
+    s.setup_lpt(dk, steps[0])
+    s.evolve(steps)
+    want, want_pgdc = s.get_particles(), s.get_pgdc()
+    s.close()
+    # the same run without the correction, to show that the comparison is sensitive to it
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+    s.setup_lpt(dk, steps[0])
+    s.evolve(steps)
+    plain = s.get_particles()
+    s.close()
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, pgdc=par)
+    g.setup_lpt(dk, steps[0])
+    g.evolve(steps)
+    x, v, pg = g.get_column("x"), g.get_column("v"), g.get_column("pgdc")
+    g.close()
+
+    def pdist(a, b):
+        d = np.abs(np.mod(a, L) - np.mod(b, L))
+        return np.minimum(d, L - d).max()
+    assert pdist(want["x"], plain["x"]) > 1e-2           # the correction moves particles by much more than the tolerance
+    assert pdist(x, want["x"]) < 1e-4                    # Mpc/h, BASELINE.json north_star
+    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+    assert np.abs(pg - want_pgdc).max() < 1e-4 * np.abs(want_pgdc).max()
