@@ -10,9 +10,6 @@
  */
 #include "internal.h"
 
-typedef void (*fpm_host_allreduce_fn)(void *buf, int count, int is_int64, int op, void *userdata);
-typedef void (*fpm_host_allgather_fn)(const void *send, int nbytes, void *recv, void *userdata);
-
 /* device side, csrc/comm.cu */
 int fpm_ipc_get_handle(void *dev_ptr, void *handle64, uint64_t *offset);
 void *fpm_ipc_open(const void *handle64, uint64_t offset);
@@ -88,6 +85,13 @@ static void peers_of(void *local, void *peers[MAXR])
 }
 
 /* ------------------------------------------------------------------ set-up by the launcher */
+/* the collectives only (no device arena): for host-side tools of a multi-process run, e.g. the snapshot writers of host/io.c */
+void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
+{
+    if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
+    g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
+}
+
 void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
 {
     libfastpm_init();

@@ -389,11 +389,10 @@ void fastpm_unset_species_snapshot(FastPMSolver *fastpm, FastPMStore *p, FastPMD
     }
     if (kick) fastpm_kick_store(kick, po, po, p->meta.a_v);
     if (drift) fastpm_drift_store(drift, po, po, p->meta.a_x);
-    /* columns are shared, only the time stamps and count need restoring */
-    double a_x = p->meta.a_x, a_v = p->meta.a_v;
+    /* columns are shared; count and meta come back from po like fastpm_store_steal does (store.c:911-921): the reverting kick /
+     * drift above have put po's time stamps back to p's, and without them (restart, src/fastpm.c:625-633) po's are what was read */
     p->np = po->np;
     p->meta = po->meta;
-    p->meta.a_x = a_x; p->meta.a_v = a_v;
     fastpm_store_wrap(p, fastpm->basepm->BoxSize);
     po->attributes = 0;
 }
@@ -521,6 +520,14 @@ void fastpm_b200_host_drift_factor(const double *cosmo, int growth_mode, int for
 { FastPMSolver s; host_only_solver(&s, cosmo, growth_mode, force_mode, nLPT); fastpm_b200_drift_factor(&s, ai, ac, af, out); }
 void fastpm_b200_host_growth(const double *cosmo, int growth_mode, double a, double *out)
 { FastPMSolver s; host_only_solver(&s, cosmo, growth_mode, 0, 0); fastpm_b200_growth(&s, a, out); }
+/* the snapshot "Header" numbers (write_snapshot_header, io.c:250-290) without a device: host/io.c */
+void fastpm_b200_host_io_header(const double *cosmo, int growth_mode, int64_t nc, double boxsize, double aout, double M0, uint64_t np_total, FpmIoHeader *h)
+{
+    FastPMSolver s;
+    host_only_solver(&s, cosmo, growth_mode, 0, 0);
+    s.config->nc = nc; s.config->boxsize = boxsize;
+    fastpm_b200_io_header_values(&s, aout, M0, np_total, h);
+}
 
 /* ------------------------------------------------------------------ synthetic ICs for benchmark sizes
  * White noise from the counter-based device generator (instead of the serial RANLUX stream of

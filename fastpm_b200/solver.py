@@ -121,6 +121,17 @@ class Solver:
             self.lib.fastpm_b200_memory_trim()
             self.h = None
 
+    # ---- snapshot files (bigfile directories, libfastpmio/io.c): csrc/host/io.c
+    def write_snapshot(self, filebase, sort_by_id=False):
+        self.lib.fastpm_b200_write_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        self.lib.fastpm_b200_write_snapshot(self.h, str(filebase).encode(), int(sort_by_id))
+
+    def read_snapshot(self, filebase):
+        """Restart: reads the catalog into the particle store, returns the scale factor of the snapshot."""
+        self.lib.fastpm_b200_read_snapshot.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.fastpm_b200_read_snapshot.restype = C.c_double
+        return float(self.lib.fastpm_b200_read_snapshot(self.h, str(filebase).encode()))
+
     # ---- particles (device-resident; these are host mirrors)
     @property
     def np(self):

@@ -494,6 +494,15 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
                                  FastPMKernelType kernel, FastPMFloat *delta_k, double Time);
 void gravity_apply_kernel_transfer(FastPMKernelType kernel, PM *pm, FastPMFloat *delta_k, FastPMFloat *canvas, FastPMFieldDescr field);
 
+/* ------------------------------------------------------------------ ranks (one process per GPU, x-slabs)
+ * The launcher supplies two host-buffer collectives (MPI_Allreduce / MPI_Allgather in an MPI build, torch.distributed in
+ * fastpm_b200/multigpu.py): allreduce(buf, count, is_int64 (else double), op (0 sum, 1 min, 2 max)), allgather(send, nbytes, recv).
+ * fastpm_b200_comm_init also maps the peers' device arenas; _init_host sets the collectives only (host-side tools: file IO). */
+typedef void (*fpm_host_allreduce_fn)(void *buf, int count, int is_int64, int op, void *userdata);
+typedef void (*fpm_host_allgather_fn)(const void *send, int nbytes, void *recv, void *userdata);
+void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather, void *userdata);
+void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather, void *userdata);
+
 /* ------------------------------------------------------------------ fastpm_b200 extensions
  * Host mirrors of device-resident data, for callers (snapshot writers, FOF, lightcone, custom event
  * handlers) that the reference lets dereference mesh buffers and store columns directly. */
@@ -510,6 +519,40 @@ int fastpm_b200_mesh_get_complex(PM *pm, const FastPMFloat *dev, float *host_dst
 int fastpm_b200_mesh_set_complex(PM *pm, FastPMFloat *dev, const float *host_src);
 /* number of floats in a host array in the reference layout: N*N*(N+2) */
 size_t fastpm_b200_mesh_host_size(PM *pm);
+/* ------------------------------------------------------------------ [io.h] snapshot / mesh files (bigfile directories)
+ * Same names, arguments and on-disk result as libfastpmio/io.c; append mode, the distributed sort and the healpix / light-cone
+ * writers are not implemented and raise. */
+typedef void (*FastPMSnapshotSorter)(const void *ptr, void *radix, void *arg);
+void FastPMSnapshotSortByID(const void *ptr, void *radix, void *arg);
+void fastpm_sort_snapshot(FastPMStore *p, MPI_Comm comm, FastPMSnapshotSorter sorter, int redistribute);     /* io.h:19 */
+int fastpm_store_write(FastPMStore *p, const char *filebase, const char *mode, int Nwriters, MPI_Comm comm);  /* io.h:22; mode "w" or "r" */
+int fastpm_store_read(FastPMStore *p, const char *filebase, int Nwriters, MPI_Comm comm);                     /* io.h:30 */
+void write_snapshot_header(FastPMSolver *fastpm, const char *filebase, MPI_Comm comm);                        /* io.h:37 */
+void read_snapshot_header(FastPMSolver *fastpm, const char *filebase, double *aout, MPI_Comm comm);           /* io.h:41 */
+int write_complex(PM *pm, FastPMFloat *data, const char *filename, const char *blockname, int Nwriters);      /* io.h:56 */
+int read_complex(PM *pm, FastPMFloat *data, const char *filename, const char *blockname, int Nwriters);       /* io.h:59 */
+/* the same writers on plain arrays (host or device), for bindings and tests */
+typedef struct { const char *name; const char *dtype_out; const char *dtype; int nmemb; void *data; int on_device; } FpmIoColumn;
+typedef struct { int64_t q_strides[3]; double q_scale[3], q_shift[3]; int64_t q_size; double a_x, a_v, M0; } FpmIoMeta;
+typedef struct {
+    int64_t NC; double BoxSize, ScalingFactor, GrowthFactor, GrowthRate, HubbleE, RSDFactor, Omega_cdm, OmegaM, OmegaLambda, HubbleParam;
+    const char *version; uint64_t TotNumPart[6]; double MassTable[6];
+} FpmIoHeader;
+int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
+                                 const FpmIoMeta *meta, MPI_Comm comm);
+int fastpm_b200_io_read_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t *np_local,
+                                FpmIoMeta *meta, MPI_Comm comm);
+int fastpm_b200_io_write_header(const char *filebase, const FpmIoHeader *h, MPI_Comm comm);
+void fastpm_b200_io_header_values(FastPMSolver *fastpm, double aout, double M0_cdm, uint64_t np_total_cdm, FpmIoHeader *h);
+int fastpm_b200_io_write_complex_rows(const char *filename, const char *blockname, int nmesh, double boxsize, int y0, int nyl,
+                                      const float *rows, size_t pitch_c, int nfile, MPI_Comm comm);
+int fastpm_b200_io_read_complex_rows(const char *filename, const char *blockname, int nmesh, int y0, int nyl, float *rows, size_t pitch_c);
+void fastpm_b200_io_argsort_u64(const uint64_t *key, size_t n, uint64_t *perm);
+/* one snapshot of the CDM species at its current time as src/fastpm.c:1190-1200,1473-1486 writes it (unit conversion, optional
+ * sort by id, Header, catalog, conversion reverted), and the restart read of src/fastpm.c:618-635; returns the header's ScalingFactor */
+void fastpm_b200_write_snapshot(FastPMSolver *fastpm, const char *filebase, int sort_by_id);
+double fastpm_b200_read_snapshot(FastPMSolver *fastpm, const char *filebase);
+
 /* a FastPMConfig/FastPMSolver pair built from scalars, for bindings that cannot lay out the structs */
 FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                      double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,

@@ -194,6 +194,25 @@ class Session:
     def set_pgdc(self, pgdc):
         lib().ref_set_pgdc(self._h, _p(np.ascontiguousarray(pgdc, dtype=np.float32)))
 
+    def write_snapshot(self, filebase):
+        """write_snapshot_header + fastpm_store_write of the unit-converted CDM store (bigfile directory `filebase`)."""
+        lib().ref_write_snapshot(self._h, C.c_char_p(str(filebase).encode()))
+
+    def snapshot_particles(self):
+        """(x, v) after fastpm_set_species_snapshot at the particles' own time: v in km/s, x wrapped into the box."""
+        x, v = np.zeros((self.np, 3)), np.zeros((self.np, 3), dtype=np.float32)
+        lib().ref_snapshot_particles(self._h, _p(x), _p(v))
+        return x, v
+
+    def read_snapshot(self, filebase, restart=False):
+        """fastpm_store_read of the CDM catalog; restart=True converts back to the integrator's units (src/fastpm.c:618-635)."""
+        lib().ref_read_snapshot.restype = C.c_double
+        return float(lib().ref_read_snapshot(self._h, C.c_char_p(str(filebase).encode()), C.c_int(int(restart))))
+
+    def write_complex(self, dk, filename, blockname, which=0, a=1.0):
+        dk = np.ascontiguousarray(dk, dtype=np.float32)
+        lib().ref_write_complex(self._h, C.c_int(which), C.c_double(a), _p(dk), C.c_char_p(str(filename).encode()), C.c_char_p(blockname.encode()))
+
     def set_particles(self, x, v=None, id=None, dx1=None, dx2=None, meta=None):
         x = np.ascontiguousarray(x, dtype=np.float64)
         c = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)

@@ -22,6 +22,7 @@
 #include <fastpm/logging.h>
 #include <fastpm/prof.h>
 #include "pmpfft.h"
+#include <fastpm/io.h>
 
 typedef struct {
     int64_t nc;
@@ -444,6 +445,90 @@ void ref_set_pgdc(RefSession *s, const float *in)
 {
     FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
     if (p->pgdc) memcpy(p->pgdc, in, sizeof(p->pgdc[0]) * p->np);
+}
+
+/* One snapshot the way src/fastpm.c:1190-1200,1473-1486 writes it, without the Lua-dependent "ParamFile" attribute and without the
+ * distributed sort: fastpm_set_species_snapshot (unit conversion + wrap, solver.c:647-702; no drift / kick: the particles already
+ * sit at aout), write_snapshot_header, fastpm_store_write, fastpm_unset_species_snapshot. */
+void ref_write_snapshot(RefSession *s, const char *filebase)
+{
+    FastPMSolver *fastpm = s->solver;
+    FastPMStore *p = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    FastPMStore po[1];
+    double aout = p->meta.a_x;
+    fastpm_set_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+    FastPMSolver snapshot[1];
+    memcpy(snapshot, fastpm, sizeof(FastPMSolver));
+    fastpm_solver_add_species(snapshot, FASTPM_SPECIES_CDM, po);
+    write_snapshot_header(snapshot, filebase, MPI_COMM_WORLD);
+    fastpm_store_write(po, filebase, "w", 0, MPI_COMM_WORLD);
+    fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+}
+
+/* the unit-converted, wrapped particles that ref_write_snapshot hands to fastpm_store_write */
+void ref_snapshot_particles(RefSession *s, double *x, float *v)
+{
+    FastPMSolver *fastpm = s->solver;
+    FastPMStore *p = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    FastPMStore po[1];
+    double aout = p->meta.a_x;
+    fastpm_set_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+    memcpy(x, po->x, sizeof(po->x[0]) * po->np);
+    memcpy(v, po->v, sizeof(po->v[0]) * po->np);
+    fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+}
+
+/* reads the particle columns of a snapshot back into the session's store (fastpm_store_read, io.c:590-597) and returns the
+ * ScalingFactor of the header (read_snapshot_header, io.c:163-226) */
+double ref_read_snapshot(RefSession *s, const char *filebase, int restart)
+{
+    FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
+    double aout = 0;
+    read_snapshot_header(s->solver, filebase, &aout, MPI_COMM_WORLD);
+    if (!restart) {                       /* the columns as they are in the file (v in km/s) */
+        p->np = 0;
+        fastpm_store_read(p, filebase, 0, MPI_COMM_WORLD);
+        return aout;
+    }
+    /* prepare_cdm with a restart path, src/fastpm.c:618-635: back to the integrator's units */
+    FastPMStore po[1];
+    fastpm_set_species_snapshot(s->solver, p, NULL, NULL, po, 1.0);
+    fastpm_store_read(po, filebase, 0, MPI_COMM_WORLD);
+    fastpm_unset_species_snapshot(s->solver, p, NULL, NULL, po, po->meta.a_x);
+    return aout;
+}
+
+/* write_complex (io.c:641-719) needs the distributed sort of depends/mpsort, not built here: the oracle writes the c8 block the same
+ * way through the bigfile library, in the [x][y][N/2+1] order that sort produces */
+void ref_write_complex(RefSession *s, int which, double a, const float *dk_in, const char *filename, const char *blockname)
+{
+    PM *pm = pick_pm(s, which, a);
+    int Nmesh = pm_nmesh(pm)[0];
+    double BoxSize = pm_boxsize(pm)[0];
+    int64_t strides[3] = { (int64_t) Nmesh * (Nmesh / 2 + 1), Nmesh / 2 + 1, 1 };
+    int64_t shape[3] = { Nmesh, Nmesh, Nmesh / 2 + 1 };
+    size_t size = (size_t) Nmesh * Nmesh * (Nmesh / 2 + 1);
+    float *buf = malloc(sizeof(float) * 2 * size);
+    PMKIter kiter;
+    for (pm_kiter_init(pm, &kiter); !pm_kiter_stop(&kiter); pm_kiter_next(&kiter)) {
+        size_t iabs = kiter.iabs[0] * strides[0] + kiter.iabs[1] * strides[1] + kiter.iabs[2] * strides[2];
+        buf[2 * iabs] = dk_in[kiter.ind]; buf[2 * iabs + 1] = dk_in[kiter.ind + 1];
+    }
+    BigFile bf; BigBlock bb; BigArray array; BigBlockPtr ptr;
+    fastpm_path_ensure_dirname(filename);
+    if (0 != big_file_mpi_create(&bf, filename, MPI_COMM_WORLD)) { fprintf(stderr, "%s\n", big_file_get_error_message()); abort(); }
+    if (0 != big_file_mpi_create_block(&bf, &bb, blockname, "c8", 1, 1, size, MPI_COMM_WORLD)) { fprintf(stderr, "%s\n", big_file_get_error_message()); abort(); }
+    big_array_init(&array, buf, "c8", 1, (size_t[]) { size, 1 }, NULL);
+    big_block_seek(&bb, &ptr, 0);
+    big_block_mpi_write(&bb, &ptr, &array, 1, MPI_COMM_WORLD);
+    big_block_set_attr(&bb, "ndarray.ndim", (int[]) { 3, }, "i4", 1);
+    big_block_set_attr(&bb, "ndarray.strides", strides, "i8", 3);
+    big_block_set_attr(&bb, "ndarray.shape", shape, "i8", 3);
+    big_block_set_attr(&bb, "Nmesh", &Nmesh, "i4", 1);
+    big_block_set_attr(&bb, "BoxSize", &BoxSize, "f8", 1);
+    big_block_mpi_close(&bb, MPI_COMM_WORLD);
+    big_file_mpi_close(&bf, MPI_COMM_WORLD);
+    free(buf);
 }
 
 void ref_decic(RefSession *s, int which, double a, const float *in, float *out)

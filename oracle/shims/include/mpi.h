@@ -37,6 +37,8 @@ typedef ptrdiff_t MPI_Aint;
 #define MPI_DOUBLE    0x708
 #define MPI_DOUBLE_INT 0x810   /* struct {double; int;} padded to 16 */
 #define MPI_UNSIGNED_LONG 0x908
+#define MPI_UNSIGNED  0xa04
+#define MPI_DATATYPE_NULL 0
 #define MPI_SHIM_DERIVED_BASE 0x10000
 
 enum { MPI_SUM = 1, MPI_MIN, MPI_MAX, MPI_LAND, MPI_LOR, MPI_MINLOC, MPI_MAXLOC };
@@ -48,6 +50,13 @@ int MPI_Comm_size(MPI_Comm comm, int *size);
 int MPI_Comm_free(MPI_Comm *comm);
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *out);
 int MPI_Cart_sub(MPI_Comm comm, const int remain_dims[], MPI_Comm *newcomm);
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *newcomm);
+int MPI_Reduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype t, MPI_Op op, int root, MPI_Comm comm);
+int MPI_Gather(const void *sendbuf, int sendcount, MPI_Datatype st, void *recvbuf, int recvcount, MPI_Datatype rt, int root, MPI_Comm comm);
+int MPI_Gatherv(const void *sendbuf, int sendcount, MPI_Datatype st, void *recvbuf, const int *recvcounts, const int *displs,
+                MPI_Datatype rt, int root, MPI_Comm comm);
+int MPI_Scatterv(const void *sendbuf, const int *sendcounts, const int *displs, MPI_Datatype st, void *recvbuf, int recvcount,
+                 MPI_Datatype rt, int root, MPI_Comm comm);
 int MPI_Barrier(MPI_Comm comm);
 int MPI_Bcast(void *buf, int count, MPI_Datatype t, int root, MPI_Comm comm);
 int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype t, MPI_Op op, MPI_Comm comm);

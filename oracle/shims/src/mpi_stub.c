@@ -23,6 +23,33 @@ int MPI_Comm_free(MPI_Comm *comm) { *comm = MPI_COMM_NULL; return 0; }
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *out) { *out = comm; return 0; }
 int MPI_Cart_sub(MPI_Comm comm, const int remain_dims[], MPI_Comm *newcomm)
 { (void) remain_dims; *newcomm = comm; return 0; }
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *newcomm) { (void) color; (void) key; *newcomm = comm; return 0; }
+int MPI_Reduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype t, MPI_Op op, int root, MPI_Comm comm)
+{
+    (void) op; (void) root; (void) comm;
+    if (sendbuf != MPI_IN_PLACE) memcpy(recvbuf, sendbuf, count * type_size(t));
+    return 0;
+}
+int MPI_Gather(const void *sendbuf, int sendcount, MPI_Datatype st, void *recvbuf, int recvcount, MPI_Datatype rt, int root, MPI_Comm comm)
+{
+    (void) recvcount; (void) rt; (void) root; (void) comm;
+    if (sendbuf != MPI_IN_PLACE) memcpy(recvbuf, sendbuf, sendcount * type_size(st));
+    return 0;
+}
+int MPI_Gatherv(const void *sendbuf, int sendcount, MPI_Datatype st, void *recvbuf, const int *recvcounts, const int *displs,
+                MPI_Datatype rt, int root, MPI_Comm comm)
+{
+    (void) recvcounts; (void) root; (void) comm;
+    if (sendbuf != MPI_IN_PLACE) memcpy((char *) recvbuf + displs[0] * type_size(rt), sendbuf, sendcount * type_size(st));
+    return 0;
+}
+int MPI_Scatterv(const void *sendbuf, const int *sendcounts, const int *displs, MPI_Datatype st, void *recvbuf, int recvcount,
+                 MPI_Datatype rt, int root, MPI_Comm comm)
+{
+    (void) recvcount; (void) rt; (void) root; (void) comm;
+    if (recvbuf != MPI_IN_PLACE) memcpy(recvbuf, (const char *) sendbuf + displs[0] * type_size(st), sendcounts[0] * type_size(st));
+    return 0;
+}
 int MPI_Barrier(MPI_Comm comm) { (void) comm; return 0; }
 int MPI_Bcast(void *buf, int count, MPI_Datatype t, int root, MPI_Comm comm)
 { (void) buf; (void) count; (void) t; (void) root; (void) comm; return 0; }

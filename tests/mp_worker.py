@@ -13,6 +13,68 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def snapshot_two_writers(lib, allreduce, allgather, rank, world):
+    """Row N2: every rank writes its slice of a catalog and its slab of a k-space mesh (csrc/host/io.c); the result is the
+    directory the compiled reference writes from one rank, byte for byte (needs oracle/_ref; skipped without it)."""
+    import filecmp
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from oracle import ref
+    if not ref.available():
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_cpu_snapshot_io import IoColumn, IoMeta, _files
+    box = [tempfile.mkdtemp(prefix="fpm_mp_io_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tmp = box[0]
+    nc, L = 8, 32.0
+    if rank == 0:
+        s = ref.Session(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+        dk, _, _ = s.ic_deltak(7, open(os.path.join(ROOT, "tests", "golden", "powerspec.txt")).read())
+        s.setup_lpt(dk, 0.1)
+        s.write_snapshot(os.path.join(tmp, "ref"))
+        s.write_complex(dk, os.path.join(tmp, "ref_dk"), "LinearDensityK", which=1)
+        x, v = s.snapshot_particles()
+        p = s.get_particles()
+        M0 = p["meta"][2]
+        pack = [x, v, p["id"], np.ascontiguousarray(np.transpose(s.complex_view(dk, which=1), (1, 0, 2))), float(M0)]
+        s.close()
+    else:
+        pack = None
+    box = [pack]
+    dist.broadcast_object_list(box, src=0)
+    x, v, ids, rows_all, M0 = box[0]
+    lib.fastpm_b200_comm_init_host.argtypes = [C.c_int, C.c_int, type(allreduce), type(allgather), C.c_void_p]
+    lib.fastpm_b200_comm_init_host(rank, world, allreduce, allgather, None)
+    n = len(x)
+    lo, hi = rank * n // world + (3 if rank else 0), (rank + 1) * n // world + (3 if rank + 1 < world else 0)      # uneven slices
+    xs, vs, js = np.ascontiguousarray(x[lo:hi]), np.ascontiguousarray(v[lo:hi]), np.ascontiguousarray(ids[lo:hi])
+    cols = (IoColumn * 3)(IoColumn(b"Position", b"f4", b"f8", 3, xs.ctypes.data, 0), IoColumn(b"Velocity", b"f4", b"f4", 3, vs.ctypes.data, 0),
+                          IoColumn(b"ID", b"i8", b"i8", 1, js.ctypes.data, 0))
+    m = IoMeta((C.c_int64 * 3)(nc * nc, nc, 1), (C.c_double * 3)(L / nc, L / nc, L / nc), (C.c_double * 3)(0, 0, 0), nc ** 3, 0.1, 0.1, M0)
+    mine = os.path.join(tmp, "mine")
+    lib.fastpm_b200_io_write_columns.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int]
+    assert lib.fastpm_b200_io_write_columns(mine.encode(), b"1", cols, 3, hi - lo, C.byref(m), 1) == 0
+    hc = nc // 2 + 1
+    pitch_c = ((hc + 15) // 16) * 16
+    nyl, y0 = nc // world, rank * (nc // world)
+    rows = np.zeros((nyl, nc, pitch_c), dtype=np.complex64)
+    rows[:, :, :hc] = rows_all[y0:y0 + nyl]
+    lib.fastpm_b200_io_write_complex_rows.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    assert lib.fastpm_b200_io_write_complex_rows(os.path.join(tmp, "mine_dk").encode(), b"LinearDensityK", nc, L, y0, nyl, rows.ctypes.data, pitch_c, 1, 1) == 0
+    dist.barrier()
+    if rank == 0:
+        for mine_d, ref_d, skip in ((mine, os.path.join(tmp, "ref"), "Header"), (os.path.join(tmp, "mine_dk"), os.path.join(tmp, "ref_dk"), None)):
+            want = [f for f in _files(ref_d) if not (skip and f.startswith(skip))]
+            assert _files(mine_d) == want, (_files(mine_d), want)
+            for f in want:
+                assert filecmp.cmp(os.path.join(mine_d, f), os.path.join(ref_d, f), shallow=False), f
+        shutil.rmtree(tmp, ignore_errors=True)
+    lib.fastpm_b200_comm_init_host(0, 1, allreduce, allgather, None)
+
+
 def main():
     mode = sys.argv[1]
     import torch
@@ -37,6 +99,8 @@ def main():
         t = torch.tensor([mine])
         dist.all_reduce(t)
         assert int(t.item()) == len(xs)
+        dist.barrier()
+        snapshot_two_writers(lib, a, g, rank, world)
         dist.barrier()
         if rank == 0:
             print("MP_CPU_OK")

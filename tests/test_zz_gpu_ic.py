@@ -139,3 +139,66 @@ def test_pgd_correction_matches_reference(ref_mod, pk_text):
     assert pdist(x, want["x"]) < 1e-4                    # Mpc/h, BASELINE.json north_star
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
     assert np.abs(pg - want_pgdc).max() < 1e-4 * np.abs(want_pgdc).max()
+
+
+def _read_block(top, name, dtype, nmemb):
+    import os
+    a = np.fromfile(os.path.join(top, "1", name, "000000"), dtype=dtype)
+    return a.reshape(-1, nmemb) if nmemb > 1 else a
+
+
+def test_snapshot_files_and_restart_match_reference(ref_mod, pk_text, tmp_path):
+    """Row N2 of SURVEY.md section 8f from the device: fastpm_b200_write_snapshot (unit conversion, header, catalog) against the
+    directory the reference writes for its own run, the reference reading ours, and a restart from the reference's snapshot on
+    both sides (src/fastpm.c:618-635)."""
+    import filecmp
+    import os
+    from fastpm_b200.solver import Solver
+    nc, L, B = 16, 32.0, 2
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+    first, second = np.linspace(0.1, 0.5, 3), np.linspace(0.5, 1.0, 3)
+    s = ref_mod.Session(**kw)
+    dk, _, _ = s.ic_deltak(7, pk_text)
+    s.setup_lpt(dk, first[0])
+    s.evolve(first)
+    ref_dir, mine = str(tmp_path / "ref_0.5000"), str(tmp_path / "mine_0.5000")
+    s.write_snapshot(ref_dir)
+    s.close()
+    g = Solver(**kw)
+    g.setup_lpt(dk, first[0])
+    g.evolve(first)
+    v_before = g.get_column("v")
+    g.write_snapshot(mine)
+    assert np.array_equal(g.get_column("v"), v_before) or np.abs(g.get_column("v") - v_before).max() < 1e-6 * np.abs(v_before).max()
+    g.close()
+    # same files; headers and attributes identical (the growth numbers of "Header" to 2e-7, see tests/test_cpu_snapshot_io.py)
+    files = sorted(os.path.relpath(os.path.join(d, f), mine) for d, _, fs in os.walk(mine) for f in fs)
+    assert files == sorted(os.path.relpath(os.path.join(d, f), ref_dir) for d, _, fs in os.walk(ref_dir) for f in fs)
+    assert filecmp.cmp(os.path.join(mine, "1", "attr-v2"), os.path.join(ref_dir, "1", "attr-v2"), shallow=False)
+    assert filecmp.cmp(os.path.join(mine, "1", "ID", "000000"), os.path.join(ref_dir, "1", "ID", "000000"), shallow=False)
+    xa, xb = _read_block(mine, "Position", np.float32, 3), _read_block(ref_dir, "Position", np.float32, 3)
+    d = np.abs(xa.astype(np.float64) - xb)
+    assert np.minimum(d, L - d).max() < 1e-4
+    va, vb = _read_block(mine, "Velocity", np.float32, 3), _read_block(ref_dir, "Velocity", np.float32, 3)
+    assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max()
+    # the reference reads our directory
+    s = ref_mod.Session(**kw)
+    assert s.read_snapshot(mine) == 0.5
+    q = s.get_particles()
+    assert np.array_equal(q["x"].astype(np.float32), xa) and np.array_equal(q["v"], va)
+    s.close()
+    # restart from the reference's snapshot on both sides
+    s = ref_mod.Session(**kw)
+    assert s.read_snapshot(ref_dir, restart=True) == 0.5
+    s.evolve(second)
+    want = s.get_particles()
+    s.close()
+    g = Solver(**kw)
+    assert g.read_snapshot(ref_dir) == 0.5
+    assert g.meta["a_x"] == 0.5 and g.meta["a_v"] == 0.5
+    g.evolve(second)
+    x, v = g.get_column("x"), g.get_column("v")
+    g.close()
+    d = np.abs(np.mod(x, L) - np.mod(want["x"], L))
+    assert np.minimum(d, L - d).max() < 1e-4
+    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
