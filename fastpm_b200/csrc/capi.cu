@@ -50,6 +50,8 @@ int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, in
 int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, double *host_out, cudaStream_t st);
 int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st);
 int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st);
+int fpm_radial_transfer_launch(const FpmMesh *m, const float *from, float *to, int mode, double param, cudaStream_t st);
+int fpm_axis_factors_launch(const FpmMesh *m, const double *d_table, const float *from, float *to, cudaStream_t st);
 int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, double alpha, double kl, double ks, cudaStream_t st);
 int fpm_pgd_shift_launch(double *x, const float *pgdc, double dyyy, double dyyy_last, long long np, cudaStream_t st);
 int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st);
@@ -478,6 +480,24 @@ int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, doub
     LAZY1(from); LAZY1(to);
     if (!(ks > 0)) { fpm_set_error("pgd transfer: ks must be positive"); return -1; }
     return fpm_pgd_transfer_launch(m, from, to, alpha, kl, ks, g_stream);
+}
+int fpm_apply_radial(const fpm_mesh *m, const float *from, float *to, int mode, double param)
+{
+    LAZY1(from); LAZY1(to);
+    if (mode != 0 && mode != 1) { fpm_set_error("radial transfer: mode %d", mode); return -1; }
+    return fpm_radial_transfer_launch(m, from, to, mode, param, g_stream);
+}
+int fpm_apply_axis_factors(const fpm_mesh *m, const float *from, float *to, const double *factors_host)
+{
+    LAZY1(from); LAZY1(to);
+    const size_t bytes = sizeof(double) * (size_t) m->geom.n;
+    double *d = NULL;
+    FPM_CUDA_OK(cudaMallocAsync(&d, bytes, g_stream));
+    FPM_CUDA_OK(cudaMemcpyAsync(d, factors_host, bytes, cudaMemcpyHostToDevice, g_stream));
+    FPM_CUDA_OK(cudaStreamSynchronize(g_stream));          // factors_host may be a stack array of the caller
+    const int rc = fpm_axis_factors_launch(m, d, from, to, g_stream);
+    FPM_CUDA_OK(cudaFreeAsync(d, g_stream));
+    return rc;
 }
 int fpm_scale(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_scale_launch(from, to, nfloats, value, g_stream); }
 int fpm_divide(const float *from, float *to, size_t nfloats, double value) { if (fpm_lazy_touch(from, 4 * nfloats) || fpm_lazy_touch(to, 4 * nfloats)) return -1; return fpm_divide_launch(from, to, nfloats, value, g_stream); }

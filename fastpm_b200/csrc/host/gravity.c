@@ -9,6 +9,7 @@
  * The particle ghosts of pmghosts.c are replaced by one mesh plane (support 2 needs planes [x0, x0+nxl]).
  */
 #include "internal.h"
+#include <math.h>
 
 void fastpm_kernel_type_get_orders(FastPMKernelType type, int *potorder, int *gradorder, int *difforder, int *deconvolveorder)
 {
@@ -35,6 +36,35 @@ void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *d
 
 size_t fastpm_b200_arena_size(void);             /* host/support.c */
 size_t fastpm_b200_arena_largest_free(void);
+
+/* gravity.c:66-102: exp(-(k_d r0)^2 / 2) per axis with r0 = N cells, tabulated in double from the float k table */
+static void apply_gaussian_softening(PM *pm, FastPMFloat *from, FastPMFloat *to, double N)
+{
+    const int n = (int) pm->Nmesh[0];
+    const double r0 = N * pm->BoxSize[0] / pm->Nmesh[0];
+    float *tab = malloc(sizeof(float) * 5 * n);
+    double *f = malloc(sizeof(double) * n);
+    FPM_MUST(fpm_mesh_ktables_host(pm->mesh, tab));
+    for (int i = 0; i < n; i++) f[i] = exp(-0.5 * pow(tab[i] * r0, 2));
+    /* the reference multiplies `to` (gravity.c:93-94); its only caller passes from == to */
+    FPM_MUST(fpm_apply_axis_factors(pm->mesh, to, to, f));
+    (void) from;
+    free(f); free(tab);
+}
+
+/* gravity.c:244-270 */
+static void apply_softening_transfer(FastPMSofteningType type, PM *pm, FastPMFloat *from, FastPMFloat *to)
+{
+    const double k_nq = M_PI / pm->BoxSize[0] * pm->Nmesh[0];
+    switch (type) {
+        case FASTPM_SOFTENING_TWO_THIRD: fastpm_apply_lowpass_transfer(pm, from, to, 2.0 / 3 * k_nq); break;
+        case FASTPM_SOFTENING_GAUSSIAN: apply_gaussian_softening(pm, from, to, 1.0); break;
+        case FASTPM_SOFTENING_GADGET_LONG_RANGE: apply_gaussian_softening(pm, from, to, pow(2, 0.5) * 1.25); break;
+        case FASTPM_SOFTENING_GAUSSIAN36: FPM_MUST(fpm_apply_radial(pm->mesh, from, to, 1, k_nq)); break;
+        case FASTPM_SOFTENING_NONE: break;
+        default: fastpm_raise(-1, "wrong softening kernel type");
+    }
+}
 
 /* opt-in; only when CDM is the only species and two more meshes fit beside what is allocated now */
 static int fused_readout_wanted(FastPMSolver *fastpm, PM *pm)
@@ -66,7 +96,6 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
 {
     (void) Time;
     fpm_store_flush(NULL);
-    if (dealias != FASTPM_SOFTENING_NONE) fastpm_raise(-1, "fastpm_b200: force softening type %d is not implemented (default is none)\n", (int) dealias);
     if (fastpm->cosmology->ncdm_linearresponse) fastpm_raise(-1, "fastpm_b200: ncdm linear response is out of scope\n");
     CLOCK(paint);
     LEAVE(paint);
@@ -106,6 +135,9 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     const double scale = (1.0 / mean_mass_per_cell) * (1.0 / pm->Norm);
     fpm_mesh_r2c(pm, canvas, delta_k, scale);
     LEAVE(r2c);
+
+    /* ---- dealiasing of the source, in place: gravity.c:476 (the FORCE/after event sees the softened field, like the reference's) */
+    if (dealias != FASTPM_SOFTENING_NONE) apply_softening_transfer(dealias, pm, delta_k, delta_k);
 
     /* ---- force components: gravity.c:359-396 */
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);

@@ -128,6 +128,20 @@ void fastpm_apply_laplace_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, i
  * `from`; only in-place calls (all its callers) actually end with zeros there.  This build always zeroes. */
 void fastpm_apply_diff_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, int dir, int order) { simple_transfer(pm, from, to, -1, 1, dir, order); }
 void fastpm_apply_decic_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to) { FPM_MUST(fpm_apply_decic(pm->mesh, from, to)); }
+/* transfer.c:8-41: exp(-k_d^2 sml^2 / 2) per axis, tabulated in double on the host from the float k^2 table like the reference's */
+void fastpm_apply_smoothing_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double sml)
+{
+    const int n = (int) pm->Nmesh[0];
+    float *tab = malloc(sizeof(float) * 5 * n);
+    double *f = malloc(sizeof(double) * n);
+    FPM_MUST(fpm_mesh_ktables_host(pm->mesh, tab));
+    for (int i = 0; i < n; i++) { double kk = tab[n + i]; f[i] = exp(-0.5 * kk * sml * sml); }
+    FPM_MUST(fpm_apply_axis_factors(pm->mesh, from, to, f));
+    free(f); free(tab);
+}
+/* transfer.c:43-66 */
+void fastpm_apply_lowpass_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double kth)
+{ FPM_MUST(fpm_apply_radial(pm->mesh, from, to, 0, kth * kth)); }
 void fastpm_apply_multiply_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double value)
 { FPM_MUST(fpm_scale(from, to, pm->allocsize, value)); }
 

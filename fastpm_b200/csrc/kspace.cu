@@ -65,6 +65,33 @@ __global__ void __launch_bounds__(256) pgd_transfer_kernel(const FpmGeom g, cons
     }
 }
 
+// Radial force softening (gravity.c:244-270): mode 0 = sharp low pass, factor 1 where kk < param (= kth^2) else 0
+// (fastpm_apply_lowpass_transfer, transfer.c:43-66); mode 1 = exp(-36 (k / k_nyquist)^36), param = k_nyquist (gaussian36,
+// gravity.c:104-109 through fastpm_apply_any_transfer, transfer.c:189-211).  kk summed in double from the float tables.
+__global__ void __launch_bounds__(256) radial_transfer_kernel(const FpmGeom g, const FpmKTables kt, const int mode, const double param,
+        const float2 *__restrict__ from, float2 *__restrict__ to, size_t total)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        double kk = 0;
+        kk += (double) kt.kk[m.ix]; kk += (double) kt.kk[m.iy]; kk += (double) kt.kk[m.iz];
+        double smth;
+        if (mode == 0) {
+            smth = kk < param ? 1 : 0;
+        } else {
+            const double x = sqrt(kk) / param;
+            smth = exp(-36 * pow(x, 36.0));
+        }
+        float2 v = from[m.off];
+        v.x = (float) ((double) v.x * smth);
+        v.y = (float) ((double) v.y * smth);
+        to[m.off] = v;
+    }
+}
+
 // transfer.c:78-113: kernel[d][i] = 1/sinc^2(k h/2) in double (table prepared on the host), product in
 // double, one rounding to float per component.
 __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const double *__restrict__ dtab,
@@ -362,6 +389,23 @@ int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, doub
     const size_t total = cplx_total(m->geom);
     const double kl2 = kl * kl, ks4 = ks * ks * ks * ks;              // pgdcorrection.c:35-36
     FPM_TIMED(FPM_K_KSPACE, st, (pgd_transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, alpha, kl2, ks4, (const float2 *) from, (float2 *) to, total)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_radial_transfer_launch(const FpmMesh *m, const float *from, float *to, int mode, double param, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    FPM_TIMED(FPM_K_KSPACE, st, (radial_transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, mode, param, (const float2 *) from, (float2 *) to, total)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// the product of one double factor per axis (same kernel as the CIC deconvolution): Gaussian softening and smoothing
+int fpm_axis_factors_launch(const FpmMesh *m, const double *d_table, const float *from, float *to, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    FPM_TIMED(FPM_K_KSPACE, st, (decic_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, d_table, (const float2 *) from, (float2 *) to, total)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -133,6 +133,11 @@ int fpm_decic_defer(const fpm_mesh *m, float *cplx);
 int fpm_decic_cancel(const float *cplx);
 /* PGD potential, apply_pgdpot_transfer pgdcorrection.c:28-59: to = alpha exp(-kl^2/k^2 - k^4/ks^4) / k^2 * from */
 int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, double alpha, double kl, double ks);
+/* force softening, gravity.c:244-270.  Radial: mode 0 = low pass, 1 where k^2 < param else 0 (fastpm_apply_lowpass_transfer,
+ * transfer.c:43); mode 1 = exp(-36 (k/param)^36) (gaussian36, gravity.c:104).  Separable: to = from * f[ix] * f[iy] * f[iz] with
+ * a host table of n doubles (apply_gaussian_softening gravity.c:66-102, fastpm_apply_smoothing_transfer transfer.c:8-41) */
+int fpm_apply_radial(const fpm_mesh *m, const float *from, float *to, int mode, double param);
+int fpm_apply_axis_factors(const fpm_mesh *m, const float *from, float *to, const double *factors_host);
 int fpm_scale(const float *from, float *to, size_t nfloats, double value); /* transfer.c:213 */
 int fpm_divide(const float *from, float *to, size_t nfloats, double value); /* solver.c:738-742 */
 int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, int sign); /* pm2lpt.c:103,118 */

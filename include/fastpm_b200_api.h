@@ -336,6 +336,8 @@ double ComovingDistance(double a, FastPMCosmology *c);
 void fastpm_apply_decic_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to);
 void fastpm_apply_diff_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, int dir, int order);
 void fastpm_apply_multiply_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double value);
+void fastpm_apply_smoothing_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double sml);    /* transfer.h, transfer.c:8 */
+void fastpm_apply_lowpass_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, double kth);       /* transfer.c:43 */
 void fastpm_apply_laplace_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, int order);
 void fastpm_apply_modify_mode_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, ptrdiff_t *mode, double value);
 
@@ -558,11 +560,12 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                      int growth_mode, int compute_potential, double nLPT,
                                      double Omega_m, double h, double T_cmb, double N_eff, int N_nu);
-/* same, with the PGD correction of src/fastpm.c:204-217: pgdc = NULL (off) or {alpha0, A, B, kl, ks} (adds COLUMN_PGDC) */
+/* same, with the PGD correction of src/fastpm.c:204-217: pgdc = NULL (off) or {alpha0, A, B, kl, ks} (adds COLUMN_PGDC), and the
+ * force softening (FastPMSofteningType, gravity.c:244-270) */
 FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                         double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                         int growth_mode, int compute_potential, double nLPT,
-                                        double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc);
+                                        double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type);
 void fastpm_b200_solver_free(FastPMSolver *solver);
 
 #ifdef __cplusplus

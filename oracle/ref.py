@@ -17,6 +17,9 @@ KERNELS = {"3_4": 0, "3_2": 1, "5_4": 2, "1_4": 3, "1_4_diff0": 4, "gadget": 5, 
 GROWTH_MODES = {"LCDM": 0, "ODE": 1}                                           # api/fastpm/cosmology.h:6-9
 
 
+SOFTENINGS = dict(none=0, gaussian=1, gadget_long_range=2, two_third=3, gaussian36=4)     # FastPMSofteningType, libfastpm.h:52-54
+
+
 class RefConfig(C.Structure):
     _fields_ = [
         ("nc", C.c_int64), ("boxsize", C.c_double), ("pm_nc_factor", C.c_double * 8),
@@ -27,7 +30,7 @@ class RefConfig(C.Structure):
         ("Omega_m", C.c_double), ("h", C.c_double), ("T_cmb", C.c_double), ("Omega_k", C.c_double),
         ("w0", C.c_double), ("wa", C.c_double), ("N_eff", C.c_double),
         ("N_nu", C.c_int), ("enforce_broadband_kmax", C.c_int),
-        ("pgdc", C.c_double * 6),
+        ("pgdc", C.c_double * 6), ("softening_type", C.c_int),
     ]
 
 
@@ -59,7 +62,7 @@ class Session:
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4",
                  growth_mode="ODE", np_alloc_factor=4.0, lpt_nc_factor=1, compute_potential=False,
                  Omega_m=0.307494, h=0.6774, T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5,
-                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None):
+                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None, softening="none"):
         """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (src/fastpm.c:204-217)."""
         cfg = RefConfig()
         cfg.nc = nc
@@ -81,6 +84,7 @@ class Session:
         cfg.Omega_m, cfg.h, cfg.T_cmb, cfg.Omega_k = Omega_m, h, T_cmb, 0.0
         cfg.w0, cfg.wa, cfg.N_eff, cfg.N_nu = -1.0, 0.0, N_eff, N_nu
         cfg.enforce_broadband_kmax = enforce_broadband_kmax
+        cfg.softening_type = SOFTENINGS[softening]
         cfg.pgdc = (C.c_double * 6)(*([0.0] * 6 if pgdc is None else [1.0] + [float(v) for v in pgdc]))
         self.cfg = cfg
         self.nc, self.boxsize, self.force_mode = nc, boxsize, force_mode

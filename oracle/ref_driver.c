@@ -41,6 +41,7 @@ typedef struct {
     int N_nu;
     int enforce_broadband_kmax;
     double pgdc[6];              /* {enabled, alpha0, A, B, kl, ks}: the PGD correction of src/fastpm.c:204-217 */
+    int softening_type;          /* FastPMSofteningType (gravity.c:244-270); 0 = none */
 } RefConfig;
 
 #define MAX_FORCE_RECORDS 256
@@ -147,7 +148,7 @@ RefSession *ref_session_new(const RefConfig *cfg)
     config->USE_SHIFT = 0;
     config->FORCE_TYPE = cfg->force_mode;
     config->KERNEL_TYPE = cfg->kernel_type;
-    config->SOFTENING_TYPE = FASTPM_SOFTENING_NONE;
+    config->SOFTENING_TYPE = (FastPMSofteningType) cfg->softening_type;
     config->PAINTER_TYPE = FASTPM_PAINTER_CIC;
     config->painter_support = 2;
     config->NprocY = 0; config->UseFFTW = 0;

@@ -294,3 +294,37 @@ def test_pgd_transfer_kernel_against_reference(kspace_emul, ref_mod, tmp_path):
         got = s.readout(s.c2r(s.complex_pack(got_k)), x)
         assert np.array_equal(got, want[:, d]), d
     s.close()
+
+
+@pytest.mark.parametrize("softening", ["gaussian", "gadget_long_range", "two_third", "gaussian36"])
+def test_softening_kernels_against_reference(kspace_emul, one_thread_ref, pk_text, tmp_path, softening):
+    """apply_softening_transfer (gravity.c:244-270) on delta_k inside fastpm_solver_compute_force: the reference's softened
+    delta_k against our sweep of its unsoftened one, bit for bit.  The two Gaussian kinds are the per-axis factor kernel (the
+    same one as the CIC deconvolution) with the table csrc/host/gravity.c builds; the other two the radial kernel."""
+    nc, L, B = 8, 40.0, 2
+    nmesh = nc * B
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+    out = {}
+    for kind in ("none", softening):
+        s = one_thread_ref.Session(softening=kind, **kw)                  # one thread: the same deposit order in both runs
+        dk, _, _ = s.ic_deltak(3, pk_text)
+        s.setup_lpt(dk, 0.5)
+        out[kind] = s.complex_view(s.compute_force(0.5, want_delta_k=True), a=0.5).copy()
+        s.close()
+    assert not np.array_equal(out["none"], out[softening])
+    tab, dec = _tables(nmesh, L)
+    k_nq = np.pi / L * nmesh
+    if softening in ("gaussian", "gadget_long_range"):
+        N = 1.0 if softening == "gaussian" else 2 ** 0.5 * 1.25
+        r0 = N * L / nmesh
+        import ctypes
+        libm = ctypes.CDLL("libm.so.6")                                   # the C library's exp, as host/gravity.c and the reference use
+        libm.exp.restype, libm.exp.argtypes = ctypes.c_double, [ctypes.c_double]
+        f = np.array([libm.exp(-0.5 * (float(k) * r0) ** 2) for k in tab[0]])          # exp(-0.5 * pow(k * r0, 2)), gravity.c:82
+        head = struct.pack("<id", nmesh, L) + tab.tobytes() + f.tobytes() + _to_device_layout(out["none"], nmesh).tobytes()
+        got = _from_device_layout(kspace_emul("decic", head, str(tmp_path)), nmesh)
+    else:
+        mode, param = (0, (2.0 / 3 * k_nq) ** 2) if softening == "two_third" else (1, k_nq)
+        head = struct.pack("<id", nmesh, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(out["none"], nmesh).tobytes()
+        got = _from_device_layout(kspace_emul("radial", head + struct.pack("<id", mode, param), str(tmp_path)), nmesh)
+    assert np.array_equal(got.view(np.float32), out[softening].view(np.float32))
