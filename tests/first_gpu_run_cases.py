@@ -1,6 +1,14 @@
-"""GPU parity of the device initial-condition generator (row N1 of SURVEY.md section 8f): fpm_fill_gaussian_gadget against the
-reference's fastpm_ic_fill_gaussiank.  The per-column arithmetic is the same source the CPU test runs bit for bit against the
-oracle; on the device only the last bit of double sin / cos / log may differ."""
+"""GPU parity cases written after this round's GPU budget was spent: NOT YET RUN ON A B200.  They are ordinary pytest tests, but
+the file name keeps them out of the default collection; tests/test_zz_first_gpu_run.py runs each one in its own pytest process
+(an abort inside the library then fails that case only) and reports it as xfail / xpass until it has been seen green once.
+
+  * device initial-condition generator (row N1 of SURVEY.md section 8f): fpm_fill_gaussian_gadget against the reference's
+    fastpm_ic_fill_gaussiank; the per-column arithmetic is the same source the CPU test runs bit for bit against the oracle, on
+    the device only the last bit of double sin / cos / log may differ
+  * the plain-C libfastpm user program of tests/abi/dropin_example.c
+  * the opt-in one-pass readout of the three force components
+  * PGD correction (N3), snapshot files + restart from the device (N2), force softening (N4)
+"""
 import numpy as np
 import pytest
 

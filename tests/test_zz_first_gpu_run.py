@@ -1,0 +1,37 @@
+"""Runs the GPU cases of tests/first_gpu_run_cases.py -- written after this round's GPU budget was spent, never yet executed on a
+B200 -- one pytest process per case.  Until a case has been seen green on hardware it is reported as xfail (it failed) or
+xpass (it passed): the validated suite stays readable either way, and the round-end log says which of these need work."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = [
+    "test_device_gadget_ic_matches_reference",
+    "test_libfastpm_user_program_runs_and_matches_fixture",
+    "test_three_component_readout_equals_three_readouts",
+    "test_fused_readout_option_gives_the_same_run",
+    "test_pgd_correction_matches_reference",
+    "test_snapshot_files_and_restart_match_reference",
+    "test_force_softening_matches_reference",
+]
+
+
+def test_case_list_is_complete():
+    """every test of first_gpu_run_cases.py is listed above (CPU check)"""
+    import re
+    src = open(os.path.join(ROOT, "tests", "first_gpu_run_cases.py")).read()
+    assert sorted(re.findall(r"^def (test_\w+)\(", src, flags=re.M)) == sorted(CASES)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first B200 run pending: written after this round's GPU budget was spent")
+@pytest.mark.parametrize("case", CASES)
+def test_first_gpu_run(case):
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(ROOT, "tests", "first_gpu_run_cases.py") + "::" + case],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:]
