@@ -51,6 +51,7 @@ int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, doub
 int fpm_transfer_launch(const FpmMesh *m, const float *from, float *to, const FpmTransferSpec *s, cudaStream_t st);
 int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_t st);
 int fpm_radial_transfer_launch(const FpmMesh *m, const float *from, float *to, int mode, double param, cudaStream_t st);
+int fpm_remove_variance_launch(const FpmMesh *m, float *dk, cudaStream_t st);
 int fpm_axis_factors_launch(const FpmMesh *m, const double *d_table, const float *from, float *to, cudaStream_t st);
 int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, double alpha, double kl, double ks, cudaStream_t st);
 int fpm_pgd_shift_launch(double *x, const float *pgdc, double dyyy, double dyyy_last, long long np, cudaStream_t st);
@@ -481,6 +482,7 @@ int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, doub
     if (!(ks > 0)) { fpm_set_error("pgd transfer: ks must be positive"); return -1; }
     return fpm_pgd_transfer_launch(m, from, to, alpha, kl, ks, g_stream);
 }
+int fpm_remove_variance(const fpm_mesh *m, float *cplx) { LAZY1(cplx); return fpm_remove_variance_launch(m, cplx, g_stream); }
 int fpm_apply_radial(const fpm_mesh *m, const float *from, float *to, int mode, double param)
 {
     LAZY1(from); LAZY1(to);

@@ -174,6 +174,8 @@ void fastpm_ic_fill_gaussiank(PM *pm, FastPMFloat *delta_k, int seed, enum FastP
     FPM_MUST(fpm_fill_gaussian_gadget(pm->mesh, delta_k, seed));
 }
 
+void fastpm_ic_remove_variance(PM *pm, FastPMFloat *delta_k) { FPM_MUST(fpm_remove_variance(pm->mesh, delta_k)); }   /* initialcondition.c:66-99 */
+
 void fastpm_ic_induce_correlation(PM *pm, FastPMFloat *delta_k, fastpm_fkfunc pkfunc, void *data)
 {
     /* initialcondition.c:56-64 multiplies by sqrt(P(k)/V) through a host callback per mode.  A host callback

@@ -65,6 +65,27 @@ __global__ void __launch_bounds__(256) pgd_transfer_kernel(const FpmGeom g, cons
     }
 }
 
+// fastpm_ic_remove_variance, initialcondition.c:66-99: every mode keeps its phase and gets unit amplitude,
+// (cos, sin)(atan2(im, re)) in double; (0, 0) stays (0, 0).
+__global__ void __launch_bounds__(256) remove_variance_kernel(const FpmGeom g, float2 *__restrict__ dk, size_t total)
+{
+    size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        ModeIdx m = mode_from_linear(g, t);
+        if (!m.valid) continue;
+        const float2 v = dk[m.off];
+        const double a = v.x, b = v.y;
+        float2 o = make_float2(0.f, 0.f);
+        if (!(a == 0 && b == 0)) {
+            const double phase = atan2(b, a);
+            o.x = (float) cos(phase);
+            o.y = (float) sin(phase);
+        }
+        dk[m.off] = o;
+    }
+}
+
 // Radial force softening (gravity.c:244-270): mode 0 = sharp low pass, factor 1 where kk < param (= kth^2) else 0
 // (fastpm_apply_lowpass_transfer, transfer.c:43-66); mode 1 = exp(-36 (k / k_nyquist)^36), param = k_nyquist (gaussian36,
 // gravity.c:104-109 through fastpm_apply_any_transfer, transfer.c:189-211).  kk summed in double from the float tables.
@@ -389,6 +410,14 @@ int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, doub
     const size_t total = cplx_total(m->geom);
     const double kl2 = kl * kl, ks4 = ks * ks * ks * ks;              // pgdcorrection.c:35-36
     FPM_TIMED(FPM_K_KSPACE, st, (pgd_transfer_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, m->ktab, alpha, kl2, ks4, (const float2 *) from, (float2 *) to, total)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_remove_variance_launch(const FpmMesh *m, float *dk, cudaStream_t st)
+{
+    const size_t total = cplx_total(m->geom);
+    FPM_TIMED(FPM_K_KSPACE, st, (remove_variance_kernel<<<sweep_grid(total), 256, 0, st>>>(m->geom, (float2 *) dk, total)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -144,6 +144,8 @@ int fpm_muladd(float *source, const float *a, const float *b, size_t nfloats, in
 int fpm_set_mode(const fpm_mesh *m, float *cplx, int ix, int iy, int iz, float re, float im); /* transfer.c:306 */
 /* delta_k *= sqrt(P(k)/V), P log-log interpolated from the table: initialcondition.c:56-64 */
 int fpm_induce_correlation(const fpm_mesh *m, float *cplx, const double *k_host, const double *p_host, int size);
+/* unit amplitude, phase kept: fastpm_ic_remove_variance, initialcondition.c:66-99 */
+int fpm_remove_variance(const fpm_mesh *m, float *cplx);
 /* Gaussian white noise in k-space with the Gadget / N-GenIC seeding scheme and RANLUX (gsl_rng_ranlxd1), the reference's
  * default generator: pmic_fill_gaussian_gadget, initialcondition.c:145-273 (fastpm_ic_fill_gaussiank, FASTPM_DELTAK_GADGET).
  * Same seed -> same field as the reference, up to the last bit of the device's double sin / cos / log. */

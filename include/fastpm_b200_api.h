@@ -365,6 +365,7 @@ enum FastPMFillDeltaKScheme { FASTPM_DELTAK_GADGET, FASTPM_DELTAK_FAST, FASTPM_D
 /* only the default scheme, FASTPM_DELTAK_GADGET, is implemented (on the device); the others raise */
 void fastpm_ic_fill_gaussiank(PM *pm, FastPMFloat *delta_k, int seed, enum FastPMFillDeltaKScheme scheme);
 void fastpm_ic_induce_correlation(PM *pm, FastPMFloat *delta_k, fastpm_fkfunc pk, void *pkdata);
+void fastpm_ic_remove_variance(PM *pm, FastPMFloat *delta_k);                                /* initialcondition.h, initialcondition.c:66 */
 
 /* ------------------------------------------------------------------ [pgdcorrection.h:3-11] */
 typedef struct { FastPMPainterType PainterType; int PainterSupport; double alpha0, A, B, kl, ks; } FastPMPGDCorrection;

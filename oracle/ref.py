@@ -198,6 +198,12 @@ class Session:
     def set_pgdc(self, pgdc):
         lib().ref_set_pgdc(self._h, _p(np.ascontiguousarray(pgdc, dtype=np.float32)))
 
+    def remove_variance(self, dk):
+        dk = np.ascontiguousarray(dk, dtype=np.float32)
+        out = np.zeros_like(dk)
+        lib().ref_remove_variance(self._h, _p(dk), _p(out))
+        return out
+
     def write_snapshot(self, filebase):
         """write_snapshot_header + fastpm_store_write of the unit-converted CDM store (bigfile directory `filebase`)."""
         lib().ref_write_snapshot(self._h, C.c_char_p(str(filebase).encode()))

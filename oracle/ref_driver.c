@@ -248,6 +248,17 @@ void ref_fill_gaussian(RefSession *s, int seed, float *delta_k_out)
     pm_free(pm, delta_k);
 }
 
+/* fastpm_ic_remove_variance (initialcondition.c:66-99) on the LPT mesh */
+void ref_remove_variance(RefSession *s, const float *in, float *out)
+{
+    PM *pm = s->solver->lptpm;
+    FastPMFloat *dk = pm_alloc(pm);
+    memcpy(dk, in, sizeof(FastPMFloat) * pm->allocsize);
+    fastpm_ic_remove_variance(pm, dk);
+    memcpy(out, dk, sizeof(FastPMFloat) * pm->allocsize);
+    pm_free(pm, dk);
+}
+
 void ref_setup_lpt(RefSession *s, const float *delta_k_in, double a0)
 {
     PM *pm = s->solver->lptpm;

@@ -9,6 +9,7 @@
 //   decic                                                                               -> complex64 out
 //   pgd:      float64 alpha, kl, ks; int32 dir                                          -> complex64 out
 //   radial:   int32 mode; float64 param                                                 -> complex64 out
+//   unitamp                                                                             -> complex64 out
 //   pk:       int32 decic                                                               -> float64 sums[3*(n/2) + 1]
 #include "cuda_emul.h"
 #include <cstdio>
@@ -57,6 +58,11 @@ int main(int argc, char **argv)
         memset(&s, 0, sizeof(s));
         s.active = 1; s.potorder = -1; s.ngrad = 1; s.graddir[0] = dir; s.gradorder = 1; s.zero_selfconj = 1; s.scale = 1.0;
         fpm_emul_launch(3, 256, 0, [&]() { transfer_kernel(g, kt, s, pot.data(), res.data(), total); });
+        fwrite(res.data(), sizeof(float2), total, out);
+    } else if (op == "unitamp") {
+        // fastpm_ic_remove_variance: in place
+        res = dk;
+        fpm_emul_launch(3, 256, 0, [&]() { remove_variance_kernel(g, res.data(), total); });
         fwrite(res.data(), sizeof(float2), total, out);
     } else if (op == "radial") {
         // int32 mode, float64 param: the radial softening sweeps (low pass, gaussian36)

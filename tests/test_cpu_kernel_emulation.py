@@ -328,3 +328,23 @@ def test_softening_kernels_against_reference(kspace_emul, one_thread_ref, pk_tex
         head = struct.pack("<id", nmesh, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(out["none"], nmesh).tobytes()
         got = _from_device_layout(kspace_emul("radial", head + struct.pack("<id", mode, param), str(tmp_path)), nmesh)
     assert np.array_equal(got.view(np.float32), out[softening].view(np.float32))
+
+
+def test_remove_variance_kernel_against_reference(kspace_emul, ref_mod, tmp_path):
+    """fastpm_ic_remove_variance (initialcondition.c:66-99): unit amplitude, phase kept; zero modes stay zero."""
+    n, L = 16, 100.0
+    s = ref_mod.Session(nc=n, boxsize=L, pm_nc_factor=1)
+    dk = s.fill_gaussian(31)
+    c = s.complex_view(dk, which=1).copy()
+    c[3, 5, 2] = 0
+    dk = s.complex_pack(c, which=1)
+    want = s.complex_view(s.remove_variance(dk), which=1)
+    s.close()
+    tab, dec = _tables(n, L)
+    head = struct.pack("<id", n, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(c, n).tobytes()
+    got = _from_device_layout(kspace_emul("unitamp", head, str(tmp_path)), n)
+    assert got[3, 5, 2] == 0
+    assert np.array_equal(got.view(np.float32), want.view(np.float32))
+    assert (c != 0).sum() > 2000
+    np.testing.assert_allclose(np.abs(got[c != 0]), 1.0, rtol=2e-7)
+    assert np.all(got[c == 0] == 0)
