@@ -548,3 +548,19 @@ void fastpm_b200_setup_synthetic_ic(FastPMSolver *fastpm, uint64_t seed, const d
     fastpm_solver_setup_lpt(fastpm, FASTPM_SPECIES_CDM, delta_k, NULL, a0);
     pm_free(pm, delta_k);
 }
+
+/* The reference's own initial conditions, src/fastpm.c:415-545 for the seed + P(k)-table path (what oracle/ref_driver.c:ref_ic_deltak
+ * restates): Gadget-scheme RANLUX white noise, optional fastpm_ic_remove_variance, colouring by the tabulated linear P(k), DC
+ * mode = 1, then 2LPT at a0.  Same seed -> same particles as the reference (up to the last bit of the device's libm). */
+void fastpm_b200_setup_gadget_ic(FastPMSolver *fastpm, int seed, int remove_variance, const double *k, const double *p, int size, double a0)
+{
+    PM *pm = fastpm->lptpm;
+    FastPMFloat *delta_k = pm_alloc_noclear(pm, __FILE__, __LINE__);
+    fastpm_ic_fill_gaussiank(pm, delta_k, seed, FASTPM_DELTAK_GADGET);
+    if (remove_variance) fastpm_ic_remove_variance(pm, delta_k);
+    FPM_MUST(fpm_induce_correlation(pm->mesh, delta_k, k, p, size));
+    ptrdiff_t mode[4] = { 0, 0, 0, 0 };
+    fastpm_apply_modify_mode_transfer(pm, delta_k, delta_k, mode, 1.0);
+    fastpm_solver_setup_lpt(fastpm, FASTPM_SPECIES_CDM, delta_k, NULL, a0);
+    pm_free(pm, delta_k);
+}

@@ -188,6 +188,13 @@ class Solver:
         p = np.ascontiguousarray(p, dtype=np.float64)
         self.lib.fastpm_b200_setup_synthetic_ic(self.h, int(seed), k.ctypes.data, p.ctypes.data, len(k), float(a0))
 
+    def setup_ic(self, seed, k, p, a0, remove_variance=False):
+        """The reference's initial conditions for this seed (Gadget-scheme RANLUX noise, table P(k), 2LPT at a0), on the device."""
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        self.lib.fastpm_b200_setup_gadget_ic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        self.lib.fastpm_b200_setup_gadget_ic(self.h, int(seed), int(remove_variance), k.ctypes.data, p.ctypes.data, len(k), float(a0))
+
     def setup_lpt_device(self, delta_k_dev_ptr, a0):
         self.lib.fastpm_solver_setup_lpt(self.h, 1, delta_k_dev_ptr, None, float(a0))
 

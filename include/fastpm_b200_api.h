@@ -568,6 +568,9 @@ FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double
                                         int growth_mode, int compute_potential, double nLPT,
                                         double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type);
 void fastpm_b200_solver_free(FastPMSolver *solver);
+/* initial conditions as src/fastpm.c:415-545 makes them from a seed and a linear P(k) table (k, p: `size` doubles each), all on the
+ * device: Gadget-scheme white noise, optional remove_variance, colouring, DC mode = 1, 2LPT at a0 */
+void fastpm_b200_setup_gadget_ic(FastPMSolver *fastpm, int seed, int remove_variance, const double *k, const double *p, int size, double a0);
 
 #ifdef __cplusplus
 }

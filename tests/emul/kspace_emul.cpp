@@ -10,6 +10,7 @@
 //   pgd:      float64 alpha, kl, ks; int32 dir                                          -> complex64 out
 //   radial:   int32 mode; float64 param                                                 -> complex64 out
 //   unitamp                                                                             -> complex64 out
+//   induce:   int32 size; float64 k[size], p[size]                                      -> complex64 out
 //   pk:       int32 decic                                                               -> float64 sums[3*(n/2) + 1]
 #include "cuda_emul.h"
 #include <cstdio>
@@ -58,6 +59,13 @@ int main(int argc, char **argv)
         memset(&s, 0, sizeof(s));
         s.active = 1; s.potorder = -1; s.ngrad = 1; s.graddir[0] = dir; s.gradorder = 1; s.zero_selfconj = 1; s.scale = 1.0;
         fpm_emul_launch(3, 256, 0, [&]() { transfer_kernel(g, kt, s, pot.data(), res.data(), total); });
+        fwrite(res.data(), sizeof(float2), total, out);
+    } else if (op == "induce") {
+        // int32 size, float64 k[size], p[size]: fastpm_ic_induce_correlation with the tabulated P(k), in place
+        const int size = one<int32_t>(in);
+        std::vector<double> tk = many<double>(in, size), tp = many<double>(in, size);
+        res = dk;
+        fpm_emul_launch(3, 256, 0, [&]() { induce_kernel(g, kt, res.data(), total, tk.data(), tp.data(), size, L * L * L); });
         fwrite(res.data(), sizeof(float2), total, out);
     } else if (op == "unitamp") {
         // fastpm_ic_remove_variance: in place

@@ -243,3 +243,29 @@ def test_force_softening_matches_reference(ref_mod, pk_text, softening):
     assert pdist(want["x"], plain["x"]) > 1e-3           # the sweep matters
     assert pdist(x, want["x"]) < 1e-4
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+
+
+@pytest.mark.parametrize("remove_variance", [False, True])
+def test_device_ic_chain_matches_reference(ref_mod, pk_text, remove_variance):
+    """Row N1 end to end: fastpm_b200_setup_gadget_ic (white noise, [remove_variance], colouring, 2LPT: all on the device) gives the
+    particles the reference makes from the same seed and P(k) table (src/fastpm.c:415-545 + fastpm_solver_setup_lpt)."""
+    import os
+    from fastpm_b200.solver import Solver
+    nc, L = 32, 128.0
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
+    s = ref_mod.Session(**kw)
+    dk, _, _ = s.ic_deltak(2024, pk_text, remove_variance=remove_variance)
+    s.setup_lpt(dk, 0.1)
+    want = s.get_particles()
+    s.close()
+    tab = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "powerspec.txt"))
+    g = Solver(**kw)
+    g.setup_ic(2024, tab[:, 0], tab[:, 1], 0.1, remove_variance=remove_variance)
+    x, v, dx1, dx2 = g.get_column("x"), g.get_column("v"), g.get_column("dx1"), g.get_column("dx2")
+    assert np.array_equal(g.get_column("id"), want["id"])
+    g.close()
+    d = np.abs(x - want["x"])
+    assert np.minimum(d, L - d).max() < 1e-5
+    assert np.abs(v - want["v"]).max() < 1e-5 * max(1.0, np.abs(want["v"]).max())
+    assert np.abs(dx1 - want["dx1"]).max() < 1e-5 * np.abs(want["dx1"]).max()
+    assert np.abs(dx2 - want["dx2"]).max() < 1e-4 * np.abs(want["dx2"]).max()

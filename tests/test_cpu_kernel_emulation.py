@@ -348,3 +348,25 @@ def test_remove_variance_kernel_against_reference(kspace_emul, ref_mod, tmp_path
     assert (c != 0).sum() > 2000
     np.testing.assert_allclose(np.abs(got[c != 0]), 1.0, rtol=2e-7)
     assert np.all(got[c == 0] == 0)
+
+
+@pytest.mark.parametrize("remove_variance", [False, True])
+def test_initial_condition_chain_against_reference(kspace_emul, ref_mod, pk_text, tmp_path, remove_variance):
+    """prepare_deltak (src/fastpm.c:415-545) = Gadget white noise -> [remove_variance] -> induce_correlation with the P(k) table:
+    the last two as kernel sources on the reference's white noise, against the reference's delta_k (the noise itself:
+    tests/test_cpu_oracle_and_host.py).  fastpm_b200_setup_gadget_ic chains exactly these on the device."""
+    n, L = 16, 200.0
+    s = ref_mod.Session(nc=n, boxsize=L, pm_nc_factor=1)
+    white = s.complex_view(s.fill_gaussian(77), which=1).copy()
+    want = s.complex_view(s.ic_deltak(77, pk_text, remove_variance=remove_variance)[0], which=1).copy()
+    s.close()
+    tab, dec = _tables(n, L)
+    base = struct.pack("<id", n, L) + tab.tobytes() + dec.tobytes()
+    cur = white
+    if remove_variance:
+        cur = _from_device_layout(kspace_emul("unitamp", base + _to_device_layout(cur, n).tobytes(), str(tmp_path)), n)
+    pk = np.loadtxt(os.path.join(ROOT, "tests", "golden", "powerspec.txt"))
+    payload = struct.pack("<i", len(pk)) + np.ascontiguousarray(pk[:, 0]).tobytes() + np.ascontiguousarray(pk[:, 1]).tobytes()
+    got = _from_device_layout(kspace_emul("induce", base + _to_device_layout(cur, n).tobytes() + payload, str(tmp_path)), n).copy()
+    got[0, 0, 0] = 1.0                                   # fastpm_apply_modify_mode_transfer, src/fastpm.c:541-544
+    assert np.array_equal(got.view(np.float32), want.view(np.float32))
