@@ -41,6 +41,8 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
 int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, const float *c2, const double *x, float *out, long long np, cudaStream_t st);
+int fpm_window_paint_launch(const FpmMesh *m, int type, int support, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
+int fpm_window_readout_launch(const FpmMesh *m, int type, int support, const float *canvas, const double *x, float *out, int out_stride, long long np, cudaStream_t st);
 int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st);
 int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
@@ -408,6 +410,19 @@ int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, 
 {
     LAZY1(canvas0); LAZY1(canvas1); LAZY1(canvas2);
     return fpm_readout3_launch(m, canvas0, canvas1, canvas2, x, out3, np, g_stream);
+}
+
+int fpm_paint_window(const fpm_mesh *m, int window, int support, float *canvas, const double *x, int64_t np, double M0, const float *mass,
+                     const float *field, int field_stride)
+{
+    LAZY1(canvas);
+    return fpm_window_paint_launch(m, window, support, canvas, x, mass, M0, field, field_stride, np, g_stream);
+}
+
+int fpm_readout_window(const fpm_mesh *m, int window, int support, const float *canvas, const double *x, int64_t np, float *out, int out_stride)
+{
+    LAZY1(canvas);
+    return fpm_window_readout_launch(m, window, support, canvas, x, out, out_stride, np, g_stream);
 }
 
 // ------------------------------------------------------------------ FFT

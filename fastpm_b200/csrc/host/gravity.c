@@ -143,7 +143,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
     const int nacc = (cdm && cdm->potential) ? 4 : 3;
     int d0 = 0;
-    if (fused_readout_wanted(fastpm, pm)) {
+    if (painter->kernel == NULL /* CIC */ && fused_readout_wanted(fastpm, pm)) {
         /* FASTPM_B200_FUSED_READOUT=1: the three inverse transforms into three meshes, then ONE pass over the particles
          * (positions read once instead of three times, ACC written as whole elements). Same values bit for bit. */
         FastPMFloat *cv[3] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__), pm_alloc_noclear(pm, __FILE__, __LINE__) };

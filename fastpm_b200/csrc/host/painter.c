@@ -2,6 +2,7 @@
  * Only the CIC window (the default, lua-runtime-fastpm.lua:132-138, and the one BASELINE.json names) runs
  * on the device; the struct keeps the reference's public layout. */
 #include "internal.h"
+#include "../window.h"
 
 static void no_host_paint(FastPMPainter *painter, FastPMFloat *canvas, double pos[3], double weight, int diffdir)
 { (void) painter; (void) canvas; (void) pos; (void) weight; (void) diffdir;
@@ -10,17 +11,43 @@ static double no_host_readout(FastPMPainter *painter, FastPMFloat *canvas, doubl
 { (void) painter; (void) canvas; (void) pos; (void) diffdir;
   fastpm_raise(-1, "painter->readout on a single particle: the canvas is device memory; use fastpm_readout_local\n"); return 0; }
 
+/* the windows as host functions too (painter->kernel is public, painter.h:27); their addresses tell the painters apart */
+static double linear_kernel(double x, double invh) { return fpm_window_linear(x, invh); }
+static double quad_kernel(double x, double invh) { return fpm_window_quad(x, invh); }
+static double lanczos_kernel(double x, double invh) { return fpm_window_lanczos(x, invh); }
+
+static int window_of(const FastPMPainter *painter)
+{
+    if (painter->kernel == NULL) return FPM_WINDOW_CIC;
+    if (painter->kernel == linear_kernel) return FPM_WINDOW_LINEAR;
+    if (painter->kernel == quad_kernel) return FPM_WINDOW_QUAD;
+    if (painter->kernel == lanczos_kernel) return FPM_WINDOW_LANCZOS;
+    fastpm_raise(-1, "fastpm_b200: custom painter kernels cannot run on the device\n");
+    return -1;
+}
+
 void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type, int support)
 {
-    if (type != FASTPM_PAINTER_CIC) fastpm_raise(-1, "fastpm_b200: only the CIC painter is implemented (painter type %d requested)\n", (int) type);
-    (void) support;
+    /* painter.c:128-174 */
     painter->pm = pm;
     painter->paint = no_host_paint; painter->readout = no_host_readout;
     painter->kernel = NULL; painter->diff = NULL;
+    switch (type) {
+        case FASTPM_PAINTER_CIC: support = 2; break;
+        case FASTPM_PAINTER_LINEAR: painter->kernel = linear_kernel; support = 2; break;
+        case FASTPM_PAINTER_QUAD: painter->kernel = quad_kernel; support = 3; break;
+        case FASTPM_PAINTER_LANCZOS: painter->kernel = lanczos_kernel; break;
+        default: fastpm_raise(-1, "fastpm_b200: painter type %d\n", (int) type);
+    }
+    if (type != FASTPM_PAINTER_CIC && pm->NTask > 1)
+        fastpm_raise(-1, "fastpm_b200: the linear / quadratic / Lanczos painters run on one GPU only (their x-halo is wider than the one mesh plane exchanged)\n");
+    if (support < 1 || support > FPM_WINDOW_MAX_SUPPORT) fastpm_raise(-1, "fastpm_b200: painter support %d (1..%d on the device)\n", support, FPM_WINDOW_MAX_SUPPORT);
     painter->diffdir = -1;
-    painter->support = 2;                       /* painter.c:134-137: CIC forces support = 2 */
-    painter->hsupport = 1.0; painter->invh = 1.0;
-    painter->left = 0; painter->Npoints = 8; painter->shift = 0;
+    painter->support = support;
+    painter->hsupport = 0.5 * support; painter->invh = 1 / (0.5 * support);
+    painter->left = (support - 1) / 2;
+    painter->Npoints = support * support * support;
+    painter->shift = support % 2 == 0 ? 0 : 0.5;
 }
 
 void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
@@ -32,6 +59,12 @@ void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore
         if (ci < 0 || !p->columns[ci] || p->_column_info[ci].membsize != 4) fastpm_raise(-1, "paint: field column must be an allocated float column\n");
         fcol = (const float *) p->columns[ci] + field.memb;
         fstride = (int) p->_column_info[ci].nmemb;
+    }
+    const int window = window_of(painter);
+    if (window != FPM_WINDOW_CIC) {
+        if (fpm_pending_wrap == p) { fpm_pending_wrap = NULL; fastpm_store_wrap(p, painter->pm->BoxSize); }
+        FPM_MUST(fpm_paint_window(painter->pm->mesh, window, painter->support, canvas, (const double *) p->x, (int64_t) size, p->meta.M0, p->mass, fcol, fstride));
+        return;
     }
     if (fpm_pending_wrap == p && size == p->np) {
         fpm_pending_wrap = NULL;
@@ -48,6 +81,11 @@ void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMSto
     int ci = fastpm_store_find_column_id(p, field.attribute);
     if (ci < 0 || !p->columns[ci] || p->_column_info[ci].from_double == NULL) fastpm_raise(-1, "readout: target column is not an allocated float column\n");
     float *out = (float *) p->columns[ci] + field.memb;
+    const int window = window_of(painter);
+    if (window != FPM_WINDOW_CIC) {
+        FPM_MUST(fpm_readout_window(painter->pm->mesh, window, painter->support, canvas, (const double *) p->x, (int64_t) size, out, (int) p->_column_info[ci].nmemb));
+        return;
+    }
     FPM_MUST(fpm_readout(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) size, out, (int) p->_column_info[ci].nmemb, 1.0));
 }
 

@@ -406,13 +406,14 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      double Omega_m_, double h, double T_cmb, double N_eff, int N_nu)
 {
     return fastpm_b200_solver_new_ex(nc, boxsize, pm_nc_factor_pairs, npairs, alloc_factor, lpt_nc_factor, force_mode, kernel_type,
-                                     growth_mode, compute_potential, nLPT, Omega_m_, h, T_cmb, N_eff, N_nu, NULL, FASTPM_SOFTENING_NONE);
+                                     growth_mode, compute_potential, nLPT, Omega_m_, h, T_cmb, N_eff, N_nu, NULL, FASTPM_SOFTENING_NONE, FASTPM_PAINTER_CIC, 2);
 }
 
 FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                         double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                         int growth_mode, int compute_potential, double nLPT,
-                                        double Omega_m_, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type)
+                                        double Omega_m_, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type,
+                                        int painter_type, int painter_support)
 {
     libfastpm_init();
     SolverBox *b = calloc(1, sizeof(*b));
@@ -430,7 +431,7 @@ FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double
         cfg->pgdc = 1; cfg->pgdc_alpha0 = pgdc[0]; cfg->pgdc_A = pgdc[1]; cfg->pgdc_B = pgdc[2]; cfg->pgdc_kl = pgdc[3]; cfg->pgdc_ks = pgdc[4];
         cfg->ExtraAttributes |= COLUMN_PGDC;
     }
-    cfg->nLPT = nLPT; cfg->PAINTER_TYPE = FASTPM_PAINTER_CIC; cfg->painter_support = 2;
+    cfg->nLPT = nLPT; cfg->PAINTER_TYPE = (FastPMPainterType) painter_type; cfg->painter_support = painter_type == FASTPM_PAINTER_CIC ? 2 : painter_support;
     cfg->FORCE_TYPE = force_mode; cfg->KERNEL_TYPE = kernel_type; cfg->SOFTENING_TYPE = (FastPMSofteningType) softening_type;
     fastpm_solver_init(&b->solver, cfg, MPI_COMM_WORLD);
     return &b->solver;

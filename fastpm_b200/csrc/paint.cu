@@ -15,6 +15,7 @@
 // plane may be the halo plane nxl, which is exchanged with the next rank (single GPU: periodic wrap).
 #include "common.cuh"
 #include "mesh.cuh"
+#include "window.h"
 #include <stdlib.h>
 
 // Traversal order.  A store filled by fastpm_store_fill (store.c:756-793) holds particle (i, j, k) of the nc^3 Lagrangian grid
@@ -206,6 +207,89 @@ __global__ void __launch_bounds__(256) cic_readout3_kernel(const FpmGeom g, cons
     }
 }
 
+// ------------------------------------------------------------------ the generic windows (painter.c:176-317): linear, quadratic, Lanczos
+// One particle per thread, support^3 mesh points.  _fill_k: per axis the window at the `support` points starting at
+// floor(x/h + shift) - left, normalised to sum 1; the deposit / gather then runs x-outermost, z-innermost with the weight
+// ((1 * kx) * ky) * kz, all in double like the reference.  One GPU only (the x-halo of these windows is wider than one plane).
+struct WindowSpec { int type, support, left; double shift, invh; };
+
+__device__ __forceinline__ void window_fill(const FpmGeom &g, const WindowSpec &w, const double pos[3], int ipos[3], double k[3][FPM_WINDOW_MAX_SUPPORT])
+{
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double gpos = pos[d] * g.inv_cellsize;
+        ipos[d] = (int) floor(gpos + w.shift) - w.left;
+        const double dx = gpos - ipos[d];
+        double sum = 0;
+        for (int i = 0; i < w.support; i++) {
+            k[d][i] = fpm_window_eval(w.type, dx - i, w.invh);
+            sum += k[d][i];
+        }
+        for (int i = 0; i < w.support; i++) k[d][i] /= sum;
+    }
+}
+
+__device__ __forceinline__ int window_wrap(int t, int n)
+{
+    while (t >= n) t -= n;
+    while (t < 0) t += n;
+    return t;
+}
+
+__global__ void __launch_bounds__(128) window_paint_kernel(const FpmGeom g, const WindowSpec w, float *__restrict__ canvas,
+        const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field, int field_stride, long long np)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    int ipos[3];
+    double k[3][FPM_WINDOW_MAX_SUPPORT];
+    window_fill(g, w, pos, ipos, k);
+    double weight = mass ? M0 + (double) mass[i] : M0;
+    if (field) weight *= (double) field[i * field_stride];
+    const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    for (int a = 0; a < w.support; a++) {
+        const int ix = window_wrap(ipos[0] + a, g.n);
+        for (int b = 0; b < w.support; b++) {
+            const int iy = window_wrap(ipos[1] + b, g.n);
+            float *row = canvas + (size_t) ix * pl + (size_t) iy * pr;
+            for (int c = 0; c < w.support; c++) {
+                const int iz = window_wrap(ipos[2] + c, g.n);
+                double kernel = 1.0;
+                kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
+                atomicAdd(row + iz, (float) (weight * kernel));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) window_readout_kernel(const FpmGeom g, const WindowSpec w, const float *__restrict__ canvas,
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, long long np)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    int ipos[3];
+    double k[3][FPM_WINDOW_MAX_SUPPORT];
+    window_fill(g, w, pos, ipos, k);
+    const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    double value = 0;
+    for (int a = 0; a < w.support; a++) {
+        const int ix = window_wrap(ipos[0] + a, g.n);
+        for (int b = 0; b < w.support; b++) {
+            const int iy = window_wrap(ipos[1] + b, g.n);
+            const float *row = canvas + (size_t) ix * pl + (size_t) iy * pr;
+            for (int c = 0; c < w.support; c++) {
+                const int iz = window_wrap(ipos[2] + c, g.n);
+                double kernel = 1.0;
+                kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
+                value += kernel * (double) __ldg(row + iz);
+            }
+        }
+    }
+    out[i * (long long) out_stride] = (float) value;
+}
+
 // adds the received halo plane into local plane 0 (multi-GPU paint epilogue)
 __global__ void plane_add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t nfloats)
 {
@@ -282,6 +366,41 @@ int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, cons
     int lag_nc = 0;
     const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
     FPM_TIMED(FPM_K_READOUT, st, (cic_readout3_kernel<<<grid, 256, 0, st>>>(m->geom, c0, c1, c2, x, out, np, lag_nc, nbrick)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+static int window_spec(const FpmMesh *m, int type, int support, WindowSpec *w)
+{
+    // fastpm_painter_init, painter.c:128-174
+    if (type == FPM_WINDOW_LINEAR) support = 2;
+    else if (type == FPM_WINDOW_QUAD) support = 3;
+    else if (type != FPM_WINDOW_LANCZOS) { fpm_set_error("window type %d", type); return -1; }
+    if (support < 1 || support > FPM_WINDOW_MAX_SUPPORT) { fpm_set_error("window support %d (1..%d on the device)", support, FPM_WINDOW_MAX_SUPPORT); return -1; }
+    if (m->geom.nranks > 1) { fpm_set_error("the linear / quadratic / Lanczos windows run on one GPU only"); return -1; }
+    w->type = type; w->support = support; w->left = (support - 1) / 2;
+    w->shift = support % 2 == 0 ? 0 : 0.5; w->invh = 1 / (0.5 * support);
+    return 0;
+}
+
+int fpm_window_paint_launch(const FpmMesh *m, int type, int support, float *canvas, const double *x, const float *mass, double M0,
+                            const float *field, int field_stride, long long np, cudaStream_t st)
+{
+    WindowSpec w;
+    if (window_spec(m, type, support, &w)) return -1;
+    if (np <= 0) return 0;
+    FPM_TIMED(FPM_K_PAINT, st, (window_paint_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, x, mass, M0, field, field_stride, np)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_window_readout_launch(const FpmMesh *m, int type, int support, const float *canvas, const double *x, float *out, int out_stride,
+                              long long np, cudaStream_t st)
+{
+    WindowSpec w;
+    if (window_spec(m, type, support, &w)) return -1;
+    if (np <= 0) return 0;
+    FPM_TIMED(FPM_K_READOUT, st, (window_readout_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, x, out, out_stride, np)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -16,6 +16,7 @@ COLUMNS = dict(mask=1 << 0, x=1 << 1, q=1 << 2, v=1 << 3, dx1=1 << 4, dx2=1 << 5
 _COL_DTYPE = dict(x=(np.float64, 3), v=(np.float32, 3), acc=(np.float32, 3), dx1=(np.float32, 3), dx2=(np.float32, 3),
                   id=(np.uint64, 1), potential=(np.float32, 1), pgdc=(np.float32, 3))
 
+WINDOWS = dict(cic=0, linear=1, quad=2, lanczos=3)                                        # FastPMPainterType, painter.h
 SOFTENINGS = dict(none=0, gaussian=1, gadget_long_range=2, two_third=3, gaussian36=4)     # FastPMSofteningType, libfastpm.h:52-54
 HANDLER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
@@ -49,7 +50,7 @@ def _bind(lib):
     lib.fastpm_b200_solver_new.restype = vp
     lib.fastpm_b200_solver_new.argtypes = [i64, dbl, vp, i32, dbl, dbl, i32, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, i32]
     lib.fastpm_b200_solver_new_ex.restype = vp
-    lib.fastpm_b200_solver_new_ex.argtypes = [i64, dbl, vp, i32, dbl, dbl, i32, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, i32, vp, i32]
+    lib.fastpm_b200_solver_new_ex.argtypes = [i64, dbl, vp, i32, dbl, dbl, i32, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, i32, vp, i32, i32, i32]
     lib.fastpm_b200_solver_free.argtypes = [vp]
     lib.fastpm_b200_solver_cdm.restype = vp
     lib.fastpm_b200_solver_cdm.argtypes = [vp]
@@ -98,9 +99,10 @@ class Solver:
 
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4", growth_mode="ODE",
                  np_alloc_factor=1.0, lpt_nc_factor=1, compute_potential=False, Omega_m=0.307494, h=0.6774,
-                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5, pgdc=None, softening="none"):
+                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5, pgdc=None, softening="none", painter="cic", painter_support=2):
         """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (pgdcorrection.c, src/fastpm.c:204-217);
-        softening: "none", "gaussian", "gadget_long_range", "two_third", "gaussian36" (gravity.c:244-270)."""
+        softening: "none", "gaussian", "gadget_long_range", "two_third", "gaussian36" (gravity.c:244-270);
+        painter: "cic", "linear", "quad", "lanczos" (+ painter_support for lanczos; painter.c:128-174; non-CIC: one GPU)."""
         self.lib = _bind(_lib.require_device())
         par = None if pgdc is None else np.array([float(v) for v in pgdc], dtype=np.float64)
         if par is not None and par.shape != (5,):
@@ -113,7 +115,8 @@ class Solver:
                                                     float(lpt_nc_factor), FORCE_MODES[force_mode], KERNELS[kernel_type],
                                                     GROWTH_MODES[growth_mode], int(compute_potential), float(nLPT),
                                                     float(Omega_m), float(h), float(T_cmb), float(N_eff), int(N_nu),
-                                                    None if par is None else par.ctypes.data, SOFTENINGS[softening])
+                                                    None if par is None else par.ctypes.data, SOFTENINGS[softening],
+                                                    WINDOWS[painter], int(painter_support))
         self.cdm = self.lib.fastpm_b200_solver_cdm(self.h)
         self.lptpm = self.lib.fastpm_b200_solver_lptpm(self.h)
 

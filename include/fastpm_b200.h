@@ -91,6 +91,12 @@ int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t
  * store, gravity.c:359-396), bit-identical to three separate calls; needs the three fields resident at the same time */
 int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3);
 
+/* the windows other than CIC, _generic_paint / _generic_readout painter.c:217-317: window = FastPMPainterType (1 linear, support 2;
+ * 2 quadratic, support 3; 3 Lanczos with the given support <= 8, including the reference's 1e-3 table quantisation); one GPU only */
+int fpm_paint_window(const fpm_mesh *m, int window, int support, float *canvas, const double *x, int64_t np, double M0, const float *mass,
+                     const float *field, int field_stride);
+int fpm_readout_window(const fpm_mesh *m, int window, int support, const float *canvas, const double *x, int64_t np, float *out, int out_stride);
+
 /* ---- K2 / K4 FFT: pm_r2c, pm_c2r, pmpfft.c:370-399 ------------------------------------------ */
 /* r2c: cplx = DFT(real) * scale.  `real` is destroyed (as with PFFT_DESTROY_INPUT, pmpfft.c:290).
  * The reference's 1/Norm (pmpfft.c:382-385) is passed as scale = 1/N^3 by the caller. */

@@ -562,11 +562,12 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      int growth_mode, int compute_potential, double nLPT,
                                      double Omega_m, double h, double T_cmb, double N_eff, int N_nu);
 /* same, with the PGD correction of src/fastpm.c:204-217: pgdc = NULL (off) or {alpha0, A, B, kl, ks} (adds COLUMN_PGDC), and the
- * force softening (FastPMSofteningType, gravity.c:244-270) */
+ * force softening (FastPMSofteningType, gravity.c:244-270) and the painter of the force step (FastPMPainterType + support) */
 FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                         double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                         int growth_mode, int compute_potential, double nLPT,
-                                        double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type);
+                                        double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type,
+                                        int painter_type, int painter_support);
 void fastpm_b200_solver_free(FastPMSolver *solver);
 /* initial conditions as src/fastpm.c:415-545 makes them from a seed and a linear P(k) table (k, p: `size` doubles each), all on the
  * device: Gadget-scheme white noise, optional remove_variance, colouring, DC mode = 1, 2LPT at a0 */

@@ -17,6 +17,7 @@ KERNELS = {"3_4": 0, "3_2": 1, "5_4": 2, "1_4": 3, "1_4_diff0": 4, "gadget": 5, 
 GROWTH_MODES = {"LCDM": 0, "ODE": 1}                                           # api/fastpm/cosmology.h:6-9
 
 
+WINDOWS = dict(cic=0, linear=1, quad=2, lanczos=3)                                        # FastPMPainterType, painter.h
 SOFTENINGS = dict(none=0, gaussian=1, gadget_long_range=2, two_third=3, gaussian36=4)     # FastPMSofteningType, libfastpm.h:52-54
 
 
@@ -30,7 +31,7 @@ class RefConfig(C.Structure):
         ("Omega_m", C.c_double), ("h", C.c_double), ("T_cmb", C.c_double), ("Omega_k", C.c_double),
         ("w0", C.c_double), ("wa", C.c_double), ("N_eff", C.c_double),
         ("N_nu", C.c_int), ("enforce_broadband_kmax", C.c_int),
-        ("pgdc", C.c_double * 6), ("softening_type", C.c_int),
+        ("pgdc", C.c_double * 6), ("softening_type", C.c_int), ("painter_type", C.c_int), ("painter_support", C.c_int),
     ]
 
 
@@ -62,7 +63,7 @@ class Session:
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4",
                  growth_mode="ODE", np_alloc_factor=4.0, lpt_nc_factor=1, compute_potential=False,
                  Omega_m=0.307494, h=0.6774, T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5,
-                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None, softening="none"):
+                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None, softening="none", painter="cic", painter_support=2):
         """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (src/fastpm.c:204-217)."""
         cfg = RefConfig()
         cfg.nc = nc
@@ -85,6 +86,7 @@ class Session:
         cfg.w0, cfg.wa, cfg.N_eff, cfg.N_nu = -1.0, 0.0, N_eff, N_nu
         cfg.enforce_broadband_kmax = enforce_broadband_kmax
         cfg.softening_type = SOFTENINGS[softening]
+        cfg.painter_type, cfg.painter_support = WINDOWS[painter], int(painter_support)
         cfg.pgdc = (C.c_double * 6)(*([0.0] * 6 if pgdc is None else [1.0] + [float(v) for v in pgdc]))
         self.cfg = cfg
         self.nc, self.boxsize, self.force_mode = nc, boxsize, force_mode
@@ -256,6 +258,20 @@ class Session:
         out = np.zeros(len(x), dtype=np.float32)
         lib().ref_readout(self._h, C.c_int(which), C.c_double(a), _p(np.ascontiguousarray(canvas, dtype=np.float32)),
                           _p(x), C.c_int64(len(x)), _p(out))
+        return out
+
+    def paint_window(self, x, window, support=0, which=0, a=1.0):
+        """window: "linear", "quad", "lanczos" (painter.c:128-174); support only matters for lanczos."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = self._buf(which, a)
+        lib().ref_paint_window(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support), _p(x), C.c_int64(len(x)), _p(out))
+        return out
+
+    def readout_window(self, canvas, x, window, support=0, which=0, a=1.0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(len(x), dtype=np.float32)
+        lib().ref_readout_window(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support),
+                                 _p(np.ascontiguousarray(canvas, dtype=np.float32)), _p(x), C.c_int64(len(x)), _p(out))
         return out
 
     def r2c(self, real_buf, which=0, a=1.0):

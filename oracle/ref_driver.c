@@ -42,6 +42,8 @@ typedef struct {
     int enforce_broadband_kmax;
     double pgdc[6];              /* {enabled, alpha0, A, B, kl, ks}: the PGD correction of src/fastpm.c:204-217 */
     int softening_type;          /* FastPMSofteningType (gravity.c:244-270); 0 = none */
+    int painter_type;            /* FastPMPainterType of the force step (config->PAINTER_TYPE); 0 = CIC */
+    int painter_support;
 } RefConfig;
 
 #define MAX_FORCE_RECORDS 256
@@ -149,8 +151,8 @@ RefSession *ref_session_new(const RefConfig *cfg)
     config->FORCE_TYPE = cfg->force_mode;
     config->KERNEL_TYPE = cfg->kernel_type;
     config->SOFTENING_TYPE = (FastPMSofteningType) cfg->softening_type;
-    config->PAINTER_TYPE = FASTPM_PAINTER_CIC;
-    config->painter_support = 2;
+    config->PAINTER_TYPE = (FastPMPainterType) cfg->painter_type;
+    config->painter_support = cfg->painter_type == 0 ? 2 : cfg->painter_support;
     config->NprocY = 0; config->UseFFTW = 0;
     config->ExtraAttributes = 0;
     if (cfg->compute_potential) config->ExtraAttributes |= COLUMN_POTENTIAL;
@@ -385,6 +387,38 @@ void ref_readout(RefSession *s, int which, double a, const float *canvas_in, con
     PM *pm = pick_pm(s, which, a);
     FastPMPainter painter[1];
     fastpm_painter_init(painter, pm, FASTPM_PAINTER_CIC, 2);
+    FastPMStore p[1];
+    tmp_store(p, x, np);
+    FastPMFloat *canvas = pm_alloc(pm);
+    memcpy(canvas, canvas_in, sizeof(FastPMFloat) * pm->allocsize);
+    FastPMFieldDescr f = { COLUMN_ACC, 0 };
+    fastpm_readout_local(painter, canvas, p, p->np, f);
+    for (int64_t i = 0; i < np; i++) out[i] = p->acc[i][0];
+    pm_free(pm, canvas);
+    fastpm_store_destroy(p);
+}
+
+/* the same two with the generic windows (fastpm_painter_init, painter.c:128-174): type = FastPMPainterType */
+void ref_paint_window(RefSession *s, int which, double a, int type, int support, const double *x, int64_t np, float *canvas_out)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMPainter painter[1];
+    fastpm_painter_init(painter, pm, (FastPMPainterType) type, support);
+    FastPMStore p[1];
+    tmp_store(p, x, np);
+    FastPMFloat *canvas = pm_alloc(pm);
+    FastPMFieldDescr none = { 0, 0 };
+    fastpm_paint_local(painter, canvas, p, p->np, none);
+    memcpy(canvas_out, canvas, sizeof(FastPMFloat) * pm->allocsize);
+    pm_free(pm, canvas);
+    fastpm_store_destroy(p);
+}
+
+void ref_readout_window(RefSession *s, int which, double a, int type, int support, const float *canvas_in, const double *x, int64_t np, float *out)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMPainter painter[1];
+    fastpm_painter_init(painter, pm, (FastPMPainterType) type, support);
     FastPMStore p[1];
     tmp_store(p, x, np);
     FastPMFloat *canvas = pm_alloc(pm);

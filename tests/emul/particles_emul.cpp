@@ -82,6 +82,30 @@ int main(int argc, char **argv)
             launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick); });
             dump(out, res);
         }
+    } else if (op == "wpaint" || op == "wreadout") {
+        // in: int32 n, int32 type, int32 support, float64 L, float64 M0, int64 np, x[np][3] f64, (wreadout: dense canvas f32[n^3])
+        const int n = in.one<int32_t>(), type = in.one<int32_t>();
+        int support = in.one<int32_t>();
+        const double L = in.one<double>(), M0 = in.one<double>();
+        const long long np = in.one<int64_t>();
+        std::vector<double> x = in.many<double>((size_t) 3 * np);
+        const FpmGeom g = geom(n, L);
+        if (type == FPM_WINDOW_LINEAR) support = 2; else if (type == FPM_WINDOW_QUAD) support = 3;
+        WindowSpec w = { type, support, (support - 1) / 2, support % 2 == 0 ? 0 : 0.5, 1 / (0.5 * support) };
+        std::vector<float> canvas((size_t) n * n * g.pitch_r, 0.f);
+        const unsigned grid = (unsigned) ((np + 127) / 128);
+        if (op == "wpaint") {
+            launch_seq(grid, 128, [&]() { window_paint_kernel(g, w, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np); });
+            std::vector<float> dense((size_t) n * n * n);
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&dense[((size_t) i * n + j) * n], &canvas[((size_t) i * n + j) * g.pitch_r], sizeof(float) * n);
+            dump(out, dense);
+        } else {
+            std::vector<float> dense = in.many<float>((size_t) n * n * n);
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
+            std::vector<float> res((size_t) np, 0.f);
+            launch_seq(grid, 128, [&]() { window_readout_kernel(g, w, canvas.data(), x.data(), res.data(), 1, np); });
+            dump(out, res);
+        }
     } else if (op == "readout3") {
         // in: int32 n, int32 lag_nc, float64 L, int64 np, x[np][3] f64, three dense canvases f32[n^3]
         // out: three separate readouts into a stride-3 column (f32[np][3]), then the one-pass kernel (f32[np][3])

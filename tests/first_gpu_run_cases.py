@@ -269,3 +269,35 @@ def test_device_ic_chain_matches_reference(ref_mod, pk_text, remove_variance):
     assert np.abs(v - want["v"]).max() < 1e-5 * max(1.0, np.abs(want["v"]).max())
     assert np.abs(dx1 - want["dx1"]).max() < 1e-5 * np.abs(want["dx1"]).max()
     assert np.abs(dx2 - want["dx2"]).max() < 1e-4 * np.abs(want["dx2"]).max()
+
+
+@pytest.mark.parametrize("painter,support", [("quad", 3), ("lanczos", 4)])
+def test_non_cic_painter_matches_reference(ref_mod, pk_text, painter, support):
+    """Row N4 (windows, painter.c:17-125,217-317): the force step with a quadratic / Lanczos window instead of CIC, one GPU."""
+    from fastpm_b200.solver import Solver
+    nc, L, B = 16, 32.0, 2
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, painter=painter, painter_support=support)
+    steps = np.linspace(0.1, 1.0, 4)
+    s = ref_mod.Session(**kw)
+    dk, _, _ = s.ic_deltak(100, pk_text)
+    s.setup_lpt(dk, steps[0])
+    s.evolve(steps)
+    want = s.get_particles()
+    s.close()
+    s = ref_mod.Session(**dict(kw, painter="cic", painter_support=2))
+    s.setup_lpt(dk, steps[0])
+    s.evolve(steps)
+    plain = s.get_particles()
+    s.close()
+    g = Solver(**kw)
+    g.setup_lpt(dk, steps[0])
+    g.evolve(steps)
+    x, v = g.get_column("x"), g.get_column("v")
+    g.close()
+
+    def pdist(a, b):
+        d = np.abs(np.mod(a, L) - np.mod(b, L))
+        return np.minimum(d, L - d).max()
+    assert pdist(want["x"], plain["x"]) > 1e-3           # the window matters
+    assert pdist(x, want["x"]) < 1e-4
+    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()

@@ -93,6 +93,27 @@ def test_three_component_readout_equals_three_readouts(emul, one_thread_ref, tmp
     s.close()
 
 
+@pytest.mark.parametrize("window,support", [("linear", 2), ("quad", 3), ("lanczos", 4), ("lanczos", 6)])
+def test_generic_window_kernels_against_reference(emul, one_thread_ref, tmp_path, window, support):
+    """_generic_paint / _generic_readout (painter.c:176-317) with the linear, quadratic and Lanczos windows (the last with the
+    reference's 1e-3 table quantisation): readout bit for bit, deposit up to the float rounding of each add (as for CIC)."""
+    nmesh, L, npart = 16, 50.0, 3000
+    rng = np.random.default_rng(13 + support)
+    x = _positions(rng, npart, L)
+    wid = {"linear": 1, "quad": 2, "lanczos": 3}[window]
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint_window(x, window, support)).copy()
+    head = struct.pack("<iiiddq", nmesh, wid, support, L, 1.0, npart)
+    got = np.frombuffer(emul("wpaint", head + x.tobytes(), str(tmp_path)), dtype=np.float32).reshape(nmesh, nmesh, nmesh)
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert abs(got.sum(dtype=np.float64) - npart) < 1e-3           # the windows are normalised: mass is conserved
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    want_r = s.readout_window(s.real_pack(field), x, window, support)
+    got_r = np.frombuffer(emul("wreadout", head + x.tobytes() + field.tobytes(), str(tmp_path)), dtype=np.float32)
+    assert np.array_equal(got_r, want_r)
+    s.close()
+
+
 def test_fused_wrap_and_brick_walk(emul, one_thread_ref, tmp_path):
     """Positions outside the box: wrap folded into the deposit == the reference's wrap followed by its paint; the Lagrangian
     brick walk (any permutation of the particles) gives the same mesh up to the order of float additions."""

@@ -17,6 +17,7 @@ CASES = [
     "test_pgd_correction_matches_reference",
     "test_snapshot_files_and_restart_match_reference",
     "test_force_softening_matches_reference",
+    "test_non_cic_painter_matches_reference",
 ]
 
 
