@@ -1,6 +1,7 @@
 /* fastpm_b200 host layer -- P(k) objects (reference: libfastpm/powerspectrum.c).  The shell sums come from
  * the device (fpm_powerspectrum_sums); table parsing, interpolation, sigma(R) and the text writer are host code. */
 #include "internal.h"
+#include <math.h>
 
 void fastpm_funck_init(FastPMFuncK *fk, const size_t size)
 { fk->size = size; fk->k = malloc(sizeof(double) * size); fk->f = malloc(sizeof(double) * size); }
@@ -124,5 +125,58 @@ double fastpm_powerspectrum_sigma(FastPMPowerSpectrum *ps, double R)
     SigmaArg s = { ps, R };
     return sqrt(fpm_integrate(sigma2_integrand, &s, 0, 500.0 * 1 / R, 0, 1e-4, 20));
 }
+/* powerspectrum.c:25-33 */
+void fastpm_powerspectrum_init_from(FastPMPowerSpectrum *ps, const FastPMPowerSpectrum *other)
+{
+    fastpm_powerspectrum_init(ps, other->base.size);
+    memcpy(ps->base.k, other->base.k, sizeof(double) * ps->base.size);
+    memcpy(ps->base.f, other->base.f, sizeof(double) * ps->base.size);
+    memcpy(ps->edges, other->edges, sizeof(double) * (ps->base.size + 1));
+    memcpy(ps->Nmodes, other->Nmodes, sizeof(double) * ps->base.size);
+}
+
+/* powerspectrum.c:127-141: sqrt(P_dest / P_src) per shell */
+void fastpm_transferfunction_init(FastPMPowerSpectrum *ps, PM *pm, FastPMFloat *src_k, FastPMFloat *dest_k)
+{
+    FastPMPowerSpectrum ps2[1];
+    fastpm_powerspectrum_init_from_delta(ps, pm, src_k, src_k);
+    fastpm_powerspectrum_init_from_delta(ps2, pm, dest_k, dest_k);
+    for (size_t i = 0; i < ps->base.size; i++) ps->base.f[i] = sqrt(ps2->base.f[i] / ps->base.f[i]);
+    fastpm_powerspectrum_destroy(ps2);
+}
+
+/* powerspectrum.c:186-226: callbacks with the inverted signature, and the value of the shell that holds k */
+double fastpm_powerspectrum_get(FastPMPowerSpectrum *ps, double k)
+{
+    if (k == 0) return 1;
+    int l = 0, r = (int) ps->base.size;
+    while (r - l > 1) {
+        const int m = (r + l) / 2;
+        if (k <= ps->edges[m]) r = m; else l = m;
+    }
+    return ps->base.f[l];
+}
+double fastpm_powerspectrum_get2(double k, FastPMPowerSpectrum *ps) { return fastpm_powerspectrum_get(ps, k); }
+
+/* powerspectrum.c:292-331: mode-weighted merge of consecutive shells */
+void fastpm_powerspectrum_rebin(FastPMPowerSpectrum *ps, size_t newsize)
+{
+    double *k1 = malloc(newsize * sizeof(double)), *p1 = malloc(newsize * sizeof(double));
+    double *Nmodes1 = malloc(newsize * sizeof(double)), *edges1 = malloc((newsize + 1) * sizeof(double));
+    for (size_t i = 0; i < newsize; i++) {
+        const size_t j1 = i * ps->base.size / newsize, j2 = (i + 1) * ps->base.size / newsize;
+        k1[i] = 0; p1[i] = 0; Nmodes1[i] = 0;
+        edges1[i] = ps->edges[j1]; edges1[i + 1] = ps->edges[j2];
+        for (size_t j = j1; j < j2; j++) {
+            k1[i] += ps->base.k[j] * ps->Nmodes[j];
+            p1[i] += ps->base.f[j] * ps->Nmodes[j];
+            Nmodes1[i] += ps->Nmodes[j];
+        }
+        if (Nmodes1[i] > 0) { k1[i] /= Nmodes1[i]; p1[i] /= Nmodes1[i]; }
+    }
+    free(ps->base.k); free(ps->base.f); free(ps->Nmodes); free(ps->edges);
+    ps->base.k = k1; ps->base.f = p1; ps->Nmodes = Nmodes1; ps->edges = edges1; ps->base.size = newsize;
+}
+
 void fastpm_powerspectrum_scale(FastPMPowerSpectrum *ps, double factor)
 { for (size_t i = 1; i < ps->base.size; i++) ps->base.f[i] *= factor; }

@@ -359,6 +359,11 @@ double fastpm_powerspectrum_eval(FastPMPowerSpectrum *ps, double k);
 double fastpm_powerspectrum_eval2(double k, FastPMPowerSpectrum *ps);
 double fastpm_powerspectrum_sigma(FastPMPowerSpectrum *ps, double R);
 void fastpm_powerspectrum_scale(FastPMPowerSpectrum *ps, double factor);
+void fastpm_powerspectrum_init_from(FastPMPowerSpectrum *ps, const FastPMPowerSpectrum *other);                      /* powerspectrum.c:25 */
+void fastpm_transferfunction_init(FastPMPowerSpectrum *ps, PM *pm, FastPMFloat *src_k, FastPMFloat *dest_k);        /* :127 */
+double fastpm_powerspectrum_get(FastPMPowerSpectrum *ps, double k);                                                  /* :200 */
+double fastpm_powerspectrum_get2(double k, FastPMPowerSpectrum *ps);                                                 /* :222 */
+void fastpm_powerspectrum_rebin(FastPMPowerSpectrum *ps, size_t newsize);                                            /* :292 */
 
 /* ------------------------------------------------------------------ [initialcondition.h:3-17] */
 enum FastPMFillDeltaKScheme { FASTPM_DELTAK_GADGET, FASTPM_DELTAK_FAST, FASTPM_DELTAK_SLOW };     /* [initialcondition.h:3-7] */
