@@ -561,6 +561,15 @@ void read_snapshot_header(FastPMSolver *fastpm, const char *filebase, double *ao
     *aout = ScalingFactor;
 }
 
+/* io.c:976-998: one more attribute on an existing block (the CLI adds "ParamFile" to "Header" this way, src/fastpm.c:97-116) */
+void write_snapshot_attr(const char *filebase, const char *dataset, const char *attrname, void *buf, const char *dtype, size_t nmemb, MPI_Comm comm)
+{
+    BfBlock b;
+    if (bf_open(&b, filebase, dataset)) fastpm_raise(-1, "Failed to open the dataset : %s/%s\n", filebase, dataset);
+    bf_set_attr(&b, attrname, buf, dtype, (int) nmemb);
+    if (bf_close(&b, comm)) fastpm_raise(-1, "Failed to write the attributes of %s/%s\n", filebase, dataset);
+}
+
 /* ------------------------------------------------------------------ k-space meshes: write_complex / read_complex, io.c:641-790
  * A c8 block of Nmesh * Nmesh * (Nmesh/2+1) items in [x][y][z] order (the order the reference's sort by `iabs` produces).
  * This rank holds ky in [y0, y0 + nyl): for every kx those rows are one contiguous run of the file. */

@@ -527,6 +527,25 @@ int fastpm_b200_mesh_get_complex(PM *pm, const FastPMFloat *dev, float *host_dst
 int fastpm_b200_mesh_set_complex(PM *pm, FastPMFloat *dev, const float *host_src);
 /* number of floats in a host array in the reference layout: N*N*(N+2) */
 size_t fastpm_b200_mesh_host_size(PM *pm);
+/* ------------------------------------------------------------------ small remaining entry points of the same headers (csrc/host/extras.c) */
+void fastpm_set_snapshot(FastPMSolver *fastpm, FastPMSolver *snapshot, FastPMDriftFactor *drift, FastPMKickFactor *kick, double aout);   /* solver.h:188 */
+void fastpm_unset_snapshot(FastPMSolver *fastpm, FastPMSolver *snapshot, FastPMDriftFactor *drift, FastPMKickFactor *kick, double aout); /* solver.h:199 */
+void fastpm_store_set_name(FastPMStore *p, const char *name);                                             /* store.h:166 */
+int fastpm_store_has_q(FastPMStore *p);
+void fastpm_store_get_q_from_id(FastPMStore *p, uint64_t id, double q[3]);
+void fastpm_store_get_iq_from_id(FastPMStore *p, uint64_t id, ptrdiff_t pabs[3]);
+void fastpm_store_steal(FastPMStore *in, FastPMStore *out, FastPMColumnTags attributes);                  /* store.h:260 */
+double fastpm_apply_get_mode_transfer(PM *pm, FastPMFloat *from, ptrdiff_t *mode);                        /* transfer.c:340 */
+void fastpm_apply_set_mode_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, ptrdiff_t *mode, double value, int method);   /* :290 */
+void fastpm_apply_normalize_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to);                         /* :223 */
+void fastpm_apply_c2r_weight_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to);                        /* :249 */
+char *fastpm_file_get_content(const char *filename);                                                      /* string.h */
+char **fastpm_strsplit(const char *str, const char *split);
+char *fastpm_strdup(const char *str);
+char *fastpm_strdup_printf(const char *fmt, ...);
+void fastpm_path_ensure_dirname(const char *path);
+int read_funck(FastPMFuncK *fk, const char filename[], MPI_Comm comm);                                    /* io.h */
+
 /* ------------------------------------------------------------------ [io.h] snapshot / mesh files (bigfile directories)
  * Same names, arguments and on-disk result as libfastpmio/io.c; append mode, the distributed sort and the healpix / light-cone
  * writers are not implemented and raise. */
@@ -537,6 +556,7 @@ int fastpm_store_write(FastPMStore *p, const char *filebase, const char *mode, i
 int fastpm_store_read(FastPMStore *p, const char *filebase, int Nwriters, MPI_Comm comm);                     /* io.h:30 */
 void write_snapshot_header(FastPMSolver *fastpm, const char *filebase, MPI_Comm comm);                        /* io.h:37 */
 void read_snapshot_header(FastPMSolver *fastpm, const char *filebase, double *aout, MPI_Comm comm);           /* io.h:41 */
+void write_snapshot_attr(const char *filebase, const char *dataset, const char *attrname, void *buf, const char *dtype, size_t nmemb, MPI_Comm comm); /* io.h:45 */
 int write_complex(PM *pm, FastPMFloat *data, const char *filename, const char *blockname, int Nwriters);      /* io.h:56 */
 int read_complex(PM *pm, FastPMFloat *data, const char *filename, const char *blockname, int Nwriters);       /* io.h:59 */
 /* the same writers on plain arrays (host or device), for bindings and tests */

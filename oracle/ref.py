@@ -206,6 +206,15 @@ class Session:
         lib().ref_remove_variance(self._h, _p(dk), _p(out))
         return out
 
+    def mode_op(self, op, dk, mode=(0, 0, 0, 0), value=0.0, method=0):
+        """op: "set_mode", "normalize", "c2r_weight" on the LPT mesh; returns (result buffer, get_mode(result, mode))."""
+        dk = np.ascontiguousarray(dk, dtype=np.float32)
+        out = np.zeros_like(dk)
+        m = np.array(mode, dtype=np.int64)
+        lib().ref_mode_op.restype = C.c_double
+        r = lib().ref_mode_op(self._h, C.c_int(dict(set_mode=0, normalize=1, c2r_weight=2)[op]), _p(dk), _p(out), _p(m), C.c_double(value), C.c_int(method))
+        return out, float(r)
+
     def write_snapshot(self, filebase):
         """write_snapshot_header + fastpm_store_write of the unit-converted CDM store (bigfile directory `filebase`)."""
         lib().ref_write_snapshot(self._h, C.c_char_p(str(filebase).encode()))

@@ -577,6 +577,23 @@ void ref_write_complex(RefSession *s, int which, double a, const float *dk_in, c
     free(buf);
 }
 
+/* the single-mode transfers of transfer.c on the LPT mesh: op 0 = set_mode (mode[4], value, method), 1 = normalize, 2 = c2r_weight;
+ * returns get_mode(out, mode) */
+double ref_mode_op(RefSession *s, int op, const float *in, float *out, const int64_t *mode4, double value, int method)
+{
+    PM *pm = s->solver->lptpm;
+    ptrdiff_t mode[4] = { mode4[0], mode4[1], mode4[2], mode4[3] };
+    FastPMFloat *a = pm_alloc(pm), *b = pm_alloc(pm);
+    memcpy(a, in, sizeof(FastPMFloat) * pm->allocsize);
+    if (op == 0) fastpm_apply_set_mode_transfer(pm, a, b, mode, value, method);
+    else if (op == 1) fastpm_apply_normalize_transfer(pm, a, b);
+    else fastpm_apply_c2r_weight_transfer(pm, a, b);
+    double r = fastpm_apply_get_mode_transfer(pm, b, mode);
+    memcpy(out, b, sizeof(FastPMFloat) * pm->allocsize);
+    pm_free(pm, b); pm_free(pm, a);
+    return r;
+}
+
 void ref_decic(RefSession *s, int which, double a, const float *in, float *out)
 {
     PM *pm = pick_pm(s, which, a);

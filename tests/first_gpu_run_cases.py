@@ -301,3 +301,50 @@ def test_non_cic_painter_matches_reference(ref_mod, pk_text, painter, support):
     assert pdist(want["x"], plain["x"]) > 1e-3           # the window matters
     assert pdist(x, want["x"]) < 1e-4
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+
+
+def test_single_mode_transfers_match_reference(ref_mod):
+    """fastpm_apply_set_mode / get_mode / normalize / c2r_weight transfers (transfer.c:223-366) on a device mesh, bit for bit."""
+    import ctypes as C
+    from fastpm_b200.solver import Solver
+    n, L = 16, 50.0
+    s = ref_mod.Session(nc=n, boxsize=L, pm_nc_factor=1)
+    dk = s.fill_gaussian(5)
+    c = s.complex_view(dk, which=1).copy()
+    c[0, 0, 0] = 2.5                                    # a mean to normalise by
+    dk = s.complex_pack(c, which=1)
+    g = Solver(nc=n, boxsize=L, pm_nc_factor=1)
+    lib, pm = g.lib, g.lptpm
+    lib.fastpm_apply_get_mode_transfer.restype = C.c_double
+    lib.fastpm_apply_get_mode_transfer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fastpm_apply_set_mode_transfer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+    lib.fastpm_apply_normalize_transfer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fastpm_apply_c2r_weight_transfer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    a, b = lib.pm_alloc_details(pm, b"test", 0), lib.pm_alloc_details(pm, b"test", 0)
+    host = np.ascontiguousarray(dk, dtype=np.float32)
+    out = np.zeros_like(host)
+
+    def run(op, mode, value=0.0, method=0):
+        assert lib.fastpm_b200_mesh_set_complex(pm, a, host.ctypes.data) == 0
+        m = (C.c_ssize_t * 4)(*mode)
+        if op == "set_mode":
+            lib.fastpm_apply_set_mode_transfer(pm, a, b, m, value, method)
+        elif op == "normalize":
+            lib.fastpm_apply_normalize_transfer(pm, a, b)
+        else:
+            lib.fastpm_apply_c2r_weight_transfer(pm, a, b)
+        r = lib.fastpm_apply_get_mode_transfer(pm, b, m)
+        assert lib.fastpm_b200_mesh_get_complex(pm, b, out.ctypes.data) == 0
+        return out.copy(), r
+    cases = [("set_mode", (3, 5, 2, 0), 1.25, 0), ("set_mode", (3, 5, 2, 1), -0.5, 1), ("set_mode", (0, 8, 0, 1), 7.0, 0),
+             ("set_mode", (2, 0, 0, 1), 0.75, 1), ("set_mode", (1, 2, 9, 0), 1.0, 0), ("normalize", (0, 0, 0, 0), 0, 0),
+             ("c2r_weight", (8, 8, 8, 0), 0, 0), ("c2r_weight", (1, 1, 1, 1), 0, 0)]
+    for op, mode, value, method in cases:
+        want, wr = s.mode_op(op, dk, mode, value, method)
+        got, gr = run(op, mode, value, method)
+        assert gr == wr, (op, mode)
+        assert np.array_equal(s.complex_view(got, which=1).view(np.float32), s.complex_view(want, which=1).view(np.float32)), (op, mode)
+    lib.pm_free(pm, b)
+    lib.pm_free(pm, a)
+    g.close()
+    s.close()

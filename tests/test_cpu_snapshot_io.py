@@ -171,3 +171,44 @@ def test_argsort_by_id_is_a_stable_radix_sort(lib):
     perm = np.zeros(300, dtype=np.uint64)
     lib.fastpm_b200_io_argsort_u64(small.ctypes.data, 300, perm.ctypes.data)
     assert np.array_equal(small[perm.astype(np.int64)], np.arange(300, dtype=np.uint64))
+
+
+def test_write_snapshot_attr_and_string_helpers(lib, run, ref_mod):
+    """write_snapshot_attr (io.c:976-998; the CLI stores the parameter file in "Header" with it) on a copy of the reference's
+    directory with both libraries: identical attr-v2.  And the string helpers of string.h against the reference's."""
+    import shutil
+    from oracle import ref
+    text = b"nc = 8\nboxsize = 32.0\n-- a parameter file\n\x00"
+    frac = C.c_double(0.25)
+    outs = []
+    for name, L in (("mine", lib), ("ref", ref.lib())):
+        top = str(run["tmp"] / ("attr_" + name))
+        shutil.copytree(run["ref_dir"], top)
+        L.write_snapshot_attr.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_size_t, C.c_int]
+        L.write_snapshot_attr(top.encode(), b"Header", b"ParamFile", text, b"S1", len(text), 1)
+        L.write_snapshot_attr(top.encode(), b"Header", b"ParticleFraction", C.byref(frac), b"f8", 1, 1)
+        outs.append(open(os.path.join(top, "Header", "attr-v2"), "rb").read())
+        assert filecmp.cmp(os.path.join(top, "Header", "header"), os.path.join(run["ref_dir"], "Header", "header"), shallow=False)
+    assert outs[0] == outs[1] and b"ParamFile" in outs[0] and b"ParticleFraction" in outs[0]
+    # fastpm_strsplit: NULL-terminated array of the pieces
+    for L in (lib, ref.lib()):
+        L.fastpm_strsplit.restype = C.POINTER(C.c_char_p)
+        L.fastpm_strsplit.argtypes = [C.c_char_p, C.c_char_p]
+    for s, sep in ((b"a,b;;c", b",;"), (b"", b","), (b"nosplit", b","), (b",lead,trail,", b",")):
+        got, want = lib.fastpm_strsplit(s, sep), ref.lib().fastpm_strsplit(s, sep)
+        i = 0
+        while want[i] is not None:
+            assert got[i] == want[i]
+            i += 1
+        assert got[i] is None
+    # fastpm_path_ensure_dirname + fastpm_file_get_content
+    deep = str(run["tmp"] / "x" / "y" / "z" / "file.txt")
+    lib.fastpm_path_ensure_dirname.argtypes = [C.c_char_p]
+    lib.fastpm_path_ensure_dirname(deep.encode())
+    assert os.path.isdir(os.path.dirname(deep)) and not os.path.exists(deep)
+    open(deep, "w").write("0.1\t2.5\n0.2\t1.5\n")
+    lib.fastpm_file_get_content.restype = C.c_void_p
+    lib.fastpm_file_get_content.argtypes = [C.c_char_p]
+    ptr = lib.fastpm_file_get_content(deep.encode())
+    assert C.string_at(ptr) == b"0.1\t2.5\n0.2\t1.5\n"
+    assert lib.fastpm_file_get_content(b"/nonexistent/file") is None

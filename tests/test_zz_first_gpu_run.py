@@ -18,6 +18,7 @@ CASES = [
     "test_snapshot_files_and_restart_match_reference",
     "test_force_softening_matches_reference",
     "test_non_cic_painter_matches_reference",
+    "test_single_mode_transfers_match_reference",
 ]
 
 
