@@ -712,3 +712,50 @@ double fastpm_b200_read_snapshot(FastPMSolver *fastpm, const char *filebase)
     fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, po->meta.a_x);
     return a_restart;
 }
+
+/* ------------------------------------------------------------------ snapshots at requested scale factors during fastpm_solver_evolve
+ * check_snapshots + take_a_snapshot of the CLI (src/fastpm.c:1130-1208, 1473-1486) as a ready-made INTERPOLATION handler: whenever a
+ * requested aout falls into (a1, a2] of the event (or equals the initial time), the particles are drifted and kicked there with
+ * the event's factors (fastpm_set_snapshot), written to "<base>_<aout, %0.04f>", and put back (fastpm_unset_snapshot). */
+typedef struct { char base[900]; double aout[64]; int nout, iout, sort_by_id; } SnapshotPlan;
+
+static int snapshot_handler(FastPMSolver *fastpm, FastPMInterpolationEvent *event, SnapshotPlan *plan)
+{
+    for (int iout = plan->iout; iout < plan->nout; iout++) {
+        const double aout = plan->aout[iout];
+        if (event->a1 == event->a2) {
+            if (event->a1 != aout) continue;                 /* initial condition, not requested */
+        } else {
+            if (event->a1 >= aout) continue;
+            if (event->a2 < aout) continue;
+        }
+        FastPMSolver snapshot[1];
+        FastPMStore cdm[1];
+        memcpy(snapshot, fastpm, sizeof(FastPMSolver));
+        fastpm_solver_add_species(snapshot, FASTPM_SPECIES_CDM, cdm);
+        fastpm_set_snapshot(fastpm, snapshot, event->drift, event->kick, aout);
+        fastpm_info("Snapshot a_x = %6.4f, a_v = %6.4f \n", cdm->meta.a_x, cdm->meta.a_v);
+        if (plan->sort_by_id) fastpm_sort_snapshot(cdm, fastpm->comm, FastPMSnapshotSortByID, 0);
+        char filebase[1024];
+        snprintf(filebase, sizeof(filebase), "%s_%0.04f", plan->base, aout);
+        write_snapshot_header(snapshot, filebase, fastpm->comm);
+        fastpm_store_write(cdm, filebase, "w", 0, fastpm->comm);
+        fastpm_unset_snapshot(fastpm, snapshot, event->drift, event->kick, aout);
+        plan->iout = iout + 1;                               /* do not rewrite this snapshot */
+    }
+    return 0;
+}
+
+static int cmp_double(const void *a, const void *b) { const double x = *(const double *) a, y = *(const double *) b; return (x > y) - (x < y); }
+
+void fastpm_b200_add_snapshot_handler(FastPMSolver *fastpm, const char *base, const double *aout, int nout, int sort_by_id)
+{
+    if (nout > 64) fastpm_raise(-1, "fastpm_b200_add_snapshot_handler: at most 64 output times\n");
+    SnapshotPlan *plan = calloc(1, sizeof(*plan));
+    snprintf(plan->base, sizeof(plan->base), "%s", base);
+    memcpy(plan->aout, aout, sizeof(double) * nout);
+    qsort(plan->aout, nout, sizeof(double), cmp_double);      /* the search above needs them ascending, src/fastpm.c:1164 */
+    plan->nout = nout; plan->sort_by_id = sort_by_id;
+    fastpm_add_event_handler_free(&fastpm->event_handlers, FASTPM_EVENT_INTERPOLATION, FASTPM_EVENT_STAGE_BEFORE,
+                                  (FastPMEventHandlerFunction) snapshot_handler, plan, free);
+}

@@ -131,6 +131,12 @@ class Solver:
         self.lib.fastpm_b200_write_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         self.lib.fastpm_b200_write_snapshot(self.h, str(filebase).encode(), int(sort_by_id))
 
+    def add_snapshots(self, base, aout, sort_by_id=False):
+        """Take snapshots "<base>_%0.04f" at the scale factors aout during the next evolve (the CLI's check_snapshots)."""
+        ao = np.ascontiguousarray(aout, dtype=np.float64)
+        self.lib.fastpm_b200_add_snapshot_handler.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+        self.lib.fastpm_b200_add_snapshot_handler(self.h, str(base).encode(), ao.ctypes.data, len(ao), int(sort_by_id))
+
     def read_snapshot(self, filebase):
         """Restart: reads the catalog into the particle store, returns the scale factor of the snapshot."""
         self.lib.fastpm_b200_read_snapshot.argtypes = [C.c_void_p, C.c_char_p]

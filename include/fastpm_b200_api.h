@@ -580,6 +580,9 @@ void fastpm_b200_io_argsort_u64(const uint64_t *key, size_t n, uint64_t *perm);
  * sort by id, Header, catalog, conversion reverted), and the restart read of src/fastpm.c:618-635; returns the header's ScalingFactor */
 void fastpm_b200_write_snapshot(FastPMSolver *fastpm, const char *filebase, int sort_by_id);
 double fastpm_b200_read_snapshot(FastPMSolver *fastpm, const char *filebase);
+/* snapshots at the scale factors aout[nout] while fastpm_solver_evolve runs, written to "<base>_%0.04f": the CLI's check_snapshots
+ * (src/fastpm.c:1130-1208) as a ready-made INTERPOLATION handler */
+void fastpm_b200_add_snapshot_handler(FastPMSolver *fastpm, const char *base, const double *aout, int nout, int sort_by_id);
 
 /* a FastPMConfig/FastPMSolver pair built from scalars, for bindings that cannot lay out the structs */
 FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,

@@ -219,6 +219,12 @@ class Session:
         """write_snapshot_header + fastpm_store_write of the unit-converted CDM store (bigfile directory `filebase`)."""
         lib().ref_write_snapshot(self._h, C.c_char_p(str(filebase).encode()))
 
+    def evolve_snapshots(self, time_step, base, aout):
+        """evolve + the CLI's snapshot taking: directories "<base>_%0.04f" for every aout inside the run."""
+        ts = np.ascontiguousarray(time_step, dtype=np.float64)
+        ao = np.ascontiguousarray(sorted(aout), dtype=np.float64)
+        lib().ref_evolve_snapshots(self._h, _p(ts), C.c_int(len(ts)), C.c_char_p(str(base).encode()), _p(ao), C.c_int(len(ao)))
+
     def snapshot_particles(self):
         """(x, v) after fastpm_set_species_snapshot at the particles' own time: v in km/s, x wrapped into the box."""
         x, v = np.zeros((self.np, 3)), np.zeros((self.np, 3), dtype=np.float32)

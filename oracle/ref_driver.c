@@ -511,6 +511,41 @@ void ref_write_snapshot(RefSession *s, const char *filebase)
     fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, aout);
 }
 
+/* fastpm_solver_evolve with snapshots at aout[] the way the CLI takes them: check_snapshots (src/fastpm.c:1130-1208) restated as
+ * an INTERPOLATION handler (it is static in the CLI), then write_snapshot_header + fastpm_store_write to "<base>_%0.04f". */
+typedef struct { const char *base; const double *aout; int nout, iout; } RefSnapPlan;
+static int ref_check_snapshots(FastPMSolver *fastpm, FastPMInterpolationEvent *event, RefSnapPlan *plan)
+{
+    for (int iout = plan->iout; iout < plan->nout; iout++) {
+        double aout = plan->aout[iout];
+        if (event->a1 == event->a2) { if (event->a1 != aout) continue; }
+        else { if (event->a1 >= aout) continue; if (event->a2 < aout) continue; }
+        FastPMSolver snapshot[1];
+        FastPMStore cdm[1];
+        memcpy(snapshot, fastpm, sizeof(FastPMSolver));
+        fastpm_solver_add_species(snapshot, FASTPM_SPECIES_CDM, cdm);
+        fastpm_set_snapshot(fastpm, snapshot, event->drift, event->kick, aout);
+        char filebase[1024];
+        sprintf(filebase, "%s_%0.04f", plan->base, aout);
+        write_snapshot_header(snapshot, filebase, fastpm->comm);
+        fastpm_store_write(cdm, filebase, "w", 0, fastpm->comm);
+        fastpm_unset_snapshot(fastpm, snapshot, event->drift, event->kick, aout);
+        plan->iout = iout + 1;
+    }
+    return 0;
+}
+
+void ref_evolve_snapshots(RefSession *s, const double *time_step, int nstep, const char *base, const double *aout_sorted, int nout)
+{
+    RefSnapPlan plan = { base, aout_sorted, nout, 0 };
+    fastpm_add_event_handler(&s->solver->event_handlers, FASTPM_EVENT_INTERPOLATION, FASTPM_EVENT_STAGE_BEFORE,
+            (FastPMEventHandlerFunction) ref_check_snapshots, &plan);
+    clear_records(s);
+    fastpm_solver_evolve(s->solver, (double *) time_step, nstep);
+    fastpm_remove_event_handler(&s->solver->event_handlers, FASTPM_EVENT_INTERPOLATION, FASTPM_EVENT_STAGE_BEFORE,
+            (FastPMEventHandlerFunction) ref_check_snapshots, &plan);
+}
+
 /* the unit-converted, wrapped particles that ref_write_snapshot hands to fastpm_store_write */
 void ref_snapshot_particles(RefSession *s, double *x, float *v)
 {

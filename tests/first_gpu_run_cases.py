@@ -348,3 +348,41 @@ def test_single_mode_transfers_match_reference(ref_mod):
     lib.pm_free(pm, a)
     g.close()
     s.close()
+
+
+def test_snapshots_during_evolve_match_reference(ref_mod, pk_text, tmp_path):
+    """The CLI's way of taking snapshots (check_snapshots, src/fastpm.c:1130-1208): at every requested aout inside a step the
+    particles are drifted / kicked there with the INTERPOLATION event's factors, written, and put back.  Same directories as the
+    reference's (data within the path's tolerances), same final state (the round trip perturbs it on both sides)."""
+    import os
+    from fastpm_b200.solver import Solver
+    nc, L = 16, 32.0
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
+    steps, aout = np.linspace(0.1, 1.0, 5), [0.1, 0.37, 0.6, 1.0]
+    s = ref_mod.Session(**kw)
+    dk, _, _ = s.ic_deltak(7, pk_text)
+    s.setup_lpt(dk, steps[0])
+    s.evolve_snapshots(steps, str(tmp_path / "ref"), aout)
+    want = s.get_particles()
+    s.close()
+    g = Solver(**kw)
+    g.setup_lpt(dk, steps[0])
+    g.add_snapshots(str(tmp_path / "mine"), aout)
+    g.evolve(steps)
+    x, v = g.get_column("x"), g.get_column("v")
+    g.close()
+    d = np.abs(np.mod(x, L) - np.mod(want["x"], L))
+    assert np.minimum(d, L - d).max() < 1e-4
+    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+    names = sorted(n for n in os.listdir(tmp_path) if n.startswith("ref_"))
+    assert names == ["ref_%0.04f" % a for a in aout]
+    for n in names:
+        a, b = str(tmp_path / n.replace("ref_", "mine_")), str(tmp_path / n)
+        assert sorted(os.listdir(os.path.join(a, "1"))) == sorted(os.listdir(os.path.join(b, "1")))      # Position Velocity ID DX1 DX2 ...
+        assert open(os.path.join(a, "1", "attr-v2")).read() == open(os.path.join(b, "1", "attr-v2")).read()
+        xa, xb = _read_block(a, "Position", np.float32, 3), _read_block(b, "Position", np.float32, 3)
+        dd = np.abs(xa.astype(np.float64) - xb)
+        assert np.minimum(dd, L - dd).max() < 1e-4, n
+        va, vb = _read_block(a, "Velocity", np.float32, 3), _read_block(b, "Velocity", np.float32, 3)
+        assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max(), n
+        assert np.array_equal(_read_block(a, "ID", np.uint64, 1), _read_block(b, "ID", np.uint64, 1))

@@ -16,6 +16,7 @@ CASES = [
     "test_fused_readout_option_gives_the_same_run",
     "test_pgd_correction_matches_reference",
     "test_snapshot_files_and_restart_match_reference",
+    "test_snapshots_during_evolve_match_reference",
     "test_force_softening_matches_reference",
     "test_non_cic_painter_matches_reference",
     "test_single_mode_transfers_match_reference",
