@@ -386,3 +386,40 @@ def test_snapshots_during_evolve_match_reference(ref_mod, pk_text, tmp_path):
         va, vb = _read_block(a, "Velocity", np.float32, 3), _read_block(b, "Velocity", np.float32, 3)
         assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max(), n
         assert np.array_equal(_read_block(a, "ID", np.uint64, 1), _read_block(b, "ID", np.uint64, 1))
+
+
+def test_cli_run_loop_program_matches_reference(ref_mod, pk_text, tmp_path):
+    """tests/abi/cli_like_example.c (reference API names only) run on the device: same snapshots and power-spectrum files as the
+    reference driven the same way."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    from test_abi_layout import build_dropin_example
+    exe = build_dropin_example(str(tmp_path), "cli_like_example")
+    nc, L, seed, aout = 16, 48.0, 42, [0.1, 0.5, 1.0]
+    r = subprocess.run([exe, os.path.join(here, "golden", "powerspec.txt"), str(tmp_path / "mine"), str(nc), str(L), str(seed),
+                        ",".join("%g" % a for a in aout)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "3 snapshots" in r.stdout, r.stdout
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
+    dk, _, _ = s.ic_deltak(seed, pk_text)
+    s.setup_lpt(dk, 0.1)
+    s.evolve_snapshots(np.array([0.1, 0.325, 0.55, 0.775, 1.0]), str(tmp_path / "ref"), aout)
+    recs = s.records()
+    s.close()
+    for a in aout:
+        mine, ref_dir = str(tmp_path / ("mine_%0.04f" % a)), str(tmp_path / ("ref_%0.04f" % a))
+        assert sorted(os.listdir(os.path.join(mine, "1"))) == sorted(os.listdir(os.path.join(ref_dir, "1")))
+        xa, xb = _read_block(mine, "Position", np.float32, 3), _read_block(ref_dir, "Position", np.float32, 3)
+        d = np.abs(xa.astype(np.float64) - xb)
+        assert np.minimum(d, L - d).max() < 1e-4, a
+        va, vb = _read_block(mine, "Velocity", np.float32, 3), _read_block(ref_dir, "Velocity", np.float32, 3)
+        assert np.abs(va - vb).max() < 1e-4 * np.abs(vb).max(), a
+    # the power spectrum files: "# k p N" rows against the reference's FORCE/after records
+    for rec in recs:
+        rows = np.loadtxt(str(tmp_path / ("mine_powerspec_%0.04f.txt" % rec["a_f"])))
+        sel = rec["nmodes"] > 0
+        assert np.array_equal(rows[:, 2], rec["nmodes"])
+        np.testing.assert_allclose(rows[sel, 0], rec["k"][sel], rtol=1e-5)          # "%g": 6 significant digits
+        np.testing.assert_allclose(rows[sel, 1], rec["p"][sel], rtol=2e-5)

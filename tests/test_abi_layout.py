@@ -32,15 +32,16 @@ def test_public_struct_layouts_match_reference(tmp_path):
     assert not diff, diff
 
 
-def build_dropin_example(tmpdir):
-    """Compiles tests/abi/dropin_example.c -- a libfastpm user program in the style of the reference's tests/testpm.c -- against
-    include/fastpm_b200_api.h and links it with libfastpm_b200.so; returns the executable."""
-    exe = os.path.join(tmpdir, "dropin_example")
+def build_dropin_example(tmpdir, name="dropin_example"):
+    """Compiles tests/abi/<name>.c -- a libfastpm user program in the style of the reference's tests/testpm.c (dropin_example) or of
+    its command-line run loop (cli_like_example) -- against include/fastpm_b200_api.h and links it with libfastpm_b200.so; returns
+    the executable."""
+    exe = os.path.join(tmpdir, name)
     libdir = os.path.join(ROOT, "fastpm_b200")
     env = dict(os.environ)
     env.pop("CC", None)
     cmd = ["gcc", "-std=gnu99", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
-           os.path.join(ROOT, "tests", "abi", "dropin_example.c"), "-L" + libdir, "-lfastpm_b200", "-Wl,-rpath," + libdir, "-lm"]
+           os.path.join(ROOT, "tests", "abi", name + ".c"), "-L" + libdir, "-lfastpm_b200", "-Wl,-rpath," + libdir, "-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     assert r.returncode == 0, r.stdout
     return exe
@@ -52,3 +53,15 @@ def test_libfastpm_user_program_compiles_and_links(tmp_path):
     exe = build_dropin_example(str(tmp_path))
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 2 and "usage" in r.stdout         # no arguments: prints its usage, touches no device
+
+
+def test_cli_run_loop_program_compiles_and_links(tmp_path):
+    """The run loop of the reference's command-line program (IC from a seed, evolve, snapshots through the INTERPOLATION event,
+    power-spectrum files) written with reference API names only -- not one fastpm_b200_* call -- builds against our header and
+    library without warnings."""
+    src = open(os.path.join(ROOT, "tests", "abi", "cli_like_example.c")).read()
+    code = src[src.index("#include"):]
+    assert "fastpm_b200_" not in code.replace("fastpm_b200_api.h", "")
+    exe = build_dropin_example(str(tmp_path), "cli_like_example")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 2 and "usage" in r.stdout

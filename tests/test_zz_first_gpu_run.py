@@ -12,6 +12,7 @@ CASES = [
     "test_device_gadget_ic_matches_reference",
     "test_device_ic_chain_matches_reference",
     "test_libfastpm_user_program_runs_and_matches_fixture",
+    "test_cli_run_loop_program_matches_reference",
     "test_three_component_readout_equals_three_readouts",
     "test_fused_readout_option_gives_the_same_run",
     "test_pgd_correction_matches_reference",
