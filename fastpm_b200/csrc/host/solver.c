@@ -389,6 +389,9 @@ void fastpm_unset_species_snapshot(FastPMSolver *fastpm, FastPMStore *p, FastPMD
     }
     if (kick) fastpm_kick_store(kick, po, po, p->meta.a_v);
     if (drift) fastpm_drift_store(drift, po, po, p->meta.a_x);
+    /* the two in-place updates above are queued under `po`, which is the caller's temporary: apply them now, before the wrap
+     * below (reference order) and before `po` goes away */
+    fpm_store_flush(NULL);
     /* columns are shared; count and meta come back from po like fastpm_store_steal does (store.c:911-921): the reverting kick /
      * drift above have put po's time stamps back to p's, and without them (restart, src/fastpm.c:625-633) po's are what was read */
     p->np = po->np;
