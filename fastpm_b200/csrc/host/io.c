@@ -541,16 +541,22 @@ void read_snapshot_header(FastPMSolver *fastpm, const char *filebase, double *ao
     BfBlock b;
     if (bf_open(&b, filebase, "Header")) fastpm_raise(-1, "Failed to open the header block of %s\n", filebase);
     double NC = 0, BoxSize = 0, ScalingFactor = 0, Omega_cdm = 0, UnitLength = 0, UnitMass = 0, UnitVelocity = 0;
+    double Omega_m = 0, OmegaLambda = 0, HubbleParam = 0;
     int64_t nc = 0;
     int UsePeculiarVelocity = 0;
     if (bf_get_attr(&b, "NC", &nc, "i8", 1) || bf_get_attr(&b, "BoxSize", &BoxSize, "f8", 1) || bf_get_attr(&b, "ScalingFactor", &ScalingFactor, "f8", 1)
         || bf_get_attr(&b, "Omega_cdm", &Omega_cdm, "f8", 1) || bf_get_attr(&b, "UsePeculiarVelocity", &UsePeculiarVelocity, "i4", 1)
+        || bf_get_attr(&b, "OmegaM", &Omega_m, "f8", 1) || bf_get_attr(&b, "OmegaLambda", &OmegaLambda, "f8", 1)
+        || bf_get_attr(&b, "HubbleParam", &HubbleParam, "f8", 1)
         || bf_get_attr(&b, "UnitLength_in_cm", &UnitLength, "f8", 1) || bf_get_attr(&b, "UnitMass_in_g", &UnitMass, "f8", 1)
         || bf_get_attr(&b, "UnitVelocity_in_cm_per_s", &UnitVelocity, "f8", 1))
         fastpm_raise(-1, "The header block of %s lacks an attribute\n", filebase);
     bf_free(&b);
     NC = (double) nc;
-    /* the consistency checks of io.c:186-218 */
+    /* the consistency checks of io.c:175-218 */
+    if (Omega_m != fastpm->cosmology->Omega_m) fastpm_raise(-1, "Omega_m mismatched %g != %g", Omega_m, fastpm->cosmology->Omega_m);
+    if (OmegaLambda != fastpm->cosmology->Omega_Lambda) fastpm_raise(-1, "OmegaLambda mismatched %g != %g", OmegaLambda, fastpm->cosmology->Omega_Lambda);
+    if (HubbleParam != fastpm->cosmology->h) fastpm_raise(-1, "HubbleParam mismatched %g != %g", HubbleParam, fastpm->cosmology->h);
     if (NC != (double) fastpm->config->nc) fastpm_raise(-1, "NC mismatched %g != %g", NC, (double) fastpm->config->nc);
     if (BoxSize != fastpm->config->boxsize) fastpm_raise(-1, "BoxSize mismatched %g != %g", BoxSize, fastpm->config->boxsize);
     if (Omega_cdm != fastpm->cosmology->Omega_cdm) fastpm_raise(-1, "Omega_cdm mismatched %g != %g", Omega_cdm, fastpm->cosmology->Omega_cdm);
