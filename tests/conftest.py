@@ -8,8 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+EMUL_LIB = os.path.join(ROOT, "tests", "emul", "_build", "libfastpm_b200_emul.so")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if os.environ.get("FASTPM_B200_TEST_EMUL"):
+        # tests/test_cpu_full_emulation.py: the `gpu` cases of this process run on the CPU against the emulated build of the whole
+        # library (tests/emul/emul_lib/: kernel sources on OS threads, fake CUDA runtime).  Test infrastructure only -- the product
+        # loader (fastpm_b200/_lib.py) knows nothing about it.
+        if not os.path.exists(EMUL_LIB):
+            raise RuntimeError("FASTPM_B200_TEST_EMUL is set but %s is not built (python tests/emul/emul_lib/build.py)" % EMUL_LIB)
+        from fastpm_b200 import _lib
+        _lib.LIB_PATH = EMUL_LIB
 
 
 @pytest.fixture(scope="session")

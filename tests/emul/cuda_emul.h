@@ -6,6 +6,8 @@
 #include <sched.h>
 #include <string.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -15,8 +17,18 @@ struct FpmEmulDim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local FpmEmulDim3 threadIdx;
 static FpmEmulDim3 blockIdx, blockDim, gridDim;
 static pthread_barrier_t fpm_emul_barrier;
+#ifdef FPM_EMUL_EXTERN_SMEM                      // several translation units in one library (emul_lib/): one of them defines it
+extern unsigned char *fpm_emul_dyn_smem;
+#else
 unsigned char *fpm_emul_dyn_smem = nullptr;     // declared extern by csrc/common.cuh under FPM_EMULATE
-#define __syncthreads() pthread_barrier_wait(&fpm_emul_barrier)
+#endif
+static bool fpm_emul_sequential = false;        // CUDA threads run one after the other (kernels without barriers only)
+static inline void fpm_emul_barrier_wait()
+{
+    if (fpm_emul_sequential) { fprintf(stderr, "cuda_emul: __syncthreads() in a kernel launched sequentially\n"); abort(); }
+    pthread_barrier_wait(&fpm_emul_barrier);
+}
+#define __syncthreads() fpm_emul_barrier_wait()
 #define __ldg(p) (*(p))
 #define __global__
 #define __grid_constant__

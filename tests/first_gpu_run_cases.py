@@ -9,10 +9,18 @@ the file name keeps them out of the default collection; tests/test_zz_first_gpu_
   * the opt-in one-pass readout of the three force components
   * PGD correction (N3), snapshot files + restart from the device (N2), force softening (N4)
 """
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+# tests/test_cpu_full_emulation.py runs these cases on the CPU against the emulated library with a smaller particle grid
+NC_SCALE = float(os.environ.get("FASTPM_B200_TEST_NC_SCALE", "1"))
+
+
+def _nc(n):
+    return max(8, int(round(n * NC_SCALE / 4)) * 4)
 
 
 @pytest.mark.parametrize("n,seed", [(32, 2004), (48, 100)])
@@ -119,7 +127,7 @@ def test_pgd_correction_matches_reference(ref_mod, pk_text):
     """Row N3 of SURVEY.md section 8f: the PGD correction (pgdcorrection.c) switched on -- the pgdc column after every force and
     the extra displacement in every drift (factors.c:108-113) -- against the oracle on identical initial conditions."""
     from fastpm_b200.solver import Solver
-    nc, L, B = 32, 64.0, 2
+    nc, L, B = _nc(32), 2.0 * _nc(32), 2
     par = (0.2, 0.5, 1.0, 1.0, 5.0)                      # alpha0, A, B, kl, ks
     steps = np.linspace(0.1, 1.0, 5)
     s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, pgdc=par)
@@ -162,7 +170,7 @@ def test_snapshot_files_and_restart_match_reference(ref_mod, pk_text, tmp_path):
     import filecmp
     import os
     from fastpm_b200.solver import Solver
-    nc, L, B = 16, 32.0, 2
+    nc, L, B = _nc(16), 2.0 * _nc(16), 2
     kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
     first, second = np.linspace(0.1, 0.5, 3), np.linspace(0.5, 1.0, 3)
     s = ref_mod.Session(**kw)
@@ -216,7 +224,7 @@ def test_snapshot_files_and_restart_match_reference(ref_mod, pk_text, tmp_path):
 def test_force_softening_matches_reference(ref_mod, pk_text, softening):
     """Row N4 (softening kernels, gravity.c:244-270): a short run with the dealiasing sweep on delta_k switched on."""
     from fastpm_b200.solver import Solver
-    nc, L, B = 16, 32.0, 2
+    nc, L, B = _nc(16), 2.0 * _nc(16), 2
     kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, softening=softening)
     steps = np.linspace(0.1, 1.0, 4)
     s = ref_mod.Session(**kw)
@@ -251,7 +259,7 @@ def test_device_ic_chain_matches_reference(ref_mod, pk_text, remove_variance):
     particles the reference makes from the same seed and P(k) table (src/fastpm.c:415-545 + fastpm_solver_setup_lpt)."""
     import os
     from fastpm_b200.solver import Solver
-    nc, L = 32, 128.0
+    nc, L = _nc(32), 4.0 * _nc(32)
     kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
     s = ref_mod.Session(**kw)
     dk, _, _ = s.ic_deltak(2024, pk_text, remove_variance=remove_variance)
@@ -275,7 +283,7 @@ def test_device_ic_chain_matches_reference(ref_mod, pk_text, remove_variance):
 def test_non_cic_painter_matches_reference(ref_mod, pk_text, painter, support):
     """Row N4 (windows, painter.c:17-125,217-317): the force step with a quadratic / Lanczos window instead of CIC, one GPU."""
     from fastpm_b200.solver import Solver
-    nc, L, B = 16, 32.0, 2
+    nc, L, B = _nc(16), 2.0 * _nc(16), 2
     kw = dict(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, painter=painter, painter_support=support)
     steps = np.linspace(0.1, 1.0, 4)
     s = ref_mod.Session(**kw)
@@ -356,7 +364,7 @@ def test_snapshots_during_evolve_match_reference(ref_mod, pk_text, tmp_path):
     reference's (data within the path's tolerances), same final state (the round trip perturbs it on both sides)."""
     import os
     from fastpm_b200.solver import Solver
-    nc, L = 16, 32.0
+    nc, L = _nc(16), 2.0 * _nc(16)
     kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
     steps, aout = np.linspace(0.1, 1.0, 5), [0.1, 0.37, 0.6, 1.0]
     s = ref_mod.Session(**kw)
@@ -398,7 +406,7 @@ def test_cli_run_loop_program_matches_reference(ref_mod, pk_text, tmp_path):
     sys.path.insert(0, here)
     from test_abi_layout import build_dropin_example
     exe = build_dropin_example(str(tmp_path), "cli_like_example")
-    nc, L, seed, aout = 16, 48.0, 42, [0.1, 0.5, 1.0]
+    nc, L, seed, aout = _nc(16), 3.0 * _nc(16), 42, [0.1, 0.5, 1.0]
     r = subprocess.run([exe, os.path.join(here, "golden", "powerspec.txt"), str(tmp_path / "mine"), str(nc), str(L), str(seed),
                         ",".join("%g" % a for a in aout)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "3 snapshots" in r.stdout, r.stdout

@@ -37,11 +37,13 @@ def build_dropin_example(tmpdir, name="dropin_example"):
     its command-line run loop (cli_like_example) -- against include/fastpm_b200_api.h and links it with libfastpm_b200.so; returns
     the executable."""
     exe = os.path.join(tmpdir, name)
-    libdir = os.path.join(ROOT, "fastpm_b200")
+    libdir, libname = os.path.join(ROOT, "fastpm_b200"), "fastpm_b200"
+    if os.environ.get("FASTPM_B200_TEST_EMUL"):          # tests/test_cpu_full_emulation.py: the CPU build of the whole library
+        libdir, libname = os.path.join(ROOT, "tests", "emul", "_build"), "fastpm_b200_emul"
     env = dict(os.environ)
     env.pop("CC", None)
     cmd = ["gcc", "-std=gnu99", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
-           os.path.join(ROOT, "tests", "abi", name + ".c"), "-L" + libdir, "-lfastpm_b200", "-Wl,-rpath," + libdir, "-lm"]
+           os.path.join(ROOT, "tests", "abi", name + ".c"), "-L" + libdir, "-l" + libname, "-Wl,-rpath," + libdir, "-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     assert r.returncode == 0, r.stdout
     return exe

@@ -32,7 +32,7 @@ def test_case_list_is_complete():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first B200 run pending: written after this round's GPU budget was spent")
+@pytest.mark.xfail(strict=False, reason="first B200 run pending: written after this round's GPU budget was spent (green on the CPU through the emulated library, tests/test_cpu_full_emulation.py)")
 @pytest.mark.parametrize("case", CASES)
 def test_first_gpu_run(case):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
