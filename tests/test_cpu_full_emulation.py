@@ -47,16 +47,51 @@ def test_groups_cover_every_case():
     assert sorted([c for g in GROUPS for c in g] + ([] if os.environ.get("FASTPM_B200_TEST_EMUL_ALL") else SLOW)) == sorted(CASES)
 
 
-def test_gpu_cases_on_the_emulated_library(emul_lib):
+@pytest.fixture(scope="module")
+def runs(emul_lib, tmp_path_factory):
+    """Everything below starts at once, as separate processes: the case groups and one bench.py run."""
     env = dict(os.environ, FASTPM_B200_TEST_EMUL="1", FASTPM_B200_TEST_NC_SCALE="0.25", OMP_NUM_THREADS="2")
-    procs = []
+    procs = {}
     for g in GROUPS:
         cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "first_gpu_run_cases.py"),
                "-k", " or ".join(g)]
-        procs.append((g, subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    failed = []
-    for g, p in procs:
-        out, _ = p.communicate(timeout=1500)
-        if p.returncode != 0:
-            failed.append((g, out[-3000:]))
+        procs[tuple(g)] = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    script = tmp_path_factory.mktemp("bench") / "run_bench.py"
+    script.write_text(
+        "import sys, runpy\n"
+        "sys.path.insert(0, %r)\n"
+        "from fastpm_b200 import _lib\n"
+        "_lib.LIB_PATH = %r\n"
+        "sys.argv = ['bench.py', '--nc', '8', '--steps', '3', '--warmup', '1', '--no-cpu-baseline']\n"
+        "runpy.run_path(%r, run_name='__main__')\n" % (ROOT, emul_lib, os.path.join(ROOT, "bench.py")))
+    bench = subprocess.Popen([sys.executable, str(script)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    out = {}
+    for g, p in procs.items():
+        o, _ = p.communicate(timeout=1500)
+        out[g] = (p.returncode, o)
+    bo, be = bench.communicate(timeout=1500)
+    out["bench"] = (bench.returncode, bo, be)
+    return out
+
+
+def test_gpu_cases_on_the_emulated_library(runs):
+    failed = [(g, r[1][-3000:]) for g, r in runs.items() if g != "bench" and r[0] != 0]
     assert not failed, "\n\n".join("%s\n%s" % (g, o) for g, o in failed)
+
+
+def test_bench_contract_on_the_emulated_library(runs):
+    """bench.py end to end (tiny grid, emulated library): one JSON line on stdout with the keys the driver reads."""
+    import json
+    rc, stdout, stderr = runs["bench"]
+    assert rc == 0, stderr[-3000:]
+    lines = [l for l in stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, stdout[-2000:]                     # exactly one line on stdout
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert line["metric"] == "pm_step_particles_per_second" and line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 1
+    assert line["value"] > 0 and line["gpu_launches"] > 0 and "workload" in line["config"]
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
