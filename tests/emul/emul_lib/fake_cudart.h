@@ -24,6 +24,8 @@ static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, _
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline void __threadfence_system() { __sync_synchronize(); }
+static inline void __threadfence() { __sync_synchronize(); }
 static inline void sincospif(float x, float *s, float *c) { *s = sinf((float) M_PI * x); *c = cosf((float) M_PI * x); }
 static inline void sincospi(double x, double *s, double *c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 

@@ -1,6 +1,7 @@
 """Worker for the multi-process tests (launched with torch.distributed.run, one process per rank).
 
 mode "cpu":  world_size-2 gloo test of the host plumbing (no GPU): callback collectives, slab ownership.
+mode "emul": the "gpu" mode on the CPU, against the emulated build of the whole library (tests/test_cpu_full_emulation.py).
 mode "gpu":  x-slab run on one GPU per rank from the committed fixture; rank 0 gathers the particles by id and checks
              them against the reference fixture (tests/golden/small_run.npz).
 """
@@ -106,8 +107,15 @@ def main():
             print("MP_CPU_OK")
         return
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    if mode == "emul":
+        # the same slab run on the CPU: every rank is a process that loads the emulated build of the whole library
+        # (tests/emul/emul_lib/), the peers' arenas are POSIX shared memory mapped through the stand-in CUDA IPC
+        _lib.LIB_PATH = os.path.join(ROOT, "tests", "emul", "_build", "libfastpm_b200_emul.so")
+        os.environ.setdefault("FASTPM_B200_ARENA_GB", "0.25")
+        dist.init_process_group(backend="gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     lib = _lib.require_device(local)
     multigpu.init_comm(lib)
     from fastpm_b200.solver import Solver

@@ -3,8 +3,8 @@ the emulated kernel sources (tests/emul/cuda_emul.h) and a stand-in CUDA runtime
 The `gpu` cases of tests/first_gpu_run_cases.py -- written after this round's GPU budget was spent -- then run HERE, unchanged
 except for a smaller particle grid, against the compiled reference: PGD correction, force softening, the other windows, the device
 initial-condition chain, snapshots written from "device" columns, restart, snapshots during evolve, the two plain-C libfastpm user
-programs.  What this does not cover: the TMA / bulk-copy FFT fast path (Nmesh >= 512; emulated kernel by kernel in
-test_cpu_oracle_and_host.py) and anything with more than one rank.
+programs.  Several ranks are several processes (arenas in POSIX shared memory): the 4-rank slab run.
+What this does not cover: the TMA / bulk-copy FFT fast path (Nmesh >= 512; emulated kernel by kernel in test_cpu_oracle_and_host.py).
 
 Test infrastructure only: the product loader never looks for this library (tests/conftest.py swaps the path when
 FASTPM_B200_TEST_EMUL is set, in a pytest process of its own)."""
@@ -95,3 +95,16 @@ def test_bench_contract_on_the_emulated_library(runs):
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
+
+
+def test_four_rank_slab_run_on_the_emulated_library(emul_lib):
+    """The x-slab run of tests/mp_worker.py ("gpu" mode on 2 and 8 B200s) with FOUR ranks -- a count no hardware run of this round
+    covered -- as four processes on the emulated library: symmetric arenas in POSIX shared memory mapped through the stand-in CUDA
+    IPC, the cross-GPU barrier kernel spinning on flags in the peers' memory, staged slab transposes, halo planes, particle
+    migration; rank 0 gathers the particles and checks them against the reference fixture."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", "29688", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"]
+    before = set(os.listdir("/dev/shm"))
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert "MP_GPU_OK ranks=4" in r.stdout, r.stdout[-3000:]
+    assert not [f for f in set(os.listdir("/dev/shm")) - before if f.startswith("fpm_emul_")]          # the arenas were unlinked
