@@ -180,7 +180,10 @@ extern "C" int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const f
     return 0;
 }
 
-// readout prologue: my halo plane (index nxl) = plane 0 of the next rank
+// readout prologue: my halo plane (index nxl) = plane 0 of the next rank.  Barriers on both sides: every rank has finished the
+// transform before anybody pulls, and everybody has pulled before any rank writes its mesh again -- the owner may reuse the block
+// for something purely local right away (the PGD potential after the last force component: without the second barrier a slow
+// neighbour pulled a plane that was already being overwritten; found with 4 emulated ranks, tests/test_cpu_full_emulation.py).
 extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank)
 {
     const FpmGeom &g = m->geom;
@@ -188,6 +191,7 @@ extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const
     cudaStream_t st = comm_stream();
     if (fpm_xbarrier_on(st)) return -1;
     FPM_CUDA_OK(cudaMemcpyAsync(canvas_local + (size_t) g.nxl * plane, canvas_next_rank, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (fpm_xbarrier_on(st)) return -1;
     return 0;
 }
 

@@ -141,6 +141,70 @@ def main():
         print("MP_GPU_OK ranks=%d max position error %.3g Mpc/h, np per rank %s" % (world, err, [len(o[0]) for o in out]))
     g.close()
     dist.barrier()
+    if os.environ.get("MP_EXTRAS"):
+        extras(rank, world)
+        dist.barrier()
+
+
+def extras(rank, world):
+    """Rows N3 and N2 on several ranks: the PGD correction (halo planes + distributed inverse transforms) against the oracle, and a
+    snapshot written by every rank from its device columns (unsorted, like sort_snapshot = false) against the reference's."""
+    import shutil
+    import tempfile
+    import torch.distributed as dist
+    from fastpm_b200.solver import Solver
+    from oracle import ref
+    if not ref.available():
+        return
+    nc, L, par, steps = 16, 32.0, (0.2, 0.5, 1.0, 1.0, 5.0), np.linspace(0.1, 1.0, 4)
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", pgdc=par)
+    box = [tempfile.mkdtemp(prefix="fpm_mp_extras_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tmp = box[0]
+    pack = None
+    if rank == 0:
+        s = ref.Session(np_alloc_factor=2.0, **kw)
+        dk, _, _ = s.ic_deltak(9, open(os.path.join(ROOT, "tests", "golden", "powerspec.txt")).read())
+        s.setup_lpt(dk, steps[0])
+        s.evolve(steps)
+        want, want_pgdc = s.get_particles(), s.get_pgdc()
+        s.write_snapshot(os.path.join(tmp, "ref"))
+        s.close()
+        pack = dk
+    box = [pack]
+    dist.broadcast_object_list(box, src=0)
+    dk = box[0]
+    g = Solver(np_alloc_factor=3.0, **kw)
+    g.setup_lpt(dk, steps[0])
+    g.evolve(steps)
+    g.write_snapshot(os.path.join(tmp, "mine"))
+    out = [None] * world
+    dist.all_gather_object(out, (g.get_column("id"), g.get_column("x"), g.get_column("v"), g.get_column("pgdc")))
+    g.close()
+    if rank == 0:
+        ids = np.concatenate([o[0] for o in out])
+        order = np.argsort(ids)
+        x, v, pg = (np.concatenate([o[i] for o in out])[order] for i in (1, 2, 3))
+        ro = np.argsort(want["id"])
+        d = np.abs(np.mod(x, L) - np.mod(want["x"][ro], L))
+        err = np.minimum(d, L - d).max()
+        assert err < 1e-4, err
+        assert np.abs(v - want["v"][ro]).max() < 1e-4 * np.abs(want["v"]).max()
+        assert np.abs(pg - want_pgdc[ro]).max() < 1e-4 * np.abs(want_pgdc).max()
+        # the snapshot: same blocks and attributes, same particles once both are ordered by id
+        mine, refd = os.path.join(tmp, "mine"), os.path.join(tmp, "ref")
+        assert sorted(os.listdir(os.path.join(mine, "1"))) == sorted(os.listdir(os.path.join(refd, "1")))
+        assert open(os.path.join(mine, "1", "attr-v2")).read() == open(os.path.join(refd, "1", "attr-v2")).read()
+        rd = lambda top, name, dt, nm: np.fromfile(os.path.join(top, "1", name, "000000"), dtype=dt).reshape(-1, nm)
+        ia, ib = rd(mine, "ID", np.uint64, 1)[:, 0], rd(refd, "ID", np.uint64, 1)[:, 0]
+        assert np.array_equal(np.sort(ia), np.sort(ib)) and len(ia) == nc ** 3
+        oa, ob = np.argsort(ia), np.argsort(ib)
+        dd = np.abs(rd(mine, "Position", np.float32, 3)[oa].astype(np.float64) - rd(refd, "Position", np.float32, 3)[ob])
+        assert np.minimum(dd, L - dd).max() < 1e-4
+        vb = rd(refd, "Velocity", np.float32, 3)[ob]
+        assert np.abs(rd(mine, "Velocity", np.float32, 3)[oa] - vb).max() < 1e-4 * np.abs(vb).max()
+        shutil.rmtree(tmp, ignore_errors=True)
+        print("MP_EXTRAS_OK ranks=%d PGD position error %.3g Mpc/h" % (world, err))
 
 
 if __name__ == "__main__":

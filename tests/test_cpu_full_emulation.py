@@ -105,6 +105,7 @@ def test_four_rank_slab_run_on_the_emulated_library(emul_lib):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
            "--master-port", "29688", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"]
     before = set(os.listdir("/dev/shm"))
-    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MP_EXTRAS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert "MP_GPU_OK ranks=4" in r.stdout, r.stdout[-3000:]
+    assert "MP_EXTRAS_OK ranks=4" in r.stdout, r.stdout[-3000:]          # PGD on several ranks, snapshot written by every rank
     assert not [f for f in set(os.listdir("/dev/shm")) - before if f.startswith("fpm_emul_")]          # the arenas were unlinked
