@@ -65,17 +65,23 @@ def runs(emul_lib, tmp_path_factory):
         "sys.argv = ['bench.py', '--nc', '8', '--steps', '3', '--warmup', '1', '--no-cpu-baseline']\n"
         "runpy.run_path(%r, run_name='__main__')\n" % (ROOT, emul_lib, os.path.join(ROOT, "bench.py")))
     bench = subprocess.Popen([sys.executable, str(script)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    shm_before = set(os.listdir("/dev/shm"))
+    ranks4 = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+                               "--master-port", "29688", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"],
+                              cwd=ROOT, env=dict(os.environ, MP_EXTRAS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     out = {}
     for g, p in procs.items():
         o, _ = p.communicate(timeout=1500)
         out[g] = (p.returncode, o)
     bo, be = bench.communicate(timeout=1500)
     out["bench"] = (bench.returncode, bo, be)
+    ro, _ = ranks4.communicate(timeout=1500)
+    out["ranks4"] = (ranks4.returncode, ro, sorted(f for f in set(os.listdir("/dev/shm")) - shm_before if f.startswith("fpm_emul_")))
     return out
 
 
 def test_gpu_cases_on_the_emulated_library(runs):
-    failed = [(g, r[1][-3000:]) for g, r in runs.items() if g != "bench" and r[0] != 0]
+    failed = [(g, r[1][-3000:]) for g, r in runs.items() if g not in ("bench", "ranks4") and r[0] != 0]
     assert not failed, "\n\n".join("%s\n%s" % (g, o) for g, o in failed)
 
 
@@ -97,15 +103,13 @@ def test_bench_contract_on_the_emulated_library(runs):
         assert key in line["roofline"], key
 
 
-def test_four_rank_slab_run_on_the_emulated_library(emul_lib):
+def test_four_rank_slab_run_on_the_emulated_library(runs):
     """The x-slab run of tests/mp_worker.py ("gpu" mode on 2 and 8 B200s) with FOUR ranks -- a count no hardware run of this round
     covered -- as four processes on the emulated library: symmetric arenas in POSIX shared memory mapped through the stand-in CUDA
     IPC, the cross-GPU barrier kernel spinning on flags in the peers' memory, staged slab transposes, halo planes, particle
-    migration; rank 0 gathers the particles and checks them against the reference fixture."""
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
-           "--master-port", "29688", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"]
-    before = set(os.listdir("/dev/shm"))
-    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MP_EXTRAS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert "MP_GPU_OK ranks=4" in r.stdout, r.stdout[-3000:]
-    assert "MP_EXTRAS_OK ranks=4" in r.stdout, r.stdout[-3000:]          # PGD on several ranks, snapshot written by every rank
-    assert not [f for f in set(os.listdir("/dev/shm")) - before if f.startswith("fpm_emul_")]          # the arenas were unlinked
+    migration; rank 0 gathers the particles and checks them against the reference fixture.  Then (MP_EXTRAS) the PGD correction on
+    four slabs against the oracle and a snapshot written by every rank from its own columns."""
+    rc, stdout, leftover = runs["ranks4"]
+    assert "MP_GPU_OK ranks=4" in stdout, stdout[-3000:]
+    assert "MP_EXTRAS_OK ranks=4" in stdout, stdout[-3000:]
+    assert not leftover                                                   # the shared-memory arenas were unlinked
