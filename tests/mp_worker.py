@@ -204,7 +204,30 @@ def extras(rank, world):
         vb = rd(refd, "Velocity", np.float32, 3)[ob]
         assert np.abs(rd(mine, "Velocity", np.float32, 3)[oa] - vb).max() < 1e-4 * np.abs(vb).max()
         shutil.rmtree(tmp, ignore_errors=True)
-        print("MP_EXTRAS_OK ranks=%d PGD position error %.3g Mpc/h" % (world, err))
+    # row N1 on several ranks: the device IC chain (every rank fills its ky-slab of the white noise) against the reference's
+    kw = dict(nc=nc, boxsize=64.0, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM")
+    pk_path = os.path.join(ROOT, "tests", "golden", "powerspec.txt")
+    tab = np.loadtxt(pk_path)
+    g = Solver(np_alloc_factor=3.0, **kw)
+    g.setup_ic(2024, tab[:, 0], tab[:, 1], 0.1, remove_variance=True)
+    out = [None] * world
+    dist.all_gather_object(out, (g.get_column("id"), g.get_column("x"), g.get_column("dx1"), g.get_column("dx2")))
+    g.close()
+    if rank == 0:
+        s = ref.Session(np_alloc_factor=2.0, **kw)
+        dk, _, _ = s.ic_deltak(2024, open(pk_path).read(), remove_variance=True)
+        s.setup_lpt(dk, 0.1)
+        w = s.get_particles()
+        s.close()
+        ids = np.concatenate([o[0] for o in out])
+        assert np.array_equal(np.sort(ids), np.sort(w["id"]))
+        order, ro = np.argsort(ids), np.argsort(w["id"])
+        x, d1, d2 = (np.concatenate([o[i] for o in out])[order] for i in (1, 2, 3))
+        dd = np.abs(x - w["x"][ro])
+        ic_err = np.minimum(dd, 64.0 - dd).max()
+        assert ic_err < 1e-5, ic_err
+        assert np.abs(d1 - w["dx1"][ro]).max() < 1e-5 * np.abs(w["dx1"]).max() and np.abs(d2 - w["dx2"][ro]).max() < 1e-4 * np.abs(w["dx2"]).max()
+        print("MP_EXTRAS_OK ranks=%d PGD position error %.3g Mpc/h, IC position error %.3g Mpc/h" % (world, err, ic_err))
 
 
 if __name__ == "__main__":
