@@ -350,6 +350,13 @@ static void meta_attrs(BfBlock *b, FpmIoMeta *m, int writing)
 
 int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
                                  const FpmIoMeta *meta, MPI_Comm comm)
+{ return fastpm_b200_io_write_columns_at(filebase, dataset, cols, ncols, np_local, meta, NULL, comm); }
+
+/* positions == NULL: the ranks' slices one after the other.  Otherwise item i of this rank goes to row positions[i] of the block
+ * (ascending; the positions of all ranks together are 0 .. total-1): how a catalog sorted by a dense particle id is written
+ * without moving particles between the GPUs -- runs of consecutive positions go out as one write each. */
+int fastpm_b200_io_write_columns_at(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
+                                    const FpmIoMeta *meta, const uint64_t *positions, MPI_Comm comm)
 {
     int64_t total = 0;
     const size_t first = rank_offset(np_local, comm, &total);
@@ -377,7 +384,14 @@ int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, cons
             const char *src = (const char *) col->data + i0 * isz_in;
             if (col->on_device) rc = fpm_memcpy_d2h(raw, src, n * isz_in); else memcpy(raw, src, n * isz_in);
             if (!rc) rc = convert_items(out, col->dtype_out, raw, col->dtype, n * col->nmemb);
-            if (!rc) rc = bf_rw(&b, first + i0, n, out, 1);
+            if (!rc && !positions) rc = bf_rw(&b, first + i0, n, out, 1);
+            for (size_t a = 0; positions && a < n && !rc; ) {
+                size_t e = a + 1;
+                while (e < n && positions[i0 + e] == positions[i0 + e - 1] + 1) e++;
+                if (positions[i0 + e - 1] >= (uint64_t) total) { rc = -1; break; }
+                rc = bf_rw(&b, (size_t) positions[i0 + a], e - a, (char *) out + a * isz_out, 1);
+                a = e;
+            }
         }
         free(raw); free(out);
         if (bf_close(&b, comm) || rc) return -1;
@@ -423,6 +437,9 @@ int fastpm_b200_io_read_columns(const char *filebase, const char *dataset, const
     return 0;
 }
 
+/* set by fastpm_sort_snapshot on several ranks, consumed by the next fastpm_store_write of the same columns */
+static struct { void *ids; size_t np; } sorted_by_dense_id;
+
 /* the column table of fastpm_store_write, io.c:392-421 */
 static const struct { const char *name, *dtype_out; FastPMColumnTags attribute; } BLOCKS[] = {
     { "Position", "f4", COLUMN_POS }, { "InitialPosition", "f4", COLUMN_Q }, { "DX1", "f4", COLUMN_DX1 }, { "DX2", "f4", COLUMN_DX2 },
@@ -461,8 +478,16 @@ int fastpm_store_write(FastPMStore *p, const char *filebase, const char *modestr
         fastpm_info("Writing a catalog to %s [%s]\n", filebase, p->name);
         const int n = store_columns(p, cols);
         meta_of(p, &m);
-        if (fastpm_b200_io_write_columns(filebase, p->name, cols, n, (int64_t) p->np, &m, comm))
-            fastpm_raise(-1, "Failed to write the catalog %s [%s]: %s\n", filebase, p->name, strerror(errno));
+        uint64_t *positions = NULL;
+        if (sorted_by_dense_id.ids == (void *) p->id && sorted_by_dense_id.np == p->np && p->id) {
+            /* fastpm_sort_snapshot on several ranks (below): row i belongs at file position id[i] */
+            positions = malloc(sizeof(uint64_t) * (p->np ? p->np : 1));
+            FPM_MUST(fpm_memcpy_d2h(positions, p->id, sizeof(uint64_t) * p->np));
+        }
+        sorted_by_dense_id.ids = NULL;
+        const int rc = fastpm_b200_io_write_columns_at(filebase, p->name, cols, n, (int64_t) p->np, &m, positions, comm);
+        free(positions);
+        if (rc) fastpm_raise(-1, "Failed to write the catalog %s [%s]: %s\n", filebase, p->name, strerror(errno));
         return 0;
     }
     if (!strcmp(modestr, "r")) {
@@ -670,13 +695,24 @@ void fastpm_sort_snapshot(FastPMStore *p, MPI_Comm comm, FastPMSnapshotSorter so
 {
     (void) redistribute;
     if (sorter != FastPMSnapshotSortByID) fastpm_raise(-1, "fastpm_b200: fastpm_sort_snapshot sorts by particle id only\n");
-    if (fpm_comm_size(comm) > 1) fastpm_raise(-1, "fastpm_b200: the distributed snapshot sort is not implemented; write with sort_snapshot = false\n");
     if (!p->id) fastpm_raise(-1, "fastpm_sort_snapshot: the store has no id column\n");
     fpm_store_flush(p);
     const size_t n = p->np;
     uint64_t *key = malloc(sizeof(uint64_t) * (n ? n : 1)), *perm = malloc(sizeof(uint64_t) * (n ? n : 1));
     FPM_MUST(fpm_memcpy_d2h(key, p->id, sizeof(uint64_t) * n));
     fastpm_b200_io_argsort_u64(key, n, perm);
+    sorted_by_dense_id.ids = NULL;
+    if (fpm_comm_size(comm) > 1) {
+        /* Several ranks: the particles stay where they are (sorted locally); the catalog comes out globally sorted because
+         * fastpm_store_write then puts every row at the file position given by its id.  That needs the ids of all ranks together
+         * to be exactly 0 .. N-1 -- what fastpm_store_fill assigns and nothing on this path changes (no sub-sampling). */
+        int64_t lo = n ? (int64_t) key[perm[0]] : INT64_MAX, hi = n ? (int64_t) key[perm[n - 1]] : -1, cnt = (int64_t) n;
+        fpm_comm_allreduce_i64(comm, &lo, 1, 1); fpm_comm_allreduce_i64(comm, &hi, 1, 2); fpm_comm_allreduce_i64(comm, &cnt, 1, 0);
+        if (lo != 0 || hi != cnt - 1)
+            fastpm_raise(-1, "fastpm_b200: the distributed snapshot sort needs dense particle ids 0 .. N-1 (found %ld .. %ld for %ld particles)\n",
+                         (long) lo, (long) hi, (long) cnt);
+        sorted_by_dense_id.ids = (void *) p->id; sorted_by_dense_id.np = n;
+    }
     free(key);
     for (int ci = 0; ci < 32; ci++) {
         if (!p->columns[ci]) continue;

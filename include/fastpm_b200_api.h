@@ -547,8 +547,8 @@ void fastpm_path_ensure_dirname(const char *path);
 int read_funck(FastPMFuncK *fk, const char filename[], MPI_Comm comm);                                    /* io.h */
 
 /* ------------------------------------------------------------------ [io.h] snapshot / mesh files (bigfile directories)
- * Same names, arguments and on-disk result as libfastpmio/io.c; append mode, the distributed sort and the healpix / light-cone
- * writers are not implemented and raise. */
+ * Same names, arguments and on-disk result as libfastpmio/io.c; append mode and the healpix / light-cone writers are not implemented and raise; on several ranks the sort by id
+ * keeps the particles in place and writes every row at the file position its (dense) id gives. */
 typedef void (*FastPMSnapshotSorter)(const void *ptr, void *radix, void *arg);
 void FastPMSnapshotSortByID(const void *ptr, void *radix, void *arg);
 void fastpm_sort_snapshot(FastPMStore *p, MPI_Comm comm, FastPMSnapshotSorter sorter, int redistribute);     /* io.h:19 */
@@ -568,6 +568,8 @@ typedef struct {
 } FpmIoHeader;
 int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
                                  const FpmIoMeta *meta, MPI_Comm comm);
+int fastpm_b200_io_write_columns_at(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
+                                    const FpmIoMeta *meta, const uint64_t *positions, MPI_Comm comm);     /* rows at given file positions */
 int fastpm_b200_io_read_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t *np_local,
                                 FpmIoMeta *meta, MPI_Comm comm);
 int fastpm_b200_io_write_header(const char *filebase, const FpmIoHeader *h, MPI_Comm comm);

@@ -178,6 +178,7 @@ def extras(rank, world):
     g.setup_lpt(dk, steps[0])
     g.evolve(steps)
     g.write_snapshot(os.path.join(tmp, "mine"))
+    g.write_snapshot(os.path.join(tmp, "mine_sorted"), sort_by_id=True)      # every row at the file position its id gives
     out = [None] * world
     dist.all_gather_object(out, (g.get_column("id"), g.get_column("x"), g.get_column("v"), g.get_column("pgdc")))
     g.close()
@@ -203,6 +204,14 @@ def extras(rank, world):
         assert np.minimum(dd, L - dd).max() < 1e-4
         vb = rd(refd, "Velocity", np.float32, 3)[ob]
         assert np.abs(rd(mine, "Velocity", np.float32, 3)[oa] - vb).max() < 1e-4 * np.abs(vb).max()
+        # sorted by id on several ranks == the one-rank reference file row by row (its store is still in id order)
+        srt = os.path.join(tmp, "mine_sorted")
+        assert np.array_equal(ib, np.arange(nc ** 3, dtype=np.uint64))
+        assert open(os.path.join(srt, "1", "ID", "000000"), "rb").read() == open(os.path.join(refd, "1", "ID", "000000"), "rb").read()
+        assert open(os.path.join(srt, "1", "ID", "header")).read() == open(os.path.join(refd, "1", "ID", "header")).read()
+        dd = np.abs(rd(srt, "Position", np.float32, 3).astype(np.float64) - rd(refd, "Position", np.float32, 3))
+        assert np.minimum(dd, L - dd).max() < 1e-4
+        assert np.abs(rd(srt, "Velocity", np.float32, 3) - rd(refd, "Velocity", np.float32, 3)).max() < 1e-4 * np.abs(vb).max()
         shutil.rmtree(tmp, ignore_errors=True)
     # row N1 on several ranks: the device IC chain (every rank fills its ky-slab of the white noise) against the reference's
     kw = dict(nc=nc, boxsize=64.0, pm_nc_factor=2, force_mode="cola", growth_mode="LCDM")
