@@ -5,8 +5,8 @@
 
 Workload (BASELINE.json): nc^3 particles on a (2 nc)^3 force mesh, COLA, K PM steps
 (time_step = linspace(0.1, 1, K): K force evaluations and K-1 kick-drift-kick cycles, the reference's own
-meaning of "K steps", tests/standard.lua:19-22), synthetic 2LPT initial conditions at a = 0.1 from the
-reference's linear P(k) table, P(k) handler on (one measurement + device->host read per force evaluation).
+meaning of "K steps", tests/standard.lua:19-22), synthetic 2LPT initial conditions at a = 0.1 (the reference's Gadget-scheme
+white noise for seed 100 coloured by the reference's linear P(k) table, generated on the device), P(k) handler on (one measurement + device->host read per force evaluation).
 
 metric  particles/s = nc^3 * K / t_evolve   (src/fastpm.c:368-370 times exactly fastpm_solver_evolve)
 value   t_evolve measured with CUDA events around fastpm_solver_evolve, particle state resident in HBM
@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pm_step_particles_per_second"
 UNIT = "particles/s"
-KCLASSES = ["paint", "readout", "fft_tile", "fft_z", "kick", "drift", "kspace", "pk", "summary", "other"]
+KCLASSES = ["paint", "readout", "fft_tile", "fft_z", "kick", "drift", "kspace", "pk", "summary", "other",
+            "memset", "barrier", "halo", "migrate", "push"]
 
 
 def read_pk():
@@ -111,9 +112,36 @@ def cpu_reference_run(nc, B, mode, K, W, threads):
     if W >= 2:
         s.evolve(ts[:W])
         s.set_particles(p0["x"], v=p0["v"], id=p0["id"], dx1=p0.get("dx1"), dx2=p0.get("dx2"), meta=p0["meta"])
+    c0 = ref.clock_table()
     t = s.evolve(ts)
+    c1 = ref.clock_table()
+    p1 = s.get_particles()
+    recs = s.records()
     s.close()
-    return dict(value=nc ** 3 * K / t, seconds=t, np=nc ** 3)
+    # the reference's own named clocks over the timed evolve (fastpm_clock_stat, prof.c:144)
+    phases = {}
+    for key, val in c1.items():
+        d = val - c0.get(key, 0.0)
+        if d > 0:
+            phases[key.split(":")[1]] = round(phases.get(key.split(":")[1], 0.0) + d, 2)
+    return dict(value=nc ** 3 * K / t, seconds=t, np=nc ** 3, phases=phases,
+                pk_bins=[float(v) for v in recs[-1]["p"][:8]] if recs else None,
+                x_checksum=position_checksum(p1["x"], p1["id"], float(nc)))
+
+
+def position_checksum(x, ids, L):
+    """Order-independent fingerprint of a particle set: sum_i w(id_i) * (x_i mod L) per component with w in (0, 1] a fixed hash
+    of the id.  Any decomposition (1, 2, 4, 8 slabs) of the same run gives the same three numbers up to float summation order."""
+    import numpy as np
+    tot = np.zeros(3)
+    n = len(ids)
+    step = 1 << 24
+    xs = np.asarray(x).reshape(-1, 3)
+    for i in range(0, n, step):
+        w = ((np.asarray(ids[i:i + step], dtype=np.uint64) * np.uint64(2654435761)) % np.uint64(1 << 20)).astype(np.float64)
+        w = (w + 1.0) / float(1 << 20)
+        tot += (np.mod(xs[i:i + step], L) * w[:, None]).sum(axis=0)
+    return [float(v) for v in tot]
 
 
 def run_reference_arm(args):
@@ -121,19 +149,23 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    nc_s = args.ref_nc
+    nc_s = args.ref_nc if args.ref_nc > 0 else 256     # C1 (nc = 256, 512^3 mesh) is the CPU-runnable case
     r = cpu_reference_run(nc_s, args.pm_nc_factor, args.mode, args.steps, args.warmup, threads)
     if r is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref/libfastpm_ref.so is not built"})
         return 0
-    sample = "nc=%d^3 particles, %d^3 mesh, %s, %d steps (bounded sample of the nc=%d workload)" % (
-        nc_s, nc_s * args.pm_nc_factor, args.mode, args.steps, args.nc)
+    sample = "nc=%d^3 particles, %d^3 mesh, %s, %d steps: the reference's own sources (oracle/_ref, shimmed FFT/GSL/MPI), 1 rank x %d threads; a bounded sample of the nc=%d workload of the GPU arm" % (
+        nc_s, nc_s * args.pm_nc_factor, args.mode, args.steps, threads, args.nc)
+    ran = argparse.Namespace(**vars(args))
+    ran.nc = nc_s                                       # `config` describes what this arm RAN, not what the GPU arm runs
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 mesh / f64 positions", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "config": dict(workload_config(ran), gpu_arm_nc=args.nc, note="CPU arm: bounded sample at nc=%d, the GPU arm runs nc=%d" % (nc_s, args.nc)),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                         "phase_seconds": r["phases"]},
+        "pk_bins": r["pk_bins"], "x_checksum": r["x_checksum"],
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -173,6 +205,20 @@ def workload_config(args):
             4.0 * (args.nc * args.pm_nc_factor) ** 2 * (args.nc * args.pm_nc_factor + 2) / 1e9)}
 
 
+IC_SEED = 100
+
+
+def setup_ic(g, k_tab, p_tab, a0):
+    """The reference's own initial conditions for seed 100 (Gadget-scheme RANLUX white noise coloured by the P(k) table, 2LPT at a0:
+    src/fastpm.c:415-545), generated on the device -- the same particles the reference arm starts from at equal nc.
+    FASTPM_B200_BENCH_IC=philox selects the counter-based white noise of round 1 instead (not comparable with the reference)."""
+    if os.environ.get("FASTPM_B200_BENCH_IC", "gadget") == "philox":
+        g.setup_synthetic_ic(IC_SEED, k_tab, p_tab, a0)
+        return "philox"
+    g.setup_ic(IC_SEED, k_tab, p_tab, a0)
+    return "gadget"
+
+
 def run_ours(args):
     import ctypes as C
     import numpy as np
@@ -191,7 +237,7 @@ def run_ours(args):
     ts = np.linspace(0.1, 1.0, K)
 
     g = Solver(nc=nc, boxsize=float(nc), pm_nc_factor=B, force_mode=args.mode, growth_mode="LCDM", np_alloc_factor=1.0)
-    g.setup_synthetic_ic(100, k_tab, p_tab, ts[0])
+    setup_ic(g, k_tab, p_tab, ts[0])
     meta0 = g.meta
     cola = args.mode == "cola"
     cols_in = ["x", "v", "id"] + (["dx1", "dx2"] if cola else [])
@@ -297,15 +343,19 @@ def run_ours(args):
                 "transforms": n_transforms},
         "stages": stages, "last_step_launches": trace,
         "evolve_wall_s": round(t_wall, 4), "result_finite": finite,
-        "pk_last_bin0": float(spectra[-1][1][0]) if spectra else None,
+        "pk_bins": [float(v) for v in spectra[-1][1][:8]] if spectra else None,
+        "x_checksum": position_checksum(host["x"][1], host["id"][1], float(nc)),
+        "np_total_after": int(g.np),
     }
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        r = cpu_reference_run(args.ref_nc, B, args.mode, min(K, args.ref_steps), 0, threads)
+        ref_nc = args.ref_nc if args.ref_nc > 0 else 128
+        r = cpu_reference_run(ref_nc, B, args.mode, min(K, args.ref_steps), 0, threads)
         if r is not None:
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
                                     "sample": "reference sources (oracle/_ref, shimmed FFT/GSL/MPI), 1 rank x %d threads: nc=%d^3, %d^3 mesh, %s, %d steps, %.1f s" % (
-                                        threads, args.ref_nc, args.ref_nc * B, args.mode, min(K, args.ref_steps), r["seconds"])}
+                                        threads, ref_nc, ref_nc * B, args.mode, min(K, args.ref_steps), r["seconds"]),
+                                    "phase_seconds": r["phases"]}
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref not built"}
     if rank == 0:
@@ -344,7 +394,7 @@ def main():
                     help="particles per side; 0 = BASELINE.json's nc=1024 (2048^3 mesh) when device and host memory allow, else 512")
     ap.add_argument("--pm-nc-factor", type=int, default=2)
     ap.add_argument("--mode", default="cola", choices=["cola", "pm", "fastpm"])
-    ap.add_argument("--ref-nc", type=int, default=128, help="particle grid of the bounded CPU sample")
+    ap.add_argument("--ref-nc", type=int, default=0, help="particle grid of the bounded CPU sample; 0 = 256 (BASELINE C1) for --impl reference, 128 for the cpu_baseline object of the GPU arm")
     ap.add_argument("--ref-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -9,6 +9,7 @@
 #include <vector>
 
 unsigned long long fpm_launch_counter = 0;
+unsigned long long fpm_path_counter[FPM_PATH_COUNT] = { 0 };
 int fpm_debug_sync = 0;
 
 // ------------------------------------------------------------------ per-class event timing (common.cuh)
@@ -218,7 +219,11 @@ int fpm_memset(void *dst, int value, size_t bytes)
     if ((const char *) dst == g_lazy_buf && bytes >= g_lazy_bytes) { g_lazy_buf = NULL; g_lazy_mesh = NULL; g_lazy_bytes = 0; }
     else if (fpm_lazy_touch(dst, bytes)) return -1;
     if (ensure_init()) return -1;
+    // large clears (pm_clear of a mesh) are a sweep like any kernel: timed under their own class
+    const bool timed = fpm_prof_on && bytes >= ((size_t) 1 << 20);
+    if (timed) fpm_prof_begin(FPM_K_MEMSET, g_stream);
     FPM_CUDA_OK(cudaMemsetAsync(dst, value, bytes, g_stream));
+    if (timed) fpm_prof_end(FPM_K_MEMSET, g_stream);
     return 0;
 }
 int fpm_sync(void)
@@ -257,6 +262,11 @@ void fpm_timer_destroy(void *timer)
     delete t;
 }
 uint64_t fpm_kernel_launch_count(void) { return fpm_launch_counter; }
+int fpm_path_counts(uint64_t *out, int n)
+{
+    for (int i = 0; i < n; i++) out[i] = i < FPM_PATH_COUNT ? fpm_path_counter[i] : 0;
+    return FPM_PATH_COUNT;
+}
 
 int fpm_prof_enable(int on) { fpm_prof_on = on; return 0; }
 int fpm_prof_reset(void) { g_prof_used = 0; g_prof_open = -1; return 0; }

@@ -116,7 +116,7 @@ int fpm_xbarrier_on(cudaStream_t st)
 {
     if (g_bar.nranks <= 1) return 0;
     g_bar.epoch++;
-    xbarrier_kernel<<<1, 32, 0, st>>>(g_peer_flags_dev, g_bar.flags, g_bar.rank, g_bar.nranks, g_bar.epoch);
+    FPM_TIMED(FPM_K_BARRIER, st, (xbarrier_kernel<<<1, 32, 0, st>>>(g_peer_flags_dev, g_bar.flags, g_bar.rank, g_bar.nranks, g_bar.epoch)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -174,7 +174,7 @@ extern "C" int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const f
     const size_t plane = (size_t) g.n * g.pitch_r;
     cudaStream_t st = comm_stream();
     if (fpm_xbarrier_on(st)) return -1;
-    halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local, canvas_prev_rank + (size_t) g.nxl * plane, plane / 4);
+    FPM_TIMED(FPM_K_HALO, st, (halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local, canvas_prev_rank + (size_t) g.nxl * plane, plane / 4)));
     FPM_CHECK_LAUNCH();
     if (fpm_xbarrier_on(st)) return -1;
     return 0;
@@ -190,7 +190,9 @@ extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const
     const size_t plane = (size_t) g.n * g.pitch_r;
     cudaStream_t st = comm_stream();
     if (fpm_xbarrier_on(st)) return -1;
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_HALO, st);
     FPM_CUDA_OK(cudaMemcpyAsync(canvas_local + (size_t) g.nxl * plane, canvas_next_rank, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (fpm_prof_on) fpm_prof_end(FPM_K_HALO, st);
     if (fpm_xbarrier_on(st)) return -1;
     return 0;
 }
@@ -315,7 +317,7 @@ extern "C" int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, in
     if (np > 0) {
         int *bad = wrap ? fpm_wrap_flag_device() : NULL;
         if (wrap && !bad) { fpm_set_error("migrate: no wrap flag"); return -1; }
-        classify_kernel<<<148 * 8, 256, 0, st>>>(m->geom, x, np, g_mig.d_send_count, g_mig.d_send_idx, g_mig.cap, g_mig.d_leaver, g_mig.d_overflow, bad);
+        FPM_TIMED(FPM_K_MIGRATE, st, (classify_kernel<<<148 * 8, 256, 0, st>>>(m->geom, x, np, g_mig.d_send_count, g_mig.d_send_idx, g_mig.cap, g_mig.d_leaver, g_mig.d_overflow, bad)));
         FPM_CHECK_LAUNCH();
         if (wrap && fpm_wrap_flag_fetch()) return -1;
     }
@@ -337,7 +339,7 @@ extern "C" int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int e
         const int cnt = send_count_host[d];
         if (d == m->geom.rank || cnt == 0) continue;
         unsigned char *dst = g_mig.d_pack + (size_t) d * g_mig.pack_bytes_per_dest + col_off_bytes * g_mig.cap;
-        pack_kernel<<<64, 256, 0, st>>>(g_mig.d_send_idx + (size_t) d * g_mig.cap, cnt, (const unsigned int *) col, (unsigned int *) dst, words);
+        FPM_TIMED(FPM_K_MIGRATE, st, (pack_kernel<<<64, 256, 0, st>>>(g_mig.d_send_idx + (size_t) d * g_mig.cap, cnt, (const unsigned int *) col, (unsigned int *) dst, words)));
         FPM_CHECK_LAUNCH();
     }
     return 0;
@@ -349,7 +351,7 @@ extern "C" int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host)
     cudaStream_t st = comm_stream();
     FPM_CUDA_OK(cudaMemsetAsync(g_mig.d_counters, 0, sizeof(int) * 2, st));
     if (np > 0) {
-        holes_kernel<<<148 * 8, 256, 0, st>>>(g_mig.d_leaver, np, np_stay, g_mig.d_holes, g_mig.d_movers, g_mig.d_counters);
+        FPM_TIMED(FPM_K_MIGRATE, st, (holes_kernel<<<148 * 8, 256, 0, st>>>(g_mig.d_leaver, np, np_stay, g_mig.d_holes, g_mig.d_movers, g_mig.d_counters)));
         FPM_CHECK_LAUNCH();
     }
     int c[2];
@@ -363,7 +365,7 @@ extern "C" int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host)
 extern "C" int fpm_migrate_fill_column(void *col, int elsize, int nholes)
 {
     if (nholes <= 0) return 0;
-    fill_kernel<<<64, 256, 0, comm_stream()>>>(g_mig.d_holes, g_mig.d_movers, nholes, (unsigned int *) col, elsize / 4);
+    FPM_TIMED(FPM_K_MIGRATE, comm_stream(), (fill_kernel<<<64, 256, 0, comm_stream()>>>(g_mig.d_holes, g_mig.d_movers, nholes, (unsigned int *) col, elsize / 4)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -373,6 +375,8 @@ extern "C" int fpm_migrate_append_column(void *col, int elsize, int64_t at, cons
 {
     if (count <= 0) return 0;
     const unsigned char *src = (const unsigned char *) peer_pack_base + (size_t) my_rank * g_mig.pack_bytes_per_dest + col_off_bytes * g_mig.cap;
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_MIGRATE, comm_stream());
     FPM_CUDA_OK(cudaMemcpyAsync((unsigned char *) col + (size_t) at * elsize, src, (size_t) count * elsize, cudaMemcpyDeviceToDevice, comm_stream()));
+    if (fpm_prof_on) fpm_prof_end(FPM_K_MIGRATE, comm_stream());
     return 0;
 }

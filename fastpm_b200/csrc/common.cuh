@@ -47,8 +47,16 @@ extern int fpm_debug_sync;                          // FASTPM_B200_DEBUG_SYNC=1:
 // the launching stream; fpm_prof_get sums the elapsed times per class.  bench.py uses it for the roofline line.
 enum FpmKernelClass {
     FPM_K_PAINT = 0, FPM_K_READOUT, FPM_K_FFT_TILE, FPM_K_FFT_Z, FPM_K_KICK, FPM_K_DRIFT, FPM_K_KSPACE,
-    FPM_K_PK, FPM_K_SUMMARY, FPM_K_OTHER, FPM_K_COUNT
+    FPM_K_PK, FPM_K_SUMMARY, FPM_K_OTHER,
+    // round 2: what used to hide between the classes above on several GPUs
+    FPM_K_MEMSET, FPM_K_BARRIER, FPM_K_HALO, FPM_K_MIGRATE, FPM_K_PUSH, FPM_K_COUNT
 };
+// which code path served a launch (tests assert that the benched kernels are the ones a parity run went through)
+enum FpmPathCounter {
+    FPM_PATH_FFT_TMA = 0, FPM_PATH_FFT_TILE_GENERIC, FPM_PATH_FFT_ZROW, FPM_PATH_FFT_Z_GENERIC, FPM_PATH_FFT_TMA_MULTI,
+    FPM_PATH_PAINT_BRICKS, FPM_PATH_READOUT_BRICKS, FPM_PATH_PK_FUSED, FPM_PATH_STAGED_TRANSPOSE, FPM_PATH_COUNT
+};
+extern unsigned long long fpm_path_counter[FPM_PATH_COUNT];
 extern int fpm_prof_on;
 void fpm_prof_begin(int cls, cudaStream_t st);
 void fpm_prof_end(int cls, cudaStream_t st);

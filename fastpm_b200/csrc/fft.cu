@@ -280,6 +280,7 @@ static int launch_tile(const FpmFftPlan *p, const TilePassArgs &a, int nouter, c
         return fpm_fft_tma_pass_from_tile(p->n, a, p->pitch_c, nouter, st);
     const unsigned grid = (unsigned) ((size_t) nouter * a.ntile_k);
     if (grid == 0) return 0;
+    fpm_path_counter[FPM_PATH_FFT_TILE_GENERIC]++;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_TILE, st);
     if (p->K == 16) fft_tile_kernel<16><<<grid, p->thr_tile, p->smem_tile, st>>>(a);
     else if (p->K == 8) fft_tile_kernel<8><<<grid, p->thr_tile, p->smem_tile, st>>>(a);
@@ -299,6 +300,7 @@ static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaSt
         return fpm_fft_zrow_pass(p->n, a.src, a.dst, a.nrows, a.pitch_c, a.scale, a.th.tw, a.twN, forward, st);
     const unsigned grid = (unsigned) ((a.nrows + p->R - 1) / p->R);
     if (grid == 0) return 0;
+    fpm_path_counter[FPM_PATH_FFT_Z_GENERIC]++;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_Z, st);
     if (p->R == 16) {
         if (forward) fft_zfwd_kernel<16><<<grid, p->thr_z, p->smem_z, st>>>(a); else fft_zbwd_kernel<16><<<grid, p->thr_z, p->smem_z, st>>>(a);
@@ -328,6 +330,7 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
         for (int i = 0; i < 8; i++) FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_chunk[i], cudaEventDisableTiming));
         FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
     }
+    fpm_path_counter[FPM_PATH_STAGED_TRANSPOSE]++;
     float2 *stage = reinterpret_cast<float2 *>(m->stage);
     const size_t blk = (size_t) per * nouter * pc;          // one destination's block: [per rows][nouter planes][pitch_c]
     // my own rows keep the direct destination the caller set up (final layout); everybody else's go to their staging block
@@ -357,7 +360,10 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
         }
     }
     FPM_CUDA_OK(cudaEventRecord(g_ev_done, g_copy_stream));
+    // the exposed tail of the pushes: time between the last chunk's kernel and the arrival of the last copy, on the compute stream
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_PUSH, st);
     FPM_CUDA_OK(cudaStreamWaitEvent(st, g_ev_done, 0));
+    if (fpm_prof_on) fpm_prof_end(FPM_K_PUSH, st);
     return 0;
 }
 

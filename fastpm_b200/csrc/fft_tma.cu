@@ -240,6 +240,7 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
     const int per_sm = (C::T * K <= 512) ? 2 : 1;
     const int grid = ntiles < nsm * per_sm ? ntiles : nsm * per_sm;
     if (grid <= 0) return 0;
+    fpm_path_counter[a.rows_per_rank == C::N ? FPM_PATH_FFT_TMA : FPM_PATH_FFT_TMA_MULTI]++;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_TILE, st);
     if (a.rows_per_rank == C::N) fft_tma_kernel<R1, R2, R3, K, false><<<grid, C::T * K, smem, st>>>(tmap, a);
     else fft_tma_kernel<R1, R2, R3, K, true><<<grid, C::T * K, smem, st>>>(tmap, a);

@@ -178,6 +178,7 @@ static int launch_zrow(const ZRowArgs &a, int forward, cudaStream_t st)
     const size_t resident = (size_t) zrow_sm_count() * MINB;
     const unsigned grid = (unsigned) (ntiles < resident ? ntiles : resident);
     if (grid == 0) return 0;
+    fpm_path_counter[FPM_PATH_FFT_ZROW]++;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_FFT_Z, st);
     if (forward) fft_zrow_kernel<R1, R2, R3, true, PREFETCH, MINB><<<grid, C::T * 8, smem, st>>>(a);
     else fft_zrow_kernel<R1, R2, R3, false, PREFETCH, MINB><<<grid, C::T * 8, smem, st>>>(a);

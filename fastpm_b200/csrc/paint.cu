@@ -337,6 +337,7 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
     int lag_nc = 0;
     const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
     #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick)
+    if (nbrick > 0) fpm_path_counter[FPM_PATH_PAINT_BRICKS]++;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_PAINT, st);
     if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
     else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
@@ -353,6 +354,7 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
     const unsigned grid = (unsigned) ((np + 255) / 256);
     int lag_nc = 0;
     const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
+    if (nbrick > 0) fpm_path_counter[FPM_PATH_READOUT_BRICKS]++;
     FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick)));
     FPM_CHECK_LAUNCH();
     return 0;
@@ -407,7 +409,7 @@ int fpm_window_readout_launch(const FpmMesh *m, int type, int support, const flo
 
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st)
 {
-    FPM_TIMED(FPM_K_OTHER, st, (plane_add_kernel<<<148 * 8, 256, 0, st>>>(dst, src, nfloats)));
+    FPM_TIMED(FPM_K_HALO, st, (plane_add_kernel<<<148 * 8, 256, 0, st>>>(dst, src, nfloats)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -78,7 +78,7 @@ def bench_main(args):
     ts = np.linspace(0.1, 1.0, K)
     alloc = float(os.environ.get("FASTPM_B200_ALLOC_FACTOR", "1.25"))
     g = Solver(nc=nc, boxsize=float(nc), pm_nc_factor=Bf, force_mode=args.mode, growth_mode="LCDM", np_alloc_factor=alloc)
-    g.setup_synthetic_ic(100, k_tab, p_tab, ts[0])
+    B.setup_ic(g, k_tab, p_tab, ts[0])
     meta0 = g.meta
     np0 = g.np
     cola = args.mode == "cola"
@@ -164,6 +164,11 @@ def bench_main(args):
     finite = bool(np.isfinite(xh[:: max(1, xh.size // 100000)]).all())
     fin = torch.tensor([1 if finite else 0], dtype=torch.int64, device="cuda")
     dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    # the same fingerprints the one-GPU line prints: P(k) bins of the last step (already reduced over ranks by the library) and the
+    # id-weighted position checksum, summed over the slabs
+    idh = np.ctypeslib.as_array(C.cast(host["id"], C.POINTER(C.c_uint64)), (n_local,))
+    chk = torch.tensor(B.position_checksum(xh, idh, float(nc)), dtype=torch.float64, device="cuda")
+    dist.all_reduce(chk)
 
     S_local = 4.0 * N * N * (N + 2) / world
     peak, peak_src = B.measured_peak()
@@ -189,7 +194,8 @@ def bench_main(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": round(avg_ms, 4)},
         "fft": {"gbs_6S_per_gpu": round(6 * S_local / (t_tr * 1e-3) / 1e9, 1) if t_tr > 0 else 0.0, "ms_per_transform": round(t_tr, 4), "transforms": ntr},
         "stages_rank0": stages, "np_total_after": int(np_local.item()), "result_finite": bool(fin.item() == 1),
-        "pk_last_bin1": float(spectra[-1][1][1]) if spectra else None,
+        "pk_bins": [float(v) for v in spectra[-1][1][:8]] if spectra else None,
+        "x_checksum": [float(v) for v in chk.tolist()],
     }
     if rank == 0:
         B.emit(line)

@@ -54,8 +54,14 @@ int fpm_timer_stop(void *timer);
 int fpm_timer_elapsed_ms(void *timer, double *ms);     /* synchronises on the stop event */
 void fpm_timer_destroy(void *timer);
 uint64_t fpm_kernel_launch_count(void);                /* kernels launched by this library so far */
+/* launches so far by code path, for tests that must know WHICH kernels a run went through; out[i], i < n, in the order:
+ * TMA tile pass (one GPU), generic tile pass, row (z) pass with bulk copies, generic z pass, TMA tile pass with several
+ * destinations (slab transpose), paint with the brick walk, readout with the brick walk, P(k) accumulated inside the forward
+ * x-pass, staged slab transposes.  Returns the number of counters the library keeps. */
+int fpm_path_counts(uint64_t *out, int n);
 /* optional per-kernel-class timing with CUDA events on the launching stream (off by default); classes in order:
- * paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other */
+ * paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other, memset, barrier (cross-GPU, includes the wait for
+ * the slowest rank), halo, migrate, push (exposed tail of the copy-engine pushes of a staged slab transpose) */
 int fpm_prof_enable(int on);
 int fpm_prof_reset(void);
 int fpm_prof_get(int64_t *counts, double *total_ms, int ncls);

@@ -350,6 +350,20 @@ class Session:
         return dict(zip(["D1", "D2", "f1", "f2", "E", "dEda", "d2Eda2", "dD1da", "d2D1da2", "Omega_a", "Omega_Lambda", "Omega_cdm"], o))
 
 
+def clock_table():
+    """Cumulative seconds of the reference's named clocks (CLOCK / ENTER / LEAVE, api/fastpm/prof.h:24-28) as printed by
+    fastpm_clock_stat (prof.c:144): {"func:name": seconds}, one rank, so min = max = mean."""
+    L = lib()
+    buf = C.create_string_buffer(1 << 16)
+    L.ref_clock_table.argtypes = [C.c_char_p, C.c_int]
+    L.ref_clock_table(buf, len(buf))
+    import re
+    out = {}
+    for m in re.finditer(r"(-?\d+\.\d+)\s+(-?\d+\.\d+)\s+(-?\d+\.\d+)\s+(\w+) : (\w+) :", buf.value.decode(errors="replace")):
+        out["%s:%s" % (m.group(5), m.group(4))] = float(m.group(3))
+    return out
+
+
 def schedule(time_step):
     ts = np.ascontiguousarray(time_step, dtype=np.float64)
     rows = np.zeros((5 * len(ts) + 8, 7))

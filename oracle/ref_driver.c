@@ -760,3 +760,23 @@ int ref_schedule(const double *time_step, int nstep, double *rows, int maxrows)
 
 void ref_clock_stat(void) { fastpm_clock_stat(MPI_COMM_WORLD); }
 
+/* the table fastpm_clock_stat prints (prof.c:144-178: "min max mean name : func : file" per clock, cumulative seconds
+ * since the library was loaded), captured as text: the clock list itself is private to prof.c */
+static char *clk_buf; static size_t clk_cap, clk_len;
+static void clk_capture(const enum FastPMLogLevel level, const enum FastPMLogType type, const int errcode,
+                        const char *message, MPI_Comm comm, void *userdata)
+{
+    (void) level; (void) type; (void) errcode; (void) comm; (void) userdata;
+    size_t n = strlen(message);
+    if (clk_len + n + 1 < clk_cap) { memcpy(clk_buf + clk_len, message, n); clk_len += n; clk_buf[clk_len] = 0; }
+}
+int ref_clock_table(char *out, int cap)
+{
+    clk_buf = out; clk_cap = (size_t) cap; clk_len = 0;
+    if (cap > 0) out[0] = 0;
+    fastpm_push_msg_handler(clk_capture, MPI_COMM_WORLD, NULL);
+    fastpm_clock_stat(MPI_COMM_WORLD);
+    fastpm_pop_msg_handler();
+    return (int) clk_len;
+}
+

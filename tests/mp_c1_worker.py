@@ -1,0 +1,79 @@
+"""Worker of tests/test_gpu_c1.py::test_c1_two_gpus_match_one_gpu (torch.distributed.run, one process per GPU).
+
+Runs BASELINE configs[1] (nc = 256, 512^3 mesh, COLA, 10 steps) on the slabs of WORLD_SIZE GPUs from the delta_k in
+$MP_C1_DIR/delta_k.npy and compares, on rank 0, the particles (matched by id) and every step's P(k) with the one-GPU run the test
+process stored in $MP_C1_DIR/one_gpu.npz.  Tolerances: BASELINE.json's (1e-4 Mpc/h, 1e-5 relative)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from fastpm_b200 import _lib, multigpu
+    from fastpm_b200.solver import Solver, ForceEvent
+    from test_gpu_c1 import path_counts, PATHS
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    lib = _lib.require_device(local)
+    multigpu.init_comm(lib)
+    d = os.environ["MP_C1_DIR"]
+    dk = np.load(os.path.join(d, "delta_k.npy"))
+    one = np.load(os.path.join(d, "one_gpu.npz"))
+    nc, L, B = int(one["nc"]), float(one["L"]), int(one["B"])
+    steps = one["steps"]
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="cola", growth_mode="LCDM", np_alloc_factor=1.5)
+    g.setup_lpt(dk, steps[0])
+    spectra = []
+
+    def on_force_after(solver_ptr, event_ptr, userdata):
+        ev = C.cast(event_ptr, C.POINTER(ForceEvent)).contents
+        spectra.append(g.powerspectrum_of(ev.pm, ev.delta_k))
+        return 0
+
+    g.add_handler("FORCE", 1, on_force_after)
+    before = path_counts(lib)
+    g.evolve(steps)
+    after = path_counts(lib)
+    used = {k: after[k] - before[k] for k in PATHS}
+    ids, x, v = g.get_column("id"), g.get_column("x"), g.get_column("v")
+    out = [None] * world
+    dist.all_gather_object(out, (ids, x, v))
+    g.close()
+    if rank == 0:
+        ids = np.concatenate([o[0] for o in out]); x = np.concatenate([o[1] for o in out]); v = np.concatenate([o[2] for o in out])
+        assert len(ids) == nc ** 3 and len(np.unique(ids)) == nc ** 3, "particles lost or duplicated in migration"
+        order = np.argsort(ids)
+        x, v = x[order], v[order]
+        ro = np.argsort(one["id"])
+        dd = np.abs(np.mod(x, L) - np.mod(one["x"][ro], L))
+        err = np.minimum(dd, L - dd).max()
+        assert err < 1e-4, "positions differ from the one-GPU run by %g Mpc/h" % err
+        assert np.abs(v - one["v"][ro]).max() < 1e-4 * np.abs(one["v"]).max()
+        assert len(spectra) == len(steps)
+        worst = 0.0
+        for i, (k, p, nm) in enumerate(spectra):
+            assert np.array_equal(nm, one["nmodes"][i])
+            sel = nm > 0
+            worst = max(worst, np.abs(p[sel] / one["p"][i][sel] - 1).max())
+        assert worst < 1e-5, "P(k) differs from the one-GPU run by %g" % worst
+        assert used["fft_tma_multi"] >= 4 * len(steps) and used["fft_tma"] >= 4 * len(steps) and used["fft_tile_generic"] == 0, used
+        if os.environ.get("FASTPM_B200_NO_STAGE"):
+            assert used["staged_transpose"] == 0, used
+        else:
+            assert used["staged_transpose"] >= 4 * len(steps), used
+        print("MP_C1_OK ranks=%d max position error vs one GPU %.3g Mpc/h, P(k) %.3g, paths %s, np per rank %s" % (
+            world, err, worst, used, [len(o[0]) for o in out]))
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,3 +36,48 @@ def run_smoke():
         assert err2 < 1e-4, "positions differ from the oracle by %g Mpc/h" % err2
         msg += "; vs oracle %.3g Mpc/h" % err2
     print(msg)
+    print(large_mesh_smoke())
+
+
+def large_mesh_smoke():
+    """Two force evaluations and one kick-drift-kick cycle on a 512^3 mesh (nc = 64, B = 8): the size from which the TMA tile pass
+    (fft_tma_kernel), the bulk-copy row pass (fft_zrow_kernel) and the fused Green's function serve the transforms -- the kernels
+    bench.py times -- checked against the oracle on the same delta_k when the compiled reference is present."""
+    import ctypes as C
+    from fastpm_b200.solver import Solver
+    from oracle import ref
+    nc, L, B = 64, 64.0, 8
+    steps = np.array([0.1, 0.15])
+    here = os.path.dirname(os.path.abspath(__file__))
+    want = None
+    if ref.available():
+        s = ref.Session(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="cola", growth_mode="LCDM", np_alloc_factor=2.0)
+        dk, _, _ = s.ic_deltak(100, open(os.path.join(here, "golden", "powerspec.txt")).read())
+        s.setup_lpt(dk, steps[0])
+        s.evolve(steps)
+        want = s.get_particles()
+        s.close()
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=B, force_mode="cola", growth_mode="LCDM", np_alloc_factor=1.0)
+    if want is not None:
+        g.setup_lpt(dk, steps[0])
+    else:
+        tab = np.loadtxt(os.path.join(here, "golden", "powerspec.txt"))
+        g.setup_ic(100, tab[:, 0], tab[:, 1], steps[0])
+    cnt = (C.c_uint64 * 4)()
+    g.lib.fpm_path_counts.argtypes = [C.c_void_p, C.c_int]
+    g.lib.fpm_path_counts(cnt, 4)
+    before = [int(v) for v in cnt]
+    g.evolve(steps)
+    g.lib.fpm_path_counts(cnt, 4)
+    used = [int(v) - b for v, b in zip(cnt, before)]
+    x = g.get_column("x")
+    g.close()
+    assert used[0] >= 16 and used[2] >= 8 and used[1] == 0 and used[3] == 0, "512^3 mesh did not take the TMA / bulk-copy FFT passes: %s" % used
+    assert np.isfinite(x).all()
+    msg = "smoke (512^3 mesh) ok: %d TMA tile passes, %d bulk-copy row passes" % (used[0], used[2])
+    if want is not None:
+        d = np.abs(np.mod(x, L) - np.mod(want["x"], L))
+        err = np.minimum(d, L - d).max()
+        assert err < 1e-4, "512^3 mesh: positions differ from the oracle by %g Mpc/h" % err
+        msg += "; max position error vs oracle %.3g Mpc/h" % err
+    return msg

@@ -1,6 +1,6 @@
-"""Runs the GPU cases of tests/first_gpu_run_cases.py -- written after this round's GPU budget was spent, never yet executed on a
-B200 -- one pytest process per case.  Until a case has been seen green on hardware it is reported as xfail (it failed) or
-xpass (it passed): the validated suite stays readable either way, and the round-end log says which of these need work."""
+"""Runs the GPU cases of tests/first_gpu_run_cases.py (rows N1-N4: device ICs, snapshots / restart, PGD, softening, the other
+windows, the C user programs), one pytest process per case.  All twelve were green on a B200 at the end of round 1
+(GPUTEST_r01.json: 12 xpassed); since round 2 they are ordinary tests -- a failure fails the suite."""
 import os
 import subprocess
 import sys
@@ -32,7 +32,6 @@ def test_case_list_is_complete():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first B200 run pending: written after this round's GPU budget was spent (green on the CPU through the emulated library, tests/test_cpu_full_emulation.py)")
 @pytest.mark.parametrize("case", CASES)
 def test_first_gpu_run(case):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
@@ -43,7 +42,6 @@ def test_first_gpu_run(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first B200 run pending (green with 2 and 4 ranks on the emulated library, tests/test_cpu_full_emulation.py)")
 def test_first_two_gpu_run_of_the_extras():
     """PGD correction on two slabs and a snapshot written by both ranks from their device columns (tests/mp_worker.py: extras)."""
     sys.path.insert(0, ROOT)
