@@ -97,6 +97,27 @@ inline void bulk_wait0() {}
 inline void fence_async_smem() {}
 #endif
 
+// ------------------------------------------------------------------ packed complex arithmetic
+// Blackwell issues FADD2 / FMUL2 / FFMA2 on a float2 held in an aligned register pair, with per-half negate and swap / broadcast
+// operand modifiers: a complex add or subtract is ONE instruction and a complex product two (no moves), against 2 and 4 scalar
+// ones.  Measured on B200 (round 2, scripts/ubench/atomics.cu and scripts/fft_passes.py): FFMA2 issues at HALF the rate of FFMA
+// (2.26 against 2 x 1.06 cycles per warp and SMSP), so the packed forms save issue slots but no pipe time, and the N = 2048 passes
+// ran 7 % SLOWER with them (in place 15.5 ms against 14.5; transposing 22.8 against 22.0; rows 19.1 / 17.1 against 18.0 / 16.0):
+// the passes are bound by shared-memory / LSU wavefronts, not by FP32 issue.  Kept as an opt-in (-DFPM_PACKED_F32) for reference.
+#if !defined(FPM_EMULATE) && defined(FPM_PACKED_F32)
+__device__ __forceinline__ float2 c2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 c2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 c2mul(float2 d, float2 w)
+{
+    const float2 t = __fmul2_rn(make_float2(d.x, d.x), w);
+    return __ffma2_rn(make_float2(d.y, d.y), make_float2(-w.y, w.x), t);
+}
+#else
+__device__ __forceinline__ float2 c2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 c2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 c2mul(float2 d, float2 w) { return make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x); }
+#endif
+
 // ------------------------------------------------------------------ register FFT (radix-2 DIF, unrolled)
 // twiddle exp(-2 pi i idx/16), idx = 0..7, as compile-time constants
 __device__ __forceinline__ float2 w16(int idx)
@@ -119,15 +140,12 @@ __device__ __forceinline__ void fft_reg(float2 (&v)[R])
             #pragma unroll
             for (int j = 0; j < half; j++) {
                 const float2 a = v[blk + j], b = v[blk + j + half];
-                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
-                const float2 d = make_float2(a.x - b.x, a.y - b.y);
+                v[blk + j] = c2add(a, b);
+                const float2 d = c2sub(a, b);
                 const int idx = j * (8 / half);              // exp(-2 pi i j / (2 half)) = w16(j * 16 / (2 half))
                 if (idx == 0) v[blk + j + half] = d;
                 else if (idx == 4) v[blk + j + half] = make_float2(d.y, -d.x);
-                else {
-                    const float2 w = w16(idx);
-                    v[blk + j + half] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
-                }
+                else v[blk + j + half] = c2mul(d, w16(idx));
             }
         }
     }
@@ -199,8 +217,7 @@ struct Fft3 {
         #pragma unroll
         for (int q = 1; q < R1; q++) {
             const float2 w = TWS ? tw1[q * t] : __ldg(tw1 + q * t);
-            const float2 y = v[bitrev<R1>(q)];
-            v[bitrev<R1>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+            v[bitrev<R1>(q)] = c2mul(v[bitrev<R1>(q)], w);
         }
 
         // ---- exchange 1 (B), then stage 2
@@ -233,8 +250,7 @@ struct Fft3 {
             #pragma unroll
             for (int q = 1; q < R2; q++) {
                 const float2 w = TWS ? tw[q * tw2i] : __ldg(tw + q * tw2i);
-                const float2 y = w2[bitrev<R2>(q)];
-                w2[bitrev<R2>(q)] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+                w2[bitrev<R2>(q)] = c2mul(w2[bitrev<R2>(q)], w);
             }
             #pragma unroll
             for (int q = 0; q < R2; q++) u[i * R2 + q] = w2[bitrev<R2>(q)];      // natural order: u[i*R2 + q2]

@@ -9,6 +9,8 @@
 #include "mesh.cuh"
 #include "ic_gadget.h"
 #include <vector>
+#include <string.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------ generic mode iterator
 // one thread per complex element of the local k-space block, kz fastest (coalesced)
@@ -252,6 +254,152 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
     }
 }
 
+// ------------------------------------------------------------------ P(k), row-streaming version (round 2)
+// The kernel above spends ~110 instructions per mode (segmented shuffle reductions on doubles every 64 modes) and runs at a
+// quarter of the HBM rate.  Here a warp takes one k-space row (ky, kx fixed) at a time and every lane owns a CONTIGUOUS chunk
+// of CH = (N/2)/32 modes of it: along kz the shell index is non-decreasing, so a lane walks runs of equal bin, keeps the
+// running sum of |delta|^2 in a register and touches the histogram only when the bin changes.
+//   * rows travel global -> shared memory with 16-byte cp.async copies (coalesced, no registers), the next row in flight while
+//     this one is processed; mode m sits at position m + 2*min(m / CH, 31), so that the lanes' 16-byte reads are bank-conflict free;
+//   * the bin is tracked incrementally (kk grows by 2 iz + 1 per step; bin advances while (bin+1)^2 <= kk): no square roots
+//     except one per chunk;
+//   * each warp has a private histogram; the runs a lane flushes while it walks are bins no other lane of the warp can touch
+//     (its first run, which may continue the previous lane's last one, is held back and merged once per row with a segmented
+//     shuffle reduction): plain read-modify-writes, no atomics;
+//   * interior modes have weight 2, the two ends of a row weight 1 (powerspectrum.c:94): runs accumulate |delta|^2 (ends: half of
+//     it) and are doubled when flushed -- scaling by 2 is exact, so this is the sum of w |delta|^2 in another order.
+// The deconvolution (solver.c:471, transfer.c:78-113) is folded into the read exactly as above: the mode is multiplied by
+// (d[ix] d[iy]) d[iz] in double and ROUNDED TO FLOAT before it is squared.  Needs (N/2) % 64 == 0; other sizes keep the kernel above.
+#define PKR_WARPS 8
+#ifndef FPM_EMULATE
+__device__ __forceinline__ void pk_cp16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void pk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pk_cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void pk_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+inline void pk_cp16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+inline void pk_cp_commit() {}
+inline void pk_cp_wait_all_but_one() {}
+inline void pk_cp_wait_all() {}
+#endif
+
+__global__ void __launch_bounds__(32 * PKR_WARPS) powerspectrum_rows_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
+        const float2 *__restrict__ dk, double *__restrict__ out /* [nbins] + 1 */)
+{
+    FPM_DYN_SMEM(smem_raw, 16);
+    const int n = g.n, h = n / 2, nbins = h, CH = h / 32;
+    const int RB = h + 66;                                       // positions of one staged row (h + 1 modes, 2 pad per chunk), even
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *dts = reinterpret_cast<double *>(smem_raw);                                          // [RB] deconvolution factors along z, staged like a row
+    double *hist_all = dts + RB;                                                                  // [PKR_WARPS][nbins + 1]
+    float2 *rows_all = reinterpret_cast<float2 *>(hist_all + (size_t) PKR_WARPS * (nbins + 1));   // [PKR_WARPS][2][RB]
+    for (int i = threadIdx.x; i < PKR_WARPS * (nbins + 1); i += blockDim.x) hist_all[i] = 0;
+    for (int m = threadIdx.x; m <= h; m += blockDim.x) dts[m + 2 * (m / CH > 31 ? 31 : m / CH)] = decic ? dtab[m] : 1.0;      // iz = h follows lane 31's chunk
+    __syncthreads();
+    double *hist = hist_all + (size_t) warp * (nbins + 1);
+    float2 *rowbuf = rows_all + (size_t) warp * 2 * RB;
+    const size_t nrows = (size_t) g.nyl * n;
+    const size_t wstride = (size_t) gridDim.x * PKR_WARPS;
+    const int nq = (h + 2) / 2;                                  // float4 (two modes) per row, including the pair that holds iz = h
+
+    auto fetch = [&](size_t row, int buf) {
+        const float4 *src = reinterpret_cast<const float4 *>(dk + row * (size_t) g.pitch_c);
+        float2 *dst = rowbuf + (size_t) buf * RB;
+        for (int q = lane; q < nq; q += 32) {
+            const int m = 2 * q;                                 // CH is even: both modes of the pair fall into the same chunk
+            pk_cp16(dst + m + 2 * (m / CH > 31 ? 31 : m / CH), src + q);
+        }
+        pk_cp_commit();
+    };
+
+    size_t row = (size_t) blockIdx.x * PKR_WARPS + warp;
+    int cur = 0;
+    if (row < nrows) fetch(row, 0);
+    double allsum = 0;
+    for (; row < nrows; row += wstride) {
+        const size_t nxt = row + wstride;
+        if (nxt < nrows) { fetch(nxt, cur ^ 1); pk_cp_wait_all_but_one(); } else pk_cp_wait_all();
+        __syncwarp();
+        const int ix = (int) (row % n), iy = (int) (row / n) + g.y0;
+        const int ikx = ix > h ? ix - n : ix, iky = iy > h ? iy - n : iy;
+        const int kxy = ikx * ikx + iky * iky;
+        const double dxy = decic ? dtab[ix] * dtab[iy] : 1.0;           // (1 * d[ix]) * d[iy], the reference's order
+        const float2 *rb = rowbuf + (size_t) cur * RB;
+        // this lane's chunk: iz in [iz0, iz0 + CH), staged at iz + 2 * lane; lane 31 also takes iz = h
+        int iz = lane * CH;
+        int kk = kxy + iz * iz;
+        int bin;
+        {
+            const float sf = sqrtf((float) kk);                          // kk < 2^24: exact in float; the estimate is off by at most 1
+            bin = (int) sf;
+            if ((bin + 1) * (bin + 1) <= kk) bin++;
+            if (bin * bin > kk) bin--;
+        }
+        int next = (bin + 1) * (bin + 1);
+        int run_bin = bin, first_bin = 0x7fffff00 + lane;                // sentinel: no first run yet (distinct per lane)
+        double run = 0, first_sum = 0;
+        bool have_first = false;
+        const float2 *src = rb + iz + 2 * lane;
+        const double *dsrc = dts + iz + 2 * lane;
+        auto step = [&](float2 v, double dz) {
+            while (kk >= next) { bin++; next = (bin + 1) * (bin + 1); }
+            if (bin != run_bin) {
+                if (!have_first) { first_bin = run_bin; first_sum = run; have_first = true; }
+                else if (run_bin < nbins && run != 0) hist[run_bin] += 2.0 * run;
+                run = 0; run_bin = bin;
+            }
+            if (decic) {
+                const double smth = dxy * dz;
+                v.x = (float) ((double) v.x * smth);
+                v.y = (float) ((double) v.y * smth);
+            }
+            double p2 = (double) v.x * (double) v.x + (double) v.y * (double) v.y;
+            if (iz == 0 || iz == h) p2 *= 0.5;                           // weight 1 instead of 2
+            allsum += p2;
+            if (kk != 0) run += p2;                                      // the DC mode belongs to no shell
+            kk += 2 * iz + 1;
+            iz++;
+        };
+        for (int j = 0; j < CH; j += 2) {                                // two modes per 16-byte read (positions are even)
+            const float4 vv = *reinterpret_cast<const float4 *>(src + j);
+            const double2 dd = *reinterpret_cast<const double2 *>(dsrc + j);
+            step(make_float2(vv.x, vv.y), dd.x);
+            step(make_float2(vv.z, vv.w), dd.y);
+        }
+        if (lane == 31) step(src[CH], dsrc[CH]);                         // iz = h
+        if (!have_first) { first_bin = run_bin; first_sum = run; }
+        else if (run_bin < nbins && run != 0) hist[run_bin] += 2.0 * run;
+        __syncwarp();
+        // first runs: contiguous groups of lanes with the same bin (bins are non-decreasing across lanes)
+        {
+            int b = first_bin;
+            double s1 = first_sum;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ob = __shfl_down_sync(0xffffffffu, b, o);
+                const double o1 = __shfl_down_sync(0xffffffffu, s1, o);
+                if (lane + o < 32 && ob == b) s1 += o1;
+            }
+            const int pb = __shfl_up_sync(0xffffffffu, b, 1);
+            if ((lane == 0 || pb != b) && b < nbins && s1 != 0) hist[b] += 2.0 * s1;
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
+    if (lane == 0) hist[nbins] += 2.0 * allsum;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
+        double t = 0;
+        #pragma unroll
+        for (int w = 0; w < PKR_WARPS; w++) t += hist_all[(size_t) w * (nbins + 1) + i];
+        if (t != 0) atomicAdd(&out[i], t);
+    }
+}
+
 // out[3*nbins + 1] = geometry sums (cached) and data sums laid out as the callers expect: [sum w][sum w |d|^2][sum w k][variance]
 __global__ void pk_assemble_kernel(const double *__restrict__ geom, const double *__restrict__ data, int nbins, double *__restrict__ out)
 {
@@ -472,7 +620,21 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
     }
     double *d_data = mm->d_pkgeom + 2 * nbins;        // [nbins] + 1
     FPM_CUDA_OK(cudaMemsetAsync(d_data, 0, sizeof(double) * (nbins + 1), st));
-    FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * PK_WARPS, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+    static int rows_mode = -1;        // FASTPM_B200_PK=generic: the shuffle-reduction kernel for every mesh size (cross-check)
+    if (rows_mode < 0) { const char *e = getenv("FASTPM_B200_PK"); rows_mode = (e && !strcmp(e, "generic")) ? 0 : 1; }
+    const int h = g.n / 2;
+    const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) PKR_WARPS * (nbins + 1) + sizeof(float2) * (size_t) PKR_WARPS * 2 * (h + 66);
+    if (rows_mode && h % 64 == 0 && smem_rows <= 227 * 1024) {
+        static bool attr_rows = false;
+        if (!attr_rows) { FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_rows = true; }
+        const int per_sm = (int) ((227 * 1024) / (smem_rows + 1024));
+        const size_t nrows = (size_t) g.nyl * g.n;
+        size_t grid = (size_t) 148 * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
+        if (grid * PKR_WARPS > nrows) grid = (nrows + PKR_WARPS - 1) / PKR_WARPS;
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_rows_kernel<<<(unsigned) grid, 32 * PKR_WARPS, smem_rows, st>>>(g, m->d_decic, decic, (const float2 *) dk, d_data)));
+    } else {
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * PK_WARPS, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+    }
     FPM_CHECK_LAUNCH();
     pk_assemble_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(mm->d_pkgeom, d_data, nbins, d_out);
     FPM_CHECK_LAUNCH();

@@ -88,6 +88,7 @@ struct FpmMesh {
     fpm_barrier_fn barrier; // cross-GPU barrier between a transposing pass and the next (multi-GPU only)
     void *comm;             // opaque communicator (multi-GPU only)
     float *stage;           // multi-GPU: local staging mesh for the slab transpose (NULL: store straight into the peers)
+    float2 *d_kkf[4][2];    // lazily built interleaved tables { kk of potorder - 1 .. 2, k / k_finite } for the fused Green's function (fft.cu)
 };
 
 int fpm_fft_plan_create(int n, FpmFftPlan **out);

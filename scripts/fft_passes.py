@@ -3,7 +3,10 @@ import ctypes as C
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fastpm_b200 import device, _lib
+from fastpm_b200 import _lib
+if len(sys.argv) > 2:                       # A/B timing of another build of the library (development only)
+    _lib.LIB_PATH = os.path.abspath(sys.argv[2])
+from fastpm_b200 import device
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 m = device.Mesh(n, float(n) / 2)

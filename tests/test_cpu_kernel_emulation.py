@@ -294,6 +294,31 @@ def test_kspace_kernels_against_reference(kspace_emul, ref_mod, tmp_path):
     s.close()
 
 
+def test_row_streaming_powerspectrum_kernel_against_reference(kspace_emul, ref_mod, tmp_path):
+    """powerspectrum.c:35-124 through powerspectrum_rows_kernel (csrc/kspace.cu; meshes with (N/2) % 64 == 0, i.e. every bench size):
+    mode counts exact, P(k) to 1e-12 of the compiled reference, plain and with the deconvolution folded into the read, and equal
+    to the shuffle-reduction kernel it replaces on those sizes."""
+    nmesh, L = 128, 200.0
+    rng = np.random.default_rng(11)
+    field = rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32)
+    s = ref_mod.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    dk = s.r2c(s.real_pack(field))
+    c = s.complex_view(dk)
+    tab, dec = _tables(nmesh, L)
+    head = struct.pack("<id", nmesh, L) + tab.tobytes() + dec.tobytes() + _to_device_layout(c, nmesh).tobytes()
+    nb = nmesh // 2
+    for decic, src in ((0, dk), (1, s.decic(dk))):
+        k0, p0, n0 = s.powerspectrum(src)
+        sums = np.frombuffer(kspace_emul("pk_rows", head + struct.pack("<i", decic), str(tmp_path)), dtype=np.float64)
+        old = np.frombuffer(kspace_emul("pk", head + struct.pack("<i", decic), str(tmp_path)), dtype=np.float64)
+        nm, sp = sums[:nb], sums[nb:2 * nb]
+        assert np.array_equal(nm, n0)
+        sel = nm > 0
+        np.testing.assert_allclose(sp[sel] / nm[sel] * L ** 3, p0[sel], rtol=1e-12)
+        np.testing.assert_allclose(sums, old, rtol=1e-12)                  # includes the all-mode variance slot
+    s.close()
+
+
 def test_pgd_transfer_kernel_against_reference(kspace_emul, ref_mod, tmp_path):
     """pgdcorrection.c:28-137: the PGD potential sweep + gradient of the kernel sources, pushed through the reference's own
     c2r and readout, equals fastpm_pgdc_calculate bit for bit (same libm exp on the CPU)."""
