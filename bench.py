@@ -347,6 +347,13 @@ def run_ours(args):
         "x_checksum": position_checksum(host["x"][1], host["id"][1], float(nc)),
         "np_total_after": int(g.np),
     }
+    if os.environ.get("FASTPM_B200_TILE_STATS"):
+        ts4 = (C.c_uint64 * 4)()
+        lib.fpm_tile_stats.argtypes = [C.c_void_p]
+        lib.fpm_tile_stats(ts4)
+        line["tile_stats"] = {"paint_particles_on_global_path": int(ts4[0]), "paint_ctas_without_tile": int(ts4[1]),
+                              "readout_particles_on_global_path": int(ts4[2]), "readout_ctas_without_tile": int(ts4[3]),
+                              "note": "summed over every deposit / gather since the library was loaded (warm-up, timed and end-to-end runs)"}
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         ref_nc = args.ref_nc if args.ref_nc > 0 else 128

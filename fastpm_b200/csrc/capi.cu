@@ -68,6 +68,7 @@ int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, flo
 void fpm_fft_force_generic(int on);
 int fpm_gadget_fill_launch(const FpmMesh *m, float *dk, int seed, cudaStream_t st);
 void fpm_set_lagrangian_hint(int nc);
+int fpm_tile_stats_fetch(unsigned long long out[4]);
 
 // ------------------------------------------------------------------ runtime state
 static char g_error[1024] = "";
@@ -712,6 +713,7 @@ int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, doub
 
 // performance hint: stores of exactly nc^3 particles are in fastpm_store_fill order (store.c:756-793); 0 clears it
 int fpm_particle_grid_hint(int nc) { fpm_set_lagrangian_hint(nc); return 0; }
+int fpm_tile_stats(uint64_t *out4) { unsigned long long t[4]; if (fpm_tile_stats_fetch(t)) return -1; for (int i = 0; i < 4; i++) out4[i] = t[i]; return 0; }
 
 int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out)
 {

@@ -307,7 +307,7 @@ extern "C" void fpm_migrate_destroy(void)
 // step 1: classify; returns the per-destination counts on the host (synchronises the stream)
 extern "C" int *fpm_wrap_flag_device(void);
 extern "C" int fpm_wrap_flag_fetch(void);
-extern "C" int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap)
+extern "C" int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap, int *overflow_host)
 {
     cudaStream_t st = comm_stream();
     const int G = m->geom.nranks;
@@ -325,8 +325,10 @@ extern "C" int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, in
     FPM_CUDA_OK(cudaMemcpyAsync(tmp, g_mig.d_send_count, sizeof(int) * FPM_MAX_RANKS, cudaMemcpyDeviceToHost, st));
     FPM_CUDA_OK(cudaMemcpyAsync(tmp + FPM_MAX_RANKS, g_mig.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     FPM_CUDA_OK(cudaStreamSynchronize(st));
-    if (tmp[FPM_MAX_RANKS]) { fpm_set_error("migrate: more than %d particles leave for one slab in a single step (Out of particle storage space, store.c:583)", g_mig.cap); return -1; }
-    for (int d = 0; d < G; d++) send_count_host[d] = tmp[d];
+    // more leavers for one destination than a pack buffer holds: this round moves the first `cap` of them (the kernel marked only
+    // those), the caller runs another round for the rest (host/comm.c)
+    *overflow_host = tmp[FPM_MAX_RANKS] ? 1 : 0;
+    for (int d = 0; d < G; d++) send_count_host[d] = tmp[d] < g_mig.cap ? tmp[d] : g_mig.cap;
     return 0;
 }
 

@@ -22,7 +22,7 @@ int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
 int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank);
 int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void *pack);
-int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap);
+int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap, int *overflow_host);
 int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes);
 int fpm_migrate_holes(int64_t np, int64_t np_stay, int *nholes_host);
 int fpm_migrate_fill_column(void *col, int elsize, int nholes);
@@ -205,13 +205,16 @@ void fpm_comm_release_migration(void)
 
 typedef struct { void *ptr; int elsize; } MigCol;
 
+/* set by fastpm_decompose (host/solver.c) around its call: the force evaluation that follows recomputes ACC, so the column need not
+ * travel.  Any other caller of the public fastpm_store_decompose gets every column moved, like the reference (store.c:302-323). */
+int fpm_decompose_skip_acc = 0;
+
 static int migrating_columns(FastPMStore *p, MigCol *cols)
 {
-    /* every allocated column except acc (recomputed by the force that follows), in column order */
     int n = 0;
     for (int ci = 0; ci < 32; ci++) {
         if (!p->columns[ci]) continue;
-        if (p->_column_info[ci].attribute == COLUMN_ACC) continue;
+        if (fpm_decompose_skip_acc && p->_column_info[ci].attribute == COLUMN_ACC) continue;
         if (p->_column_info[ci].elsize % 4 != 0) fastpm_raise(-1, "column %s cannot migrate (element size %zu)\n", p->_column_info[ci].name, p->_column_info[ci].elsize);
         cols[n].ptr = p->columns[ci]; cols[n].elsize = (int) p->_column_info[ci].elsize; n++;
     }
@@ -237,50 +240,64 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
         mig_cap = (int) (frac * p->np_upper);
         if (mig_cap < 4096) mig_cap = 4096;
         if ((size_t) mig_cap > p->np_upper) mig_cap = (int) p->np_upper;
-        mig_row_bytes = row;
-        pack_local = fastpm_memory_alloc(p->mem, "migration pack buffers", (size_t) g_size * mig_cap * row, FASTPM_MEMORY_FLOATING);
-        if (fpm_migrate_init(g_size, mig_cap, (long long) p->np_upper, row, pack_local) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        /* sized for every allocated column (the solver's own calls leave ACC behind, other callers move it too) */
+        size_t row_all = 0;
+        for (int ci = 0; ci < 32; ci++) if (p->columns[ci]) row_all += p->_column_info[ci].elsize;
+        mig_row_bytes = row_all;
+        pack_local = fastpm_memory_alloc(p->mem, "migration pack buffers", (size_t) g_size * mig_cap * row_all, FASTPM_MEMORY_FLOATING);
+        if (fpm_migrate_init(g_size, mig_cap, (long long) p->np_upper, row_all, pack_local) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
         peers_of(pack_local, pack_peers);
     }
-    if (row != mig_row_bytes) fastpm_raise(-1, "fastpm_b200: the set of particle columns changed between decompositions\n");
+    if (row > mig_row_bytes) fastpm_raise(-1, "fastpm_b200: particle columns were added between decompositions\n");
 
-    int send[MAXR], all[MAXR * MAXR];
-    memset(send, 0, sizeof(send));
-    const int wrap = (fpm_pending_wrap == p);              /* fastpm_decompose left the periodic wrap to the classification pass */
+    /* The reference moves any fraction of the store in one exchange (store.c:486-657) and fails only when a rank would hold more
+     * than np_upper.  The pack buffers here hold `mig_cap` particles per destination: when more than that leave for one slab
+     * (thin slabs, a restart from a snapshot that every rank read an even share of) the exchange runs in rounds -- each round
+     * moves up to mig_cap particles per destination, the rest stay put and are classified again.  Every rank takes the same
+     * number of rounds (the overflow flag is all-reduced), so nobody waits in a collective the others never enter. */
+    int wrap = (fpm_pending_wrap == p);                    /* fastpm_decompose left the periodic wrap to the classification pass */
     if (wrap) fpm_pending_wrap = NULL;
-    if (fpm_migrate_classify(pm->mesh, (double *) p->x, (int64_t) p->np, send, wrap) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
-    allgather(send, sizeof(int) * MAXR, all);
-    int64_t nsend = 0, nrecv = 0;
-    for (int r = 0; r < g_size; r++) { if (r != g_rank) { nsend += send[r]; nrecv += all[r * MAXR + g_rank]; } }
-    const int64_t np_stay = (int64_t) p->np - nsend;
-    int64_t over = (np_stay + nrecv > (int64_t) p->np_upper) ? 1 : 0;
-    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &over, 1, 2);
-    if (over) return -1;                                   /* "Out of particle storage space", solver.c:585-590 */
+    for (int round = 0; ; round++) {
+        int send[MAXR], all[MAXR * MAXR], overflow = 0;
+        memset(send, 0, sizeof(send));
+        if (fpm_migrate_classify(pm->mesh, (double *) p->x, (int64_t) p->np, send, wrap, &overflow) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        wrap = 0;
+        allgather(send, sizeof(int) * MAXR, all);
+        int64_t nsend = 0, nrecv = 0;
+        for (int r = 0; r < g_size; r++) { if (r != g_rank) { nsend += send[r]; nrecv += all[r * MAXR + g_rank]; } }
+        const int64_t np_stay = (int64_t) p->np - nsend;
+        int64_t flags[2] = { (np_stay + nrecv > (int64_t) p->np_upper) ? 1 : 0, overflow };
+        fpm_comm_allreduce_i64(MPI_COMM_WORLD, flags, 2, 2);
+        if (flags[0]) return -1;                           /* "Out of particle storage space", solver.c:585-590 */
 
-    size_t off = 0;
-    for (int j = 0; j < ncol; j++) {
-        FPM_MUST(fpm_migrate_pack_column(pm->mesh, cols[j].ptr, cols[j].elsize, send, off));
-        off += cols[j].elsize;
-    }
-    int nholes = 0;
-    if (fpm_migrate_holes((int64_t) p->np, np_stay, &nholes) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
-    for (int j = 0; j < ncol; j++) FPM_MUST(fpm_migrate_fill_column(cols[j].ptr, cols[j].elsize, nholes));
-    FPM_MUST(fpm_xbarrier());                              /* every rank has packed */
-    int64_t at = np_stay;
-    for (int r = 0; r < g_size; r++) {
-        if (r == g_rank) continue;
-        const int cnt = all[r * MAXR + g_rank];
-        off = 0;
+        size_t off = 0;
         for (int j = 0; j < ncol; j++) {
-            FPM_MUST(fpm_migrate_append_column(cols[j].ptr, cols[j].elsize, at, pack_peers[r], g_rank, cnt, off));
+            FPM_MUST(fpm_migrate_pack_column(pm->mesh, cols[j].ptr, cols[j].elsize, send, off));
             off += cols[j].elsize;
         }
-        at += cnt;
+        int nholes = 0;
+        if (fpm_migrate_holes((int64_t) p->np, np_stay, &nholes) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        for (int j = 0; j < ncol; j++) FPM_MUST(fpm_migrate_fill_column(cols[j].ptr, cols[j].elsize, nholes));
+        FPM_MUST(fpm_xbarrier());                          /* every rank has packed */
+        int64_t at = np_stay;
+        for (int r = 0; r < g_size; r++) {
+            if (r == g_rank) continue;
+            const int cnt = all[r * MAXR + g_rank];
+            off = 0;
+            for (int j = 0; j < ncol; j++) {
+                FPM_MUST(fpm_migrate_append_column(cols[j].ptr, cols[j].elsize, at, pack_peers[r], g_rank, cnt, off));
+                off += cols[j].elsize;
+            }
+            at += cnt;
+        }
+        FPM_MUST(fpm_xbarrier());                          /* every rank has pulled: pack buffers may be reused */
+        p->np = (size_t) at;
+        if (!flags[1]) break;                              /* nobody had more leavers than a pack buffer holds */
+        if (round > 4096) fastpm_raise(-1, "fastpm_b200: particle migration does not converge\n");
     }
-    FPM_MUST(fpm_xbarrier());                              /* every rank has pulled: pack buffers may be reused */
-    p->np = (size_t) at;
     return 0;
 }
+
 
 /* ------------------------------------------------------------------ host-only self test of the callback plumbing
  * (no device: used by the world_size-2 gloo test on CPU).  Returns 0 when the collectives behave as the host layer

@@ -331,7 +331,15 @@ void fastpm_solver_evolve(FastPMSolver *fastpm, double *time_step, int nstep)
  * positions in between): fastpm_paint_local wraps while it reads x, see cic_paint_kernel<.., WRAP> in csrc/paint.cu. */
 FastPMStore *fpm_pending_wrap = NULL;
 
+extern int fpm_decompose_skip_acc;       /* host/comm.c */
+static void fastpm_decompose_inner(FastPMSolver *fastpm, PM *pm);
 static void fastpm_decompose(FastPMSolver *fastpm, PM *pm)
+{
+    fpm_decompose_skip_acc = 1;          /* a force evaluation follows: ACC is recomputed for every particle */
+    fastpm_decompose_inner(fastpm, pm);
+    fpm_decompose_skip_acc = 0;
+}
+static void fastpm_decompose_inner(FastPMSolver *fastpm, PM *pm)
 {
     if (fastpm->NTask > 1) fpm_store_flush(NULL);
     int before_handlers = 0, nspecies = 0;

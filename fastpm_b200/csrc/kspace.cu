@@ -631,6 +631,7 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
         const size_t nrows = (size_t) g.nyl * g.n;
         size_t grid = (size_t) 148 * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
         if (grid * PKR_WARPS > nrows) grid = (nrows + PKR_WARPS - 1) / PKR_WARPS;
+        fpm_path_counter[FPM_PATH_PK_ROWS]++;
         FPM_TIMED(FPM_K_PK, st, (powerspectrum_rows_kernel<<<(unsigned) grid, 32 * PKR_WARPS, smem_rows, st>>>(g, m->d_decic, decic, (const float2 *) dk, d_data)));
     } else {
         FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * PK_WARPS, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));

@@ -39,6 +39,7 @@ __device__ __forceinline__ long long cic_particle_index(int lag_nc, int nbrick_b
 }
 
 struct CicIndex {
+    int u[3];                          // floor(x / h) before the periodic wrap
     int lx0, lx1, j0, j1, k0, k1;      // lx*: local plane index or -1 when outside this rank
     double D[3], T[3];
 };
@@ -52,15 +53,22 @@ __device__ __forceinline__ void cic_setup(const FpmGeom &g, const double *pos, C
         const double xyz = pos[d] * g.inv_cellsize;
         const double fl = floor(xyz);
         I[d] = (int) fl;
+        c.u[d] = I[d];
         c.D[d] = xyz - (double) I[d];
         c.T[d] = 1. - c.D[d];
     }
+    // periodic images (painter-cic.c:65-70 loops `while (I >= N) I -= N; while (I < 0) I += N`): a wrapped position gives
+    // I in [0, n], so one conditional subtraction serves nearly every particle; anything further out takes the division
     int I1[3];
     #pragma unroll
     for (int d = 0; d < 3; d++) {
-        I1[d] = I[d] + 1;
-        I[d] %= n; if (I[d] < 0) I[d] += n;
-        I1[d] %= n; if (I1[d] < 0) I1[d] += n;
+        int i0 = I[d];
+        if ((unsigned) i0 >= (unsigned) n) {
+            if (i0 == n) i0 = 0;
+            else { i0 %= n; if (i0 < 0) i0 += n; }
+        }
+        I[d] = i0;
+        I1[d] = (i0 + 1 == n) ? 0 : i0 + 1;
     }
     c.j0 = I[1]; c.j1 = I1[1]; c.k0 = I[2]; c.k1 = I1[2];
     if (g.nranks == 1) {
@@ -102,10 +110,11 @@ __device__ __forceinline__ void cic_add_pair(float *row, int k0, int k1, float w
 template <int VEC, bool WRAP>
 __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
         double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
-        int field_stride, long long np, int *__restrict__ bad, int lag_nc, int nbrick_blocks)
+        int field_stride, long long np, int *__restrict__ bad, int lag_nc, int nbrick_blocks, long long first)
 {
-    const long long i = cic_particle_index(lag_nc, nbrick_blocks, np);
+    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first);
     if (i < 0) return;
+    i += first;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
     if (WRAP) {
         const double L = g.boxsize;
@@ -141,10 +150,12 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
 }
 
 __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
-        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc, int nbrick_blocks)
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc, int nbrick_blocks,
+        long long first)
 {
-    const long long i = cic_particle_index(lag_nc, nbrick_blocks, np);
+    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first);
     if (i < 0) return;
+    i += first;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
     CicIndex c;
     cic_setup(g, pos, c);
@@ -205,6 +216,296 @@ __global__ void __launch_bounds__(256) cic_readout3_kernel(const FpmGeom g, cons
         }
         out[3 * i + d] = (float) value;
     }
+}
+
+// ------------------------------------------------------------------ shared-memory mesh tiles (round 2)
+// Measured on B200 (scripts/ubench/atomics.cu): a float atomicAdd on shared memory costs 0.19 cycles per lane and SM, a
+// red.global.add (any vector width) 1.2 - 1.6 when the mesh lines sit in L2 and 3 - 15 when they do not -- the deposit above is
+// bound by the latter.  With the Lagrangian hint a CTA of 512 threads takes an 8 x 8 x 8 brick of the particle grid.  Such a
+// brick stays compact under the displacement field, so the CTA
+//   1. finds the box of mesh cells its particles touch: mean cell offset from thread 0's cell (a few stray particles barely move
+//      it), then min / max over the particles within FPM_TILE_REACH cells of the mean, z origin aligned to 4 cells;
+//   2. deposit: accumulates the 8 weights of every in-box particle into a zeroed tile in shared memory (atomicAdd on shared
+//      memory) and flushes the tile ONCE, row by row, as aligned red.global.add.v4.f32 -- whole 16-byte groups, consecutive lanes
+//      on consecutive addresses, all-zero groups skipped;  gather: copies the box into the tile with aligned 16-byte loads and
+//      reads the 8 cells of every in-box particle from shared memory;
+//   3. particles outside the box (and whole CTAs whose box exceeds the tile) take the global path of the kernels above.
+// Arithmetic is unchanged: same double weights in the same product order, the gather sums the same eight products in the same
+// order (bit-identical results); the deposit adds the same float32 increments to each cell in another order.
+// Stores that are not in (nearly) Lagrangian order simply fail step 1 and run at the speed of the kernels above.
+#define FPM_TILE_THREADS 512
+#define FPM_TILE_CAP 14336          // floats of the tile: 56 KB, 4 CTAs per SM
+#define FPM_TILE_REACH 15           // first attempt: cells from the mean offset; a box too large for the tile is retried with 10
+
+struct TileFrame {
+    int ref[3];                      // unwrapped cell of thread 0's particle (x: local plane on several GPUs)
+    int sum[3];
+    int lo[3], hi[3];                // min / max offset from ref over the in-reach particles
+    int org[3];                      // coordinate of tile cell (0, 0, 0); org[2] is a multiple of 4
+    int ext[3];                      // tile extents, ext[2] a multiple of 4; ext[0] == 0: no tile for this CTA
+    int nin;
+};
+
+#ifndef FPM_EMULATE
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
+#else
+static inline int warp_sum_i(int v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+static inline int warp_min_i(int v) { for (int o = 16; o > 0; o >>= 1) { const int w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; } return v; }
+static inline int warp_max_i(int v) { for (int o = 16; o > 0; o >>= 1) { const int w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; } return v; }
+#endif
+
+// particle of this thread: 8 x 8 x 8 bricks of the Lagrangian grid, consecutive CTAs along k, then j, then i
+__device__ __forceinline__ long long tile_particle_index(int lag_nc)
+{
+    const int b = blockIdx.x, nb = lag_nc >> 3;
+    const int bk = b % nb, bj = (b / nb) % nb, bi = b / (nb * nb);
+    const int tk = threadIdx.x & 7, tj = (threadIdx.x >> 3) & 7, ti = threadIdx.x >> 6;
+    return ((long long) (bi * 8 + ti) * lag_nc + (bj * 8 + tj)) * lag_nc + (bk * 8 + tk);
+}
+
+__device__ __forceinline__ int tile_wrap(int v, int n)
+{
+    while (v >= n) v -= n;
+    while (v < 0) v += n;
+    return v;
+}
+
+// Steps 1 of the comment above.  u: this thread's unwrapped cell (x already local on several GPUs), valid: the particle may use
+// the tile at all.  Returns whether it does; d[] = its offset from f->ref.
+__device__ __forceinline__ bool tile_setup(const FpmGeom &g, const int u[3], bool valid, TileFrame *f, int d[3])
+{
+    const int n = g.n, tid = threadIdx.x, lane = tid & 31, half = n >> 1;
+    if (tid == 0) {
+        f->ref[0] = u[0]; f->ref[1] = u[1]; f->ref[2] = u[2];
+        f->sum[0] = f->sum[1] = f->sum[2] = 0;
+        f->ext[0] = valid ? 1 : 0;
+        f->nin = 0;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        d[a] = u[a] - f->ref[a];
+        if (a > 0 || g.nranks == 1) { if (d[a] > half) d[a] -= n; else if (d[a] < -half) d[a] += n; }
+    }
+    {
+        const int s0 = warp_sum_i(valid ? d[0] : 0), s1 = warp_sum_i(valid ? d[1] : 0), s2 = warp_sum_i(valid ? d[2] : 0);
+        if (lane == 0) { atomicAdd(&f->sum[0], s0); atomicAdd(&f->sum[1], s1); atomicAdd(&f->sum[2], s2); }
+    }
+    __syncthreads();
+    if (f->ext[0] == 0) return false;                                // thread 0's particle is not usable as the reference
+    const int m0 = f->sum[0] / FPM_TILE_THREADS, m1 = f->sum[1] / FPM_TILE_THREADS, m2 = f->sum[2] / FPM_TILE_THREADS;
+    bool in = false;
+    for (int reach = FPM_TILE_REACH; ; reach = 10) {
+        __syncthreads();                                             // everybody has read the previous attempt's verdict
+        if (tid == 0) {
+            #pragma unroll
+            for (int a = 0; a < 3; a++) { f->lo[a] = 0x7fffffff; f->hi[a] = -0x7fffffff; }
+        }
+        __syncthreads();
+        in = valid && abs(d[0] - m0) <= reach && abs(d[1] - m1) <= reach && abs(d[2] - m2) <= reach;
+        #pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int lo = warp_min_i(in ? d[a] : 0x7fffffff), hi = warp_max_i(in ? d[a] : -0x7fffffff);
+            if (lane == 0 && lo <= hi) { atomicMin(&f->lo[a], lo); atomicMax(&f->hi[a], hi); }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (f->lo[0] > f->hi[0]) f->ext[0] = 0;                  // nobody in reach
+            else {
+                f->org[0] = f->ref[0] + f->lo[0]; f->ext[0] = f->hi[0] - f->lo[0] + 2;
+                f->org[1] = f->ref[1] + f->lo[1]; f->ext[1] = f->hi[1] - f->lo[1] + 2;
+                const int z0 = f->ref[2] + f->lo[2], z0a = z0 - (((z0 % 4) + 4) % 4);
+                f->org[2] = z0a; f->ext[2] = ((f->ref[2] + f->hi[2] + 2 - z0a) + 3) & ~3;
+                // several GPUs: the planes of the tile must exist locally (0 .. nxl, the last one being the halo plane)
+                if (g.nranks > 1 && (f->org[0] < 0 || f->org[0] + f->ext[0] - 1 > g.nxl)) f->ext[0] = 0;
+                else if ((long long) f->ext[0] * f->ext[1] * f->ext[2] > FPM_TILE_CAP) f->ext[0] = (reach > 10) ? -1 : 0;
+            }
+        }
+        __syncthreads();
+        if (f->ext[0] >= 0) break;                                   // a tile, or none at all
+    }
+    return in && f->ext[0] > 0;
+}
+
+// rows of the tile are walked by the warps in groups: RPW rows per warp and pass, LPR lanes (16-byte groups) per row
+struct TileRows {
+    int nq, lpr, rpw, nrow, tx, ty, r, sx, sy, step, q;
+    __device__ __forceinline__ TileRows(const TileFrame *f)
+    {
+        nq = f->ext[2] >> 2;
+        lpr = nq <= 8 ? 8 : (nq <= 16 ? 16 : 32);
+        rpw = 32 / lpr;
+        nrow = f->ext[0] * f->ext[1];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        q = lane % lpr;
+        r = warp * rpw + lane / lpr;
+        tx = r / f->ext[1]; ty = r - tx * f->ext[1];
+        step = nwarp * rpw;
+        sx = step / f->ext[1]; sy = step - sx * f->ext[1];
+    }
+    __device__ __forceinline__ bool active() const { return r < nrow && q < nq; }
+    __device__ __forceinline__ bool more() const { return (r - (int) ((threadIdx.x & 31) / lpr)) < nrow; }     // warp-uniform
+    __device__ __forceinline__ void next(const TileFrame *f)
+    {
+        r += step; tx += sx; ty += sy;
+        if (ty >= f->ext[1]) { ty -= f->ext[1]; tx++; }
+    }
+};
+
+__device__ __forceinline__ size_t tile_row_offset(const FpmGeom &g, const TileFrame *f, int tx, int ty)
+{
+    const int px = g.nranks == 1 ? tile_wrap(f->org[0] + tx, g.n) : f->org[0] + tx;
+    const int py = tile_wrap(f->org[1] + ty, g.n);
+    return (size_t) px * ((size_t) g.n * g.pitch_r) + (size_t) py * g.pitch_r;
+}
+
+template <bool WRAP>
+__global__ void __launch_bounds__(FPM_TILE_THREADS) cic_paint_tile_kernel(const FpmGeom g, float *__restrict__ canvas,
+        double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
+        int field_stride, int *__restrict__ bad, int lag_nc, unsigned long long *__restrict__ stats)
+{
+    FPM_DYN_SMEM(tile_raw, 16);                   // FPM_TILE_CAP floats (more than the 48 KB a static array may have)
+    float *tile = reinterpret_cast<float *>(tile_raw);
+    __shared__ TileFrame frame;
+    const long long i = tile_particle_index(lag_nc);
+    double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    if (WRAP) {
+        const double L = g.boxsize;
+        #pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double xi = pos[d];
+            if (xi >= 0 && xi < L) continue;
+            const double nwrap = (double) abs((int) (xi / L));
+            double x1 = remainder(xi, L);
+            while (x1 < 0) x1 += L;
+            while (x1 > L) x1 -= L;
+            if (nwrap > 10000) atomicExch(bad, 1);
+            pos[d] = x1;
+            x[3 * i + d] = x1;
+        }
+    }
+    CicIndex c;
+    cic_setup(g, pos, c);
+    double weight = mass ? M0 + (double) mass[i] : M0;
+    if (field) weight *= (double) field[i * field_stride];
+    c.D[1] *= weight; c.T[1] *= weight;
+    int u[3] = { g.nranks == 1 ? c.u[0] : c.lx0, c.u[1], c.u[2] };
+    const bool valid = g.nranks == 1 || (c.lx0 >= 0 && c.lx0 < g.nxl);
+    int d[3];
+    const bool in = tile_setup(g, u, valid, &frame, d);
+    const int ex = frame.ext[0], ey = frame.ext[1], ez = frame.ext[2];
+    if (ex > 0) {
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        const int nf4 = (ex * ey * ez) >> 2;
+        for (int q = threadIdx.x; q < nf4; q += FPM_TILE_THREADS) t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+    }
+    if (in) {
+        float *p = tile + ((d[0] - frame.lo[0]) * ey + (d[1] - frame.lo[1])) * ez + (frame.ref[2] + d[2] - frame.org[2]);
+        const int sy = ez, sx = ey * ez;
+        atomicAdd(p, (float) (c.T[2] * c.T[0] * c.T[1]));
+        atomicAdd(p + 1, (float) (c.D[2] * c.T[0] * c.T[1]));
+        atomicAdd(p + sy, (float) (c.T[2] * c.T[0] * c.D[1]));
+        atomicAdd(p + sy + 1, (float) (c.D[2] * c.T[0] * c.D[1]));
+        atomicAdd(p + sx, (float) (c.T[2] * c.D[0] * c.T[1]));
+        atomicAdd(p + sx + 1, (float) (c.D[2] * c.D[0] * c.T[1]));
+        atomicAdd(p + sx + sy, (float) (c.T[2] * c.D[0] * c.D[1]));
+        atomicAdd(p + sx + sy + 1, (float) (c.D[2] * c.D[0] * c.D[1]));
+    } else {
+        const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+        if (c.lx0 >= 0) {
+            float *p0 = canvas + (size_t) c.lx0 * pl;
+            cic_add_pair<4>(p0 + c.j0 * pr, c.k0, c.k1, (float) (c.T[2] * c.T[0] * c.T[1]), (float) (c.D[2] * c.T[0] * c.T[1]));
+            cic_add_pair<4>(p0 + c.j1 * pr, c.k0, c.k1, (float) (c.T[2] * c.T[0] * c.D[1]), (float) (c.D[2] * c.T[0] * c.D[1]));
+        }
+        if (c.lx1 >= 0) {
+            float *p1 = canvas + (size_t) c.lx1 * pl;
+            cic_add_pair<4>(p1 + c.j0 * pr, c.k0, c.k1, (float) (c.T[2] * c.D[0] * c.T[1]), (float) (c.D[2] * c.D[0] * c.T[1]));
+            cic_add_pair<4>(p1 + c.j1 * pr, c.k0, c.k1, (float) (c.T[2] * c.D[0] * c.D[1]), (float) (c.D[2] * c.D[0] * c.D[1]));
+        }
+    }
+    if (stats) {
+        const int nout = warp_sum_i(in ? 0 : 1);
+        if ((threadIdx.x & 31) == 0 && nout) atomicAdd(stats, (unsigned long long) nout);
+        if (threadIdx.x == 0 && ex <= 0) atomicAdd(stats + 1, 1ull);
+    }
+    if (ex <= 0) return;
+    __syncthreads();
+    const float4 *t4 = reinterpret_cast<const float4 *>(tile);
+    for (TileRows w(&frame); w.more(); w.next(&frame)) {
+        if (!w.active()) continue;
+        const float4 v = t4[(w.r * ez >> 2) + w.q];
+        if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+        const int pz = tile_wrap(frame.org[2] + 4 * w.q, g.n);
+        atomicAdd(reinterpret_cast<float4 *>(canvas + tile_row_offset(g, &frame, w.tx, w.ty) + pz), v);
+    }
+}
+
+__global__ void __launch_bounds__(FPM_TILE_THREADS) cic_readout_tile_kernel(const FpmGeom g, const float *__restrict__ canvas,
+        const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, int lag_nc, unsigned long long *__restrict__ stats)
+{
+    FPM_DYN_SMEM(tile_raw, 16);
+    float *tile = reinterpret_cast<float *>(tile_raw);
+    __shared__ TileFrame frame;
+    const long long i = tile_particle_index(lag_nc);
+    double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
+    CicIndex c;
+    cic_setup(g, pos, c);
+    int u[3] = { g.nranks == 1 ? c.u[0] : c.lx0, c.u[1], c.u[2] };
+    const bool valid = g.nranks == 1 || (c.lx0 >= 0 && c.lx0 < g.nxl);
+    int d[3];
+    const bool in = tile_setup(g, u, valid, &frame, d);
+    const int ex = frame.ext[0], ey = frame.ext[1], ez = frame.ext[2];
+    #define CELLV(val) (prescale == 1.0 ? (val) : (float) ((double) (val) * prescale))
+    if (ex > 0) {
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        for (TileRows w(&frame); w.more(); w.next(&frame)) {
+            if (!w.active()) continue;
+            const int pz = tile_wrap(frame.org[2] + 4 * w.q, g.n);
+            float4 v = __ldg(reinterpret_cast<const float4 *>(canvas + tile_row_offset(g, &frame, w.tx, w.ty) + pz));
+            v.x = CELLV(v.x); v.y = CELLV(v.y); v.z = CELLV(v.z); v.w = CELLV(v.w);
+            t4[(w.r * ez >> 2) + w.q] = v;
+        }
+        __syncthreads();
+    }
+    if (stats) {
+        const int nout = warp_sum_i(in ? 0 : 1);
+        if ((threadIdx.x & 31) == 0 && nout) atomicAdd(stats, (unsigned long long) nout);
+        if (threadIdx.x == 0 && ex <= 0) atomicAdd(stats + 1, 1ull);
+    }
+    double value = 0;
+    if (in) {
+        const float *p = tile + ((d[0] - frame.lo[0]) * ey + (d[1] - frame.lo[1])) * ez + (frame.ref[2] + d[2] - frame.org[2]);
+        const int sy = ez, sx = ey * ez;
+        value += (double) p[0] * (c.T[2] * c.T[0] * c.T[1]);
+        value += (double) p[1] * (c.D[2] * c.T[0] * c.T[1]);
+        value += (double) p[sy] * (c.T[2] * c.T[0] * c.D[1]);
+        value += (double) p[sy + 1] * (c.D[2] * c.T[0] * c.D[1]);
+        value += (double) p[sx] * (c.T[2] * c.D[0] * c.T[1]);
+        value += (double) p[sx + 1] * (c.D[2] * c.D[0] * c.T[1]);
+        value += (double) p[sx + sy] * (c.T[2] * c.D[0] * c.D[1]);
+        value += (double) p[sx + sy + 1] * (c.D[2] * c.D[0] * c.D[1]);
+    } else {
+        const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+        if (c.lx0 >= 0) {
+            const float *p0 = canvas + (size_t) c.lx0 * pl;
+            value += (double) CELLV(__ldg(p0 + c.j0 * pr + c.k0)) * (c.T[2] * c.T[0] * c.T[1]);
+            value += (double) CELLV(__ldg(p0 + c.j0 * pr + c.k1)) * (c.D[2] * c.T[0] * c.T[1]);
+            value += (double) CELLV(__ldg(p0 + c.j1 * pr + c.k0)) * (c.T[2] * c.T[0] * c.D[1]);
+            value += (double) CELLV(__ldg(p0 + c.j1 * pr + c.k1)) * (c.D[2] * c.T[0] * c.D[1]);
+        }
+        if (c.lx1 >= 0) {
+            const float *p1 = canvas + (size_t) c.lx1 * pl;
+            value += (double) CELLV(__ldg(p1 + c.j0 * pr + c.k0)) * (c.T[2] * c.D[0] * c.T[1]);
+            value += (double) CELLV(__ldg(p1 + c.j0 * pr + c.k1)) * (c.D[2] * c.D[0] * c.T[1]);
+            value += (double) CELLV(__ldg(p1 + c.j1 * pr + c.k0)) * (c.T[2] * c.D[0] * c.D[1]);
+            value += (double) CELLV(__ldg(p1 + c.j1 * pr + c.k1)) * (c.D[2] * c.D[0] * c.D[1]);
+        }
+    }
+    #undef CELLV
+    out[i * out_stride] = (float) value;
 }
 
 // ------------------------------------------------------------------ the generic windows (painter.c:176-317): linear, quadratic, Lanczos
@@ -325,24 +626,73 @@ static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc)
     return (int) (ngroups * group / 256);
 }
 
+// Shared-memory tiles (cic_paint_tile_kernel / cic_readout_tile_kernel): for the leading complete groups of 8 i-planes of a store
+// with the Lagrangian hint, when a brick of 8 particles per side spans at most ~21 mesh cells (Nmesh / nc <= 2.5) and rows can be
+// moved in aligned 16-byte groups.  FASTPM_B200_TILES=0 switches them off (the kernels above then serve everything).
+static unsigned long long *g_tile_stats = nullptr;      // [4] device counters when FASTPM_B200_TILE_STATS is set: particles that took
+                                                        // the global path and CTAs without a tile, for the deposit and for the gather
+static long long fpm_tile_particles(long long np, const FpmGeom &g)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("FASTPM_B200_TILES");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+        if (on && getenv("FASTPM_B200_TILE_STATS") && cudaMalloc(&g_tile_stats, 4 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(g_tile_stats, 0, 4 * sizeof(unsigned long long));
+    }
+    if (!on || !g_lag_nc || g.n % 4 != 0 || 2 * g.n > 5 * g_lag_nc) return 0;
+    const long long group = 8LL * g_lag_nc * g_lag_nc;
+    return (np / group) * group;
+}
+int fpm_tile_stats_fetch(unsigned long long out[4])
+{
+    for (int i = 0; i < 4; i++) out[i] = 0;
+    if (!g_tile_stats) return 0;
+    FPM_CUDA_OK(cudaMemcpy(out, g_tile_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int tile_attrs()
+{
+    static bool done = false;
+    if (done) return 0;
+    FPM_CUDA_OK(cudaFuncSetAttribute(cic_paint_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FPM_TILE_CAP * sizeof(float))));
+    FPM_CUDA_OK(cudaFuncSetAttribute(cic_paint_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FPM_TILE_CAP * sizeof(float))));
+    FPM_CUDA_OK(cudaFuncSetAttribute(cic_readout_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (FPM_TILE_CAP * sizeof(float))));
+    done = true;
+    return 0;
+}
+
 // wrap_bad != NULL: wrap the positions on the way (x is then written where it changed)
 int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0,
                      const float *field, int field_stride, long long np, int *wrap_bad, cudaStream_t st)
 {
     if (np <= 0) return 0;
-    const unsigned grid = (unsigned) ((np + 255) / 256);
     static int vec = -1;          // FASTPM_B200_PAINT_VEC = 0 | 2 | 4 (default): width of the vector reductions
     if (vec < 0) { const char *e = getenv("FASTPM_B200_PAINT_VEC"); vec = e ? atoi(e) : 4; }
     double *xw = const_cast<double *>(x);
-    int lag_nc = 0;
-    const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
-    #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick)
-    if (nbrick > 0) fpm_path_counter[FPM_PATH_PAINT_BRICKS]++;
+    // leading complete groups of 8 i-planes: shared-memory tiles; the rest (and everything without the hint): global reductions
+    const long long ntile = fpm_tile_particles(np, m->geom);
     if (fpm_prof_on) fpm_prof_begin(FPM_K_PAINT, st);
-    if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
-    else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
+    if (ntile > 0) {
+        if (tile_attrs()) return -1;
+        const unsigned tgrid = (unsigned) (ntile / FPM_TILE_THREADS);
+        fpm_path_counter[FPM_PATH_PAINT_TILES]++;
+        if (wrap_bad) cic_paint_tile_kernel<true><<<tgrid, FPM_TILE_THREADS, FPM_TILE_CAP * sizeof(float), st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, wrap_bad, g_lag_nc, g_tile_stats);
+        else cic_paint_tile_kernel<false><<<tgrid, FPM_TILE_THREADS, FPM_TILE_CAP * sizeof(float), st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, wrap_bad, g_lag_nc, g_tile_stats);
+        fpm_launch_counter++;
+    }
+    const long long nrest = np - ntile;
+    if (nrest > 0) {
+        const unsigned grid = (unsigned) ((nrest + 255) / 256);
+        int lag_nc = 0;
+        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc);
+        #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick, ntile)
+        if (nbrick > 0) fpm_path_counter[FPM_PATH_PAINT_BRICKS]++;
+        if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
+        else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
+        #undef PAINT_LAUNCH
+    }
     if (fpm_prof_on) fpm_prof_end(FPM_K_PAINT, st);
-    #undef PAINT_LAUNCH
     FPM_CHECK_LAUNCH();
     return 0;
 }
@@ -351,11 +701,23 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
                        double prescale, long long np, cudaStream_t st)
 {
     if (np <= 0) return 0;
-    const unsigned grid = (unsigned) ((np + 255) / 256);
-    int lag_nc = 0;
-    const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
-    if (nbrick > 0) fpm_path_counter[FPM_PATH_READOUT_BRICKS]++;
-    FPM_TIMED(FPM_K_READOUT, st, (cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick)));
+    const long long ntile = fpm_tile_particles(np, m->geom);
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_READOUT, st);
+    if (ntile > 0) {
+        if (tile_attrs()) return -1;
+        fpm_path_counter[FPM_PATH_READOUT_TILES]++;
+        cic_readout_tile_kernel<<<(unsigned) (ntile / FPM_TILE_THREADS), FPM_TILE_THREADS, FPM_TILE_CAP * sizeof(float), st>>>(m->geom, canvas, x, out, out_stride, prescale, g_lag_nc, g_tile_stats ? g_tile_stats + 2 : nullptr);
+        fpm_launch_counter++;
+    }
+    const long long nrest = np - ntile;
+    if (nrest > 0) {
+        const unsigned grid = (unsigned) ((nrest + 255) / 256);
+        int lag_nc = 0;
+        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc);
+        if (nbrick > 0) fpm_path_counter[FPM_PATH_READOUT_BRICKS]++;
+        cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick, ntile);
+    }
+    if (fpm_prof_on) fpm_prof_end(FPM_K_READOUT, st);
     FPM_CHECK_LAUNCH();
     return 0;
 }

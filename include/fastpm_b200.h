@@ -57,7 +57,8 @@ uint64_t fpm_kernel_launch_count(void);                /* kernels launched by th
 /* launches so far by code path, for tests that must know WHICH kernels a run went through; out[i], i < n, in the order:
  * TMA tile pass (one GPU), generic tile pass, row (z) pass with bulk copies, generic z pass, TMA tile pass with several
  * destinations (slab transpose), paint with the brick walk, readout with the brick walk, P(k) accumulated inside the forward
- * x-pass, staged slab transposes.  Returns the number of counters the library keeps. */
+ * x-pass (unused: the row-streaming P(k) kernel is counted here), staged slab transposes, paint through shared-memory tiles,
+ * readout through shared-memory tiles.  Returns the number of counters the library keeps. */
 int fpm_path_counts(uint64_t *out, int n);
 /* optional per-kernel-class timing with CUDA events on the launching stream (off by default); classes in order:
  * paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other, memset, barrier (cross-GPU, includes the wait for
@@ -88,6 +89,12 @@ int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np,
  * bricks for L2 locality when the mesh is large.  nc = 0 clears the hint.  Results do not depend on it (any traversal order
  * is valid, every particle is visited exactly once). */
 int fpm_particle_grid_hint(int nc);
+/* With the hint set and Nmesh / nc <= 2.5 the deposit and the gather run through shared-memory tiles: a CTA takes an 8 x 8 x 8
+ * brick of the particle grid, accumulates / stages the box of mesh cells it touches in shared memory and moves that box to / from
+ * the mesh in aligned 16-byte groups; particles far from their brick's box (and stores that are not in grid order) use global
+ * reductions / loads, so results never depend on the order.  Diagnostic counters, kept when FASTPM_B200_TILE_STATS is set in the
+ * environment: out4 = { deposit: particles that took the global path, CTAs without a tile; gather: the same two }. */
+int fpm_tile_stats(uint64_t *out4);
 /* ---- K5 CIC readout: fastpm_readout_local + cic_readout_tuned, painter.c:358 / painter-cic.c:113 */
 /* out[i*out_stride] = (float) sum_8 (float)(canvas * prescale) * w   (prescale 1.0 = none) */
 int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np,

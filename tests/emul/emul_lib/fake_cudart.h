@@ -22,6 +22,8 @@ static inline void atomicAdd(float2 *p, float2 v) { atomicAdd(&p->x, v.x); atomi
 static inline void atomicAdd(float4 *p, float4 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); atomicAdd(&p->z, v.z); atomicAdd(&p->w, v.w); }
 static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return o; }
+static inline int atomicMax(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return o; }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline void __threadfence_system() { __sync_synchronize(); }
@@ -39,7 +41,7 @@ static void fpm_emul_launch_auto(const char *name, unsigned grid, unsigned block
 {
     // kernels with barriers or warp shuffles need one OS thread per CUDA thread; all others run their threads one after the other
     const std::string n(name);
-    const bool threaded = n.find("fft_") != std::string::npos || n.find("powerspectrum") != std::string::npos || n.find("summary") != std::string::npos;
+    const bool threaded = n.find("fft_") != std::string::npos || n.find("powerspectrum") != std::string::npos || n.find("summary") != std::string::npos || n.find("_tile_kernel") != std::string::npos;
     if (threaded) { fpm_emul_sequential = false; fpm_emul_launch(grid, block, smem, kernel); return; }
     fpm_emul_sequential = true;
     gridDim.x = grid; blockDim.x = block;

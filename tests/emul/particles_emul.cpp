@@ -11,10 +11,21 @@
 #include <cmath>
 #include <string>
 #include <cuda_runtime.h>
-static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
-static inline void atomicAdd(float2 *p, float2 v) { p->x += v.x; p->y += v.y; }
-static inline void atomicAdd(float4 *p, float4 v) { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }
-static inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
+// real atomics: the tile kernels run with one OS thread per CUDA thread (the others one thread after the other, where these are plain updates)
+static inline float atomicAdd(float *p, float v)
+{
+    unsigned int *u = reinterpret_cast<unsigned int *>(p), o = __atomic_load_n(u, __ATOMIC_RELAXED), n;
+    float of;
+    do { memcpy(&of, &o, 4); const float nf = of + v; memcpy(&n, &nf, 4); } while (!__atomic_compare_exchange_n(u, &o, n, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return of;
+}
+static inline void atomicAdd(float2 *p, float2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+static inline void atomicAdd(float4 *p, float4 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); atomicAdd(&p->z, v.z); atomicAdd(&p->w, v.w); }
+static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return o; }
+static inline int atomicMax(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return o; }
 #include "../../fastpm_b200/csrc/paint.cu"
 #include "../../fastpm_b200/csrc/particles.cu"
 
@@ -63,11 +74,11 @@ int main(int argc, char **argv)
         int bad = 0;
         if (op == "paint") {
             auto k = [&]() {
-                if (wrap) { if (vec == 4) cic_paint_kernel<4, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick);
-                            else cic_paint_kernel<0, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick); }
-                else { if (vec == 4) cic_paint_kernel<4, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick);
-                       else if (vec == 2) cic_paint_kernel<2, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick);
-                       else cic_paint_kernel<0, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick); }
+                if (wrap) { if (vec == 4) cic_paint_kernel<4, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0);
+                            else cic_paint_kernel<0, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0); }
+                else { if (vec == 4) cic_paint_kernel<4, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0);
+                       else if (vec == 2) cic_paint_kernel<2, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0);
+                       else cic_paint_kernel<0, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0); }
             };
             launch_seq(grid, 256, k);
             std::vector<float> dense((size_t) n * n * n);            // unpadded [x][y][z]
@@ -79,9 +90,45 @@ int main(int argc, char **argv)
             std::vector<float> dense = in.many<float>((size_t) n * n * n);
             for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
             std::vector<float> res((size_t) np, 0.f);
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick, 0); });
             dump(out, res);
         }
+    } else if (op == "tpaint" || op == "treadout") {
+        // the shared-memory tile kernels (one OS thread per CUDA thread).  in: as for paint / readout, plus int32 nranks, rank after M0's
+        // np; lag_nc a multiple of 8, np a multiple of 8 lag_nc^2.  Several "ranks": x-slab geometry of one of them, canvas with the
+        // halo plane, particles of that slab only.  out: the canvas rows / readout values, then uint64 stats[2] (particles on the
+        // global path, CTAs without a tile)
+        const int n = in.one<int32_t>(), lag_nc = in.one<int32_t>(), wrap = in.one<int32_t>(), vec = in.one<int32_t>();
+        const double L = in.one<double>(), M0 = in.one<double>();
+        const long long np = in.one<int64_t>();
+        const int nranks = in.one<int32_t>(), rank = in.one<int32_t>();
+        (void) vec;
+        std::vector<double> x = in.many<double>((size_t) 3 * np);
+        FpmGeom g = geom(n, L);
+        g.nranks = nranks; g.rank = rank; g.nxl = n / nranks; g.x0 = rank * g.nxl;
+        const int planes = g.nxl + (nranks > 1 ? 1 : 0);
+        std::vector<float> canvas((size_t) planes * n * g.pitch_r, 0.f);
+        const unsigned grid = (unsigned) (np / FPM_TILE_THREADS);
+        unsigned long long stats[2] = { 0, 0 };
+        int bad = 0;
+        if (op == "tpaint") {
+            fpm_emul_launch(grid, FPM_TILE_THREADS, FPM_TILE_CAP * sizeof(float), [&]() {
+                if (wrap) cic_paint_tile_kernel<true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, &bad, lag_nc, stats);
+                else cic_paint_tile_kernel<false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, nullptr, lag_nc, stats);
+            });
+            std::vector<float> dense((size_t) planes * n * n);
+            for (int i = 0; i < planes; i++) for (int j = 0; j < n; j++) memcpy(&dense[((size_t) i * n + j) * n], &canvas[((size_t) i * n + j) * g.pitch_r], sizeof(float) * n);
+            dump(out, dense);
+            dump(out, x);
+            std::vector<int32_t> flag(1, bad); dump(out, flag);
+        } else {
+            std::vector<float> dense = in.many<float>((size_t) planes * n * n);
+            for (int i = 0; i < planes; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
+            std::vector<float> res((size_t) np, 0.f);
+            fpm_emul_launch(grid, FPM_TILE_THREADS, FPM_TILE_CAP * sizeof(float), [&]() { cic_readout_tile_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, lag_nc, stats); });
+            dump(out, res);
+        }
+        std::vector<uint64_t> st(stats, stats + 2); dump(out, st);
     } else if (op == "wpaint" || op == "wreadout") {
         // in: int32 n, int32 type, int32 support, float64 L, float64 M0, int64 np, x[np][3] f64, (wreadout: dense canvas f32[n^3])
         const int n = in.one<int32_t>(), type = in.one<int32_t>();
@@ -125,7 +172,7 @@ int main(int argc, char **argv)
         if (lag_nc) nbrick = (int) ((np / (4LL * lag_nc * lag_nc)) * (4LL * lag_nc * lag_nc) / 256);
         std::vector<float> sep((size_t) 3 * np, -7.f), one((size_t) 3 * np, -9.f);
         for (int d = 0; d < 3; d++)
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick, 0); });
         launch_seq(grid, 256, [&]() { cic_readout3_kernel(g, canvas[0].data(), canvas[1].data(), canvas[2].data(), x.data(), one.data(), np, lag_nc, nbrick); });
         dump(out, sep);
         dump(out, one);

