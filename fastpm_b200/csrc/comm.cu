@@ -129,6 +129,7 @@ static int mesh_barrier(FpmMesh *m, cudaStream_t st) { (void) m; return fpm_xbar
 // the transposing pass through m->barrier.
 // local staging mesh for the slab transposes of this mesh (fft.cu: staged_transpose); NULL = direct peer stores
 extern "C" int fpm_mesh_set_stage(fpm_mesh *m, float *stage) { m->stage = stage; return 0; }
+extern "C" int fpm_mesh_set_stage2(fpm_mesh *m, float *stage) { m->stage2 = stage; return 0; }
 
 int fpm_lazy_touch(const void *p, size_t bytes);      // capi.cu: applies a deferred deconvolution of that buffer first
 extern "C" int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale)
@@ -150,6 +151,27 @@ extern "C" int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_p
         return fpm_fft_c2r(m, cplx, real_peers, NULL, &s, comm_stream());
     }
     return fpm_fft_c2r(m, cplx, real_peers, NULL, NULL, comm_stream());
+}
+
+static void to_spec(const fpm_transfer *kernel, FpmTransferSpec *s)
+{
+    s->active = kernel->active; s->potorder = kernel->potorder; s->negate = kernel->negate; s->ngrad = kernel->ngrad;
+    s->graddir[0] = kernel->graddir[0]; s->graddir[1] = kernel->graddir[1]; s->gradorder = kernel->gradorder;
+    s->zero_selfconj = kernel->zero_selfconj; s->scale = kernel->scale;
+}
+// the two halves of fpm_c2r_dist (fft.cu: fpm_fft_c2r_begin / _finish); `set` selects the staging mesh and the events
+extern "C" int fpm_c2r_dist_begin(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel, int set)
+{
+    if (fpm_lazy_touch(cplx, 0) || fpm_lazy_touch(real_peers[m->geom.rank], 0)) return -1;
+    m->barrier = mesh_barrier;
+    FpmTransferSpec s;
+    if (kernel && kernel->active) { to_spec(kernel, &s); return fpm_fft_c2r_begin(m, cplx, real_peers, &s, set, comm_stream()); }
+    return fpm_fft_c2r_begin(m, cplx, real_peers, NULL, set, comm_stream());
+}
+extern "C" int fpm_c2r_dist_finish(fpm_mesh *m, float *const *real_peers, int set)
+{
+    m->barrier = mesh_barrier;
+    return fpm_fft_c2r_finish(m, real_peers, NULL, set, comm_stream());
 }
 
 // ------------------------------------------------------------------ halo planes

@@ -328,9 +328,23 @@ static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaSt
 // half of the link rate.  Staged: the pass writes into a LOCAL buffer laid out [destination rank][its row][my plane][kz],
 // chunk of planes by chunk, and each finished chunk is pushed to its owners by the copy engines as large 2-D copies on a second
 // stream while the next chunk is being transformed -- NVLink runs at its bulk rate, overlapped with the arithmetic.
+// Two sets of events / staging meshes (`set` 0 and 1): the pushes of one transform may still be in flight while the next
+// transform's transposing pass fills the other staging mesh (pipelined inverse transforms of the force components, host/gravity.c).
 static cudaStream_t g_copy_stream = nullptr;
-static cudaEvent_t g_ev_chunk[8], g_ev_done;
-static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float *const *final_peers, int nouter, int off0, cudaStream_t st)
+static cudaEvent_t g_ev_chunk[2][16], g_ev_done[2];
+static int g_push_pending[2] = { 0, 0 };
+// waits (on the compute stream) for the pushes of `set` issued by the last staged_transpose
+static int staged_transpose_wait(int set, cudaStream_t st)
+{
+    if (!g_push_pending[set]) return 0;
+    // the exposed tail of the pushes: time between the end of the work queued before this point and the arrival of the last copy
+    if (fpm_prof_on) fpm_prof_begin(FPM_K_PUSH, st);
+    FPM_CUDA_OK(cudaStreamWaitEvent(st, g_ev_done[set], 0));
+    if (fpm_prof_on) fpm_prof_end(FPM_K_PUSH, st);
+    g_push_pending[set] = 0;
+    return 0;
+}
+static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float *const *final_peers, int nouter, int off0, int set, cudaStream_t st)
 {
     const FpmGeom &g = m->geom;
     const FpmFftPlan *p = m->plan;
@@ -338,18 +352,23 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
     const size_t pc = (size_t) g.pitch_c, plane = (size_t) n * pc;
     if (!g_copy_stream) {
         FPM_CUDA_OK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; i++) FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_chunk[i], cudaEventDisableTiming));
-        FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_done, cudaEventDisableTiming));
+        for (int s2 = 0; s2 < 2; s2++) {
+            for (int i = 0; i < 16; i++) FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_chunk[s2][i], cudaEventDisableTiming));
+            FPM_CUDA_OK(cudaEventCreateWithFlags(&g_ev_done[s2], cudaEventDisableTiming));
+        }
     }
     fpm_path_counter[FPM_PATH_STAGED_TRANSPOSE]++;
-    float2 *stage = reinterpret_cast<float2 *>(m->stage);
+    float2 *stage = reinterpret_cast<float2 *>(set ? m->stage2 : m->stage);
     const size_t blk = (size_t) per * nouter * pc;          // one destination's block: [per rows][nouter planes][pitch_c]
     // my own rows keep the direct destination the caller set up (final layout); everybody else's go to their staging block
     a.self_rank = g.rank; a.self_dst = a.dst[g.rank]; a.self_estride = a.dst_estride; a.self_ostride = a.dst_ostride;
     const int self_ooffset0 = a.dst_ooffset;
     for (int d = 0; d < G; d++) a.dst[d] = stage + (size_t) d * blk;
     a.rows_per_rank = per; a.dst_estride = (size_t) nouter * pc; a.dst_ostride = pc;
-    int nch = nouter >= 64 ? 4 : 1;
+    // chunks of planes: every finished chunk is pushed while the next is transformed; the last chunk's push is the exposed tail
+    static int want_chunks = -1;       // FASTPM_B200_TRANSPOSE_CHUNKS (default 8; round 1 used 4: the tail was 12 ms per step on 2 GPUs)
+    if (want_chunks < 0) { const char *e = getenv("FASTPM_B200_TRANSPOSE_CHUNKS"); want_chunks = e ? atoi(e) : 8; if (want_chunks < 1) want_chunks = 1; if (want_chunks > 16) want_chunks = 16; }
+    int nch = nouter >= 16 * want_chunks ? want_chunks : (nouter >= 64 ? 4 : 1);
     while (nouter % nch) nch--;
     const int cp = nouter / nch;
     const int outer0 = a.outer0;
@@ -359,8 +378,8 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
         a.self_ooffset = self_ooffset0 + ch * cp;
         a.outer0 = outer0 + ch * cp;
         if (launch_tile(p, a, cp, st)) return -1;
-        FPM_CUDA_OK(cudaEventRecord(g_ev_chunk[ch], st));
-        FPM_CUDA_OK(cudaStreamWaitEvent(g_copy_stream, g_ev_chunk[ch], 0));
+        FPM_CUDA_OK(cudaEventRecord(g_ev_chunk[set][ch], st));
+        FPM_CUDA_OK(cudaStreamWaitEvent(g_copy_stream, g_ev_chunk[set][ch], 0));
         for (int dd = 0; dd < G - 1; dd++) {
             const int d = (g.rank + 1 + dd) % G;            // start with the neighbour: spreads the traffic over the links
             // my planes [off0 + ch*cp, +cp) of every row kl that rank d owns: final[d][kl][off0 + ch*cp ..][kz]
@@ -370,11 +389,8 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
                                           (size_t) cp * pc * sizeof(float2), per, cudaMemcpyDeviceToDevice, g_copy_stream));
         }
     }
-    FPM_CUDA_OK(cudaEventRecord(g_ev_done, g_copy_stream));
-    // the exposed tail of the pushes: time between the last chunk's kernel and the arrival of the last copy, on the compute stream
-    if (fpm_prof_on) fpm_prof_begin(FPM_K_PUSH, st);
-    FPM_CUDA_OK(cudaStreamWaitEvent(st, g_ev_done, 0));
-    if (fpm_prof_on) fpm_prof_end(FPM_K_PUSH, st);
+    FPM_CUDA_OK(cudaEventRecord(g_ev_done[set], g_copy_stream));
+    g_push_pending[set] = 1;
     return 0;
 }
 
@@ -401,7 +417,7 @@ int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cpl
     for (int d = 0; d < g.nranks; d++) a.dst[d] = reinterpret_cast<float2 *>(cplx_peers[d]);
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.x0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 0; a.outer0 = g.x0; a.t = p->tN; a.xfer.active = 0; a.kt = m->ktab;
-    if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, cplx_peers, g.nxl, g.x0, st)) return -1; }
+    if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, cplx_peers, g.nxl, g.x0, 0, st) || staged_transpose_wait(0, st)) return -1; }
     else if (launch_tile(p, a, g.nxl, st)) return -1;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // F3: in place on the local k-space buffer: outer = local ky plane, rows = kx
@@ -416,7 +432,11 @@ int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cpl
 // Backward: cplx (preserved) -> real field, optionally multiplied by a k-space kernel on the way in.
 // real_peers[d] is rank d's work buffer for the x- and y-pass; the last (z) pass writes `real_out`, which may
 // be real_peers[rank] itself or any other buffer (e.g. cplx, for the in-place public pm_c2r).
-int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *real_out, const FpmTransferSpec *xfer, cudaStream_t st)
+// Two halves, so that on several GPUs the slab transpose of one field can travel while another field is finished and read out:
+//   begin   barrier, B1 (x-pass, transposing, kernel fused in) into the peers' buffers -- with a staging mesh the copy-engine
+//           pushes of `set` are left in flight;
+//   finish  waits for those pushes, barrier, B2 (y-pass) and B3 (z-pass) in place.
+int fpm_fft_c2r_begin(FpmMesh *m, const float *cplx, float *const *real_peers, const FpmTransferSpec *xfer, int set, cudaStream_t st)
 {
     const FpmGeom &g = m->geom;
     const FpmFftPlan *p = m->plan;
@@ -440,20 +460,38 @@ int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *
         a.kkf = m->d_kkf[pi][gi];
     }
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
-    if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, real_peers, g.nyl, g.y0, st)) return -1; }
+    if (g.nranks > 1 && (set ? m->stage2 : m->stage)) { if (staged_transpose(m, a, a.src, real_peers, g.nyl, g.y0, set, st)) return -1; }
     else if (launch_tile(p, a, g.nyl, st)) return -1;
+    return 0;
+}
+
+int fpm_fft_c2r_finish(FpmMesh *m, float *const *real_peers, float *real_out, int set, cudaStream_t st)
+{
+    const FpmGeom &g = m->geom;
+    const FpmFftPlan *p = m->plan;
+    const int n = g.n;
+    const size_t plane = (size_t) n * g.pitch_c;
+    if (g.nranks > 1 && staged_transpose_wait(set, st)) return -1;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // B2: in place, outer = local x plane, rows = ky
     float *real = real_peers[g.rank];
-    TilePassArgs b = a;
-    b.xfer.active = 0;
-    b.src = reinterpret_cast<const float2 *>(real); b.dst[0] = reinterpret_cast<float2 *>(real);
+    TilePassArgs b = {};
+    b.self_rank = -1; b.conj = 1; b.t = p->tN; b.kt = m->ktab; b.xfer.active = 0;
+    b.ntile_k = (n / 2 + 1 + p->K - 1) / p->K;
+    b.src = reinterpret_cast<const float2 *>(real); b.src_estride = g.pitch_c; b.src_ostride = plane;
+    b.dst[0] = reinterpret_cast<float2 *>(real);
     b.rows_per_rank = n; b.dst_estride = g.pitch_c; b.dst_ostride = plane; b.dst_ooffset = 0; b.outer0 = g.x0;
     if (launch_tile(p, b, g.nxl, st)) return -1;
     // B3
     ZPassArgs z; z.src = real; z.dst = real_out ? real_out : real; z.nrows = (size_t) g.nxl * n; z.pitch_c = g.pitch_c; z.scale = 1.f; z.th = p->tH; z.twN = p->d_twN;
     if (launch_z(p, z, 0, st)) return -1;
     return 0;
+}
+
+int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *real_out, const FpmTransferSpec *xfer, cudaStream_t st)
+{
+    if (fpm_fft_c2r_begin(m, cplx, real_peers, xfer, 0, st)) return -1;
+    return fpm_fft_c2r_finish(m, real_peers, real_out, 0, st);
 }
 
 // adapter: the generic tile-pass description -> the TMA kernel's arguments (fft_tma.cu)

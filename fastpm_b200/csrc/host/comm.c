@@ -17,6 +17,9 @@ int fpm_xbarrier_init(int nranks, int rank, void *local_flags);
 int fpm_xbarrier_set_peers(void *const *peer_flag_ptrs);
 int fpm_xbarrier(void);
 int fpm_mesh_set_stage(fpm_mesh *m, float *stage);
+int fpm_mesh_set_stage2(fpm_mesh *m, float *stage);
+int fpm_c2r_dist_begin(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel, int set);
+int fpm_c2r_dist_finish(fpm_mesh *m, float *const *real_peers, int set);
 int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scale);
 int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel);
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
@@ -149,6 +152,37 @@ static void ensure_stage(PM *pm)
     if (fastpm_b200_arena_largest_free() < need + need / 8) { pm->stage_off = 1; return; }
     pm->stage = fastpm_memory_alloc(pm->mem, "FFT transpose staging", need, FASTPM_MEMORY_FLOATING);
     FPM_MUST(fpm_mesh_set_stage(pm->mesh, pm->stage));
+}
+
+/* Pipelined inverse transforms (host/gravity.c): the second staging mesh, taken once and only when every rank has room for it
+ * beside one more canvas (all ranks see the same arena state, the decision is the same everywhere).  Returns 1 when available. */
+int fpm_dist_pipeline_ready(PM *pm)
+{
+    ensure_stage(pm);
+    if (!pm->stage || getenv("FASTPM_B200_NO_PIPELINE")) return 0;
+    const size_t need = sizeof(FastPMFloat) * pm->allocsize;
+    if (!pm->stage2) {
+        if (pm->stage2_off) return 0;
+        if (fastpm_b200_arena_largest_free() < 2 * (need + need / 8)) { pm->stage2_off = 1; return 0; }      /* stage 2 and the second canvas */
+        pm->stage2 = fastpm_memory_alloc(pm->mem, "FFT transpose staging (second set)", need, FASTPM_MEMORY_FLOATING);
+        FPM_MUST(fpm_mesh_set_stage2(pm->mesh, pm->stage2));
+    }
+    return fastpm_b200_arena_largest_free() >= need + need / 8;                                               /* the second canvas */
+}
+
+void fpm_dist_c2r_begin(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel, int set)
+{
+    void *peers[MAXR];
+    if (real == cplx) fastpm_raise(-1, "distributed c2r is out of place\n");
+    peers_of(real, peers);
+    FPM_MUST(fpm_c2r_dist_begin(pm->mesh, cplx, (float *const *) peers, kernel, set));
+}
+
+void fpm_dist_c2r_finish(PM *pm, FastPMFloat *real, int set)
+{
+    void *peers[MAXR];
+    peers_of(real, peers);
+    FPM_MUST(fpm_c2r_dist_finish(pm->mesh, (float *const *) peers, set));
 }
 
 void fpm_dist_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale)

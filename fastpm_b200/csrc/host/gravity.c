@@ -163,6 +163,39 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         pm_free(pm, cv[1]);
         d0 = 3;
     }
+    if (d0 == 0 && pm->NTask > 1 && fpm_dist_pipeline_ready(pm)) {
+        /* Several GPUs: the slab transpose of component d + 1 travels (copy engines, NVLink) while component d is finished
+         * (y- and z-pass) and read out -- two canvases and two staging meshes, used alternately.  The arithmetic of every
+         * component is that of fpm_mesh_c2r + readout; only the order in which the work is queued differs. */
+        FastPMFloat *cv[2] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__) };
+        fpm_transfer t;
+        ENTER(c2r);
+        if (fpm_transfer_for_kernel((int) kernel, 0, 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        fpm_dist_c2r_begin(pm, delta_k, cv[0], &t, 0);
+        LEAVE(c2r);
+        for (int d = 0; d < nacc; d++) {
+            ENTER(c2r);
+            if (d + 1 < nacc) {
+                const int e = d + 1;
+                if (fpm_transfer_for_kernel((int) kernel, e < 3 ? 0 : 1, e < 3 ? e : 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+                fpm_dist_c2r_begin(pm, delta_k, cv[e & 1], &t, e & 1);
+            }
+            fpm_dist_c2r_finish(pm, cv[d & 1], d & 1);
+            fpm_halo_fetch(pm, cv[d & 1]);
+            LEAVE(c2r);
+            ENTER(readout);
+            for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
+                FastPMStore *p = fastpm_solver_get_species(fastpm, si);
+                if (!p) continue;
+                FastPMFieldDescr f = { d < 3 ? COLUMN_ACC : COLUMN_POTENTIAL, d < 3 ? d : 0 };
+                if (d == 3 && !p->potential) continue;
+                fastpm_readout_local(painter, cv[d & 1], p, p->np, f);
+            }
+            LEAVE(readout);
+        }
+        pm_free(pm, cv[1]);
+        d0 = nacc;
+    }
     for (int d = d0; d < nacc; d++) {
         fpm_transfer t;
         if (fpm_transfer_for_kernel((int) kernel, d < 3 ? 0 : 1, d < 3 ? d : 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());

@@ -30,6 +30,8 @@ struct PM {
     FastPMFloat *scratch;         /* lazily allocated, for the in-place public pm_c2r / pm_r2c */
     FastPMFloat *stage;           /* several GPUs: staging mesh of the slab transposes (lazily allocated) */
     int stage_off;                /* no room for it in the arena: direct peer stores */
+    FastPMFloat *stage2;          /* second staging mesh: pipelined inverse transforms of the force components */
+    int stage2_off;
     int transposed;
     int pitch_r, pitch_c, nxl, x0, nyl, y0, halo;
 };
@@ -60,6 +62,10 @@ void fpm_halo_add(PM *pm, FastPMFloat *canvas);
 void fpm_halo_fetch(PM *pm, FastPMFloat *canvas);
 void fpm_mesh_r2c(PM *pm, FastPMFloat *real, FastPMFloat *cplx, double scale);
 void fpm_mesh_c2r(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel);
+/* several GPUs: the two halves of the inverse transform and the check that a second canvas + staging mesh fit (host/comm.c) */
+int fpm_dist_pipeline_ready(PM *pm);
+void fpm_dist_c2r_begin(PM *pm, const FastPMFloat *cplx, FastPMFloat *real, const fpm_transfer *kernel, int set);
+void fpm_dist_c2r_finish(PM *pm, FastPMFloat *real, int set);
 void fpm_mesh_readout(PM *pm, FastPMFloat *canvas, const double *x, int64_t np, float *out, int stride, double prescale);
 
 /* solver.c: store whose wrap is folded into the next fastpm_paint_local */

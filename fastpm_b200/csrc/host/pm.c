@@ -45,6 +45,7 @@ void pm_delete(PM *pm)
 {
     if (!pm) return;
     if (pm->scratch) fpm_free(pm->scratch);
+    if (pm->stage2) fastpm_memory_free(pm->mem, pm->stage2);
     if (pm->stage) fastpm_memory_free(pm->mem, pm->stage);
     fpm_mesh_destroy(pm->mesh);
     free(pm);

@@ -259,13 +259,12 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
 // quarter of the HBM rate.  Here a warp takes one k-space row (ky, kx fixed) at a time and every lane owns a CONTIGUOUS chunk
 // of CH = (N/2)/32 modes of it: along kz the shell index is non-decreasing, so a lane walks runs of equal bin, keeps the
 // running sum of |delta|^2 in a register and touches the histogram only when the bin changes.
-//   * rows travel global -> shared memory with 16-byte cp.async copies (coalesced, no registers), the next row in flight while
-//     this one is processed; mode m sits at position m + 2*min(m / CH, 31), so that the lanes' 16-byte reads are bank-conflict free;
-//   * the bin is tracked incrementally (kk grows by 2 iz + 1 per step; bin advances while (bin+1)^2 <= kk): no square roots
-//     except one per chunk;
-//   * each warp has a private histogram; the runs a lane flushes while it walks are bins no other lane of the warp can touch
-//     (its first run, which may continue the previous lane's last one, is held back and merged once per row with a segmented
-//     shuffle reduction): plain read-modify-writes, no atomics;
+//   * rows travel global -> shared memory with 16-byte cp.async copies (coalesced, no registers); mode m sits at position
+//     m + 2*min(m / CH, 31), so that the lanes' 16-byte reads are bank-conflict free; many warps per SM hide the latency;
+//   * the bin is tracked incrementally: kk grows by 2 iz + 1 per step, which is at most (bin+1)^2 - bin^2 because bin >= iz,
+//     so the bin advances by at most one per step -- one square root per chunk, no loop;
+//   * one histogram per CTA in shared memory, updated with atomicAdd(double) when a run ends (a compare-and-swap loop, measured
+//     at a fraction of a cycle per lane on B200 -- scripts/ubench/atomics.cu -- and needed only every few modes);
 //   * interior modes have weight 2, the two ends of a row weight 1 (powerspectrum.c:94): runs accumulate |delta|^2 (ends: half of
 //     it) and are doubled when flushed -- scaling by 2 is exact, so this is the sum of w |delta|^2 in another order.
 // The deconvolution (solver.c:471, transfer.c:78-113) is folded into the read exactly as above: the mode is multiplied by
@@ -277,14 +276,22 @@ __device__ __forceinline__ void pk_cp16(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void pk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void pk_cp_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void pk_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else
 inline void pk_cp16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
 inline void pk_cp_commit() {}
-inline void pk_cp_wait_all_but_one() {}
 inline void pk_cp_wait_all() {}
 #endif
+
+__device__ __forceinline__ double pk_round_to_float(double t)
+{
+    unsigned long long u;
+    memcpy(&u, &t, 8);
+    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+    u &= ~0x1FFFFFFFull;
+    memcpy(&t, &u, 8);
+    return t;
+}
 
 __global__ void __launch_bounds__(32 * PKR_WARPS) powerspectrum_rows_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
         const float2 *__restrict__ dk, double *__restrict__ out /* [nbins] + 1 */)
@@ -293,43 +300,41 @@ __global__ void __launch_bounds__(32 * PKR_WARPS) powerspectrum_rows_kernel(cons
     const int n = g.n, h = n / 2, nbins = h, CH = h / 32;
     const int RB = h + 66;                                       // positions of one staged row (h + 1 modes, 2 pad per chunk), even
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *dts = reinterpret_cast<double *>(smem_raw);                                          // [RB] deconvolution factors along z, staged like a row
-    double *hist_all = dts + RB;                                                                  // [PKR_WARPS][nbins + 1]
-    float2 *rows_all = reinterpret_cast<float2 *>(hist_all + (size_t) PKR_WARPS * (nbins + 1));   // [PKR_WARPS][2][RB]
-    for (int i = threadIdx.x; i < PKR_WARPS * (nbins + 1); i += blockDim.x) hist_all[i] = 0;
-    for (int m = threadIdx.x; m <= h; m += blockDim.x) dts[m + 2 * (m / CH > 31 ? 31 : m / CH)] = decic ? dtab[m] : 1.0;      // iz = h follows lane 31's chunk
+    double *dts = reinterpret_cast<double *>(smem_raw);                      // [RB] deconvolution factors along z, staged like a row
+    double *hist = dts + RB;                                                  // [nbins + 1], one per CTA
+    float2 *rowbuf = reinterpret_cast<float2 *>(hist + nbins + 2) + (size_t) warp * RB;      // [PKR_WARPS][RB]
+    const unsigned chinv = (65536u + CH - 1) / CH;               // m / CH == (m * chinv) >> 16 for m < 8192
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) hist[i] = 0;
+    for (int m = threadIdx.x; m <= h; m += blockDim.x) {
+        const int c = (int) ((m * chinv) >> 16);
+        dts[m + 2 * (c > 31 ? 31 : c)] = decic ? dtab[m] : 1.0;           // iz = h follows lane 31's chunk
+    }
     __syncthreads();
-    double *hist = hist_all + (size_t) warp * (nbins + 1);
-    float2 *rowbuf = rows_all + (size_t) warp * 2 * RB;
-    const size_t nrows = (size_t) g.nyl * n;
-    const size_t wstride = (size_t) gridDim.x * PKR_WARPS;
+    const int nrows_i = g.nyl * n;                               // < 2^31 for every supported mesh
+    const int wstride = (int) gridDim.x * PKR_WARPS;
     const int nq = (h + 2) / 2;                                  // float4 (two modes) per row, including the pair that holds iz = h
-
-    auto fetch = [&](size_t row, int buf) {
-        const float4 *src = reinterpret_cast<const float4 *>(dk + row * (size_t) g.pitch_c);
-        float2 *dst = rowbuf + (size_t) buf * RB;
-        for (int q = lane; q < nq; q += 32) {
-            const int m = 2 * q;                                 // CH is even: both modes of the pair fall into the same chunk
-            pk_cp16(dst + m + 2 * (m / CH > 31 ? 31 : m / CH), src + q);
-        }
-        pk_cp_commit();
-    };
-
-    size_t row = (size_t) blockIdx.x * PKR_WARPS + warp;
-    int cur = 0;
-    if (row < nrows) fetch(row, 0);
+    int row = (int) blockIdx.x * PKR_WARPS + warp;
+    int ix = row % n, iyl = row / n;
+    const int dix = wstride % n, diy = wstride / n;
     double allsum = 0;
-    for (; row < nrows; row += wstride) {
-        const size_t nxt = row + wstride;
-        if (nxt < nrows) { fetch(nxt, cur ^ 1); pk_cp_wait_all_but_one(); } else pk_cp_wait_all();
-        __syncwarp();
-        const int ix = (int) (row % n), iy = (int) (row / n) + g.y0;
+    const int iz0 = lane * CH;
+    const float2 *src = rowbuf + iz0 + 2 * lane;
+    const double *dsrc = dts + iz0 + 2 * lane;
+    for (; row < nrows_i; row += wstride) {
+        {
+            const float4 *gsrc = reinterpret_cast<const float4 *>(dk + (size_t) row * (size_t) g.pitch_c);
+            for (int q = lane; q < nq; q += 32) {
+                const int m = 2 * q;                             // CH is even: both modes of the pair fall into the same chunk
+                const int c = (int) ((m * chinv) >> 16);
+                pk_cp16(rowbuf + m + 2 * (c > 31 ? 31 : c), gsrc + q);
+            }
+            pk_cp_commit();
+        }
+        const int iy = iyl + g.y0;
         const int ikx = ix > h ? ix - n : ix, iky = iy > h ? iy - n : iy;
         const int kxy = ikx * ikx + iky * iky;
         const double dxy = decic ? dtab[ix] * dtab[iy] : 1.0;           // (1 * d[ix]) * d[iy], the reference's order
-        const float2 *rb = rowbuf + (size_t) cur * RB;
-        // this lane's chunk: iz in [iz0, iz0 + CH), staged at iz + 2 * lane; lane 31 also takes iz = h
-        int iz = lane * CH;
+        int iz = iz0;
         int kk = kxy + iz * iz;
         int bin;
         {
@@ -339,65 +344,66 @@ __global__ void __launch_bounds__(32 * PKR_WARPS) powerspectrum_rows_kernel(cons
             if (bin * bin > kk) bin--;
         }
         int next = (bin + 1) * (bin + 1);
-        int run_bin = bin, first_bin = 0x7fffff00 + lane;                // sentinel: no first run yet (distinct per lane)
-        double run = 0, first_sum = 0;
-        bool have_first = false;
-        const float2 *src = rb + iz + 2 * lane;
-        const double *dsrc = dts + iz + 2 * lane;
-        auto step = [&](float2 v, double dz) {
-            while (kk >= next) { bin++; next = (bin + 1) * (bin + 1); }
+        int run_bin = bin;
+        double run = 0;
+        pk_cp_wait_all();
+        __syncwarp();
+        // one mode: bin bookkeeping, deconvolution, |delta|^2 (weight applied by the caller)
+        auto mode_p2 = [&](float2 v, double dz) -> double {
+            const bool up = kk >= next;                                  // at most one shell further than the previous mode
+            bin += up ? 1 : 0;
+            next += up ? 2 * bin + 1 : 0;
             if (bin != run_bin) {
-                if (!have_first) { first_bin = run_bin; first_sum = run; have_first = true; }
-                else if (run_bin < nbins && run != 0) hist[run_bin] += 2.0 * run;
+                if (run_bin < nbins && run != 0) atomicAdd(hist + run_bin, 2.0 * run);
                 run = 0; run_bin = bin;
             }
+            double ax = (double) v.x, ay = (double) v.y;
             if (decic) {
+                // (double) (float) (ax * smth) without the two conversions (the conversion pipe was the busiest unit of this kernel):
+                // round the product to a 24-bit significand, nearest-even, on the bit pattern -- identical for every value in the
+                // normal float range (|x| between 1.2e-38 and 3.4e38; density modes never leave it)
                 const double smth = dxy * dz;
-                v.x = (float) ((double) v.x * smth);
-                v.y = (float) ((double) v.y * smth);
+                ax = pk_round_to_float(ax * smth);
+                ay = pk_round_to_float(ay * smth);
             }
-            double p2 = (double) v.x * (double) v.x + (double) v.y * (double) v.y;
-            if (iz == 0 || iz == h) p2 *= 0.5;                           // weight 1 instead of 2
-            allsum += p2;
-            if (kk != 0) run += p2;                                      // the DC mode belongs to no shell
             kk += 2 * iz + 1;
             iz++;
+            return ax * ax + ay * ay;
         };
-        for (int j = 0; j < CH; j += 2) {                                // two modes per 16-byte read (positions are even)
+        {
+            // first pair of the chunk: holds iz = 0 (weight 1; the DC mode belongs to no shell) for lane 0
+            const float4 vv = *reinterpret_cast<const float4 *>(src);
+            const double2 dd = *reinterpret_cast<const double2 *>(dsrc);
+            const bool first0 = iz == 0, dc = first0 && kxy == 0;
+            double p2 = mode_p2(make_float2(vv.x, vv.y), dd.x);
+            if (first0) p2 *= 0.5;
+            allsum += p2;
+            if (!dc) run += p2;
+            p2 = mode_p2(make_float2(vv.z, vv.w), dd.y);
+            allsum += p2; run += p2;
+        }
+        for (int j = 2; j < CH; j += 2) {                                // two modes per 16-byte read (positions are even)
             const float4 vv = *reinterpret_cast<const float4 *>(src + j);
             const double2 dd = *reinterpret_cast<const double2 *>(dsrc + j);
-            step(make_float2(vv.x, vv.y), dd.x);
-            step(make_float2(vv.z, vv.w), dd.y);
+            double p2 = mode_p2(make_float2(vv.x, vv.y), dd.x);
+            allsum += p2; run += p2;
+            p2 = mode_p2(make_float2(vv.z, vv.w), dd.y);
+            allsum += p2; run += p2;
         }
-        if (lane == 31) step(src[CH], dsrc[CH]);                         // iz = h
-        if (!have_first) { first_bin = run_bin; first_sum = run; }
-        else if (run_bin < nbins && run != 0) hist[run_bin] += 2.0 * run;
-        __syncwarp();
-        // first runs: contiguous groups of lanes with the same bin (bins are non-decreasing across lanes)
-        {
-            int b = first_bin;
-            double s1 = first_sum;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int ob = __shfl_down_sync(0xffffffffu, b, o);
-                const double o1 = __shfl_down_sync(0xffffffffu, s1, o);
-                if (lane + o < 32 && ob == b) s1 += o1;
-            }
-            const int pb = __shfl_up_sync(0xffffffffu, b, 1);
-            if ((lane == 0 || pb != b) && b < nbins && s1 != 0) hist[b] += 2.0 * s1;
+        if (lane == 31) {                                                // iz = h, weight 1
+            const double p2 = 0.5 * mode_p2(src[CH], dsrc[CH]);
+            allsum += p2; run += p2;
         }
-        __syncwarp();
-        cur ^= 1;
+        if (run_bin < nbins && run != 0) atomicAdd(hist + run_bin, 2.0 * run);
+        __syncwarp();                                                    // every lane is done with the row buffer
+        ix += dix; iyl += diy;
+        if (ix >= n) { ix -= n; iyl++; }
     }
     for (int o = 16; o > 0; o >>= 1) allsum += __shfl_xor_sync(0xffffffffu, allsum, o);
-    if (lane == 0) hist[nbins] += 2.0 * allsum;
+    if (lane == 0) atomicAdd(hist + nbins, 2.0 * allsum);
     __syncthreads();
-    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
-        double t = 0;
-        #pragma unroll
-        for (int w = 0; w < PKR_WARPS; w++) t += hist_all[(size_t) w * (nbins + 1) + i];
-        if (t != 0) atomicAdd(&out[i], t);
-    }
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x)
+        if (hist[i] != 0) atomicAdd(&out[i], hist[i]);
 }
 
 // out[3*nbins + 1] = geometry sums (cached) and data sums laid out as the callers expect: [sum w][sum w |d|^2][sum w k][variance]
@@ -623,13 +629,15 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
     static int rows_mode = -1;        // FASTPM_B200_PK=generic: the shuffle-reduction kernel for every mesh size (cross-check)
     if (rows_mode < 0) { const char *e = getenv("FASTPM_B200_PK"); rows_mode = (e && !strcmp(e, "generic")) ? 0 : 1; }
     const int h = g.n / 2;
-    const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) PKR_WARPS * (nbins + 1) + sizeof(float2) * (size_t) PKR_WARPS * 2 * (h + 66);
-    if (rows_mode && h % 64 == 0 && smem_rows <= 227 * 1024) {
+    const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) (nbins + 2) + sizeof(float2) * (size_t) PKR_WARPS * (h + 66);
+    if (rows_mode && h % 64 == 0 && h <= 4096 && smem_rows <= 227 * 1024 && (size_t) g.nyl * g.n < ((size_t) 1 << 31)) {
         static bool attr_rows = false;
         if (!attr_rows) { FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_rows = true; }
-        const int per_sm = (int) ((227 * 1024) / (smem_rows + 1024));
+        int per_sm = (int) ((227 * 1024) / (smem_rows + 1024));
+        if (per_sm > 6) per_sm = 6;                       // 48 warps per SM
+        if (per_sm < 1) per_sm = 1;
         const size_t nrows = (size_t) g.nyl * g.n;
-        size_t grid = (size_t) 148 * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
+        size_t grid = (size_t) 148 * per_sm;
         if (grid * PKR_WARPS > nrows) grid = (nrows + PKR_WARPS - 1) / PKR_WARPS;
         fpm_path_counter[FPM_PATH_PK_ROWS]++;
         FPM_TIMED(FPM_K_PK, st, (powerspectrum_rows_kernel<<<(unsigned) grid, 32 * PKR_WARPS, smem_rows, st>>>(g, m->d_decic, decic, (const float2 *) dk, d_data)));

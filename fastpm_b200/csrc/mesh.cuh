@@ -88,6 +88,7 @@ struct FpmMesh {
     fpm_barrier_fn barrier; // cross-GPU barrier between a transposing pass and the next (multi-GPU only)
     void *comm;             // opaque communicator (multi-GPU only)
     float *stage;           // multi-GPU: local staging mesh for the slab transpose (NULL: store straight into the peers)
+    float *stage2;          // second staging mesh (pipelined inverse transforms: set 1), NULL when there is no room for it
     float2 *d_kkf[4][2];    // lazily built interleaved tables { kk of potorder - 1 .. 2, k / k_finite } for the fused Green's function (fft.cu)
 };
 
@@ -95,3 +96,5 @@ int fpm_fft_plan_create(int n, FpmFftPlan **out);
 void fpm_fft_plan_destroy(FpmFftPlan *p);
 int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cplx_peers, float scale, cudaStream_t st);
 int fpm_fft_c2r(FpmMesh *m, const float *cplx, float *const *real_peers, float *real_out, const FpmTransferSpec *xfer, cudaStream_t st);
+int fpm_fft_c2r_begin(FpmMesh *m, const float *cplx, float *const *real_peers, const FpmTransferSpec *xfer, int set, cudaStream_t st);
+int fpm_fft_c2r_finish(FpmMesh *m, float *const *real_peers, float *real_out, int set, cudaStream_t st);

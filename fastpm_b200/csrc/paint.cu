@@ -628,7 +628,9 @@ static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc)
 
 // Shared-memory tiles (cic_paint_tile_kernel / cic_readout_tile_kernel): for the leading complete groups of 8 i-planes of a store
 // with the Lagrangian hint, when a brick of 8 particles per side spans at most ~21 mesh cells (Nmesh / nc <= 2.5) and rows can be
-// moved in aligned 16-byte groups.  FASTPM_B200_TILES=0 switches them off (the kernels above then serve everything).
+// moved in aligned 16-byte groups.  OFF by default (FASTPM_B200_TILES=1 switches them on): measured on B200 at nc = 1024 / N = 2048
+// (round 2, gpurun_out/r02b_bench_*.json) the deposit takes 88 ms through the tiles against 42 ms with global reductions and the
+// gather 85 ms against 21 ms -- see DESIGN.md section 3 for why.
 static unsigned long long *g_tile_stats = nullptr;      // [4] device counters when FASTPM_B200_TILE_STATS is set: particles that took
                                                         // the global path and CTAs without a tile, for the deposit and for the gather
 static long long fpm_tile_particles(long long np, const FpmGeom &g)
@@ -636,7 +638,7 @@ static long long fpm_tile_particles(long long np, const FpmGeom &g)
     static int on = -1;
     if (on < 0) {
         const char *e = getenv("FASTPM_B200_TILES");
-        on = (e && atoi(e) == 0) ? 0 : 1;
+        on = (e && atoi(e) != 0) ? 1 : 0;
         if (on && getenv("FASTPM_B200_TILE_STATS") && cudaMalloc(&g_tile_stats, 4 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(g_tile_stats, 0, 4 * sizeof(unsigned long long));
     }

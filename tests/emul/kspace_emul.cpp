@@ -96,7 +96,7 @@ int main(int argc, char **argv)
         const double k0 = 2 * M_PI / L;
         std::vector<double> geom((size_t) 2 * nbins, 0.0), data((size_t) nbins + 1, 0.0), sums((size_t) 3 * nbins + 1);
         fpm_emul_launch(2, 32 * PK_WARPS, sizeof(double) * 2 * nbins * PK_WARPS, [&]() { powerspectrum_kernel<true>(g, dtab.data(), 0, nullptr, k0, geom.data()); });
-        const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) PKR_WARPS * (nbins + 1) + sizeof(float2) * (size_t) PKR_WARPS * 2 * (h + 66);
+        const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) (nbins + 2) + sizeof(float2) * (size_t) PKR_WARPS * (h + 66);
         fpm_emul_launch(3, 32 * PKR_WARPS, smem_rows, [&]() { powerspectrum_rows_kernel(g, dtab.data(), decic, dk.data(), data.data()); });
         gridDim.x = 1; blockDim.x = 256; blockIdx.x = 0;
         for (unsigned t = 0; t < 256; t++) { threadIdx.x = t; pk_assemble_kernel(geom.data(), data.data(), nbins, sums.data()); }
