@@ -376,7 +376,6 @@ void fpm_mesh_destroy(fpm_mesh *m)
     if (!m) return;
     fpm_fft_plan_destroy(m->plan);
     cudaFree(m->d_ktab_store); cudaFree(m->d_decic); cudaFree(m->d_pkgeom);
-    for (int i = 0; i < 4; i++) for (int j = 0; j < 2; j++) cudaFree(m->d_kkf[i][j]);
     delete m;
 }
 

@@ -20,7 +20,6 @@
 
 // ------------------------------------------------------------------ tile pass
 struct TilePassArgs {
-    const float2 *kkf;      // interleaved { kk, kf } row table of xfer (TMA pass only)
     const float2 *src;
     size_t src_estride;     // elements between successive FFT inputs of one column
     size_t src_ostride;     // elements between outer indices
@@ -90,16 +89,6 @@ __global__ void __launch_bounds__(512) fft_tile_kernel(const TilePassArgs a)
             else a.dst[d][(size_t) kl * a.dst_estride + obase] = v;
         }
     }
-}
-
-// { kk[potorder][i], kf[gradorder][i] } per index, for the fused Green's function of the TMA pass (fft_tma.cu)
-__global__ void kkf_table_kernel(const FpmKTables kt, int potorder, int gradorder, float2 *out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kt.n) return;
-    const float *kk = potorder == 1 ? kt.kk_finite : (potorder == 2 ? kt.kk_finite2 : kt.kk);
-    const float *kf = gradorder == 0 ? kt.k : kt.k_finite;
-    out[i] = make_float2(potorder >= 0 ? kk[i] : 0.f, kf[i]);
 }
 
 // ------------------------------------------------------------------ z passes
@@ -450,15 +439,6 @@ int fpm_fft_c2r_begin(FpmMesh *m, const float *cplx, float *const *real_peers, c
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.y0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 1; a.outer0 = g.y0; a.t = p->tN; a.kt = m->ktab;
     if (xfer) a.xfer = *xfer; else a.xfer.active = 0;
-    if (a.xfer.active) {
-        const int pi = a.xfer.potorder < 0 ? 0 : (a.xfer.potorder > 2 ? 3 : a.xfer.potorder + 1), gi = a.xfer.gradorder == 0 ? 0 : 1;
-        if (!m->d_kkf[pi][gi]) {
-            FPM_CUDA_OK(cudaMalloc(&m->d_kkf[pi][gi], sizeof(float2) * n));
-            kkf_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->ktab, a.xfer.potorder, a.xfer.gradorder, m->d_kkf[pi][gi]);
-            FPM_CHECK_LAUNCH();
-        }
-        a.kkf = m->d_kkf[pi][gi];
-    }
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     if (g.nranks > 1 && (set ? m->stage2 : m->stage)) { if (staged_transpose(m, a, a.src, real_peers, g.nyl, g.y0, set, st)) return -1; }
     else if (launch_tile(p, a, g.nyl, st)) return -1;
@@ -502,7 +482,7 @@ int fpm_fft_tma_pass_from_tile(int n, const TilePassArgs &a, int pitch_c, int no
     for (int d = 0; d < FPM_MAX_RANKS; d++) t.dst[d] = a.dst[d];
     t.rows_per_rank = a.rows_per_rank; t.dst_estride = a.dst_estride; t.dst_ostride = a.dst_ostride; t.dst_ooffset = a.dst_ooffset;
     t.self_rank = a.self_rank; t.self_ooffset = a.self_ooffset; t.self_dst = a.self_dst; t.self_estride = a.self_estride; t.self_ostride = a.self_ostride;
-    t.ntile_k = 0; t.nouter = nouter; t.conj = a.conj; t.outer0 = a.outer0; t.tw = a.t.tw; t.xfer = a.xfer; t.kt = a.kt; t.kkf = a.kkf;
+    t.ntile_k = 0; t.nouter = nouter; t.conj = a.conj; t.outer0 = a.outer0; t.tw = a.t.tw; t.xfer = a.xfer; t.kt = a.kt;
     return fpm_fft_tma_pass(n, a.src, pitch_c, nouter, t, st);
 }
 #endif

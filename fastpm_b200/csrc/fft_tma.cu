@@ -118,52 +118,67 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
         if (a.early == 1) { __syncthreads(); prefetch_next(); }
 
         const int iy = a.outer0 + o, iz = kz0 + c;
+        // Per-row factors kk[ix], kf[ix] with ix = t + k * M1 come from the reference-ordered float tables through L1.  The gradient
+        // along the rows (direction 0) has its own loop with a compile-time stride: with a run-time stride (0 for the uniform
+        // directions, M1 for this one) the pass took 27.2 ms at N = 2048 instead of 21.2.  Measured alternatives (round 2,
+        // gpurun_out/r02f_passes_x*.txt): one interleaved { kk, kf } 8-byte load per element 27.5 ms, tables permuted to [t][k]
+        // and read 16 bytes at a time 21.6 ms -- neither beats this form.
         if (xf && iz <= h) {
-            // element by element, in the order of fpm_apply_transfer (mesh.cuh): Green's function, sign, gradients, scale.  The
-            // row-dependent factors kk[ix] (and k_finite[ix] when the first gradient runs along the rows) come from ONE interleaved
-            // table a.kkf = { kk, kf } per row index: one 8-byte load per element instead of two 4-byte ones.
             const float *kkt = a.xfer.potorder == 1 ? a.kt.kk_finite : (a.xfer.potorder == 2 ? a.kt.kk_finite2 : a.kt.kk);
             const float *kft = a.xfer.gradorder == 0 ? a.kt.k : a.kt.k_finite;
             const int ngrad = a.xfer.ngrad;
             const bool has_pot = a.xfer.potorder >= 0, has_scale = a.xfer.scale != 1.0, negate = a.xfer.negate != 0;
             const bool sc_yz = (iy == 0 || iy == h) && (iz == 0 || iz == h);
-            const bool pot_zero = has_pot && iy == 0 && iz == 0 && t == 0;                 // s == 0 (transfer.c:176-181)
-            const bool grad_zero = a.xfer.zero_selfconj && sc_yz && t == 0 && ngrad > 0;   // gravity.c:48-56: ix in {0, N/2}
-            const double yz = has_pot ? (double) __ldg(kkt + iy) + (double) __ldg(kkt + iz) : 0.0;
-            const int dir0 = ngrad > 0 ? a.xfer.graddir[0] : 1, dir1 = ngrad > 1 ? a.xfer.graddir[1] : 1;
-            const float f0u = ngrad > 0 && dir0 != 0 ? __ldg(kft + (dir0 == 1 ? iy : iz)) : 0.f;
-            const float f1u = ngrad > 1 && dir1 != 0 ? __ldg(kft + (dir1 == 1 ? iy : iz)) : 0.f;
-            const bool rowgrad = (ngrad > 0 && dir0 == 0) || (ngrad > 1 && dir1 == 0);
-            #pragma unroll
-            for (int k = 0; k < E; k++) {
-                float2 x = v[k];
-                float2 rowf = make_float2(0.f, 0.f);
-                if (has_pot || rowgrad) rowf = __ldg(a.kkf + t + k * M1);
-                if (has_pot) {
-                    const double sd = yz + (double) rowf.x;
+            if (has_pot) {
+                const double yz = (double) __ldg(kkt + iy) + (double) __ldg(kkt + iz);
+                #pragma unroll
+                for (int k = 0; k < E; k++) {
+                    const float rowkk = __ldg(kkt + t + k * M1);
+                    const double sd = yz + (double) rowkk;
                     const float s_hi = (float) sd;
                     const float s_lo = (float) (sd - (double) s_hi);
                     const float r = fpm_rcp_approx(s_hi);
-                    const float qx = __fmul_rn(x.x, r), qy = __fmul_rn(x.y, r);
-                    const float rx = __fmaf_rn(-qx, s_lo, __fmaf_rn(-qx, s_hi, x.x));
-                    const float ry = __fmaf_rn(-qy, s_lo, __fmaf_rn(-qy, s_hi, x.y));
-                    x.x = __fmaf_rn(rx, r, qx);
-                    x.y = __fmaf_rn(ry, r, qy);
-                    if (k == 0 && pot_zero) x = make_float2(0.f, 0.f);
+                    const float qx = __fmul_rn(v[k].x, r), qy = __fmul_rn(v[k].y, r);
+                    const float rx = __fmaf_rn(-qx, s_lo, __fmaf_rn(-qx, s_hi, v[k].x));
+                    const float ry = __fmaf_rn(-qy, s_lo, __fmaf_rn(-qy, s_hi, v[k].y));
+                    v[k].x = __fmaf_rn(rx, r, qx);
+                    v[k].y = __fmaf_rn(ry, r, qy);
                 }
-                if (negate) { x.x = -x.x; x.y = -x.y; }
-                if (ngrad > 0) {
-                    const float f = dir0 == 0 ? rowf.y : f0u;
-                    x = make_float2(-__fmul_rn(x.y, f), __fmul_rn(x.x, f));
-                    if ((k == 0 || k == E / 2) && grad_zero) x = make_float2(0.f, 0.f);
+                if (iy == 0 && iz == 0 && t == 0) v[0] = make_float2(0.f, 0.f);          // s == 0 (transfer.c:176-181)
+            }
+            if (negate) {
+                #pragma unroll
+                for (int k = 0; k < E; k++) { v[k].x = -v[k].x; v[k].y = -v[k].y; }
+            }
+            #pragma unroll
+            for (int g = 0; g < 2; g++) {
+                if (g < ngrad) {
+                    // factor of element k: direction 0 runs along the rows of the tile (one factor per element), 1 and 2 are uniform
+                    const int dir = a.xfer.graddir[g];
+                    if (dir == 0) {
+                        #pragma unroll
+                        for (int k = 0; k < E; k++) {
+                            const float f = __ldg(kft + t + k * M1);
+                            const float re = -__fmul_rn(v[k].y, f), im = __fmul_rn(v[k].x, f);
+                            v[k].x = re; v[k].y = im;
+                        }
+                    } else {
+                        const float f = __ldg(kft + (dir == 1 ? iy : iz));
+                        #pragma unroll
+                        for (int k = 0; k < E; k++) {
+                            const float re = -__fmul_rn(v[k].y, f), im = __fmul_rn(v[k].x, f);
+                            v[k].x = re; v[k].y = im;
+                        }
+                    }
+                    if (a.xfer.zero_selfconj && sc_yz && t == 0) {                           // gravity.c:48-56: ix in {0, N/2}
+                        v[0] = make_float2(0.f, 0.f);
+                        v[E / 2] = make_float2(0.f, 0.f);
+                    }
                 }
-                if (ngrad > 1) {
-                    const float f = dir1 == 0 ? rowf.y : f1u;
-                    x = make_float2(-__fmul_rn(x.y, f), __fmul_rn(x.x, f));
-                    if ((k == 0 || k == E / 2) && grad_zero) x = make_float2(0.f, 0.f);
-                }
-                if (has_scale) { x.x = (float) ((double) x.x * a.xfer.scale); x.y = (float) ((double) x.y * a.xfer.scale); }
-                v[k] = x;
+            }
+            if (has_scale) {
+                #pragma unroll
+                for (int k = 0; k < E; k++) { v[k].x = (float) ((double) v[k].x * a.xfer.scale); v[k].y = (float) ((double) v[k].y * a.xfer.scale); }
             }
         }
         if (a.conj) {

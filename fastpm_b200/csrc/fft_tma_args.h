@@ -18,7 +18,6 @@ struct TmaPassArgs {
     int early;                  // 1: prefetch the next tile before the arithmetic of this one
     int outer0;
     const float2 *tw;           // [N] exp(-2 pi i t / N)
-    const float2 *kkf;          // [N] { kk (of xfer.potorder), k or k_finite (of xfer.gradorder) } per row index; set when xfer.active
     FpmTransferSpec xfer;
     FpmKTables kt;
 };

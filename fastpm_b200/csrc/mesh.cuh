@@ -89,7 +89,6 @@ struct FpmMesh {
     void *comm;             // opaque communicator (multi-GPU only)
     float *stage;           // multi-GPU: local staging mesh for the slab transpose (NULL: store straight into the peers)
     float *stage2;          // second staging mesh (pipelined inverse transforms: set 1), NULL when there is no room for it
-    float2 *d_kkf[4][2];    // lazily built interleaved tables { kk of potorder - 1 .. 2, k / k_finite } for the fused Green's function (fft.cu)
 };
 
 int fpm_fft_plan_create(int n, FpmFftPlan **out);

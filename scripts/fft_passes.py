@@ -28,11 +28,12 @@ def run(tag, fn):
     print("%-28s" % tag, "  ".join("%s %.2f" % (names[cls[i]][4:], ms[i]) for i in range(nl)))
 
 
-kern = m.transfer_for_kernel("1_4", 0, 1)
+kerns = [m.transfer_for_kernel("1_4", 0, d) for d in range(3)]
 for rep in range(2):
     run("r2c a->b", lambda: m.r2c(a, b))
     run("c2r b->a plain", lambda: m.c2r(b, a))
-    run("c2r b->a kernel", lambda: m.c2r(b, a, kern))
+    for d in range(3):
+        run("c2r b->a force d=%d" % d, lambda: m.c2r(b, a, kerns[d]))
     run("r2c b->a", lambda: m.r2c(b, a))
     run("c2r a->b plain", lambda: m.c2r(a, b))
     _lib.check(lib.fpm_fill_whitenoise(m.h, a.ptr, 2), "noise")

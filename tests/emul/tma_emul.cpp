@@ -99,9 +99,6 @@ static int run(int nouter, unsigned grid, int what_mask)
         a.outer0 = outer0;
         a.xfer.active = 1; a.xfer.potorder = 0; a.xfer.negate = 1; a.xfer.ngrad = 1; a.xfer.graddir[0] = dir; a.xfer.gradorder = 1;
         a.xfer.zero_selfconj = 1; a.xfer.scale = 1.0;
-        std::vector<float2> kkf(n);                       // the interleaved { kk, k_finite } row table fft.cu builds for this kernel
-        for (int i = 0; i < n; i++) kkf[i] = make_float2(tb.kt.kk[i], tb.kt.k_finite[i]);
-        a.kkf = kkf.data();
         CUtensorMap tm = make_tmap(in.data(), n, pitch_c, K);
         fpm_emul_launch(grid, C::T * K, smem, [&]() { fft_tma_kernel<R1, R2, R3, K, false>(tm, a); });
         char what[64]; snprintf(what, sizeof what, "inverse, force d=%d ky0=%d", dir, outer0);
