@@ -25,7 +25,12 @@
 // walk k, then j, then i, so that the CTAs in flight cover a compact 4 x ~70 x nc slab (footprint ~40 MB at N = 2048) and
 // successive waves reuse each other's mesh lines in L2.  Any permutation of thread -> particle is a valid traversal: the
 // hint affects speed only.
-__device__ __forceinline__ long long cic_particle_index(int lag_nc, int nbrick_blocks, long long np)
+// Round 2: the bricks are walked in SUPER-BLOCKS of sb_i x sb_j bricks (times all of k): k fastest, then j inside the block, then
+// i inside the block, then the next block.  A mesh plane is touched by every brick whose particles reach it -- with the plain
+// k, j, i order that is several consecutive groups of i-planes, a full j-sweep (more than the L2) apart, so the plane came in from
+// DRAM several times per deposit; inside a super-block (default 8 x 4 bricks: 32 x 32 x nc particles, ~35 MB of mesh at B = 2) the
+// revisits hit L2.  sb packs (sb_i << 16 | sb_j); 0 = the plain order.
+__device__ __forceinline__ long long cic_particle_index(int lag_nc, int nbrick_blocks, long long np, int sb = 0)
 {
     const int b = blockIdx.x;
     if (b >= nbrick_blocks) {            // no hint, or the tail beyond the last complete group of 4 i-planes: linear
@@ -33,7 +38,18 @@ __device__ __forceinline__ long long cic_particle_index(int lag_nc, int nbrick_b
         return i < np ? i : -1;
     }
     const int nb = lag_nc >> 3;
-    const int bk = b % nb, bj = (b / nb) % nb, bi = b / (nb * nb);
+    int bk, bj, bi;
+    if (sb == 0) {
+        bk = b % nb; bj = (b / nb) % nb; bi = b / (nb * nb);
+    } else {
+        const int sbi = sb >> 16, sbj = sb & 0xffff;
+        const int per = sbi * sbj * nb;                  // bricks per super-block
+        const int s = b / per, r = b - s * per;
+        bk = r % nb;
+        const int q = r / nb, bjl = q % sbj, bil = q / sbj;
+        const int nsj = nb / sbj, sj = s % nsj, si = s / nsj;
+        bj = sj * sbj + bjl; bi = si * sbi + bil;
+    }
     const int tk = threadIdx.x & 7, tj = (threadIdx.x >> 3) & 7, ti = threadIdx.x >> 6;
     return ((long long) (bi * 4 + ti) * lag_nc + (bj * 8 + tj)) * lag_nc + (bk * 8 + tk);
 }
@@ -110,9 +126,9 @@ __device__ __forceinline__ void cic_add_pair(float *row, int k0, int k1, float w
 template <int VEC, bool WRAP>
 __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *__restrict__ canvas,
         double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field,
-        int field_stride, long long np, int *__restrict__ bad, int lag_nc, int nbrick_blocks, long long first)
+        int field_stride, long long np, int *__restrict__ bad, int lag_nc, int nbrick_blocks, long long first, int sb)
 {
-    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first);
+    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first, sb);
     if (i < 0) return;
     i += first;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
@@ -151,9 +167,9 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
 
 __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
         const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc, int nbrick_blocks,
-        long long first)
+        long long first, int sb)
 {
-    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first);
+    long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first, sb);
     if (i < 0) return;
     i += first;
     double pos[3] = { x[3 * i], x[3 * i + 1], x[3 * i + 2] };
@@ -614,8 +630,23 @@ void fpm_set_lagrangian_hint(int nc)
 // Bricks pay off only when the linear walk's footprint (~24 mesh planes) no longer fits the 126 MB L2: measured on B200, they
 // cost 15 % at N = 1024 (4.3 MB planes, linear walk already L2 resident) and gain 25 % at N = 2048 (17 MB planes).
 // Returns the number of leading 256-particle blocks that use the brick mapping (0: linear walk).
-static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc)
+static int fpm_superblock(int lag_nc, long long ngroups)
 {
+    static int sbi = -1, sbj = -1;       // FASTPM_B200_SUPERBLOCK=IxJ bricks (default 8x4; 1x1 = the plain k, j, i order of round 1)
+    if (sbi < 0) {
+        sbi = 8; sbj = 4;
+        const char *e = getenv("FASTPM_B200_SUPERBLOCK");
+        if (e) { int a = 0, b = 0; if (sscanf(e, "%dx%d", &a, &b) == 2 && a > 0 && b > 0) { sbi = a; sbj = b; } }
+    }
+    const int nb = lag_nc >> 3;
+    int bi = sbi, bj = sbj;
+    while (bj > 1 && nb % bj) bj--;
+    while (bi > 1 && ngroups % bi) bi--;
+    return (bi == 1 && bj == 1) ? 0 : ((bi << 16) | bj);
+}
+static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc, int *sb = nullptr)
+{
+    if (sb) *sb = 0;
     const size_t plane_bytes = (size_t) g.n * g.pitch_r * sizeof(float);
     *lag_nc = 0;
     if (!g_lag_nc || (plane_bytes <= ((size_t) 6 << 20) && !g_lag_force)) return 0;
@@ -623,6 +654,7 @@ static int fpm_lagrangian_hint(long long np, const FpmGeom &g, int *lag_nc)
     const long long ngroups = np / group;
     if (ngroups == 0) return 0;
     *lag_nc = g_lag_nc;
+    if (sb) *sb = fpm_superblock(g_lag_nc, ngroups);
     return (int) (ngroups * group / 256);
 }
 
@@ -686,9 +718,9 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
     const long long nrest = np - ntile;
     if (nrest > 0) {
         const unsigned grid = (unsigned) ((nrest + 255) / 256);
-        int lag_nc = 0;
-        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc);
-        #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick, ntile)
+        int lag_nc = 0, sb = 0;
+        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc, &sb);
+        #define PAINT_LAUNCH(V, W) cic_paint_kernel<V, W><<<grid, 256, 0, st>>>(m->geom, canvas, xw, mass, M0, field, field_stride, np, wrap_bad, lag_nc, nbrick, ntile, sb)
         if (nbrick > 0) fpm_path_counter[FPM_PATH_PAINT_BRICKS]++;
         if (wrap_bad) { if (vec >= 4) PAINT_LAUNCH(4, true); else if (vec >= 2) PAINT_LAUNCH(2, true); else PAINT_LAUNCH(0, true); }
         else { if (vec >= 4) PAINT_LAUNCH(4, false); else if (vec >= 2) PAINT_LAUNCH(2, false); else PAINT_LAUNCH(0, false); }
@@ -714,10 +746,12 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
     const long long nrest = np - ntile;
     if (nrest > 0) {
         const unsigned grid = (unsigned) ((nrest + 255) / 256);
-        int lag_nc = 0;
-        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc);
+        // the gather keeps the plain brick order: measured at nc = 1024 (gpurun_out/r02g_sb_*.json) super-blocks take 10 % off the
+        // deposit (47.6 -> 42.8 ms) and nothing off the gather (26.6 -> 27.1 ms)
+        int lag_nc = 0, sb = 0;
+        const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc, nullptr);
         if (nbrick > 0) fpm_path_counter[FPM_PATH_READOUT_BRICKS]++;
-        cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick, ntile);
+        cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick, ntile, sb);
     }
     if (fpm_prof_on) fpm_prof_end(FPM_K_READOUT, st);
     FPM_CHECK_LAUNCH();

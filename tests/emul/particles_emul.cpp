@@ -74,11 +74,11 @@ int main(int argc, char **argv)
         int bad = 0;
         if (op == "paint") {
             auto k = [&]() {
-                if (wrap) { if (vec == 4) cic_paint_kernel<4, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0);
-                            else cic_paint_kernel<0, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0); }
-                else { if (vec == 4) cic_paint_kernel<4, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0);
-                       else if (vec == 2) cic_paint_kernel<2, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0);
-                       else cic_paint_kernel<0, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0); }
+                if (wrap) { if (vec == 4) cic_paint_kernel<4, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0, 0);
+                            else cic_paint_kernel<0, true>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, &bad, lag_nc, nbrick, 0, 0); }
+                else { if (vec == 4) cic_paint_kernel<4, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0, 0);
+                       else if (vec == 2) cic_paint_kernel<2, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0, 0);
+                       else cic_paint_kernel<0, false>(g, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np, nullptr, lag_nc, nbrick, 0, 0); }
             };
             launch_seq(grid, 256, k);
             std::vector<float> dense((size_t) n * n * n);            // unpadded [x][y][z]
@@ -90,7 +90,7 @@ int main(int argc, char **argv)
             std::vector<float> dense = in.many<float>((size_t) n * n * n);
             for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
             std::vector<float> res((size_t) np, 0.f);
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick, 0); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick, 0, 0); });
             dump(out, res);
         }
     } else if (op == "tpaint" || op == "treadout") {
@@ -172,7 +172,7 @@ int main(int argc, char **argv)
         if (lag_nc) nbrick = (int) ((np / (4LL * lag_nc * lag_nc)) * (4LL * lag_nc * lag_nc) / 256);
         std::vector<float> sep((size_t) 3 * np, -7.f), one((size_t) 3 * np, -9.f);
         for (int d = 0; d < 3; d++)
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick, 0); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick, 0, 0); });
         launch_seq(grid, 256, [&]() { cic_readout3_kernel(g, canvas[0].data(), canvas[1].data(), canvas[2].data(), x.data(), one.data(), np, lag_nc, nbrick); });
         dump(out, sep);
         dump(out, one);
