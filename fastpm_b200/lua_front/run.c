@@ -25,7 +25,7 @@
 #include <string.h>
 #include <math.h>
 #include <unistd.h>
-#include "fastpm_b200_api.h"
+#include <fastpm/libfastpm.h>          /* shim/fastpm/libfastpm.h: fastpm_b200_api.h + the option enums of out-of-scope features */
 #include "lua-config.h"
 #include "param.h"
 
@@ -398,10 +398,10 @@ int main(int argc, char **argv)
         return 0;
     }
 
+    refuse(prr);                          /* before any device is touched */
     libfastpm_init();
     MPI_Comm comm = MPI_COMM_WORLD;
     libfastpm_set_memory_bound(prr->cli->MemoryPerRank * 1024 * 1024);
-    refuse(prr);
 
     /* pm_nc_factor -> VPMInit, src/fastpm.c:158-181 */
     VPMInit *vpminit = NULL;
