@@ -104,8 +104,10 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
     /* arena: FASTPM_B200_ARENA_GB, else 85 % of what is free now; the smallest over ranks so that offsets stay in range everywhere */
     size_t free_b = 0, total_b = 0;
     if (fpm_device_mem_info(&free_b, &total_b) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
-    const char *e = getenv("FASTPM_B200_ARENA_GB");
-    int64_t want = e ? (int64_t) (atof(e) * 1073741824.0) : (int64_t) (0.85 * free_b);
+    const char *e = getenv("FASTPM_B200_ARENA_GB"), *ef = getenv("FASTPM_B200_ARENA_FRAC");
+    double arena_frac = ef ? atof(ef) : 0.85;             /* capacity runs (BASELINE configs[4]) raise it: little else is allocated */
+    if (!(arena_frac > 0.05 && arena_frac <= 0.97)) arena_frac = 0.85;
+    int64_t want = e ? (int64_t) (atof(e) * 1073741824.0) : (int64_t) (arena_frac * free_b);
     fpm_comm_allreduce_i64(MPI_COMM_WORLD, &want, 1, 1);
     if (fastpm_b200_arena_init((size_t) want) != 0) fastpm_raise(-1, "arena of %lld bytes: %s\n", (long long) want, fpm_last_error());
     unsigned char h[72], hall[MAXR * 72];
@@ -268,7 +270,11 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
     size_t row = 0;
     for (int j = 0; j < ncol; j++) row += cols[j].elsize;
     if (!pack_local) {
-        double frac = 0.08;
+        /* pack buffers: g_size destinations x this fraction of np_upper.  A step moves ~1 % of a slab across each face; more than a
+         * buffer holds goes in a further round (below), so the fraction only trades memory against rounds: 8 % on 2 GPUs, 4 % on 4,
+         * 2 % on 8 (16 % of a store in total in every case) */
+        double frac = 0.16 / g_size;
+        if (frac > 0.08) frac = 0.08;
         const char *e = getenv("FASTPM_B200_MIGRATE_FRAC");
         if (e) frac = atof(e);
         mig_cap = (int) (frac * p->np_upper);

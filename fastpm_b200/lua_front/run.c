@@ -401,6 +401,7 @@ int main(int argc, char **argv)
     refuse(prr);                          /* before any device is touched */
     libfastpm_init();
     MPI_Comm comm = MPI_COMM_WORLD;
+    fastpm_set_msg_handler(fastpm_default_msg_handler, comm, NULL);      /* the command line logs like the reference's (src/fastpm.c:136) */
     libfastpm_set_memory_bound(prr->cli->MemoryPerRank * 1024 * 1024);
 
     /* pm_nc_factor -> VPMInit, src/fastpm.c:158-181 */

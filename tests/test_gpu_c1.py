@@ -88,7 +88,7 @@ def check_pair(r, L, nsteps):
         assert a_f == rec["a_f"]
         assert np.array_equal(nm, rec["nmodes"])
         sel = rec["nmodes"] > 0
-        np.testing.assert_allclose(k[sel], rec["k"][sel], rtol=1e-12)
+        np.testing.assert_allclose(k[sel], rec["k"][sel], rtol=1e-10)       # mean |k| of up to 5e8 modes, summed in another order
         worst = max(worst, np.abs(p[sel] / rec["p"][sel] - 1).max())
         np.testing.assert_allclose(p[sel], rec["p"][sel], rtol=1e-5)
     return xerr, worst
