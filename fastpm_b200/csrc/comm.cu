@@ -17,6 +17,12 @@
 cudaStream_t fpm_internal_stream(void);
 static cudaStream_t comm_stream(void) { return fpm_internal_stream(); }
 
+// Bytes this rank moved over NVLink since start-up, counted where the transfers are issued: [0] slab-transpose pushes by the copy
+// engines (fft.cu), [1] halo planes pulled, [2] migrating particles pulled, [3] rows stored straight into peers by the transposing
+// FFT pass when no staging mesh is used.  (nvidia-smi nvlink -gt d reports N/A on these B200 boxes.)
+unsigned long long fpm_comm_bytes[4] = { 0, 0, 0, 0 };
+extern "C" int fpm_comm_byte_counts(uint64_t *out4) { for (int i = 0; i < 4; i++) out4[i] = fpm_comm_bytes[i]; return 0; }
+
 // ------------------------------------------------------------------ IPC
 // cudaMalloc sub-allocates small blocks out of larger ones and an IPC handle always names the WHOLE underlying
 // allocation: a pointer is therefore published as (handle of its allocation, offset inside it), and a handle is
@@ -175,6 +181,17 @@ extern "C" int fpm_c2r_dist_finish(fpm_mesh *m, float *const *real_peers, int se
 }
 
 // ------------------------------------------------------------------ halo planes
+// dst = src (one mesh plane pulled from the neighbour with plain loads over NVLink): the copy engines are busy pushing the slab
+// transposes of the next force component (pipelined inverse transforms), where a cudaMemcpyAsync of this plane queued for ~0.6 ms
+__global__ void __launch_bounds__(256) halo_copy_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t n4)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    float4 *d = reinterpret_cast<float4 *>(dst);
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    for (; i < n4; i += stride) d[i] = s[i];
+}
+
 __global__ void __launch_bounds__(256) halo_add_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t n4)
 {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,6 +214,7 @@ extern "C" int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const f
     cudaStream_t st = comm_stream();
     if (fpm_xbarrier_on(st)) return -1;
     FPM_TIMED(FPM_K_HALO, st, (halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local, canvas_prev_rank + (size_t) g.nxl * plane, plane / 4)));
+    fpm_comm_bytes[1] += plane * sizeof(float);
     FPM_CHECK_LAUNCH();
     if (fpm_xbarrier_on(st)) return -1;
     return 0;
@@ -212,9 +230,9 @@ extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const
     const size_t plane = (size_t) g.n * g.pitch_r;
     cudaStream_t st = comm_stream();
     if (fpm_xbarrier_on(st)) return -1;
-    if (fpm_prof_on) fpm_prof_begin(FPM_K_HALO, st);
-    FPM_CUDA_OK(cudaMemcpyAsync(canvas_local + (size_t) g.nxl * plane, canvas_next_rank, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (fpm_prof_on) fpm_prof_end(FPM_K_HALO, st);
+    FPM_TIMED(FPM_K_HALO, st, (halo_copy_kernel<<<148 * 4, 256, 0, st>>>(canvas_local + (size_t) g.nxl * plane, canvas_next_rank, plane / 4)));
+    FPM_CHECK_LAUNCH();
+    fpm_comm_bytes[1] += plane * sizeof(float);
     if (fpm_xbarrier_on(st)) return -1;
     return 0;
 }
@@ -401,6 +419,7 @@ extern "C" int fpm_migrate_append_column(void *col, int elsize, int64_t at, cons
     const unsigned char *src = (const unsigned char *) peer_pack_base + (size_t) my_rank * g_mig.pack_bytes_per_dest + col_off_bytes * g_mig.cap;
     if (fpm_prof_on) fpm_prof_begin(FPM_K_MIGRATE, comm_stream());
     FPM_CUDA_OK(cudaMemcpyAsync((unsigned char *) col + (size_t) at * elsize, src, (size_t) count * elsize, cudaMemcpyDeviceToDevice, comm_stream()));
+    fpm_comm_bytes[2] += (unsigned long long) count * elsize;
     if (fpm_prof_on) fpm_prof_end(FPM_K_MIGRATE, comm_stream());
     return 0;
 }

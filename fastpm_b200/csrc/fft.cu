@@ -319,6 +319,7 @@ static int launch_z(const FpmFftPlan *p, const ZPassArgs &a, int forward, cudaSt
 // stream while the next chunk is being transformed -- NVLink runs at its bulk rate, overlapped with the arithmetic.
 // Two sets of events / staging meshes (`set` 0 and 1): the pushes of one transform may still be in flight while the next
 // transform's transposing pass fills the other staging mesh (pipelined inverse transforms of the force components, host/gravity.c).
+extern unsigned long long fpm_comm_bytes[4];      // comm.cu
 static cudaStream_t g_copy_stream = nullptr;
 static cudaEvent_t g_ev_chunk[2][16], g_ev_done[2];
 static int g_push_pending[2] = { 0, 0 };
@@ -376,6 +377,7 @@ static int staged_transpose(FpmMesh *m, TilePassArgs a, const float2 *src, float
             const float2 *s2 = stage + (size_t) d * blk + (size_t) ch * cp * pc;
             FPM_CUDA_OK(cudaMemcpy2DAsync(dst, plane * sizeof(float2), s2, (size_t) nouter * pc * sizeof(float2),
                                           (size_t) cp * pc * sizeof(float2), per, cudaMemcpyDeviceToDevice, g_copy_stream));
+            fpm_comm_bytes[0] += (unsigned long long) cp * pc * sizeof(float2) * per;
         }
     }
     FPM_CUDA_OK(cudaEventRecord(g_ev_done[set], g_copy_stream));
@@ -407,7 +409,10 @@ int fpm_fft_r2c(FpmMesh *m, const float *real_in, float *work, float *const *cpl
     a.rows_per_rank = n / g.nranks; a.dst_estride = plane; a.dst_ostride = g.pitch_c; a.dst_ooffset = g.x0;
     a.ntile_k = (n / 2 + 1 + p->K - 1) / p->K; a.conj = 0; a.outer0 = g.x0; a.t = p->tN; a.xfer.active = 0; a.kt = m->ktab;
     if (g.nranks > 1 && m->stage) { if (staged_transpose(m, a, a.src, cplx_peers, g.nxl, g.x0, 0, st) || staged_transpose_wait(0, st)) return -1; }
-    else if (launch_tile(p, a, g.nxl, st)) return -1;
+    else {
+        if (launch_tile(p, a, g.nxl, st)) return -1;
+        if (g.nranks > 1) fpm_comm_bytes[3] += (unsigned long long) g.nxl * n * g.pitch_c * sizeof(float2) / g.nranks * (g.nranks - 1);
+    }
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     // F3: in place on the local k-space buffer: outer = local ky plane, rows = kx
     TilePassArgs b = a;
@@ -441,7 +446,10 @@ int fpm_fft_c2r_begin(FpmMesh *m, const float *cplx, float *const *real_peers, c
     if (xfer) a.xfer = *xfer; else a.xfer.active = 0;
     if (g.nranks > 1 && m->barrier && m->barrier(m, st)) return -1;
     if (g.nranks > 1 && (set ? m->stage2 : m->stage)) { if (staged_transpose(m, a, a.src, real_peers, g.nyl, g.y0, set, st)) return -1; }
-    else if (launch_tile(p, a, g.nyl, st)) return -1;
+    else {
+        if (launch_tile(p, a, g.nyl, st)) return -1;
+        if (g.nranks > 1) fpm_comm_bytes[3] += (unsigned long long) g.nyl * n * g.pitch_c * sizeof(float2) / g.nranks * (g.nranks - 1);
+    }
     return 0;
 }
 

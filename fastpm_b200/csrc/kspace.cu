@@ -156,15 +156,16 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
     double *hist_all = reinterpret_cast<double *>(hist_raw);
     const int nbins = g.n / 2;
     const int nslots = GEOM ? 2 * nbins : nbins + 1;
-    for (int i = threadIdx.x; i < nslots * PK_WARPS; i += blockDim.x) hist_all[i] = 0;
+    const int nwarps = blockDim.x >> 5;                 // <= PK_WARPS: fewer when the per-warp histograms of a large mesh would not fit
+    for (int i = threadIdx.x; i < nslots * nwarps; i += blockDim.x) hist_all[i] = 0;
     __syncthreads();
     volatile double *hist = hist_all + (size_t) (threadIdx.x >> 5) * nslots;
     const int n = g.n, h = n / 2, lane = threadIdx.x & 31;
     const size_t nrows = (size_t) g.nyl * n;
-    const size_t wstride = (size_t) gridDim.x * PK_WARPS;
+    const size_t wstride = (size_t) gridDim.x * nwarps;
     const int nchunk = (h + 1 + 63) / 64;
     double allsum = 0;
-    for (size_t row = (size_t) blockIdx.x * PK_WARPS + (threadIdx.x >> 5); row < nrows; row += wstride) {
+    for (size_t row = (size_t) blockIdx.x * nwarps + (threadIdx.x >> 5); row < nrows; row += wstride) {
         const int ix = (int) (row % n), iy = (int) (row / n) + g.y0;
         const int ikx = ix > h ? ix - n : ix, iky = iy > h ? iy - n : iy;
         const int kxy = ikx * ikx + iky * iky;
@@ -248,8 +249,7 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
     __syncthreads();
     for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
         double t = 0;
-        #pragma unroll
-        for (int w = 0; w < PK_WARPS; w++) t += hist_all[(size_t) w * nslots + i];
+        for (int w = 0; w < nwarps; w++) t += hist_all[(size_t) w * nslots + i];
         if (t != 0) atomicAdd(&out[i], t);
     }
 }
@@ -607,21 +607,25 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
 {
     const FpmGeom &g = m->geom;
     const int nbins = g.n / 2;
-    const size_t smem_geom = sizeof(double) * (size_t) (2 * nbins) * PK_WARPS, smem_data = sizeof(double) * (size_t) (nbins + 1) * PK_WARPS;
+    // per-warp histograms: as many warps per CTA as fit (8 up to N = 2048; 4 for the geometry sums of a 4096^3 mesh)
+    int w_geom = PK_WARPS, w_data = PK_WARPS;
+    while (w_geom > 1 && sizeof(double) * (size_t) (2 * nbins) * w_geom > 227 * 1024) w_geom >>= 1;
+    while (w_data > 1 && sizeof(double) * (size_t) (nbins + 1) * w_data > 227 * 1024) w_data >>= 1;
+    const size_t smem_geom = sizeof(double) * (size_t) (2 * nbins) * w_geom, smem_data = sizeof(double) * (size_t) (nbins + 1) * w_data;
     static bool attr_done = false;
     if (!attr_done) {
         FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    if (smem_geom > 227 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
+    if (smem_geom > 227 * 1024 || smem_data > 227 * 1024) { fpm_set_error("powerspectrum: too many bins"); return -1; }
     const int ctas_per_sm = smem_data <= 56 * 1024 ? 4 : (smem_data <= 75 * 1024 ? 3 : (smem_data <= 113 * 1024 ? 2 : 1));
     const double k0 = 2 * M_PI / g.boxsize;
     FpmMesh *mm = const_cast<FpmMesh *>(m);           // the per-mesh cache of the geometry sums
     if (!mm->d_pkgeom) {
         FPM_CUDA_OK(cudaMalloc(&mm->d_pkgeom, sizeof(double) * (3 * nbins + 1)));
         FPM_CUDA_OK(cudaMemsetAsync(mm->d_pkgeom, 0, sizeof(double) * (3 * nbins + 1), st));
-        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<true><<<148, 32 * PK_WARPS, smem_geom, st>>>(g, m->d_decic, 0, nullptr, k0, mm->d_pkgeom)));
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<true><<<148, 32 * w_geom, smem_geom, st>>>(g, m->d_decic, 0, nullptr, k0, mm->d_pkgeom)));
         FPM_CHECK_LAUNCH();
     }
     double *d_data = mm->d_pkgeom + 2 * nbins;        // [nbins] + 1
@@ -642,7 +646,7 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
         fpm_path_counter[FPM_PATH_PK_ROWS]++;
         FPM_TIMED(FPM_K_PK, st, (powerspectrum_rows_kernel<<<(unsigned) grid, 32 * PKR_WARPS, smem_rows, st>>>(g, m->d_decic, decic, (const float2 *) dk, d_data)));
     } else {
-        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * PK_WARPS, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * w_data, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
     }
     FPM_CHECK_LAUNCH();
     pk_assemble_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(mm->d_pkgeom, d_data, nbins, d_out);

@@ -120,6 +120,9 @@ def bench_main(args):
     lib.fpm_prof_reset()
     lib.fpm_prof_enable(1)
     launches0 = int(lib.fpm_kernel_launch_count())
+    nvl0 = (C.c_uint64 * 4)()
+    lib.fpm_comm_byte_counts.argtypes = [C.c_void_p]
+    lib.fpm_comm_byte_counts(nvl0)
     sampler = B.ClockSampler(local) if rank == 0 else None
     _lib.check(lib.fpm_sync())
     torch.cuda.synchronize()
@@ -134,6 +137,9 @@ def bench_main(args):
     dist.barrier()
     clocks = sampler.stop() if sampler else None
     launches = int(lib.fpm_kernel_launch_count()) - launches0
+    nvl1 = (C.c_uint64 * 4)()
+    lib.fpm_comm_byte_counts(nvl1)
+    nvl = [int(b) - int(a) for a, b in zip(nvl0, nvl1)]
     lib.fpm_prof_enable(0)
     counts = (C.c_int64 * len(B.KCLASSES))()
     totals = (C.c_double * len(B.KCLASSES))()
@@ -196,6 +202,10 @@ def bench_main(args):
         "stages_rank0": stages, "np_total_after": int(np_local.item()), "result_finite": bool(fin.item() == 1),
         "pk_bins": [float(v) for v in spectra[-1][1][:8]] if spectra else None,
         "x_checksum": [float(v) for v in chk.tolist()],
+        # bytes rank 0 moved over NVLink in the timed run, counted where the transfers are issued (nvidia-smi's NVLink counters read
+        # N/A on these boxes); a slab transpose moves S/G * (G-1)/G out of every GPU
+        "nvlink_rank0": {"transpose_push_bytes_per_transform": (nvl[0] + nvl[3]) / max(1, ntr), "expected_bytes_per_transform": S_local * (world - 1) / world,
+                         "halo_bytes_per_step": nvl[1] / K, "migration_bytes_per_step": nvl[2] / K},
     }
     if rank == 0:
         B.emit(line)

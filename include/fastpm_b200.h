@@ -60,6 +60,9 @@ uint64_t fpm_kernel_launch_count(void);                /* kernels launched by th
  * x-pass (unused: the row-streaming P(k) kernel is counted here), staged slab transposes, paint through shared-memory tiles,
  * readout through shared-memory tiles.  Returns the number of counters the library keeps. */
 int fpm_path_counts(uint64_t *out, int n);
+/* bytes this rank moved to / from its peers over NVLink so far, counted where the transfers are issued: out4 = { slab-transpose
+ * pushes by the copy engines, halo planes, migrating particles, rows the transposing FFT pass stored straight into peers } */
+int fpm_comm_byte_counts(uint64_t *out4);
 /* optional per-kernel-class timing with CUDA events on the launching stream (off by default); classes in order:
  * paint, readout, fft_tile, fft_z, kick, drift, kspace, pk, summary, other, memset, barrier (cross-GPU, includes the wait for
  * the slowest rank), halo, migrate, push (exposed tail of the copy-engine pushes of a staged slab transpose) */
