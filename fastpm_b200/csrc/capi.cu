@@ -117,6 +117,8 @@ int fpm_lazy_touch(const void *p, size_t bytes)
     return fpm_decic_launch(m, buf, buf, g_stream);
 }
 #define LAZY1(p) do { if (fpm_lazy_touch((p), 0)) return -1; } while (0)
+// applies the pending deferred deconvolution, whatever buffer it belongs to (fpm_sync_deferred, include/fastpm_b200.h)
+int fpm_lazy_flush_all(void) { return g_lazy_buf ? fpm_lazy_touch(g_lazy_buf, 0) : 0; }
 
 extern "C" {
 
@@ -596,6 +598,13 @@ int fpm_decic_defer(const fpm_mesh *m, float *cplx)
     fpm_mesh_info(m, info);
     g_lazy_mesh = m; g_lazy_buf = (const char *) cplx; g_lazy_bytes = (size_t) info[1] * sizeof(float);
     return 0;
+}
+/* Work this library defers is invisible to code that reads the public device pointers with its own CUDA kernels: call this first.
+ * Applies the pending in-place deconvolution of fpm_decic_defer (if any) and waits for the stream. */
+int fpm_sync_deferred(void)
+{
+    if (fpm_lazy_flush_all()) return -1;
+    return fpm_sync();
 }
 int fpm_decic_cancel(const float *cplx)
 {

@@ -331,6 +331,16 @@ void fastpm_solver_evolve(FastPMSolver *fastpm, double *time_step, int nstep)
  * positions in between): fastpm_paint_local wraps while it reads x, see cic_paint_kernel<.., WRAP> in csrc/paint.cu. */
 FastPMStore *fpm_pending_wrap = NULL;
 
+/* A FORCE / TRANSITION / INTERPOLATION handler (or any caller between library calls) that reads p->x, p->v, event->delta_k ... with
+ * its OWN device code must call this first: it applies the queued in-place kicks and drifts (factors.c) and the deferred CIC
+ * deconvolution of event->delta_k (do_force), then waits for the device.  Handlers that only use this library's entry points need
+ * not: every entry point does it for the buffers it is handed. */
+void fastpm_b200_sync_state(void)
+{
+    fpm_store_flush(NULL);
+    FPM_MUST(fpm_sync_deferred());
+}
+
 extern int fpm_decompose_skip_acc;       /* host/comm.c */
 static void fastpm_decompose_inner(FastPMSolver *fastpm, PM *pm);
 static void fastpm_decompose(FastPMSolver *fastpm, PM *pm)

@@ -153,6 +153,10 @@ int fpm_apply_decic(const fpm_mesh *m, const float *from, float *to);      /* tr
  * library that is handed the buffer applies it first, fpm_decic_cancel drops it (solver.c:471 before the FORCE/after event) */
 int fpm_decic_defer(const fpm_mesh *m, float *cplx);
 int fpm_decic_cancel(const float *cplx);
+/* Deferred work is applied by every entry point of this library that is handed the buffer, but it is invisible to code that
+ * reads a device pointer directly (own CUDA kernels, torch on the pointer): call this first.  Applies the pending deconvolution
+ * of fpm_decic_defer, if any, and waits for the library stream. */
+int fpm_sync_deferred(void);
 /* PGD potential, apply_pgdpot_transfer pgdcorrection.c:28-59: to = alpha exp(-kl^2/k^2 - k^4/ks^4) / k^2 * from */
 int fpm_apply_pgd_transfer(const fpm_mesh *m, const float *from, float *to, double alpha, double kl, double ks);
 /* force softening, gravity.c:244-270.  Radial: mode 0 = low pass, 1 where k^2 < param else 0 (fastpm_apply_lowpass_transfer,

@@ -515,6 +515,13 @@ void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allred
  * Host mirrors of device-resident data, for callers (snapshot writers, FOF, lightcone, custom event
  * handlers) that the reference lets dereference mesh buffers and store columns directly. */
 /* copy `count` elements of a store column to / from host memory (elements are whole rows, e.g. double[3]) */
+/* Deferred work and direct access to device pointers.  Between two force evaluations the library queues the in-place kicks and drifts of a
+ * store and applies them in ONE pass (host/factors.c), and do_force records the CIC deconvolution of event->delta_k instead of sweeping
+ * the mesh when the FORCE/after handler is the P(k) measurement (host/solver.c).  Every entry point of this library applies what is
+ * pending on the buffers it is handed, so code that goes through the API never sees the difference.  A handler that reads p->x, p->v,
+ * event->delta_k, ... with its OWN device code (a CUDA kernel, torch on the pointer) must call this first: it applies everything pending
+ * and waits for the device. */
+void fastpm_b200_sync_state(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count);
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count);
