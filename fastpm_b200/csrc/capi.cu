@@ -39,7 +39,7 @@ void fpm_prof_end(int cls, cudaStream_t st)
 
 // launchers defined in the kernel files
 int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, int *wrap_bad, cudaStream_t st);
-int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st);
+int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st, const float *pack0 = nullptr, const float *pack1 = nullptr);
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
 int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, const float *c2, const double *x, float *out, long long np, cudaStream_t st);
 int fpm_window_paint_launch(const FpmMesh *m, int type, int support, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
@@ -417,6 +417,13 @@ int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t
 {
     LAZY1(canvas);
     return fpm_readout_launch(m, canvas, x, out, out_stride, prescale, np, g_stream);
+}
+
+int fpm_readout_pack3(const fpm_mesh *m, const float *canvas, const double *x, int64_t np, const float *comp0, const float *comp1, float *out3)
+{
+    LAZY1(canvas);
+    if (!comp0 || !comp1) { fpm_set_error("fpm_readout_pack3: the two stored components are required"); return -1; }
+    return fpm_readout_launch(m, canvas, x, out3, 3, 1.0, np, g_stream, comp0, comp1);
 }
 
 int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3)

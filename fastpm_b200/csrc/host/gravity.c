@@ -91,6 +91,43 @@ static int fused_readout_wanted(FastPMSolver *fastpm, PM *pm)
     return all > 0.5;
 }
 
+/* Readout of force component d of every species.  With the CIC window and a scratch block `planes` (2 x np_upper floats, CDM only)
+ * components 0 and 1 go to planar arrays and component 2 writes the ACC rows whole (fpm_readout_pack3): same values, 28 instead
+ * of 72 bytes of DRAM traffic per particle for the results. */
+static void readout_component(FastPMSolver *fastpm, FastPMPainter *painter, FastPMFloat *canvas, int d, float *planes)
+{
+    for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
+        FastPMStore *p = fastpm_solver_get_species(fastpm, si);
+        if (!p) continue;
+        FastPMFieldDescr f = { d < 3 ? COLUMN_ACC : COLUMN_POTENTIAL, d < 3 ? d : 0 };
+        if (d == 3 && !p->potential) continue;
+        if (planes && si == FASTPM_SPECIES_CDM && d < 3) {
+            fpm_store_flush(p);
+            float *t0 = planes, *t1 = planes + p->np_upper;
+            if (d < 2) FPM_MUST(fpm_readout(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) p->np, d == 0 ? t0 : t1, 1, 1.0));
+            else FPM_MUST(fpm_readout_pack3(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) p->np, t0, t1, (float *) p->acc));
+            continue;
+        }
+        fastpm_readout_local(painter, canvas, p, p->np, f);
+    }
+}
+
+/* the scratch block for readout_component, or NULL: CIC window, CDM with an ACC column, and room for it (every rank decides alike:
+ * all ranks see the same arena state; FASTPM_B200_NO_PACKED_READOUT=1 switches it off) */
+static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter)
+{
+    static int off = -1;
+    if (off < 0) off = getenv("FASTPM_B200_NO_PACKED_READOUT") ? 1 : 0;
+    FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    if (off || painter->kernel != NULL || !cdm || !cdm->acc || cdm->np == 0) return NULL;
+    const size_t need = 2 * sizeof(float) * cdm->np_upper;
+    int ok;
+    if (fastpm_b200_arena_size() > 0) ok = fastpm_b200_arena_largest_free() >= need + (need >> 2) + ((size_t) 64 << 20);
+    else { size_t fr = 0, tot = 0; ok = fpm_device_mem_info(&fr, &tot) == 0 && fr >= need + (need >> 2) + ((size_t) 256 << 20); }
+    (void) pm;
+    return ok ? fastpm_memory_alloc(cdm->mem, "ACC component planes", need, FASTPM_MEMORY_STACK) : NULL;
+}
+
 void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, FastPMSofteningType dealias,
                                  FastPMKernelType kernel, FastPMFloat *delta_k, double Time)
 {
@@ -163,6 +200,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         pm_free(pm, cv[1]);
         d0 = 3;
     }
+    float *planes = d0 == 0 ? acc_planes_alloc(fastpm, pm, painter) : NULL;       /* freed last (LIFO): allocated before the second canvas */
     if (d0 == 0 && pm->NTask > 1 && fpm_dist_pipeline_ready(pm)) {
         /* Several GPUs: the slab transpose of component d + 1 travels (copy engines, NVLink) while component d is finished
          * (y- and z-pass) and read out -- two canvases and two staging meshes, used alternately.  The arithmetic of every
@@ -184,13 +222,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
             fpm_halo_fetch(pm, cv[d & 1]);
             LEAVE(c2r);
             ENTER(readout);
-            for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
-                FastPMStore *p = fastpm_solver_get_species(fastpm, si);
-                if (!p) continue;
-                FastPMFieldDescr f = { d < 3 ? COLUMN_ACC : COLUMN_POTENTIAL, d < 3 ? d : 0 };
-                if (d == 3 && !p->potential) continue;
-                fastpm_readout_local(painter, cv[d & 1], p, p->np, f);
-            }
+            readout_component(fastpm, painter, cv[d & 1], d, planes);
             LEAVE(readout);
         }
         pm_free(pm, cv[1]);
@@ -204,14 +236,9 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         if (pm->NTask > 1) fpm_halo_fetch(pm, canvas);
         LEAVE(c2r);
         ENTER(readout);
-        for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++) {
-            FastPMStore *p = fastpm_solver_get_species(fastpm, si);
-            if (!p) continue;
-            FastPMFieldDescr f = { d < 3 ? COLUMN_ACC : COLUMN_POTENTIAL, d < 3 ? d : 0 };
-            if (d == 3 && !p->potential) continue;
-            fastpm_readout_local(painter, canvas, p, p->np, f);
-        }
+        readout_component(fastpm, painter, canvas, d, planes);
         LEAVE(readout);
     }
+    if (planes) fastpm_memory_free(fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM)->mem, planes);
     pm_free(pm, canvas);
 }

@@ -165,9 +165,13 @@ __global__ void __launch_bounds__(256) cic_paint_kernel(const FpmGeom g, float *
     }
 }
 
+// pack0 / pack1 != NULL: `out` is a column of 3-float rows; the row is written WHOLE as { pack0[i], pack1[i], value }.  The three
+// force components then cost 4 + 4 + (8 read, 12 written) bytes per particle instead of three strided 4-byte stores into 12-byte
+// rows, each of which dirtied the whole 32-byte sector (measured at nc = 1024: 12.9 GB written and 12.9 GB of fill reads per pass
+// for 4.3 GB of results, gpurun_out/r02_traffic_particles_nc1024.csv).
 __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const float *__restrict__ canvas,
         const double *__restrict__ x, float *__restrict__ out, int out_stride, double prescale, long long np, int lag_nc, int nbrick_blocks,
-        long long first, int sb)
+        long long first, int sb, const float *__restrict__ pack0, const float *__restrict__ pack1)
 {
     long long i = cic_particle_index(lag_nc, nbrick_blocks, np - first, sb);
     if (i < 0) return;
@@ -194,7 +198,12 @@ __global__ void __launch_bounds__(256) cic_readout_kernel(const FpmGeom g, const
         value += CELL(p1 + c.j1 * pr + c.k1) * (c.D[2] * c.D[0] * c.D[1]);
     }
     #undef CELL
-    out[i * out_stride] = (float) value;
+    if (pack0) {
+        float *o = out + 3 * i;
+        o[0] = pack0[i]; o[1] = pack1[i]; o[2] = (float) value;
+    } else {
+        out[i * out_stride] = (float) value;
+    }
 }
 
 // The three force components in ONE pass over the particles (x read once, acc written as whole 12-byte elements): each
@@ -732,10 +741,10 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
 }
 
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride,
-                       double prescale, long long np, cudaStream_t st)
+                       double prescale, long long np, cudaStream_t st, const float *pack0 = nullptr, const float *pack1 = nullptr)
 {
     if (np <= 0) return 0;
-    const long long ntile = fpm_tile_particles(np, m->geom);
+    const long long ntile = pack0 ? 0 : fpm_tile_particles(np, m->geom);
     if (fpm_prof_on) fpm_prof_begin(FPM_K_READOUT, st);
     if (ntile > 0) {
         if (tile_attrs()) return -1;
@@ -751,7 +760,7 @@ int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, f
         int lag_nc = 0, sb = 0;
         const int nbrick = fpm_lagrangian_hint(nrest, m->geom, &lag_nc, nullptr);
         if (nbrick > 0) fpm_path_counter[FPM_PATH_READOUT_BRICKS]++;
-        cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick, ntile, sb);
+        cic_readout_kernel<<<grid, 256, 0, st>>>(m->geom, canvas, x, out, out_stride, prescale, np, lag_nc, nbrick, ntile, sb, pack0, pack1);
     }
     if (fpm_prof_on) fpm_prof_end(FPM_K_READOUT, st);
     FPM_CHECK_LAUNCH();

@@ -103,6 +103,12 @@ int fpm_tile_stats(uint64_t *out4);
 int fpm_readout(const fpm_mesh *m, const float *canvas, const double *x, int64_t np,
                 float *out, int out_stride, double prescale);
 
+/* The last of three component readouts into a column of 3-float rows: out3[i] = { comp0[i], comp1[i], readout(canvas)[i] }, written as
+ * whole rows.  comp0 / comp1 are the first two components read out into planar scratch arrays (fpm_readout with out_stride 1): the three
+ * passes then move 28 bytes per particle of results instead of the 72 that three strided 4-byte stores into 12-byte rows cost in DRAM
+ * (every pass dirties and re-fills whole 32-byte sectors).  Values are those of three fpm_readout calls, bit for bit. */
+int fpm_readout_pack3(const fpm_mesh *m, const float *canvas, const double *x, int64_t np, const float *comp0, const float *comp1, float *out3);
+
 /* three readouts in one pass over the particles: out3[i][d] = fpm_readout(canvas_d) for d = 0, 1, 2 (the ACC column of the
  * store, gravity.c:359-396), bit-identical to three separate calls; needs the three fields resident at the same time */
 int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3);

@@ -90,7 +90,7 @@ int main(int argc, char **argv)
             std::vector<float> dense = in.many<float>((size_t) n * n * n);
             for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
             std::vector<float> res((size_t) np, 0.f);
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick, 0, 0); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas.data(), x.data(), res.data(), 1, 1.0, np, lag_nc, nbrick, 0, 0, nullptr, nullptr); });
             dump(out, res);
         }
     } else if (op == "tpaint" || op == "treadout") {
@@ -172,7 +172,7 @@ int main(int argc, char **argv)
         if (lag_nc) nbrick = (int) ((np / (4LL * lag_nc * lag_nc)) * (4LL * lag_nc * lag_nc) / 256);
         std::vector<float> sep((size_t) 3 * np, -7.f), one((size_t) 3 * np, -9.f);
         for (int d = 0; d < 3; d++)
-            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick, 0, 0); });
+            launch_seq(grid, 256, [&]() { cic_readout_kernel(g, canvas[d].data(), x.data(), sep.data() + d, 3, 1.0, np, lag_nc, nbrick, 0, 0, nullptr, nullptr); });
         launch_seq(grid, 256, [&]() { cic_readout3_kernel(g, canvas[0].data(), canvas[1].data(), canvas[2].data(), x.data(), one.data(), np, lag_nc, nbrick); });
         dump(out, sep);
         dump(out, one);

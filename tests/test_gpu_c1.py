@@ -102,7 +102,7 @@ def test_c1_matches_reference(ref_mod, pk_text):
     u = r["used"]
     assert u["fft_tma"] >= 8 * len(steps) and u["fft_zrow"] >= 4 * len(steps), u       # 4 transforms per force evaluation
     assert u["fft_tile_generic"] == 0 and u["fft_z_generic"] == 0, u
-    assert u["paint_tiles"] >= len(steps) and u["readout_tiles"] >= 3 * len(steps) and u["pk_rows"] >= len(steps), u
+    assert u["pk_rows"] >= len(steps), u                 # the row-streaming P(k) kernel (the shared-memory tiles of paint / readout are opt-in)
     xerr, perr = check_pair(r, L, len(steps))
     print("C1: max position error %.3g Mpc/h, max P(k) deviation %.3g, paths %s" % (xerr, perr, u))
 
