@@ -36,6 +36,7 @@ void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *d
 
 size_t fastpm_b200_arena_size(void);             /* host/support.c */
 size_t fastpm_b200_arena_largest_free(void);
+int fastpm_b200_device_room(size_t need, size_t slack);
 
 /* gravity.c:66-102: exp(-(k_d r0)^2 / 2) per axis with r0 = N cells, tabulated in double from the float k table */
 static void apply_gaussian_softening(PM *pm, FastPMFloat *from, FastPMFloat *to, double N)
@@ -121,11 +122,11 @@ static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *pain
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
     if (off || painter->kernel != NULL || !cdm || !cdm->acc || cdm->np == 0) return NULL;
     const size_t need = 2 * sizeof(float) * cdm->np_upper;
-    int ok;
-    if (fastpm_b200_arena_size() > 0) ok = fastpm_b200_arena_largest_free() >= need + (need >> 2) + ((size_t) 64 << 20);
-    else { size_t fr = 0, tot = 0; ok = fpm_device_mem_info(&fr, &tot) == 0 && fr >= need + (need >> 2) + ((size_t) 256 << 20); }
     (void) pm;
-    return ok ? fastpm_memory_alloc(cdm->mem, "ACC component planes", need, FASTPM_MEMORY_STACK) : NULL;
+    if (cdm->mem->used_bytes + need > cdm->mem->total_bytes) return NULL;
+    /* leave room for what may still be taken after this block: the second canvas of the pipelined transforms is checked for later */
+    if (!fastpm_b200_device_room(need, (need >> 2) + ((size_t) 256 << 20))) return NULL;
+    return fastpm_memory_alloc(cdm->mem, "ACC component planes", need, FASTPM_MEMORY_STACK);
 }
 
 void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, FastPMSofteningType dealias,

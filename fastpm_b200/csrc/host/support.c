@@ -281,6 +281,17 @@ int fastpm_b200_arena_selftest(void)
     return bad;
 }
 
+/* Is there room for an optional block of `need` bytes (plus `slack`)?  Several GPUs: the largest free block of the symmetric arena
+ * (identical on every rank).  One GPU: free device memory plus what the buffer cache would give back when asked. */
+int fastpm_b200_device_room(size_t need, size_t slack)
+{
+    if (arena_base) return fastpm_b200_arena_largest_free() >= need + slack;
+    size_t fr = 0, tot = 0, cached = 0;
+    if (fpm_device_mem_info(&fr, &tot) != 0) return 0;
+    for (int i = 0; i < NCACHE; i++) if (cache[i].p) cached += cache[i].size;
+    return fr + cached >= need + slack;
+}
+
 void *fastpm_memory_alloc_details(FastPMMemory *m, const char *name, size_t s, enum FastPMMemoryLocation loc, const char *file, const int line)
 {
     if (s == 0) s = 1;
