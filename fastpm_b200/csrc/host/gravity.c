@@ -115,7 +115,7 @@ static void readout_component(FastPMSolver *fastpm, FastPMPainter *painter, Fast
 
 /* the scratch block for readout_component, or NULL: CIC window, CDM with an ACC column, and room for it (every rank decides alike:
  * all ranks see the same arena state; FASTPM_B200_NO_PACKED_READOUT=1 switches it off) */
-static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter)
+static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter, size_t reserve)
 {
     static int off = -1;
     if (off < 0) off = getenv("FASTPM_B200_NO_PACKED_READOUT") ? 1 : 0;
@@ -124,8 +124,8 @@ static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *pain
     const size_t need = 2 * sizeof(float) * cdm->np_upper;
     (void) pm;
     if (cdm->mem->used_bytes + need > cdm->mem->total_bytes) return NULL;
-    /* leave room for what may still be taken after this block: the second canvas of the pipelined transforms is checked for later */
-    if (!fastpm_b200_device_room(need, (need >> 2) + ((size_t) 256 << 20))) return NULL;
+    /* `reserve`: what is still to be taken after this block (the second canvas of the pipelined transforms) */
+    if (!fastpm_b200_device_room(need, reserve + (need >> 2) + ((size_t) 256 << 20))) return NULL;
     return fastpm_memory_alloc(cdm->mem, "ACC component planes", need, FASTPM_MEMORY_STACK);
 }
 
@@ -201,8 +201,11 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         pm_free(pm, cv[1]);
         d0 = 3;
     }
-    float *planes = d0 == 0 ? acc_planes_alloc(fastpm, pm, painter) : NULL;       /* freed last (LIFO): allocated before the second canvas */
-    if (d0 == 0 && pm->NTask > 1 && fpm_dist_pipeline_ready(pm)) {
+    const int pipeline = d0 == 0 && pm->NTask > 1 && fpm_dist_pipeline_ready(pm);
+    const size_t canvas_bytes = sizeof(FastPMFloat) * pm->allocsize;
+    /* freed last (LIFO): allocated before the second canvas, for which room is kept */
+    float *planes = d0 == 0 ? acc_planes_alloc(fastpm, pm, painter, pipeline ? canvas_bytes + (canvas_bytes >> 3) : 0) : NULL;
+    if (pipeline) {
         /* Several GPUs: the slab transpose of component d + 1 travels (copy engines, NVLink) while component d is finished
          * (y- and z-pass) and read out -- two canvases and two staging meshes, used alternately.  The arithmetic of every
          * component is that of fpm_mesh_c2r + readout; only the order in which the work is queued differs. */
