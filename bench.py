@@ -38,10 +38,18 @@ def read_pk():
 
 
 def measured_traffic(nmesh):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    """DRAM bytes (read + written) per launch of the dominant kernel -- the strided FFT tile pass -- at this mesh size, averaged over the
+    launches of the committed ncu capture (profiles/r02_dram_traffic_n2048.csv, written by the round-2 summary script from the
+    .ncu-rep files: dram__bytes_read.sum + dram__bytes_write.sum per launch), or None when no capture at this size is committed."""
+    import csv
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return float(json.load(f)["fft_tile_bytes_per_launch"][str(nmesh)])
+        tot, n = 0.0, 0
+        with open(os.path.join(ROOT, "profiles", "r02_dram_traffic_n2048.csv")) as f:
+            for row in csv.DictReader(f):
+                if row["kernel"].startswith("fft_tma_kernel") and int(row["nmesh"]) == int(nmesh):
+                    tot += float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])
+                    n += 1
+        return tot / n if n else None
     except Exception:
         return None
 
