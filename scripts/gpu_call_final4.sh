@@ -8,5 +8,5 @@ python - <<'PY'
 import json
 l = [x for x in open("gpurun_out/r02k_bench_2gpu.json") if x.startswith("{")][-1]
 d = json.loads(l)
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], {k: (v["launches"], round(v["ms"], 1)) for k, v in d["stages"].items() if v["launches"]}, d["clocks"], d["pk_bins"][:3], d["x_checksum"], d.get("nvlink_rank0"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], {k: (v["launches"], round(v["ms"], 1)) for k, v in d.get("stages", d.get("stages_rank0")).items() if v["launches"]}, d["clocks"], d["pk_bins"][:3], d["x_checksum"], d.get("nvlink_rank0"))
 PY
