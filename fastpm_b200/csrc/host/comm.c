@@ -40,10 +40,21 @@ static void *g_cb_data = NULL;
 int fpm_comm_rank(MPI_Comm comm) { (void) comm; return g_rank; }
 int fpm_comm_size(MPI_Comm comm) { (void) comm; return g_size; }
 
+/* host/shmcoll.c: the same collectives through a shared segment when all ranks sit on one host */
+int fpm_shm_setup(int rank, int size, fpm_host_allgather_fn gather, void *userdata);
+int fpm_shm_active(void);
+static int g_callbacks_only = 0;            /* self test of the callbacks */
+#define SHM_ON() (!g_callbacks_only && fpm_shm_active())
+void fpm_shm_allreduce(void *v, int n, int type, int op);
+void fpm_shm_allgather(const void *send, int nbytes, void *recv);
+
+int fastpm_b200_host_collectives_shared(void) { return g_size > 1 && SHM_ON(); }
+
 void fpm_comm_allreduce_double(MPI_Comm comm, double *v, int n, int op)
 {
     (void) comm;
     if (g_size == 1) return;
+    if (SHM_ON()) { fpm_shm_allreduce(v, n, 0, op); return; }
     if (!g_allreduce) fastpm_raise(-1, "multi-rank run without an all-reduce callback\n");
     g_allreduce(v, n, 0, op, g_cb_data);
 }
@@ -51,6 +62,7 @@ void fpm_comm_allreduce_i64(MPI_Comm comm, int64_t *v, int n, int op)
 {
     (void) comm;
     if (g_size == 1) return;
+    if (SHM_ON()) { fpm_shm_allreduce(v, n, 1, op); return; }
     if (!g_allreduce) fastpm_raise(-1, "multi-rank run without an all-reduce callback\n");
     g_allreduce(v, n, 1, op, g_cb_data);
 }
@@ -59,6 +71,7 @@ void fpm_comm_barrier(MPI_Comm comm) { int64_t z = 0; fpm_comm_allreduce_i64(com
 static void allgather(const void *send, int nbytes, void *recv)
 {
     if (g_size == 1) { memcpy(recv, send, nbytes); return; }
+    if (SHM_ON()) { fpm_shm_allgather(send, nbytes, recv); return; }
     if (!g_allgather) fastpm_raise(-1, "multi-rank run without an all-gather callback\n");
     g_allgather(send, nbytes, recv, g_cb_data);
 }
@@ -93,6 +106,7 @@ void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allred
 {
     if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
     g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
+    fpm_shm_setup(rank, size, allgather_cb, userdata);
 }
 
 void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
@@ -100,6 +114,7 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
     libfastpm_init();
     if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
     g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
+    fpm_shm_setup(rank, size, allgather_cb, userdata);
     if (size == 1) return;
     /* arena: FASTPM_B200_ARENA_GB, else 85 % of what is free now; the smallest over ranks so that offsets stay in range everywhere */
     size_t free_b = 0, total_b = 0;
@@ -348,19 +363,35 @@ int fastpm_b200_comm_selftest(int rank, int size, fpm_host_allreduce_fn allreduc
     fpm_host_allreduce_fn sa = g_allreduce; fpm_host_allgather_fn sg = g_allgather; void *sd = g_cb_data;
     g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
     int bad = 0;
-    double v[3] = { rank + 1.0, rank + 1.0, rank + 1.0 };
-    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[0], 1, 0);
-    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[1], 1, 1);
-    fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[2], 1, 2);
-    if (v[0] != size * (size + 1) / 2.0 || v[1] != 1.0 || v[2] != (double) size) bad |= 1;
-    int64_t n = 1000 + rank;
-    fpm_comm_allreduce_i64(MPI_COMM_WORLD, &n, 1, 0);
-    if (n != 1000 * (int64_t) size + size * (size - 1) / 2) bad |= 2;
-    uint64_t mine = 0xabc00000ull + rank, all[MAXR];
-    allgather(&mine, 8, all);
-    for (int r = 0; r < size; r++) if (all[r] != 0xabc00000ull + r) bad |= 4;
+    for (int pass = 0; pass < 2; pass++) {
+        /* pass 0: the launcher's callbacks; pass 1: the shared segment of host/shmcoll.c (set up through those callbacks) */
+        g_callbacks_only = pass == 0;
+        if (pass == 1 && !(size > 1 && fpm_shm_setup(rank, size, allgather_cb, userdata))) break;
+        double v[3] = { rank + 1.0, rank + 1.0, rank + 1.0 };
+        fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[0], 1, 0);
+        fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[1], 1, 1);
+        fpm_comm_allreduce_double(MPI_COMM_WORLD, &v[2], 1, 2);
+        if (v[0] != size * (size + 1) / 2.0 || v[1] != 1.0 || v[2] != (double) size) bad |= 1 << (4 * pass);
+        int64_t n = 1000 + rank;
+        fpm_comm_allreduce_i64(MPI_COMM_WORLD, &n, 1, 0);
+        if (n != 1000 * (int64_t) size + size * (size - 1) / 2) bad |= 2 << (4 * pass);
+        uint64_t mine = 0xabc00000ull + rank, all[MAXR];
+        allgather(&mine, 8, all);
+        for (int r = 0; r < size; r++) if (all[r] != 0xabc00000ull + r) bad |= 4 << (4 * pass);
+        /* a payload of several slots (the P(k) bins of a large mesh), twice, so that both parities are reused */
+        enum { NBIG = 20000 };
+        double *big = (double *) malloc(NBIG * sizeof(double));
+        for (int rep = 0; rep < 2; rep++) {
+            for (int i = 0; i < NBIG; i++) big[i] = (double) (i % 97) * (rank + 1) + rep;
+            fpm_comm_allreduce_double(MPI_COMM_WORLD, big, NBIG, 0);
+            for (int i = 0; i < NBIG; i++) if (big[i] != (double) (i % 97) * (size * (size + 1) / 2) + rep * size) { bad |= 8 << (4 * pass); break; }
+        }
+        free(big);
+    }
+    g_callbacks_only = 0;
     /* the slab owner rule used by the migration kernel (pm_pos_to_rank, pmpfft.c:344-368) */
     g_rank = save_rank; g_size = save_size; g_allreduce = sa; g_allgather = sg; g_cb_data = sd;
+    fpm_shm_setup(save_rank, save_size, sg, sd);
     return bad;
 }
 

@@ -199,6 +199,7 @@ def bench_main(args):
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": round(avg_ms, 4)},
         "fft": {"gbs_6S_per_gpu": round(6 * S_local / (t_tr * 1e-3) / 1e9, 1) if t_tr > 0 else 0.0, "ms_per_transform": round(t_tr, 4), "transforms": ntr},
+        "host_collectives": "shared memory (host/shmcoll.c)" if lib.fastpm_b200_host_collectives_shared() else "launcher callbacks (torch.distributed)",
         "stages_rank0": stages, "np_total_after": int(np_local.item()), "result_finite": bool(fin.item() == 1),
         "pk_bins": [float(v) for v in spectra[-1][1][:8]] if spectra else None,
         "x_checksum": [float(v) for v in chk.tolist()],

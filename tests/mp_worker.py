@@ -118,6 +118,9 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     lib = _lib.require_device(local)
     multigpu.init_comm(lib)
+    # host scalars go through the shared segment of host/shmcoll.c on one host, through the callbacks when asked to
+    want_shared = 0 if os.environ.get("FASTPM_B200_HOST_COLL") == "callbacks" else 1
+    assert lib.fastpm_b200_host_collectives_shared() == want_shared, "host collectives: shared = %d" % lib.fastpm_b200_host_collectives_shared()
     from fastpm_b200.solver import Solver
     fx = np.load(os.path.join(ROOT, "tests", "golden", "small_run.npz"))
     L = 32.0
