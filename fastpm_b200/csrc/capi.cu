@@ -42,11 +42,13 @@ int fpm_paint_launch(const FpmMesh *m, float *canvas, const double *x, const flo
 int fpm_readout_launch(const FpmMesh *m, const float *canvas, const double *x, float *out, int out_stride, double prescale, long long np, cudaStream_t st, const float *pack0 = nullptr, const float *pack1 = nullptr);
 int fpm_plane_add_launch(float *dst, const float *src, size_t nfloats, cudaStream_t st);
 int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, const float *c2, const double *x, float *out, long long np, cudaStream_t st);
-int fpm_window_paint_launch(const FpmMesh *m, int type, int support, float *canvas, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
-int fpm_window_readout_launch(const FpmMesh *m, int type, int support, const float *canvas, const double *x, float *out, int out_stride, long long np, cudaStream_t st);
+int fpm_window_paint_launch(const FpmMesh *m, int type, int support, int diffdir, float *canvas, float *halo, const double *x, const float *mass, double M0, const float *field, int field_stride, long long np, cudaStream_t st);
+int fpm_window_readout_launch(const FpmMesh *m, int type, int support, int diffdir, const float *canvas, const float *halo, const double *x, float *out, int out_stride, long long np, cudaStream_t st);
+int fpm_window_halo(int type, int support, int *left, int *right);
 int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const float *dx1, const float *dx2, double dda, double q1, double q2, double Dv1, double Dv2, int cola, long long np, cudaStream_t st);
 int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
+int fpm_shift_launch(double *x, long long np, double s0, double s1, double s2, cudaStream_t st);
 int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np, int nops, const double *ops, cudaStream_t st);
 int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2, long long np, cudaStream_t st);
 int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st);
@@ -436,14 +438,31 @@ int fpm_paint_window(const fpm_mesh *m, int window, int support, float *canvas, 
                      const float *field, int field_stride)
 {
     LAZY1(canvas);
-    return fpm_window_paint_launch(m, window, support, canvas, x, mass, M0, field, field_stride, np, g_stream);
+    return fpm_window_paint_launch(m, window, support, -1, canvas, nullptr, x, mass, M0, field, field_stride, np, g_stream);
 }
 
 int fpm_readout_window(const fpm_mesh *m, int window, int support, const float *canvas, const double *x, int64_t np, float *out, int out_stride)
 {
     LAZY1(canvas);
-    return fpm_window_readout_launch(m, window, support, canvas, x, out, out_stride, np, g_stream);
+    return fpm_window_readout_launch(m, window, support, -1, canvas, nullptr, x, out, out_stride, np, g_stream);
 }
+
+// the same with a derivative direction (fastpm_painter_init_diff; window 0 = CIC allowed) and, on several GPUs, the block of halo planes
+int fpm_paint_window_ex(const fpm_mesh *m, int window, int support, int diffdir, float *canvas, float *halo, const double *x, int64_t np, double M0,
+                        const float *mass, const float *field, int field_stride)
+{
+    LAZY1(canvas);
+    return fpm_window_paint_launch(m, window, support, diffdir, canvas, halo, x, mass, M0, field, field_stride, np, g_stream);
+}
+
+int fpm_readout_window_ex(const fpm_mesh *m, int window, int support, int diffdir, const float *canvas, const float *halo, const double *x, int64_t np,
+                          float *out, int out_stride)
+{
+    LAZY1(canvas);
+    return fpm_window_readout_launch(m, window, support, diffdir, canvas, halo, x, out, out_stride, np, g_stream);
+}
+
+int fpm_window_halo_planes(int window, int support, int *left, int *right) { return fpm_window_halo(window, support, left, right); }
 
 // ------------------------------------------------------------------ FFT
 static void to_spec(const fpm_transfer *k, FpmTransferSpec *s)
@@ -651,6 +670,12 @@ int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, co
 // The "too far" flag of the previous wrap is examined when the next one is issued (or by fpm_wrap_check), so that
 // the integrator never drains the stream just to look at it.
 static int *d_wrap_bad = NULL, *h_wrap_bad = NULL;
+int fpm_shift_positions(double *x, int64_t np, double s0, double s1, double s2)
+{
+    if (ensure_init()) return -1;
+    return fpm_shift_launch(x, np, s0, s1, s2, g_stream);
+}
+
 int fpm_wrap_check(void)
 {
     if (!h_wrap_bad) return 0;

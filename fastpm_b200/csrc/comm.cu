@@ -237,6 +237,40 @@ extern "C" int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const
     return 0;
 }
 
+// The same for the wider windows (linear excepted: it has the CIC reach): every rank keeps the planes outside its slab in a halo
+// block, hl planes below the slab followed by hr planes above it (paint.cu: window_plane).  After the deposit my first hr planes
+// receive what the previous rank put above its slab and my last hl planes what the next rank put below its own; before the gather
+// my halo block is filled with the next rank's first hr planes and the previous rank's last hl planes.
+extern "C" int fpm_halo_add_wide_from(const fpm_mesh *m, float *canvas_local, const float *halo_prev_rank, const float *halo_next_rank, int hl, int hr)
+{
+    const FpmGeom &g = m->geom;
+    const size_t plane = (size_t) g.n * g.pitch_r;
+    if (hl > g.nxl || hr > g.nxl) { fpm_set_error("halo of %d + %d planes on slabs of %d planes", hl, hr, g.nxl); return -1; }
+    cudaStream_t st = comm_stream();
+    if (fpm_xbarrier_on(st)) return -1;
+    if (hr > 0) FPM_TIMED(FPM_K_HALO, st, (halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local, halo_prev_rank + (size_t) hl * plane, (size_t) hr * plane / 4)));
+    if (hl > 0) FPM_TIMED(FPM_K_HALO, st, (halo_add_kernel<<<148 * 8, 256, 0, st>>>(canvas_local + (size_t) (g.nxl - hl) * plane, halo_next_rank, (size_t) hl * plane / 4)));
+    fpm_comm_bytes[1] += (size_t) (hl + hr) * plane * sizeof(float);
+    FPM_CHECK_LAUNCH();
+    if (fpm_xbarrier_on(st)) return -1;
+    return 0;
+}
+
+extern "C" int fpm_halo_fetch_wide_from(const fpm_mesh *m, float *halo_local, const float *canvas_prev_rank, const float *canvas_next_rank, int hl, int hr)
+{
+    const FpmGeom &g = m->geom;
+    const size_t plane = (size_t) g.n * g.pitch_r;
+    if (hl > g.nxl || hr > g.nxl) { fpm_set_error("halo of %d + %d planes on slabs of %d planes", hl, hr, g.nxl); return -1; }
+    cudaStream_t st = comm_stream();
+    if (fpm_xbarrier_on(st)) return -1;
+    if (hl > 0) FPM_TIMED(FPM_K_HALO, st, (halo_copy_kernel<<<148 * 4, 256, 0, st>>>(halo_local, canvas_prev_rank + (size_t) (g.nxl - hl) * plane, (size_t) hl * plane / 4)));
+    if (hr > 0) FPM_TIMED(FPM_K_HALO, st, (halo_copy_kernel<<<148 * 4, 256, 0, st>>>(halo_local + (size_t) hl * plane, canvas_next_rank, (size_t) hr * plane / 4)));
+    FPM_CHECK_LAUNCH();
+    fpm_comm_bytes[1] += (size_t) (hl + hr) * plane * sizeof(float);
+    if (fpm_xbarrier_on(st)) return -1;
+    return 0;
+}
+
 // ------------------------------------------------------------------ particle migration
 // owner slab of a position: floor(x * inv_cell) mod N, divided by the slab thickness (pm_pos_to_rank, pmpfft.c:344-368)
 // wrap_bad != NULL: fastpm_store_wrap (store.c:447-475) folded in -- same operations as wrap_kernel (particles.cu), positions

@@ -24,6 +24,8 @@ int fpm_r2c_dist(fpm_mesh *m, float *real, float *const *cplx_peers, double scal
 int fpm_c2r_dist(fpm_mesh *m, const float *cplx, float *const *real_peers, const fpm_transfer *kernel);
 int fpm_halo_add_from(const fpm_mesh *m, float *canvas_local, const float *canvas_prev_rank);
 int fpm_halo_fetch_from(const fpm_mesh *m, float *canvas_local, const float *canvas_next_rank);
+int fpm_halo_add_wide_from(const fpm_mesh *m, float *canvas_local, const float *halo_prev_rank, const float *halo_next_rank, int hl, int hr);
+int fpm_halo_fetch_wide_from(const fpm_mesh *m, float *halo_local, const float *canvas_prev_rank, const float *canvas_next_rank, int hl, int hr);
 int fpm_migrate_init(int nranks, int cap, long long np_upper, size_t row_bytes, void *pack);
 int fpm_migrate_classify(const fpm_mesh *m, double *x, int64_t np, int *send_count_host, int wrap, int *overflow_host);
 int fpm_migrate_pack_column(const fpm_mesh *m, const void *col, int elsize, const int *send_count_host, size_t col_off_bytes);
@@ -147,6 +149,11 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
 void fpm_halo_add(PM *pm, FastPMFloat *canvas)
 {
     void *peers[MAXR];
+    if (pm->whalo) {            /* a window wider than CIC: what the neighbours put into their halo blocks (pm->whalo, host/gravity.c) */
+        peers_of(pm->whalo, peers);
+        FPM_MUST(fpm_halo_add_wide_from(pm->mesh, canvas, peers[(g_rank - 1 + g_size) % g_size], peers[(g_rank + 1) % g_size], pm->whl, pm->whr));
+        return;
+    }
     peers_of(canvas, peers);
     FPM_MUST(fpm_halo_add_from(pm->mesh, canvas, peers[(g_rank - 1 + g_size) % g_size]));
 }
@@ -155,6 +162,10 @@ void fpm_halo_fetch(PM *pm, FastPMFloat *canvas)
 {
     void *peers[MAXR];
     peers_of(canvas, peers);
+    if (pm->whalo) {
+        FPM_MUST(fpm_halo_fetch_wide_from(pm->mesh, pm->whalo, peers[(g_rank - 1 + g_size) % g_size], peers[(g_rank + 1) % g_size], pm->whl, pm->whr));
+        return;
+    }
     FPM_MUST(fpm_halo_fetch_from(pm->mesh, canvas, peers[(g_rank + 1) % g_size]));
 }
 

@@ -120,7 +120,7 @@ static float *acc_planes_alloc(FastPMSolver *fastpm, PM *pm, FastPMPainter *pain
     static int off = -1;
     if (off < 0) off = getenv("FASTPM_B200_NO_PACKED_READOUT") ? 1 : 0;
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
-    if (off || painter->kernel != NULL || !cdm || !cdm->acc || cdm->np == 0) return NULL;
+    if (off || painter->kernel != NULL || painter->diffdir >= 0 || !cdm || !cdm->acc || cdm->np == 0) return NULL;
     const size_t need = 2 * sizeof(float) * cdm->np_upper;
     (void) pm;
     if (cdm->mem->used_bytes + need > cdm->mem->total_bytes) return NULL;
@@ -145,6 +145,17 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     LEAVE(readout);
 
     FastPMFloat *canvas = pm_alloc_noclear(pm, __FILE__, __LINE__);
+    /* Several GPUs and a window that reaches further than CIC's one plane above the slab: the planes outside the slab are kept
+     * in a halo block that fpm_halo_add / fpm_halo_fetch exchange with the neighbours (the reference: ghost particles,
+     * pmghosts.c:45-78, which handle any support). */
+    int whl = 0, whr = 0;
+    FPM_MUST(fpm_window_halo_planes(fpm_painter_window(painter), painter->support, &whl, &whr));
+    if (pm->NTask > 1 && (painter->kernel != NULL || painter->diffdir >= 0)) {
+        const size_t hbytes = sizeof(FastPMFloat) * (size_t) (whl + whr) * pm->Nmesh[1] * pm->pitch_r;
+        pm->whalo = fastpm_memory_alloc(pm->mem, "window halo planes", hbytes, FASTPM_MEMORY_HEAP);
+        pm->whl = whl; pm->whr = whr;
+        FPM_MUST(fpm_memset(pm->whalo, 0, hbytes));
+    }
 
     /* ---- density: gravity.c:305-353 */
     ENTER(paint);
@@ -181,7 +192,7 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
     const int nacc = (cdm && cdm->potential) ? 4 : 3;
     int d0 = 0;
-    if (painter->kernel == NULL /* CIC */ && fused_readout_wanted(fastpm, pm)) {
+    if (painter->kernel == NULL && painter->diffdir < 0 /* CIC */ && fused_readout_wanted(fastpm, pm)) {
         /* FASTPM_B200_FUSED_READOUT=1: the three inverse transforms into three meshes, then ONE pass over the particles
          * (positions read once instead of three times, ACC written as whole elements). Same values bit for bit. */
         FastPMFloat *cv[3] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__), pm_alloc_noclear(pm, __FILE__, __LINE__) };
@@ -244,5 +255,6 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         LEAVE(readout);
     }
     if (planes) fastpm_memory_free(fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM)->mem, planes);
+    if (pm->whalo) { fastpm_memory_free(pm->mem, pm->whalo); pm->whalo = NULL; }
     pm_free(pm, canvas);
 }

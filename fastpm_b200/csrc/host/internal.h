@@ -32,6 +32,8 @@ struct PM {
     int stage_off;                /* no room for it in the arena: direct peer stores */
     FastPMFloat *stage2;          /* second staging mesh: pipelined inverse transforms of the force components */
     int stage2_off;
+    FastPMFloat *whalo;           /* several GPUs, windows wider than CIC: halo planes below / above the slab (host/gravity.c) */
+    int whl, whr;
     int transposed;
     int pitch_r, pitch_c, nxl, x0, nyl, y0, halo;
 };
@@ -42,6 +44,7 @@ struct VPM {
     double pm_nc_factor;
     int end;
 };
+int fpm_painter_window(const FastPMPainter *painter);      /* FPM_WINDOW_* of csrc/window.h */
 VPM *vpm_create(VPMInit *vpminit, int base_nmesh, double boxsize, MPI_Comm comm);
 VPM *vpm_find(VPM *vpm, double a);
 void vpm_free(VPM *vpm);

@@ -1,6 +1,7 @@
 /* fastpm_b200 host layer -- painter object (reference: libfastpm/painter.c:128-374, painter-cic.c).
- * Only the CIC window (the default, lua-runtime-fastpm.lua:132-138, and the one BASELINE.json names) runs
- * on the device; the struct keeps the reference's public layout. */
+ * The CIC window (the default, lua-runtime-fastpm.lua:132-138, and the one BASELINE.json names) has its own kernels; the linear,
+ * quadratic and Lanczos windows and the derivative painters of fastpm_painter_init_diff share the generic ones (csrc/paint.cu).
+ * The struct keeps the reference's public layout. */
 #include "internal.h"
 #include "../window.h"
 
@@ -15,8 +16,11 @@ static double no_host_readout(FastPMPainter *painter, FastPMFloat *canvas, doubl
 static double linear_kernel(double x, double invh) { return fpm_window_linear(x, invh); }
 static double quad_kernel(double x, double invh) { return fpm_window_quad(x, invh); }
 static double lanczos_kernel(double x, double invh) { return fpm_window_lanczos(x, invh); }
+static double linear_diff(double x, double invh) { return fpm_window_linear_diff(x, invh); }
+static double quad_diff(double x, double invh) { return fpm_window_quad_diff(x, invh); }
+static double lanczos_diff(double x, double invh) { return fpm_window_lanczos_diff(x, invh); }
 
-static int window_of(const FastPMPainter *painter)
+int fpm_painter_window(const FastPMPainter *painter)
 {
     if (painter->kernel == NULL) return FPM_WINDOW_CIC;
     if (painter->kernel == linear_kernel) return FPM_WINDOW_LINEAR;
@@ -34,13 +38,11 @@ void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type,
     painter->kernel = NULL; painter->diff = NULL;
     switch (type) {
         case FASTPM_PAINTER_CIC: support = 2; break;
-        case FASTPM_PAINTER_LINEAR: painter->kernel = linear_kernel; support = 2; break;
-        case FASTPM_PAINTER_QUAD: painter->kernel = quad_kernel; support = 3; break;
-        case FASTPM_PAINTER_LANCZOS: painter->kernel = lanczos_kernel; break;
+        case FASTPM_PAINTER_LINEAR: painter->kernel = linear_kernel; painter->diff = linear_diff; support = 2; break;
+        case FASTPM_PAINTER_QUAD: painter->kernel = quad_kernel; painter->diff = quad_diff; support = 3; break;
+        case FASTPM_PAINTER_LANCZOS: painter->kernel = lanczos_kernel; painter->diff = lanczos_diff; break;
         default: fastpm_raise(-1, "fastpm_b200: painter type %d\n", (int) type);
     }
-    if (type != FASTPM_PAINTER_CIC && pm->NTask > 1)
-        fastpm_raise(-1, "fastpm_b200: the linear / quadratic / Lanczos painters run on one GPU only (their x-halo is wider than the one mesh plane exchanged)\n");
     if (support < 1 || support > FPM_WINDOW_MAX_SUPPORT) fastpm_raise(-1, "fastpm_b200: painter support %d (1..%d on the device)\n", support, FPM_WINDOW_MAX_SUPPORT);
     painter->diffdir = -1;
     painter->support = support;
@@ -49,6 +51,16 @@ void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type,
     painter->Npoints = support * support * support;
     painter->shift = support % 2 == 0 ? 0 : 0.5;
 }
+
+/* painter.c:178-182 */
+void fastpm_painter_init_diff(FastPMPainter *painter, FastPMPainter *base, int diffdir)
+{
+    *painter = *base;
+    painter->diffdir = diffdir;
+}
+
+/* the generic kernels serve every window but plain CIC */
+static int generic_path(const FastPMPainter *painter, int window) { return window != FPM_WINDOW_CIC || painter->diffdir >= 0; }
 
 void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field)
 {
@@ -60,10 +72,11 @@ void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore
         fcol = (const float *) p->columns[ci] + field.memb;
         fstride = (int) p->_column_info[ci].nmemb;
     }
-    const int window = window_of(painter);
-    if (window != FPM_WINDOW_CIC) {
+    const int window = fpm_painter_window(painter);
+    if (generic_path(painter, window)) {
         if (fpm_pending_wrap == p) { fpm_pending_wrap = NULL; fastpm_store_wrap(p, painter->pm->BoxSize); }
-        FPM_MUST(fpm_paint_window(painter->pm->mesh, window, painter->support, canvas, (const double *) p->x, (int64_t) size, p->meta.M0, p->mass, fcol, fstride));
+        FPM_MUST(fpm_paint_window_ex(painter->pm->mesh, window, painter->support, painter->diffdir, canvas, painter->pm->whalo, (const double *) p->x,
+                                     (int64_t) size, p->meta.M0, p->mass, fcol, fstride));
         return;
     }
     if (fpm_pending_wrap == p && size == p->np) {
@@ -81,9 +94,10 @@ void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMSto
     int ci = fastpm_store_find_column_id(p, field.attribute);
     if (ci < 0 || !p->columns[ci] || p->_column_info[ci].from_double == NULL) fastpm_raise(-1, "readout: target column is not an allocated float column\n");
     float *out = (float *) p->columns[ci] + field.memb;
-    const int window = window_of(painter);
-    if (window != FPM_WINDOW_CIC) {
-        FPM_MUST(fpm_readout_window(painter->pm->mesh, window, painter->support, canvas, (const double *) p->x, (int64_t) size, out, (int) p->_column_info[ci].nmemb));
+    const int window = fpm_painter_window(painter);
+    if (generic_path(painter, window)) {
+        FPM_MUST(fpm_readout_window_ex(painter->pm->mesh, window, painter->support, painter->diffdir, canvas, painter->pm->whalo, (const double *) p->x,
+                                       (int64_t) size, out, (int) p->_column_info[ci].nmemb));
         return;
     }
     FPM_MUST(fpm_readout(painter->pm->mesh, canvas, (const double *) p->x, (int64_t) size, out, (int) p->_column_info[ci].nmemb, 1.0));

@@ -84,7 +84,9 @@ static fpm_transfer lpt_kernel(int potorder, int difforder, int d1, int d2)
 void pm_2lpt_solve(PM *pm, FastPMFloat *delta_k, FastPMFuncK *growth_rate_func_k, FastPMStore *p, double shift[3], FastPMKernelType type)
 {
     if (growth_rate_func_k || p->dv1) fastpm_raise(-1, "fastpm_b200: scale-dependent growth (dv1) is out of scope of this build\n");
-    if (shift[0] != 0 || shift[1] != 0 || shift[2] != 0) fastpm_raise(-1, "fastpm_b200: shifted ICs are not implemented\n");
+    /* pm2lpt.c:30-34: the displacements are read out at the de-shifted (grid) positions; the shift is put back at the end */
+    const int shifted = shift[0] != 0 || shift[1] != 0 || shift[2] != 0;
+    if (shifted) FPM_MUST(fpm_shift_positions((double *) p->x, (int64_t) p->np, -shift[0], -shift[1], -shift[2]));
     int potorder, gradorder, difforder, deconvolveorder;
     fastpm_kernel_type_get_orders(type, &potorder, &gradorder, &difforder, &deconvolveorder);
     const size_t nf = pm->allocsize;
@@ -122,6 +124,7 @@ void pm_2lpt_solve(PM *pm, FastPMFloat *delta_k, FastPMFuncK *growth_rate_func_k
         /* the 3/7 of pm2lpt.c:133 is applied to each mesh value (rounded to float) inside the gather */
         fpm_mesh_readout(pm, w2, (const double *) p->x, (int64_t) p->np, (float *) p->dx2 + d, 3, 3.0 / 7);
     }
+    if (shifted) FPM_MUST(fpm_shift_positions((double *) p->x, (int64_t) p->np, shift[0], shift[1], shift[2]));      /* pm2lpt.c:141-145 */
     for (int d = 0; d < 3; d++) pm_free(pm, field[2 - d]);
     pm_free(pm, workspace);
     pm_free(pm, source);
@@ -430,6 +433,10 @@ FastPMSolver *fastpm_b200_solver_new(int64_t nc, double boxsize, const double *p
                                      growth_mode, compute_potential, nLPT, Omega_m_, h, T_cmb, N_eff, N_nu, NULL, FASTPM_SOFTENING_NONE, FASTPM_PAINTER_CIC, 2);
 }
 
+/* options of FastPMConfig that the scalar constructors below have no argument for; they apply to the NEXT solver made, then reset */
+static int g_next_use_shift = 0, g_next_use_dx1_only = 0;
+void fastpm_b200_solver_next_options(int use_shift, int use_dx1_only) { g_next_use_shift = use_shift; g_next_use_dx1_only = use_dx1_only; }
+
 FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double *pm_nc_factor_pairs, int npairs,
                                         double alloc_factor, double lpt_nc_factor, int force_mode, int kernel_type,
                                         int growth_mode, int compute_potential, double nLPT,
@@ -446,7 +453,8 @@ FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double
     c->N_ncdm = 0; c->ncdm_matterlike = 1; c->ncdm_freestreaming = 1; c->ncdm_linearresponse = 0; c->growth_mode = growth_mode;
     FastPMConfig *cfg = &b->config;                /* src/fastpm.c:186-217 */
     cfg->nc = nc; cfg->boxsize = boxsize; cfg->alloc_factor = alloc_factor; cfg->lpt_nc_factor = lpt_nc_factor;
-    cfg->cosmology = c; cfg->vpminit = b->vpminit; cfg->USE_DX1_ONLY = 0; cfg->USE_SHIFT = 0;
+    cfg->cosmology = c; cfg->vpminit = b->vpminit; cfg->USE_DX1_ONLY = g_next_use_dx1_only; cfg->USE_SHIFT = g_next_use_shift;
+    g_next_use_dx1_only = g_next_use_shift = 0;
     cfg->ExtraAttributes = compute_potential ? COLUMN_POTENTIAL : 0;
     if (pgdc) {
         cfg->pgdc = 1; cfg->pgdc_alpha0 = pgdc[0]; cfg->pgdc_A = pgdc[1]; cfg->pgdc_B = pgdc[2]; cfg->pgdc_kl = pgdc[3]; cfg->pgdc_ks = pgdc[4];

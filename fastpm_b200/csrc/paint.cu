@@ -536,20 +536,35 @@ __global__ void __launch_bounds__(FPM_TILE_THREADS) cic_readout_tile_kernel(cons
 // ------------------------------------------------------------------ the generic windows (painter.c:176-317): linear, quadratic, Lanczos
 // One particle per thread, support^3 mesh points.  _fill_k: per axis the window at the `support` points starting at
 // floor(x/h + shift) - left, normalised to sum 1; the deposit / gather then runs x-outermost, z-innermost with the weight
-// ((1 * kx) * ky) * kz, all in double like the reference.  One GPU only (the x-halo of these windows is wider than one plane).
-struct WindowSpec { int type, support, left; double shift, invh; };
+// ((1 * kx) * ky) * kz, all in double like the reference.
+//   * diffdir >= 0 (fastpm_painter_init_diff, painter.c:178-205): along that axis the window is replaced by its derivative times
+//     1/cellsize, the normalisation staying that of the window itself.  The CIC window goes through these kernels as well then
+//     (cic_paint_tuned / cic_readout_tuned with D = 1/cellsize, T = -1/cellsize, painter-cic.c:57-60,137-140), with the tuned
+//     routines' own order of products.
+//   * several GPUs: planes outside the slab [x0, x0 + nxl) live in a separate halo block, hl planes for x0 - hl .. x0 - 1 followed
+//     by hr planes for x0 + nxl .. x0 + nxl + hr - 1 (hl = left, hr = support - 1 - left, one more for the odd supports whose
+//     base cell is floor(x + 0.5)); comm.cu adds / fetches them (the reference: ghost particles, pmghosts.c:45-78).
+struct WindowSpec { int type, support, left, diffdir, hl, hr; double shift, invh; };
 
 __device__ __forceinline__ void window_fill(const FpmGeom &g, const WindowSpec &w, const double pos[3], int ipos[3], double k[3][FPM_WINDOW_MAX_SUPPORT])
 {
     #pragma unroll
     for (int d = 0; d < 3; d++) {
         const double gpos = pos[d] * g.inv_cellsize;
+        if (w.type == FPM_WINDOW_CIC) {
+            ipos[d] = (int) floor(gpos);
+            const double D = gpos - ipos[d];
+            k[d][0] = d == w.diffdir ? -g.inv_cellsize : 1. - D;
+            k[d][1] = d == w.diffdir ? g.inv_cellsize : D;
+            continue;
+        }
         ipos[d] = (int) floor(gpos + w.shift) - w.left;
         const double dx = gpos - ipos[d];
         double sum = 0;
         for (int i = 0; i < w.support; i++) {
             k[d][i] = fpm_window_eval(w.type, dx - i, w.invh);
             sum += k[d][i];
+            if (d == w.diffdir) k[d][i] = fpm_window_diff_eval(w.type, dx - i, w.invh) * g.inv_cellsize;
         }
         for (int i = 0; i < w.support; i++) k[d][i] /= sum;
     }
@@ -562,8 +577,24 @@ __device__ __forceinline__ int window_wrap(int t, int n)
     return t;
 }
 
-__global__ void __launch_bounds__(128) window_paint_kernel(const FpmGeom g, const WindowSpec w, float *__restrict__ canvas,
-        const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field, int field_stride, long long np)
+// plane ix (global, before the periodic wrap) of the canvas as this rank holds it; NULL when the slab and its halo do not reach it
+template <typename F>
+__device__ __forceinline__ F *window_plane(const FpmGeom &g, const WindowSpec &w, F *canvas, F *halo, int ix, size_t pl)
+{
+    if (g.nranks == 1) return canvas + (size_t) window_wrap(ix, g.n) * pl;
+    int lx = ix - g.x0;
+    if (lx >= g.nxl + w.hr) lx -= g.n;                // the periodic image nearest to the slab
+    else if (lx < -w.hl) lx += g.n;
+    if (lx >= 0 && lx < g.nxl) return canvas + (size_t) lx * pl;
+    if (halo == nullptr) return nullptr;
+    if (lx < 0 && lx >= -w.hl) return halo + (size_t) (lx + w.hl) * pl;
+    if (lx >= g.nxl && lx < g.nxl + w.hr) return halo + (size_t) (w.hl + lx - g.nxl) * pl;
+    return nullptr;
+}
+
+__global__ void __launch_bounds__(128) window_paint_kernel(const FpmGeom g, const WindowSpec w, float *__restrict__ canvas, float *__restrict__ halo,
+        const double *__restrict__ x, const float *__restrict__ mass, double M0, const float *__restrict__ field, int field_stride, long long np,
+        int *__restrict__ outside)
 {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -574,23 +605,30 @@ __global__ void __launch_bounds__(128) window_paint_kernel(const FpmGeom g, cons
     double weight = mass ? M0 + (double) mass[i] : M0;
     if (field) weight *= (double) field[i * field_stride];
     const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    const bool cic = w.type == FPM_WINDOW_CIC;
     for (int a = 0; a < w.support; a++) {
-        const int ix = window_wrap(ipos[0] + a, g.n);
+        float *plane = window_plane(g, w, canvas, halo, ipos[0] + a, pl);
+        if (plane == nullptr) { if (outside) atomicAdd(outside, 1); continue; }
         for (int b = 0; b < w.support; b++) {
             const int iy = window_wrap(ipos[1] + b, g.n);
-            float *row = canvas + (size_t) ix * pl + (size_t) iy * pr;
+            float *row = plane + (size_t) iy * pr;
+            const double wy = k[1][b] * weight;                 // painter-cic.c:79-80: the weight is folded into the y factors
             for (int c = 0; c < w.support; c++) {
                 const int iz = window_wrap(ipos[2] + c, g.n);
-                double kernel = 1.0;
-                kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
-                atomicAdd(row + iz, (float) (weight * kernel));
+                if (cic) {
+                    atomicAdd(row + iz, (float) (k[2][c] * k[0][a] * wy));
+                } else {
+                    double kernel = 1.0;
+                    kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
+                    atomicAdd(row + iz, (float) (weight * kernel));
+                }
             }
         }
     }
 }
 
 __global__ void __launch_bounds__(128) window_readout_kernel(const FpmGeom g, const WindowSpec w, const float *__restrict__ canvas,
-        const double *__restrict__ x, float *__restrict__ out, int out_stride, long long np)
+        const float *__restrict__ halo, const double *__restrict__ x, float *__restrict__ out, int out_stride, long long np, int *__restrict__ outside)
 {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -599,17 +637,23 @@ __global__ void __launch_bounds__(128) window_readout_kernel(const FpmGeom g, co
     double k[3][FPM_WINDOW_MAX_SUPPORT];
     window_fill(g, w, pos, ipos, k);
     const size_t pr = (size_t) g.pitch_r, pl = (size_t) g.n * pr;
+    const bool cic = w.type == FPM_WINDOW_CIC;
     double value = 0;
     for (int a = 0; a < w.support; a++) {
-        const int ix = window_wrap(ipos[0] + a, g.n);
+        const float *plane = window_plane(g, w, canvas, halo, ipos[0] + a, pl);
+        if (plane == nullptr) { if (outside) atomicAdd(outside, 1); continue; }
         for (int b = 0; b < w.support; b++) {
             const int iy = window_wrap(ipos[1] + b, g.n);
-            const float *row = canvas + (size_t) ix * pl + (size_t) iy * pr;
+            const float *row = plane + (size_t) iy * pr;
             for (int c = 0; c < w.support; c++) {
                 const int iz = window_wrap(ipos[2] + c, g.n);
-                double kernel = 1.0;
-                kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
-                value += kernel * (double) __ldg(row + iz);
+                if (cic) {
+                    value += (double) __ldg(row + iz) * (k[2][c] * k[0][a] * k[1][b]);
+                } else {
+                    double kernel = 1.0;
+                    kernel *= k[0][a]; kernel *= k[1][b]; kernel *= k[2][c];
+                    value += kernel * (double) __ldg(row + iz);
+                }
             }
         }
     }
@@ -779,37 +823,78 @@ int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, cons
     return 0;
 }
 
-static int window_spec(const FpmMesh *m, int type, int support, WindowSpec *w)
+// halo planes a window needs below / above a slab: the lowest cell of a particle at x0 <= x/h < x0 + nxl is floor(x/h + shift) - left
+// >= x0 - left, the highest floor(x/h + shift) - left + support - 1 <= x0 + nxl - 1 + (support - 1 - left) + (shift > 0)
+int fpm_window_halo(int type, int support, int *left, int *right)
 {
-    // fastpm_painter_init, painter.c:128-174
-    if (type == FPM_WINDOW_LINEAR) support = 2;
+    if (type == FPM_WINDOW_CIC || type == FPM_WINDOW_LINEAR) support = 2;
     else if (type == FPM_WINDOW_QUAD) support = 3;
-    else if (type != FPM_WINDOW_LANCZOS) { fpm_set_error("window type %d", type); return -1; }
-    if (support < 1 || support > FPM_WINDOW_MAX_SUPPORT) { fpm_set_error("window support %d (1..%d on the device)", support, FPM_WINDOW_MAX_SUPPORT); return -1; }
-    if (m->geom.nranks > 1) { fpm_set_error("the linear / quadratic / Lanczos windows run on one GPU only"); return -1; }
-    w->type = type; w->support = support; w->left = (support - 1) / 2;
-    w->shift = support % 2 == 0 ? 0 : 0.5; w->invh = 1 / (0.5 * support);
+    const int l = type == FPM_WINDOW_CIC ? 0 : (support - 1) / 2;
+    *left = l;
+    *right = support - 1 - l + ((type != FPM_WINDOW_CIC && support % 2) ? 1 : 0);
     return 0;
 }
 
-int fpm_window_paint_launch(const FpmMesh *m, int type, int support, float *canvas, const double *x, const float *mass, double M0,
+static int window_spec(const FpmMesh *m, int type, int support, int diffdir, bool have_halo, WindowSpec *w)
+{
+    // fastpm_painter_init, painter.c:128-174
+    if (type == FPM_WINDOW_LINEAR || type == FPM_WINDOW_CIC) support = 2;
+    else if (type == FPM_WINDOW_QUAD) support = 3;
+    else if (type != FPM_WINDOW_LANCZOS) { fpm_set_error("window type %d", type); return -1; }
+    if (support < 1 || support > FPM_WINDOW_MAX_SUPPORT) { fpm_set_error("window support %d (1..%d on the device)", support, FPM_WINDOW_MAX_SUPPORT); return -1; }
+    if (diffdir < -1 || diffdir > 2) { fpm_set_error("window derivative direction %d", diffdir); return -1; }
+    w->type = type; w->support = support; w->left = type == FPM_WINDOW_CIC ? 0 : (support - 1) / 2; w->diffdir = diffdir;
+    w->shift = (type != FPM_WINDOW_CIC && support % 2) ? 0.5 : 0; w->invh = 1 / (0.5 * support);
+    fpm_window_halo(type, support, &w->hl, &w->hr);
+    if (m->geom.nranks > 1) {
+        if (!have_halo) { fpm_set_error("the linear / quadratic / Lanczos / derivative windows need their halo block on several GPUs"); return -1; }
+        if (w->hl > m->geom.nxl || w->hr > m->geom.nxl) { fpm_set_error("window halo of %d + %d planes on slabs of %d planes", w->hl, w->hr, m->geom.nxl); return -1; }
+    }
+    return 0;
+}
+
+// particles whose window left the slab and its halo (a store that was not decomposed): counted, reported by the next call
+static int *g_window_outside = nullptr;
+static int window_outside_check(cudaStream_t st)
+{
+    if (!g_window_outside) {
+        FPM_CUDA_OK(cudaMalloc(&g_window_outside, sizeof(int)));
+        FPM_CUDA_OK(cudaMemsetAsync(g_window_outside, 0, sizeof(int), st));
+        return 0;
+    }
+    int n = 0;
+    FPM_CUDA_OK(cudaMemcpyAsync(&n, g_window_outside, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    if (n) {
+        FPM_CUDA_OK(cudaMemsetAsync(g_window_outside, 0, sizeof(int), st));
+        fpm_set_error("window paint / readout: %d mesh planes of particles outside this rank's slab and halo (store not decomposed?)", n);
+        return -1;
+    }
+    return 0;
+}
+
+int fpm_window_paint_launch(const FpmMesh *m, int type, int support, int diffdir, float *canvas, float *halo, const double *x, const float *mass, double M0,
                             const float *field, int field_stride, long long np, cudaStream_t st)
 {
     WindowSpec w;
-    if (window_spec(m, type, support, &w)) return -1;
+    if (window_spec(m, type, support, diffdir, halo != nullptr, &w)) return -1;
     if (np <= 0) return 0;
-    FPM_TIMED(FPM_K_PAINT, st, (window_paint_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, x, mass, M0, field, field_stride, np)));
+    int *outside = nullptr;
+    if (m->geom.nranks > 1) { if (window_outside_check(st)) return -1; outside = g_window_outside; }
+    FPM_TIMED(FPM_K_PAINT, st, (window_paint_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, halo, x, mass, M0, field, field_stride, np, outside)));
     FPM_CHECK_LAUNCH();
     return 0;
 }
 
-int fpm_window_readout_launch(const FpmMesh *m, int type, int support, const float *canvas, const double *x, float *out, int out_stride,
-                              long long np, cudaStream_t st)
+int fpm_window_readout_launch(const FpmMesh *m, int type, int support, int diffdir, const float *canvas, const float *halo, const double *x, float *out,
+                              int out_stride, long long np, cudaStream_t st)
 {
     WindowSpec w;
-    if (window_spec(m, type, support, &w)) return -1;
+    if (window_spec(m, type, support, diffdir, halo != nullptr, &w)) return -1;
     if (np <= 0) return 0;
-    FPM_TIMED(FPM_K_READOUT, st, (window_readout_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, x, out, out_stride, np)));
+    int *outside = nullptr;
+    if (m->geom.nranks > 1) { if (window_outside_check(st)) return -1; outside = g_window_outside; }
+    FPM_TIMED(FPM_K_READOUT, st, (window_readout_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(m->geom, w, canvas, halo, x, out, out_stride, np, outside)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -132,6 +132,17 @@ __global__ void __launch_bounds__(256) fused_update_kernel(const FusedArgs a)
     }
 }
 
+// x[i][d] += s[d]: the (de-)shift of the particles around the 2LPT readouts when the ICs sit at cell centres (pm2lpt.c:30-34,141-145)
+__global__ void __launch_bounds__(256) shift_kernel(double *x, long long n3, double s0, double s1, double s2)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < n3; i += stride) {
+        const int d = (int) (i % 3);
+        x[i] += d == 0 ? s0 : (d == 1 ? s1 : s2);
+    }
+}
+
 // store.c:447-475: remainder() then fold into [0, L]; a particle further than 10000 boxes away is an error
 __global__ void __launch_bounds__(256) wrap_kernel(double *x, long long n3, double L, int *bad)
 {
@@ -283,6 +294,14 @@ int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *
     if (a.any_kick && !acc) { fpm_set_error("fused update: a kick needs the acc column"); return -1; }
     if (a.any_dx && !dx1) { fpm_set_error("fused update: COLA / LPT operations need the dx1 (and dx2) columns"); return -1; }
     FPM_TIMED(a.any_drift ? FPM_K_DRIFT : FPM_K_KICK, st, (fused_update_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_shift_launch(double *x, long long np, double s0, double s1, double s2, cudaStream_t st)
+{
+    if (np <= 0) return 0;
+    FPM_TIMED(FPM_K_OTHER, st, (shift_kernel<<<stream_grid(3 * np), 256, 0, st>>>(x, 3 * np, s0, s1, s2)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

@@ -54,4 +54,57 @@ FPM_WINDOW_HD double fpm_window_eval(int type, double x, double invh)
 {
     return type == FPM_WINDOW_LINEAR ? fpm_window_linear(x, invh) : (type == FPM_WINDOW_QUAD ? fpm_window_quad(x, invh) : fpm_window_lanczos(x, invh));
 }
+
+/* ---- the derivatives of the windows (painter.c:20-27, 43-59, 85-125), used by a painter made with fastpm_painter_init_diff */
+FPM_WINDOW_HD double fpm_window_linear_diff(double x, double invh) { return x < 0 ? 1 * invh : -1 * invh; }
+
+FPM_WINDOW_HD double fpm_window_quad_diff(double x, double invh)
+{
+    double factor;
+    x *= invh;
+    if (x < 0) { x = -x; factor = -1 * invh; }
+    else factor = +1 * invh;
+    if (x < 0.5) return factor * (-2 * x);
+    return factor * (-(1.5 - x));
+}
+
+FPM_WINDOW_HD double fpm_window_dsinc(double x)
+{
+    x *= 3.1415927;
+    double r = 3.1415927;
+    if (x < 1e-5 && x > -1e-5) {
+        const double xx = x * x, xxxx = xx * xx;
+        r *= -x / 3 + x * xx / 30 - xxxx * x / 840 + xxxx * xx * x / 45360;
+    } else {
+        r *= 1 / x * cos(x) - 1 / (x * x) * sin(x);
+    }
+    return r;
+}
+
+/* _lanczos_diff (painter.c:117-125) looks all four factors up through ONE table and one "filled" flag: whichever function is asked
+ * for first fills it -- the sinc -- and the two dsinc factors then read sinc values from it whenever 1e-3 < x < 16.384; only outside
+ * that range (every negative argument in particular) they are the true derivative.  That is what the reference computes, so that is
+ * what is restated here. */
+FPM_WINDOW_HD double fpm_window_cached_dsinc_as_in_reference(double x)
+{
+    const double dx = 1e-3;
+    const double tablemax = dx * 16384, tablemin = dx * 1;
+    if (x > tablemin && x < tablemax) {
+        const int i = (int) (fabs(x) / dx);
+        return fpm_window_sinc(dx * i);
+    }
+    return fpm_window_dsinc(x);
+}
+
+FPM_WINDOW_HD double fpm_window_lanczos_diff(double x, double invh)
+{
+    const double u1 = fpm_window_cached_sinc(x), u2 = fpm_window_cached_dsinc_as_in_reference(x);
+    const double v1 = fpm_window_cached_sinc(x * invh), v2 = fpm_window_cached_dsinc_as_in_reference(x * invh) * invh;
+    return u1 * v2 + u2 * v1;
+}
+
+FPM_WINDOW_HD double fpm_window_diff_eval(int type, double x, double invh)
+{
+    return type == FPM_WINDOW_LINEAR ? fpm_window_linear_diff(x, invh) : (type == FPM_WINDOW_QUAD ? fpm_window_quad_diff(x, invh) : fpm_window_lanczos_diff(x, invh));
+}
 #endif

@@ -99,10 +99,11 @@ class Solver:
 
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4", growth_mode="ODE",
                  np_alloc_factor=1.0, lpt_nc_factor=1, compute_potential=False, Omega_m=0.307494, h=0.6774,
-                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5, pgdc=None, softening="none", painter="cic", painter_support=2):
+                 T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5, pgdc=None, softening="none", painter="cic", painter_support=2, use_shift=False, use_dx1_only=False):
         """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (pgdcorrection.c, src/fastpm.c:204-217);
         softening: "none", "gaussian", "gadget_long_range", "two_third", "gaussian36" (gravity.c:244-270);
-        painter: "cic", "linear", "quad", "lanczos" (+ painter_support for lanczos; painter.c:128-174; non-CIC: one GPU)."""
+        painter: "cic", "linear", "quad", "lanczos" (+ painter_support for lanczos; painter.c:128-174; any number of GPUs);
+        use_shift: ICs at cell centres (FastPMConfig.USE_SHIFT, solver.c:142-150)."""
         self.lib = _bind(_lib.require_device())
         par = None if pgdc is None else np.array([float(v) for v in pgdc], dtype=np.float64)
         if par is not None and par.shape != (5,):
@@ -111,6 +112,7 @@ class Solver:
         flat = np.array([v for pr in pairs for v in pr], dtype=np.float64)
         self.nc, self.boxsize, self.force_mode = int(nc), float(boxsize), force_mode
         self._handlers = []
+        self.lib.fastpm_b200_solver_next_options(int(use_shift), int(use_dx1_only))
         self.h = self.lib.fastpm_b200_solver_new_ex(int(nc), float(boxsize), flat.ctypes.data, len(pairs), float(np_alloc_factor),
                                                     float(lpt_nc_factor), FORCE_MODES[force_mode], KERNELS[kernel_type],
                                                     GROWTH_MODES[growth_mode], int(compute_potential), float(nLPT),

@@ -118,6 +118,16 @@ int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, 
 int fpm_paint_window(const fpm_mesh *m, int window, int support, float *canvas, const double *x, int64_t np, double M0, const float *mass,
                      const float *field, int field_stride);
 int fpm_readout_window(const fpm_mesh *m, int window, int support, const float *canvas, const double *x, int64_t np, float *out, int out_stride);
+/* the same with (a) a derivative direction, fastpm_painter_init_diff painter.c:178-205: along axis diffdir (0..2, -1 none) the window
+ * is replaced by its derivative / cellsize -- window 0 (CIC) allowed here: cic_paint_tuned / cic_readout_tuned with diffdir,
+ * painter-cic.c:57-60,137-140 -- and (b) on several GPUs the block of halo planes that stands in for the reference's ghost particles
+ * (pmghosts.c:45-78): fpm_window_halo_planes() says how many planes lie below (left) and above (right) a slab, `halo` holds
+ * left + right planes in that order, zeroed before a deposit; NULL on one GPU */
+int fpm_paint_window_ex(const fpm_mesh *m, int window, int support, int diffdir, float *canvas, float *halo, const double *x, int64_t np, double M0,
+                        const float *mass, const float *field, int field_stride);
+int fpm_readout_window_ex(const fpm_mesh *m, int window, int support, int diffdir, const float *canvas, const float *halo, const double *x, int64_t np,
+                          float *out, int out_stride);
+int fpm_window_halo_planes(int window, int support, int *left, int *right);
 
 /* ---- K2 / K4 FFT: pm_r2c, pm_c2r, pmpfft.c:370-399 ------------------------------------------ */
 /* r2c: cplx = DFT(real) * scale.  `real` is destroyed (as with PFFT_DESTROY_INPUT, pmpfft.c:290).
@@ -215,6 +225,8 @@ int fpm_wrap(double *x, int64_t np, double boxsize);
  * where wrapping changed it).  store.c:447 + painter.c:320 */
 int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, double M0, const float *mass, const float *field, int field_stride);
 int fpm_wrap_check(void);
+/* x[i][d] += s_d in place: the (de-)shift around the 2LPT readouts of cell-centred ICs (USE_SHIFT, pm2lpt.c:30-34,141-145) */
+int fpm_shift_positions(double *x, int64_t np, double s0, double s1, double s2);
 /* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;
  * host_out[ncomp][4] = min, max, sum, sum of squares */
 int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out);

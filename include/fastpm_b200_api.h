@@ -282,6 +282,7 @@ struct FastPMPainter {
     double shift;
 };
 void fastpm_painter_init(FastPMPainter *painter, PM *pm, FastPMPainterType type, int support);
+void fastpm_painter_init_diff(FastPMPainter *painter, FastPMPainter *base, int diffdir);      /* painter.c:178 */
 void fastpm_paint_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field);
 void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, size_t size, FastPMFieldDescr field);
 void fastpm_paint(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, FastPMFieldDescr field);
@@ -608,6 +609,8 @@ FastPMSolver *fastpm_b200_solver_new_ex(int64_t nc, double boxsize, const double
                                         int growth_mode, int compute_potential, double nLPT,
                                         double Omega_m, double h, double T_cmb, double N_eff, int N_nu, const double *pgdc, int softening_type,
                                         int painter_type, int painter_support);
+/* FastPMConfig.USE_SHIFT (ICs at cell centres, solver.c:142-150) and USE_DX1_ONLY for the next solver these constructors make */
+void fastpm_b200_solver_next_options(int use_shift, int use_dx1_only);
 void fastpm_b200_solver_free(FastPMSolver *solver);
 /* initial conditions as src/fastpm.c:415-545 makes them from a seed and a linear P(k) table (k, p: `size` doubles each), all on the
  * device: Gadget-scheme white noise, optional remove_variance, colouring, DC mode = 1, 2LPT at a0 */

@@ -32,6 +32,7 @@ class RefConfig(C.Structure):
         ("w0", C.c_double), ("wa", C.c_double), ("N_eff", C.c_double),
         ("N_nu", C.c_int), ("enforce_broadband_kmax", C.c_int),
         ("pgdc", C.c_double * 6), ("softening_type", C.c_int), ("painter_type", C.c_int), ("painter_support", C.c_int),
+        ("use_shift", C.c_int),
     ]
 
 
@@ -63,9 +64,10 @@ class Session:
     def __init__(self, nc, boxsize, pm_nc_factor=2, force_mode="fastpm", kernel_type="1_4",
                  growth_mode="ODE", np_alloc_factor=4.0, lpt_nc_factor=1, compute_potential=False,
                  Omega_m=0.307494, h=0.6774, T_cmb=0.0, N_eff=3.046, N_nu=0, nLPT=-2.5,
-                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None, softening="none", painter="cic", painter_support=2):
+                 use_dx1_only=False, verbose=False, enforce_broadband_kmax=4, pgdc=None, softening="none", painter="cic", painter_support=2, use_shift=False):
         """pgdc: None, or (alpha0, A, B, kl, ks) to switch the PGD correction on (src/fastpm.c:204-217)."""
         cfg = RefConfig()
+        cfg.use_shift = int(use_shift)
         cfg.nc = nc
         cfg.boxsize = boxsize
         pairs = pm_nc_factor if isinstance(pm_nc_factor, (list, tuple)) else [(0.0, pm_nc_factor)]
@@ -275,16 +277,25 @@ class Session:
                           _p(x), C.c_int64(len(x)), _p(out))
         return out
 
-    def paint_window(self, x, window, support=0, which=0, a=1.0):
-        """window: "linear", "quad", "lanczos" (painter.c:128-174); support only matters for lanczos."""
+    def paint_window(self, x, window, support=0, which=0, a=1.0, diffdir=-1):
+        """window: "linear", "quad", "lanczos" (painter.c:128-174); support only matters for lanczos.  diffdir >= 0: through a
+        derivative painter (fastpm_painter_init_diff), "cic" allowed then."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = self._buf(which, a)
+        if diffdir >= 0:
+            lib().ref_paint_window_diff(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support), C.c_int(diffdir),
+                                        _p(x), C.c_int64(len(x)), _p(out))
+            return out
         lib().ref_paint_window(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support), _p(x), C.c_int64(len(x)), _p(out))
         return out
 
-    def readout_window(self, canvas, x, window, support=0, which=0, a=1.0):
+    def readout_window(self, canvas, x, window, support=0, which=0, a=1.0, diffdir=-1):
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(len(x), dtype=np.float32)
+        if diffdir >= 0:
+            lib().ref_readout_window_diff(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support), C.c_int(diffdir),
+                                          _p(np.ascontiguousarray(canvas, dtype=np.float32)), _p(x), C.c_int64(len(x)), _p(out))
+            return out
         lib().ref_readout_window(self._h, C.c_int(which), C.c_double(a), C.c_int(WINDOWS[window]), C.c_int(support),
                                  _p(np.ascontiguousarray(canvas, dtype=np.float32)), _p(x), C.c_int64(len(x)), _p(out))
         return out

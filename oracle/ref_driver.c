@@ -44,6 +44,7 @@ typedef struct {
     int softening_type;          /* FastPMSofteningType (gravity.c:244-270); 0 = none */
     int painter_type;            /* FastPMPainterType of the force step (config->PAINTER_TYPE); 0 = CIC */
     int painter_support;
+    int use_shift;               /* config->USE_SHIFT: ICs at cell centres (solver.c:142-150,201-209) */
 } RefConfig;
 
 #define MAX_FORCE_RECORDS 256
@@ -147,7 +148,7 @@ RefSession *ref_session_new(const RefConfig *cfg)
     config->cosmology = c;
     config->USE_DX1_ONLY = cfg->use_dx1_only;
     config->nLPT = cfg->nLPT;
-    config->USE_SHIFT = 0;
+    config->USE_SHIFT = cfg->use_shift;
     config->FORCE_TYPE = cfg->force_mode;
     config->KERNEL_TYPE = cfg->kernel_type;
     config->SOFTENING_TYPE = (FastPMSofteningType) cfg->softening_type;
@@ -419,6 +420,40 @@ void ref_readout_window(RefSession *s, int which, double a, int type, int suppor
     PM *pm = pick_pm(s, which, a);
     FastPMPainter painter[1];
     fastpm_painter_init(painter, pm, (FastPMPainterType) type, support);
+    FastPMStore p[1];
+    tmp_store(p, x, np);
+    FastPMFloat *canvas = pm_alloc(pm);
+    memcpy(canvas, canvas_in, sizeof(FastPMFloat) * pm->allocsize);
+    FastPMFieldDescr f = { COLUMN_ACC, 0 };
+    fastpm_readout_local(painter, canvas, p, p->np, f);
+    for (int64_t i = 0; i < np; i++) out[i] = p->acc[i][0];
+    pm_free(pm, canvas);
+    fastpm_store_destroy(p);
+}
+
+/* the same two through a derivative painter (fastpm_painter_init_diff, painter.c:178-205; type 0 = CIC: painter-cic.c:57-60) */
+void ref_paint_window_diff(RefSession *s, int which, double a, int type, int support, int diffdir, const double *x, int64_t np, float *canvas_out)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMPainter base[1], painter[1];
+    fastpm_painter_init(base, pm, (FastPMPainterType) type, support);
+    fastpm_painter_init_diff(painter, base, diffdir);
+    FastPMStore p[1];
+    tmp_store(p, x, np);
+    FastPMFloat *canvas = pm_alloc(pm);
+    FastPMFieldDescr none = { 0, 0 };
+    fastpm_paint_local(painter, canvas, p, p->np, none);
+    memcpy(canvas_out, canvas, sizeof(FastPMFloat) * pm->allocsize);
+    pm_free(pm, canvas);
+    fastpm_store_destroy(p);
+}
+
+void ref_readout_window_diff(RefSession *s, int which, double a, int type, int support, int diffdir, const float *canvas_in, const double *x, int64_t np, float *out)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMPainter base[1], painter[1];
+    fastpm_painter_init(base, pm, (FastPMPainterType) type, support);
+    fastpm_painter_init_diff(painter, base, diffdir);
     FastPMStore p[1];
     tmp_store(p, x, np);
     FastPMFloat *canvas = pm_alloc(pm);

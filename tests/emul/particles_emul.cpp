@@ -130,27 +130,74 @@ int main(int argc, char **argv)
         }
         std::vector<uint64_t> st(stats, stats + 2); dump(out, st);
     } else if (op == "wpaint" || op == "wreadout") {
-        // in: int32 n, int32 type, int32 support, float64 L, float64 M0, int64 np, x[np][3] f64, (wreadout: dense canvas f32[n^3])
+        // in: int32 n, int32 type, int32 support, int32 diffdir, int32 nslab, float64 L, float64 M0, int64 np, x[np][3] f64,
+        //     (wreadout: dense canvas f32[n^3])
+        // nslab > 1: the mesh is cut into x-slabs as on several GPUs; every slab deposits its own particles into its planes and its
+        // halo block, and the halo planes are exchanged as csrc/comm.cu does (fpm_halo_add_wide_from / fpm_halo_fetch_wide_from)
         const int n = in.one<int32_t>(), type = in.one<int32_t>();
         int support = in.one<int32_t>();
+        const int diffdir = in.one<int32_t>(), nslab = in.one<int32_t>();
         const double L = in.one<double>(), M0 = in.one<double>();
         const long long np = in.one<int64_t>();
         std::vector<double> x = in.many<double>((size_t) 3 * np);
-        const FpmGeom g = geom(n, L);
-        if (type == FPM_WINDOW_LINEAR) support = 2; else if (type == FPM_WINDOW_QUAD) support = 3;
-        WindowSpec w = { type, support, (support - 1) / 2, support % 2 == 0 ? 0 : 0.5, 1 / (0.5 * support) };
-        std::vector<float> canvas((size_t) n * n * g.pitch_r, 0.f);
-        const unsigned grid = (unsigned) ((np + 127) / 128);
+        FpmGeom g = geom(n, L);
+        if (type == FPM_WINDOW_LINEAR || type == FPM_WINDOW_CIC) support = 2; else if (type == FPM_WINDOW_QUAD) support = 3;
+        const bool cic = type == FPM_WINDOW_CIC;
+        WindowSpec w = { type, support, cic ? 0 : (support - 1) / 2, diffdir, 0, 0, (!cic && support % 2) ? 0.5 : 0, 1 / (0.5 * support) };
+        w.hl = w.left; w.hr = support - 1 - w.left + ((!cic && support % 2) ? 1 : 0);
+        const size_t pl = (size_t) n * g.pitch_r;
+        std::vector<float> canvas((size_t) n * pl, 0.f);
+        const int nxl = n / nslab;
+        // particles of every slab, in their original order (owner: floor(x / h) mod N / nxl, comm.cu classify_kernel)
+        std::vector<std::vector<long long>> mine(nslab);
+        for (long long i = 0; i < np; i++) {
+            int ix = (int) floor(x[3 * i] * g.inv_cellsize);
+            ix %= n; if (ix < 0) ix += n;
+            mine[ix / nxl].push_back(i);
+        }
+        std::vector<std::vector<float>> halo(nslab, std::vector<float>((size_t) (w.hl + w.hr) * pl + 1, 0.f));
+        std::vector<float> res((size_t) np, 0.f);
+        int outside = 0;
+        if (op == "wreadout") {
+            std::vector<float> dense = in.many<float>((size_t) n * n * n);
+            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
+            // fetch: left part <- the previous slab's last hl planes, right part <- the next slab's first hr planes
+            if (nslab > 1) for (int r = 0; r < nslab; r++) {
+                const int prev = (r - 1 + nslab) % nslab, next = (r + 1) % nslab;
+                memcpy(halo[r].data(), &canvas[(size_t) (prev * nxl + nxl - w.hl) * pl], sizeof(float) * w.hl * pl);
+                memcpy(halo[r].data() + (size_t) w.hl * pl, &canvas[(size_t) (next * nxl) * pl], sizeof(float) * w.hr * pl);
+            }
+        }
+        for (int r = 0; r < nslab; r++) {
+            if (nslab > 1) { g.nranks = nslab; g.rank = r; g.nxl = nxl; g.x0 = r * nxl; }
+            const long long npr = nslab > 1 ? (long long) mine[r].size() : np;
+            std::vector<double> xr;
+            if (nslab > 1) { xr.resize((size_t) 3 * npr); for (long long i = 0; i < npr; i++) for (int d = 0; d < 3; d++) xr[3 * i + d] = x[3 * mine[r][i] + d]; }
+            const double *xp = nslab > 1 ? xr.data() : x.data();
+            float *cv = canvas.data() + (size_t) (nslab > 1 ? r * nxl : 0) * pl;
+            float *hp = nslab > 1 ? halo[r].data() : nullptr;
+            const unsigned grid = (unsigned) ((npr + 127) / 128);
+            if (npr == 0) continue;
+            if (op == "wpaint") {
+                launch_seq(grid, 128, [&]() { window_paint_kernel(g, w, cv, hp, xp, nullptr, M0, nullptr, 1, npr, &outside); });
+            } else {
+                std::vector<float> rr((size_t) npr, 0.f);
+                launch_seq(grid, 128, [&]() { window_readout_kernel(g, w, cv, hp, xp, rr.data(), 1, npr, &outside); });
+                for (long long i = 0; i < npr; i++) res[nslab > 1 ? mine[r][i] : i] = rr[i];
+            }
+        }
+        if (outside) { fprintf(stderr, "%d planes outside slab + halo\n", outside); return 3; }
         if (op == "wpaint") {
-            launch_seq(grid, 128, [&]() { window_paint_kernel(g, w, canvas.data(), x.data(), nullptr, M0, nullptr, 1, np); });
+            // add: my first hr planes += the previous slab's right part, my last hl planes += the next slab's left part
+            if (nslab > 1) for (int r = 0; r < nslab; r++) {
+                const int prev = (r - 1 + nslab) % nslab, next = (r + 1) % nslab;
+                for (size_t i = 0; i < (size_t) w.hr * pl; i++) canvas[(size_t) (r * nxl) * pl + i] += halo[prev][(size_t) w.hl * pl + i];
+                for (size_t i = 0; i < (size_t) w.hl * pl; i++) canvas[(size_t) (r * nxl + nxl - w.hl) * pl + i] += halo[next][i];
+            }
             std::vector<float> dense((size_t) n * n * n);
             for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&dense[((size_t) i * n + j) * n], &canvas[((size_t) i * n + j) * g.pitch_r], sizeof(float) * n);
             dump(out, dense);
         } else {
-            std::vector<float> dense = in.many<float>((size_t) n * n * n);
-            for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) memcpy(&canvas[((size_t) i * n + j) * g.pitch_r], &dense[((size_t) i * n + j) * n], sizeof(float) * n);
-            std::vector<float> res((size_t) np, 0.f);
-            launch_seq(grid, 128, [&]() { window_readout_kernel(g, w, canvas.data(), x.data(), res.data(), 1, np); });
             dump(out, res);
         }
     } else if (op == "readout3") {

@@ -254,6 +254,41 @@ def test_force_softening_matches_reference(ref_mod, pk_text, softening):
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
 
 
+def test_shifted_ics_match_reference(ref_mod, pk_text):
+    """FastPMConfig.USE_SHIFT (solver.c:142-150,201-209; the Lua option `shift`): the particle grid sits at the cell centres, the 2LPT
+    displacements are read out at the de-shifted positions (pm2lpt.c:30-34,141-145); ICs and a short run against the reference."""
+    from fastpm_b200.solver import Solver
+    nc, L = _nc(16), 2.0 * _nc(16)
+    kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0, use_shift=True)
+    steps = np.linspace(0.1, 1.0, 4)
+    s = ref_mod.Session(**kw)
+    dk, _, _ = s.ic_deltak(100, pk_text)
+    s.setup_lpt(dk, steps[0])
+    ic = s.get_particles()
+    s.evolve(steps)
+    want = s.get_particles()
+    s.close()
+    s = ref_mod.Session(**dict(kw, use_shift=False))
+    s.setup_lpt(dk, steps[0])
+    plain_ic = s.get_particles()
+    s.close()
+    g = Solver(**kw)
+    g.setup_lpt(dk, steps[0])
+    x0, v0 = g.get_column("x"), g.get_column("v")
+    g.evolve(steps)
+    x, v = g.get_column("x"), g.get_column("v")
+    g.close()
+
+    def pdist(a, b):
+        d = np.abs(np.mod(a, L) - np.mod(b, L))
+        return np.minimum(d, L - d).max()
+    assert abs(pdist(ic["x"], plain_ic["x"]) - 0.5 * L / nc) < 0.05 * L / nc      # the grid really moved by half a particle spacing
+    assert pdist(x0, ic["x"]) < 1e-5
+    assert np.abs(v0 - ic["v"]).max() < 1e-5 * np.abs(ic["v"]).max()
+    assert pdist(x, want["x"]) < 1e-4
+    assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
+
+
 @pytest.mark.parametrize("remove_variance", [False, True])
 def test_device_ic_chain_matches_reference(ref_mod, pk_text, remove_variance):
     """Row N1 end to end: fastpm_b200_setup_gadget_ic (white noise, [remove_variance], colouring, 2LPT: all on the device) gives the

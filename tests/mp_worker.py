@@ -240,6 +240,41 @@ def extras(rank, world):
         assert ic_err < 1e-5, ic_err
         assert np.abs(d1 - w["dx1"][ro]).max() < 1e-5 * np.abs(w["dx1"]).max() and np.abs(d2 - w["dx2"][ro]).max() < 1e-4 * np.abs(w["dx2"]).max()
         print("MP_EXTRAS_OK ranks=%d PGD position error %.3g Mpc/h, IC position error %.3g Mpc/h" % (world, err, ic_err))
+    # row N4 on several ranks: the quadratic and a Lanczos window, whose reach beyond the slab (1 + 2 and 2 + 3 mesh planes) is kept
+    # in a halo block and exchanged with both neighbours (host/gravity.c, csrc/comm.cu) where the reference moves ghost particles;
+    # one kick-drift-kick cycle (two force evaluations) against the reference, like the one-GPU case of first_gpu_run_cases.py
+    short = np.linspace(0.1, 1.0, 4)[:2]
+    errs = {}
+    for painter, support in (("quad", 3), ("lanczos", 6)):
+        kw = dict(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", painter=painter, painter_support=support)
+        box = [None]
+        if rank == 0:
+            s = ref.Session(np_alloc_factor=2.0, **kw)
+            dk, _, _ = s.ic_deltak(11, open(pk_path).read())
+            s.setup_lpt(dk, short[0])
+            s.evolve(short)
+            box = [(dk, s.get_particles())]
+            s.close()
+        dist.broadcast_object_list(box, src=0)
+        dk, want = box[0]
+        g = Solver(np_alloc_factor=3.0, **kw)
+        g.setup_lpt(dk, short[0])
+        g.evolve(short)
+        out = [None] * world
+        dist.all_gather_object(out, (g.get_column("id"), g.get_column("x"), g.get_column("v")))
+        g.close()
+        if rank == 0:
+            ids = np.concatenate([o[0] for o in out])
+            assert np.array_equal(np.sort(ids), np.sort(want["id"]))
+            order, ro = np.argsort(ids), np.argsort(want["id"])
+            x, v = (np.concatenate([o[i] for o in out])[order] for i in (1, 2))
+            dd = np.abs(np.mod(x, L) - np.mod(want["x"][ro], L))
+            errs[painter] = np.minimum(dd, L - dd).max()
+            assert errs[painter] < 2e-5, (painter, errs[painter])
+            verr = np.abs(v - want["v"][ro]).max() / np.abs(want["v"]).max()
+            assert verr < 1e-4, (painter, verr)
+    if rank == 0:
+        print("MP_WINDOWS_OK ranks=%d one kick-drift-kick: quadratic %.3g, Lanczos(6) %.3g Mpc/h from the reference" % (world, errs["quad"], errs["lanczos"]))
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ def emul_lib():
 GROUPS = [
     ["test_three_component_readout_equals_three_readouts", "test_device_gadget_ic_matches_reference", "test_single_mode_transfers_match_reference",
      "test_device_ic_chain_matches_reference", "test_pgd_correction_matches_reference"],
-    ["test_force_softening_matches_reference", "test_non_cic_painter_matches_reference"],
+    ["test_force_softening_matches_reference", "test_non_cic_painter_matches_reference", "test_shifted_ics_match_reference"],
     ["test_snapshot_files_and_restart_match_reference", "test_snapshots_during_evolve_match_reference"],
     ["test_cli_run_loop_program_matches_reference"],
 ]
@@ -112,4 +112,5 @@ def test_four_rank_slab_run_on_the_emulated_library(runs):
     rc, stdout, leftover = runs["ranks4"]
     assert "MP_GPU_OK ranks=4" in stdout, stdout[-3000:]
     assert "MP_EXTRAS_OK ranks=4" in stdout, stdout[-3000:]
+    assert "MP_WINDOWS_OK ranks=4" in stdout, stdout[-3000:]          # quadratic / Lanczos windows: halo planes on both sides of a slab
     assert not leftover                                                   # the shared-memory arenas were unlinked

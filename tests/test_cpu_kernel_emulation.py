@@ -193,25 +193,53 @@ def test_three_component_readout_equals_three_readouts(emul, one_thread_ref, tmp
     s.close()
 
 
+WINDOW_IDS = {"cic": 0, "linear": 1, "quad": 2, "lanczos": 3}
+
+
+def _window_case(emul, ref, tmp_path, window, support, diffdir, nslab, seed, exact_readout=True):
+    nmesh, L, npart = 16, 50.0, 3000
+    rng = np.random.default_rng(seed)
+    x = _positions(rng, npart, L)
+    s = ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint_window(x, window, support, diffdir=diffdir)).copy()
+    head = struct.pack("<iiiiiddq", nmesh, WINDOW_IDS[window], support, diffdir, nslab, L, 1.0, npart)
+    got = np.frombuffer(emul("wpaint", head + x.tobytes(), str(tmp_path)), dtype=np.float32).reshape(nmesh, nmesh, nmesh)
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    if diffdir < 0:
+        assert abs(got.sum(dtype=np.float64) - npart) < 1e-3       # the windows are normalised: mass is conserved
+    else:
+        assert np.abs(want).max() > 0.1                            # the derivative painter really did something
+    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
+    want_r = s.readout_window(s.real_pack(field), x, window, support, diffdir=diffdir)
+    got_r = np.frombuffer(emul("wreadout", head + x.tobytes() + field.tobytes(), str(tmp_path)), dtype=np.float32)
+    if exact_readout:
+        assert np.array_equal(got_r, want_r)
+    else:
+        assert np.abs(got_r - want_r).max() <= 1e-6 * np.abs(want_r).max()
+    s.close()
+
+
 @pytest.mark.parametrize("window,support", [("linear", 2), ("quad", 3), ("lanczos", 4), ("lanczos", 6)])
 def test_generic_window_kernels_against_reference(emul, one_thread_ref, tmp_path, window, support):
     """_generic_paint / _generic_readout (painter.c:176-317) with the linear, quadratic and Lanczos windows (the last with the
     reference's 1e-3 table quantisation): readout bit for bit, deposit up to the float rounding of each add (as for CIC)."""
-    nmesh, L, npart = 16, 50.0, 3000
-    rng = np.random.default_rng(13 + support)
-    x = _positions(rng, npart, L)
-    wid = {"linear": 1, "quad": 2, "lanczos": 3}[window]
-    s = one_thread_ref.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
-    want = s.real_view(s.paint_window(x, window, support)).copy()
-    head = struct.pack("<iiiddq", nmesh, wid, support, L, 1.0, npart)
-    got = np.frombuffer(emul("wpaint", head + x.tobytes(), str(tmp_path)), dtype=np.float32).reshape(nmesh, nmesh, nmesh)
-    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
-    assert abs(got.sum(dtype=np.float64) - npart) < 1e-3           # the windows are normalised: mass is conserved
-    field = rng.standard_normal((nmesh, nmesh, nmesh)).astype(np.float32)
-    want_r = s.readout_window(s.real_pack(field), x, window, support)
-    got_r = np.frombuffer(emul("wreadout", head + x.tobytes() + field.tobytes(), str(tmp_path)), dtype=np.float32)
-    assert np.array_equal(got_r, want_r)
-    s.close()
+    _window_case(emul, one_thread_ref, tmp_path, window, support, -1, 1, 13 + support)
+
+
+@pytest.mark.parametrize("window,support,diffdir", [("cic", 2, 0), ("cic", 2, 2), ("linear", 2, 1), ("quad", 3, 0), ("lanczos", 4, 2), ("lanczos", 6, 1)])
+def test_derivative_painters_against_reference(emul, one_thread_ref, tmp_path, window, support, diffdir):
+    """fastpm_painter_init_diff (painter.c:178-205, painter-cic.c:57-60): the window along one axis replaced by its derivative /
+    cellsize, the CIC window included; the Lanczos derivative with the reference's shared-table behaviour (csrc/window.h)."""
+    _window_case(emul, one_thread_ref, tmp_path, window, support, diffdir, 1, 31 + support + diffdir)
+
+
+@pytest.mark.parametrize("window,support,diffdir,nslab", [("quad", 3, -1, 2), ("lanczos", 4, -1, 4), ("lanczos", 6, -1, 2), ("linear", 2, -1, 4),
+                                                          ("lanczos", 6, 0, 4), ("cic", 2, 1, 2)])
+def test_window_kernels_on_slabs(emul, one_thread_ref, tmp_path, window, support, diffdir, nslab):
+    """The same kernels in their several-GPU form: every slab deposits into its planes and its block of halo planes, the blocks
+    are exchanged the way csrc/comm.cu does (fpm_halo_add_wide_from / fpm_halo_fetch_wide_from), and the result is the
+    reference's full mesh / readout (the reference moves ghost particles instead, pmghosts.c:45-78)."""
+    _window_case(emul, one_thread_ref, tmp_path, window, support, diffdir, nslab, 57 + support + nslab)
 
 
 def test_fused_wrap_and_brick_walk(emul, one_thread_ref, tmp_path):

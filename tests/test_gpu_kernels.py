@@ -71,6 +71,34 @@ def test_readout_bit_exact(dev, ref_mod, nmesh, kind):
     s.close()
 
 
+@pytest.mark.parametrize("window,support,diffdir", [("cic", 2, 0), ("linear", 2, 2), ("quad", 3, 1), ("lanczos", 6, 0), ("lanczos", 4, -1)])
+def test_window_and_derivative_painters_match_reference(dev, ref_mod, window, support, diffdir):
+    """fpm_paint_window_ex / fpm_readout_window_ex: the generic windows (painter.c:217-317) and the derivative painters of
+    fastpm_painter_init_diff (painter.c:178-205; CIC: painter-cic.c:57-60): readout bit for bit, deposit to the float rounding of
+    the adds."""
+    nmesh, L = 32, 50.0
+    rng = np.random.default_rng(77 + support + diffdir)
+    x = _positions(rng, 20000, L, "uniform")
+    wid = {"cic": 0, "linear": 1, "quad": 2, "lanczos": 3}[window]
+    s = ref_mod.Session(nc=nmesh, boxsize=L, pm_nc_factor=1)
+    want = s.real_view(s.paint_window(x, window, support, diffdir=diffdir)).copy()
+    m = dev.Mesh(nmesh, L)
+    lib = m.lib
+    canvas = m.alloc()
+    dev.check(lib.fpm_memset(canvas.ptr, 0, canvas.nbytes))
+    xd = dev.DeviceBuffer.from_host(x)
+    dev.check(lib.fpm_paint_window_ex(m.h, wid, support, diffdir, canvas.ptr, None, xd.ptr, len(x), 1.0, None, None, 1))
+    got = m.download_real(canvas)
+    assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max()
+    field = rng.normal(size=(nmesh, nmesh, nmesh)).astype(np.float32)
+    want_r = s.readout_window(s.real_pack(field), x, window, support, diffdir=diffdir)
+    m.upload_real(canvas, field)
+    out = dev.DeviceBuffer(4 * len(x))
+    dev.check(lib.fpm_readout_window_ex(m.h, wid, support, diffdir, canvas.ptr, None, xd.ptr, len(x), out.ptr, 1))
+    assert np.array_equal(out.download(np.float32), want_r)
+    s.close()
+
+
 def test_empty_and_single_particle(dev, ref_mod):
     """Edge cases of the store loops (painter.c:320-374, factors.c:176-197): np = 0 leaves everything untouched, np = 1 on a
     cell corner, on the box edge and outside the box deposits unit mass into the periodic images the reference uses."""

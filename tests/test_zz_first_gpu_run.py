@@ -21,6 +21,7 @@ CASES = [
     "test_force_softening_matches_reference",
     "test_non_cic_painter_matches_reference",
     "test_single_mode_transfers_match_reference",
+    "test_shifted_ics_match_reference",
 ]
 
 
@@ -53,3 +54,4 @@ def test_first_two_gpu_run_of_the_extras():
     r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MP_EXTRAS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     print(r.stdout[-3000:])
     assert "MP_EXTRAS_OK" in r.stdout
+    assert "MP_WINDOWS_OK" in r.stdout
