@@ -60,7 +60,7 @@ int fpm_remove_variance_launch(const FpmMesh *m, float *dk, cudaStream_t st);
 int fpm_axis_factors_launch(const FpmMesh *m, const double *d_table, const float *from, float *to, cudaStream_t st);
 int fpm_pgd_transfer_launch(const FpmMesh *m, const float *from, float *to, double alpha, double kl, double ks, cudaStream_t st);
 int fpm_pgd_shift_launch(double *x, const float *pgdc, double dyyy, double dyyy_last, long long np, cudaStream_t st);
-int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st);
+int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st, const float *dk2 = nullptr);
 int fpm_scale_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
 int fpm_divide_launch(const float *from, float *to, size_t nfloats, double value, cudaStream_t st);
 int fpm_muladd_launch(float *source, const float *a, const float *b, size_t nfloats, int sign, cudaStream_t st);
@@ -591,6 +591,23 @@ int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, doub
     double *d_out = NULL;
     FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
     int rc = fpm_powerspectrum_launch(m, cplx, decic, d_out, g_stream);
+    if (!rc) {
+        FPM_CUDA_OK(cudaMemcpyAsync(sums_host, d_out, sizeof(double) * (3 * nbins + 1), cudaMemcpyDeviceToHost, g_stream));
+        FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// cross spectrum of two fields, sum of w * Re(d1 conj d2) per shell (powerspectrum.c:87-105); same layout of sums_host
+int fpm_cross_powerspectrum_sums(const fpm_mesh *m, const float *cplx1, const float *cplx2, double *sums_host)
+{
+    if (cplx1 == cplx2) return fpm_powerspectrum_sums(m, cplx1, 0, sums_host);
+    LAZY1(cplx1); LAZY1(cplx2);
+    const int nbins = m->geom.n / 2;
+    double *d_out = NULL;
+    FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
+    int rc = fpm_powerspectrum_launch(m, cplx1, 0, d_out, g_stream, cplx2);
     if (!rc) {
         FPM_CUDA_OK(cudaMemcpyAsync(sums_host, d_out, sizeof(double) * (3 * nbins + 1), cudaMemcpyDeviceToHost, g_stream));
         FPM_CUDA_OK(cudaStreamSynchronize(g_stream));

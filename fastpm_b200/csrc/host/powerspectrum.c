@@ -61,7 +61,6 @@ void fastpm_powerspectrum_destroy(FastPMPowerSpectrum *ps) { free(ps->edges); fr
 
 void fastpm_powerspectrum_init_from_delta(FastPMPowerSpectrum *ps, PM *pm, const FastPMFloat *delta1_k, const FastPMFloat *delta2_k)
 {
-    if (delta1_k != delta2_k) fastpm_raise(-1, "fastpm_b200: cross power spectra are not implemented\n");
     const int nb = (int) pm->Nmesh[0] / 2;
     fastpm_powerspectrum_init(ps, nb);
     ps->pm = pm;
@@ -69,7 +68,8 @@ void fastpm_powerspectrum_init_from_delta(FastPMPowerSpectrum *ps, PM *pm, const
     ps->k0 = 2 * M_PI / pm->BoxSize[0];
     for (int i = 0; i <= nb; i++) ps->edges[i] = i * ps->k0;
     double *sums = malloc(sizeof(double) * (3 * nb + 1));
-    FPM_MUST(fpm_powerspectrum_sums(pm->mesh, delta1_k, 0, sums));
+    if (delta1_k == delta2_k) FPM_MUST(fpm_powerspectrum_sums(pm->mesh, delta1_k, 0, sums));
+    else FPM_MUST(fpm_cross_powerspectrum_sums(pm->mesh, delta1_k, delta2_k, sums));      /* powerspectrum.c:87-91 */
     fpm_comm_allreduce_double(pm->comm, sums, 3 * nb, 0);          /* powerspectrum.c:113-115 */
     for (int i = 0; i < nb; i++) {
         ps->Nmodes[i] = sums[i];

@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(256) decic_kernel(const FpmGeom g, const doubl
 // by instruction issue (fp64, shuffles), see DESIGN.md section 9.
 template <bool GEOM>
 __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmGeom g, const double *__restrict__ dtab, int decic,
-        const float2 *__restrict__ dk, double k0, double *__restrict__ out /* GEOM: [2][nbins]; else [nbins] + 1 */)
+        const float2 *__restrict__ dk, double k0, double *__restrict__ out /* GEOM: [2][nbins]; else [nbins] + 1 */,
+        const float2 *__restrict__ dk2 = nullptr /* cross spectrum: Re(dk conj(dk2)), powerspectrum.c:87-91 */)
 {
     FPM_DYN_SMEM(hist_raw, 8);
     double *hist_all = reinterpret_cast<double *>(hist_raw);
@@ -171,13 +172,15 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
         const int kxy = ikx * ikx + iky * iky;
         const double dxy = (!GEOM && decic) ? dtab[ix] * dtab[iy] : 1.0;      // (1 * d[ix]) * d[iy], the reference's order
         const float4 *src = reinterpret_cast<const float4 *>(dk + row * (size_t) g.pitch_c);
+        const float4 *src2 = reinterpret_cast<const float4 *>(dk2 + row * (size_t) g.pitch_c);
         for (int c0 = 0; c0 < nchunk; c0 += PK_UNROLL) {
-            float4 vv[PK_UNROLL];
+            float4 vv[PK_UNROLL], vv2[PK_UNROLL];
             if (!GEOM) {
                 #pragma unroll
                 for (int u = 0; u < PK_UNROLL; u++) {
                     const int iz = (c0 + u) * 64 + 2 * lane;          // pitch_c is a multiple of 16: iz + 1 stays inside the row
                     vv[u] = (c0 + u < nchunk && iz <= h) ? __ldg(src + (iz >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vv2[u] = (dk2 != nullptr && c0 + u < nchunk && iz <= h) ? __ldg(src2 + (iz >> 1)) : vv[u];
                 }
             }
             #pragma unroll
@@ -207,7 +210,9 @@ __global__ void __launch_bounds__(32 * PK_WARPS) powerspectrum_kernel(const FpmG
                             v.x = (float) ((double) v.x * smth);
                             v.y = (float) ((double) v.y * smth);
                         }
-                        const double p2 = w * ((double) v.x * (double) v.x + (double) v.y * (double) v.y);
+                        // the second field of a cross spectrum (never with a pending deconvolution: the launcher sees to that)
+                        const float2 v2 = dk2 == nullptr ? v : (e ? make_float2(vv2[u].z, vv2[u].w) : make_float2(vv2[u].x, vv2[u].y));
+                        const double p2 = w * ((double) v.x * (double) v2.x + (double) v.y * (double) v2.y);
                         if (inrow) allsum += p2;
                         if (counted) acc[e] = p2;
                     }
@@ -603,7 +608,7 @@ int fpm_decic_launch(const FpmMesh *m, const float *from, float *to, cudaStream_
 
 // d_out: [3][n/2] = Nmodes, sum w*|d|^2, sum w*k (not yet normalised; multi-GPU callers all-reduce first), then 1 slot:
 // the sum of w*|d|^2 over every mode including DC and the corners beyond the last shell
-int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st)
+int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, double *d_out, cudaStream_t st, const float *dk2)
 {
     const FpmGeom &g = m->geom;
     const int nbins = g.n / 2;
@@ -634,7 +639,9 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
     if (rows_mode < 0) { const char *e = getenv("FASTPM_B200_PK"); rows_mode = (e && !strcmp(e, "generic")) ? 0 : 1; }
     const int h = g.n / 2;
     const size_t smem_rows = sizeof(double) * (size_t) (h + 66) + sizeof(double) * (size_t) (nbins + 2) + sizeof(float2) * (size_t) PKR_WARPS * (h + 66);
-    if (rows_mode && h % 64 == 0 && h <= 4096 && smem_rows <= 227 * 1024 && (size_t) g.nyl * g.n < ((size_t) 1 << 31)) {
+    if (dk2 == dk) dk2 = nullptr;
+    if (dk2 != nullptr && decic) { fpm_set_error("cross power spectrum with a pending deconvolution"); return -1; }
+    if (dk2 == nullptr && rows_mode && h % 64 == 0 && h <= 4096 && smem_rows <= 227 * 1024 && (size_t) g.nyl * g.n < ((size_t) 1 << 31)) {
         static bool attr_rows = false;
         if (!attr_rows) { FPM_CUDA_OK(cudaFuncSetAttribute(powerspectrum_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_rows = true; }
         int per_sm = (int) ((227 * 1024) / (smem_rows + 1024));
@@ -646,7 +653,7 @@ int fpm_powerspectrum_launch(const FpmMesh *m, const float *dk, int decic, doubl
         fpm_path_counter[FPM_PATH_PK_ROWS]++;
         FPM_TIMED(FPM_K_PK, st, (powerspectrum_rows_kernel<<<(unsigned) grid, 32 * PKR_WARPS, smem_rows, st>>>(g, m->d_decic, decic, (const float2 *) dk, d_data)));
     } else {
-        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * w_data, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data)));
+        FPM_TIMED(FPM_K_PK, st, (powerspectrum_kernel<false><<<148 * ctas_per_sm, 32 * w_data, smem_data, st>>>(g, m->d_decic, decic, (const float2 *) dk, k0, d_data, (const float2 *) dk2)));
     }
     FPM_CHECK_LAUNCH();
     pk_assemble_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(mm->d_pkgeom, d_data, nbins, d_out);

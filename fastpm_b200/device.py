@@ -161,6 +161,18 @@ class Mesh:
         check(self.lib.fpm_powerspectrum(self.h, cplx.ptr, int(decic), k.ctypes.data, p.ctypes.data, nm.ctypes.data), "fpm_powerspectrum")
         return k, p, nm
 
+    def cross_powerspectrum(self, cplx1, cplx2):
+        """sum of w Re(d1 conj d2) per shell, normalised like powerspectrum() (powerspectrum.c:87-123)"""
+        nb = self.n // 2
+        sums = np.zeros(3 * nb + 1)
+        check(self.lib.fpm_cross_powerspectrum_sums(self.h, cplx1.ptr, cplx2.ptr, sums.ctypes.data), "fpm_cross_powerspectrum_sums")
+        nm = sums[:nb].copy()
+        ok = nm > 0
+        k, p = np.zeros(nb), np.zeros(nb)
+        k[ok] = sums[2 * nb:3 * nb][ok] / nm[ok]
+        p[ok] = sums[nb:2 * nb][ok] / nm[ok] * self.boxsize ** 3
+        return k, p, nm
+
     def fill_gaussian_gadget(self, cplx, seed):
         """fastpm_ic_fill_gaussiank(..., FASTPM_DELTAK_GADGET): RANLUX white noise with the Gadget seeding scheme."""
         check(self.lib.fpm_fill_gaussian_gadget(self.h, cplx.ptr, int(seed)), "fpm_fill_gaussian_gadget")

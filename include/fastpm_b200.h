@@ -202,6 +202,9 @@ int fpm_powerspectrum(const fpm_mesh *m, const float *cplx, int decic, double *k
 /* raw sums for multi-GPU callers: sums_host[3*(N/2) + 1] = sum w, sum w |delta|^2, sum w |k| per shell, then the sum of
  * w |delta|^2 over ALL modes (pm_compute_variance, pmapi.c:277-295) */
 int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, double *sums_host);
+/* the same for a cross spectrum: sum of w * Re(d1 conj d2) per shell (delta1_k != delta2_k in fastpm_powerspectrum_init_from_delta,
+ * powerspectrum.c:87-105); a deconvolution pending on either field is applied first */
+int fpm_cross_powerspectrum_sums(const fpm_mesh *m, const float *cplx1, const float *cplx2, double *sums_host);
 
 /* ---- K6 / K7 kick, drift: fastpm_kick_store / fastpm_drift_store, factors.c:176,374 ----------- */
 /* factors are the already interpolated differences (fastpm_kick_one, factors.c:148-171) */

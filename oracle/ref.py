@@ -334,6 +334,13 @@ class Session:
                                 _p(k), _p(p), _p(nm))
         return k, p, nm
 
+    def cross_powerspectrum(self, delta1_k, delta2_k, which=0, a=1.0):
+        n = self.pm_info(which, a)["Nmesh"] // 2
+        k, p, nm = np.zeros(n), np.zeros(n), np.zeros(n)
+        lib().ref_cross_powerspectrum(self._h, C.c_int(which), C.c_double(a), _p(np.ascontiguousarray(delta1_k, dtype=np.float32)),
+                                      _p(np.ascontiguousarray(delta2_k, dtype=np.float32)), _p(k), _p(p), _p(nm))
+        return k, p, nm
+
     def compute_force(self, a, want_delta_k=False):
         dk = self._buf(0, a) if want_delta_k else None
         lib().ref_compute_force(self._h, C.c_double(a), _p(dk))

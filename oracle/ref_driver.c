@@ -705,6 +705,25 @@ int ref_powerspectrum(RefSession *s, int which, double a, const float *delta_k_i
     return n;
 }
 
+/* the cross spectrum of two fields (delta1_k != delta2_k, powerspectrum.c:87-91) */
+int ref_cross_powerspectrum(RefSession *s, int which, double a, const float *delta1_k_in, const float *delta2_k_in, double *k, double *p, double *nmodes)
+{
+    PM *pm = pick_pm(s, which, a);
+    FastPMFloat *dk1 = pm_alloc(pm), *dk2 = pm_alloc(pm);
+    memcpy(dk1, delta1_k_in, sizeof(FastPMFloat) * pm->allocsize);
+    memcpy(dk2, delta2_k_in, sizeof(FastPMFloat) * pm->allocsize);
+    FastPMPowerSpectrum ps;
+    fastpm_powerspectrum_init_from_delta(&ps, pm, dk1, dk2);
+    int n = (int) ps.base.size;
+    memcpy(k, ps.base.k, sizeof(double) * n);
+    memcpy(p, ps.base.f, sizeof(double) * n);
+    memcpy(nmodes, ps.Nmodes, sizeof(double) * n);
+    fastpm_powerspectrum_destroy(&ps);
+    pm_free(pm, dk2);
+    pm_free(pm, dk1);
+    return n;
+}
+
 /* One force evaluation on the session's particles at time a (solver.c:404 without events):
  * wrap + decompose + fastpm_solver_compute_force; delta_k (before decic) optionally returned. */
 void ref_compute_force(RefSession *s, double a, float *delta_k_out)

@@ -273,6 +273,22 @@ def test_powerspectrum_matches_reference(dev, ref_mod):
     assert np.array_equal(got, s.complex_view(s.decic(dk)))
     k5, p5, n5 = m.powerspectrum(src)                    # now materialised: a plain measurement gives the same numbers
     np.testing.assert_allclose(p5, p2, rtol=1e-12)
+    # cross spectrum of two different fields (delta1_k != delta2_k, powerspectrum.c:87-91); a pending deconvolution is applied first
+    field2 = (0.6 * field + 0.8 * rng.normal(size=field.shape)).astype(np.float32)
+    dkb = s.r2c(s.real_pack(field2))
+    kc, pc, nc_ = s.cross_powerspectrum(dk, dkb)
+    src1, src2 = m.alloc(), m.alloc()
+    m.upload_complex(src1, s.complex_view(dk))
+    m.upload_complex(src2, s.complex_view(dkb))
+    k6, p6, n6 = m.cross_powerspectrum(src1, src2)
+    assert np.array_equal(n6, nc_)
+    np.testing.assert_allclose(k6, kc, rtol=1e-13)
+    np.testing.assert_allclose(p6, pc, rtol=1e-11, atol=1e-12 * np.abs(pc).max())
+    assert np.abs(pc - p0).max() > 0.05 * np.abs(p0).max()        # really a different quantity from the auto spectrum
+    dev.check(m.lib.fpm_decic_defer(m.h, src1.ptr))
+    k7, p7, n7 = m.cross_powerspectrum(src1, src2)
+    kd, pd, nd = s.cross_powerspectrum(s.decic(dk), dkb)
+    np.testing.assert_allclose(p7, pd, rtol=1e-11, atol=1e-12 * np.abs(pd).max())
     s.close()
 
 
