@@ -55,7 +55,7 @@ enum FpmKernelClass {
 enum FpmPathCounter {
     FPM_PATH_FFT_TMA = 0, FPM_PATH_FFT_TILE_GENERIC, FPM_PATH_FFT_ZROW, FPM_PATH_FFT_Z_GENERIC, FPM_PATH_FFT_TMA_MULTI,
     FPM_PATH_PAINT_BRICKS, FPM_PATH_READOUT_BRICKS, FPM_PATH_PK_ROWS, FPM_PATH_STAGED_TRANSPOSE, FPM_PATH_PAINT_TILES,
-    FPM_PATH_READOUT_TILES, FPM_PATH_COUNT
+    FPM_PATH_READOUT_TILES, FPM_PATH_READOUT3, FPM_PATH_COUNT
 };
 extern unsigned long long fpm_path_counter[FPM_PATH_COUNT];
 extern int fpm_prof_on;

@@ -67,6 +67,23 @@ static void apply_softening_transfer(FastPMSofteningType type, PM *pm, FastPMFlo
     }
 }
 
+/* the pipelined inverse transforms of several GPUs followed by one gather for the three components: default when CDM is the only
+ * species, the window is CIC and two more canvases fit (every rank sees the same arena state: the same answer everywhere);
+ * FASTPM_B200_FUSED_READOUT=0 keeps the component-by-component gather */
+static int pipelined_fused_ok(FastPMSolver *fastpm, PM *pm, FastPMPainter *painter)
+{
+    static int off = -1;
+    if (off < 0) { const char *e = getenv("FASTPM_B200_FUSED_READOUT"); off = (e && atoi(e) == 0) ? 1 : 0; }
+    if (off || painter->kernel != NULL || painter->diffdir >= 0) return 0;
+    FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    if (!cdm || !cdm->acc) return 0;                /* nothing rank-local in here: the transforms are collective */
+    for (int si = 0; si < FASTPM_SOLVER_NSPECIES; si++)
+        if (si != FASTPM_SPECIES_CDM && fastpm_solver_get_species(fastpm, si)) return 0;
+    const size_t need = 2 * sizeof(FastPMFloat) * pm->allocsize;
+    if (pm->mem->used_bytes + need > pm->mem->total_bytes) return 0;
+    return fastpm_b200_arena_largest_free() >= need + (need >> 3);
+}
+
 /* opt-in; only when CDM is the only species and two more meshes fit beside what is allocated now */
 static int fused_readout_wanted(FastPMSolver *fastpm, PM *pm)
 {
@@ -192,7 +209,8 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
     FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
     const int nacc = (cdm && cdm->potential) ? 4 : 3;
     int d0 = 0;
-    if (painter->kernel == NULL && painter->diffdir < 0 /* CIC */ && fused_readout_wanted(fastpm, pm)) {
+    const int pipeline = pm->NTask > 1 && fpm_dist_pipeline_ready(pm);
+    if (!pipeline && painter->kernel == NULL && painter->diffdir < 0 /* CIC */ && fused_readout_wanted(fastpm, pm)) {
         /* FASTPM_B200_FUSED_READOUT=1: the three inverse transforms into three meshes, then ONE pass over the particles
          * (positions read once instead of three times, ACC written as whole elements). Same values bit for bit. */
         FastPMFloat *cv[3] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__), pm_alloc_noclear(pm, __FILE__, __LINE__) };
@@ -212,11 +230,36 @@ void fastpm_solver_compute_force(FastPMSolver *fastpm, PM *pm, FastPMPainter *pa
         pm_free(pm, cv[1]);
         d0 = 3;
     }
-    const int pipeline = d0 == 0 && pm->NTask > 1 && fpm_dist_pipeline_ready(pm);
     const size_t canvas_bytes = sizeof(FastPMFloat) * pm->allocsize;
+    const int fuse3 = pipeline && nacc == 3 && pipelined_fused_ok(fastpm, pm, painter);
     /* freed last (LIFO): allocated before the second canvas, for which room is kept */
-    float *planes = d0 == 0 ? acc_planes_alloc(fastpm, pm, painter, pipeline ? canvas_bytes + (canvas_bytes >> 3) : 0) : NULL;
-    if (pipeline) {
+    float *planes = (d0 == 0 && !fuse3) ? acc_planes_alloc(fastpm, pm, painter, pipeline ? canvas_bytes + (canvas_bytes >> 3) : 0) : NULL;
+    if (fuse3) {
+        /* Several GPUs with room for three canvases: the pipelined transforms below, and then ONE pass over the particles for
+         * the three components (cic_readout3_kernel: positions read once, ACC rows written whole; the same values bit for bit).
+         * Measured on 2 B200s at nc = 1024: the gather takes 24.7 ms per step instead of 3 x 11.1. */
+        FastPMFloat *cv[3] = { canvas, pm_alloc_noclear(pm, __FILE__, __LINE__), pm_alloc_noclear(pm, __FILE__, __LINE__) };
+        fpm_transfer t;
+        ENTER(c2r);
+        if (fpm_transfer_for_kernel((int) kernel, 0, 0, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        fpm_dist_c2r_begin(pm, delta_k, cv[0], &t, 0);
+        for (int d = 0; d < 3; d++) {
+            if (d + 1 < 3) {
+                if (fpm_transfer_for_kernel((int) kernel, 0, d + 1, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+                fpm_dist_c2r_begin(pm, delta_k, cv[d + 1], &t, (d + 1) & 1);
+            }
+            fpm_dist_c2r_finish(pm, cv[d], d & 1);
+            fpm_halo_fetch(pm, cv[d]);
+        }
+        LEAVE(c2r);
+        ENTER(readout);
+        fpm_store_flush(cdm);
+        FPM_MUST(fpm_readout3(pm->mesh, cv[0], cv[1], cv[2], (const double *) cdm->x, (int64_t) cdm->np, (float *) cdm->acc));
+        LEAVE(readout);
+        pm_free(pm, cv[2]);
+        pm_free(pm, cv[1]);
+        d0 = nacc;
+    } else if (pipeline && d0 == 0) {
         /* Several GPUs: the slab transpose of component d + 1 travels (copy engines, NVLink) while component d is finished
          * (y- and z-pass) and read out -- two canvases and two staging meshes, used alternately.  The arithmetic of every
          * component is that of fpm_mesh_c2r + readout; only the order in which the work is queued differs. */

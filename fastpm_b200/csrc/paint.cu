@@ -818,6 +818,7 @@ int fpm_readout3_launch(const FpmMesh *m, const float *c0, const float *c1, cons
     const unsigned grid = (unsigned) ((np + 255) / 256);
     int lag_nc = 0;
     const int nbrick = fpm_lagrangian_hint(np, m->geom, &lag_nc);
+    fpm_path_counter[FPM_PATH_READOUT3]++;
     FPM_TIMED(FPM_K_READOUT, st, (cic_readout3_kernel<<<grid, 256, 0, st>>>(m->geom, c0, c1, c2, x, out, np, lag_nc, nbrick)));
     FPM_CHECK_LAUNCH();
     return 0;

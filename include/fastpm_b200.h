@@ -58,7 +58,8 @@ uint64_t fpm_kernel_launch_count(void);                /* kernels launched by th
  * TMA tile pass (one GPU), generic tile pass, row (z) pass with bulk copies, generic z pass, TMA tile pass with several
  * destinations (slab transpose), paint with the brick walk, readout with the brick walk, P(k) accumulated inside the forward
  * x-pass (unused: the row-streaming P(k) kernel is counted here), staged slab transposes, paint through shared-memory tiles,
- * readout through shared-memory tiles.  Returns the number of counters the library keeps. */
+ * readout through shared-memory tiles, the three force components gathered in one pass (cic_readout3_kernel).  Returns the number
+ * of counters the library keeps. */
 int fpm_path_counts(uint64_t *out, int n);
 /* bytes this rank moved to / from its peers over NVLink so far, counted where the transfers are issued: out4 = { slab-transpose
  * pushes by the copy engines, halo planes, migrating particles, rows the transposing FFT pass stored straight into peers } */

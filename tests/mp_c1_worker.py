@@ -72,6 +72,8 @@ def main():
             assert used["staged_transpose"] == 0, used
         else:
             assert used["staged_transpose"] >= 4 * len(steps), used
+            # staged transposes are pipelined, and with room for three canvases the three components are gathered in one pass
+            assert used["readout3"] == len(steps), used
         print("MP_C1_OK ranks=%d max position error vs one GPU %.3g Mpc/h, P(k) %.3g, paths %s, np per rank %s" % (
             world, err, worst, used, [len(o[0]) for o in out]))
     dist.barrier()

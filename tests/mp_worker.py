@@ -127,7 +127,15 @@ def main():
     os.environ.setdefault("FASTPM_B200_MIGRATE_FRAC", "1.0")
     g = Solver(nc=16, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=3.0)
     g.setup_lpt(fx["delta_k"], 0.1)
+    cnt = (C.c_uint64 * 16)()
+    lib.fpm_path_counts.argtypes = [C.c_void_p, C.c_int]
+    lib.fpm_path_counts(cnt, 16)
+    r3_before = cnt[11]                                      # "readout3" (tests/test_gpu_c1.py: PATHS)
     g.evolve(fx["steps"])
+    lib.fpm_path_counts(cnt, 16)
+    # staged + pipelined transposes with room for three canvases: one gather for the three force components per force evaluation
+    if not (os.environ.get("FASTPM_B200_NO_STAGE") or os.environ.get("FASTPM_B200_NO_PIPELINE") or os.environ.get("FASTPM_B200_FUSED_READOUT") == "0"):
+        assert cnt[11] - r3_before == len(fx["steps"]), (cnt[11] - r3_before, len(fx["steps"]))
     ids, x, v = g.get_column("id"), g.get_column("x"), g.get_column("v")
     out = [None] * world
     dist.all_gather_object(out, (ids, x, v))

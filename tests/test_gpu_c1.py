@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PATHS = ["fft_tma", "fft_tile_generic", "fft_zrow", "fft_z_generic", "fft_tma_multi", "paint_bricks", "readout_bricks", "pk_rows",
-         "staged_transpose", "paint_tiles", "readout_tiles"]
+         "staged_transpose", "paint_tiles", "readout_tiles", "readout3"]
 
 
 def path_counts(lib):
