@@ -157,6 +157,46 @@ template <int R> __device__ __forceinline__ constexpr int bitrev(int q)
     return r;
 }
 
+// ---- radix 24 = 3 x 8 (mesh sizes 3 * 2^k: N = 1536 = 24 * 8 * 8, rows of N/2 = 768 = 24 * 8 * 4)
+// One radix-3 DIF step over the three thirds of the array, twiddled by w24^(j r), then a radix-8 transform of each third:
+// X[3 p + r] ends up in v[8 r + bitrev8(p)].
+__device__ __forceinline__ float2 w24(int idx)          // exp(-2 pi i idx / 24), idx = 0 .. 14
+{
+    constexpr float c[15] = { 1.0f, 0.96592582628906829f, 0.86602540378443865f, 0.70710678118654752f, 0.5f, 0.25881904510252076f, 0.0f,
+                              -0.25881904510252076f, -0.5f, -0.70710678118654752f, -0.86602540378443865f, -0.96592582628906829f, -1.0f,
+                              -0.96592582628906829f, -0.86602540378443865f };
+    constexpr float s[15] = { 0.0f, -0.25881904510252076f, -0.5f, -0.70710678118654752f, -0.86602540378443865f, -0.96592582628906829f, -1.0f,
+                              -0.96592582628906829f, -0.86602540378443865f, -0.70710678118654752f, -0.5f, -0.25881904510252076f, 0.0f,
+                              0.25881904510252076f, 0.5f };
+    return make_float2(c[idx], s[idx]);
+}
+template <> __device__ __forceinline__ void fft_reg<24>(float2 (&v)[24])
+{
+    constexpr float S3 = 0.86602540378443865f;           // sin(2 pi / 3)
+    #pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float2 a = v[j], b = v[j + 8], c = v[j + 16];
+        const float2 sum = c2add(b, c), dif = c2sub(b, c);
+        v[j] = c2add(a, sum);
+        const float2 m = make_float2(a.x - 0.5f * sum.x, a.y - 0.5f * sum.y);
+        const float2 r = make_float2(S3 * dif.y, -S3 * dif.x);            // -i sin(2 pi / 3) (b - c)
+        const float2 y1 = c2add(m, r), y2 = c2sub(m, r);                  // a + w3 b + w3^2 c,  a + w3^2 b + w3 c
+        v[j + 8] = j == 0 ? y1 : c2mul(y1, w24(j));
+        v[j + 16] = j == 0 ? y2 : c2mul(y2, w24(2 * j));
+    }
+    #pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float2 w[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = v[8 * r + j];
+        fft_reg<8>(w);
+        #pragma unroll
+        for (int j = 0; j < 8; j++) v[8 * r + j] = w[j];
+    }
+}
+// where fft_reg<R> leaves output q
+template <int R> __device__ __forceinline__ constexpr int fft_pos(int q) { return R == 24 ? 8 * (q % 3) + bitrev<8>(q / 3) : bitrev<R>(q); }
+
 // ------------------------------------------------------------------ the kernel
 
 template <int R1, int R2, int R3> struct TmaCfg {
@@ -217,7 +257,7 @@ struct Fft3 {
         #pragma unroll
         for (int q = 1; q < R1; q++) {
             const float2 w = TWS ? tw1[q * t] : __ldg(tw1 + q * t);
-            v[bitrev<R1>(q)] = c2mul(v[bitrev<R1>(q)], w);
+            v[fft_pos<R1>(q)] = c2mul(v[fft_pos<R1>(q)], w);
         }
 
         // ---- exchange 1 (B), then stage 2
@@ -228,7 +268,7 @@ struct Fft3 {
             if (half == 0) after_first_barrier();
             #pragma unroll
             for (int q = 0; q < R1; q++) {
-                const float2 y = v[bitrev<R1>(q)];
+                const float2 y = v[fft_pos<R1>(q)];
                 Bx1w[q * M1 * K] = half ? y.y : y.x;
             }
             __syncthreads();

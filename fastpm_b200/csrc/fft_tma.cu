@@ -11,7 +11,8 @@
 //     frequency order (k = q1 + R1*q2 + R1*R2*q3), optionally to a peer GPU's buffer (slab transpose).
 // The gravity kernel (Green's function x i k_d, mesh.cuh) is applied as the tile leaves buffer A in the
 // first pass of an inverse transform, exactly as in the generic path (fft.cu), which remains the
-// fallback for mesh sizes with factors 3 or 5 and the cross-check for this one.
+// fallback for the other mesh sizes with factors 3 or 5 and the cross-check for this one.  N = 1536 = 24 * 8 * 8 (the 3x mesh of
+// an nc = 512 run, BASELINE configs[3]) has a radix-24 first stage (fft_reg.cuh).
 #include "common.cuh"
 #include "fft_core.h"
 #include "mesh.cuh"
@@ -35,7 +36,7 @@ __device__ __forceinline__ float2 *pick_dst(const TmaPassArgs &a, int d)
 // MULTI: the output rows are spread over several destination buffers (slab transpose on several GPUs).  A separate
 // instantiation: the extra addressing of that path costs the one-GPU kernel registers and 30 % of its speed otherwise.
 template <int R1, int R2, int R3, int K, bool MULTI>
-__global__ void __launch_bounds__(TmaCfg<R1, R2, R3>::T * K, (TmaCfg<R1, R2, R3>::T * K <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(TmaCfg<R1, R2, R3>::T * K, (TmaCfg<R1, R2, R3>::T * K <= 512 && R1 <= 16) ? 2 : 1)
 fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
 {
     using C = TmaCfg<R1, R2, R3>;
@@ -251,7 +252,7 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
         attr = true;
     }
     const int ntiles = a.nouter * a.ntile_k;
-    const int per_sm = (C::T * K <= 512) ? 2 : 1;
+    const int per_sm = (C::T * K <= 512 && R1 <= 16) ? 2 : 1;        // 24 elements per thread: one 512-thread CTA per SM, 128 registers
     const int grid = ntiles < nsm * per_sm ? ntiles : nsm * per_sm;
     if (grid <= 0) return 0;
     fpm_path_counter[a.rows_per_rank == C::N ? FPM_PATH_FFT_TMA : FPM_PATH_FFT_TMA_MULTI]++;
@@ -263,7 +264,7 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
     return 0;
 }
 
-int fpm_fft_tma_supported(int n) { return n == 512 || n == 1024 || n == 2048 || n == 4096; }
+int fpm_fft_tma_supported(int n) { return n == 512 || n == 1024 || n == 1536 || n == 2048 || n == 4096; }
 // tile width (complex per row): wide tiles give 128 B row segments with one 1024-thread CTA per SM, narrow ones two
 // 512-thread CTAs per SM whose phases (shared-memory exchange, arithmetic, stores) interleave
 static int g_narrow = -1;
@@ -271,6 +272,7 @@ int fpm_fft_tma_tile_k(int n)
 {
     if (g_narrow < 0) { const char *e = getenv("FASTPM_B200_FFT_NARROW"); g_narrow = e ? atoi(e) : 0; }
     if (n == 4096) return 4;
+    if (n == 1536) return 8;          // 24 * 8 * 8: 24 elements per thread, 64 threads per column
     if (n == 2048) return g_narrow ? 4 : 8;
     if (n == 1024) return g_narrow ? 8 : 16;
     return 16;
@@ -310,6 +312,7 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     a.chunk = chunk > 0 ? chunk : 1;
     switch (n) {
         case 512: return launch_cfg<8, 8, 8, 16>(tmap, a, nsm, st);
+        case 1536: return launch_cfg<24, 8, 8, 8>(tmap, a, nsm, st);
         case 1024: return K == 8 ? launch_cfg<16, 16, 4, 8>(tmap, a, nsm, st) : launch_cfg<16, 16, 4, 16>(tmap, a, nsm, st);
         case 2048: return K == 4 ? launch_cfg<16, 16, 8, 4>(tmap, a, nsm, st) : launch_cfg<16, 16, 8, 8>(tmap, a, nsm, st);
         case 4096: return launch_cfg<16, 16, 16, 4>(tmap, a, nsm, st);

@@ -406,10 +406,12 @@ def test_tma_fft_matches_generic_and_oracle(dev, nmesh):
     assert np.abs(back - field).max() < 1e-5 * np.abs(field).max()
 
 
-def test_fft_2048_round_trip_and_generic_planes(dev):
-    """BASELINE.json's full mesh size (2048^3, 34 GB per buffer): size-independent properties instead of the oracle --
-    r2c -> c2r is the identity, Parseval's sum, and the TMA/register passes agree with the generic ones on sampled planes."""
-    n, L = 2048, 1024.0
+@pytest.mark.parametrize("n", [2048, 1536])
+def test_fft_2048_round_trip_and_generic_planes(dev, n):
+    """BASELINE.json's full mesh size (2048^3, 34 GB per buffer) and the 1536^3 mesh of configs[3] (radix-24 first stage):
+    size-independent properties instead of the oracle -- r2c -> c2r is the identity, Parseval's sum, and the TMA/register passes
+    agree with the generic ones on sampled planes, without and with the fused gravity kernel."""
+    L = 1024.0
     m = dev.Mesh(n, L)
     lib = m.lib
     import ctypes as C
@@ -445,6 +447,18 @@ def test_fft_2048_round_trip_and_generic_planes(dev):
     for p in sample:
         back = work.download(np.float32, plane, p * plane * 4).reshape(n, m.pitch_r)[:, :n]
         assert np.abs(back - orig[p]).max() < 2e-5 * np.abs(orig[p]).max(), p
+    # the inverse with the fused gravity kernel (Green's function x i k_d, every direction): register passes against generic ones
+    _lib.check(lib.fpm_r2c_ws(m.h, real.ptr, work.ptr, ck.ptr, 1.0 / float(n) ** 3), "r2c")
+    for d in range(3):
+        kern = m.transfer_for_kernel("1_4", 0, d)
+        _lib.check(lib.fpm_c2r_ws(m.h, ck.ptr, work.ptr, work.ptr, C.byref(kern)), "c2r kernel")
+        fast = {p: work.download(np.float32, plane, p * plane * 4).reshape(n, m.pitch_r)[:, :n].copy() for p in sample}
+        lib.fpm_fft_set_generic(1)
+        _lib.check(lib.fpm_c2r_ws(m.h, ck.ptr, work.ptr, work.ptr, C.byref(kern)), "c2r kernel generic")
+        lib.fpm_fft_set_generic(0)
+        for p in sample:
+            g = work.download(np.float32, plane, p * plane * 4).reshape(n, m.pitch_r)[:, :n]
+            assert np.abs(g - fast[p]).max() < 1e-5 * np.abs(g).max(), (d, p)
     for b in (real, work, ck):
         b.free()
     m.close()
