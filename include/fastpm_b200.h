@@ -44,6 +44,13 @@ void *fpm_host_alloc_pinned(size_t bytes);
 void fpm_host_free_pinned(void *ptr);
 int fpm_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int fpm_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+/* the same on a second stream (pinned host memory), for callers that overlap the PCIe traffic of a run with its first / last force
+ * evaluation: a copy is ordered after everything the library has queued when it is issued and nothing queued later waits for it
+ * until fpm_copy_fence() (device-side wait of the library stream); fpm_copy_wait() blocks the host until the copies are done */
+int fpm_memcpy_h2d_async(void *dst_dev, const void *src_host, size_t bytes);
+int fpm_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes);
+int fpm_copy_fence(void);
+int fpm_copy_wait(void);
 int fpm_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes);    /* pm_assign, pmapi.c:24 */
 int fpm_memset(void *dst_dev, int value, size_t bytes);                  /* pm_clear, pmapi.c:30 */
 int fpm_sync(void);
