@@ -268,7 +268,7 @@ def run_ours(args):
 
     spectra = []
     # state of the end-to-end arm (below): which force evaluation is running, whether the uploads have been fenced
-    e2e = dict(on=False, nforce=0, nforce_total=-1, fenced=False)
+    e2e = dict(on=False, nforce=0, nforce_total=-1)
 
     def on_force_after(solver_ptr, event_ptr, userdata):      # the reference's write_powerspectrum handler, src/fastpm.c:1711-1776
         ev = C.cast(event_ptr, C.POINTER(ForceEvent)).contents
@@ -281,25 +281,7 @@ def run_ours(args):
                 _lib.check(lib.fpm_memcpy_d2h_async(host[c][0], g.column_ptr(c), Np * itemsize[c]), "result d2h (async)")
         return 0
 
-    class _Transition(C.Structure):                           # api/fastpm/timemachine.h:19-35
-        _fields_ = [("states", C.c_void_p), ("istart", C.c_int), ("iend", C.c_int), ("start", C.c_void_p), ("end", C.c_void_p),
-                    ("action", C.c_int)]
-
-    class _TransitionEvent(C.Structure):
-        _fields_ = [("type", C.c_char * 32), ("stage", C.c_int), ("transition", C.POINTER(_Transition))]
-
-    def on_transition_before(solver_ptr, event_ptr, userdata):
-        # uploads still in flight on the copy stream (v, id, dx1, dx2) are needed by the first transition that is not a force
-        # evaluation (FASTPM_ACTION_FORCE = 0): the library stream waits for them there, on the device
-        if e2e["on"] and not e2e["fenced"]:
-            ev = C.cast(event_ptr, C.POINTER(_TransitionEvent)).contents
-            if ev.transition.contents.action != 0:
-                _lib.check(lib.fpm_copy_fence(), "copy fence")
-                e2e["fenced"] = True
-        return 0
-
     g.add_handler("FORCE", 1, on_force_after)
-    g.add_handler("TRANSITION", 0, on_transition_before)
 
     if W >= 1:                                          # warm-up: the first max(W,2) entries of the same table
         g.evolve(ts[:max(W, 2)])
@@ -341,20 +323,21 @@ def run_ours(args):
 
     # ---- end-to-end run: host buffers in, host buffers out.  The PCIe traffic overlaps the first and the last force evaluation
     # (FASTPM_B200_BENCH_E2E_OVERLAP=0: everything up, run, everything down): x goes up first, the other columns follow on the
-    # copy stream while the first force evaluation -- which reads only x -- runs (on_transition_before); x and id go down during
+    # copy stream while the first force evaluation -- which reads only x -- runs (fpm_copy_fence_before_update); x and id go down during
     # the inverse transforms and the gather of the last one (on_force_after); v follows when the run is over.
     overlap = os.environ.get("FASTPM_B200_BENCH_E2E_OVERLAP", "1") != "0"
     _lib.check(lib.fpm_sync())
     t0 = time.perf_counter()
     if overlap:
-        e2e.update(on=True, nforce=0, fenced=False)
+        e2e.update(on=True, nforce=0)
         _lib.check(lib.fpm_memcpy_h2d(g.column_ptr("x"), host["x"][0], Np * itemsize["x"]), "restore IC")
         for c in cols_in:
             if c != "x":
                 _lib.check(lib.fpm_memcpy_h2d_async(g.column_ptr(c), host[c][0], Np * itemsize[c]), "restore IC (async)")
+        _lib.check(lib.fpm_copy_fence_before_update(), "fence")      # the first kick waits (on the device) for these uploads
         g.set_meta(meta0["a_x"], meta0["a_v"], meta0["M0"])
         g.evolve(ts)
-        assert e2e["fenced"] and e2e["nforce"] == e2e["nforce_total"]
+        assert e2e["nforce"] == e2e["nforce_total"]
         e2e["on"] = False
         _lib.check(lib.fpm_memcpy_d2h(host["v"][0], g.column_ptr("v"), Np * itemsize["v"]), "result d2h")
         _lib.check(lib.fpm_copy_wait(), "copy wait")

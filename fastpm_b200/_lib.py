@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfastpm_b200.so")
 ABI_SYMBOLS = [
     "fpm_last_error", "fpm_version", "fpm_device_init", "fpm_device_count", "fpm_device_mem_info", "fpm_debug_state",
     "fpm_malloc", "fpm_free", "fpm_host_alloc_pinned", "fpm_host_free_pinned",
-    "fpm_memcpy_h2d", "fpm_memcpy_d2h", "fpm_memcpy_h2d_async", "fpm_memcpy_d2h_async", "fpm_copy_fence", "fpm_copy_wait", "fpm_memcpy_d2d", "fpm_memset", "fpm_sync",
+    "fpm_memcpy_h2d", "fpm_memcpy_d2h", "fpm_memcpy_h2d_async", "fpm_memcpy_d2h_async", "fpm_copy_fence", "fpm_copy_wait", "fpm_copy_fence_before_update", "fpm_memcpy_d2d", "fpm_memset", "fpm_sync",
     "fpm_timer_create", "fpm_timer_start", "fpm_timer_stop", "fpm_timer_elapsed_ms", "fpm_timer_destroy",
     "fpm_kernel_launch_count", "fpm_path_counts", "fpm_comm_byte_counts", "fpm_prof_enable", "fpm_prof_reset", "fpm_prof_get", "fpm_prof_get_launches",
     "fpm_mesh_create", "fpm_mesh_destroy", "fpm_mesh_info", "fpm_mesh_ktables_host",

@@ -251,6 +251,16 @@ int fpm_copy_fence(void)
     FPM_CUDA_OK(cudaStreamWaitEvent(g_stream, g_copy_ev, 0));
     return 0;
 }
+// the same fence, applied in front of the next kick / drift / fused particle update the library launches (uploads of v, dx1, dx2
+// that may still travel while a force evaluation -- which reads only the positions -- runs)
+static int g_fence_before_update = 0;
+int fpm_copy_fence_before_update(void) { g_fence_before_update = 1; return 0; }
+static int fence_if_requested()
+{
+    if (!g_fence_before_update) return 0;
+    g_fence_before_update = 0;
+    return fpm_copy_fence();
+}
 // the host waits for them
 int fpm_copy_wait(void)
 {
@@ -708,6 +718,7 @@ int fpm_kick(float *v_out, const float *v_in, const float *acc, const float *dx1
 {
     const int cola = (forcemode == 2);
     if (cola && (!dx1 || !dx2)) { fpm_set_error("COLA kick needs the dx1 and dx2 columns (solver.c:84-88)"); return -1; }
+    if (fence_if_requested()) return -1;
     return fpm_kick_launch(v_out, v_in, acc, dx1, dx2, dda, q1, q2, Dv1, Dv2, cola, np, g_stream);
 }
 
@@ -715,6 +726,7 @@ int fpm_drift(double *x_out, const double *x_in, const float *v, const float *dx
               int forcemode, double dyyy, double da1, double da2, double Dv1, double Dv2)
 {
     if (forcemode >= 2 && (!dx1 || (forcemode != 4 && !dx2))) { fpm_set_error("drift mode %d needs the dx1/dx2 columns", forcemode); return -1; }
+    if (fence_if_requested()) return -1;
     return fpm_drift_launch(x_out, x_in, v, dx1, dx2, dyyy, da1, da2, Dv1, Dv2, forcemode, np, g_stream);
 }
 
@@ -727,7 +739,7 @@ int fpm_pgd_shift(double *x, const float *pgdc, int64_t np, double dyyy, double 
 
 int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, const float *dx2, int64_t np, int nops, const double *ops)
 {
-    if (ensure_init()) return -1;
+    if (ensure_init() || fence_if_requested()) return -1;
     return fpm_fused_update_launch(x, v, acc, dx1, dx2, np, nops, ops, g_stream);
 }
 

@@ -51,6 +51,9 @@ int fpm_memcpy_h2d_async(void *dst_dev, const void *src_host, size_t bytes);
 int fpm_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes);
 int fpm_copy_fence(void);
 int fpm_copy_wait(void);
+/* the fence, placed in front of the next kick / drift / fused particle update the library launches: uploads of v, dx1, dx2, id may
+ * travel while a force evaluation (which reads the positions only) runs; no handler, hence no flush of the queued updates, is needed */
+int fpm_copy_fence_before_update(void);
 int fpm_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes);    /* pm_assign, pmapi.c:24 */
 int fpm_memset(void *dst_dev, int value, size_t bytes);                  /* pm_clear, pmapi.c:30 */
 int fpm_sync(void);
