@@ -640,19 +640,33 @@ int fpm_fill_gaussian_gadget(const fpm_mesh *m, float *cplx, int seed)
 
 int fpm_fill_whitenoise(const fpm_mesh *m, float *real, uint64_t seed) { LAZY1(real); return fpm_whitenoise_launch(m, real, seed, g_stream); }
 
+// the device block the shell sums land in: kept between calls (cudaMalloc / cudaFree synchronise the whole device, copy streams included,
+// and P(k) is measured in every step)
+static double *pk_sums_buffer(int nbins)
+{
+    static double *d_buf = NULL;
+    static int cap = 0;
+    if (nbins > cap) {
+        if (d_buf) cudaFree(d_buf);
+        d_buf = NULL; cap = 0;
+        if (cudaMalloc(&d_buf, sizeof(double) * (3 * (size_t) nbins + 1)) != cudaSuccess) { fpm_set_error("P(k) sums: out of device memory"); cudaGetLastError(); return NULL; }
+        cap = nbins;
+    }
+    return d_buf;
+}
+
 int fpm_powerspectrum_sums(const fpm_mesh *m, const float *cplx, int decic, double *sums_host)
 {
     if ((const char *) cplx == g_lazy_buf && m == g_lazy_mesh && !decic) decic = 1;      // pending deconvolution folded into the read
     else LAZY1(cplx);
     const int nbins = m->geom.n / 2;
-    double *d_out = NULL;
-    FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
+    double *d_out = pk_sums_buffer(nbins);
+    if (!d_out) return -1;
     int rc = fpm_powerspectrum_launch(m, cplx, decic, d_out, g_stream);
     if (!rc) {
         FPM_CUDA_OK(cudaMemcpyAsync(sums_host, d_out, sizeof(double) * (3 * nbins + 1), cudaMemcpyDeviceToHost, g_stream));
         FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(d_out);
     return rc;
 }
 
@@ -662,14 +676,13 @@ int fpm_cross_powerspectrum_sums(const fpm_mesh *m, const float *cplx1, const fl
     if (cplx1 == cplx2) return fpm_powerspectrum_sums(m, cplx1, 0, sums_host);
     LAZY1(cplx1); LAZY1(cplx2);
     const int nbins = m->geom.n / 2;
-    double *d_out = NULL;
-    FPM_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (3 * nbins + 1)));
+    double *d_out = pk_sums_buffer(nbins);
+    if (!d_out) return -1;
     int rc = fpm_powerspectrum_launch(m, cplx1, 0, d_out, g_stream, cplx2);
     if (!rc) {
         FPM_CUDA_OK(cudaMemcpyAsync(sums_host, d_out, sizeof(double) * (3 * nbins + 1), cudaMemcpyDeviceToHost, g_stream));
         FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
     }
-    cudaFree(d_out);
     return rc;
 }
 
