@@ -267,6 +267,10 @@ void fpm_comm_release_migration(void)
 
 typedef struct { void *ptr; int elsize; } MigCol;
 
+/* the largest number of exchange rounds any fastpm_store_decompose of this process needed (diagnostics, tests) */
+static int g_migrate_rounds_max = 0;
+int fastpm_b200_migrate_rounds_max(void) { return g_migrate_rounds_max; }
+
 /* set by fastpm_decompose (host/solver.c) around its call: the force evaluation that follows recomputes ACC, so the column need not
  * travel.  Any other caller of the public fastpm_store_decompose gets every column moved, like the reference (store.c:302-323). */
 int fpm_decompose_skip_acc = 0;
@@ -305,6 +309,8 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
         if (e) frac = atof(e);
         mig_cap = (int) (frac * p->np_upper);
         if (mig_cap < 4096) mig_cap = 4096;
+        const char *ec = getenv("FASTPM_B200_MIGRATE_CAP");            /* tests: a buffer of a few particles forces several rounds */
+        if (ec && atoi(ec) > 0) mig_cap = atoi(ec);
         if ((size_t) mig_cap > p->np_upper) mig_cap = (int) p->np_upper;
         /* sized for every allocated column (the solver's own calls leave ACC behind, other callers move it too) */
         size_t row_all = 0;
@@ -359,6 +365,7 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
         FPM_MUST(fpm_xbarrier());                          /* every rank has pulled: pack buffers may be reused */
         p->np = (size_t) at;
         if (!flags[1]) break;                              /* nobody had more leavers than a pack buffer holds */
+        if (round + 1 > g_migrate_rounds_max) g_migrate_rounds_max = round + 1;
         if (round > 4096) fastpm_raise(-1, "fastpm_b200: particle migration does not converge\n");
     }
     return 0;

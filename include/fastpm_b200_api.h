@@ -526,6 +526,8 @@ void fastpm_b200_sync_state(void);
 /* 1 when the host-scalar collectives of a multi-rank run go through the shared-memory segment of host/shmcoll.c (all ranks on one
  * host), 0 when they go through the launcher's callbacks (FASTPM_B200_HOST_COLL=callbacks, several hosts) or there is one rank */
 int fastpm_b200_host_collectives_shared(void);
+/* the largest number of exchange rounds a fastpm_store_decompose of this process has needed so far (1 unless a pack buffer overflowed) */
+int fastpm_b200_migrate_rounds_max(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count);
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count);

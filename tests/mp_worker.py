@@ -149,7 +149,8 @@ def main():
         err = np.minimum(d, L - d).max()
         assert err < 1e-4, "positions differ from the reference fixture by %g Mpc/h" % err
         assert np.abs(v - fx["v1"][ref_order]).max() < 1e-4 * np.abs(fx["v1"]).max()
-        print("MP_GPU_OK ranks=%d max position error %.3g Mpc/h, np per rank %s" % (world, err, [len(o[0]) for o in out]))
+        print("MP_GPU_OK ranks=%d max position error %.3g Mpc/h, np per rank %s, migration rounds <= %d" % (
+            world, err, [len(o[0]) for o in out], lib.fastpm_b200_migrate_rounds_max()))
     g.close()
     dist.barrier()
     if os.environ.get("MP_EXTRAS"):

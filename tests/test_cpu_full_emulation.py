@@ -69,6 +69,10 @@ def runs(emul_lib, tmp_path_factory):
     ranks4 = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
                                "--master-port", "29688", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"],
                               cwd=ROOT, env=dict(os.environ, MP_EXTRAS="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # two ranks whose migration buffers hold 16 particles per destination: every decompose needs several exchange rounds
+    ranks2 = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                               "--master-port", "29687", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"],
+                              cwd=ROOT, env=dict(os.environ, FASTPM_B200_MIGRATE_CAP="16"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     out = {}
     for g, p in procs.items():
         o, _ = p.communicate(timeout=1500)
@@ -76,6 +80,8 @@ def runs(emul_lib, tmp_path_factory):
     bo, be = bench.communicate(timeout=1500)
     out["bench"] = (bench.returncode, bo, be)
     ro, _ = ranks4.communicate(timeout=1500)
+    r2o, _ = ranks2.communicate(timeout=1500)
+    out["ranks2_rounds"] = (ranks2.returncode, r2o)
     out["ranks4"] = (ranks4.returncode, ro, sorted(f for f in set(os.listdir("/dev/shm")) - shm_before if f.startswith("fpm_emul_")))
     return out
 
@@ -114,3 +120,13 @@ def test_four_rank_slab_run_on_the_emulated_library(runs):
     assert "MP_EXTRAS_OK ranks=4" in stdout, stdout[-3000:]
     assert "MP_WINDOWS_OK ranks=4" in stdout, stdout[-3000:]          # quadratic / Lanczos windows: halo planes on both sides of a slab
     assert not leftover                                                   # the shared-memory arenas were unlinked
+
+
+def test_migration_in_rounds_on_the_emulated_library(runs):
+    """More leavers for one slab than a pack buffer holds (store.c:486-657 moves any number): the exchange runs in rounds,
+    every rank the same number of them.  Two emulated ranks with 16-particle buffers reproduce the reference fixture."""
+    import re
+    rc, stdout = runs["ranks2_rounds"]
+    m = re.search(r"MP_GPU_OK ranks=2 .* migration rounds <= (\d+)", stdout)
+    assert m, stdout[-3000:]
+    assert int(m.group(1)) > 1, stdout[-3000:]
