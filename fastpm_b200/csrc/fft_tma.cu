@@ -264,7 +264,7 @@ static int launch_cfg(const CUtensorMap &tmap, const TmaPassArgs &a, int nsm, cu
     return 0;
 }
 
-int fpm_fft_tma_supported(int n) { return n == 512 || n == 1024 || n == 1536 || n == 2048 || n == 4096; }
+int fpm_fft_tma_supported(int n) { return n == 512 || n == 768 || n == 1024 || n == 1536 || n == 2048 || n == 4096; }
 // tile width (complex per row): wide tiles give 128 B row segments with one 1024-thread CTA per SM, narrow ones two
 // 512-thread CTAs per SM whose phases (shared-memory exchange, arithmetic, stores) interleave
 static int g_narrow = -1;
@@ -312,6 +312,7 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     a.chunk = chunk > 0 ? chunk : 1;
     switch (n) {
         case 512: return launch_cfg<8, 8, 8, 16>(tmap, a, nsm, st);
+        case 768: return launch_cfg<24, 8, 4, 16>(tmap, a, nsm, st);
         case 1536: return launch_cfg<24, 8, 8, 8>(tmap, a, nsm, st);
         case 1024: return K == 8 ? launch_cfg<16, 16, 4, 8>(tmap, a, nsm, st) : launch_cfg<16, 16, 4, 16>(tmap, a, nsm, st);
         case 2048: return K == 4 ? launch_cfg<16, 16, 8, 4>(tmap, a, nsm, st) : launch_cfg<16, 16, 8, 8>(tmap, a, nsm, st);

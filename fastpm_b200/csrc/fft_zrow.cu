@@ -189,7 +189,7 @@ static int launch_zrow(const ZRowArgs &a, int forward, cudaStream_t st)
 
 int fpm_fft_zrow_supported(int n, size_t nrows)
 {
-    return (n == 512 || n == 1024 || n == 1536 || n == 2048 || n == 4096) && (nrows % 8 == 0) && nrows / 8 < ((size_t) 1 << 31);
+    return (n == 512 || n == 768 || n == 1024 || n == 1536 || n == 2048 || n == 4096) && (nrows % 8 == 0) && nrows / 8 < ((size_t) 1 << 31);
 }
 
 int fpm_fft_zrow_pass(int n, const float *src, float *dst, size_t nrows, int pitch_c, float scale,
@@ -202,6 +202,7 @@ int fpm_fft_zrow_pass(int n, const float *src, float *dst, size_t nrows, int pit
     if (single < 0) { const char *e = getenv("FASTPM_B200_ZROW_SINGLE"); single = e ? atoi(e) : 0; }
     switch (n) {
         case 512: return launch_zrow<8, 8, 4, true, 3>(a, forward, st);
+        case 768: return launch_zrow<24, 4, 4, true, 4>(a, forward, st);            // rows of 384 = 24 * 4 * 4 complex
         case 1024: return launch_zrow<8, 8, 8, true, 2>(a, forward, st);
         case 1536: return launch_zrow<24, 8, 4, true, 2>(a, forward, st);          // rows of 768 = 24 * 8 * 4 complex
         case 2048: return single ? launch_zrow<16, 16, 4, false, 2>(a, forward, st) : launch_zrow<16, 16, 4, true, 1>(a, forward, st);

@@ -132,6 +132,7 @@ int main(int argc, char **argv)
     const bool full = argc > 1 && !strcmp(argv[1], "full");      // ~2.5 min; the default subset (~40 s) is what pytest runs
     int bad = 0;
     bad += run<8, 8, 8, 16>(2, 3, 7);
+    bad += run<24, 8, 4, 16>(2, 3, full ? 7 : 13);    // N = 768
     bad += run<16, 16, 4, 16>(2, 3, full ? 7 : 12);
     bad += run<24, 8, 8, 8>(2, 3, full ? 7 : 13);     // N = 1536: radix-24 first stage; plain, one force direction, 2-rank transpose
     bad += run<16, 16, 8, 8>(1, 3, full ? 7 : 9);

@@ -51,6 +51,7 @@ int main()
 {
     int bad = 0;
     bad += run<8, 8, 4, true>(512, 40, 2);           // 5 tiles over 2 persistent CTAs
+    bad += run<24, 4, 4, true>(768, 24, 2);          // rows of 384 = 24 * 4 * 4 complex
     bad += run<8, 8, 8, true>(1024, 24, 2);
     bad += run<24, 8, 4, true>(1536, 24, 2);         // rows of 768 = 24 * 8 * 4 complex: radix-24 first stage
     bad += run<16, 16, 4, true>(2048, 24, 2);

@@ -361,7 +361,7 @@ def test_wrap_and_summary(dev):
     assert lib.fpm_wrap_check() != 0
 
 
-@pytest.mark.parametrize("nmesh", [512, 1024])
+@pytest.mark.parametrize("nmesh", [512, 768, 1024])
 def test_tma_fft_matches_generic_and_oracle(dev, nmesh):
     """The TMA/register FFT passes (fft_tma.cu) against the generic shared-memory passes (fft.cu) and the oracle's CPU FFT."""
     import ctypes as C
