@@ -21,14 +21,28 @@ void fastpm_kernel_type_get_orders(FastPMKernelType type, int *potorder, int *gr
     *deconvolveorder = (type == FASTPM_KERNEL_EASTWOOD || type == FASTPM_KERNEL_GADGET) ? 2 : 0;
 }
 
-/* stand-alone version of the fused kernel: canvas = kernel(delta_k) for one field component */
+/* stand-alone version of the fused kernel: canvas = kernel(delta_k) for one field component (gravity.c:172-241) */
 void gravity_apply_kernel_transfer(FastPMKernelType type, PM *pm, FastPMFloat *delta_k, FastPMFloat *canvas, FastPMFieldDescr field)
 {
     fpm_transfer t;
+    if (field.attribute == COLUMN_DENSITY) {               /* fastpm_apply_multiply_transfer(pm, delta_k, canvas, 1.0) */
+        fastpm_apply_multiply_transfer(pm, delta_k, canvas, 1.0);
+        return;
+    }
+    if (field.attribute == COLUMN_TIDAL) {
+        /* potential, then the gradient along d1 and along d2: memb 0..5 = xx, yy, zz, xy, yz, zx (gravity.c:194-231) */
+        static const int D1[6] = { 0, 1, 2, 0, 1, 2 }, D2[6] = { 0, 1, 2, 1, 2, 0 };
+        if (field.memb < 0 || field.memb > 5) fastpm_raise(-1, "tidal component %d\n", (int) field.memb);
+        if (fpm_transfer_for_kernel((int) type, 0, D1[field.memb], &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
+        t.ngrad = 2;
+        t.graddir[1] = D2[field.memb];
+        FPM_MUST(fpm_apply_transfer(pm->mesh, delta_k, canvas, &t));
+        return;
+    }
     int attr;
     if (field.attribute == COLUMN_ACC) attr = 0;
     else if (field.attribute == COLUMN_POTENTIAL) attr = 1;
-    else { fastpm_raise(-1, "fastpm_b200: gravity attribute %d (density / tidal) is not implemented\n", (int) field.attribute); return; }
+    else { fastpm_raise(-1, "Unknown type for gravity attribute\n"); return; }
     if (fpm_transfer_for_kernel((int) type, attr, field.memb, &t) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
     FPM_MUST(fpm_apply_transfer(pm->mesh, delta_k, canvas, &t));
 }

@@ -148,7 +148,7 @@ int fpm_r2c(fpm_mesh *m, float *real, float *cplx, double scale);
 int fpm_r2c_ws(fpm_mesh *m, const float *real, float *work, float *cplx, double scale);
 
 /* 1: force the generic shared-memory FFT passes (any Nmesh = 2^a 3^b 5^c); 0 (default): the TMA + register passes for
- * Nmesh in {512, 1024, 2048, 4096}.  Used by the tests to cross-check one against the other. */
+ * Nmesh in {512, 768, 1024, 1536, 2048, 4096}.  Used by the tests to cross-check one against the other. */
 int fpm_fft_set_generic(int on);
 
 /* k-space kernel description: see FpmTransferSpec in csrc/mesh.cuh.  Fused into the first pass of c2r. */

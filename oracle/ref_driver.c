@@ -491,7 +491,8 @@ void ref_kernel_transfer(RefSession *s, int which, double a, const float *delta_
     PM *pm = pick_pm(s, which, a);
     FastPMFloat *dk = pm_alloc(pm), *canvas = pm_alloc(pm);
     memcpy(dk, delta_k_in, sizeof(FastPMFloat) * pm->allocsize);
-    FastPMFieldDescr f = { attr == 0 ? COLUMN_ACC : COLUMN_POTENTIAL, memb };
+    /* attr: 0 acceleration, 1 potential, 2 density, 3 tidal (memb 0..5) */
+    FastPMFieldDescr f = { attr == 0 ? COLUMN_ACC : (attr == 1 ? COLUMN_POTENTIAL : (attr == 2 ? COLUMN_DENSITY : COLUMN_TIDAL)), memb };
     gravity_apply_kernel_transfer(s->solver->config->KERNEL_TYPE, pm, dk, canvas, f);
     memcpy(out, canvas, sizeof(FastPMFloat) * pm->allocsize);
     pm_free(pm, canvas); pm_free(pm, dk);

@@ -204,6 +204,17 @@ def test_gravity_kernel_bit_exact(dev, ref_mod, kernel_type):
         m.apply_transfer(src, dst, m.transfer_for_kernel(kernel_type, attr, memb))
         got = m.download_complex(dst)
         assert np.array_equal(got.view(np.float32), want.view(np.float32)), (kernel_type, attr, memb)
+    # the tidal components (gravity.c:194-231): potential, gradient along d1, gradient along d2 -- the same spec with two gradients
+    # (what host/gravity.c: gravity_apply_kernel_transfer builds for COLUMN_TIDAL)
+    D1, D2 = (0, 1, 2, 0, 1, 2), (0, 1, 2, 1, 2, 0)
+    for memb in range(6):
+        want = s.complex_view(s.kernel_transfer(dk, memb, attr=3))
+        t = m.transfer_for_kernel(kernel_type, 0, D1[memb])
+        t.ngrad = 2
+        t.graddir[1] = D2[memb]
+        m.apply_transfer(src, dst, t)
+        got = m.download_complex(dst)
+        assert np.array_equal(got.view(np.float32), want.view(np.float32)), (kernel_type, "tidal", memb)
     assert np.all(np.isfinite(kt["k_finite"]))
     s.close()
 
