@@ -226,6 +226,7 @@ static int bf_open(BfBlock *b, const char *filebase, const char *blockname)
         ptrdiff_t sz;
         if (fscanf(f, " %X : %td : %u : %u", &fid, &sz, &cks, &folded) != 4 || (int) fid >= b->nfile) { fclose(f); bf_free(b); return -1; }
         b->fsize[fid] = (size_t) sz;
+        b->fchecksum[fid] = (int64_t) cks;          /* of use when the block grows (append): a reader never looks at it */
     }
     fclose(f);
     for (int i = 0; i < b->nfile; i++) b->foffset[i + 1] = b->foffset[i] + b->fsize[i];
@@ -255,6 +256,33 @@ static int bf_open(BfBlock *b, const char *filebase, const char *blockname)
     }
     b->attrs_dirty = 0;
     return 0;
+}
+
+/* big_block_mpi_grow_simple (bigfile-mpi.c:213-272, bigfile.c:411-447): nfile_grow more files holding size_grow more items, spread
+ * evenly; the files that exist keep their sizes and checksums.  fchecksum is "this rank's share" (summed at close): the stored
+ * checksums stay on rank 0 only. */
+static int bf_grow(BfBlock *b, int nfile_grow, size_t size_grow, MPI_Comm comm)
+{
+    const int old = b->nfile, nfile = old + nfile_grow;
+    size_t *fsize = calloc(nfile + 1, sizeof(size_t)), *foffset = calloc(nfile + 1, sizeof(size_t));
+    int64_t *fchecksum = calloc(nfile + 1, sizeof(int64_t));
+    for (int i = 0; i < old; i++) { fsize[i] = b->fsize[i]; fchecksum[i] = fpm_comm_rank(comm) == 0 ? b->fchecksum[i] : 0; }
+    for (int i = 0; i < nfile_grow; i++) fsize[old + i] = size_grow * (i + 1) / nfile_grow - size_grow * i / nfile_grow;
+    for (int i = 0; i < nfile; i++) foffset[i + 1] = foffset[i] + fsize[i];
+    free(b->fsize); free(b->foffset); free(b->fchecksum);
+    b->fsize = fsize; b->foffset = foffset; b->fchecksum = fchecksum;
+    b->nfile = nfile; b->size = foffset[nfile]; b->header_dirty = 1;
+    int rc = 0;
+    if (fpm_comm_rank(comm) == 0) {
+        for (int i = old; i < nfile && !rc; i++) {
+            char fn[1200];
+            snprintf(fn, sizeof(fn), "%s%06X", b->path, (unsigned) i);
+            FILE *f = fopen(fn, "w");
+            if (!f) rc = -1; else fclose(f);
+        }
+    }
+    fpm_comm_barrier(comm);
+    return rc;
 }
 
 /* items [offset, offset + n) of the block <-> buf (already in the file's type) */
@@ -355,18 +383,36 @@ int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, cons
 /* positions == NULL: the ranks' slices one after the other.  Otherwise item i of this rank goes to row positions[i] of the block
  * (ascending; the positions of all ranks together are 0 .. total-1): how a catalog sorted by a dense particle id is written
  * without moving particles between the GPUs -- runs of consecutive positions go out as one write each. */
+static int write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
+                         const FpmIoMeta *meta, const uint64_t *positions, int append, MPI_Comm comm);
+
 int fastpm_b200_io_write_columns_at(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
                                     const FpmIoMeta *meta, const uint64_t *positions, MPI_Comm comm)
+{ return write_columns(filebase, dataset, cols, ncols, np_local, meta, positions, 0, comm); }
+
+/* fastpm_store_write in a mode other than "w" / "r" (io.c:334-340,522-537): every column block grows by ceil(total / 32 Mi) files
+ * holding the ranks' items one after the other; the dataset's own attributes are left alone; nothing happens when there is nothing
+ * to write */
+int fastpm_b200_io_append_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local, MPI_Comm comm)
+{ return write_columns(filebase, dataset, cols, ncols, np_local, NULL, NULL, 1, comm); }
+
+static int write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
+                         const FpmIoMeta *meta, const uint64_t *positions, int append, MPI_Comm comm)
 {
     int64_t total = 0;
-    const size_t first = rank_offset(np_local, comm, &total);
+    size_t first = rank_offset(np_local, comm, &total);
     if (fpm_comm_rank(comm) == 0 && mkdir_p(filebase) != 0) { fpm_comm_barrier(comm); return -1; }
     fpm_comm_barrier(comm);
     BfBlock b;
-    if (bf_create(&b, filebase, dataset, NULL, 0, 0, 0, comm)) return -1;          /* io.c:431-436: the dataset's attributes */
-    FpmIoMeta m = *meta;
-    meta_attrs(&b, &m, 1);
-    if (bf_close(&b, comm)) return -1;
+    if (!append) {
+        if (bf_create(&b, filebase, dataset, NULL, 0, 0, 0, comm)) return -1;      /* io.c:431-436: the dataset's attributes */
+        FpmIoMeta m = *meta;
+        meta_attrs(&b, &m, 1);
+        if (bf_close(&b, comm)) return -1;
+    } else if (total == 0) {
+        return 0;
+    }
+    const size_t first0 = first;
     const size_t items_per_file = 32 * 1024 * 1024;                                /* io.c:351 */
     int nfile = (int) (((size_t) total + items_per_file - 1) / items_per_file);
     if (nfile < 1) nfile = 1;
@@ -375,7 +421,16 @@ int fastpm_b200_io_write_columns_at(const char *filebase, const char *dataset, c
         if (!col->data && np_local > 0) continue;
         char blockname[256];
         snprintf(blockname, sizeof(blockname), "%s/%s", dataset, col->name);
-        if (bf_create(&b, filebase, blockname, col->dtype_out, col->nmemb, nfile, (size_t) total, comm)) return -1;
+        if (!append) {
+            if (bf_create(&b, filebase, blockname, col->dtype_out, col->nmemb, nfile, (size_t) total, comm)) return -1;
+        } else {
+            /* open what is there (an empty block if there is nothing yet), grow it, write behind the old end */
+            if (bf_open(&b, filebase, blockname) != 0 && bf_create(&b, filebase, blockname, col->dtype_out, col->nmemb, 0, 0, comm)) return -1;
+            fpm_comm_barrier(comm);
+            const size_t oldsize = b.size;
+            if (bf_grow(&b, nfile, (size_t) total, comm)) { bf_free(&b); return -1; }
+            first = oldsize + first0;
+        }
         const size_t isz_in = (size_t) dtype_itemsize(col->dtype) * col->nmemb, isz_out = (size_t) dtype_itemsize(col->dtype_out) * col->nmemb;
         void *raw = malloc(IO_CHUNK * isz_in + 1), *out = malloc(IO_CHUNK * isz_out + 1);
         int rc = 0;
@@ -502,8 +557,13 @@ int fastpm_store_write(FastPMStore *p, const char *filebase, const char *modestr
         p->meta._q_size = m.q_size; p->meta.a_x = m.a_x; p->meta.a_v = m.a_v; p->meta.M0 = m.M0;
         return 0;
     }
-    fastpm_raise(-1, "fastpm_b200: fastpm_store_write mode \"%s\" (append) is not implemented\n", modestr);
-    return -1;
+    /* any other mode string appends (io.c:334-340) */
+    fastpm_info("Appending a catalog to %s [%s]\n", filebase, p->name);
+    sorted_by_dense_id.ids = NULL;
+    const int n = store_columns(p, cols);
+    if (fastpm_b200_io_append_columns(filebase, p->name, cols, n, (int64_t) p->np, comm))
+        fastpm_raise(-1, "Failed to append to the catalog %s [%s]: %s\n", filebase, p->name, strerror(errno));
+    return 0;
 }
 
 int fastpm_store_read(FastPMStore *p, const char *filebase, int Nreaders, MPI_Comm comm)

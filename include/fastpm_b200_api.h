@@ -582,7 +582,10 @@ typedef struct {
 int fastpm_b200_io_write_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
                                  const FpmIoMeta *meta, MPI_Comm comm);
 int fastpm_b200_io_write_columns_at(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local,
-                                    const FpmIoMeta *meta, const uint64_t *positions, MPI_Comm comm);     /* rows at given file positions */
+                                    const FpmIoMeta *meta, const uint64_t *positions, MPI_Comm comm); /* the append mode of fastpm_store_write (io.c:522-537): every column block grows (big_block_mpi_grow_simple) and the ranks' items are
+ * written behind its old end; the dataset's own attributes are left alone */
+int fastpm_b200_io_append_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t np_local, MPI_Comm comm);
+    /* rows at given file positions */
 int fastpm_b200_io_read_columns(const char *filebase, const char *dataset, const FpmIoColumn *cols, int ncols, int64_t *np_local,
                                 FpmIoMeta *meta, MPI_Comm comm);
 int fastpm_b200_io_write_header(const char *filebase, const FpmIoHeader *h, MPI_Comm comm);

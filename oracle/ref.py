@@ -221,6 +221,10 @@ class Session:
         """write_snapshot_header + fastpm_store_write of the unit-converted CDM store (bigfile directory `filebase`)."""
         lib().ref_write_snapshot(self._h, C.c_char_p(str(filebase).encode()))
 
+    def append_snapshot(self, filebase):
+        """fastpm_store_write(..., "a"): the unit-converted CDM store appended to the catalog in `filebase`."""
+        lib().ref_append_snapshot(self._h, C.c_char_p(str(filebase).encode()))
+
     def evolve_snapshots(self, time_step, base, aout):
         """evolve + the CLI's snapshot taking: directories "<base>_%0.04f" for every aout inside the run."""
         ts = np.ascontiguousarray(time_step, dtype=np.float64)

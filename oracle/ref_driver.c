@@ -547,6 +547,18 @@ void ref_write_snapshot(RefSession *s, const char *filebase)
     fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, aout);
 }
 
+/* the same store appended to the catalog once more (mode "a", io.c:522-537: every block grows) */
+void ref_append_snapshot(RefSession *s, const char *filebase)
+{
+    FastPMSolver *fastpm = s->solver;
+    FastPMStore *p = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    FastPMStore po[1];
+    double aout = p->meta.a_x;
+    fastpm_set_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+    fastpm_store_write(po, filebase, "a", 0, MPI_COMM_WORLD);
+    fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, aout);
+}
+
 /* fastpm_solver_evolve with snapshots at aout[] the way the CLI takes them: check_snapshots (src/fastpm.c:1130-1208) restated as
  * an INTERPOLATION handler (it is static in the CLI), then write_snapshot_header + fastpm_store_write to "<base>_%0.04f". */
 typedef struct { const char *base; const double *aout; int nout, iout; } RefSnapPlan;

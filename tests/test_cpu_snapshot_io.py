@@ -114,6 +114,44 @@ def test_snapshot_directory_is_byte_identical(lib, run):
             assert a[name][3] == b[name][3], name
 
 
+def test_appended_catalog_is_byte_identical(lib, run, tmp_path):
+    """fastpm_store_write in append mode (io.c:522-537): every column block grows by big_block_mpi_grow_simple and the new items land
+    behind the old end; appending to a catalog that does not exist yet creates empty blocks first.  Same files, byte for byte, as the
+    reference's, after write + append and after append + append."""
+    s, n, nc, L = run["session"], len(run["x"]), run["nc"], run["L"]
+    x, v, p = run["x"], run["v"], run["p"]
+    pot = _potential(run["ref_dir"], n)
+    ids = p["id"]
+    keep = [x, v, p["dx1"], p["dx2"], ids, pot]
+    cols = (IoColumn * 6)(
+        IoColumn(b"Position", b"f4", b"f8", 3, x.ctypes.data, 0), IoColumn(b"DX1", b"f4", b"f4", 3, p["dx1"].ctypes.data, 0),
+        IoColumn(b"DX2", b"f4", b"f4", 3, p["dx2"].ctypes.data, 0), IoColumn(b"Velocity", b"f4", b"f4", 3, v.ctypes.data, 0),
+        IoColumn(b"ID", b"i8", b"i8", 1, ids.ctypes.data, 0), IoColumn(b"Potential", b"f4", b"f4", 1, pot.ctypes.data, 0))
+    m = IoMeta((C.c_int64 * 3)(nc * nc, nc, 1), (C.c_double * 3)(L / nc, L / nc, L / nc), (C.c_double * 3)(0, 0, 0), nc ** 3, run["a"], run["a"],
+               float(p["meta"][2]))
+    lib.fastpm_b200_io_write_columns.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int]
+    lib.fastpm_b200_io_append_columns.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]
+    for first in ("w", "a"):
+        ref_dir, mine = str(tmp_path / ("ref_" + first)), str(tmp_path / ("mine_" + first))
+        if first == "w":
+            s.write_snapshot(ref_dir)
+            assert lib.fastpm_b200_io_write_columns(mine.encode(), b"1", cols, 6, n, C.byref(m), 1) == 0
+        else:
+            s.append_snapshot(ref_dir)
+            assert lib.fastpm_b200_io_append_columns(mine.encode(), b"1", cols, 6, n, 1) == 0
+        s.append_snapshot(ref_dir)
+        assert lib.fastpm_b200_io_append_columns(mine.encode(), b"1", cols, 6, n, 1) == 0
+        theirs = [f for f in _files(ref_dir) if f.startswith("1" + os.sep)]
+        ours = [f for f in _files(mine) if f.startswith("1" + os.sep)]
+        assert ours == theirs, (first, ours, theirs)
+        for f in theirs:
+            assert filecmp.cmp(os.path.join(mine, f), os.path.join(ref_dir, f), shallow=False), (first, f)
+        # two files of n items each per column now
+        head = open(os.path.join(mine, "1", "ID", "header")).read()
+        assert "NFILE: 2" in head and head.count(": %d :" % n) == 2, head
+    del keep
+
+
 def test_reference_reads_our_snapshot_and_we_read_theirs(lib, run, ref_mod, pk_text):
     nc, L, n = run["nc"], run["L"], len(run["x"])
     mine = str(run["tmp"] / "mine_0.9000")
