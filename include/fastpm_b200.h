@@ -125,7 +125,7 @@ int fpm_readout_pack3(const fpm_mesh *m, const float *canvas, const double *x, i
 int fpm_readout3(const fpm_mesh *m, const float *canvas0, const float *canvas1, const float *canvas2, const double *x, int64_t np, float *out3);
 
 /* the windows other than CIC, _generic_paint / _generic_readout painter.c:217-317: window = FastPMPainterType (1 linear, support 2;
- * 2 quadratic, support 3; 3 Lanczos with the given support <= 8, including the reference's 1e-3 table quantisation); one GPU only */
+ * 2 quadratic, support 3; 3 Lanczos with the given support <= 8, including the reference's 1e-3 table quantisation); one GPU: several GPUs go through the _ex forms below with a halo block */
 int fpm_paint_window(const fpm_mesh *m, int window, int support, float *canvas, const double *x, int64_t np, double M0, const float *mass,
                      const float *field, int field_stride);
 int fpm_readout_window(const fpm_mesh *m, int window, int support, const float *canvas, const double *x, int64_t np, float *out, int out_stride);

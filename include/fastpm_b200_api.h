@@ -560,7 +560,7 @@ void fastpm_path_ensure_dirname(const char *path);
 int read_funck(FastPMFuncK *fk, const char filename[], MPI_Comm comm);                                    /* io.h */
 
 /* ------------------------------------------------------------------ [io.h] snapshot / mesh files (bigfile directories)
- * Same names, arguments and on-disk result as libfastpmio/io.c; append mode and the healpix / light-cone writers are not implemented and raise; on several ranks the sort by id
+ * Same names, arguments and on-disk result as libfastpmio/io.c; the healpix / light-cone writers are not implemented; on several ranks the sort by id
  * keeps the particles in place and writes every row at the file position its (dense) id gives. */
 typedef void (*FastPMSnapshotSorter)(const void *ptr, void *radix, void *arg);
 void FastPMSnapshotSortByID(const void *ptr, void *radix, void *arg);
