@@ -62,8 +62,7 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaPassArgs a)
     __syncthreads();
 
     // A CTA may take `chunk` kz-adjacent tiles in a row before it jumps ahead (so that the two 64-byte halves of a line are
-    // written by the same SM close in time at N = 2048).  Measured: no gain for the transposing passes, 10-25 % loss for the
-    // in-place ones (scripts/fft_passes.py with FASTPM_B200_TMA_CHUNK = 2, 4); kept as a diagnostic, default 1.
+    // written by the same SM close in time); which passes gain from it is measured, see fpm_fft_tma_pass below.
     const int chunk = a.chunk;
     const int jump = 1 + ((int) gridDim.x - 1) * chunk;
     auto next_tile = [&](int tl) { return (tl % chunk != chunk - 1) ? tl + 1 : tl + jump; };
@@ -307,9 +306,15 @@ int fpm_fft_tma_pass(int n, const float2 *src, int pitch_c, int nouter, const Tm
     a.early = early == 4 ? ((transposing && !args.xfer.active && n >= 2048) ? 5 : 3) : early;
     a.nouter = nouter;
     a.ntile_k = (n / 2 + 1 + K - 1) / K;
-    static int chunk = -1;        // FASTPM_B200_TMA_CHUNK: kz-adjacent tiles a CTA processes back to back (diagnostic, default 1)
-    if (chunk < 0) { const char *e = getenv("FASTPM_B200_TMA_CHUNK"); chunk = e ? atoi(e) : 1; }
-    a.chunk = chunk > 0 ? chunk : 1;
+    // kz-adjacent tiles a CTA processes back to back, so that the two 64-byte halves of an output line meet in L2 microseconds
+    // apart instead of whenever the neighbouring CTA gets there (ncu at N = 1536: the transposing passes READ 1.8 x the mesh from
+    // DRAM -- half-written lines are completed from memory -- and only 1.02 x in place).  Measured (scripts/fft_passes.py,
+    // gpurun_out/r02w_passes_*): N = 1536 transposing 10.7 -> 7.8 ms plain, 10.2 -> 9.3 ms with the force kernel at 4 tiles, in
+    // place 6.3 -> 6.9 (worse); N = 2048 nothing to gain (22.2 -> 21.5 / 22.2 plain, the other passes 6-30 % slower).  Hence: 4 for
+    // the transposing passes at N = 1536, 1 everywhere else; FASTPM_B200_TMA_CHUNK overrides.
+    static int chunk = -1;
+    if (chunk < 0) { const char *e = getenv("FASTPM_B200_TMA_CHUNK"); chunk = e ? atoi(e) : 0; }
+    a.chunk = chunk > 0 ? chunk : ((n == 1536 && transposing) ? 4 : 1);
     switch (n) {
         case 512: return launch_cfg<8, 8, 8, 16>(tmap, a, nsm, st);
         case 768: return launch_cfg<24, 8, 4, 16>(tmap, a, nsm, st);
