@@ -348,6 +348,8 @@ static int run_fastpm(FastPMConfig *config, RunData *prr, MPI_Comm comm)
     fastpm_add_event_handler(&fastpm->event_handlers, FASTPM_EVENT_FORCE, FASTPM_EVENT_STAGE_AFTER, (FastPMEventHandlerFunction) write_powerspectrum, prr);
     fastpm_add_event_handler(&fastpm->event_handlers, FASTPM_EVENT_INTERPOLATION, FASTPM_EVENT_STAGE_BEFORE, (FastPMEventHandlerFunction) check_snapshots, prr);
     fastpm_add_event_handler(&fastpm->event_handlers, FASTPM_EVENT_TRANSITION, FASTPM_EVENT_STAGE_BEFORE, (FastPMEventHandlerFunction) print_transition, prr);
+    /* print_transition only prints: no need to apply the queued kicks and drifts for it (keeps the fused particle update) */
+    fastpm_b200_mark_handler_passive((FastPMEventHandlerFunction) print_transition);
 
     double a_restart = 0.0;
     if (prr->cli->RestartSnapshotPath) {

@@ -523,6 +523,9 @@ void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allred
  * event->delta_k, ... with its OWN device code (a CUDA kernel, torch on the pointer) must call this first: it applies everything pending
  * and waits for the device. */
 void fastpm_b200_sync_state(void);
+/* Promise that an event handler never reads the particles (it prints a progress line, say): events are delivered to it without first
+ * applying the queued kicks and drifts, which keeps the fused particle update alive.  Ordinary handlers see a fully updated store. */
+void fastpm_b200_mark_handler_passive(FastPMEventHandlerFunction function);
 /* 1 when the host-scalar collectives of a multi-rank run go through the shared-memory segment of host/shmcoll.c (all ranks on one
  * host), 0 when they go through the launcher's callbacks (FASTPM_B200_HOST_COLL=callbacks, several hosts) or there is one rank */
 int fastpm_b200_host_collectives_shared(void);

@@ -22,6 +22,7 @@ CASES = [
     "test_non_cic_painter_matches_reference",
     "test_single_mode_transfers_match_reference",
     "test_shifted_ics_match_reference",
+    "test_passive_handler_keeps_the_fused_update",
 ]
 
 
