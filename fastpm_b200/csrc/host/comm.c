@@ -111,6 +111,20 @@ void fastpm_b200_comm_init_host(int rank, int size, fpm_host_allreduce_fn allred
     fpm_shm_setup(rank, size, allgather_cb, userdata);
 }
 
+static void comm_init_device(int rank, int size);
+static void *g_xbarrier_flags = NULL;
+
+/* the end of a multi-rank program that goes on to libfastpm_cleanup (which insists that every block has been returned): every rank
+ * has finished its device work, then the communicator's own block goes back */
+void fastpm_b200_comm_finalize(void)
+{
+    if (g_size <= 1 || !g_xbarrier_flags) return;
+    FPM_MUST(fpm_sync());
+    fpm_comm_barrier(MPI_COMM_WORLD);
+    fastpm_memory_free(_libfastpm_get_gmem(), g_xbarrier_flags);
+    g_xbarrier_flags = NULL;
+}
+
 void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, fpm_host_allgather_fn allgather_cb, void *userdata)
 {
     libfastpm_init();
@@ -118,6 +132,24 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
     g_rank = rank; g_size = size; g_allreduce = allreduce; g_allgather = allgather_cb; g_cb_data = userdata;
     fpm_shm_setup(rank, size, allgather_cb, userdata);
     if (size == 1) return;
+    comm_init_device(rank, size);
+}
+
+/* The same for the ranks of a one-node run that have no launcher to supply callbacks (fastpm_b200_run -n N): they attach to the
+ * shared segment their parent process made (fastpm_b200_local_segment_create) and exchange everything through it. */
+int fpm_shm_attach(int rank, int size, const char *name);
+void fastpm_b200_comm_init_local(int rank, int size, const char *segment)
+{
+    libfastpm_init();
+    if (size > MAXR) fastpm_raise(-1, "at most %d slabs (one node) are supported\n", MAXR);
+    g_rank = rank; g_size = size; g_allreduce = NULL; g_allgather = NULL; g_cb_data = NULL;
+    if (size == 1) return;
+    if (fpm_shm_attach(rank, size, segment) != 0) fastpm_raise(-1, "rank %d cannot attach to the shared segment %s\n", rank, segment);
+    comm_init_device(rank, size);
+}
+
+static void comm_init_device(int rank, int size)
+{
     /* arena: FASTPM_B200_ARENA_GB, else 85 % of what is free now; the smallest over ranks so that offsets stay in range everywhere */
     size_t free_b = 0, total_b = 0;
     if (fpm_device_mem_info(&free_b, &total_b) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
@@ -139,6 +171,7 @@ void fastpm_b200_comm_init(int rank, int size, fpm_host_allreduce_fn allreduce, 
         if (!arena_peer[r]) fastpm_raise(-1, "mapping rank %d's arena: %s\n", r, fpm_last_error());
     }
     void *flags = fastpm_memory_alloc(_libfastpm_get_gmem(), "xbarrier flags", 4096, FASTPM_MEMORY_FLOATING), *peers[MAXR];
+    g_xbarrier_flags = flags;
     if (fpm_xbarrier_init(size, rank, flags) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
     peers_of(flags, peers);
     if (fpm_xbarrier_set_peers(peers) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());

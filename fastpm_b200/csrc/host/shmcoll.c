@@ -145,3 +145,30 @@ int fpm_shm_setup(int rank, int size, fpm_host_allgather_fn gather, void *userda
     g_seg = seg; g_shm_rank = rank; g_shm_size = size;          /* ftruncate zero-filled it: arrived == 0 */
     return 1;
 }
+
+/* ---- a one-node run without a launcher: the parent of the rank processes makes the segment before it forks them
+ * (fastpm_b200_run -n N, lua_front/run.c), every rank attaches by name; no callbacks are involved at all */
+int fastpm_b200_local_segment_create(char *name_out, size_t cap)
+{
+    snprintf(name_out, cap, "/fastpm_b200_%ld_%lx", (long) getpid(), (unsigned long) (now_s() * 1e6));
+    const int fd = shm_open(name_out, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return -1;
+    if (ftruncate(fd, sizeof(ShmSeg)) != 0) { close(fd); shm_unlink(name_out); return -1; }
+    close(fd);
+    return 0;
+}
+int fastpm_b200_local_segment_unlink(const char *name) { return shm_unlink(name); }
+
+int fpm_shm_attach(int rank, int size, const char *name)
+{
+    if (g_seg) { munmap((void *) g_seg, sizeof(ShmSeg)); g_seg = NULL; }
+    g_calls = 0;
+    if (size < 1 || size > SHM_MAXR) return -1;
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) return -1;
+    void *p = mmap(NULL, sizeof(ShmSeg), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return -1;
+    g_seg = (ShmSeg *) p; g_shm_rank = rank; g_shm_size = size;
+    return 0;
+}

@@ -1,7 +1,10 @@
 /* fastpm_b200_run -- the FastPM command-line run for the force step / integrator path, driven by the reference's own Lua
  * parameter surface.
  *
- *     fastpm_b200_run [-r restart_snapshot] [-W Nwriters] [-m MemoryMB] [--dump-config] paramfile.lua [args ...]
+ *     fastpm_b200_run [-n NGPUS] [-r restart_snapshot] [-W Nwriters] [-m MemoryMB] [--dump-config] paramfile.lua [args ...]
+ *
+ * -n N (2, 4 or 8; where the reference says `mpirun -n N fastpm`): the process forks N ranks, one per GPU, x-slabs of the mesh, BEFORE
+ * anything touches a device; they find each other through a shared-memory segment the parent made (fastpm_b200_comm_init_local).
  *
  * The parameter file is evaluated by the reference's Lua runtime (vendored lua/ + src/lua-runtime-{dump,config,fastpm}.lua,
  * compiled in place by this directory's Makefile; schema and validation are the reference's, lua-runtime-fastpm.lua:14-346) and
@@ -25,6 +28,8 @@
 #include <string.h>
 #include <math.h>
 #include <unistd.h>
+#include <signal.h>
+#include <sys/wait.h>
 #include <fastpm/libfastpm.h>          /* shim/fastpm/libfastpm.h: fastpm_b200_api.h + the option enums of out-of-scope features */
 #include "lua-config.h"
 #include "param.h"
@@ -377,13 +382,15 @@ static int run_fastpm(FastPMConfig *config, RunData *prr, MPI_Comm comm)
 int main(int argc, char **argv)
 {
     /* --dump-config: handled before anything touches a device */
-    int dump = 0;
+    int dump = 0, nranks = 1;
     char **av = malloc(sizeof(char *) * (argc + 1));
     int ac = 0;
     for (int i = 0; i < argc; i++) {
         if (i > 0 && !strcmp(argv[i], "--dump-config")) { dump = 1; continue; }
+        if (i > 0 && !strcmp(argv[i], "-n") && i + 1 < argc && ac == 1) { nranks = atoi(argv[++i]); continue; }      /* first option only */
         av[ac++] = argv[i];
     }
+    if (nranks != 1 && nranks != 2 && nranks != 4 && nranks != 8) { fprintf(stderr, "-n %d: 1, 2, 4 or 8 GPUs of one node\n", nranks); return 1; }
     av[ac] = NULL;
     RunData prr[1];
     memset(prr, 0, sizeof(prr));
@@ -401,6 +408,37 @@ int main(int argc, char **argv)
     }
 
     refuse(prr);                          /* before any device is touched */
+    if (nranks > 1) {
+        /* one process per GPU, forked before the first CUDA call; the parent only waits (and takes the others down if one fails) */
+        char segment[64];
+        if (fastpm_b200_local_segment_create(segment, sizeof(segment)) != 0) { fprintf(stderr, "cannot create the shared segment of the ranks\n"); return 1; }
+        pid_t pids[8];
+        int rank = -1;
+        fflush(NULL);
+        for (int r = 0; r < nranks; r++) {
+            pids[r] = fork();
+            if (pids[r] < 0) { perror("fork"); for (int q = 0; q < r; q++) kill(pids[q], SIGTERM); fastpm_b200_local_segment_unlink(segment); return 1; }
+            if (pids[r] == 0) { rank = r; break; }
+        }
+        if (rank < 0) {
+            int failed = 0;
+            for (int left = nranks; left > 0; left--) {
+                int status = 0;
+                const pid_t done = wait(&status);
+                if (done < 0) break;
+                if (!(WIFEXITED(status) && WEXITSTATUS(status) == 0) && !failed) {
+                    failed = WIFEXITED(status) ? WEXITSTATUS(status) : 128 + WTERMSIG(status);
+                    for (int q = 0; q < nranks; q++) if (pids[q] != done) kill(pids[q], SIGTERM);      /* the others would wait for it forever */
+                }
+            }
+            fastpm_b200_local_segment_unlink(segment);
+            return failed;
+        }
+        char dev[16];
+        snprintf(dev, sizeof(dev), "%d", rank);
+        setenv("FASTPM_B200_DEVICE", dev, 1);                                              /* rank r drives GPU r */
+        fastpm_b200_comm_init_local(rank, nranks, segment);
+    }
     libfastpm_init();
     MPI_Comm comm = MPI_COMM_WORLD;
     fastpm_set_msg_handler(fastpm_default_msg_handler, comm, NULL);      /* the command line logs like the reference's (src/fastpm.c:136) */
@@ -476,6 +514,7 @@ int main(int argc, char **argv)
     free(vpminit);
     free_lua_parameters(prr->lua);
     free_cli_parameters(prr->cli);
+    if (nranks > 1) fastpm_b200_comm_finalize();
     libfastpm_cleanup();
     return 0;
 }

@@ -529,6 +529,13 @@ void fastpm_b200_mark_handler_passive(FastPMEventHandlerFunction function);
 /* 1 when the host-scalar collectives of a multi-rank run go through the shared-memory segment of host/shmcoll.c (all ranks on one
  * host), 0 when they go through the launcher's callbacks (FASTPM_B200_HOST_COLL=callbacks, several hosts) or there is one rank */
 int fastpm_b200_host_collectives_shared(void);
+/* The ranks of a one-node run without a launcher (fastpm_b200_run -n N forks them): the parent makes the segment before forking --
+ * no CUDA call may precede the fork --, every rank attaches by name; no callbacks are involved.  The parent unlinks it at the end. */
+int fastpm_b200_local_segment_create(char *name_out, size_t cap);
+int fastpm_b200_local_segment_unlink(const char *name);
+void fastpm_b200_comm_init_local(int rank, int size, const char *segment);
+/* before libfastpm_cleanup in a multi-rank program: waits for every rank, returns the communicator's own device block */
+void fastpm_b200_comm_finalize(void);
 /* the largest number of exchange rounds a fastpm_store_decompose of this process has needed so far (1 unless a pack buffer overflowed) */
 int fastpm_b200_migrate_rounds_max(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);

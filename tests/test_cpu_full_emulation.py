@@ -12,6 +12,8 @@ import os
 import subprocess
 import sys
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,6 +76,19 @@ def runs(emul_lib, tmp_path_factory):
     ranks2 = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                                "--master-port", "29687", os.path.join(ROOT, "tests", "mp_worker.py"), "emul"],
                               cwd=ROOT, env=dict(os.environ, FASTPM_B200_MIGRATE_CAP="16"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # the command line (fastpm_b200/lua_front) linked against the emulated library: one process, and `-n 2` (two forked ranks that find
+    # each other through the shared segment their parent made -- no launcher, no callbacks)
+    cli = {}
+    if os.path.isdir("/root/reference/lua"):
+        import shutil
+        mk = subprocess.run(["make", "-C", os.path.join(ROOT, "fastpm_b200", "lua_front"), "emul"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert mk.returncode == 0, mk.stdout[-2000:]
+        exe = os.path.join(ROOT, "fastpm_b200", "lua_front", "_build", "fastpm_b200_run_emul")
+        for tag, extra in (("one", []), ("two", ["-n", "2"])):
+            d = tmp_path_factory.mktemp("cli_" + tag)
+            shutil.copy(os.path.join(ROOT, "tests", "golden", "powerspec.txt"), str(d))
+            cli[tag] = (str(d), subprocess.Popen([exe] + extra + [os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), "8", "3"], cwd=str(d),
+                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     out = {}
     for g, p in procs.items():
         o, _ = p.communicate(timeout=1500)
@@ -83,12 +98,16 @@ def runs(emul_lib, tmp_path_factory):
     ro, _ = ranks4.communicate(timeout=1500)
     r2o, _ = ranks2.communicate(timeout=1500)
     out["ranks2_rounds"] = (ranks2.returncode, r2o)
+    out["cli"] = {}
+    for tag, (d, p) in cli.items():
+        o, _ = p.communicate(timeout=1500)
+        out["cli"][tag] = (p.returncode, d, o)
     out["ranks4"] = (ranks4.returncode, ro, sorted(f for f in set(os.listdir("/dev/shm")) - shm_before if f.startswith("fpm_emul_")))
     return out
 
 
 def test_gpu_cases_on_the_emulated_library(runs):
-    failed = [(g, r[1][-3000:]) for g, r in runs.items() if g not in ("bench", "ranks4") and r[0] != 0]
+    failed = [(g, r[1][-3000:]) for g, r in runs.items() if isinstance(g, tuple) and r[0] != 0]       # the case groups
     assert not failed, "\n\n".join("%s\n%s" % (g, o) for g, o in failed)
 
 
@@ -131,3 +150,38 @@ def test_migration_in_rounds_on_the_emulated_library(runs):
     m = re.search(r"MP_GPU_OK ranks=2 .* migration rounds <= (\d+)", stdout)
     assert m, stdout[-3000:]
     assert int(m.group(1)) > 1, stdout[-3000:]
+
+
+def test_command_line_with_two_forked_ranks(runs):
+    """fastpm_b200_run -n 2 (where the reference says `mpirun -n 2 fastpm`): the run loop of lua_front/run.c on two slabs against the same
+    program on one -- same log lines of the power spectrum, same P(k) files, same snapshot (sorted by id) up to the float order of the
+    deposits; nothing left in /dev/shm.  Linked against the emulated library: the program logic, not the GPU, is under test."""
+    import re
+    if not runs["cli"]:
+        pytest.skip("needs /root/reference (the Lua runtime is compiled from there)")
+    (rc1, d1, o1), (rc2, d2, o2) = runs["cli"]["one"], runs["cli"]["two"]
+    assert rc1 == 0, o1[-3000:]
+    assert rc2 == 0, o2[-3000:]
+    pat = re.compile(r"D\^2\(([0-9.]+), 1.0\) P\(k<[0-9.]+\) = ([0-9.eE+-]+) Sigma8 = ([0-9.eE+-]+)")
+    l1, l2 = pat.findall(o1), pat.findall(o2)
+    assert len(l1) == 3 and len(l1) == len(l2), (l1, l2)
+    for (a1, p1, s1), (a2, p2, s2) in zip(l1, l2):
+        assert a1 == a2 and abs(float(p1) / float(p2) - 1) < 1e-5 and abs(float(s1) / float(s2) - 1) < 1e-5, (l1, l2)
+    assert "ThisTask = 1" not in o2                                   # only rank 0 logs
+    for f in sorted(os.listdir(os.path.join(d1, "out"))):
+        if not f.endswith(".txt"):
+            continue
+        x, y = np.loadtxt(os.path.join(d1, "out", f)), np.loadtxt(os.path.join(d2, "out", f))
+        assert x.shape == y.shape and np.array_equal(x[:, 2], y[:, 2]), f
+        sel = x[:, 2] > 0
+        np.testing.assert_allclose(x[sel, 1], y[sel, 1], rtol=1e-5, err_msg=f)
+    rd = lambda top, name, dt, nm: np.fromfile(os.path.join(top, "out", "fastpm_1.0000", "1", name, "000000"), dtype=dt).reshape(-1, nm)
+    ia, ib = rd(d1, "ID", np.uint64, 1)[:, 0], rd(d2, "ID", np.uint64, 1)[:, 0]
+    assert np.array_equal(ia, np.arange(8 ** 3, dtype=np.uint64)) and np.array_equal(ia, ib)      # sorted by id, on two ranks as on one
+    dd = np.abs(rd(d1, "Position", np.float32, 3).astype(np.float64) - rd(d2, "Position", np.float32, 3))
+    assert np.minimum(dd, 16.0 - dd).max() < 1e-4
+    va, vb = rd(d1, "Velocity", np.float32, 3), rd(d2, "Velocity", np.float32, 3)
+    assert np.abs(va - vb).max() < 1e-4 * np.abs(va).max()
+    hdr = lambda d: open(os.path.join(d, "out", "fastpm_1.0000", "Header", "attr-v2")).read()
+    assert hdr(d1) == hdr(d2)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("fastpm_b200_")]
