@@ -69,6 +69,56 @@ static inline double atomicAdd(double *p, double v)
     return o;
 }
 
+// The CUDA threads of a CTA are OS threads that must all be alive at once (__syncthreads() is a real barrier); creating and joining up to
+// 1024 of them for every CTA of every launch dominated the run time of the emulation, so they are kept in a pool (one per translation
+// unit, like everything else in this header) and handed one CTA at a time.
+#include <atomic>
+#include <memory>
+#include <semaphore.h>
+namespace {          // internal linkage: every translation unit that includes this header needs ITS OWN copy of these member functions,
+                     // because they touch that unit's thread_local threadIdx (one shared inline definition would set somebody else's)
+struct FpmEmulPool {
+    struct Worker { sem_t go; std::thread th; };
+    std::vector<std::unique_ptr<Worker>> workers;       // worker i plays CUDA thread i of the current CTA; only the first `block` are woken
+    sem_t done;
+    const std::function<void()> *job = nullptr;
+    std::atomic<unsigned> remaining{0};
+    std::atomic<bool> stop{false};
+    FpmEmulPool() { sem_init(&done, 0, 0); }
+    void run(unsigned id)
+    {
+        Worker *w = workers[id].get();
+        for (;;) {
+            while (sem_wait(&w->go) != 0) { }
+            if (stop.load()) return;
+            threadIdx.x = id;
+            (*job)();
+            if (remaining.fetch_sub(1) == 1) sem_post(&done);
+        }
+    }
+    void cta(unsigned block, const std::function<void()> &k)
+    {
+        while (workers.size() < block) {
+            const unsigned id = (unsigned) workers.size();
+            workers.emplace_back(new Worker);
+            sem_init(&workers[id]->go, 0, 0);
+        }
+        for (unsigned id = 0; id < block; id++)
+            if (!workers[id]->th.joinable()) workers[id]->th = std::thread([this, id]() { run(id); });
+        job = &k;
+        remaining.store(block);
+        for (unsigned id = 0; id < block; id++) sem_post(&workers[id]->go);
+        while (sem_wait(&done) != 0) { }
+    }
+    ~FpmEmulPool()
+    {
+        stop.store(true);
+        for (auto &w : workers) if (w->th.joinable()) { sem_post(&w->go); w->th.join(); }
+    }
+};
+}
+static FpmEmulPool fpm_emul_pool;
+
 // runs kernel(args...) as a grid of `grid` CTAs of `block` threads with `smem_bytes` of dynamic shared memory, CTA after CTA
 template <typename Kernel>
 static void fpm_emul_launch(unsigned grid, unsigned block, size_t smem_bytes, Kernel kernel)
@@ -76,14 +126,13 @@ static void fpm_emul_launch(unsigned grid, unsigned block, size_t smem_bytes, Ke
     std::vector<unsigned char> smem(smem_bytes + 1024);
     fpm_emul_dyn_smem = (unsigned char *) (((uintptr_t) smem.data() + 1023) & ~(uintptr_t) 1023);
     gridDim.x = grid; blockDim.x = block;
+    const std::function<void()> body = [&]() { kernel(); };
     for (unsigned b = 0; b < grid; b++) {
         blockIdx.x = b;
         pthread_barrier_init(&fpm_emul_barrier, NULL, block);
         for (unsigned w = 0; w < (block + 31) / 32 && w < 32; w++)
             pthread_barrier_init(&fpm_emul_warp_barrier[w], NULL, (w + 1) * 32 <= block ? 32 : block - w * 32);
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < block; t++) pool.emplace_back([&, t]() { threadIdx.x = t; kernel(); });
-        for (auto &th : pool) th.join();
+        fpm_emul_pool.cta(block, body);
         pthread_barrier_destroy(&fpm_emul_barrier);
         for (unsigned w = 0; w < (block + 31) / 32 && w < 32; w++) pthread_barrier_destroy(&fpm_emul_warp_barrier[w]);
     }

@@ -102,6 +102,7 @@ def runs(emul_lib, tmp_path_factory):
     for tag, (d, p) in cli.items():
         o, _ = p.communicate(timeout=1500)
         out["cli"][tag] = (p.returncode, d, o)
+    out["cli_shm_left"] = sorted(set(os.listdir("/dev/shm")) - shm_before)      # evaluated when every process of this fixture has ended
     out["ranks4"] = (ranks4.returncode, ro, sorted(f for f in set(os.listdir("/dev/shm")) - shm_before if f.startswith("fpm_emul_")))
     return out
 
@@ -184,4 +185,4 @@ def test_command_line_with_two_forked_ranks(runs):
     assert np.abs(va - vb).max() < 1e-4 * np.abs(va).max()
     hdr = lambda d: open(os.path.join(d, "out", "fastpm_1.0000", "Header", "attr-v2")).read()
     assert hdr(d1) == hdr(d2)
-    assert not [f for f in os.listdir("/dev/shm") if f.startswith("fastpm_b200_")]
+    assert not [f for f in runs["cli_shm_left"] if f.startswith("fastpm_b200_") or f.startswith("fpm_emul_")], runs["cli_shm_left"]
