@@ -1,6 +1,7 @@
 // fastpm_b200 -- the extern "C" boundary declared in include/fastpm_b200.h.
 #include "common.cuh"
 #include "mesh.cuh"
+#include "ranlux.h"
 #include "../../include/fastpm_b200.h"
 #include <stdarg.h>
 #include <string.h>
@@ -49,6 +50,7 @@ int fpm_kick_launch(float *v_out, const float *v_in, const float *acc, const flo
 int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const float *dx1, const float *dx2, double dyyy, double da1, double da2, double Dv1, double Dv2, int mode, long long np, cudaStream_t st);
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
 int fpm_shift_launch(double *x, long long np, double s0, double s1, double s2, cudaStream_t st);
+int fpm_cast_f64_f32_launch(float *dst, const double *src, long long n, cudaStream_t st);
 int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np, int nops, const double *ops, cudaStream_t st);
 int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2, long long np, cudaStream_t st);
 int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st);
@@ -759,6 +761,35 @@ int fpm_update_fused(double *x, float *v, const float *acc, const float *dx1, co
 // The "too far" flag of the previous wrap is examined when the next one is issued (or by fpm_wrap_check), so that
 // the integrator never drains the stream just to look at it.
 static int *d_wrap_bad = NULL, *h_wrap_bad = NULL;
+int fpm_cast_f64_to_f32(float *dst, const double *src, int64_t n)
+{
+    if (ensure_init()) return -1;
+    return fpm_cast_f64_f32_launch(dst, src, n, g_stream);
+}
+
+// _fastpm_store_fill_rand (store.c:694-720): uniform deviates of ONE serial RANLUX stream per rank over the np_upper entries of the
+// column.  The seed of rank r is 0x7fffffff times the (8 r)-th deviate of the generator seeded with 1231584 (the fixed seed itself on
+// rank 0), truncated to an integer as gsl_rng_set takes it.  A serial stream cannot be split over CUDA threads: the host draws it,
+// a chunk at a time, and the chunks are copied up.
+int fpm_fill_rand(float *rand_dev, int64_t n, int rank)
+{
+    if (ensure_init()) return -1;
+    FpmRanlux g;
+    double seed = 1231584;
+    fpm_ranlux_seed(g, (unsigned long long) seed);
+    for (int d = 0; d < rank * 8; d++) seed = 0x7fffffff * fpm_ranlux_uniform(g);
+    fpm_ranlux_seed(g, (unsigned long long) seed);
+    const int64_t chunk = 1 << 22;
+    std::vector<float> buf((size_t) (n < chunk ? (n > 0 ? n : 1) : chunk));
+    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+        const int64_t m = n - i0 < chunk ? n - i0 : chunk;
+        for (int64_t i = 0; i < m; i++) buf[(size_t) i] = (float) fpm_ranlux_uniform(g);
+        FPM_CUDA_OK(cudaMemcpyAsync(rand_dev + i0, buf.data(), sizeof(float) * (size_t) m, cudaMemcpyHostToDevice, g_stream));
+        FPM_CUDA_OK(cudaStreamSynchronize(g_stream));
+    }
+    return 0;
+}
+
 int fpm_shift_positions(double *x, int64_t np, double s0, double s1, double s2)
 {
     if (ensure_init()) return -1;

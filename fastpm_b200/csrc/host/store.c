@@ -105,8 +105,7 @@ size_t fastpm_store_get_np_total(FastPMStore *p, MPI_Comm comm)
 }
 
 /* store.c:723-806: one particle per cell of the Nc^3 grid, this rank's x-slab; id = i*Nc^2 + j*Nc + k.
- * The `rand` column is left zero: it only feeds sub-sampling (store.c:967-997), which is out of scope, and
- * filling it needs a serial RANLUX stream over np_upper entries (declared deviation). */
+ * The `rand` column (it feeds sub-sampling, store.c:967-997) is this rank's serial RANLUX stream, drawn on the host. */
 void fastpm_store_fill(FastPMStore *p, PM *pm, double *shift, ptrdiff_t *Nc)
 {
     ptrdiff_t nc[3];
@@ -127,8 +126,26 @@ void fastpm_store_fill(FastPMStore *p, PM *pm, double *shift, ptrdiff_t *Nc)
                            pm->BoxSize[0], p->meta._q_shift[0]));
     /* i-planes of nc x nc particles in id order: let paint / readout walk them in Lagrangian bricks */
     FPM_MUST(fpm_particle_grid_hint((int) nc[0]));
-    if (p->q) fastpm_raise(-1, "fastpm_b200: the q column is not filled on the device yet\n");
+    if (p->q) FPM_MUST(fpm_cast_f64_to_f32((float *) p->q, (const double *) p->x, (int64_t) (3 * p->np)));      /* store.c:784-789 */
+    if (p->mask) FPM_MUST(fpm_memset(p->mask, 0, sizeof(p->mask[0]) * p->np));
+    if (p->rmom) FPM_MUST(fpm_memset(p->rmom, 0, sizeof(p->rmom[0]) * p->np));
     p->meta.a_x = p->meta.a_v = 0.;
+    /* store.c:804: one serial RANLUX stream per rank over all np_upper entries */
+    if (p->rand) FPM_MUST(fpm_fill_rand((float *) p->rand, (int64_t) p->np_upper, pm->ThisTask));
+}
+
+/* for bindings that cannot lay out FastPMStore: a scratch store with the q and rand columns, filled on pm's grid by fastpm_store_fill;
+ * q_host [np][3] and rand_host [np_upper] receive the columns.  Returns np. */
+int64_t fastpm_b200_fill_probe(PM *pm, int64_t np_upper, float *q_host, float *rand_host)
+{
+    FastPMStore p[1];
+    fastpm_store_init(p, "probe", (size_t) np_upper, COLUMN_POS | COLUMN_ID | COLUMN_Q | COLUMN_RAND | COLUMN_MASK, FASTPM_MEMORY_HEAP);
+    fastpm_store_fill(p, pm, NULL, NULL);
+    const int64_t np = (int64_t) p->np;
+    FPM_MUST(fpm_memcpy_d2h(q_host, p->q, sizeof(p->q[0]) * p->np));
+    FPM_MUST(fpm_memcpy_d2h(rand_host, p->rand, sizeof(p->rand[0]) * p->np_upper));
+    fastpm_store_destroy(p);
+    return np;
 }
 
 void fastpm_store_wrap(FastPMStore *p, double BoxSize[3])

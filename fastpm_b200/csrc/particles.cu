@@ -132,6 +132,14 @@ __global__ void __launch_bounds__(256) fused_update_kernel(const FusedArgs a)
     }
 }
 
+// dst[i] = (float) src[i]: the q column of a freshly filled store is the position rounded to float (store.c:784-789)
+__global__ void __launch_bounds__(256) cast_f64_f32_kernel(float *__restrict__ dst, const double *__restrict__ src, long long n)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (float) src[i];
+}
+
 // x[i][d] += s[d]: the (de-)shift of the particles around the 2LPT readouts when the ICs sit at cell centres (pm2lpt.c:30-34,141-145)
 __global__ void __launch_bounds__(256) shift_kernel(double *x, long long n3, double s0, double s1, double s2)
 {
@@ -294,6 +302,14 @@ int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *
     if (a.any_kick && !acc) { fpm_set_error("fused update: a kick needs the acc column"); return -1; }
     if (a.any_dx && !dx1) { fpm_set_error("fused update: COLA / LPT operations need the dx1 (and dx2) columns"); return -1; }
     FPM_TIMED(a.any_drift ? FPM_K_DRIFT : FPM_K_KICK, st, (fused_update_kernel<<<stream_grid(a.n3), 256, 0, st>>>(a)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_cast_f64_f32_launch(float *dst, const double *src, long long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    FPM_TIMED(FPM_K_OTHER, st, (cast_f64_f32_kernel<<<stream_grid(n), 256, 0, st>>>(dst, src, n)));
     FPM_CHECK_LAUNCH();
     return 0;
 }

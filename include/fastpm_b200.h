@@ -241,6 +241,10 @@ int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, doub
 int fpm_wrap_check(void);
 /* x[i][d] += s_d in place: the (de-)shift around the 2LPT readouts of cell-centred ICs (USE_SHIFT, pm2lpt.c:30-34,141-145) */
 int fpm_shift_positions(double *x, int64_t np, double s0, double s1, double s2);
+/* the q column of a freshly filled store: dst[i] = (float) src[i] (store.c:784-789) */
+int fpm_cast_f64_to_f32(float *dst, const double *src, int64_t n);
+/* the rand column, _fastpm_store_fill_rand store.c:694-720: n deviates of this rank's serial RANLUX stream (drawn on the host, copied up) */
+int fpm_fill_rand(float *rand_dev, int64_t n, int rank);
 /* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;
  * host_out[ncomp][4] = min, max, sum, sum of squares */
 int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out);

@@ -539,6 +539,8 @@ void fastpm_b200_comm_finalize(void);
 /* the largest number of exchange rounds a fastpm_store_decompose of this process has needed so far (1 unless a pack buffer overflowed) */
 int fastpm_b200_migrate_rounds_max(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
+/* a scratch store with q and rand columns filled by fastpm_store_fill on pm's grid, mirrored to the host (bindings, tests); returns np */
+int64_t fastpm_b200_fill_probe(PM *pm, int64_t np_upper, float *q_host, float *rand_host);
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count);
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count);
 /* mesh buffers: copy to / from a host array in the REFERENCE's layouts -- real [x][y][N+2] floats

@@ -366,6 +366,20 @@ static void tmp_store(FastPMStore *p, const double *x, int64_t np)
     p->meta.M0 = 1.0;
 }
 
+/* fastpm_store_fill (store.c:723-806) of a scratch store with q and rand columns on the particle grid of the LPT mesh */
+int64_t ref_fill_probe(RefSession *s, int64_t np_upper, float *q_out, float *rand_out)
+{
+    PM *pm = s->solver->lptpm;
+    FastPMStore p[1];
+    fastpm_store_init(p, "probe", np_upper, COLUMN_POS | COLUMN_ID | COLUMN_Q | COLUMN_RAND | COLUMN_MASK, FASTPM_MEMORY_HEAP);
+    fastpm_store_fill(p, pm, NULL, NULL);
+    const int64_t np = p->np;
+    memcpy(q_out, p->q, sizeof(p->q[0]) * p->np);
+    memcpy(rand_out, p->rand, sizeof(p->rand[0]) * p->np_upper);
+    fastpm_store_destroy(p);
+    return np;
+}
+
 /* fastpm_paint_local (painter.c:320) of unit-mass particles onto a cleared canvas */
 void ref_paint(RefSession *s, int which, double a, const double *x, int64_t np, float *canvas_out)
 {

@@ -254,6 +254,28 @@ def test_force_softening_matches_reference(ref_mod, pk_text, softening):
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
 
 
+def test_store_fill_q_and_rand_columns_match_reference(ref_mod):
+    """fastpm_store_fill with the q and rand columns allocated (store.c:723-806): q is the grid position rounded to float, rand this
+    rank's serial RANLUX stream over all np_upper entries (_fastpm_store_fill_rand, store.c:694-720) -- bit for bit."""
+    import ctypes as C
+    from fastpm_b200.solver import Solver
+    nc, L = 12, 60.0
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=2, np_alloc_factor=2.0)
+    n_up = 2 * nc ** 3 + 17
+    q0, r0 = s.fill_probe(n_up)
+    s.close()
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=2, np_alloc_factor=2.0)
+    q1 = np.zeros((n_up, 3), dtype=np.float32)
+    r1 = np.zeros(n_up, dtype=np.float32)
+    g.lib.fastpm_b200_fill_probe.restype = C.c_int64
+    g.lib.fastpm_b200_fill_probe.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    n = g.lib.fastpm_b200_fill_probe(g.lptpm, n_up, q1.ctypes.data, r1.ctypes.data)
+    g.close()
+    assert n == nc ** 3 == len(q0)
+    assert np.array_equal(q1[:n], q0)
+    assert np.array_equal(r1, r0) and r0.min() >= 0 and r0.max() < 1 and len(np.unique(r0)) > 0.99 * n_up
+
+
 def test_passive_handler_keeps_the_fused_update(pk_text):
     """Every event handler sees a fully updated store: the queued kicks and drifts are applied before it runs, which splits the
     fused K-K-D-D pass.  A handler marked passive (fastpm_b200_mark_handler_passive: it never reads the particles, like the

@@ -23,6 +23,7 @@ CASES = [
     "test_single_mode_transfers_match_reference",
     "test_shifted_ics_match_reference",
     "test_passive_handler_keeps_the_fused_update",
+    "test_store_fill_q_and_rand_columns_match_reference",
 ]
 
 
