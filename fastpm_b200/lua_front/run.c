@@ -29,6 +29,7 @@
 #include <math.h>
 #include <unistd.h>
 #include <signal.h>
+#include <errno.h>
 #include <sys/wait.h>
 #include <fastpm/libfastpm.h>          /* shim/fastpm/libfastpm.h: fastpm_b200_api.h + the option enums of out-of-scope features */
 #include "lua-config.h"
@@ -379,6 +380,14 @@ static int run_fastpm(FastPMConfig *config, RunData *prr, MPI_Comm comm)
     return 0;
 }
 
+/* -n N: the parent passes an interrupt on to the ranks it forked (exact pids), the wait loop below then cleans up */
+static pid_t rank_pids[8];
+static int n_rank_pids = 0;
+static void forward_signal(int sig)
+{
+    for (int i = 0; i < n_rank_pids; i++) if (rank_pids[i] > 0) kill(rank_pids[i], sig);
+}
+
 int main(int argc, char **argv)
 {
     /* --dump-config: handled before anything touches a device */
@@ -421,10 +430,15 @@ int main(int argc, char **argv)
             if (pids[r] == 0) { rank = r; break; }
         }
         if (rank < 0) {
+            for (int r = 0; r < nranks; r++) rank_pids[r] = pids[r];
+            n_rank_pids = nranks;
+            signal(SIGINT, forward_signal);
+            signal(SIGTERM, forward_signal);
             int failed = 0;
             for (int left = nranks; left > 0; left--) {
                 int status = 0;
-                const pid_t done = wait(&status);
+                pid_t done;
+                while ((done = wait(&status)) < 0 && errno == EINTR) { }       /* a forwarded signal interrupted the wait */
                 if (done < 0) break;
                 if (!(WIFEXITED(status) && WEXITSTATUS(status) == 0) && !failed) {
                     failed = WIFEXITED(status) ? WEXITSTATUS(status) : 128 + WTERMSIG(status);
