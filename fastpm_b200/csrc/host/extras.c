@@ -202,3 +202,32 @@ int read_funck(FastPMFuncK *fk, const char filename[], MPI_Comm comm)
     free(content);
     return 0;
 }
+
+/* ------------------------------------------------------------------ the public mesh calls in one chain (bindings, tests)
+ * fastpm_paint (CIC) of the CDM store -> pm_r2c -> fastpm_powerspectrum_init_from_delta -> pm_c2r -> fastpm_readout_local into
+ * ACC[:, 0]: what a user's own density / P(k) code does with libfastpm, on one GPU or on the slabs of several.  k, p, nmodes hold
+ * Nmesh / 2 bins; dens_host receives the painted density read back at this rank's particles (np values).  Returns np. */
+int64_t fastpm_b200_public_mesh_probe(FastPMSolver *fastpm, double a, double *k, double *p, double *nmodes, float *dens_host)
+{
+    PM *pm = fastpm_find_pm(fastpm, a);
+    FastPMStore *cdm = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
+    FastPMPainter painter[1];
+    fastpm_painter_init(painter, pm, FASTPM_PAINTER_CIC, 2);
+    FastPMFloat *canvas = pm_alloc(pm), *delta_k = pm_alloc(pm);
+    FastPMFieldDescr none = { 0, 0 }, acc0 = { COLUMN_ACC, 0 };
+    fastpm_paint(painter, canvas, cdm, none);
+    pm_r2c(pm, canvas, delta_k);
+    FastPMPowerSpectrum ps;
+    fastpm_powerspectrum_init_from_delta(&ps, pm, delta_k, delta_k);
+    for (size_t i = 0; i < ps.base.size; i++) { k[i] = ps.base.k[i]; p[i] = ps.base.f[i]; nmodes[i] = ps.Nmodes[i]; }
+    fastpm_powerspectrum_destroy(&ps);
+    pm_c2r(pm, delta_k);
+    fastpm_readout_local(painter, delta_k, cdm, cdm->np, acc0);
+    float *tmp = malloc(sizeof(float) * 3 * (cdm->np ? cdm->np : 1));
+    FPM_MUST(fpm_memcpy_d2h(tmp, cdm->acc, sizeof(float) * 3 * cdm->np));
+    for (size_t i = 0; i < cdm->np; i++) dens_host[i] = tmp[3 * i];
+    free(tmp);
+    pm_free(pm, delta_k);
+    pm_free(pm, canvas);
+    return (int64_t) cdm->np;
+}

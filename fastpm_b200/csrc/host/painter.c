@@ -106,7 +106,22 @@ void fastpm_readout_local(FastPMPainter *painter, FastPMFloat *canvas, FastPMSto
 /* painter.c:342-356: clear + paint (the ghost exchange of the reference is the mesh-plane halo here) */
 void fastpm_paint(FastPMPainter *painter, FastPMFloat *canvas, FastPMStore *p, FastPMFieldDescr field)
 {
-    pm_clear(painter->pm, canvas);
+    PM *pm = painter->pm;
+    pm_clear(pm, canvas);
+    if (pm->NTask == 1) { fastpm_paint_local(painter, canvas, p, p->np, field); return; }
+    /* several GPUs: what the particles of this slab deposit outside it goes to the neighbours -- the plane above the slab for CIC,
+     * a block of planes on both sides for the wider windows (host/gravity.c does the same inside the force step) */
+    const int generic = generic_path(painter, fpm_painter_window(painter));
+    FastPMFloat *halo = NULL, *saved = pm->whalo;
+    if (generic) {
+        int whl = 0, whr = 0;
+        FPM_MUST(fpm_window_halo_planes(fpm_painter_window(painter), painter->support, &whl, &whr));
+        const size_t hbytes = sizeof(FastPMFloat) * (size_t) (whl + whr) * pm->Nmesh[1] * pm->pitch_r;
+        halo = fastpm_memory_alloc(pm->mem, "window halo planes", hbytes, FASTPM_MEMORY_HEAP);
+        FPM_MUST(fpm_memset(halo, 0, hbytes));
+        pm->whalo = halo; pm->whl = whl; pm->whr = whr;
+    }
     fastpm_paint_local(painter, canvas, p, p->np, field);
-    if (painter->pm->NTask > 1) fastpm_raise(-1, "fastpm_paint on several GPUs: use fastpm_solver_compute_force in this build\n");
+    fpm_halo_add(pm, canvas);
+    if (halo) { pm->whalo = saved; fastpm_memory_free(pm->mem, halo); }
 }

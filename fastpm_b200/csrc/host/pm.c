@@ -103,7 +103,19 @@ static FastPMFloat *scratch_of(PM *pm)
  * overwritten with the z/y-pass intermediate only when from != to; from == to goes through the scratch mesh. */
 void pm_r2c(PM *pm, FastPMFloat *from, FastPMFloat *to)
 {
-    if (pm->NTask != 1) fastpm_raise(-1, "pm_r2c on several GPUs goes through fastpm_solver_compute_force in this build\n");
+    if (pm->NTask != 1) {
+        /* x-slabs on several GPUs: the distributed transform is out of place and uses its input as work space (PFFT with
+         * PFFT_DESTROY_INPUT does the same, pmpfft.c:277-279); an in-place call goes through a copy */
+        if (from == to) {
+            FastPMFloat *tmp = pm_alloc_noclear(pm, __FILE__, __LINE__);
+            pm_assign(pm, from, tmp);
+            fpm_mesh_r2c(pm, tmp, to, 1.0 / pm->Norm);
+            pm_free(pm, tmp);
+        } else {
+            fpm_mesh_r2c(pm, from, to, 1.0 / pm->Norm);
+        }
+        return;
+    }
     if (from == to) FPM_MUST(fpm_r2c_ws(pm->mesh, from, scratch_of(pm), to, 1.0 / pm->Norm));
     else FPM_MUST(fpm_r2c(pm->mesh, from, to, 1.0 / pm->Norm));
 }
@@ -111,7 +123,16 @@ void pm_r2c(PM *pm, FastPMFloat *from, FastPMFloat *to)
 /* pm_c2r, pmpfft.c:390-399: in place, unnormalised */
 void pm_c2r(PM *pm, FastPMFloat *inplace)
 {
-    if (pm->NTask != 1) fastpm_raise(-1, "pm_c2r on several GPUs goes through fastpm_solver_compute_force in this build\n");
+    if (pm->NTask != 1) {
+        /* out of place underneath, then back; the plane above the slab is fetched from the x-neighbour right away, so that a CIC
+         * fastpm_readout_local on the result is complete (the reference reads the ghosts of its particles instead) */
+        FastPMFloat *tmp = pm_alloc_noclear(pm, __FILE__, __LINE__);
+        fpm_mesh_c2r(pm, inplace, tmp, NULL);
+        pm_assign(pm, tmp, inplace);
+        pm_free(pm, tmp);
+        fpm_halo_fetch(pm, inplace);
+        return;
+    }
     FPM_MUST(fpm_c2r_ws(pm->mesh, inplace, scratch_of(pm), inplace, NULL));
 }
 

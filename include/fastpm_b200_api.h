@@ -541,6 +541,9 @@ int fastpm_b200_migrate_rounds_max(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
 /* a scratch store with q and rand columns filled by fastpm_store_fill on pm's grid, mirrored to the host (bindings, tests); returns np */
 int64_t fastpm_b200_fill_probe(PM *pm, int64_t np_upper, float *q_host, float *rand_host);
+/* fastpm_paint (CIC) of the CDM store -> pm_r2c -> fastpm_powerspectrum_init_from_delta -> pm_c2r -> fastpm_readout_local into ACC[:, 0],
+ * on one GPU or on the slabs of several: P(k) (Nmesh / 2 bins) and the density read back at this rank's particles; returns np */
+int64_t fastpm_b200_public_mesh_probe(FastPMSolver *fastpm, double a, double *k, double *p, double *nmodes, float *dens_host);
 int fastpm_b200_store_get_column(FastPMStore *p, FastPMColumnTags attribute, void *host_dst, size_t first, size_t count);
 int fastpm_b200_store_set_column(FastPMStore *p, FastPMColumnTags attribute, const void *host_src, size_t first, size_t count);
 /* mesh buffers: copy to / from a host array in the REFERENCE's layouts -- real [x][y][N+2] floats

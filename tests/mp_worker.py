@@ -193,6 +193,18 @@ def extras(rank, world):
     g.write_snapshot(os.path.join(tmp, "mine_sorted"), sort_by_id=True)      # every row at the file position its id gives
     out = [None] * world
     dist.all_gather_object(out, (g.get_column("id"), g.get_column("x"), g.get_column("v"), g.get_column("pgdc")))
+    # the public mesh calls on the slabs (fastpm_paint with its halo exchange, pm_r2c, the P(k) measurement, pm_c2r, readout): what a
+    # user's own density / P(k) code does with libfastpm -- against the reference's paint -> r2c -> P(k) and readout on one rank
+    nb = nc * 2 // 2
+    kk, pp, nm = np.zeros(nb), np.zeros(nb), np.zeros(nb)
+    dens = np.zeros(len(out[rank][0]), dtype=np.float32)
+    g.lib.fastpm_b200_public_mesh_probe.restype = C.c_int64
+    g.lib.fastpm_b200_public_mesh_probe.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n_here = g.lib.fastpm_b200_public_mesh_probe(g.h, 1.0, kk.ctypes.data, pp.ctypes.data, nm.ctypes.data, dens.ctypes.data)
+    assert n_here == len(dens)
+    M0 = float(g.meta["M0"])                      # the store's particle mass: the reference side below paints unit masses
+    probe = [None] * world
+    dist.all_gather_object(probe, (out[rank][0], dens / M0, kk, pp / M0 ** 2, nm))
     g.close()
     if rank == 0:
         ids = np.concatenate([o[0] for o in out])
@@ -204,6 +216,19 @@ def extras(rank, world):
         assert err < 1e-4, err
         assert np.abs(v - want["v"][ro]).max() < 1e-4 * np.abs(want["v"]).max()
         assert np.abs(pg - want_pgdc[ro]).max() < 1e-4 * np.abs(want_pgdc).max()
+        # public mesh chain: the same P(k) on every rank, equal to the reference's of OUR final particles; density at the particles
+        s2 = ref.Session(np_alloc_factor=2.0, **kw)
+        canvas = s2.paint(x, a=1.0)
+        k0, p0, n0 = s2.powerspectrum(s2.r2c(canvas, a=1.0), a=1.0)
+        d0 = s2.readout(canvas, x, a=1.0)
+        s2.close()
+        for r in range(world):
+            assert np.array_equal(probe[r][4], n0)
+            sel = n0 > 0
+            np.testing.assert_allclose(probe[r][3][sel], p0[sel], rtol=2e-5)
+        pid = np.concatenate([q[0] for q in probe])
+        pd = np.concatenate([q[1] for q in probe])[np.argsort(pid)]
+        assert np.abs(pd - d0).max() < 2e-5 * np.abs(d0).max(), np.abs(pd - d0).max()
         # the snapshot: same blocks and attributes, same particles once both are ordered by id
         mine, refd = os.path.join(tmp, "mine"), os.path.join(tmp, "ref")
         assert sorted(os.listdir(os.path.join(mine, "1"))) == sorted(os.listdir(os.path.join(refd, "1")))
