@@ -267,12 +267,13 @@ class Session:
                             acc_std=sc[10:13].copy(), Plin=sc[13], a_x=sc[14], a_v=sc[15], k=k, p=p, nmodes=nm))
         return out
 
-    def fill_probe(self, np_upper):
-        """fastpm_store_fill of a scratch store with q and rand columns -> (q [np][3], rand [np_upper])"""
+    def fill_probe(self, np_upper, as_rank=0):
+        """fastpm_store_fill of a scratch store with q and rand columns -> (q [np][3], rand [np_upper]); as_rank: what MPI_Comm_rank
+        answers meanwhile (selects the seed of the rand stream, store.c:704-708)"""
         q = np.zeros((int(np_upper), 3), dtype=np.float32)
         r = np.zeros(int(np_upper), dtype=np.float32)
-        lib().ref_fill_probe.restype = C.c_int64
-        n = lib().ref_fill_probe(self._h, C.c_int64(int(np_upper)), _p(q), _p(r))
+        lib().ref_fill_probe_as_rank.restype = C.c_int64
+        n = lib().ref_fill_probe_as_rank(self._h, C.c_int(int(as_rank)), C.c_int64(int(np_upper)), _p(q), _p(r))
         return q[:n].copy(), r
 
     # ---- per-kernel

@@ -367,8 +367,13 @@ static void tmp_store(FastPMStore *p, const double *x, int64_t np)
 }
 
 /* fastpm_store_fill (store.c:723-806) of a scratch store with q and rand columns on the particle grid of the LPT mesh */
-int64_t ref_fill_probe(RefSession *s, int64_t np_upper, float *q_out, float *rand_out)
+void ref_set_fake_rank(int r);               /* shims/src/mpi_stub.c */
+int64_t ref_fill_probe_as_rank(RefSession *s, int rank, int64_t np_upper, float *q_out, float *rand_out);
+int64_t ref_fill_probe(RefSession *s, int64_t np_upper, float *q_out, float *rand_out) { return ref_fill_probe_as_rank(s, 0, np_upper, q_out, rand_out); }
+/* the same with MPI_Comm_rank answering `rank` while the store is filled: the seed chain of _fastpm_store_fill_rand for that rank */
+int64_t ref_fill_probe_as_rank(RefSession *s, int rank, int64_t np_upper, float *q_out, float *rand_out)
 {
+    ref_set_fake_rank(rank);
     PM *pm = s->solver->lptpm;
     FastPMStore p[1];
     fastpm_store_init(p, "probe", np_upper, COLUMN_POS | COLUMN_ID | COLUMN_Q | COLUMN_RAND | COLUMN_MASK, FASTPM_MEMORY_HEAP);
@@ -377,6 +382,7 @@ int64_t ref_fill_probe(RefSession *s, int64_t np_upper, float *q_out, float *ran
     memcpy(q_out, p->q, sizeof(p->q[0]) * p->np);
     memcpy(rand_out, p->rand, sizeof(p->rand[0]) * p->np_upper);
     fastpm_store_destroy(p);
+    ref_set_fake_rank(0);
     return np;
 }
 

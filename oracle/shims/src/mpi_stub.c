@@ -17,7 +17,11 @@ static size_t type_size(MPI_Datatype t)
 
 int MPI_Init(int *argc, char ***argv) { (void) argc; (void) argv; return 0; }
 int MPI_Finalize(void) { return 0; }
-int MPI_Comm_rank(MPI_Comm comm, int *rank) { (void) comm; *rank = 0; return 0; }
+/* one rank; a test may ask the reference what it would do AS another rank where that only selects a branch or a seed (the rand
+ * column of store.c:694-720): ref_set_fake_rank() */
+static int fake_rank = 0;
+void ref_set_fake_rank(int r) { fake_rank = r; }
+int MPI_Comm_rank(MPI_Comm comm, int *rank) { (void) comm; *rank = fake_rank; return 0; }
 int MPI_Comm_size(MPI_Comm comm, int *size) { (void) comm; *size = 1; return 0; }
 int MPI_Comm_free(MPI_Comm *comm) { *comm = MPI_COMM_NULL; return 0; }
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *out) { *out = comm; return 0; }

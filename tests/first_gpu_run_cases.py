@@ -274,6 +274,18 @@ def test_store_fill_q_and_rand_columns_match_reference(ref_mod):
     assert n == nc ** 3 == len(q0)
     assert np.array_equal(q1[:n], q0)
     assert np.array_equal(r1, r0) and r0.min() >= 0 and r0.max() < 1 and len(np.unique(r0)) > 0.99 * n_up
+    # the streams of the other ranks (seed = 0x7fffffff times the (8 r)-th deviate of the fixed seed's stream): the device-layer call
+    # against the reference filling the same store while its MPI stub answers as rank r
+    from fastpm_b200 import device
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=2, np_alloc_factor=2.0)
+    for r in (1, 5):
+        _, want = s.fill_probe(nc ** 3 + 300, as_rank=r)
+        buf = device.DeviceBuffer(4 * len(want))
+        device.check(buf.lib.fpm_fill_rand(buf.ptr, len(want), r), "fpm_fill_rand")
+        got = buf.download(np.float32)
+        assert np.array_equal(got, want), r
+        assert not np.array_equal(got, r0[:len(want)])
+    s.close()
 
 
 def test_passive_handler_keeps_the_fused_update(pk_text):
