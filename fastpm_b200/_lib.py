@@ -59,6 +59,9 @@ def load():
     lib.fpm_memcpy_h2d.argtypes = [vp, vp, sz]
     lib.fpm_memcpy_d2h.argtypes = [vp, vp, sz]
     lib.fpm_memcpy_h2d_async.argtypes = [vp, vp, sz]
+    lib.fpm_fill_rand.argtypes = [vp, i64, i32]
+    lib.fpm_cast_f64_to_f32.argtypes = [vp, vp, i64]
+    lib.fpm_shift_positions.argtypes = [vp, i64, dbl, dbl, dbl]
     lib.fpm_memcpy_d2h_async.argtypes = [vp, vp, sz]
     lib.fpm_memcpy_d2d.argtypes = [vp, vp, sz]
     lib.fpm_memset.argtypes = [vp, i32, sz]
