@@ -363,6 +363,7 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
     int wrap = (fpm_pending_wrap == p);                    /* fastpm_decompose left the periodic wrap to the classification pass */
     if (wrap) fpm_pending_wrap = NULL;
     for (int round = 0; ; round++) {
+        if (round + 1 > g_migrate_rounds_max) g_migrate_rounds_max = round + 1;
         int send[MAXR], all[MAXR * MAXR], overflow = 0;
         memset(send, 0, sizeof(send));
         if (fpm_migrate_classify(pm->mesh, (double *) p->x, (int64_t) p->np, send, wrap, &overflow) != 0) fastpm_raise(-1, "%s\n", fpm_last_error());
@@ -398,7 +399,6 @@ int fastpm_store_decompose(FastPMStore *p, fastpm_store_target_func target_func,
         FPM_MUST(fpm_xbarrier());                          /* every rank has pulled: pack buffers may be reused */
         p->np = (size_t) at;
         if (!flags[1]) break;                              /* nobody had more leavers than a pack buffer holds */
-        if (round + 1 > g_migrate_rounds_max) g_migrate_rounds_max = round + 1;
         if (round > 4096) fastpm_raise(-1, "fastpm_b200: particle migration does not converge\n");
     }
     return 0;

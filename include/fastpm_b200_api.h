@@ -536,7 +536,7 @@ int fastpm_b200_local_segment_unlink(const char *name);
 void fastpm_b200_comm_init_local(int rank, int size, const char *segment);
 /* before libfastpm_cleanup in a multi-rank program: waits for every rank, returns the communicator's own device block */
 void fastpm_b200_comm_finalize(void);
-/* the largest number of exchange rounds a fastpm_store_decompose of this process has needed so far (1 unless a pack buffer overflowed) */
+/* the largest number of exchange rounds a fastpm_store_decompose of this process has needed so far (1 unless a pack buffer overflowed; 0 before the first) */
 int fastpm_b200_migrate_rounds_max(void);
 int fastpm_b200_store_set_np(FastPMStore *p, int64_t np);
 /* a scratch store with q and rand columns filled by fastpm_store_fill on pm's grid, mirrored to the host (bindings, tests); returns np */
