@@ -51,6 +51,8 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
 int fpm_shift_launch(double *x, long long np, double s0, double s1, double s2, cudaStream_t st);
 int fpm_cast_f64_f32_launch(float *dst, const double *src, long long n, cudaStream_t st);
+int fpm_id_order_launch(const unsigned long long *id, long long n, unsigned long long id0, unsigned long long *host_counts, cudaStream_t st);
+int fpm_permute_by_id_launch(void *dst, const void *src, const unsigned long long *id, long long n, unsigned long long id0, int elsize, cudaStream_t st);
 int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np, int nops, const double *ops, cudaStream_t st);
 int fpm_lpt_evolve_launch(double *x, float *v, const float *dx1, const float *dx2, double D1, double D2, double Dv1, double Dv2, long long np, cudaStream_t st);
 int fpm_fill_grid_launch(double *x, unsigned long long *id, float *v, int nc, int i0, long long np, double scale, double shift, cudaStream_t st);
@@ -72,6 +74,7 @@ int fpm_set_mode_launch(const FpmMesh *m, float *dk, int ix, int iy, int iz, flo
 void fpm_fft_force_generic(int on);
 int fpm_gadget_fill_launch(const FpmMesh *m, float *dk, int seed, cudaStream_t st);
 void fpm_set_lagrangian_hint(int nc);
+int fpm_get_lagrangian_hint(void);
 int fpm_tile_stats_fetch(unsigned long long out[4]);
 
 // ------------------------------------------------------------------ runtime state
@@ -767,6 +770,22 @@ int fpm_cast_f64_to_f32(float *dst, const double *src, int64_t n)
     return fpm_cast_f64_f32_launch(dst, src, n, g_stream);
 }
 
+// fastpm_sort_snapshot by a dense id (libfastpmio/io.c:860-960) on the device: see particles.cu
+int fpm_id_order_counts(const uint64_t *id, int64_t n, uint64_t id0, uint64_t *host_counts)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    unsigned long long c[2];
+    if (fpm_id_order_launch((const unsigned long long *) id, n, id0, c, g_stream)) return -1;
+    host_counts[0] = c[0]; host_counts[1] = c[1];
+    return 0;
+}
+int fpm_permute_by_id(void *dst, const void *src, const uint64_t *id, int64_t n, uint64_t id0, int elsize)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    if (dst == src) { fpm_set_error("permute by id: out of place only"); return -1; }
+    return fpm_permute_by_id_launch(dst, src, (const unsigned long long *) id, n, id0, elsize, g_stream);
+}
+
 // _fastpm_store_fill_rand (store.c:694-720): uniform deviates of ONE serial RANLUX stream per rank over the np_upper entries of the
 // column.  The seed of rank r is 0x7fffffff times the (8 r)-th deviate of the generator seeded with 1231584 (the fixed seed itself on
 // rank 0), truncated to an integer as gsl_rng_set takes it.  A serial stream cannot be split over CUDA threads: the host draws it,
@@ -873,6 +892,7 @@ int fpm_wrap_paint(const fpm_mesh *m, float *canvas, double *x, int64_t np, doub
 
 // performance hint: stores of exactly nc^3 particles are in fastpm_store_fill order (store.c:756-793); 0 clears it
 int fpm_particle_grid_hint(int nc) { fpm_set_lagrangian_hint(nc); return 0; }
+int fpm_particle_grid_hint_get(void) { return fpm_get_lagrangian_hint(); }
 int fpm_tile_stats(uint64_t *out4) { unsigned long long t[4]; if (fpm_tile_stats_fetch(t)) return -1; for (int i = 0; i < 4; i++) out4[i] = t[i]; return 0; }
 
 int fpm_summary(const void *column, int dtype, int ncomp, int64_t np, double *host_out)

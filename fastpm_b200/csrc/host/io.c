@@ -751,6 +751,56 @@ void fastpm_b200_io_argsort_u64(const uint64_t *key, size_t n, uint64_t *perm)
     if (a != perm) { memcpy(perm, a, sizeof(uint64_t) * n); free(a); } else free(b);
 }
 
+/* the integer cube root of n when n is a cube, else 0 */
+static int cube_root_of(size_t n)
+{
+    int c = (int) (cbrt((double) n) + 0.5);
+    return (c > 0 && (size_t) c * c * c == n) ? c : 0;
+}
+
+/* A store of one rank whose rows are in the order of the Lagrangian ids 0 .. nc^3-1 of fastpm_store_fill (after a sort by id, or read
+ * back from a catalog that was written sorted): the deposit and the gather may walk it in Lagrangian bricks (paint.cu), as they do
+ * for a freshly filled store.  The walk is a permutation of the rows whatever their order, so a wrong guess costs speed only. */
+static void lagrangian_order_hint(const FastPMStore *p)
+{
+    const int nc = cube_root_of(p->np);
+    if (nc >= 8 && nc % 8 == 0) FPM_MUST(fpm_particle_grid_hint(nc));
+}
+
+/* One rank, ids exactly a permutation of 0 .. n-1 (what fastpm_store_fill assigns and nothing on this path changes): the sorted
+ * position of a row is its id, so every column is scattered once on the device (fpm_permute_by_id) through one scratch column
+ * instead of going through the host.  Returns 1 when the store is now in id order, 0 when this path does not apply (ids not dense,
+ * duplicates, no room for the scratch column, FASTPM_B200_HOST_SORT=1): the caller sorts on the host as before. */
+static int sort_by_dense_id_on_device(FastPMStore *p)
+{
+    const size_t n = p->np;
+    const char *off = getenv("FASTPM_B200_HOST_SORT");
+    if (off && atoi(off)) return 0;
+    if (n == 0) return 1;
+    uint64_t cnt[2];
+    FPM_MUST(fpm_id_order_counts(p->id, (int64_t) n, 0, cnt));
+    if (cnt[0]) return 0;
+    if (cnt[1] == 0) return 1;                               /* already in id order */
+    size_t maxel = sizeof(uint64_t);
+    for (int ci = 0; ci < 32; ci++) if (p->columns[ci] && p->_column_info[ci].elsize > maxel) maxel = p->_column_info[ci].elsize;
+    void *scratch = fpm_malloc(maxel * n);
+    if (!scratch) return 0;
+    /* duplicates leave a slot of the scattered id column unwritten: it keeps the fill pattern and shows up as displaced */
+    FPM_MUST(fpm_memset(scratch, 0xff, sizeof(uint64_t) * n));
+    FPM_MUST(fpm_permute_by_id(scratch, p->id, p->id, (int64_t) n, 0, (int) sizeof(uint64_t)));
+    FPM_MUST(fpm_id_order_counts(scratch, (int64_t) n, 0, cnt));
+    if (cnt[0] || cnt[1]) { fpm_free(scratch); return 0; }
+    for (int pass = 0; pass < 2; pass++)                     /* the id column last: it is the key of every scatter */
+        for (int ci = 0; ci < 32; ci++) {
+            if (!p->columns[ci] || (pass == 1) != (p->columns[ci] == (void *) p->id)) continue;
+            const size_t el = p->_column_info[ci].elsize;
+            FPM_MUST(fpm_permute_by_id(scratch, p->columns[ci], p->id, (int64_t) n, 0, (int) el));
+            FPM_MUST(fpm_memcpy_d2d(p->columns[ci], scratch, el * n));
+        }
+    fpm_free(scratch);
+    return 1;
+}
+
 void fastpm_sort_snapshot(FastPMStore *p, MPI_Comm comm, FastPMSnapshotSorter sorter, int redistribute)
 {
     (void) redistribute;
@@ -758,6 +808,11 @@ void fastpm_sort_snapshot(FastPMStore *p, MPI_Comm comm, FastPMSnapshotSorter so
     if (!p->id) fastpm_raise(-1, "fastpm_sort_snapshot: the store has no id column\n");
     fpm_store_flush(p);
     const size_t n = p->np;
+    if (fpm_comm_size(comm) == 1 && sort_by_dense_id_on_device(p)) {
+        sorted_by_dense_id.ids = NULL;
+        lagrangian_order_hint(p);
+        return;
+    }
     uint64_t *key = malloc(sizeof(uint64_t) * (n ? n : 1)), *perm = malloc(sizeof(uint64_t) * (n ? n : 1));
     FPM_MUST(fpm_memcpy_d2h(key, p->id, sizeof(uint64_t) * n));
     fastpm_b200_io_argsort_u64(key, n, perm);
@@ -810,6 +865,12 @@ double fastpm_b200_read_snapshot(FastPMSolver *fastpm, const char *filebase)
     FastPMStore *p = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM), po[1];
     fastpm_set_species_snapshot(fastpm, p, NULL, NULL, po, 1.0);
     fastpm_store_read(po, filebase, 0, fastpm->comm);
+    if (fpm_comm_size(fastpm->comm) == 1 && po->id && po->np) {
+        /* a catalog written sorted by id (the command line's default): the rows are back in Lagrangian order */
+        uint64_t cnt[2];
+        FPM_MUST(fpm_id_order_counts(po->id, (int64_t) po->np, 0, cnt));
+        if (cnt[0] == 0 && cnt[1] == 0) lagrangian_order_hint(po);
+    }
     if (po->meta.a_x != po->meta.a_v) fastpm_raise(-1, "Snapshot velocity and position are out of sync. a_x =% g, a_v = %g.\n", po->meta.a_x, po->meta.a_v);
     fastpm_unset_species_snapshot(fastpm, p, NULL, NULL, po, po->meta.a_x);
     return a_restart;

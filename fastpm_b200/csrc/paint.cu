@@ -680,6 +680,7 @@ void fpm_set_lagrangian_hint(int nc)
     if (nc < 0) nc = -nc;
     g_lag_nc = (nc > 0 && nc % 8 == 0 && !off) ? nc : 0;
 }
+int fpm_get_lagrangian_hint(void) { return g_lag_nc; }
 // Bricks pay off only when the linear walk's footprint (~24 mesh planes) no longer fits the 126 MB L2: measured on B200, they
 // cost 15 % at N = 1024 (4.3 MB planes, linear walk already L2 resident) and gain 25 % at N = 2048 (17 MB planes).
 // Returns the number of leading 256-particle blocks that use the brick mapping (0: linear walk).

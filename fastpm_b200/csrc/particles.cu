@@ -247,6 +247,40 @@ __global__ void __launch_bounds__(256) summary_kernel(const T *col, long long np
     }
 }
 
+// ------------------------------------------------------------------ sort by a dense particle id without sorting
+// fastpm_sort_snapshot (libfastpmio/io.c:860-960) orders a catalog by id with a distributed radix sort.  The ids of this path are the
+// Lagrangian indices 0 .. n-1 (store.c:676-692), so the sorted position of a row IS its id: one scatter per column replaces the sort.
+// counts[0] += rows whose id lies outside [id0, id0 + n), counts[1] += rows with id[i] != id0 + i (0: the store is in id order)
+__global__ void __launch_bounds__(256) id_order_kernel(const unsigned long long *__restrict__ id, long long n, unsigned long long id0,
+        unsigned long long *counts)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    unsigned long long outside = 0, displaced = 0;
+    for (; i < n; i += stride) {
+        const unsigned long long j = id[i] - id0;                   // unsigned: an id below id0 wraps to a huge value
+        outside += j >= (unsigned long long) n;
+        displaced += j != (unsigned long long) i;
+    }
+    if (outside) atomicAdd(counts, outside);
+    if (displaced) atomicAdd(counts + 1, displaced);
+}
+
+// dst[id[i] - id0] = src[i] for rows of `units` elements of T (T = 4-byte words, or bytes for the odd column); reads are coalesced,
+// every row is written whole by `units` neighbouring threads
+template <typename T>
+__global__ void __launch_bounds__(256) permute_by_id_kernel(T *__restrict__ dst, const T *__restrict__ src,
+        const unsigned long long *__restrict__ id, long long total, int units, unsigned long long id0)
+{
+    long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const long long i = t / units;
+        const int w = (int) (t - i * units);
+        dst[(long long) (id[i] - id0) * units + w] = src[t];
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 static inline unsigned stream_grid(long long n)
 {
@@ -371,6 +405,37 @@ int fpm_summary_launch(const void *col, int dtype, int ncomp, long long np, doub
         }
     free(h);
     FPM_CUDA_OK(cudaFree(d_partial));
+    return 0;
+}
+
+int fpm_id_order_launch(const unsigned long long *id, long long n, unsigned long long id0, unsigned long long *host_counts, cudaStream_t st)
+{
+    host_counts[0] = host_counts[1] = 0;
+    if (n <= 0) return 0;
+    unsigned long long *d_counts = nullptr;
+    FPM_CUDA_OK(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
+    FPM_CUDA_OK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), st));
+    FPM_TIMED(FPM_K_OTHER, st, (id_order_kernel<<<stream_grid(n), 256, 0, st>>>(id, n, id0, d_counts)));
+    FPM_CHECK_LAUNCH();
+    FPM_CUDA_OK(cudaMemcpyAsync(host_counts, d_counts, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    FPM_CUDA_OK(cudaFree(d_counts));
+    return 0;
+}
+
+// every id must lie in [id0, id0 + n) (fpm_id_order_launch: counts[0] == 0), or the scatter writes outside dst
+int fpm_permute_by_id_launch(void *dst, const void *src, const unsigned long long *id, long long n, unsigned long long id0, int elsize, cudaStream_t st)
+{
+    if (elsize < 1) { fpm_set_error("permute by id: element size %d", elsize); return -1; }
+    if (n <= 0) return 0;
+    if (elsize % 4 == 0 && (uintptr_t) dst % 4 == 0 && (uintptr_t) src % 4 == 0) {
+        const long long total = n * (elsize / 4);
+        FPM_TIMED(FPM_K_OTHER, st, (permute_by_id_kernel<unsigned int><<<stream_grid(total), 256, 0, st>>>((unsigned int *) dst, (const unsigned int *) src, id, total, elsize / 4, id0)));
+    } else {
+        const long long total = n * elsize;
+        FPM_TIMED(FPM_K_OTHER, st, (permute_by_id_kernel<unsigned char><<<stream_grid(total), 256, 0, st>>>((unsigned char *) dst, (const unsigned char *) src, id, total, elsize, id0)));
+    }
+    FPM_CHECK_LAUNCH();
     return 0;
 }
 #endif

@@ -103,6 +103,9 @@ int fpm_paint(const fpm_mesh *m, float *canvas, const double *x, int64_t np,
  * bricks for L2 locality when the mesh is large.  nc = 0 clears the hint.  Results do not depend on it (any traversal order
  * is valid, every particle is visited exactly once). */
 int fpm_particle_grid_hint(int nc);
+/* the hint in force (0: none).  Set by fastpm_store_fill, by fastpm_sort_snapshot on one rank and by a restart from a catalog in id
+ * order (csrc/host/io.c); FASTPM_B200_NO_BRICKS=1 keeps it at 0. */
+int fpm_particle_grid_hint_get(void);
 /* With the hint set and Nmesh / nc <= 2.5 the deposit and the gather run through shared-memory tiles: a CTA takes an 8 x 8 x 8
  * brick of the particle grid, accumulates / stages the box of mesh cells it touches in shared memory and moves that box to / from
  * the mesh in aligned 16-byte groups; particles far from their brick's box (and stores that are not in grid order) use global
@@ -243,6 +246,13 @@ int fpm_wrap_check(void);
 int fpm_shift_positions(double *x, int64_t np, double s0, double s1, double s2);
 /* the q column of a freshly filled store: dst[i] = (float) src[i] (store.c:784-789) */
 int fpm_cast_f64_to_f32(float *dst, const double *src, int64_t n);
+/* ---- fastpm_sort_snapshot by particle id (libfastpmio/io.c:860-960, FastPMSnapshotSortByID) when the ids are dense: the sorted
+ * position of a row is id - id0, so one scatter per column replaces the reference's distributed radix sort (mpsort).
+ * fpm_id_order_counts: host_counts[0] = rows whose id lies outside [id0, id0 + n), host_counts[1] = rows with id[i] != id0 + i
+ * (0: already in id order -- for the Lagrangian ids of fastpm_store_fill, store.c:676-692, the order paint / readout walk fastest).
+ * fpm_permute_by_id: dst[id[i] - id0] = src[i] for n rows of elsize bytes, out of place; needs host_counts[0] == 0. */
+int fpm_id_order_counts(const uint64_t *id, int64_t n, uint64_t id0, uint64_t *host_counts);
+int fpm_permute_by_id(void *dst, const void *src, const uint64_t *id, int64_t n, uint64_t id0, int elsize);
 /* the rand column, _fastpm_store_fill_rand store.c:694-720: n deviates of this rank's serial RANLUX stream (drawn on the host, copied up) */
 int fpm_fill_rand(float *rand_dev, int64_t n, int rank);
 /* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;

@@ -221,6 +221,130 @@ def test_snapshot_files_and_restart_match_reference(ref_mod, pk_text, tmp_path):
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
 
 
+def test_permute_by_dense_id_kernels():
+    """fpm_id_order_counts / fpm_permute_by_id (the sort by a dense particle id of fastpm_sort_snapshot, libfastpmio/io.c:860-960, as
+    one scatter per column): rows of 24, 12, 8 and 1 bytes, a non-zero first id, ids outside the range, duplicates."""
+    import ctypes as C
+    from fastpm_b200 import device as dev
+    lib = dev._lib.require_device()
+    rng = np.random.default_rng(5)
+    n, id0 = 70001, 12345
+
+    def counts(ids, first):
+        d, out = dev.DeviceBuffer.from_host(ids), np.zeros(2, dtype=np.uint64)
+        dev._lib.check(lib.fpm_id_order_counts(d.ptr, len(ids), first, out.ctypes.data), "fpm_id_order_counts")
+        return int(out[0]), int(out[1])
+
+    perm = rng.permutation(n).astype(np.uint64)
+    ids = perm + np.uint64(id0)
+    assert counts(np.arange(n, dtype=np.uint64) + np.uint64(id0), id0) == (0, 0)
+    assert counts(ids, id0) == (0, int((perm != np.arange(n)).sum()))
+    assert counts(ids, 0)[0] == int((ids >= n).sum())                       # ids beyond the range
+    assert counts(ids, id0 + 7)[0] == 7                                     # ids below the first one wrap around
+    assert counts(np.zeros(0, dtype=np.uint64), 0) == (0, 0)
+    idd = dev.DeviceBuffer.from_host(ids)
+    for dtype, nm in ((np.float64, 3), (np.float32, 3), (np.uint64, 1), (np.uint8, 1), (np.uint8, 3)):
+        col = rng.integers(0, 250, size=(n, nm)).astype(dtype) if dtype == np.uint8 else rng.normal(size=(n, nm)).astype(dtype)
+        if dtype == np.uint64:
+            col = ids.reshape(n, 1).copy()
+        src, dst = dev.DeviceBuffer.from_host(col), dev.DeviceBuffer(col.nbytes)
+        dev._lib.check(lib.fpm_permute_by_id(dst.ptr, src.ptr, idd.ptr, n, id0, col.itemsize * nm), "fpm_permute_by_id")
+        want = np.empty_like(col)
+        want[perm.astype(np.int64)] = col
+        assert np.array_equal(dst.download(dtype).reshape(n, nm), want)
+        if dtype == np.uint64:
+            assert counts(want.ravel(), id0) == (0, 0)
+    # a duplicate id leaves one slot of the scattered id column unwritten: it shows up as displaced
+    dup = ids.copy()
+    dup[17] = dup[4711]
+    scat = dev.DeviceBuffer(8 * n)
+    dev._lib.check(lib.fpm_memset(scat.ptr, 0xff, 8 * n), "fpm_memset")
+    dupd = dev.DeviceBuffer.from_host(dup)
+    dev._lib.check(lib.fpm_permute_by_id(scat.ptr, dupd.ptr, dupd.ptr, n, id0, 8), "fpm_permute_by_id")
+    c = counts(scat.download(np.uint64), id0)
+    assert c[0] == 1 and c[1] == 1
+    assert lib.fpm_permute_by_id(scat.ptr, scat.ptr, dupd.ptr, n, id0, 8) != 0          # in place is refused
+
+
+def test_sorted_snapshot_of_a_shuffled_store(pk_text, tmp_path):
+    """fastpm_sort_snapshot(FastPMSnapshotSortByID) on one rank (libfastpmio/io.c:860-960; the command line's default sort_snapshot):
+    a store in arbitrary order is written as the same catalog as the store in id order -- by the device scatter (dense ids) and,
+    with FASTPM_B200_HOST_SORT=1 or ids that are not dense, by the radix sort on the host; the store itself ends up in id order."""
+    import filecmp
+    import os
+    from fastpm_b200.solver import Solver
+    nc, L = _nc(16), 2.0 * _nc(16)
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+    kk, pp = np.loadtxt(pk_text.splitlines(), unpack=True)
+    g.setup_ic(11, kk, pp, 0.1)
+    g.evolve(np.linspace(0.1, 0.3, 2))
+    names = [c for c in ("x", "v", "id", "dx1", "dx2", "acc") if g.column_ptr(c)]
+    assert set(names) >= {"x", "v", "id", "acc"}
+    cols = {c: g.get_column(c) for c in names}
+    n = g.np
+    assert np.array_equal(cols["id"], np.arange(n, dtype=np.uint64))
+    plain = str(tmp_path / "plain")
+    g.write_snapshot(plain)
+    perm = np.random.default_rng(3).permutation(n)
+    blocks = [("Position", np.float32, 3), ("Velocity", np.float32, 3), ("ID", np.uint64, 1)]
+
+    launches = {}
+
+    def shuffled_run(tag, env_host, break_density=False):
+        for c in names:
+            g.set_column(c, cols[c][perm])
+        if break_density:                     # ids 0, 2, 4, ...: sorted order is unchanged, but the scatter does not apply
+            g.set_column("id", (cols["id"] * np.uint64(2))[perm])
+        out = str(tmp_path / tag)
+        old = os.environ.pop("FASTPM_B200_HOST_SORT", None)
+        if env_host:
+            os.environ["FASTPM_B200_HOST_SORT"] = "1"
+        before = g.lib.fpm_kernel_launch_count()
+        try:
+            g.write_snapshot(out, sort_by_id=True)
+        finally:
+            launches[tag] = g.lib.fpm_kernel_launch_count() - before
+            os.environ.pop("FASTPM_B200_HOST_SORT", None)
+            if old is not None:
+                os.environ["FASTPM_B200_HOST_SORT"] = old
+        want_id = cols["id"] * np.uint64(2) if break_density else cols["id"]
+        assert np.array_equal(g.get_column("id"), want_id)
+        for c in names[3:]:
+            assert np.array_equal(g.get_column(c), cols[c]), c
+        assert np.array_equal(np.mod(g.get_column("x"), L), np.mod(cols["x"], L))      # x comes back wrapped into the box
+        return out
+
+    dev_dir, host_dir, sparse_dir = shuffled_run("dev", False), shuffled_run("host", True), shuffled_run("sparse", False, True)
+    # the dense ids went through the scatter kernels (two order checks, the trial scatter of the ids, one scatter per column); the
+    # other two runs were sorted on the host
+    assert launches["dev"] - launches["host"] >= 3 + len(names) and launches["sparse"] - launches["host"] == 1, launches
+    for name, dtype, nm in blocks:
+        a = _read_block(dev_dir, name, dtype, nm)
+        assert np.array_equal(a, _read_block(host_dir, name, dtype, nm)), name
+        if name != "ID":
+            assert np.array_equal(a, _read_block(sparse_dir, name, dtype, nm)), name
+        if name != "Velocity":                # the plain snapshot's unit conversion and its inverse may move the last bit of v
+            assert np.array_equal(a, _read_block(plain, name, dtype, nm)), name
+    va, vb = _read_block(dev_dir, "Velocity", np.float32, 3), _read_block(plain, "Velocity", np.float32, 3)
+    assert np.abs(va - vb).max() <= 1e-6 * np.abs(vb).max()
+    assert filecmp.cmp(os.path.join(dev_dir, "1", "attr-v2"), os.path.join(host_dir, "1", "attr-v2"), shallow=False)
+    # a catalog in id order read back on one rank is in Lagrangian order again: the deposit / gather get their brick walk back
+    # (a speed hint only); a catalog in any other order leaves the hint alone
+    assert g.lib.fpm_particle_grid_hint_get() == nc
+    for c in names:
+        g.set_column(c, cols[c][perm])
+    unsorted_dir = str(tmp_path / "unsorted")
+    g.write_snapshot(unsorted_dir)
+    g.close()
+    for catalog, want in ((unsorted_dir, 0), (dev_dir, nc)):
+        g = Solver(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+        g.lib.fpm_particle_grid_hint(0)
+        g.read_snapshot(catalog)
+        assert g.lib.fpm_particle_grid_hint_get() == want, catalog
+        assert np.array_equal(g.get_column("id"), cols["id"][perm] if want == 0 else cols["id"])
+        g.close()
+
+
 @pytest.mark.parametrize("softening", ["gaussian", "two_third", "gaussian36"])
 def test_force_softening_matches_reference(ref_mod, pk_text, softening):
     """Row N4 (softening kernels, gravity.c:244-270): a short run with the dealiasing sweep on delta_k switched on."""
