@@ -784,6 +784,7 @@ static int sort_by_dense_id_on_device(FastPMStore *p)
     size_t maxel = sizeof(uint64_t);
     for (int ci = 0; ci < 32; ci++) if (p->columns[ci] && p->_column_info[ci].elsize > maxel) maxel = p->_column_info[ci].elsize;
     void *scratch = fpm_malloc(maxel * n);
+    if (!scratch) { fastpm_b200_memory_trim(); scratch = fpm_malloc(maxel * n); }      /* cached mesh buffers make room */
     if (!scratch) return 0;
     /* duplicates leave a slot of the scattered id column unwritten: it keeps the fill pattern and shows up as displaced */
     FPM_MUST(fpm_memset(scratch, 0xff, sizeof(uint64_t) * n));

@@ -110,6 +110,8 @@ void *fastpm_memory_alloc_details(FastPMMemory *m, const char *name, size_t s, e
 void fastpm_memory_dump_status_str(FastPMMemory *m, char *buf, int n);
 #define fastpm_memory_alloc(m, name, s, loc) fastpm_memory_alloc_details(m, name, s, loc, __FILE__, __LINE__)
 FastPMMemory *_libfastpm_get_gmem(void);
+/* freed mesh buffers are kept by size so that no cudaMalloc happens inside a step (csrc/host/support.c): this returns them to the device */
+void fastpm_b200_memory_trim(void);
 
 /* ------------------------------------------------------------------ [logging.h:16-79] */
 enum FastPMLogLevel { ERROR = 100, INFO = 1 };
