@@ -182,6 +182,29 @@ def test_product_fails_loudly_without_a_device(lib):
     assert b"CUDA device" in lib.fpm_last_error()
 
 
+def test_product_never_reaches_for_the_oracle():
+    """oracle/ is test infrastructure: nothing under fastpm_b200/ imports it, opens it or names one of its files (comments may
+    mention it), and the shipped library has no dependency on anything under oracle/ or tests/."""
+    import re
+    import subprocess
+    pat = re.compile(r"(^\s*(from|import)\s+oracle\b)|(oracle[/.](_ref|ref|port|shims))|(libfastpm_ref)|(liboracle_port)")
+    hits = []
+    for d, _, fs in os.walk(os.path.join(ROOT, "fastpm_b200")):
+        if os.path.basename(d) in ("build", "_build", "__pycache__"):
+            continue
+        for f in fs:
+            if not f.endswith((".py", ".c", ".h", ".cu", ".cuh", ".lua")) and f != "Makefile":
+                continue
+            for n, line in enumerate(open(os.path.join(d, f), errors="replace"), 1):
+                code = line.split("#")[0] if f.endswith(".py") else line
+                if pat.search(code) and not code.lstrip().startswith(("//", "*", "/*")):
+                    hits.append("%s:%d: %s" % (os.path.relpath(os.path.join(d, f), ROOT), n, line.strip()))
+    assert not hits, hits
+    so = os.path.join(ROOT, "fastpm_b200", "libfastpm_b200.so")
+    needed = subprocess.run(["ldd", so], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in needed and "libfastpm_ref" not in needed and "/tests/" not in needed, needed
+
+
 def test_symmetric_arena_placement_is_deterministic(lib):
     """The multi-GPU buffers of every rank live at the same offsets of a per-process arena (csrc/host/support.c): the
     placement policy (first fit, 1 MiB granular, gap reuse, clean failure when full) is checked on the host."""
