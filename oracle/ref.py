@@ -252,6 +252,16 @@ class Session:
         v, id, dx1, dx2, meta = c(v, np.float32), c(id, np.uint64), c(dx1, np.float32), c(dx2, np.float32), c(meta, np.float64)
         lib().ref_set_particles(self._h, C.c_int64(len(x)), _p(x), _p(v), _p(id), _p(dx1), _p(dx2), _p(meta))
 
+    def wrap(self):
+        """fastpm_store_wrap of the session's particles into [0, boxsize]"""
+        lib().ref_wrap(self._h)
+
+    def summary(self, column):
+        """fastpm_store_summary of the 3-component column 'x' or 'v': dict of min, max, mean, std"""
+        out = np.zeros(12)
+        lib().ref_summary(self._h, C.c_int({"x": 1 << 1, "v": 1 << 3}[column]), _p(out))
+        return dict(min=out[0:3], max=out[3:6], mean=out[6:9], std=out[9:12])
+
     # ---- evolve
     def evolve(self, time_step):
         ts = np.ascontiguousarray(time_step, dtype=np.float64)

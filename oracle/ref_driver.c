@@ -327,6 +327,20 @@ void ref_set_particles(RefSession *s, int64_t np, const double *x, const float *
     if (meta) { p->meta.a_x = meta[0]; p->meta.a_v = meta[1]; p->meta.M0 = meta[2]; }
 }
 
+/* fastpm_store_wrap (store.c:447-475) on the session's particles, and fastpm_store_summary (store.c:808-909) of one column:
+ * out[0..2] = min, out[3..5] = max, out[6..8] = mean, out[9..11] = std ('<', '>', '-', 's') */
+void ref_wrap(RefSession *s)
+{
+    FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
+    fastpm_store_wrap(p, pm_boxsize(s->solver->basepm));
+}
+
+void ref_summary(RefSession *s, int column_tag, double *out)
+{
+    FastPMStore *p = fastpm_solver_get_species(s->solver, FASTPM_SPECIES_CDM);
+    fastpm_store_summary(p, (FastPMColumnTags) column_tag, MPI_COMM_WORLD, "<>-s", out, out + 3, out + 6, out + 9);
+}
+
 /* ------------------------------------------------------------------ evolve */
 double ref_evolve(RefSession *s, const double *time_step, int nstep)
 {

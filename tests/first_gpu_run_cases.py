@@ -221,6 +221,38 @@ def test_snapshot_files_and_restart_match_reference(ref_mod, pk_text, tmp_path):
     assert np.abs(v - want["v"]).max() < 1e-4 * np.abs(want["v"]).max()
 
 
+def test_wrap_and_summary_match_reference(ref_mod):
+    """Rows a3 and a16 of SURVEY.md section 8 against the reference itself: fpm_wrap == fastpm_store_wrap (store.c:447-475) bit for bit
+    (remainder() is exact), positions on the box faces, at exact multiples of the box and up to 9999 boxes away included; fpm_summary
+    == fastpm_store_summary (store.c:808-909): extrema exact, mean and deviation to the order of summation."""
+    from fastpm_b200 import device as dev
+    lib = dev._lib.require_device()
+    nc, L = 16, 50.0
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", np_alloc_factor=2.0)
+    rng = np.random.default_rng(3)
+    n = nc ** 3
+    x = rng.uniform(-3 * L, 4 * L, size=(n, 3))
+    x[0], x[1], x[2], x[3] = [L, -L, 0.0], [2 * L, -0.0, 9999.5 * L], [-9999.25 * L, 1e-300, -1e-300], [np.nextafter(L, 0), np.nextafter(L, 2 * L), L / 2]
+    x[4:1000] = np.round(x[4:1000] / (L / 8)) * (L / 8)                    # many exact multiples of the cell size and of the box
+    v = rng.normal(size=(n, 3)).astype(np.float32) * 3
+    s.set_particles(x, v=v, id=np.arange(n, dtype=np.uint64))
+    s.wrap()
+    want = s.get_particles()["x"]
+    xd = dev.DeviceBuffer.from_host(x)
+    dev.check(lib.fpm_wrap(xd.ptr, n, L), "fpm_wrap")
+    assert lib.fpm_wrap_check() == 0
+    got = xd.download(np.float64).reshape(n, 3)
+    assert np.array_equal(got, want) and np.array_equal(np.signbit(got), np.signbit(want))
+    assert got.min() >= 0 and got.max() <= L
+    vd = dev.DeviceBuffer.from_host(v)
+    for col, buf, dtype in (("x", xd, np.float64), ("v", vd, np.float32)):
+        a, b = dev.summary(buf, dtype, 3, n), s.summary(col)
+        assert np.array_equal(a["min"], b["min"]) and np.array_equal(a["max"], b["max"]), col
+        np.testing.assert_allclose(a["mean"], b["mean"], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(a["std"], b["std"], rtol=1e-11)
+    s.close()
+
+
 def test_permute_by_dense_id_kernels():
     """fpm_id_order_counts / fpm_permute_by_id (the sort by a dense particle id of fastpm_sort_snapshot, libfastpmio/io.c:860-960, as
     one scatter per column): rows of 24, 12, 8 and 1 bytes, a non-zero first id, ids outside the range, duplicates."""

@@ -36,7 +36,7 @@ GROUPS = [
      "test_device_ic_chain_matches_reference", "test_pgd_correction_matches_reference"],
     ["test_force_softening_matches_reference", "test_non_cic_painter_matches_reference", "test_shifted_ics_match_reference"],
     ["test_passive_handler_keeps_the_fused_update", "test_store_fill_q_and_rand_columns_match_reference", "test_permute_by_dense_id_kernels",
-     "test_sorted_snapshot_of_a_shuffled_store"],
+     "test_wrap_and_summary_match_reference", "test_sorted_snapshot_of_a_shuffled_store"],
     ["test_snapshot_files_and_restart_match_reference", "test_snapshots_during_evolve_match_reference"],
     ["test_cli_run_loop_program_matches_reference"],
 ]
