@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "fpm_paint", "fpm_readout", "fpm_readout3", "fpm_readout_pack3", "fpm_paint_window", "fpm_readout_window", "fpm_paint_window_ex", "fpm_readout_window_ex", "fpm_window_halo_planes", "fpm_particle_grid_hint", "fpm_tile_stats", "fpm_r2c", "fpm_r2c_ws", "fpm_c2r", "fpm_c2r_ws", "fpm_fft_set_generic", "fpm_transfer_for_kernel",
     "fpm_apply_transfer", "fpm_apply_decic", "fpm_decic_defer", "fpm_decic_cancel", "fpm_sync_deferred", "fpm_apply_pgd_transfer", "fpm_apply_radial", "fpm_remove_variance", "fpm_apply_axis_factors", "fpm_scale", "fpm_divide", "fpm_muladd", "fpm_set_mode",
     "fpm_induce_correlation", "fpm_fill_gaussian_gadget", "fpm_fill_whitenoise", "fpm_powerspectrum", "fpm_powerspectrum_sums", "fpm_cross_powerspectrum_sums",
-    "fpm_kick", "fpm_drift", "fpm_update_fused", "fpm_pgd_shift", "fpm_wrap", "fpm_wrap_paint", "fpm_wrap_check", "fpm_shift_positions", "fpm_cast_f64_to_f32", "fpm_particle_grid_hint_get", "fpm_id_order_counts", "fpm_permute_by_id", "fpm_fill_rand", "fpm_summary", "fpm_fill_grid", "fpm_lpt_evolve",
+    "fpm_kick", "fpm_drift", "fpm_update_fused", "fpm_pgd_shift", "fpm_wrap", "fpm_wrap_paint", "fpm_wrap_check", "fpm_shift_positions", "fpm_cast_f64_to_f32", "fpm_particle_grid_hint_get", "fpm_id_order_counts", "fpm_subsample_mask", "fpm_mask_scan", "fpm_compact_rows", "fpm_gather_rows", "fpm_permute_by_id", "fpm_fill_rand", "fpm_summary", "fpm_fill_grid", "fpm_lpt_evolve",
 ]
 
 
@@ -63,6 +63,10 @@ def load():
     lib.fpm_cast_f64_to_f32.argtypes = [vp, vp, i64]
     lib.fpm_id_order_counts.argtypes = [vp, i64, C.c_uint64, vp]
     lib.fpm_permute_by_id.argtypes = [vp, vp, vp, i64, C.c_uint64, i32]
+    lib.fpm_subsample_mask.argtypes = [vp, vp, dbl, i64, vp]
+    lib.fpm_mask_scan.argtypes = [vp, i64, vp, vp]
+    lib.fpm_compact_rows.argtypes = [vp, vp, vp, vp, i64, i32]
+    lib.fpm_gather_rows.argtypes = [vp, vp, vp, i64, i32]
     lib.fpm_shift_positions.argtypes = [vp, i64, dbl, dbl, dbl]
     lib.fpm_memcpy_d2h_async.argtypes = [vp, vp, sz]
     lib.fpm_memcpy_d2d.argtypes = [vp, vp, sz]

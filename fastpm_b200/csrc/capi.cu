@@ -51,6 +51,10 @@ int fpm_drift_launch(double *x_out, const double *x_in, const float *v, const fl
 int fpm_wrap_launch(double *x, long long np, double L, int *d_bad, cudaStream_t st);
 int fpm_shift_launch(double *x, long long np, double s0, double s1, double s2, cudaStream_t st);
 int fpm_cast_f64_f32_launch(float *dst, const double *src, long long n, cudaStream_t st);
+int fpm_subsample_mask_launch(const float *rnd, const double *fraction_each, double fraction, long long n, unsigned char *mask, cudaStream_t st);
+int fpm_mask_scan_launch(const unsigned char *mask, long long n, long long *dest, long long *host_total, cudaStream_t st);
+int fpm_compact_rows_launch(void *dst, const void *src, const unsigned char *mask, const long long *dest, long long n, int elsize, cudaStream_t st);
+int fpm_gather_rows_launch(void *dst, const void *src, const int *ind, long long n, int elsize, cudaStream_t st);
 int fpm_id_order_launch(const unsigned long long *id, long long n, unsigned long long id0, unsigned long long *host_counts, cudaStream_t st);
 int fpm_permute_by_id_launch(void *dst, const void *src, const unsigned long long *id, long long n, unsigned long long id0, int elsize, cudaStream_t st);
 int fpm_fused_update_launch(double *x, float *v, const float *acc, const float *dx1, const float *dx2, long long np, int nops, const double *ops, cudaStream_t st);
@@ -778,6 +782,32 @@ int fpm_id_order_counts(const uint64_t *id, int64_t n, uint64_t id0, uint64_t *h
     if (fpm_id_order_launch((const unsigned long long *) id, n, id0, c, g_stream)) return -1;
     host_counts[0] = c[0]; host_counts[1] = c[1];
     return 0;
+}
+// sub-sampling and whole-row moves of a store (store.c:380-412, 967-1034): see particles.cu
+int fpm_subsample_mask(const float *rand_dev, const double *fraction_each_dev, double fraction, int64_t n, uint8_t *mask)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    return fpm_subsample_mask_launch(rand_dev, fraction_each_dev, fraction, n, mask, g_stream);
+}
+int fpm_mask_scan(const uint8_t *mask, int64_t n, int64_t *dest, int64_t *host_total)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    long long total = 0;
+    if (fpm_mask_scan_launch(mask, n, (long long *) dest, &total, g_stream)) return -1;
+    *host_total = total;
+    return 0;
+}
+int fpm_compact_rows(void *dst, const void *src, const uint8_t *mask, const int64_t *dest, int64_t n, int elsize)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    if (dst == src) { fpm_set_error("compact rows: out of place only"); return -1; }
+    return fpm_compact_rows_launch(dst, src, mask, (const long long *) dest, n, elsize, g_stream);
+}
+int fpm_gather_rows(void *dst, const void *src, const int32_t *ind, int64_t n, int elsize)
+{
+    if (ensure_init() || fence_if_requested()) return -1;
+    if (dst == src) { fpm_set_error("gather rows: out of place only"); return -1; }
+    return fpm_gather_rows_launch(dst, src, ind, n, elsize, g_stream);
 }
 int fpm_permute_by_id(void *dst, const void *src, const uint64_t *id, int64_t n, uint64_t id0, int elsize)
 {

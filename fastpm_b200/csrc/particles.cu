@@ -281,6 +281,65 @@ __global__ void __launch_bounds__(256) permute_by_id_kernel(T *__restrict__ dst,
     }
 }
 
+// ------------------------------------------------------------------ sub-sampling and whole-row moves (store.c:380-412, 967-1034)
+// mask[i] = fraction >= 1 || rand[i] <= fraction (store.c:975-979; fraction_each: one fraction per particle, store.c:991-995)
+__global__ void __launch_bounds__(256) subsample_mask_kernel(const float *__restrict__ rnd, const double *__restrict__ fraction_each, double fraction,
+        long long n, unsigned char *__restrict__ mask)
+{
+    long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double f = fraction_each ? fraction_each[i] : fraction;
+        const double rand_i = rnd[i];
+        mask[i] = (f >= 1 || rand_i <= f) ? 1 : 0;
+    }
+}
+
+// Stable compaction = exclusive prefix sum of the mask.  Every thread owns a contiguous segment of `seg` rows: first pass counts,
+// the (few) per-thread counts are scanned on the host, second pass writes dest[i] = rows kept before row i.
+__global__ void __launch_bounds__(256) mask_count_kernel(const unsigned char *__restrict__ mask, long long n, long long seg, long long *__restrict__ counts)
+{
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long b = t * seg, e = b + seg < n ? b + seg : n;
+    long long c = 0;
+    for (long long i = b; i < e; i++) c += mask[i] != 0;
+    counts[t] = c;
+}
+__global__ void __launch_bounds__(256) mask_dest_kernel(const unsigned char *__restrict__ mask, long long n, long long seg, const long long *__restrict__ offsets,
+        long long *__restrict__ dest)
+{
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long b = t * seg, e = b + seg < n ? b + seg : n;
+    long long at = offsets[t];
+    for (long long i = b; i < e; i++) { dest[i] = at; at += mask[i] != 0; }
+}
+
+// dst[dest[i]] = src[i] for the rows with a non-zero mask (rows of `units` elements of T)
+template <typename T>
+__global__ void __launch_bounds__(256) compact_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, const unsigned char *__restrict__ mask,
+        const long long *__restrict__ dest, long long total, int units)
+{
+    long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const long long i = t / units;
+        if (!mask[i]) continue;
+        dst[dest[i] * units + (t - i * units)] = src[t];
+    }
+}
+
+// dst[i] = src[ind[i]] (fastpm_store_permute, store.c:380-399)
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, const int *__restrict__ ind, long long total, int units)
+{
+    long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (; t < total; t += stride) {
+        const long long i = t / units;
+        dst[t] = src[(long long) ind[i] * units + (t - i * units)];
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 static inline unsigned stream_grid(long long n)
 {
@@ -434,6 +493,74 @@ int fpm_permute_by_id_launch(void *dst, const void *src, const unsigned long lon
     } else {
         const long long total = n * elsize;
         FPM_TIMED(FPM_K_OTHER, st, (permute_by_id_kernel<unsigned char><<<stream_grid(total), 256, 0, st>>>((unsigned char *) dst, (const unsigned char *) src, id, total, elsize, id0)));
+    }
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_subsample_mask_launch(const float *rnd, const double *fraction_each, double fraction, long long n, unsigned char *mask, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    FPM_TIMED(FPM_K_OTHER, st, (subsample_mask_kernel<<<stream_grid(n), 256, 0, st>>>(rnd, fraction_each, fraction, n, mask)));
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+// dest may be NULL (count only); *host_total = number of non-zero mask entries
+int fpm_mask_scan_launch(const unsigned char *mask, long long n, long long *dest, long long *host_total, cudaStream_t st)
+{
+    *host_total = 0;
+    if (n <= 0) return 0;
+    const unsigned grid = stream_grid((n + 63) / 64);            // at least 64 rows per thread
+    const long long nthr = (long long) grid * 256, seg = (n + nthr - 1) / nthr;
+    long long *d_counts = nullptr;
+    FPM_CUDA_OK(cudaMalloc(&d_counts, sizeof(long long) * nthr));
+    FPM_TIMED(FPM_K_OTHER, st, (mask_count_kernel<<<grid, 256, 0, st>>>(mask, n, seg, d_counts)));
+    FPM_CHECK_LAUNCH();
+    long long *h = (long long *) malloc(sizeof(long long) * nthr);
+    FPM_CUDA_OK(cudaMemcpyAsync(h, d_counts, sizeof(long long) * nthr, cudaMemcpyDeviceToHost, st));
+    FPM_CUDA_OK(cudaStreamSynchronize(st));
+    long long at = 0;
+    for (long long t = 0; t < nthr; t++) { const long long c = h[t]; h[t] = at; at += c; }
+    *host_total = at;
+    if (dest) {
+        FPM_CUDA_OK(cudaMemcpyAsync(d_counts, h, sizeof(long long) * nthr, cudaMemcpyHostToDevice, st));
+        FPM_TIMED(FPM_K_OTHER, st, (mask_dest_kernel<<<grid, 256, 0, st>>>(mask, n, seg, d_counts, dest)));
+        FPM_CHECK_LAUNCH();
+        FPM_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    free(h);
+    FPM_CUDA_OK(cudaFree(d_counts));
+    return 0;
+}
+
+static inline bool rows_as_words(const void *a, const void *b, int elsize) { return elsize % 4 == 0 && (uintptr_t) a % 4 == 0 && (uintptr_t) b % 4 == 0; }
+
+int fpm_compact_rows_launch(void *dst, const void *src, const unsigned char *mask, const long long *dest, long long n, int elsize, cudaStream_t st)
+{
+    if (elsize < 1) { fpm_set_error("compact rows: element size %d", elsize); return -1; }
+    if (n <= 0) return 0;
+    if (rows_as_words(dst, src, elsize)) {
+        const long long total = n * (elsize / 4);
+        FPM_TIMED(FPM_K_OTHER, st, (compact_rows_kernel<unsigned int><<<stream_grid(total), 256, 0, st>>>((unsigned int *) dst, (const unsigned int *) src, mask, dest, total, elsize / 4)));
+    } else {
+        const long long total = n * elsize;
+        FPM_TIMED(FPM_K_OTHER, st, (compact_rows_kernel<unsigned char><<<stream_grid(total), 256, 0, st>>>((unsigned char *) dst, (const unsigned char *) src, mask, dest, total, elsize)));
+    }
+    FPM_CHECK_LAUNCH();
+    return 0;
+}
+
+int fpm_gather_rows_launch(void *dst, const void *src, const int *ind, long long n, int elsize, cudaStream_t st)
+{
+    if (elsize < 1) { fpm_set_error("gather rows: element size %d", elsize); return -1; }
+    if (n <= 0) return 0;
+    if (rows_as_words(dst, src, elsize)) {
+        const long long total = n * (elsize / 4);
+        FPM_TIMED(FPM_K_OTHER, st, (gather_rows_kernel<unsigned int><<<stream_grid(total), 256, 0, st>>>((unsigned int *) dst, (const unsigned int *) src, ind, total, elsize / 4)));
+    } else {
+        const long long total = n * elsize;
+        FPM_TIMED(FPM_K_OTHER, st, (gather_rows_kernel<unsigned char><<<stream_grid(total), 256, 0, st>>>((unsigned char *) dst, (const unsigned char *) src, ind, total, elsize)));
     }
     FPM_CHECK_LAUNCH();
     return 0;

@@ -253,6 +253,17 @@ int fpm_cast_f64_to_f32(float *dst, const double *src, int64_t n);
  * fpm_permute_by_id: dst[id[i] - id0] = src[i] for n rows of elsize bytes, out of place; needs host_counts[0] == 0. */
 int fpm_id_order_counts(const uint64_t *id, int64_t n, uint64_t id0, uint64_t *host_counts);
 int fpm_permute_by_id(void *dst, const void *src, const uint64_t *id, int64_t n, uint64_t id0, int elsize);
+/* ---- sub-sampling and whole-row moves of a store (all pointers device memory)
+ * fpm_subsample_mask: mask[i] = f >= 1 || rand[i] <= f with f = fraction, or fraction_each_dev[i] when that is not NULL
+ *   (fastpm_store_fill_subsample_mask / _from_array, store.c:967-997).
+ * fpm_mask_scan: *host_total = non-zero entries of mask; dest (may be NULL) receives dest[i] = non-zero entries before i, the row a
+ *   kept particle moves to in a stable compaction (fastpm_store_subsample, store.c:1004-1034; fastpm_store_get_mask_sum, store.c:289).
+ * fpm_compact_rows: dst[dest[i]] = src[i] for the rows with a non-zero mask, rows of elsize bytes, out of place.
+ * fpm_gather_rows: dst[i] = src[ind[i]] (fastpm_store_permute, store.c:380-399), out of place. */
+int fpm_subsample_mask(const float *rand_dev, const double *fraction_each_dev, double fraction, int64_t n, uint8_t *mask);
+int fpm_mask_scan(const uint8_t *mask, int64_t n, int64_t *dest, int64_t *host_total);
+int fpm_compact_rows(void *dst, const void *src, const uint8_t *mask, const int64_t *dest, int64_t n, int elsize);
+int fpm_gather_rows(void *dst, const void *src, const int32_t *ind, int64_t n, int elsize);
 /* the rand column, _fastpm_store_fill_rand store.c:694-720: n deviates of this rank's serial RANLUX stream (drawn on the host, copied up) */
 int fpm_fill_rand(float *rand_dev, int64_t n, int rank);
 /* ---- K10 summary: fastpm_store_summary, store.c:808.  dtype 4 = float32, 8 = float64;

@@ -565,6 +565,25 @@ int fastpm_store_has_q(FastPMStore *p);
 void fastpm_store_get_q_from_id(FastPMStore *p, uint64_t id, double q[3]);
 void fastpm_store_get_iq_from_id(FastPMStore *p, uint64_t id, ptrdiff_t pabs[3]);
 void fastpm_store_steal(FastPMStore *in, FastPMStore *out, FastPMColumnTags attributes);                  /* store.h:260 */
+/* store.h:224-268: whole particles between / inside stores, sub-sampling, local sort (csrc/host/store_ops.c).  `mask` and a per-particle
+ * `fraction` array are device memory (fastpm_memory_alloc hands out device memory); fastpm_store_permute takes a HOST index array
+ * as in the reference; fastpm_store_sort accepts the comparator libfastpm itself uses, FastPMLocalSortByID. */
+void fastpm_store_copy(FastPMStore *p, FastPMStore *po);
+void fastpm_store_take(FastPMStore *p, ptrdiff_t i, FastPMStore *po, ptrdiff_t j);
+void fastpm_store_extend(FastPMStore *p, FastPMStore *extra);
+void fastpm_store_get_position(FastPMStore *p, ptrdiff_t index, double pos[3]);
+void fastpm_store_get_lagrangian_position(FastPMStore *p, ptrdiff_t index, double pos[3]);
+size_t fastpm_store_get_mask_sum(FastPMStore *p, MPI_Comm comm);
+void fastpm_store_fill_subsample_mask(FastPMStore *p, double fraction, FastPMParticleMaskType *mask);
+void fastpm_store_fill_subsample_mask_from_array(FastPMStore *p, double *fraction, FastPMParticleMaskType *mask);
+size_t fastpm_store_subsample(FastPMStore *p, FastPMParticleMaskType *mask, FastPMStore *po);
+void fastpm_store_permute(FastPMStore *p, int *ind);
+int FastPMLocalSortByID(const int i1, const int i2, FastPMStore *p);
+void fastpm_store_sort(FastPMStore *p, int (*cmp_func)(const int i1, const int i2, FastPMStore *p));
+/* bindings / tests: fill a scratch store on pm's grid, sub-sample it at `fraction` (into a second store or in place), optionally reverse
+ * it with fastpm_store_permute and sort it back with fastpm_store_sort, mirror the kept
+ * ids and positions; returns the number kept */
+int64_t fastpm_b200_subsample_probe(PM *pm, int64_t np_upper, double fraction, int in_place, int sort_back, uint64_t *id_host, double *x_host, int64_t *mask_sum);
 double fastpm_apply_get_mode_transfer(PM *pm, FastPMFloat *from, ptrdiff_t *mode);                        /* transfer.c:340 */
 void fastpm_apply_set_mode_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to, ptrdiff_t *mode, double value, int method);   /* :290 */
 void fastpm_apply_normalize_transfer(PM *pm, FastPMFloat *from, FastPMFloat *to);                         /* :223 */

@@ -277,6 +277,15 @@ class Session:
                             acc_std=sc[10:13].copy(), Plin=sc[13], a_x=sc[14], a_v=sc[15], k=k, p=p, nmodes=nm))
         return out
 
+    def subsample_probe(self, np_upper, fraction, in_place=False, sort_back=False):
+        """fill a scratch store, fastpm_store_fill_subsample_mask + fastpm_store_subsample [+ permute (reverse) + sort by id]
+        -> (ids, x, mask_sum)"""
+        ids, x, ms = np.zeros(np_upper, dtype=np.uint64), np.zeros((np_upper, 3)), C.c_int64(0)
+        lib().ref_subsample_probe.restype = C.c_int64
+        n = lib().ref_subsample_probe(self._h, C.c_int64(np_upper), C.c_double(fraction), C.c_int(int(in_place)), C.c_int(int(sort_back)),
+                                      _p(ids), _p(x), C.byref(ms))
+        return ids[:n].copy(), x[:n].copy(), int(ms.value)
+
     def fill_probe(self, np_upper, as_rank=0):
         """fastpm_store_fill of a scratch store with q and rand columns -> (q [np][3], rand [np_upper]); as_rank: what MPI_Comm_rank
         answers meanwhile (selects the seed of the rand stream, store.c:704-708)"""

@@ -400,6 +400,40 @@ int64_t ref_fill_probe_as_rank(RefSession *s, int rank, int64_t np_upper, float 
     return np;
 }
 
+/* the command line's particle_fraction (src/fastpm.c:1449-1461) on a scratch store filled on the LPT mesh's particle grid:
+ * fastpm_store_fill_subsample_mask + fastpm_store_subsample into a second store (or in place), fastpm_store_get_mask_sum; then
+ * fastpm_store_sort(FastPMLocalSortByID) of the kept particles after they were reversed by fastpm_store_permute (sort_back != 0) */
+int64_t ref_subsample_probe(RefSession *s, int64_t np_upper, double fraction, int in_place, int sort_back, uint64_t *id_out, double *x_out, int64_t *mask_sum)
+{
+    PM *pm = s->solver->lptpm;
+    FastPMStore p[1], po[1];
+    const FastPMColumnTags attrs = COLUMN_POS | COLUMN_ID | COLUMN_Q | COLUMN_RAND | COLUMN_MASK;
+    fastpm_store_init(p, "probe", np_upper, attrs, FASTPM_MEMORY_HEAP);
+    fastpm_store_fill(p, pm, NULL, NULL);
+    fastpm_store_fill_subsample_mask(p, fraction, p->mask);
+    *mask_sum = (int64_t) fastpm_store_get_mask_sum(p, MPI_COMM_WORLD);
+    FastPMStore *out = p;
+    if (!in_place) {
+        fastpm_store_init(po, "kept", fastpm_store_subsample(p, p->mask, NULL) + 1, attrs & ~COLUMN_MASK, FASTPM_MEMORY_HEAP);
+        out = po;
+    }
+    fastpm_store_subsample(p, p->mask, out);
+    if (sort_back && out->np) {
+        int *ind = malloc(sizeof(int) * out->np);
+        for (size_t i = 0; i < out->np; i++) ind[i] = (int) (out->np - 1 - i);
+        fastpm_store_permute(out, ind);
+        free(ind);
+        if (out->id[0] < out->id[out->np - 1]) fastpm_raise(-1, "ref_subsample_probe: the permutation did not reverse the store\n");
+        fastpm_store_sort(out, FastPMLocalSortByID);
+    }
+    const int64_t kept = out->np;
+    memcpy(id_out, out->id, sizeof(out->id[0]) * out->np);
+    memcpy(x_out, out->x, sizeof(out->x[0]) * out->np);
+    if (!in_place) fastpm_store_destroy(po);
+    fastpm_store_destroy(p);
+    return kept;
+}
+
 /* fastpm_paint_local (painter.c:320) of unit-mass particles onto a cleared canvas */
 void ref_paint(RefSession *s, int which, double a, const double *x, int64_t np, float *canvas_out)
 {

@@ -253,6 +253,78 @@ def test_wrap_and_summary_match_reference(ref_mod):
     s.close()
 
 
+@pytest.mark.parametrize("fraction", [0.3, 1.0, 0.0])
+def test_store_subsample_matches_reference(ref_mod, fraction):
+    """The command line's particle_fraction (src/fastpm.c:1449-1461) with the reference's own store calls: fastpm_store_fill (rand
+    column) -> fastpm_store_fill_subsample_mask -> fastpm_store_get_mask_sum -> fastpm_store_subsample (count only, into a second
+    store, in place) [-> fastpm_store_permute (reversed) -> fastpm_store_sort(FastPMLocalSortByID)]: the same particles, in the same
+    order, as the reference keeps (store.c:289-299, 380-446, 967-1034)."""
+    import ctypes as C
+    from fastpm_b200.solver import Solver
+    nc, L = 12, 60.0
+    n_up = 2 * nc ** 3 + 17
+    s = ref_mod.Session(nc=nc, boxsize=L, pm_nc_factor=2, np_alloc_factor=2.0)
+    want = {(ip, sb): s.subsample_probe(n_up, fraction, in_place=ip, sort_back=sb) for ip in (False, True) for sb in (False, True)}
+    s.close()
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=2, np_alloc_factor=2.0)
+    g.lib.fastpm_b200_subsample_probe.restype = C.c_int64
+    g.lib.fastpm_b200_subsample_probe.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    for (ip, sb), (ids0, x0, ms0) in want.items():
+        ids, x, ms = np.zeros(n_up, dtype=np.uint64), np.zeros((n_up, 3)), C.c_int64(0)
+        n = g.lib.fastpm_b200_subsample_probe(g.lptpm, n_up, fraction, int(ip), int(sb), ids.ctypes.data, x.ctypes.data, C.byref(ms))
+        assert n == len(ids0) == ms.value == ms0, (ip, sb)
+        assert np.array_equal(ids[:n], ids0) and np.array_equal(x[:n], x0), (ip, sb)
+        assert np.all(np.diff(ids0.astype(np.int64)) > 0)
+    g.close()
+    n = len(want[(False, False)][0])
+    assert n == nc ** 3 if fraction >= 1 else (n <= 2 if fraction == 0 else 0.2 * nc ** 3 < n < 0.4 * nc ** 3)
+
+
+def test_store_copy_take_extend(pk_text):
+    """fastpm_store_copy / _take / _extend / _get_position (store.c:106-111, 925-966) between two stores with device columns."""
+    import ctypes as C
+    from fastpm_b200.solver import Solver, COLUMNS
+    nc, L = 8, 32.0
+    g = Solver(nc=nc, boxsize=L, pm_nc_factor=2, force_mode="fastpm", growth_mode="LCDM", np_alloc_factor=2.0)
+    kk, pp = np.loadtxt(pk_text.splitlines(), unpack=True)
+    g.setup_ic(5, kk, pp, 0.2)
+    x, v, ids = g.get_column("x"), g.get_column("v"), g.get_column("id")
+    n = g.np
+    lib, vp = g.lib, C.c_void_p
+    store = C.create_string_buffer(1 << 16)                   # room for one FastPMStore (its layout is the library's business)
+    other = C.cast(store, vp)
+    lib.fastpm_store_init_details.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_uint64, C.c_int, C.c_char_p, C.c_int]
+    lib.fastpm_store_init_details(other, b"other", 3 * n, COLUMNS["x"] | COLUMNS["v"] | COLUMNS["id"], 0, b"test", 0)
+    for f in (lib.fastpm_store_copy, lib.fastpm_store_extend):
+        f.argtypes = [vp, vp]
+    lib.fastpm_store_take.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t]
+    lib.fastpm_store_get_position.argtypes = [vp, C.c_ssize_t, vp]
+    lib.fastpm_store_destroy.argtypes = [vp]
+    lib.fastpm_b200_store_np.argtypes = [vp]
+    lib.fastpm_b200_store_np.restype = C.c_int64
+
+    def column(name, count):
+        dt, nm = {"x": (np.float64, 3), "v": (np.float32, 3), "id": (np.uint64, 1)}[name]
+        out = np.empty((count, nm) if nm > 1 else (count,), dtype=dt)
+        assert lib.fastpm_b200_store_get_column(other, COLUMNS[name], out.ctypes.data, 0, count) == 0
+        return out
+
+    lib.fastpm_store_copy(g.cdm, other)
+    assert lib.fastpm_b200_store_np(other) == n
+    assert np.array_equal(column("x", n), x) and np.array_equal(column("v", n), v) and np.array_equal(column("id", n), ids)
+    lib.fastpm_store_extend(other, g.cdm)                     # other = cdm + cdm
+    assert lib.fastpm_b200_store_np(other) == 2 * n
+    assert np.array_equal(column("id", 2 * n), np.concatenate([ids, ids])) and np.array_equal(column("x", 2 * n), np.concatenate([x, x]))
+    lib.fastpm_store_take(g.cdm, 7, other, 2 * n)             # one more particle at the end
+    assert lib.fastpm_b200_store_np(other) == 2 * n + 1
+    assert np.array_equal(column("x", 2 * n + 1)[-1], x[7]) and column("id", 2 * n + 1)[-1] == ids[7]
+    pos = np.zeros(3)
+    lib.fastpm_store_get_position(other, 2 * n, pos.ctypes.data)
+    assert np.array_equal(pos, x[7])
+    lib.fastpm_store_destroy(other)
+    g.close()
+
+
 def test_permute_by_dense_id_kernels():
     """fpm_id_order_counts / fpm_permute_by_id (the sort by a dense particle id of fastpm_sort_snapshot, libfastpmio/io.c:860-960, as
     one scatter per column): rows of 24, 12, 8 and 1 bytes, a non-zero first id, ids outside the range, duplicates."""

@@ -25,6 +25,8 @@ CASES = [
     "test_passive_handler_keeps_the_fused_update",
     "test_store_fill_q_and_rand_columns_match_reference",
     "test_wrap_and_summary_match_reference",
+    "test_store_subsample_matches_reference",
+    "test_store_copy_take_extend",
     "test_permute_by_dense_id_kernels",
     "test_sorted_snapshot_of_a_shuffled_store",
 ]
