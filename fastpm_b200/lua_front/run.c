@@ -59,7 +59,6 @@ static void refuse(RunData *prr)
     OUT_OF_SCOPE(CONF(prr->lua, read_grafic) != NULL, "read_grafic");
     OUT_OF_SCOPE(CONF(prr->lua, read_runpbic) != NULL, "read_runpbic");
     OUT_OF_SCOPE(CONF(prr->lua, write_runpb_snapshot) != NULL, "write_runpb_snapshot");
-    OUT_OF_SCOPE(CONF(prr->lua, particle_fraction) < 1, "particle_fraction < 1");
     OUT_OF_SCOPE(CONF(prr->lua, read_linear_growth_rate) != NULL, "read_linear_growth_rate");
 #undef OUT_OF_SCOPE
 }
@@ -164,6 +163,7 @@ static void prepare_cdm(FastPMSolver *fastpm, RunData *prr, double a0)
 {
     MPI_Comm comm = fastpm->comm;
     if (prr->cli->RestartSnapshotPath) {
+        if (CONF(prr->lua, particle_fraction) != 1) fastpm_raise(-1, "Cannot restart because subsampling of particles is enabled.\n");
         fastpm_info("Restarting from snapshot at `%s`.\n", prr->cli->RestartSnapshotPath);
         FastPMStore *p = fastpm_solver_get_species(fastpm, FASTPM_SPECIES_CDM);
         FastPMStore po[1];
@@ -224,16 +224,31 @@ static int take_a_snapshot(FastPMSolver *fastpm, RunData *prr)
         pm_free(fastpm->basepm, rho_x);
         free(filename);
     }
+    /* particle_fraction < 1 (src/fastpm.c:1449-1461): the snapshot holds the particles whose `rand` deviate is below the fraction,
+     * compacted into a store of their own (every column but ACC) */
+    double particle_fraction = CONF(prr->lua, particle_fraction);
+    FastPMStore subsample[1], *all = cdm;
+    if (particle_fraction < 1) {
+        FastPMParticleMaskType *mask = fastpm_memory_alloc(cdm->mem, "SubsampleMask", sizeof(mask[0]) * cdm->np_upper, FASTPM_MEMORY_FLOATING);
+        fastpm_store_fill_subsample_mask(cdm, particle_fraction, mask);
+        fastpm_store_init(subsample, cdm->name, fastpm_store_subsample(cdm, mask, NULL), cdm->attributes & (~COLUMN_ACC) & (~COLUMN_MASK),
+                          FASTPM_MEMORY_FLOATING);
+        fastpm_store_subsample(cdm, mask, subsample);
+        fastpm_memory_free(cdm->mem, mask);
+        cdm = subsample;
+    }
     if (CONF(prr->lua, sort_snapshot)) fastpm_sort_snapshot(cdm, fastpm->comm, FastPMSnapshotSortByID, 0);
     if (CONF(prr->lua, write_snapshot)) {
         char *filebase = fastpm_strdup_printf("%s_%0.04f", CONF(prr->lua, write_snapshot), aout);
         write_snapshot_header(fastpm, filebase, fastpm->comm);
         /* write_parameters (src/fastpm.c:1210-1225): the parameter file as the reference stores it, attribute "ParamFile" of Header */
         write_snapshot_attr(filebase, "Header", "ParamFile", prr->lua->string, "S1", strlen(prr->lua->string) + 1, fastpm->comm);
+        write_snapshot_attr(filebase, "Header", "ParticleFraction", &particle_fraction, "f8", 1, fastpm->comm);
         fastpm_store_write(cdm, filebase, "w", prr->cli->Nwriters, fastpm->comm);
         fastpm_info("snapshot %s [%s] written at z = %6.4f a = %6.4f \n", filebase, "1", z_out, aout);
         free(filebase);
     }
+    if (cdm != all) fastpm_store_destroy(subsample);
     return 0;
 }
 
@@ -522,6 +537,8 @@ int main(int argc, char **argv)
     config->pgdc_ks = CONF(prr->lua, pgdc_ks);
     if (CONF(prr->lua, compute_potential)) config->ExtraAttributes |= COLUMN_POTENTIAL;
     if (CONF(prr->lua, pgdc)) config->ExtraAttributes |= COLUMN_PGDC;
+    /* the reference's CDM store always carries MASK and RAND (solver.c:93-97); here RAND is there when sub-sampling needs it */
+    if (CONF(prr->lua, particle_fraction) < 1) config->ExtraAttributes |= COLUMN_RAND;
 
     run_fastpm(config, prr, comm);
 

@@ -86,10 +86,10 @@ def runs(emul_lib, tmp_path_factory):
         mk = subprocess.run(["make", "-C", os.path.join(ROOT, "fastpm_b200", "lua_front"), "emul"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert mk.returncode == 0, mk.stdout[-2000:]
         exe = os.path.join(ROOT, "fastpm_b200", "lua_front", "_build", "fastpm_b200_run_emul")
-        for tag, extra in (("one", []), ("two", ["-n", "2"])):
+        for tag, extra, more in (("one", [], []), ("two", ["-n", "2"], []), ("sub", [], ["0.3"])):
             d = tmp_path_factory.mktemp("cli_" + tag)
             shutil.copy(os.path.join(ROOT, "tests", "golden", "powerspec.txt"), str(d))
-            cli[tag] = (str(d), subprocess.Popen([exe] + extra + [os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), "8", "3"], cwd=str(d),
+            cli[tag] = (str(d), subprocess.Popen([exe] + extra + [os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), "8", "3"] + more, cwd=str(d),
                                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     out = {}
     for g, p in procs.items():
@@ -188,3 +188,37 @@ def test_command_line_with_two_forked_ranks(runs):
     hdr = lambda d: open(os.path.join(d, "out", "fastpm_1.0000", "Header", "attr-v2")).read()
     assert hdr(d1) == hdr(d2)
     assert not [f for f in runs["cli_shm_left"] if f.startswith("fastpm_b200_") or f.startswith("fpm_emul_")], runs["cli_shm_left"]
+
+
+def test_command_line_particle_fraction(runs):
+    """particle_fraction = 0.3 (src/fastpm.c:1449-1461): the snapshot holds exactly the particles the reference's
+    fastpm_store_fill_subsample_mask / fastpm_store_subsample keep on the same grid (rand column = the rank's serial RANLUX stream),
+    sorted by id, with the rows they have in the full snapshot; the rest of the run is untouched."""
+    if not runs["cli"]:
+        pytest.skip("needs /root/reference (the Lua runtime is compiled from there)")
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libfastpm_ref.so not built")
+    (rc1, d1, o1), (rc3, d3, o3) = runs["cli"]["one"], runs["cli"]["sub"]
+    assert rc1 == 0 and rc3 == 0, o3[-3000:]
+    rd = lambda top, name, dt, nm: np.fromfile(os.path.join(top, "out", "fastpm_1.0000", "1", name, "000000"), dtype=dt).reshape(-1, nm)
+    s = ref.Session(nc=8, boxsize=16.0, pm_nc_factor=2, np_alloc_factor=3.0)
+    want_ids, _, _ = s.subsample_probe(3 * 8 ** 3, 0.3)
+    s.close()
+    ids = rd(d3, "ID", np.uint64, 1)[:, 0]
+    assert 0.2 * 8 ** 3 < len(ids) < 0.4 * 8 ** 3 and np.array_equal(ids, want_ids)
+    sel = ids.astype(np.int64)
+    for name, dt, nm in (("Position", np.float32, 3), ("Velocity", np.float32, 3), ("DX1", np.float32, 3), ("DX2", np.float32, 3)):
+        a, b = rd(d3, name, dt, nm).astype(np.float64), rd(d1, name, dt, nm)[sel].astype(np.float64)       # two runs: the float order of
+        dd = np.abs(a - b)                                                                                   # the deposits differs
+        if name == "Position":
+            dd = np.minimum(dd, 16.0 - dd)
+        assert dd.max() < 1e-4 * max(1.0, np.abs(b).max()), name
+    assert sorted(os.listdir(os.path.join(d3, "out", "fastpm_1.0000", "1"))) == sorted(os.listdir(os.path.join(d1, "out", "fastpm_1.0000", "1")))
+    hdr = open(os.path.join(d3, "out", "fastpm_1.0000", "Header", "attr-v2")).read()
+    assert "ParticleFraction <f8 1" in hdr and "[ 0.3 ]" in hdr
+    for f in sorted(os.listdir(os.path.join(d1, "out"))):                      # the power spectra do not know about the sub-sample
+        if f.endswith(".txt"):
+            x, y = np.loadtxt(os.path.join(d1, "out", f)), np.loadtxt(os.path.join(d3, "out", f))
+            assert x.shape == y.shape and np.array_equal(x[:, 2], y[:, 2]), f
+            np.testing.assert_allclose(x[x[:, 2] > 0, 1], y[x[:, 2] > 0, 1], rtol=1e-5, err_msg=f)
