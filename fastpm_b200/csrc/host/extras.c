@@ -231,3 +231,24 @@ int64_t fastpm_b200_public_mesh_probe(FastPMSolver *fastpm, double a, double *k,
     pm_free(pm, canvas);
     return (int64_t) cdm->np;
 }
+
+/* ------------------------------------------------------------------ analytic spectra for fastpm_ic_induce_correlation (utils.h:3-14)
+ * fastpm_utils_powerspec_eh, utils.c:118-149: P(k) = Norm k T(k)^2 with the zero-baryon-wiggle Eisenstein & Hu (1998) transfer
+ * function in the form the reference took from Martin White -- what tests/testpm.c:67-74 hands to fastpm_ic_induce_correlation. */
+double fastpm_utils_powerspec_eh(double k, struct fastpm_powerspec_eh_params *param)
+{
+    const double h = param->hubble_param, om_h2 = param->omegam * h * h, ob_h2 = param->omegab * h * h;
+    const double theta_cmb = 2.728 / 2.7, fb = ob_h2 / om_h2;
+    const double sound = 44.5 * log(9.83 / om_h2) / sqrt(1. + 10. * exp(0.75 * log(ob_h2))) * h;
+    const double alpha = 1. - 0.328 * log(431. * om_h2) * fb + 0.380 * log(22.3 * om_h2) * fb * fb;
+    double shape = alpha + (1. - alpha) / (1. + exp(4 * log(0.43 * k * sound)));
+    shape *= param->omegam * h;
+    const double q = k * theta_cmb * theta_cmb / shape;
+    const double L0 = log(2. * exp(1.) + 1.8 * q), C0 = 14.2 + 731. / (1. + 62.5 * q);
+    const double tk = L0 / (L0 + C0 * q * q);
+    return param->Norm * k * pow(tk, 2);
+}
+
+/* utils.c:151-155 */
+double fastpm_utils_powerspec_white(double k, double *amplitude) { (void) k; return *amplitude; }
+

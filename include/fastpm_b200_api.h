@@ -580,6 +580,10 @@ size_t fastpm_store_subsample(FastPMStore *p, FastPMParticleMaskType *mask, Fast
 void fastpm_store_permute(FastPMStore *p, int *ind);
 int FastPMLocalSortByID(const int i1, const int i2, FastPMStore *p);
 void fastpm_store_sort(FastPMStore *p, int (*cmp_func)(const int i1, const int i2, FastPMStore *p));
+/* utils.h:3-14: analytic spectra to pass to fastpm_ic_induce_correlation (tests/testpm.c:67-74) */
+struct fastpm_powerspec_eh_params { double hubble_param; double omegam; double omegab; double Norm; };
+double fastpm_utils_powerspec_eh(double k, struct fastpm_powerspec_eh_params *param);   /* Eisenstein & Hu, no wiggles */
+double fastpm_utils_powerspec_white(double k, double *amplitude);
 /* bindings / tests: fill a scratch store on pm's grid, sub-sample it at `fraction` (into a second store or in place), optionally reverse
  * it with fastpm_store_permute and sort it back with fastpm_store_sort, mirror the kept
  * ids and positions; returns the number kept */

@@ -382,3 +382,26 @@ def test_powerspectrum_helpers_match_reference(lib, ref_mod):
         L.fastpm_powerspectrum_destroy(C.byref(cp))
     assert np.array_equal(out["mine"], out["ref"])
     del rng
+
+
+def test_analytic_spectra_match_reference(lib, ref_mod):
+    """fastpm_utils_powerspec_eh / _white (utils.c:118-155; what tests/testpm.c:67-74 passes to fastpm_ic_induce_correlation): the same
+    parameter struct handed to both libraries."""
+    import ctypes as C
+    from oracle import ref
+
+    class EH(C.Structure):                                   # utils.h:3-8
+        _fields_ = [("hubble_param", C.c_double), ("omegam", C.c_double), ("omegab", C.c_double), ("Norm", C.c_double)]
+
+    r = ref.lib()
+    for L in (lib, r):
+        L.fastpm_utils_powerspec_eh.restype = C.c_double
+        L.fastpm_utils_powerspec_eh.argtypes = [C.c_double, C.POINTER(EH)]
+        L.fastpm_utils_powerspec_white.restype = C.c_double
+        L.fastpm_utils_powerspec_white.argtypes = [C.c_double, C.POINTER(C.c_double)]
+    amp = C.c_double(3.25)
+    for par in (EH(0.7, 0.260, 0.044, 10000.0), EH(0.6774, 0.3075, 0.0486, 1.0)):
+        for k in np.concatenate([np.logspace(-4, 2, 61), [0.0490625]]):
+            a, b = lib.fastpm_utils_powerspec_eh(k, C.byref(par)), r.fastpm_utils_powerspec_eh(k, C.byref(par))
+            assert b > 0 and abs(a / b - 1) < 1e-14, (k, a, b)
+    assert lib.fastpm_utils_powerspec_white(0.3, C.byref(amp)) == r.fastpm_utils_powerspec_white(0.3, C.byref(amp)) == 3.25
