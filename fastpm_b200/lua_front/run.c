@@ -231,8 +231,16 @@ static int take_a_snapshot(FastPMSolver *fastpm, RunData *prr)
     if (particle_fraction < 1) {
         FastPMParticleMaskType *mask = fastpm_memory_alloc(cdm->mem, "SubsampleMask", sizeof(mask[0]) * cdm->np_upper, FASTPM_MEMORY_FLOATING);
         fastpm_store_fill_subsample_mask(cdm, particle_fraction, mask);
-        fastpm_store_init(subsample, cdm->name, fastpm_store_subsample(cdm, mask, NULL), cdm->attributes & (~COLUMN_ACC) & (~COLUMN_MASK),
-                          FASTPM_MEMORY_FLOATING);
+        size_t room = fastpm_store_subsample(cdm, mask, NULL);
+        if (fastpm->NTask > 1) {
+            /* several GPUs: device blocks come from the symmetric arena, where every rank must ask for the same sizes in the same
+             * order -- a bound that is the same everywhere instead of this rank's own count */
+            size_t bound = (size_t) (cdm->np_upper * particle_fraction * 1.5) + 4096;
+            if (bound > cdm->np_upper) bound = cdm->np_upper;
+            if (room > bound) fastpm_raise(-1, "fastpm_b200_run: %td particles of this rank pass particle_fraction = %g, room for %td\n", (ptrdiff_t) room, particle_fraction, (ptrdiff_t) bound);
+            room = bound;
+        }
+        fastpm_store_init(subsample, cdm->name, room, cdm->attributes & (~COLUMN_ACC) & (~COLUMN_MASK), FASTPM_MEMORY_FLOATING);
         fastpm_store_subsample(cdm, mask, subsample);
         fastpm_memory_free(cdm->mem, mask);
         cdm = subsample;

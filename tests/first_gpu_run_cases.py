@@ -803,3 +803,29 @@ def test_cli_run_loop_program_matches_reference(ref_mod, pk_text, tmp_path):
         assert np.array_equal(rows[:, 2], rec["nmodes"])
         np.testing.assert_allclose(rows[sel, 0], rec["k"][sel], rtol=1e-5)          # "%g": 6 significant digits
         np.testing.assert_allclose(rows[sel, 1], rec["p"][sel], rtol=2e-5)
+
+
+def test_command_line_particle_fraction_snapshot(ref_mod, tmp_path):
+    """particle_fraction = 0.25 through fastpm_b200_run (src/fastpm.c:1449-1461): the snapshot of the command line holds exactly the
+    particles the reference's fastpm_store_fill_subsample_mask / fastpm_store_subsample keep on the same particle grid, sorted by
+    id.  (On the CPU the same run goes through the emulated library: tests/test_cpu_full_emulation.py.)"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run_bin = os.path.join(root, "fastpm_b200", "lua_front", "_build", "fastpm_b200_run")
+    if os.environ.get("FASTPM_B200_TEST_EMUL") or not os.path.exists(run_bin):
+        pytest.skip("needs the command line built against the CUDA library")
+    nc = 16
+    shutil.copy(os.path.join(root, "tests", "golden", "powerspec.txt"), str(tmp_path / "powerspec.txt"))
+    r = subprocess.run([run_bin, os.path.join(root, "tests", "lua", "small_nc16.lua"), str(nc), "3", "0.25"], cwd=str(tmp_path),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    top = tmp_path / "out" / "fastpm_1.0000"
+    ids = np.fromfile(str(top / "1" / "ID" / "000000"), dtype=np.uint64)
+    s = ref_mod.Session(nc=nc, boxsize=2.0 * nc, pm_nc_factor=2, np_alloc_factor=3.0)
+    want, _, _ = s.subsample_probe(3 * nc ** 3, 0.25)
+    s.close()
+    assert 0.15 * nc ** 3 < len(ids) < 0.35 * nc ** 3 and np.array_equal(ids, want)
+    x = np.fromfile(str(top / "1" / "Position" / "000000"), dtype=np.float32).reshape(-1, 3)
+    assert len(x) == len(ids) and np.isfinite(x).all() and x.min() >= 0 and x.max() <= 2.0 * nc
+    assert "[ 0.25 ]" in open(str(top / "Header" / "attr-v2")).read()

@@ -38,7 +38,7 @@ GROUPS = [
     ["test_passive_handler_keeps_the_fused_update", "test_store_fill_q_and_rand_columns_match_reference", "test_permute_by_dense_id_kernels",
      "test_wrap_and_summary_match_reference", "test_sorted_snapshot_of_a_shuffled_store"],
     ["test_snapshot_files_and_restart_match_reference", "test_snapshots_during_evolve_match_reference"],
-    ["test_store_subsample_matches_reference", "test_store_copy_take_extend"],
+    ["test_store_subsample_matches_reference", "test_store_copy_take_extend", "test_command_line_particle_fraction_snapshot"],      # the last one skips here
     ["test_cli_run_loop_program_matches_reference"],
 ]
 # the two cases built on the committed nc = 16 fixture take 3 minutes each under emulation (all 17 cases: 8 minutes, all green on

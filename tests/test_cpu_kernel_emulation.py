@@ -36,7 +36,19 @@ def emul(tmp_path_factory):
 def one_thread_ref(ref_mod):
     old = os.environ.get("OMP_NUM_THREADS")
     os.environ["OMP_NUM_THREADS"] = "1"          # serial deposit order on the reference side
+    # the variable is read once, when the OpenMP runtime starts: if an earlier test of this process has already run the reference,
+    # the runtime itself has to be told
+    import ctypes
+    gomp, old_n = None, 0
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        old_n = gomp.omp_get_max_threads()
+        gomp.omp_set_num_threads(1)
+    except OSError:
+        pass
     yield ref_mod
+    if gomp is not None and old_n > 0:
+        gomp.omp_set_num_threads(old_n)
     if old is None:
         os.environ.pop("OMP_NUM_THREADS", None)
     else:

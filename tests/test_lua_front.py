@@ -105,25 +105,3 @@ def test_golden_log_of_the_reference_run(run_bin, tmp_path):
     assert "written at z = 0.0000 a = 1.0000" in log
     assert os.path.isdir(tmp_path / "golden_nc64" / "fastpm_1.0000" / "1" / "Position")
     assert len([f for f in os.listdir(tmp_path / "golden_nc64") if f.startswith("powerspec_") and f.endswith(".txt")]) == 9   # 8 + linear
-
-
-@pytest.mark.gpu
-def test_particle_fraction_snapshot_keeps_the_reference_subsample(run_bin, tmp_path):
-    """particle_fraction = 0.25 (src/fastpm.c:1449-1461): the snapshot of the command line holds exactly the particles the reference's
-    fastpm_store_fill_subsample_mask / fastpm_store_subsample keep on the same particle grid, sorted by id."""
-    from oracle import ref
-    if not ref.available():
-        pytest.skip("oracle/_ref/libfastpm_ref.so not built")
-    nc = 16
-    shutil.copy(os.path.join(ROOT, "tests", "golden", "powerspec.txt"), str(tmp_path / "powerspec.txt"))
-    r = _run(run_bin, [os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), str(nc), "3", "0.25"], str(tmp_path))
-    assert r.returncode == 0, r.stdout[-3000:]
-    top = tmp_path / "out" / "fastpm_1.0000"
-    ids = np.fromfile(str(top / "1" / "ID" / "000000"), dtype=np.uint64)
-    s = ref.Session(nc=nc, boxsize=2.0 * nc, pm_nc_factor=2, np_alloc_factor=3.0)
-    want, _, _ = s.subsample_probe(3 * nc ** 3, 0.25)
-    s.close()
-    assert 0.15 * nc ** 3 < len(ids) < 0.35 * nc ** 3 and np.array_equal(ids, want)
-    x = np.fromfile(str(top / "1" / "Position" / "000000"), dtype=np.float32).reshape(-1, 3)
-    assert len(x) == len(ids) and np.isfinite(x).all() and x.min() >= 0 and x.max() <= 2.0 * nc
-    assert "[ 0.25 ]" in open(str(top / "Header" / "attr-v2")).read()

@@ -29,6 +29,7 @@ CASES = [
     "test_store_copy_take_extend",
     "test_permute_by_dense_id_kernels",
     "test_sorted_snapshot_of_a_shuffled_store",
+    "test_command_line_particle_fraction_snapshot",
 ]
 
 
