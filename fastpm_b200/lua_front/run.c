@@ -47,7 +47,7 @@ static int cmp_double(const void *a, const void *b)
     return (x > y) - (x < y);
 }
 
-static void refuse(RunData *prr)
+static void refuse(RunData *prr, int nranks)
 {
 #define OUT_OF_SCOPE(cond, what) do { if (cond) fastpm_raise(-1, "fastpm_b200_run: %s is outside the force-step path of this build (DESIGN.md section 8)\n", what); } while (0)
     OUT_OF_SCOPE(CONF(prr->lua, lc_write_usmesh) != NULL, "lc_write_usmesh (light cone)");
@@ -61,6 +61,10 @@ static void refuse(RunData *prr)
     OUT_OF_SCOPE(CONF(prr->lua, write_runpb_snapshot) != NULL, "write_runpb_snapshot");
     OUT_OF_SCOPE(CONF(prr->lua, read_linear_growth_rate) != NULL, "read_linear_growth_rate");
 #undef OUT_OF_SCOPE
+    /* the distributed sort by id places every row at the file position its id names, which needs the dense ids of a full store: a
+     * sub-sampled snapshot written by several ranks comes out sorted inside each rank's part only */
+    if (nranks > 1 && CONF(prr->lua, particle_fraction) < 1 && CONF(prr->lua, sort_snapshot) && CONF(prr->lua, write_snapshot))
+        fastpm_raise(-1, "fastpm_b200_run: particle_fraction < 1 on several GPUs needs sort_snapshot = false in this build\n");
 }
 
 /* ------------------------------------------------------------------ initial conditions: src/fastpm.c:79,399-586,1779-1812 */
@@ -439,7 +443,7 @@ int main(int argc, char **argv)
         return 0;
     }
 
-    refuse(prr);                          /* before any device is touched */
+    refuse(prr, nranks);                  /* before any device is touched */
     if (nranks > 1) {
         /* one process per GPU, forked before the first CUDA call; the parent only waits (and takes the others down if one fails) */
         char segment[64];

@@ -68,6 +68,10 @@ def test_options_outside_the_path_are_refused_before_any_device_is_touched(run_b
     r = _run(run_bin, [os.path.join(ROOT, "tests", "lua", "c0_standard.lua"), "cola", "lightcone"], str(tmp_path))
     assert r.returncode != 0
     assert "lc_write_usmesh" in r.stdout and "outside the force-step path" in r.stdout, r.stdout
+    # a sorted sub-sampled snapshot from several ranks needs the distributed sort of non-dense ids: refused up front, not at the
+    # first snapshot
+    r = _run(run_bin, ["-n", "2", os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), "8", "3", "0.3"], str(tmp_path))
+    assert r.returncode != 0 and "sort_snapshot = false" in r.stdout, r.stdout
 
 
 GOLDEN = [                                     # /root/reference/tests/run-test-lightcone.check:1-5,8,28,42,56,64,72,80,88
