@@ -86,7 +86,7 @@ def runs(emul_lib, tmp_path_factory):
         mk = subprocess.run(["make", "-C", os.path.join(ROOT, "fastpm_b200", "lua_front"), "emul"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert mk.returncode == 0, mk.stdout[-2000:]
         exe = os.path.join(ROOT, "fastpm_b200", "lua_front", "_build", "fastpm_b200_run_emul")
-        for tag, extra, more in (("one", [], []), ("two", ["-n", "2"], []), ("sub", [], ["0.3"])):
+        for tag, extra, more in (("one", [], []), ("two", ["-n", "2"], []), ("sub", [], ["0.3"]), ("sub2", ["-n", "2"], ["0.3", "false"])):
             d = tmp_path_factory.mktemp("cli_" + tag)
             shutil.copy(os.path.join(ROOT, "tests", "golden", "powerspec.txt"), str(d))
             cli[tag] = (str(d), subprocess.Popen([exe] + extra + [os.path.join(ROOT, "tests", "lua", "small_nc16.lua"), "8", "3"] + more, cwd=str(d),
@@ -222,3 +222,32 @@ def test_command_line_particle_fraction(runs):
             x, y = np.loadtxt(os.path.join(d1, "out", f)), np.loadtxt(os.path.join(d3, "out", f))
             assert x.shape == y.shape and np.array_equal(x[:, 2], y[:, 2]), f
             np.testing.assert_allclose(x[x[:, 2] > 0, 1], y[x[:, 2] > 0, 1], rtol=1e-5, err_msg=f)
+
+
+def test_command_line_particle_fraction_on_two_ranks(runs):
+    """The same on two forked ranks (sort_snapshot = false: the distributed sort needs dense ids): every rank keeps the particles whose
+    deviate of ITS OWN serial stream (store.c:694-720: the seed depends on the rank) is below the fraction -- the `rand` column having
+    travelled with the particles through every migration of the run.  Expected set: the reference's streams for rank 0 and rank 1
+    applied to the particles each rank was filled with."""
+    if not runs["cli"]:
+        pytest.skip("needs /root/reference (the Lua runtime is compiled from there)")
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libfastpm_ref.so not built")
+    rc, d, o = runs["cli"]["sub2"]
+    assert rc == 0, o[-3000:]
+    ids = np.fromfile(os.path.join(d, "out", "fastpm_1.0000", "1", "ID", "000000"), dtype=np.uint64)
+    nc, per_rank = 8, 8 ** 3 // 2
+    s = ref.Session(nc=nc, boxsize=16.0, pm_nc_factor=2, np_alloc_factor=3.0)
+    want = []
+    for r in range(2):
+        _, rnd = s.fill_probe(int(3.0 * nc ** 3 / 2), as_rank=r)
+        want.append(np.nonzero(rnd[:per_rank] <= 0.3)[0] + r * per_rank)      # rank r was filled with the ids [r, r + 1) * nc^3 / 2
+    s.close()
+    want = np.concatenate(want).astype(np.uint64)
+    assert len(ids) == len(want) == len(set(ids.tolist())) and np.array_equal(np.sort(ids), want)
+    x = np.fromfile(os.path.join(d, "out", "fastpm_1.0000", "1", "Position", "000000"), dtype=np.float32).reshape(-1, 3)
+    d1 = runs["cli"]["one"][1]
+    full = np.fromfile(os.path.join(d1, "out", "fastpm_1.0000", "1", "Position", "000000"), dtype=np.float32).reshape(-1, 3)
+    dd = np.abs(x.astype(np.float64) - full[ids.astype(np.int64)])
+    assert np.minimum(dd, 16.0 - dd).max() < 1e-4                                # the rows are the ones of the full one-rank snapshot
